@@ -1,0 +1,271 @@
+// extern "C" boundary (include/vaura_b200.h): argument checking, workspace carving, launch
+// sequencing and CUDA-graph replay of the decode step.  No device memory is allocated here.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/vaura_b200.h"
+#include "kernels.h"
+
+using namespace vaura;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail(VAURA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));   \
+  } while (0)
+
+struct vaura_sampler {
+  vaura_sampler_dims d;
+  vaura_sampler_weights w;
+  cudaGraphExec_t graph_exec = nullptr;  // decode-step graph of the current generate() call
+};
+
+extern "C" int vaura_version(void) { return 1; }
+extern "C" const char* vaura_arch(void) { return "sm_100a"; }
+extern "C" const char* vaura_last_error(void) { return g_err; }
+
+extern "C" int vaura_sampler_create(const vaura_sampler_dims* dims, const vaura_sampler_weights* weights,
+                                    vaura_sampler** out) {
+  if (!dims || !weights || !out) return fail(VAURA_ERR_INVALID, "null argument");
+  const vaura_sampler_dims& d = *dims;
+  if (d.nhead <= 0 || d.d_model % d.nhead != 0 || d.d_model / d.nhead != kHeadDim)
+    return fail(VAURA_ERR_UNSUPPORTED, "head_dim %d unsupported (kernels are built for %d)",
+                d.nhead > 0 ? d.d_model / d.nhead : -1, kHeadDim);
+  if (d.d_model % 64 || d.ffn_dim % 64 || d.cond_dim % 4 || (d.d_model - d.cond_dim) % 4)
+    return fail(VAURA_ERR_UNSUPPORTED, "d_model/ffn_dim must be multiples of 64");
+  if (d.vocab != 1024) return fail(VAURA_ERR_UNSUPPORTED, "vocab %d unsupported (sampling kernel is built for 1024)", d.vocab);
+  if (d.num_codebooks < 1 || d.num_codebooks > 16) return fail(VAURA_ERR_UNSUPPORTED, "num_codebooks must be 1..16");
+  if (d.block_size > kMaxCtx) return fail(VAURA_ERR_UNSUPPORTED, "block_size > %d", kMaxCtx);
+  int dev = 0, major = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(VAURA_ERR_CUDA, "device compute capability %d.x is not sm_100; no fallback path exists", major);
+  vaura_sampler* s = new (std::nothrow) vaura_sampler();
+  if (!s) return fail(VAURA_ERR_INVALID, "out of host memory");
+  s->d = d;
+  s->w = *weights;
+  *out = s;
+  return VAURA_OK;
+}
+
+extern "C" void vaura_sampler_destroy(vaura_sampler* s) {
+  if (!s) return;
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  delete s;
+}
+
+extern "C" int vaura_sampler_cond_project(vaura_sampler* s, const float* feats, int32_t rows, int32_t tv,
+                                          float* rows_out, void* stream) {
+  if (!s || !feats || !rows_out || rows <= 0 || tv <= 0) return fail(VAURA_ERR_INVALID, "bad argument");
+  CU(launch_cond_project(feats, s->w.fc1, s->w.fc2, s->w.empty_video_emb, rows_out, rows, tv, s->d.cond_in,
+                         s->d.cond_dim, (cudaStream_t)stream));
+  return VAURA_OK;
+}
+
+// ---- workspace layout (fp32act) ---------------------------------------------------------------------
+struct Workspace {
+  StepState* state;
+  float *h, *q, *attn, *act, *logits;
+  size_t bytes;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static Workspace carve(const vaura_sampler_dims& d, int rows, int max_pos, void* base) {
+  Workspace w;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(n);
+    return r;
+  };
+  const size_t R = (size_t)rows * max_pos;
+  w.state = (StepState*)take(sizeof(StepState));
+  w.h = (float*)take(R * d.d_model * 4);
+  w.q = (float*)take(R * d.d_model * 4);
+  w.attn = (float*)take(R * d.d_model * 4);
+  w.act = (float*)take(R * d.ffn_dim * 4);
+  w.logits = (float*)take((size_t)rows * d.num_codebooks * d.vocab * 4);
+  w.bytes = off;
+  return w;
+}
+
+extern "C" size_t vaura_sampler_workspace_bytes(const vaura_sampler* s, int32_t rows, int32_t max_positions,
+                                                int32_t precision) {
+  (void)precision;
+  if (!s || rows <= 0 || max_positions <= 0) return 0;
+  return carve(s->d, rows, max_positions, nullptr).bytes;
+}
+
+static KvView kv_view(const vaura_kv_cache* kv, int nhead) {
+  KvView v;
+  v.pages = kv->pages;
+  v.page_table = kv->page_table;
+  v.num_pages = kv->num_pages;
+  v.page_size = kv->page_size;
+  v.max_pages_per_seq = kv->max_pages_per_seq;
+  v.nhead = nhead;
+  return v;
+}
+
+// One transformer pass over `npos` new positions per sequence row (fp32act path).
+//   state != nullptr: positions come from the device-resident loop state (graph replay);
+//   otherwise pos0 is the first new position.
+//   logits_all: write logits of every position to logits_dst [rows*npos][K*V]; else only the last
+//   position of each row to logits_dst [rows][K*V].
+static int transformer_pass(const vaura_sampler* s, const Workspace& ws, const int32_t* seq, int batch, int S,
+                            const float* cond_rows, int rows, int npos, int pos0, const StepState* state,
+                            const KvView& kv, float* logits_dst, bool logits_all, cudaStream_t st) {
+  const vaura_sampler_dims& d = s->d;
+  const vaura_sampler_weights& w = s->w;
+  const int R = rows * npos;
+  EmbedArgs e{};
+  e.seq = seq; e.cond_rows = cond_rows; e.tables = w.tok_tables; e.h = ws.h; e.state = state; e.pos0 = pos0;
+  e.npos = npos; e.batch = batch; e.K = d.num_codebooks; e.S = S; e.vocab = d.vocab; e.d_model = d.d_model;
+  e.cond_dim = d.cond_dim; e.cond_tokens = d.cond_tokens; e.atpvf = d.audio_tokens_per_video_frame;
+  CU(launch_embed(e, R, st));
+  const size_t D = d.d_model, F = d.ffn_dim;
+  for (int l = 0; l < d.num_layers; ++l) {
+    GemvArgs g{};
+    g.state = state; g.pos0 = pos0; g.npos = npos; g.R = R; g.layer = l; g.d_model = d.d_model; g.eps = d.norm_eps;
+    g.kv = kv; g.rope = w.rope;
+    // attention_norm -> wqkv -> RoPE -> KV append
+    g.W = w.wqkv + (size_t)l * 3 * D * D; g.x = ws.h; g.ldx = D; g.norm_w = w.attn_norm + l * D;
+    g.out = ws.q; g.ldo = D; g.N = 3 * D; g.K = D;
+    CU(launch_gemv(EPI_QKV, true, g, st));
+    AttnArgs a{};
+    a.q = ws.q; a.out = ws.attn; a.kv = kv; a.state = state; a.pos0 = pos0; a.npos = npos; a.layer = l;
+    a.d_model = d.d_model; a.scale = 1.0f / sqrtf((float)kHeadDim);
+    CU(launch_attn(a, d.nhead, R, st));
+    // wo + residual
+    g.W = w.wo + (size_t)l * D * D; g.x = ws.attn; g.ldx = D; g.out = ws.h; g.ldo = D; g.N = D; g.K = D;
+    CU(launch_gemv(EPI_RESID, false, g, st));
+    // ffn_norm -> w1|w3 -> silu*mul
+    g.W = w.w13 + (size_t)l * 2 * F * D; g.x = ws.h; g.ldx = D; g.norm_w = w.ffn_norm + l * D;
+    g.out = ws.act; g.ldo = F; g.N = 2 * F; g.K = D;
+    CU(launch_gemv(EPI_SWIGLU, true, g, st));
+    // w2 + residual
+    g.W = w.w2 + (size_t)l * D * F; g.x = ws.act; g.ldx = F; g.out = ws.h; g.ldo = D; g.N = D; g.K = F;
+    CU(launch_gemv(EPI_RESID, false, g, st));
+  }
+  GemvArgs g{};
+  g.state = state; g.pos0 = pos0; g.npos = npos; g.layer = 0; g.d_model = d.d_model; g.eps = d.norm_eps;
+  g.W = w.w_heads; g.norm_w = w.final_norm; g.N = d.num_codebooks * d.vocab; g.K = D; g.ldo = g.N; g.out = logits_dst;
+  if (logits_all) { g.x = ws.h; g.ldx = D; g.R = R; g.perm_S = npos; g.perm_V = d.vocab; }
+  else { g.x = ws.h + (size_t)(npos - 1) * D; g.ldx = (size_t)npos * D; g.R = rows; }
+  CU(launch_gemv(EPI_STORE, true, g, st));
+  return VAURA_OK;
+}
+
+static int check_kv(const vaura_sampler* s, const vaura_kv_cache* kv, int want_dtype) {
+  if (!kv || !kv->pages || !kv->page_table) return fail(VAURA_ERR_INVALID, "kv cache missing");
+  if (kv->page_size != 16 && kv->page_size != 32) return fail(VAURA_ERR_INVALID, "page_size must be 16 or 32");
+  if (kv->max_pages_per_seq * kv->page_size < s->d.block_size)
+    return fail(VAURA_ERR_INVALID, "page table covers %d positions < block_size %d", kv->max_pages_per_seq * kv->page_size,
+                s->d.block_size);
+  if (kv->dtype != want_dtype) return fail(VAURA_ERR_INVALID, "kv dtype %d does not match precision mode", kv->dtype);
+  return VAURA_OK;
+}
+
+extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_params* p, const vaura_kv_cache* kv,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (!s || !p || !workspace) return fail(VAURA_ERR_INVALID, "null argument");
+  const vaura_sampler_dims& d = s->d;
+  const int K = d.num_codebooks, S = p->timesteps + K;
+  if (p->batch <= 0 || p->timesteps <= 0 || !p->sequence || !p->cond_rows) return fail(VAURA_ERR_INVALID, "bad params");
+  if (p->start_offset < 1 || p->start_offset >= S || p->end_offset > S || p->end_offset <= p->start_offset)
+    return fail(VAURA_ERR_INVALID, "bad offsets [%d,%d) for S=%d", p->start_offset, p->end_offset, S);
+  // sequence positions >= block_size overflow the RoPE table in the reference too (llama.py:493-497)
+  if (S - 1 > d.block_size) return fail(VAURA_ERR_INVALID, "sequence of %d columns exceeds block_size %d", S, d.block_size);
+  int precision = p->precision == VAURA_PRECISION_AUTO ? VAURA_PRECISION_FP32ACT : p->precision;
+  if (precision != VAURA_PRECISION_FP32ACT) return fail(VAURA_ERR_UNSUPPORTED, "precision mode %d not built yet", precision);
+  int rc = check_kv(s, kv, VAURA_KV_F32);
+  if (rc) return rc;
+  const int rows = p->batch * (p->use_cfg ? 2 : 1);
+  const int npre = p->start_offset;  // columns [0, start) are consumed by the first pass (prefill when > 1)
+  Workspace ws = carve(d, rows, npre, workspace);
+  if (ws.bytes > workspace_bytes) return fail(VAURA_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const KvView kvv = kv_view(kv, d.nhead);
+
+  SampleArgs sa{};
+  sa.logits = ws.logits; sa.sequence = p->sequence; sa.logits_out = p->logits_out; sa.clip_ids = p->clip_ids;
+  sa.B = p->batch; sa.K = K; sa.V = d.vocab; sa.S = S; sa.T = p->timesteps; sa.use_cfg = p->use_cfg;
+  sa.use_sampling = p->use_sampling; sa.top_k = p->top_k; sa.cfg_scale = p->cfg_scale; sa.temp = p->temp;
+  sa.top_p = p->top_p; sa.seed_lo = (uint32_t)p->seed; sa.seed_hi = (uint32_t)(p->seed >> 32);
+
+  // first pass: positions [0, start) -> sample column start
+  rc = transformer_pass(s, ws, p->sequence, p->batch, S, p->cond_rows, rows, npre, 0, nullptr, kvv, ws.logits, false, st);
+  if (rc) return rc;
+  sa.state = nullptr; sa.offset = p->start_offset;
+  CU(launch_sample(sa, st));
+  const int nsteps = p->end_offset - (p->start_offset + 1);
+  if (nsteps <= 0) return VAURA_OK;
+
+  // decode steps: capture one step (reads its position from the device state) and replay it
+  CU(launch_set_state(ws.state, p->start_offset + 1, st));
+  cudaGraph_t graph = nullptr;
+  CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  rc = transformer_pass(s, ws, p->sequence, p->batch, S, p->cond_rows, rows, 1, 0, ws.state, kvv, ws.logits, false, st);
+  if (rc == VAURA_OK) {
+    sa.state = ws.state;
+    cudaError_t e = launch_sample(sa, st);
+    if (e != cudaSuccess) rc = fail(VAURA_ERR_CUDA, "launch_sample: %s", cudaGetErrorString(e));
+  }
+  cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return fail(VAURA_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+  if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+  ce = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return fail(VAURA_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+  for (int i = 0; i < nsteps; ++i) CU(cudaGraphLaunch(s->graph_exec, st));
+  return VAURA_OK;
+}
+
+extern "C" int vaura_sampler_forward(vaura_sampler* s, const int32_t* sequence, const float* cond_rows, int32_t rows,
+                                     int32_t S, float* logits_out, const vaura_kv_cache* kv, int32_t precision,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (!s || !sequence || !cond_rows || !logits_out || !workspace || rows <= 0 || S <= 0)
+    return fail(VAURA_ERR_INVALID, "bad argument");
+  const vaura_sampler_dims& d = s->d;
+  if (S > d.block_size) return fail(VAURA_ERR_INVALID, "S=%d exceeds block_size %d (llama.py:493-497)", S, d.block_size);
+  if (precision == VAURA_PRECISION_AUTO) precision = VAURA_PRECISION_FP32ACT;
+  if (precision != VAURA_PRECISION_FP32ACT) return fail(VAURA_ERR_UNSUPPORTED, "precision mode %d not built yet", precision);
+  int rc = check_kv(s, kv, VAURA_KV_F32);
+  if (rc) return rc;
+  Workspace ws = carve(d, rows, S, workspace);
+  if (ws.bytes > workspace_bytes) return fail(VAURA_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+  // the heads GEMV stores straight into the reference layout [rows][K][S][V] (llama.py:504 torch.stack(dim=1))
+  return transformer_pass(s, ws, sequence, rows, S, cond_rows, rows, S, 0, nullptr, kv_view(kv, d.nhead), logits_out, true,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int vaura_sample_logits(const float* logits, int32_t rows, int32_t K, int32_t V, int32_t use_cfg,
+                                   float cfg_scale, int32_t use_sampling, float temp, int32_t top_k, float top_p,
+                                   uint64_t seed, const int32_t* clip_ids, int32_t offset, int32_t* tokens_out,
+                                   float* probs_out, void* stream) {
+  if (!logits || !tokens_out || rows <= 0 || K <= 0) return fail(VAURA_ERR_INVALID, "bad argument");
+  if (V != 1024) return fail(VAURA_ERR_UNSUPPORTED, "vocab %d unsupported (sampling kernel is built for 1024)", V);
+  SampleArgs sa{};
+  sa.logits = logits; sa.tokens_out = tokens_out; sa.probs_out = probs_out; sa.clip_ids = clip_ids; sa.offset = offset;
+  sa.B = rows; sa.K = K; sa.V = V; sa.S = 0; sa.T = 0; sa.use_cfg = use_cfg; sa.use_sampling = use_sampling;
+  sa.top_k = top_k; sa.cfg_scale = cfg_scale; sa.temp = temp; sa.top_p = top_p; sa.seed_lo = (uint32_t)seed;
+  sa.seed_hi = (uint32_t)(seed >> 32);
+  CU(launch_sample(sa, (cudaStream_t)stream));
+  return VAURA_OK;
+}

@@ -1,0 +1,343 @@
+// fp32-activation decode path (VAURA_PRECISION_FP32ACT): bf16 weights streamed once per step,
+// fp32 activations / KV / accumulation on the CUDA cores.  This is the HBM-bound small-batch
+// regime: arithmetic is free, bytes are not, and keeping activations in fp32 is
+// what makes greedy token parity with the fp32 reference well-posed (SURVEY §7 "hard parts").
+//
+// Reference code replaced (paths relative to /root/reference):
+//   embed_kernel        llama.py:455-472 (+ :60-73 folded tables, :555-586 repeat/pad)
+//   gemv_kernel<QKV>    llama.py:153-158 (RMSNorm), :228 (wqkv), :633-650 (RoPE), KV append
+//   attn_kernel         llama.py:246-255 (causal SDPA, scale 1/sqrt(96))
+//   gemv_kernel<RESID>  llama.py:259 / :177 (wo, w2) + residual adds :279-283
+//   gemv_kernel<SWIGLU> llama.py:176-177 (silu(w1 x) * w3 x)
+//   gemv_kernel<STORE>  llama.py:503-504 (final norm + 9 heads)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vaura {
+
+// ------------------------------------------------------------------------------------------------
+// embedding sum + channel concat
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a) {
+  const int r = blockIdx.x;  // row = b * npos + j
+  const int b = r / a.npos, j = r % a.npos;
+  const int pos0 = a.state ? a.state->offset - a.npos : a.pos0;
+  const int p = pos0 + j;
+  const int bt = b % a.batch;  // CFG halves share the token sequence (vaura_model.py:795)
+  const int C = a.cond_dim, D = a.d_model, TD = D - C;
+  int vrow = p / a.atpvf;
+  if (vrow > a.cond_tokens) vrow = a.cond_tokens;  // >= Tv -> empty_video_emb row (llama.py:569-572)
+  const float* cr = a.cond_rows + ((size_t)b * (a.cond_tokens + 1) + vrow) * C;
+  float* out = a.h + (size_t)r * D;
+  __shared__ int tok[16];
+  if (threadIdx.x < a.K) {
+    int t = a.seq[((size_t)bt * a.K + threadIdx.x) * a.S + p];
+    tok[threadIdx.x] = t;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) out[i] = cr[i];
+  for (int i = threadIdx.x; i < TD; i += blockDim.x) {
+    float s = 0.f;  // python sum() starts from 0 and adds codebooks in order (llama.py:455-460)
+    for (int k = 0; k < a.K; ++k) s += a.tables[((size_t)k * (a.vocab + 1) + tok[k]) * TD + i];
+    out[C + i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight-streaming GEMV with fused RMSNorm prologue and fused epilogues
+// ------------------------------------------------------------------------------------------------
+// x permutation in shared memory: element k = 8c + j lives at (j < 4 ? 0 : K/2) + 4c + (j & 3), so a
+// lane's two float4 reads of chunk c are each conflict-free across the warp.
+template <int NB, int EPI, bool NORM>
+__global__ void __launch_bounds__(256) gemv_kernel(GemvArgs a) {
+  extern __shared__ float xs[];  // [NB][K]
+  const int K = a.K, K8 = K >> 3, halfK = K >> 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * NB;
+  const int nrows = min(NB, a.R - r0);
+
+  // ---- stage x (optionally RMS-normalised): warp w stages rows w, w+8, ...
+  for (int rr = warp; rr < NB; rr += 8) {
+    float* xr = xs + (size_t)rr * K;
+    if (rr < nrows) {
+      const float* src = a.x + (size_t)(r0 + rr) * a.ldx;
+      float ss = 0.f;
+      for (int c = lane; c < K8; c += 32) {
+        float4 lo = *reinterpret_cast<const float4*>(src + 8 * c);
+        float4 hi = *reinterpret_cast<const float4*>(src + 8 * c + 4);
+        if (NORM) {
+          ss += lo.x * lo.x + lo.y * lo.y + lo.z * lo.z + lo.w * lo.w;
+          ss += hi.x * hi.x + hi.y * hi.y + hi.z * hi.z + hi.w * hi.w;
+        }
+        *reinterpret_cast<float4*>(xr + 4 * c) = lo;
+        *reinterpret_cast<float4*>(xr + halfK + 4 * c) = hi;
+      }
+      if (NORM) {
+        ss = warp_sum(ss);
+        const float rs = rsqrtf(ss / (float)K + a.eps);  // llama.py:153-154
+        __syncwarp();
+        for (int c = lane; c < K8; c += 32) {
+          float4 lo = *reinterpret_cast<float4*>(xr + 4 * c);
+          float4 hi = *reinterpret_cast<float4*>(xr + halfK + 4 * c);
+          float4 wl = *reinterpret_cast<const float4*>(a.norm_w + 8 * c);
+          float4 wh = *reinterpret_cast<const float4*>(a.norm_w + 8 * c + 4);
+          // (x * rs) * w, the reference's order (llama.py:157-158)
+          lo.x = lo.x * rs * wl.x; lo.y = lo.y * rs * wl.y; lo.z = lo.z * rs * wl.z; lo.w = lo.w * rs * wl.w;
+          hi.x = hi.x * rs * wh.x; hi.y = hi.y * rs * wh.y; hi.z = hi.z * rs * wh.z; hi.w = hi.w * rs * wh.w;
+          *reinterpret_cast<float4*>(xr + 4 * c) = lo;
+          *reinterpret_cast<float4*>(xr + halfK + 4 * c) = hi;
+        }
+      }
+    } else {
+      for (int c = lane; c < K8; c += 32) {
+        *reinterpret_cast<float4*>(xr + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(xr + halfK + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  __syncthreads();
+
+  const int pos0 = a.state ? a.state->offset - a.npos : a.pos0;
+  const int npairs = a.N >> 1;
+  for (int q = blockIdx.x * 8 + warp; q < npairs; q += gridDim.x * 8) {
+    const uint4* w0 = reinterpret_cast<const uint4*>(a.W + (size_t)(2 * q) * K);
+    const uint4* w1 = w0 + K8;
+    float acc0[NB], acc1[NB];
+#pragma unroll
+    for (int r = 0; r < NB; ++r) acc0[r] = acc1[r] = 0.f;
+#pragma unroll 2
+    for (int c = lane; c < K8; c += 32) {
+      const uint4 wa = ldg_stream16(w0 + c);
+      const uint4 wb = ldg_stream16(w1 + c);
+#pragma unroll
+      for (int r = 0; r < NB; ++r) {
+        const float4 xl = *reinterpret_cast<const float4*>(xs + (size_t)r * K + 4 * c);
+        const float4 xh = *reinterpret_cast<const float4*>(xs + (size_t)r * K + halfK + 4 * c);
+        float s0 = acc0[r], s1 = acc1[r];
+        s0 = fmaf(bf16_lo(wa.x), xl.x, s0); s0 = fmaf(bf16_hi(wa.x), xl.y, s0);
+        s0 = fmaf(bf16_lo(wa.y), xl.z, s0); s0 = fmaf(bf16_hi(wa.y), xl.w, s0);
+        s0 = fmaf(bf16_lo(wa.z), xh.x, s0); s0 = fmaf(bf16_hi(wa.z), xh.y, s0);
+        s0 = fmaf(bf16_lo(wa.w), xh.z, s0); s0 = fmaf(bf16_hi(wa.w), xh.w, s0);
+        s1 = fmaf(bf16_lo(wb.x), xl.x, s1); s1 = fmaf(bf16_hi(wb.x), xl.y, s1);
+        s1 = fmaf(bf16_lo(wb.y), xl.z, s1); s1 = fmaf(bf16_hi(wb.y), xl.w, s1);
+        s1 = fmaf(bf16_lo(wb.z), xh.x, s1); s1 = fmaf(bf16_hi(wb.z), xh.y, s1);
+        s1 = fmaf(bf16_lo(wb.w), xh.z, s1); s1 = fmaf(bf16_hi(wb.w), xh.w, s1);
+        acc0[r] = s0; acc1[r] = s1;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NB; ++r) { acc0[r] = warp_sum(acc0[r]); acc1[r] = warp_sum(acc1[r]); }
+
+    const int n = 2 * q;
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      if (lane != r || r >= nrows) continue;
+      const int row = r0 + r;
+      const float y0 = acc0[r], y1 = acc1[r];
+      if (EPI == EPI_STORE) {
+        size_t o = (size_t)row * a.ldo + n;
+        if (a.perm_S > 0) {
+          const int b = row / a.perm_S, j = row % a.perm_S, kk = n / a.perm_V;
+          o = (((size_t)b * (a.N / a.perm_V) + kk) * a.perm_S + j) * a.perm_V + (n % a.perm_V);
+        }
+        a.out[o] = y0;
+        a.out[o + 1] = y1;
+      } else if (EPI == EPI_RESID) {
+        float* o = a.out + (size_t)row * a.ldo + n;  // in-place residual stream
+        o[0] += y0;
+        o[1] += y1;
+      } else if (EPI == EPI_SWIGLU) {
+        // rows 2j / 2j+1 are w1[j] / w3[j]: silu(w1 x) * (w3 x)  (llama.py:177)
+        const float s = y0 / (1.f + expf(-y0));
+        a.out[(size_t)row * a.ldo + q] = s * y1;
+      } else {  // EPI_QKV: RoPE on q,k (adjacent pairs, llama.py:633-650) + KV append
+        const int D = a.d_model;
+        const int sec = n / D, within = n % D;
+        const int hd = within / kHeadDim, e = within % kHeadDim;
+        const int b = row / a.npos, j = row % a.npos;
+        const int p = pos0 + j;
+        if (sec == 2) {
+          float* v = reinterpret_cast<float*>(a.kv.pages) + a.kv.row(a.layer, 1, b, p, hd) + e;
+          v[0] = y0;
+          v[1] = y1;
+        } else {
+          const float2 cs = *reinterpret_cast<const float2*>(a.rope + ((size_t)p * (kHeadDim / 2) + (e >> 1)) * 2);
+          const float o0 = y0 * cs.x - y1 * cs.y;
+          const float o1 = y1 * cs.x + y0 * cs.y;
+          if (sec == 0) {
+            a.out[(size_t)row * a.ldo + within] = o0;
+            a.out[(size_t)row * a.ldo + within + 1] = o1;
+          } else {
+            float* kk = reinterpret_cast<float*>(a.kv.pages) + a.kv.row(a.layer, 0, b, p, hd) + e;
+            kk[0] = o0;
+            kk[1] = o1;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NB, int EPI, bool NORM>
+static cudaError_t launch_gemv_t(const GemvArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)NB * a.K * sizeof(float);
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemv_kernel<NB, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int npairs = a.N / 2;
+  int gx = (npairs + 7) / 8;
+  const int cap = 148 * 8;
+  if (gx > cap) gx = cap;
+  dim3 grid(gx, (a.R + NB - 1) / NB);
+  gemv_kernel<NB, EPI, NORM><<<grid, 256, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int EPI, bool NORM>
+static cudaError_t launch_gemv_nb(const GemvArgs& a, cudaStream_t st) {
+  // rows per weight pass: as many as fit the register/smem budget (<= 8); K=4096 caps smem at NB<=8 (128 KB)
+  if (a.R <= 1) return launch_gemv_t<1, EPI, NORM>(a, st);
+  if (a.R <= 2) return launch_gemv_t<2, EPI, NORM>(a, st);
+  if (a.R <= 4) return launch_gemv_t<4, EPI, NORM>(a, st);
+  return launch_gemv_t<8, EPI, NORM>(a, st);
+}
+
+cudaError_t launch_gemv(int epi, bool norm, const GemvArgs& a, cudaStream_t st) {
+  if (a.K % 8 != 0 || a.N % 2 != 0) return cudaErrorInvalidValue;
+  switch (epi) {
+    case EPI_QKV: return launch_gemv_nb<EPI_QKV, true>(a, st);
+    case EPI_SWIGLU: return launch_gemv_nb<EPI_SWIGLU, true>(a, st);
+    case EPI_RESID: return launch_gemv_nb<EPI_RESID, false>(a, st);
+    case EPI_STORE: return norm ? launch_gemv_nb<EPI_STORE, true>(a, st) : launch_gemv_nb<EPI_STORE, false>(a, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_embed(const EmbedArgs& a, int rows, cudaStream_t st) {
+  embed_kernel<<<rows, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// causal attention over the paged fp32 KV cache: one CTA per (head, query row)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_kernel(AttnArgs a) {
+  __shared__ float qs[kHeadDim];
+  __shared__ float sc[kMaxCtx];
+  __shared__ float red[4];
+  const int h = blockIdx.x, row = blockIdx.y;
+  const int b = row / a.npos, j = row % a.npos;
+  const int pos0 = a.state ? a.state->offset - a.npos : a.pos0;
+  const int p = pos0 + j, nctx = p + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* kvp = reinterpret_cast<const float*>(a.kv.pages);
+  if (tid < kHeadDim) qs[tid] = a.q[(size_t)row * a.d_model + h * kHeadDim + tid];
+  __syncthreads();
+
+  // scores: 8 lanes per key position, 12 dims each
+  const int g = tid >> 3, t = tid & 7;
+  float q12[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) q12[i] = qs[t * 12 + i];
+  const int nround = (nctx + 15) & ~15;  // every lane of a warp runs the same trip count (shuffles below)
+  for (int jj = g; jj < nround; jj += 16) {
+    float s = 0.f;
+    if (jj < nctx) {
+      const float4* kr = reinterpret_cast<const float4*>(kvp + a.kv.row(a.layer, 0, b, jj, h) + t * 12);
+      const float4 k0 = kr[0], k1 = kr[1], k2 = kr[2];
+      s = q12[0] * k0.x + q12[1] * k0.y + q12[2] * k0.z + q12[3] * k0.w + q12[4] * k1.x + q12[5] * k1.y +
+          q12[6] * k1.z + q12[7] * k1.w + q12[8] * k2.x + q12[9] * k2.y + q12[10] * k2.z + q12[11] * k2.w;
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (t == 0 && jj < nctx) sc[jj] = s * a.scale;
+  }
+  __syncthreads();
+
+  float m = -INFINITY;
+  for (int jj = tid; jj < nctx; jj += 128) m = fmaxf(m, sc[jj]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int jj = tid; jj < nctx; jj += 128) {
+    const float e = expf(sc[jj] - m);
+    sc[jj] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = red[0] + red[1] + red[2] + red[3];
+
+  if (tid < kHeadDim) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int jj = 0;
+    for (; jj + 3 < nctx; jj += 4) {
+      a0 = fmaf(sc[jj], kvp[a.kv.row(a.layer, 1, b, jj, h) + tid], a0);
+      a1 = fmaf(sc[jj + 1], kvp[a.kv.row(a.layer, 1, b, jj + 1, h) + tid], a1);
+      a2 = fmaf(sc[jj + 2], kvp[a.kv.row(a.layer, 1, b, jj + 2, h) + tid], a2);
+      a3 = fmaf(sc[jj + 3], kvp[a.kv.row(a.layer, 1, b, jj + 3, h) + tid], a3);
+    }
+    for (; jj < nctx; ++jj) a0 = fmaf(sc[jj], kvp[a.kv.row(a.layer, 1, b, jj, h) + tid], a0);
+    a.out[(size_t)row * a.d_model + h * kHeadDim + tid] = ((a0 + a1) + (a2 + a3)) / sum;
+  }
+}
+
+cudaError_t launch_attn(const AttnArgs& a, int nhead, int rows, cudaStream_t st) {
+  attn_kernel<<<dim3(nhead, rows), 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// conditioning MLP (once per clip): rows_out[r][t] = fc2(gelu_tanh(fc1(feats[r][t])))  llama.py:79-92
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cond_project_kernel(const float* __restrict__ feats, const float* __restrict__ fc1,
+                                                           const float* __restrict__ fc2, const float* __restrict__ empty,
+                                                           float* __restrict__ out, int tv, int cin, int C) {
+  extern __shared__ float sm[];  // x[cin] + hid[C]
+  float* x = sm;
+  float* hid = sm + cin;
+  const int r = blockIdx.y, t = blockIdx.x;
+  float* o = out + ((size_t)r * (tv + 1) + t) * C;
+  if (t == tv) {  // appended empty_video_emb row (llama.py:336-338, :569-572)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) o[i] = empty[i];
+    return;
+  }
+  const float* f = feats + ((size_t)r * tv + t) * cin;
+  for (int i = threadIdx.x; i < cin; i += blockDim.x) x[i] = f[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int n = warp; n < C; n += 8) {
+    float s = 0.f;
+    for (int k = lane; k < cin; k += 32) s = fmaf(fc1[(size_t)n * cin + k], x[k], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      // GELU tanh approximation (llama.py:85)
+      const float c0 = 0.7978845608028654f, c1 = 0.044715f;
+      hid[n] = 0.5f * s * (1.f + tanhf(c0 * (s + c1 * s * s * s)));
+    }
+  }
+  __syncthreads();
+  for (int n = warp; n < C; n += 8) {
+    float s = 0.f;
+    for (int k = lane; k < C; k += 32) s = fmaf(fc2[(size_t)n * C + k], hid[k], s);
+    s = warp_sum(s);
+    if (lane == 0) o[n] = s;
+  }
+}
+
+cudaError_t launch_cond_project(const float* feats, const float* fc1, const float* fc2, const float* empty, float* out,
+                                int rows, int tv, int cin, int C, cudaStream_t st) {
+  cond_project_kernel<<<dim3(tv + 1, rows), 256, (cin + C) * sizeof(float), st>>>(feats, fc1, fc2, empty, out, tv, cin, C);
+  return cudaGetLastError();
+}
+
+}  // namespace vaura

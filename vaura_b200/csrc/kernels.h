@@ -1,0 +1,70 @@
+// Internal launch interfaces between the C-ABI glue (cabi.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace vaura {
+
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_QKV = 3 };
+
+struct EmbedArgs {
+  const int32_t* seq;       // [B][K][S]
+  const float* cond_rows;   // [rows][cond_tokens+1][cond_dim]
+  const float* tables;      // [K][V+1][d - cond_dim]
+  float* h;                 // [rows*npos][d]
+  const StepState* state;   // nullptr -> use pos0
+  int pos0, npos;
+  int batch, K, S, vocab, d_model, cond_dim, cond_tokens, atpvf;
+};
+
+struct GemvArgs {
+  const uint16_t* W;   // [N][K] bf16
+  const float* x;      // row r at x + r*ldx
+  const float* norm_w; // RMSNorm weight (NORM variants)
+  float* out;          // row r at out + r*ldo
+  const float* rope;   // EPI_QKV
+  KvView kv;           // EPI_QKV
+  const StepState* state;
+  int pos0, npos;
+  int N, K, R, ldx, ldo;
+  int layer, d_model;
+  int perm_S, perm_V;  // EPI_STORE: when perm_S > 0, row = b*perm_S + j is stored at [b][n / perm_V][j][n % perm_V]
+  float eps;
+};
+
+struct AttnArgs {
+  const float* q;   // [rows*npos][d]
+  float* out;       // [rows*npos][d]
+  KvView kv;
+  const StepState* state;
+  int pos0, npos;
+  int layer, d_model;
+  float scale;
+};
+
+struct SampleArgs {
+  const float* logits;   // [rows_eff][K][V]; cond rows first, then uncond rows
+  int32_t* sequence;     // [B][K][S] or nullptr (then tokens_out is written)
+  int32_t* tokens_out;   // [B][K] optional
+  float* probs_out;      // [B][K][V] optional
+  float* logits_out;     // [S][B][K][V] optional (entry [offset])
+  const int32_t* clip_ids;
+  StepState* state;      // nullptr -> use offset, no advance
+  int offset;
+  int B, K, V, S, T;
+  int use_cfg, use_sampling, top_k;
+  float cfg_scale, temp, top_p;
+  uint32_t seed_lo, seed_hi;
+};
+
+cudaError_t launch_embed(const EmbedArgs& a, int rows, cudaStream_t st);
+cudaError_t launch_gemv(int epi, bool norm, const GemvArgs& a, cudaStream_t st);
+cudaError_t launch_attn(const AttnArgs& a, int nhead, int rows, cudaStream_t st);
+cudaError_t launch_cond_project(const float* feats, const float* fc1, const float* fc2, const float* empty, float* out,
+                                int rows, int tv, int cin, int C, cudaStream_t st);
+cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st);
+cudaError_t launch_set_state(StepState* s, int offset, cudaStream_t st);
+
+}  // namespace vaura

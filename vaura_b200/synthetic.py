@@ -1,0 +1,214 @@
+"""Deterministic synthetic weights / inputs for the V-AURA generation path.
+
+There is no network and no trained checkpoint in this environment, so every
+test, golden fixture and benchmark runs on random-init weights of the named
+architecture.  The tensors are produced here, *not* by the reference's own
+initialisers, so the same bytes can be regenerated on a box that has no copy of
+the reference: each tensor is drawn from a CPU ``torch.Generator`` seeded by
+``(seed, crc32(key))`` and is therefore independent of creation order.
+
+Key names follow the reference's Lightning checkpoint layout:
+``sampler.*`` mirrors ``models/modules/sampler/llama.py`` module names,
+``audio_encoder.model.*`` mirrors descript-audio-codec 1.0.0 (``dac.DAC``).
+
+Deviations from the reference's own init, on purpose:
+  * ``lm_heads`` are zero-initialised there (llama.py:383-385) -> all logits 0;
+    here N(0, 0.02).
+  * ``empty_video_emb`` is ``torch.empty`` there (llama.py:336-338); here N(0, 0.02).
+  * every sampler tensor is rounded to a bf16-representable value so that the
+    bf16 weight storage used on the GPU is lossless w.r.t. the fp32 oracle.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from dataclasses import dataclass, field
+from typing import Dict, Tuple
+
+import torch
+
+
+def find_multiple(n: int, k: int) -> int:
+    # llama.py:24-27
+    return n if n % k == 0 else n + k - (n % k)
+
+
+@dataclass(frozen=True)
+class SamplerDims:
+    """Shape parameters of the AR transformer (llama.py:286-377)."""
+
+    num_layers: int = 24
+    d_model: int = 1536
+    nhead: int = 16
+    d_codebook: int = 1024          # vocab (special id == d_codebook)
+    num_codebooks: int = 9
+    block_size: int = 256           # RoPE table length (llama.py:317, :364-368)
+    cond_in: int = 768              # AVCLIP feature width
+    cond_tokens: int = 32           # AVCLIPEmbedder.token_num
+    cond_feature_channel_scaler: int = 3
+    codebook_dim: int = 8           # DAC factorised code dim
+    norm_eps: float = 1e-5
+    rope_base: int = 10000
+
+    @property
+    def head_dim(self) -> int:
+        return self.d_model // self.nhead
+
+    @property
+    def cond_dim(self) -> int:
+        return self.d_model // self.cond_feature_channel_scaler
+
+    @property
+    def tok_dim(self) -> int:
+        # channel concat: d_model = cond_dim + tok_dim (llama.py:472)
+        return self.d_model - self.cond_dim
+
+    @property
+    def ffn_dim(self) -> int:
+        # llama.py:164-169 (the YAML's dim_feedforward is ignored there)
+        return find_multiple(int(2 * (4 * self.d_model) / 3), 256)
+
+
+@dataclass(frozen=True)
+class CodecDims:
+    """Shape parameters of the DAC decoder (dac 1.0.0 ``DAC.__init__``)."""
+
+    latent_dim: int = 1024
+    decoder_dim: int = 1536
+    decoder_rates: Tuple[int, ...] = (8, 8, 4, 2)
+    n_codebooks: int = 9
+    codebook_size: int = 1024
+    codebook_dim: int = 8
+    sample_rate: int = 44100
+
+    @property
+    def hop_length(self) -> int:
+        return int(math.prod(self.decoder_rates))
+
+
+FULL_SAMPLER = SamplerDims()
+FULL_CODEC = CodecDims()
+# Small shapes for fast parity cases: same head_dim (96), same vocabulary.
+TINY_SAMPLER = SamplerDims(num_layers=2, d_model=384, nhead=4)
+TINY_CODEC = CodecDims(latent_dim=256, decoder_dim=256)
+
+
+def _gen(seed: int, key: str) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed((seed * 1000003 + zlib.crc32(key.encode())) % (2**63 - 1))
+    return g
+
+
+def _randn(seed: int, key: str, shape, std: float = 1.0) -> torch.Tensor:
+    return torch.randn(*shape, generator=_gen(seed, key), dtype=torch.float32) * std
+
+
+def _rand(seed: int, key: str, shape, lo: float, hi: float) -> torch.Tensor:
+    return torch.rand(*shape, generator=_gen(seed, key), dtype=torch.float32) * (hi - lo) + lo
+
+
+def _bf16r(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def make_sampler_state_dict(dims: SamplerDims = FULL_SAMPLER, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """State dict for ``llama.Transformer`` after ``initialize_embeddings`` (no prefix)."""
+    sd: Dict[str, torch.Tensor] = {}
+    d, F, C, V, K = dims.d_model, dims.ffn_dim, dims.cond_dim, dims.d_codebook, dims.num_codebooks
+    std = 0.02
+
+    def put(key, t):
+        sd[key] = _bf16r(t)
+
+    for k in range(K):
+        p = f"tok_embeddings.{k}"
+        put(f"{p}.emb.weight", _randn(seed, f"{p}.emb.weight", (V + 1, dims.codebook_dim)))
+        v = _randn(seed, f"{p}.out_proj.weight_v", (dims.tok_dim, dims.codebook_dim, 1), 0.3)
+        put(f"{p}.out_proj.weight_v", v)
+        g = v.flatten(1).norm(dim=1).view(-1, 1, 1) * _rand(seed, f"{p}.out_proj.weight_g", (dims.tok_dim, 1, 1), 0.5, 1.5)
+        put(f"{p}.out_proj.weight_g", g)
+        put(f"{p}.out_proj.bias", _randn(seed, f"{p}.out_proj.bias", (dims.tok_dim,), std))
+    put("cls_embeddings.projection.fc1.weight", _randn(seed, "fc1", (C, dims.cond_in), std))
+    put("cls_embeddings.projection.fc2.weight", _randn(seed, "fc2", (C, C), std))
+    put("cls_embeddings.uncond_embedding",
+        _randn(seed, "uncond", (dims.cond_tokens, dims.cond_in)) / dims.cond_in ** 0.5)
+    put("empty_video_emb", _randn(seed, "empty_video_emb", (1, 1, C), std))
+    for i in range(dims.num_layers):
+        p = f"layers.{i}"
+        put(f"{p}.attention.wqkv.weight", _randn(seed, f"{p}.wqkv", (3 * d, d), std))
+        put(f"{p}.attention.wo.weight", _randn(seed, f"{p}.wo", (d, d), std))
+        put(f"{p}.feed_forward.w1.weight", _randn(seed, f"{p}.w1", (F, d), std))
+        put(f"{p}.feed_forward.w3.weight", _randn(seed, f"{p}.w3", (F, d), std))
+        put(f"{p}.feed_forward.w2.weight", _randn(seed, f"{p}.w2", (d, F), std))
+        put(f"{p}.attention_norm.weight", 1.0 + _randn(seed, f"{p}.an", (d,), 0.1))
+        put(f"{p}.ffn_norm.weight", 1.0 + _randn(seed, f"{p}.fn", (d,), 0.1))
+    put("norm.weight", 1.0 + _randn(seed, "norm", (d,), 0.1))
+    for k in range(K):
+        put(f"lm_heads.{k}.weight", _randn(seed, f"lm_heads.{k}", (V, d), std))
+    return sd
+
+
+def _wn(sd, seed, key, shape, fan_in, norm_dims):
+    """Old-style torch weight_norm parameters (dim=0): weight = g * v / ||v||."""
+    v = _randn(seed, key + ".weight_v", shape, 1.0 / math.sqrt(fan_in))
+    nrm = v.pow(2).sum(dim=norm_dims, keepdim=True).sqrt()
+    g = nrm * _rand(seed, key + ".weight_g", tuple(nrm.shape), 0.7, 1.3)
+    sd[key + ".weight_v"] = v
+    sd[key + ".weight_g"] = g
+    sd[key + ".bias"] = _randn(seed, key + ".bias", (shape[0],), 0.05)
+
+
+def make_codec_state_dict(dims: CodecDims = FULL_CODEC, seed: int = 100) -> Dict[str, torch.Tensor]:
+    """State dict for the decode half of ``dac.DAC`` (dac 1.0.0 names, no prefix).
+
+    ``quantizer.quantizers.{k}.codebook.weight``, ``...out_proj.{weight_g,weight_v,bias}``,
+    ``decoder.model.0`` (conv k7), ``decoder.model.{1+i}.block.{0: Snake alpha, 1: ConvTranspose1d,
+    2..4: ResidualUnit.block.{0: alpha, 1: conv k7 dilated, 2: alpha, 3: conv k1}}``,
+    ``decoder.model.{n+1}.alpha``, ``decoder.model.{n+2}`` (conv k7 -> 1).  Encoder / in_proj are
+    not on the path and are not generated.
+    """
+    sd: Dict[str, torch.Tensor] = {}
+    for k in range(dims.n_codebooks):
+        p = f"quantizer.quantizers.{k}"
+        sd[f"{p}.codebook.weight"] = _randn(seed, f"{p}.codebook", (dims.codebook_size, dims.codebook_dim))
+        _wn(sd, seed, f"{p}.out_proj", (dims.latent_dim, dims.codebook_dim, 1), dims.codebook_dim * dims.n_codebooks, (1, 2))
+    ch = dims.decoder_dim
+    _wn(sd, seed, "decoder.model.0", (ch, dims.latent_dim, 7), dims.latent_dim * 7, (1, 2))
+    for i, s in enumerate(dims.decoder_rates):
+        cin, cout = ch // 2 ** i, ch // 2 ** (i + 1)
+        p = f"decoder.model.{i + 1}.block"
+        sd[f"{p}.0.alpha"] = _rand(seed, f"{p}.0.alpha", (1, cin, 1), 0.5, 2.0)
+        # ConvTranspose1d weight is (Cin, Cout, k); weight_norm dim=0 -> norm per *input* channel
+        v = _randn(seed, f"{p}.1.weight_v", (cin, cout, 2 * s), 0.6 / math.sqrt(cin * 2))
+        nrm = v.pow(2).sum(dim=(1, 2), keepdim=True).sqrt()
+        sd[f"{p}.1.weight_v"] = v
+        sd[f"{p}.1.weight_g"] = nrm * _rand(seed, f"{p}.1.weight_g", tuple(nrm.shape), 0.7, 1.3)
+        sd[f"{p}.1.bias"] = _randn(seed, f"{p}.1.bias", (cout,), 0.05)
+        for j in range(3):
+            q = f"{p}.{2 + j}.block"
+            sd[f"{q}.0.alpha"] = _rand(seed, f"{q}.0.alpha", (1, cout, 1), 0.5, 2.0)
+            _wn(sd, seed, f"{q}.1", (cout, cout, 7), cout * 7 * 2, (1, 2))
+            sd[f"{q}.2.alpha"] = _rand(seed, f"{q}.2.alpha", (1, cout, 1), 0.5, 2.0)
+            _wn(sd, seed, f"{q}.3", (cout, cout, 1), cout * 8, (1, 2))
+    n = len(dims.decoder_rates)
+    cl = ch // 2 ** n
+    sd[f"decoder.model.{n + 1}.alpha"] = _rand(seed, "final.alpha", (1, cl, 1), 0.5, 2.0)
+    _wn(sd, seed, f"decoder.model.{n + 2}", (1, cl, 7), cl * 7 * 4, (1, 2))
+    return sd
+
+
+def make_checkpoint_state_dict(sdims: SamplerDims = FULL_SAMPLER, cdims: CodecDims = FULL_CODEC,
+                               seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Lightning-style flat state dict: ``sampler.*`` + ``audio_encoder.model.*``."""
+    sd = {"sampler." + k: v for k, v in make_sampler_state_dict(sdims, seed).items()}
+    sd.update({"audio_encoder.model." + k: v for k, v in make_codec_state_dict(cdims, seed + 100).items()})
+    return sd
+
+
+def make_avclip_features(batch: int, seed: int, segments: int = 4, tokens_per_segment: int = 8,
+                         width: int = 768) -> torch.Tensor:
+    """Synthetic Segment-AVCLIP output ``(B, S, t, D)`` as MotionFormer returns it
+    (motionformer.py:252-342); clip ``b`` only depends on ``(seed, b)``."""
+    return torch.stack([
+        _randn(seed, f"avclip.{b}", (segments, tokens_per_segment, width)) for b in range(batch)
+    ])
