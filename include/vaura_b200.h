@@ -48,6 +48,15 @@ int vaura_version(void);                 /* ABI version, currently 1 */
 const char* vaura_arch(void);            /* "sm_100a" */
 const char* vaura_last_error(void);      /* thread-local, never NULL */
 
+/* Number of kernels this library has launched in the calling process (graph replays count their
+ * kernel nodes).  bench.py reports the difference over its timed region as "gpu_launches". */
+unsigned long long vaura_launch_count(void);
+
+/* Weight-streaming GEMV, the dominant kernel of the fp32-activation decode path, as a stand-alone op:
+ * y[r][n] = sum_k W[n][k] * x[r][k]; W bf16 [N][K] row-major, x f32 [R][K], y f32 [R][N]; fp32 accumulate.
+ * (What nn.Linear does at llama.py:228/:259/:176-177/:504 for one position.)  N even, K % 8 == 0. */
+int vaura_gemv_bf16w(const uint16_t* W, const float* x, float* y, int32_t N, int32_t K, int32_t R, void* stream);
+
 /* ---- AR transformer ("sampler"), replaces models/modules/sampler/llama.py:286-586 -------------- */
 typedef struct {
   int32_t num_layers;    /* 24 */

@@ -187,9 +187,10 @@ def build_reference_model(sdims, cdims, seed=0, codec_half=False):
                                  "params": {"n_q": sdims.num_codebooks}},
         flatten_vis_feats=True,
     )
-    # vaura_model.py:92 halves the codec; on CPU we keep the oracle in fp32 unless asked.
+    # vaura_model.py:92 halves the codec (weights rounded to fp16).  For the fp32 oracle run, restore
+    # fp32 and reload the unrounded weights; with codec_half=True the reference's fp16 state is kept.
     if not codec_half:
-        model.audio_encoder.model.float()
+        load_dac_names_into_hf(model.audio_encoder.model.float(), codec_sd)
     missing, unexpected = model.sampler.load_state_dict(make_sampler_state_dict(sdims, seed), strict=True)
     assert not missing and not unexpected
     model.eval()

@@ -1,0 +1,170 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every compute call goes through the C ABI
+(libvaura_b200.so) via the host mirror; the CPU oracle is only the checker."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vaura_oracle as vo
+from oracle.dac_oracle import DacDecodeOracle
+from vaura_b200 import VAURAModel, _cabi
+from vaura_b200.synthetic import (FULL_CODEC, FULL_SAMPLER, TINY_CODEC, TINY_SAMPLER, make_avclip_features,
+                                  make_checkpoint_state_dict, make_codec_state_dict, make_sampler_state_dict)
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def build_model(sdims, cdims, seed=0):
+    cfg = dict(
+        use_visual_conditioning=True,
+        feature_extractor_config={"target": "models.modules.feature_extractors.avclip.motionformer.MotionFormer",
+                                  "params": {}},
+        audio_encoder_config={"target": "models.modules.dac.model.DacModelWrapper",
+                              "params": {"model_sr": 44100, "dims": cdims}},
+        sampler_config={"target": "models.modules.sampler.llama.Transformer",
+                        "params": dict(num_layers=sdims.num_layers, d_model=sdims.d_model, d_codebook=sdims.d_codebook,
+                                       nhead=sdims.nhead, num_codebooks=sdims.num_codebooks,
+                                       block_size_audio=sdims.block_size, block_size_video=64,
+                                       cond_feature_channel_scaler=sdims.cond_feature_channel_scaler)},
+        visual_bridge_config={"target": "torch.nn.Identity"},
+        pattern_provider_config={"target": "models.modules.misc.codebook_patterns.DelayedPatternProvider",
+                                 "params": {"n_q": sdims.num_codebooks}},
+        flatten_vis_feats=True,
+    )
+    m = VAURAModel(**cfg)
+    m.load_state_dict(make_checkpoint_state_dict(sdims, cdims, seed), device="cuda:0")
+    m.eval()
+    m.sampler.audio_tokens_per_video_frame = 7
+    return m
+
+
+@pytest.fixture(scope="module")
+def tiny_model():
+    return build_model(TINY_SAMPLER, TINY_CODEC)
+
+
+@pytest.fixture(scope="module")
+def tiny_oracle():
+    return vo.SamplerOracle(make_sampler_state_dict(TINY_SAMPLER, 0), TINY_SAMPLER)
+
+
+def snr_db(ref, x):
+    ref, x = ref.double().flatten().cpu(), x.double().flatten().cpu()
+    return float(10 * torch.log10(ref.pow(2).sum() / (ref - x).pow(2).sum().clamp_min(1e-30)))
+
+
+def rel_err(a, ref):
+    return float((a.cpu().double() - ref.double()).abs().max() / ref.double().abs().max())
+
+
+# fp32-activation path: logits tolerance of the north star for fp32 (1e-5, normalised by max |logit|,
+# SURVEY §7 "hard parts"); measured error is summation-order noise.
+FP32_LOGIT_TOL = 1e-5
+
+
+def test_forward_teacher_forced_matches_oracle(tiny_model, tiny_oracle):
+    g = torch.Generator().manual_seed(3)
+    seq = torch.randint(0, 1025, (2, 9, 229), generator=g)
+    feats = make_avclip_features(2, 5).reshape(2, 32, 768)
+    logits, a, b = tiny_model.sampler(tgt=seq.cuda(), memory=feats.cuda())
+    assert a is None and b is None and logits.shape == (2, 9, 229, 1024)
+    ref = tiny_oracle.forward_full(seq, feats)
+    assert rel_err(logits, ref) < FP32_LOGIT_TOL
+    gold = np.load(os.path.join(GOLD, "tiny_teacher_forced.npz"))
+    seq_g = torch.from_numpy(gold["seq"].astype(np.int64))
+    lg, _, _ = tiny_model.sampler(tgt=seq_g.cuda(), memory=feats.cuda())
+    assert rel_err(lg[:, :, gold["keep"].tolist()], torch.from_numpy(gold["logits_keep"])) < FP32_LOGIT_TOL
+
+
+@pytest.mark.parametrize("name", ["tiny_greedy", "tiny_cfg_prompt"])
+def test_generate_greedy_matches_reference_golden(tiny_model, tiny_oracle, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    B, T = int(g["B"]), int(g["T"])
+    feats = make_avclip_features(B, int(g["feat_seed"]))
+    prompt = torch.from_numpy(g["prompt"].astype(np.int64))
+    out = tiny_model.generate(frames=feats.cuda(), audio=prompt.cuda() if prompt.shape[-1] else None, max_new_tokens=T,
+                              use_sampling=False, prompt_is_encoded=True, return_sampled_indices=True,
+                              cfg_scale=float(g["cfg_scale"]), check=True, _return_logits=True)
+    codes = out["sampled_indices"].cpu()
+    assert torch.equal(codes, torch.from_numpy(g["codes"].astype(np.int64)))  # bit-exact tokens
+    # per-step post-CFG logits vs the reference's (kept steps) and vs the oracle (all steps)
+    start = prompt.shape[-1] + 1
+    for n, s in enumerate(g["keep_steps"]):
+        if int(s) + 1 >= start:
+            assert rel_err(out["_logits"][int(s) + 1], torch.from_numpy(g["logits_keep"][n])) < FP32_LOGIT_TOL
+    _, ologits = vo.generate_tokens(tiny_oracle, feats.reshape(B, 32, 768), prompt=prompt if prompt.shape[-1] else None,
+                                    max_new_tokens=T, cfg_scale=float(g["cfg_scale"]), collect_logits=True)
+    assert rel_err(out["_logits"][start:], ologits) < FP32_LOGIT_TOL
+    wav = out["generated_audio"]
+    assert wav.dtype == torch.float16 and wav.shape == (B, 1, T * 512)
+    assert snr_db(torch.from_numpy(g["wav_fp16"]).float(), wav.float()) > 40.0  # fp16 storage, fp32 accumulate
+
+
+def test_generate_api_contract(tiny_model):
+    feats = make_avclip_features(3, 9).cuda()
+    out = tiny_model.generate(frames=feats, max_new_tokens=12, use_sampling=True, top_k=128, prompt_is_encoded=True)
+    assert set(out) == {"generated_audio", "s_attn_weights", "mha_attn_weights", "sampled_indices"}
+    assert out["sampled_indices"] is None and out["s_attn_weights"] is None and out["mha_attn_weights"] is None
+    assert out["generated_audio"].shape == (3, 1, 12 * 512)
+    out = tiny_model.generate(frames=feats, max_new_tokens=12, return_sampled_indices=True, prompt_is_encoded=True,
+                              audio=torch.randint(0, 1024, (3, 9, 5)).cuda(), remove_prompts=True)
+    assert out["sampled_indices"].shape == (3, 9, 7) and out["sampled_indices"].dtype == torch.long
+    assert int(out["sampled_indices"].min()) >= 0 and int(out["sampled_indices"].max()) < 1024
+    with pytest.raises(AssertionError):  # vaura_model.py:476-478
+        tiny_model.generate(frames=feats, audio=torch.zeros(3, 9, 12, dtype=torch.long).cuda(), max_new_tokens=12,
+                            prompt_is_encoded=True)
+    with pytest.raises(RuntimeError):  # RoPE table has 256 rows (llama.py:364-368): 250+9 columns do not fit
+        tiny_model.generate(frames=feats, max_new_tokens=250, prompt_is_encoded=True)
+    # sampling is reproducible per (seed, clip id, column, codebook) and independent of batch composition
+    a = tiny_model.generate(frames=feats, max_new_tokens=12, top_k=64, return_sampled_indices=True,
+                            clip_indices=torch.tensor([7, 8, 9]), _decode_audio=False)["sampled_indices"]
+    b = tiny_model.generate(frames=feats[1:2], max_new_tokens=12, top_k=64, return_sampled_indices=True,
+                            clip_indices=torch.tensor([8]), _decode_audio=False)["sampled_indices"]
+    assert torch.equal(a[1:2], b)
+
+
+def test_codec_decode_matches_oracle(tiny_model):
+    g = torch.Generator().manual_seed(0)
+    codes = torch.randint(0, 1024, (2, 9, 33), generator=g)  # ragged w.r.t. the 64-row tiles
+    wav = tiny_model.audio_encoder.decode([(codes.cuda(), None)])
+    ref = DacDecodeOracle(make_codec_state_dict(TINY_CODEC, 100), TINY_CODEC).decode(codes)
+    assert wav.shape == ref.shape == (2, 1, 33 * 512)
+    assert snr_db(ref, wav.float()) > 40.0
+    with pytest.raises(IndexError):
+        tiny_model.audio_encoder.decode(torch.full((1, 9, 4), 1024).cuda())  # special id is not a codec code
+
+
+def test_full_size_greedy_matches_reference_golden():
+    """BASELINE.json config 1 on the B200: 24 layers, B=1, 2.56 s clip, greedy; the tokens are the ones the
+    unmodified reference produced (tests/golden/full_greedy.npz)."""
+    g = np.load(os.path.join(GOLD, "full_greedy.npz"))
+    m = build_model(FULL_SAMPLER, FULL_CODEC)
+    feats = make_avclip_features(1, int(g["feat_seed"]))
+    out = m.generate(frames=feats.cuda(), max_new_tokens=220, use_sampling=False, prompt_is_encoded=True,
+                     return_sampled_indices=True, check=True, _return_logits=True)
+    codes = out["sampled_indices"].cpu()
+    ref = torch.from_numpy(g["codes"].astype(np.int64))
+    # north star: bit-exact for the first 64 steps, >= 99 % agreement over the clip
+    seq_m, _ = vo.build_pattern_sequence(codes, 1024)
+    seq_r, _ = vo.build_pattern_sequence(ref, 1024)
+    assert torch.equal(seq_m[..., :65], seq_r[..., :65])
+    assert (codes == ref).float().mean().item() >= 0.99
+    for n, s in enumerate(g["keep_steps"]):
+        assert rel_err(out["_logits"][int(s) + 1], torch.from_numpy(g["logits_keep"][n])) < 2e-5
+    wav = out["generated_audio"]
+    assert wav.shape == (1, 1, 112640)
+    if torch.equal(codes, ref):
+        assert snr_db(torch.from_numpy(g["wav_fp16"]).float(), wav.float()) > 35.0
+    # 4 clips + CFG at full size exercises the 8-row weight pass
+    f4 = make_avclip_features(4, 77)
+    o4 = m.generate(frames=f4.cuda(), max_new_tokens=16, use_sampling=False, prompt_is_encoded=True, cfg_scale=3.0,
+                    return_sampled_indices=True, _decode_audio=False)["sampled_indices"].cpu()
+    oracle = vo.SamplerOracle(make_sampler_state_dict(FULL_SAMPLER, 0), FULL_SAMPLER)
+    r4, lg = vo.generate_tokens(oracle, f4.reshape(4, 32, 768), max_new_tokens=16, cfg_scale=3.0, collect_logits=True)
+    gaps = torch.topk(lg, 2, dim=-1).values
+    if float((gaps[..., 0] - gaps[..., 1]).min()) > 1e-3:
+        assert torch.equal(o4, r4)
+    else:
+        assert (o4 == r4).float().mean().item() > 0.9

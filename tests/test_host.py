@@ -1,0 +1,179 @@
+"""CPU tests of the host-side mirror: config loading, delay pattern, weight packing, C-ABI exports."""
+import math
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_stubs, vaura_oracle as vo
+from vaura_b200 import _cabi, config as vcfg
+from vaura_b200.patterns import DelayedPatternProvider
+from vaura_b200.synthetic import (FULL_SAMPLER, TINY_CODEC, TINY_SAMPLER, make_codec_state_dict,
+                                  make_sampler_state_dict)
+from vaura_b200.weights import convt_polyphase, fold_weight_norm, pack_codec, pack_sampler
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAVE_REF = ref_stubs.reference_available()
+
+
+# ---- config ------------------------------------------------------------------------------------------
+def test_config_resolvers_and_targets():
+    cfg = vcfg.load_config(os.path.join(ROOT, "tests/fixtures/configs/model_tiny.yaml"), base_dir=ROOT)
+    assert cfg["model"]["batch_size"] == 2
+    assert cfg["dataloader"]["partition_audio_to_clips"] is False  # negation of flatten_vis_feats
+    sp = cfg["model"]["sampler_config"]
+    assert sp["target"] == "models.modules.sampler.llama.Transformer"
+    assert sp["params"]["layer_norm_eps"] == pytest.approx(1e-5)  # "1e-5" must parse as float like OmegaConf
+    from vaura_b200.sampler import Transformer
+    assert vcfg.get_obj_from_str(sp["target"]) is Transformer
+    with pytest.raises(KeyError):
+        vcfg.instantiate_from_config({"params": {}})
+    ident = vcfg.instantiate_from_config({"target": "torch.nn.Identity"})
+    assert isinstance(ident, torch.nn.Identity)
+
+
+def test_config_dotlist_overrides():
+    cfg = vcfg.load_config(os.path.join(ROOT, "tests/fixtures/configs/model_tiny.yaml"),
+                           overrides=["dataloader.batch_size=7", "model.flatten_vis_feats=false"], base_dir=ROOT)
+    assert cfg["model"]["batch_size"] == 7
+    assert cfg["dataloader"]["partition_audio_to_clips"] is True
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not present")
+def test_reference_yamls_load_unchanged():
+    ref = ref_stubs.REFERENCE_ROOT
+    cfg = vcfg.load_config(os.path.join(ref, "configs/vaura_defaults.yaml"), base_dir=ref)
+    assert cfg["model"]["sampler_config"]["params"]["d_model"] == 1536
+    assert cfg["model"]["pattern_provider_config"]["params"]["n_q"] == 9
+    gen = vcfg.load_config(os.path.join(ref, "configs/generate_vgg.yaml"), base_dir=ref,
+                           overrides=["experiment_path=/tmp/exp"])
+    assert gen["checkpoint_path"] == "/tmp/exp/checkpoints/"
+    assert (gen["top_k"], gen["cfg_scale"], gen["temperature"]) == (128, 6.0, 1.0)
+    from vaura_b200 import VAURAModel
+    m = VAURAModel(**{k: v for k, v in cfg["model"].items() if k != "name"})
+    assert m.sampler.dims == FULL_SAMPLER and m.sampler.dims.ffn_dim == 4096 and m.num_codebooks == 9
+
+
+def test_model_construction_mirrors_reference_attributes():
+    from vaura_b200 import VAURAModel
+    cfg = vcfg.load_config(os.path.join(ROOT, "tests/fixtures/configs/model_tiny.yaml"), base_dir=ROOT)
+    m = VAURAModel(**cfg["model"])
+    assert m.using_avclip and m.flatten_vis_feats
+    assert m.special_token_id == 1024 and m.num_codebooks == 9
+    assert m.sampler.config.block_size == 256  # scripts/generate.py:224 reads this
+    assert m.sampler.codebook_pattern == "DelayedPatternProvider"
+    assert m.sampler.audio_tokens_per_video_frame is None
+    m.sampler.audio_tokens_per_video_frame = 7  # scripts/generate.py:216
+    assert m.training  # like any nn.Module until .eval() is called
+    with pytest.raises(AssertionError):
+        m.generate(frames=torch.zeros(1, 4, 8, 768))  # vaura_model.py:437
+    m.eval()
+    with pytest.raises(NotImplementedError):
+        m.generate(frames=torch.zeros(1, 4, 8, 768), return_attention_weights=True)
+
+
+# ---- delay pattern -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K,T,Tp", [(9, 220, 0), (9, 24, 9), (2, 5, 1), (9, 1, 0)])
+def test_pattern_matches_oracle_closed_form(K, T, Tp):
+    g = torch.Generator().manual_seed(K * 1000 + T)
+    codes = torch.randint(0, 1024, (3, K, T), generator=g)
+    codes[..., Tp:] = -1
+    pat = DelayedPatternProvider(K).get_pattern(T)
+    seq, idx, mask = pat.build_pattern_sequence(codes, 1024)
+    oseq, omask = vo.build_pattern_sequence(codes, 1024)
+    assert torch.equal(seq, oseq) and torch.equal(mask, omask)
+    assert seq.shape[-1] == T + K and (seq[..., 0] == 1024).all()
+    assert pat.get_first_step_with_timesteps(Tp) == vo.first_step_with_timestep(Tp)
+    full = torch.randint(0, 1024, (3, K, T), generator=g)
+    s2, _, _ = pat.build_pattern_sequence(full, 1024)
+    back, _, bmask = pat.revert_pattern_sequence(s2, special_token=-1)
+    assert torch.equal(back, full) and bmask.all()
+    assert torch.equal(back, vo.revert_pattern_sequence(s2, T))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not present")
+@pytest.mark.parametrize("K,T", [(9, 220), (9, 7), (4, 30)])
+def test_pattern_matches_reference_class(K, T):
+    ref_stubs.install_stubs(TINY_CODEC, make_codec_state_dict(TINY_CODEC, 100))
+    from models.modules.misc.codebook_patterns import DelayedPatternProvider as RefProvider
+    g = torch.Generator().manual_seed(T)
+    codes = torch.randint(0, 1024, (2, K, T), generator=g)
+    codes[..., T // 2:] = -1
+    rp, mp = RefProvider(K).get_pattern(T), DelayedPatternProvider(K).get_pattern(T)
+    rs, ri, rm = rp.build_pattern_sequence(codes, 1024)
+    ms, mi, mm = mp.build_pattern_sequence(codes, 1024)
+    assert torch.equal(rs, ms) and torch.equal(ri, mi) and torch.equal(rm, mm)
+    rv, rvi, rvm = rp.revert_pattern_sequence(rs, special_token=-1)
+    mv, mvi, mvm = mp.revert_pattern_sequence(ms, special_token=-1)
+    assert torch.equal(rv, mv) and torch.equal(rvi, mvi) and torch.equal(rvm, mvm)
+    for t in (0, 1, T - 1):
+        assert rp.get_first_step_with_timesteps(t) == mp.get_first_step_with_timesteps(t)
+
+
+# ---- weight packing ------------------------------------------------------------------------------------
+def test_pack_sampler_layouts():
+    d = TINY_SAMPLER
+    sd = make_sampler_state_dict(d, 0)
+    w = pack_sampler(sd, d, "cpu")
+    o = vo.SamplerOracle(sd, d)
+    assert torch.allclose(w["tok_tables"], torch.stack(o.tables), atol=1e-6)
+    assert w["w13"].shape == (d.num_layers, 2 * d.ffn_dim, d.d_model)
+    assert torch.equal(w["w13"][1, 0::2].float(), sd["layers.1.feed_forward.w1.weight"])  # bf16-exact weights
+    assert torch.equal(w["w13"][1, 1::2].float(), sd["layers.1.feed_forward.w3.weight"])
+    assert torch.equal(w["w_heads"][1024:2048].float(), sd["lm_heads.1.weight"])
+    assert torch.allclose(w["rope"], o.rope)
+    assert w["wqkv"].dtype == torch.bfloat16 and w["attn_norm"].dtype == torch.float32
+
+
+@pytest.mark.parametrize("s", [2, 4, 8, 6])
+def test_convtranspose_polyphase_equals_torch(s):
+    g = torch.Generator().manual_seed(s)
+    cin, cout, L = 6, 5, 11
+    w = torch.randn(cin, cout, 2 * s, generator=g)
+    x = torch.randn(2, cin, L, generator=g)
+    ref = F.conv_transpose1d(x, w, stride=s, padding=math.ceil(s / 2))
+    wp, offs = convt_polyphase(w, s)
+    out = torch.zeros(2, cout, L * s)
+    xp = F.pad(x, (1, 1))
+    for r in range(s):
+        for tap in range(2):
+            o = offs[2 * r + tap]
+            xs = xp[:, :, 1 + o: 1 + o + L]
+            out[:, :, r::s] += torch.einsum("oc,bcl->bol", wp[r, tap], xs)
+    assert ref.shape == out.shape and torch.allclose(ref, out, atol=1e-5)
+
+
+def test_pack_codec_slots():
+    c = TINY_CODEC
+    sd = make_codec_state_dict(c, 100)
+    blob, offs = pack_codec(sd, c, "cpu")
+    n = len(c.decoder_rates)
+    assert len(offs) == 3 + 21 * n + 3 + 1 and all(o % 256 == 0 for o in offs)
+    w_in = fold_weight_norm(sd["decoder.model.0.weight_g"], sd["decoder.model.0.weight_v"]).permute(2, 0, 1)
+    got = blob[offs[1]: offs[1] + w_in.numel() * 2].view(torch.float16).view(7, c.decoder_dim, c.latent_dim)
+    assert torch.allclose(got.float(), w_in, atol=2e-3)
+    taps = blob[offs[-1]:].view(torch.int32)
+    assert taps[:7].tolist() == [-3, -2, -1, 0, 1, 2, 3] and taps[7:14].tolist() == [-9, -6, -3, 0, 3, 6, 9]
+    assert taps[21].item() == 0 and taps[29:29 + 16].tolist() == [0, -1] * 4 + [0, 1] * 4  # stride 8, pad 4
+
+
+# ---- C ABI ---------------------------------------------------------------------------------------------
+def test_cabi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "vaura_b200.h")).read()
+    declared = set(re.findall(r"\b(vaura_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
+    lib = _cabi.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.vaura_version() == 1 and lib.vaura_arch() == b"sm_100a"
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vaura_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f

@@ -1,0 +1,119 @@
+"""Host mirror of ``DacModelWrapper`` (models/modules/dac/model.py:11-61) for the decode direction.
+
+The class keeps the reference's name (checked at models/vaura_model.py:87) and call shapes:
+``decode(codes | [(codes, None)]) -> (B, 1, hop*T) float16`` (fp16 because the reference halves the
+codec, vaura_model.py:92).  Weights come from the Lightning checkpoint's ``audio_encoder.model.*``
+entries (dac 1.0.0 names); the reference's ``dac.utils.download`` needs the network and is not mirrored.
+``encode`` (wav -> codes) is a "next" row and raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import typing as tp
+
+import torch
+
+from . import _cabi
+from .synthetic import CodecDims
+from .weights import pack_codec
+
+MODEL_SR = [16000, 24000, 44000, 44100]
+
+
+class DacModelWrapper(torch.nn.Module):
+    def __init__(self, model_sr: int = 24000, ckpt_path: tp.Optional[str] = None, dims: tp.Optional[CodecDims] = None):
+        super().__init__()
+        assert model_sr in MODEL_SR, "Invalid model samplerate"
+        self.model_sr = model_sr
+        self.dims = dims or CodecDims(sample_rate=model_sr)
+        self._blob = None
+        self._offsets = None
+        self._handle = None
+        self._ws = None
+        if ckpt_path is not None:
+            sd = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+            self.load_state_dict(sd.get("state_dict", sd))
+
+    @property
+    def model(self):
+        """Callers reach for ``.model.half()`` (vaura_model.py:92); the wrapper and the codec are one object here."""
+        return self
+
+    def half(self):  # the compute path already stores fp16 (vaura_model.py:92)
+        return self
+
+    def load_state_dict(self, state_dict, strict: bool = True, device=None):
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._blob, self._offsets = pack_codec(state_dict, self.dims, device)
+        self._destroy()
+        return torch.nn.modules.module._IncompatibleKeys([], [])
+
+    def _destroy(self):
+        if self._handle is not None:
+            _cabi.load().vaura_codec_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def handle(self):
+        if self._blob is None:
+            raise RuntimeError("codec weights are not loaded")
+        if self._handle is None:
+            lib = _cabi.load()
+            d = self.dims
+            rates = (C.c_int32 * 8)(*d.decoder_rates)
+            dc = _cabi.CodecDimsC(d.latent_dim, d.decoder_dim, len(d.decoder_rates), rates, d.n_codebooks, d.codebook_size)
+            offs = (C.c_int64 * len(self._offsets))(*self._offsets)
+            wc = _cabi.CodecWeightsC(self._blob.data_ptr(), offs, len(self._offsets))
+            h = C.c_void_p()
+            _cabi.check(lib.vaura_codec_create(C.byref(dc), C.byref(wc), C.byref(h)), "vaura_codec_create")
+            self._handle = h
+        return self._handle
+
+    def forward(self, wav: torch.Tensor):
+        return self.encode(wav)
+
+    def encode(self, wav: torch.Tensor):
+        raise NotImplementedError("DAC encode (wav -> codes) is outside the built hot path (SURVEY §8f row 3)")
+
+    @torch.no_grad()
+    def decode(self, codes: tp.Union[torch.Tensor, tp.List[tp.Tuple[torch.Tensor, tp.Any]]], max_batch: int = 16):
+        if type(codes) == list:  # EnCodec-style frames (models/modules/dac/model.py:43-44)
+            codes = codes[0][0]
+        lib = _cabi.load()
+        dev = self._blob.device
+        codes = codes.to(device=dev, dtype=torch.int32).contiguous()
+        B, Kc, T = codes.shape
+        if Kc != self.dims.n_codebooks:
+            raise ValueError(f"expected {self.dims.n_codebooks} codebooks, got {Kc}")
+        if codes.numel() and (int(codes.min()) < 0 or int(codes.max()) >= self.dims.codebook_size):
+            raise IndexError("codec code out of range")  # F.embedding would raise in the reference
+        hop = self.dims.hop_length
+        wav = torch.empty(B, 1, T * hop, dtype=torch.float16, device=dev)
+        h = self.handle()
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            for b0 in range(0, B, max_batch):  # bound the activation workspace
+                nb = min(max_batch, B - b0)
+                nbytes = lib.vaura_codec_workspace_bytes(h, nb, T)
+                if self._ws is None or self._ws.numel() < nbytes:
+                    self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                _cabi.check(lib.vaura_codec_decode(h, codes[b0:b0 + nb].data_ptr(), nb, T, wav[b0:b0 + nb].data_ptr(),
+                                                   self._ws.data_ptr(), self._ws.numel(), st), "vaura_codec_decode")
+        return wav
+
+    @property
+    def sample_rate(self):
+        return self.dims.sample_rate
+
+    @property
+    def channels(self):
+        return 1
+
+    @property
+    def frame_rate(self):
+        return None

@@ -21,11 +21,18 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static unsigned long long g_launches = 0;  // kernels launched (see vaura_launch_count)
+static unsigned long long g_capture_nodes = 0;
+static bool g_capturing = false;
+#define LAUNCHED(n) do { if (g_capturing) g_capture_nodes += (n); else g_launches += (n); } while (0)
+
 #define CU(expr)                                                                                   \
   do {                                                                                             \
     cudaError_t _e = (expr);                                                                       \
     if (_e != cudaSuccess) return fail(VAURA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));   \
   } while (0)
+
+#define CUL(expr) do { CU(expr); LAUNCHED(1); } while (0)
 
 struct vaura_sampler {
   vaura_sampler_dims d;
@@ -36,6 +43,16 @@ struct vaura_sampler {
 extern "C" int vaura_version(void) { return 1; }
 extern "C" const char* vaura_arch(void) { return "sm_100a"; }
 extern "C" const char* vaura_last_error(void) { return g_err; }
+extern "C" unsigned long long vaura_launch_count(void) { return g_launches; }
+
+extern "C" int vaura_gemv_bf16w(const uint16_t* W, const float* x, float* y, int32_t N, int32_t K, int32_t R, void* stream) {
+  if (!W || !x || !y || N <= 0 || K <= 0 || R <= 0 || (N & 1) || (K & 7)) return fail(VAURA_ERR_INVALID, "bad argument");
+  CU(init_decode_kernels());
+  GemvArgs g{};
+  g.W = W; g.x = x; g.out = y; g.N = N; g.K = K; g.R = R; g.ldx = K; g.ldo = N; g.npos = 1;
+  CUL(launch_gemv(EPI_STORE, false, g, (cudaStream_t)stream));
+  return VAURA_OK;
+}
 
 extern "C" int vaura_sampler_create(const vaura_sampler_dims* dims, const vaura_sampler_weights* weights,
                                     vaura_sampler** out) {
@@ -53,6 +70,7 @@ extern "C" int vaura_sampler_create(const vaura_sampler_dims* dims, const vaura_
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   if (major != 10) return fail(VAURA_ERR_CUDA, "device compute capability %d.x is not sm_100; no fallback path exists", major);
+  CU(init_decode_kernels());
   vaura_sampler* s = new (std::nothrow) vaura_sampler();
   if (!s) return fail(VAURA_ERR_INVALID, "out of host memory");
   s->d = d;
@@ -70,7 +88,7 @@ extern "C" void vaura_sampler_destroy(vaura_sampler* s) {
 extern "C" int vaura_sampler_cond_project(vaura_sampler* s, const float* feats, int32_t rows, int32_t tv,
                                           float* rows_out, void* stream) {
   if (!s || !feats || !rows_out || rows <= 0 || tv <= 0) return fail(VAURA_ERR_INVALID, "bad argument");
-  CU(launch_cond_project(feats, s->w.fc1, s->w.fc2, s->w.empty_video_emb, rows_out, rows, tv, s->d.cond_in,
+  CUL(launch_cond_project(feats, s->w.fc1, s->w.fc2, s->w.empty_video_emb, rows_out, rows, tv, s->d.cond_in,
                          s->d.cond_dim, (cudaStream_t)stream));
   return VAURA_OK;
 }
@@ -137,7 +155,7 @@ static int transformer_pass(const vaura_sampler* s, const Workspace& ws, const i
   e.seq = seq; e.cond_rows = cond_rows; e.tables = w.tok_tables; e.h = ws.h; e.state = state; e.pos0 = pos0;
   e.npos = npos; e.batch = batch; e.K = d.num_codebooks; e.S = S; e.vocab = d.vocab; e.d_model = d.d_model;
   e.cond_dim = d.cond_dim; e.cond_tokens = d.cond_tokens; e.atpvf = d.audio_tokens_per_video_frame;
-  CU(launch_embed(e, R, st));
+  CUL(launch_embed(e, R, st));
   const size_t D = d.d_model, F = d.ffn_dim;
   for (int l = 0; l < d.num_layers; ++l) {
     GemvArgs g{};
@@ -146,28 +164,28 @@ static int transformer_pass(const vaura_sampler* s, const Workspace& ws, const i
     // attention_norm -> wqkv -> RoPE -> KV append
     g.W = w.wqkv + (size_t)l * 3 * D * D; g.x = ws.h; g.ldx = D; g.norm_w = w.attn_norm + l * D;
     g.out = ws.q; g.ldo = D; g.N = 3 * D; g.K = D;
-    CU(launch_gemv(EPI_QKV, true, g, st));
+    CUL(launch_gemv(EPI_QKV, true, g, st));
     AttnArgs a{};
     a.q = ws.q; a.out = ws.attn; a.kv = kv; a.state = state; a.pos0 = pos0; a.npos = npos; a.layer = l;
     a.d_model = d.d_model; a.scale = 1.0f / sqrtf((float)kHeadDim);
-    CU(launch_attn(a, d.nhead, R, st));
+    CUL(launch_attn(a, d.nhead, R, st));
     // wo + residual
     g.W = w.wo + (size_t)l * D * D; g.x = ws.attn; g.ldx = D; g.out = ws.h; g.ldo = D; g.N = D; g.K = D;
-    CU(launch_gemv(EPI_RESID, false, g, st));
+    CUL(launch_gemv(EPI_RESID, false, g, st));
     // ffn_norm -> w1|w3 -> silu*mul
     g.W = w.w13 + (size_t)l * 2 * F * D; g.x = ws.h; g.ldx = D; g.norm_w = w.ffn_norm + l * D;
     g.out = ws.act; g.ldo = F; g.N = 2 * F; g.K = D;
-    CU(launch_gemv(EPI_SWIGLU, true, g, st));
+    CUL(launch_gemv(EPI_SWIGLU, true, g, st));
     // w2 + residual
     g.W = w.w2 + (size_t)l * D * F; g.x = ws.act; g.ldx = F; g.out = ws.h; g.ldo = D; g.N = D; g.K = F;
-    CU(launch_gemv(EPI_RESID, false, g, st));
+    CUL(launch_gemv(EPI_RESID, false, g, st));
   }
   GemvArgs g{};
   g.state = state; g.pos0 = pos0; g.npos = npos; g.layer = 0; g.d_model = d.d_model; g.eps = d.norm_eps;
   g.W = w.w_heads; g.norm_w = w.final_norm; g.N = d.num_codebooks * d.vocab; g.K = D; g.ldo = g.N; g.out = logits_dst;
   if (logits_all) { g.x = ws.h; g.ldx = D; g.R = R; g.perm_S = npos; g.perm_V = d.vocab; }
   else { g.x = ws.h + (size_t)(npos - 1) * D; g.ldx = (size_t)npos * D; g.R = rows; }
-  CU(launch_gemv(EPI_STORE, true, g, st));
+  CUL(launch_gemv(EPI_STORE, true, g, st));
   return VAURA_OK;
 }
 
@@ -212,20 +230,24 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   rc = transformer_pass(s, ws, p->sequence, p->batch, S, p->cond_rows, rows, npre, 0, nullptr, kvv, ws.logits, false, st);
   if (rc) return rc;
   sa.state = nullptr; sa.offset = p->start_offset;
-  CU(launch_sample(sa, st));
+  CUL(launch_sample(sa, st));
   const int nsteps = p->end_offset - (p->start_offset + 1);
   if (nsteps <= 0) return VAURA_OK;
 
   // decode steps: capture one step (reads its position from the device state) and replay it
-  CU(launch_set_state(ws.state, p->start_offset + 1, st));
+  CUL(launch_set_state(ws.state, p->start_offset + 1, st));
   cudaGraph_t graph = nullptr;
   CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  g_capturing = true;
+  g_capture_nodes = 0;
   rc = transformer_pass(s, ws, p->sequence, p->batch, S, p->cond_rows, rows, 1, 0, ws.state, kvv, ws.logits, false, st);
   if (rc == VAURA_OK) {
     sa.state = ws.state;
     cudaError_t e = launch_sample(sa, st);
     if (e != cudaSuccess) rc = fail(VAURA_ERR_CUDA, "launch_sample: %s", cudaGetErrorString(e));
+    LAUNCHED(1);
   }
+  g_capturing = false;
   cudaError_t ce = cudaStreamEndCapture(st, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
   if (ce != cudaSuccess) return fail(VAURA_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
@@ -233,7 +255,10 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   ce = cudaGraphInstantiate(&s->graph_exec, graph, 0);
   cudaGraphDestroy(graph);
   if (ce != cudaSuccess) return fail(VAURA_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
-  for (int i = 0; i < nsteps; ++i) CU(cudaGraphLaunch(s->graph_exec, st));
+  for (int i = 0; i < nsteps; ++i) {
+    CU(cudaGraphLaunch(s->graph_exec, st));
+    g_launches += g_capture_nodes;
+  }
   return VAURA_OK;
 }
 
@@ -266,6 +291,132 @@ extern "C" int vaura_sample_logits(const float* logits, int32_t rows, int32_t K,
   sa.B = rows; sa.K = K; sa.V = V; sa.S = 0; sa.T = 0; sa.use_cfg = use_cfg; sa.use_sampling = use_sampling;
   sa.top_k = top_k; sa.cfg_scale = cfg_scale; sa.temp = temp; sa.top_p = top_p; sa.seed_lo = (uint32_t)seed;
   sa.seed_hi = (uint32_t)(seed >> 32);
-  CU(launch_sample(sa, (cudaStream_t)stream));
+  CUL(launch_sample(sa, (cudaStream_t)stream));
+  return VAURA_OK;
+}
+
+// ---- codec ------------------------------------------------------------------------------------------
+// slot order of the weight blob (must match vaura_b200/weights.py: CODEC_SLOTS)
+//   0 code_tables f16 [Kc][Vc][latent]     1 conv_in W f16 [7][C0][latent]     2 conv_in bias f32
+//   per block i (base 3 + 21 i): +0 snake alpha f32 [Cin]  +1 convT W f16 [s][2][Cout][Cin]  +2 convT bias
+//       per residual unit j (base +3 + 6 j): +0 alpha1  +1 conv7 W f16 [7][C][C]  +2 bias  +3 alpha2
+//                                            +4 conv1 W f16 [1][C][C]  +5 bias
+//   tail (base 3 + 21 n): +0 final alpha f32 [Cl]  +1 conv_out W f32 [7][Cl]  +2 conv_out bias f32 [1]
+//   last slot: tap-offset tables int32 (built by weights.py): [k7 d1][k7 d3][k7 d9][k1][k7 pad3] then per block
+//   [s][2] conv-transpose offsets
+struct vaura_codec {
+  vaura_codec_dims d;
+  const char* blob;
+  std::vector<int64_t> off;
+};
+
+extern "C" int vaura_codec_create(const vaura_codec_dims* dims, const vaura_codec_weights* w, vaura_codec** out) {
+  if (!dims || !w || !out || !w->blob || !w->offsets) return fail(VAURA_ERR_INVALID, "null argument");
+  const int want = 3 + 21 * dims->n_blocks + 3 + 1;
+  if (w->n_offsets != want) return fail(VAURA_ERR_INVALID, "codec blob has %d slots, expected %d", w->n_offsets, want);
+  if (dims->n_blocks < 1 || dims->n_blocks > 8) return fail(VAURA_ERR_INVALID, "n_blocks must be 1..8");
+  if ((dims->decoder_dim >> dims->n_blocks) % 16 != 0 || dims->latent_dim % 16 != 0)
+    return fail(VAURA_ERR_UNSUPPORTED, "channel counts must be multiples of 16");
+  if (dims->n_codebooks > 16) return fail(VAURA_ERR_UNSUPPORTED, "n_codebooks > 16");
+  vaura_codec* c = new (std::nothrow) vaura_codec();
+  if (!c) return fail(VAURA_ERR_INVALID, "out of host memory");
+  c->d = *dims;
+  c->blob = (const char*)w->blob;
+  c->off.assign(w->offsets, w->offsets + w->n_offsets);
+  *out = c;
+  return VAURA_OK;
+}
+
+extern "C" void vaura_codec_destroy(vaura_codec* c) { delete c; }
+
+struct CodecWs {
+  __half *z, *x, *a0, *a1, *h;
+  size_t bytes;
+};
+
+static CodecWs codec_carve(const vaura_codec_dims& d, int B, int T, void* base) {
+  CodecWs w;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(n);
+    return (__half*)r;
+  };
+  size_t maxel = (size_t)T * d.decoder_dim, t = T;
+  for (int i = 0; i < d.n_blocks; ++i) {
+    t *= d.rates[i];
+    const size_t el = t * (size_t)(d.decoder_dim >> (i + 1));
+    if (el > maxel) maxel = el;
+  }
+  w.z = take((size_t)B * T * d.latent_dim * 2);
+  w.x = take(B * maxel * 2);
+  w.a0 = take(B * maxel * 2);
+  w.a1 = take(B * maxel * 2);
+  w.h = take(B * maxel * 2);
+  w.bytes = off;
+  return w;
+}
+
+extern "C" size_t vaura_codec_workspace_bytes(const vaura_codec* c, int32_t batch, int32_t frames) {
+  if (!c || batch <= 0 || frames <= 0) return 0;
+  return codec_carve(c->d, batch, frames, nullptr).bytes;
+}
+
+extern "C" int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t B, int32_t T, uint16_t* wav_out,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  if (!c || !codes || !wav_out || !workspace || B <= 0 || T <= 0) return fail(VAURA_ERR_INVALID, "bad argument");
+  const vaura_codec_dims& d = c->d;
+  CodecWs ws = codec_carve(d, B, T, workspace);
+  if (ws.bytes > workspace_bytes) return fail(VAURA_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  auto H = [&](int slot) { return (const __half*)(c->blob + c->off[slot]); };
+  auto F = [&](int slot) { return (const float*)(c->blob + c->off[slot]); };
+  const int tail = 3 + 21 * d.n_blocks;
+  const int* taps = (const int*)(c->blob + c->off[tail + 3]);
+  const int* taps_k7[3] = {taps, taps + 7, taps + 14};
+  const int* taps_k1 = taps + 21;
+  const int* taps_in = taps + 22;
+  const int* taps_ct = taps + 29;
+
+  CUL(launch_from_codes(codes, H(0), ws.z, B, d.n_codebooks, T, d.codebook_size, d.latent_dim, st));
+  // conv_in k7 pad 3: z -> (activated with block 0's snake) a0
+  ConvArgs a{};
+  a.in = ws.z; a.W = H(1); a.tap_off = taps_in; a.bias = F(2); a.alpha = F(3); a.residual = nullptr; a.out_raw = nullptr;
+  a.out_act = ws.a0; a.Tin = T; a.Tq = T; a.Tout = T; a.Cin = d.latent_dim; a.Cout = d.decoder_dim; a.ntaps = 7;
+  a.nphase = 1; a.ostride = 1;
+  CUL(launch_conv_gemm(a, B, st));
+  __half* act_in = ws.a0;
+  __half* act_out = ws.a1;
+  int t = T;
+  for (int i = 0; i < d.n_blocks; ++i) {
+    const int base = 3 + 21 * i, s = d.rates[i];
+    const int cin = d.decoder_dim >> i, cout = d.decoder_dim >> (i + 1);
+    // conv-transpose (polyphase): act_in -> x (raw) and act_out = snake(x, alpha of res unit 0)
+    ConvArgs ct{};
+    ct.in = act_in; ct.W = H(base + 1); ct.tap_off = taps_ct; ct.bias = F(base + 2); ct.alpha = F(base + 3);
+    ct.out_raw = ws.x; ct.out_act = act_out; ct.Tin = t; ct.Tq = t; ct.Tout = t * s; ct.Cin = cin; ct.Cout = cout;
+    ct.ntaps = 2; ct.nphase = s; ct.ostride = s;
+    CUL(launch_conv_gemm(ct, B, st));
+    taps_ct += 2 * s;
+    t *= s;
+    for (int j = 0; j < 3; ++j) {
+      const int rb = base + 3 + 6 * j;
+      ConvArgs c7{};
+      c7.in = act_out; c7.W = H(rb + 1); c7.tap_off = taps_k7[j]; c7.bias = F(rb + 2); c7.alpha = F(rb + 3);
+      c7.out_act = ws.h; c7.Tin = t; c7.Tq = t; c7.Tout = t; c7.Cin = cout; c7.Cout = cout; c7.ntaps = 7; c7.nphase = 1;
+      c7.ostride = 1;
+      CUL(launch_conv_gemm(c7, B, st));
+      // alpha of whatever consumes the block output next: next res unit, next block's snake, or the final snake
+      const float* next_alpha = j < 2 ? F(rb + 6) : (i + 1 < d.n_blocks ? F(3 + 21 * (i + 1)) : F(tail));
+      ConvArgs c1{};
+      c1.in = ws.h; c1.W = H(rb + 4); c1.tap_off = taps_k1; c1.bias = F(rb + 5); c1.alpha = next_alpha; c1.residual = ws.x;
+      c1.out_raw = j < 2 ? ws.x : nullptr; c1.out_act = act_out; c1.Tin = t; c1.Tq = t; c1.Tout = t; c1.Cin = cout;
+      c1.Cout = cout; c1.ntaps = 1; c1.nphase = 1; c1.ostride = 1;
+      CUL(launch_conv_gemm(c1, B, st));
+    }
+    __half* tmp = act_in; act_in = act_out; act_out = tmp;
+  }
+  CUL(launch_conv_out_tanh(act_in, F(tail + 1), F(tail + 2), (__half*)wav_out, B, t, d.decoder_dim >> d.n_blocks, st));
   return VAURA_OK;
 }

@@ -178,16 +178,12 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvArgs a) {
   }
 }
 
+constexpr int kGemvMaxSmem = 200 * 1024;
+
 template <int NB, int EPI, bool NORM>
 static cudaError_t launch_gemv_t(const GemvArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)NB * a.K * sizeof(float);
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemv_kernel<NB, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         200 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (smem > (size_t)kGemvMaxSmem) return cudaErrorInvalidValue;
   const int npairs = a.N / 2;
   int gx = (npairs + 7) / 8;
   const int cap = 148 * 8;
@@ -195,6 +191,29 @@ static cudaError_t launch_gemv_t(const GemvArgs& a, cudaStream_t st) {
   dim3 grid(gx, (a.R + NB - 1) / NB);
   gemv_kernel<NB, EPI, NORM><<<grid, 256, smem, st>>>(a);
   return cudaGetLastError();
+}
+
+template <int EPI, bool NORM>
+static cudaError_t init_gemv_epi() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(gemv_kernel<1, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem))) return e;
+  if ((e = cudaFuncSetAttribute(gemv_kernel<2, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem))) return e;
+  if ((e = cudaFuncSetAttribute(gemv_kernel<4, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem))) return e;
+  return cudaFuncSetAttribute(gemv_kernel<8, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem);
+}
+
+// opt every instantiation into large dynamic shared memory once, outside any stream capture
+cudaError_t init_decode_kernels() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e;
+  if ((e = init_gemv_epi<EPI_QKV, true>())) return e;
+  if ((e = init_gemv_epi<EPI_SWIGLU, true>())) return e;
+  if ((e = init_gemv_epi<EPI_RESID, false>())) return e;
+  if ((e = init_gemv_epi<EPI_STORE, true>())) return e;
+  if ((e = init_gemv_epi<EPI_STORE, false>())) return e;
+  done = true;
+  return cudaSuccess;
 }
 
 template <int EPI, bool NORM>

@@ -59,6 +59,25 @@ struct SampleArgs {
   uint32_t seed_lo, seed_hi;
 };
 
+struct ConvArgs {
+  const __half* in;        // [B][Tin][Cin]
+  const __half* W;         // [nphase][ntaps][Cout][Cin]
+  const int* tap_off;      // device [nphase][ntaps]: input index = q + off
+  const float* bias;       // [Cout]
+  const float* alpha;      // [Cout] Snake alpha for out_act
+  const __half* residual;  // [B][Tout][Cout] or nullptr
+  __half* out_raw;         // [B][Tout][Cout] or nullptr
+  __half* out_act;         // [B][Tout][Cout] or nullptr (Snake applied)
+  int Tin, Tq, Tout, Cin, Cout, ntaps, nphase, ostride;  // t_out = q*ostride + phase
+};
+
+cudaError_t launch_from_codes(const int32_t* codes, const __half* tables, __half* z, int B, int Kc, int T, int Vc,
+                              int latent, cudaStream_t st);
+cudaError_t launch_conv_gemm(const ConvArgs& a, int B, cudaStream_t st);
+cudaError_t launch_conv_out_tanh(const __half* in, const float* W, const float* bias, __half* wav, int B, int T, int C,
+                                 cudaStream_t st);
+cudaError_t init_decode_kernels();
+
 cudaError_t launch_embed(const EmbedArgs& a, int rows, cudaStream_t st);
 cudaError_t launch_gemv(int epi, bool norm, const GemvArgs& a, cudaStream_t st);
 cudaError_t launch_attn(const AttnArgs& a, int nhead, int rows, cudaStream_t st);

@@ -1,0 +1,194 @@
+"""Checkpoint reading and weight packing (load-time plumbing; torch is used for memory only).
+
+* ``load_lightning_checkpoint`` reads a reference ``.ckpt`` (``torch.load(...)["state_dict"]``) and
+  splits it by the prefixes the reference uses: ``sampler.``, ``audio_encoder.model.``,
+  ``visual_feature_extractor.``.
+* ``pack_sampler`` folds the weight-normed token embeddings into tables (llama.py:60-73), stacks the
+  per-layer matrices in the layouts ``include/vaura_b200.h`` documents (bf16), interleaves w1/w3 rows so
+  the SwiGLU epilogue sees both halves in one warp, stacks the 9 heads, and precomputes the RoPE table
+  (llama.py:593-603).
+* ``pack_codec`` folds weight norm for every DAC conv, re-lays them out as per-tap [Cout][Cin] GEMM
+  operands (polyphase for the transposed convs) in one fp16/fp32 blob.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Tuple
+
+import torch
+
+from .synthetic import CodecDims, SamplerDims
+
+
+def fold_weight_norm(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """torch.nn.utils.weight_norm, dim=0: w = g * v / ||v||, norm over every dim but 0."""
+    dims = tuple(range(1, v.dim()))
+    return g * v / v.pow(2).sum(dim=dims, keepdim=True).sqrt()
+
+
+def split_state_dict(sd: Dict[str, torch.Tensor]):
+    out = {"sampler": {}, "codec": {}, "feature_extractor": {}, "other": {}}
+    for k, v in sd.items():
+        if k.startswith("sampler."):
+            out["sampler"][k[len("sampler."):]] = v
+        elif k.startswith("audio_encoder.model."):
+            out["codec"][k[len("audio_encoder.model."):]] = v
+        elif k.startswith("visual_feature_extractor."):
+            out["feature_extractor"][k[len("visual_feature_extractor."):]] = v
+        else:
+            out["other"][k] = v
+    return out
+
+
+def load_lightning_checkpoint(path: str, map_location="cpu"):
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    sd = ckpt["state_dict"] if "state_dict" in ckpt else ckpt
+    return split_state_dict(sd), ckpt.get("hyper_parameters")
+
+
+def rope_table(n_pos: int, head_dim: int, base: float = 10000.0) -> torch.Tensor:
+    """llama.py:593-603 -> (n_pos, head_dim/2, 2) with (cos, sin)."""
+    freqs = 1.0 / (base ** (torch.arange(0, head_dim, 2)[: head_dim // 2].float() / head_dim))
+    ang = torch.outer(torch.arange(n_pos).float(), freqs)
+    return torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous()
+
+
+def pack_sampler(sd: Dict[str, torch.Tensor], dims: SamplerDims, device) -> Dict[str, torch.Tensor]:
+    """-> dict of contiguous device tensors named like the fields of ``vaura_sampler_weights``."""
+    L, d, F, K, V = dims.num_layers, dims.d_model, dims.ffn_dim, dims.num_codebooks, dims.d_codebook
+
+    def f32(key):
+        return sd[key].detach().to(torch.float32)
+
+    def bf16_stack(keys):
+        return torch.stack([sd[k].detach().to(device=device, dtype=torch.bfloat16) for k in keys]).contiguous()
+
+    out = {}
+    out["wqkv"] = bf16_stack([f"layers.{i}.attention.wqkv.weight" for i in range(L)])
+    out["wo"] = bf16_stack([f"layers.{i}.attention.wo.weight" for i in range(L)])
+    w13 = []
+    for i in range(L):
+        w1 = sd[f"layers.{i}.feed_forward.w1.weight"].detach().to(device=device, dtype=torch.bfloat16)
+        w3 = sd[f"layers.{i}.feed_forward.w3.weight"].detach().to(device=device, dtype=torch.bfloat16)
+        w13.append(torch.stack([w1, w3], dim=1).reshape(2 * F, d))
+    out["w13"] = torch.stack(w13).contiguous()
+    out["w2"] = bf16_stack([f"layers.{i}.feed_forward.w2.weight" for i in range(L)])
+    out["w_heads"] = torch.cat([sd[f"lm_heads.{k}.weight"].detach().to(device=device, dtype=torch.bfloat16)
+                                for k in range(K)]).contiguous()
+    out["attn_norm"] = torch.stack([f32(f"layers.{i}.attention_norm.weight") for i in range(L)]).to(device).contiguous()
+    out["ffn_norm"] = torch.stack([f32(f"layers.{i}.ffn_norm.weight") for i in range(L)]).to(device).contiguous()
+    out["final_norm"] = f32("norm.weight").to(device).contiguous()
+    tables = []
+    for k in range(K):
+        p = f"tok_embeddings.{k}"
+        if f"{p}.out_proj.weight_g" in sd:
+            W = fold_weight_norm(f32(f"{p}.out_proj.weight_g"), f32(f"{p}.out_proj.weight_v"))[:, :, 0]
+        else:  # new-style parametrisation or already folded
+            W = f32(f"{p}.out_proj.weight")[:, :, 0]
+        tables.append(f32(f"{p}.emb.weight") @ W.t() + f32(f"{p}.out_proj.bias"))
+    out["tok_tables"] = torch.stack(tables).to(device).contiguous()
+    assert out["tok_tables"].shape == (K, V + 1, dims.tok_dim), out["tok_tables"].shape
+    out["rope"] = rope_table(dims.block_size, dims.head_dim, dims.rope_base).to(device)
+    out["fc1"] = f32("cls_embeddings.projection.fc1.weight").to(device).contiguous()
+    out["fc2"] = f32("cls_embeddings.projection.fc2.weight").to(device).contiguous()
+    out["empty_video_emb"] = f32("empty_video_emb").reshape(-1).to(device).contiguous()
+    out["uncond_embedding"] = f32("cls_embeddings.uncond_embedding").to(device).contiguous()
+    return out
+
+
+def sampler_step_bytes(dims: SamplerDims) -> int:
+    """Algorithmic weight bytes streamed by one decode step: layers + final norm + heads."""
+    d, F = dims.d_model, dims.ffn_dim
+    per_layer = (3 * d * d + d * d + 3 * d * F) * 2 + 2 * d * 4
+    return dims.num_layers * per_layer + d * 4 + dims.num_codebooks * dims.d_codebook * d * 2
+
+
+# ---- codec -------------------------------------------------------------------------------------------
+def _conv_w(sd, key) -> torch.Tensor:
+    if key + ".weight_g" in sd:
+        return fold_weight_norm(sd[key + ".weight_g"].float(), sd[key + ".weight_v"].float())
+    return sd[key + ".weight"].float()
+
+
+def convt_polyphase(w: torch.Tensor, stride: int) -> Tuple[torch.Tensor, List[int]]:
+    """ConvTranspose1d weight (Cin, Cout, 2s), padding ceil(s/2) -> ([s][2][Cout][Cin], offsets [s][2]).
+
+    out[q*s + r] = sum_ci W[:, :, r+pad] x[q] + W[:, :, j1] x[q + o1]; (j1, o1) = (r+pad-s, +1) when
+    r+pad >= s else (r+pad+s, -1).  Every output phase has exactly two taps."""
+    if stride % 2 or w.shape[-1] != 2 * stride:
+        raise ValueError("polyphase split needs an even stride and kernel = 2*stride (output length = L*stride)")
+    pad = math.ceil(stride / 2)
+    phases, offs = [], []
+    for r in range(stride):
+        j0 = r + pad
+        j1, o1 = (j0 - stride, 1) if j0 >= stride else (j0 + stride, -1)
+        phases.append(torch.stack([w[:, :, j0].t(), w[:, :, j1].t()]))
+        offs += [0, o1]
+    return torch.stack(phases).contiguous(), offs
+
+
+def pack_codec(sd: Dict[str, torch.Tensor], dims: CodecDims, device):
+    """-> (blob uint8 device tensor, offsets list[int] in bytes).  Slot order: see csrc/cabi.cu."""
+    parts: List[torch.Tensor] = []
+
+    def h(t):
+        parts.append(t.to(torch.float16).contiguous())
+
+    def f(t):
+        parts.append(t.to(torch.float32).contiguous())
+
+    n = len(dims.decoder_rates)
+    tables = []
+    for k in range(dims.n_codebooks):
+        p = f"quantizer.quantizers.{k}"
+        W = _conv_w(sd, f"{p}.out_proj")[:, :, 0]  # (latent, 8)
+        tables.append(sd[f"{p}.codebook.weight"].float() @ W.t() + sd[f"{p}.out_proj.bias"].float())
+    h(torch.stack(tables))
+    h(_conv_w(sd, "decoder.model.0").permute(2, 0, 1))  # (Cout,Cin,7) -> [7][Cout][Cin]
+    f(sd["decoder.model.0.bias"])
+    tap_tables: List[int] = []
+    for dil in (1, 3, 9):
+        tap_tables += [j * dil - (6 * dil) // 2 for j in range(7)]
+    tap_tables += [0]
+    tap_tables += [j - 3 for j in range(7)]
+    for i, s in enumerate(dims.decoder_rates):
+        p = f"decoder.model.{i + 1}.block"
+        f(sd[f"{p}.0.alpha"].reshape(-1))
+        wt, offs = convt_polyphase(_conv_w(sd, f"{p}.1"), s)
+        h(wt)
+        tap_tables += offs
+        f(sd[f"{p}.1.bias"])
+        for j in range(3):
+            q = f"{p}.{2 + j}.block"
+            f(sd[f"{q}.0.alpha"].reshape(-1))
+            h(_conv_w(sd, f"{q}.1").permute(2, 0, 1))
+            f(sd[f"{q}.1.bias"])
+            f(sd[f"{q}.2.alpha"].reshape(-1))
+            h(_conv_w(sd, f"{q}.3").permute(2, 0, 1))
+            f(sd[f"{q}.3.bias"])
+    f(sd[f"decoder.model.{n + 1}.alpha"].reshape(-1))
+    f(_conv_w(sd, f"decoder.model.{n + 2}")[0].t())  # (1,Cl,7) -> [7][Cl] fp32
+    f(sd[f"decoder.model.{n + 2}.bias"])
+    parts.append(torch.tensor(tap_tables, dtype=torch.int32))
+
+    offsets, cur = [], 0
+    for t in parts:
+        offsets.append(cur)
+        cur += (t.numel() * t.element_size() + 255) // 256 * 256
+    blob = torch.zeros(cur, dtype=torch.uint8)
+    for o, t in zip(offsets, parts):
+        blob[o:o + t.numel() * t.element_size()] = t.view(-1).view(torch.uint8)
+    return blob.to(device), offsets
+
+
+def codec_flops(dims: CodecDims, frames: int) -> float:
+    """2*Cin*Cout*k*Lout per conv (ConvT counted over its input length), SURVEY Appendix A."""
+    fl = 2.0 * dims.latent_dim * dims.decoder_dim * 7 * frames
+    t = frames
+    for i, s in enumerate(dims.decoder_rates):
+        cin, cout = dims.decoder_dim >> i, dims.decoder_dim >> (i + 1)
+        fl += 2.0 * cin * cout * 2 * s * t
+        t *= s
+        fl += 3 * (2.0 * cout * cout * 7 * t + 2.0 * cout * cout * t)
+    fl += 2.0 * (dims.decoder_dim >> len(dims.decoder_rates)) * 7 * t
+    return fl
