@@ -8,9 +8,10 @@
  * code it replaces.  Conventions:
  *   - plain C types only; every tensor is a raw DEVICE pointer owned by the caller (weights, KV
  *     pages, workspaces, sequences, outputs).  The library allocates no device memory.
- *   - every launch goes to the `stream` argument (a cudaStream_t passed as void*); no internal
- *     streams, no host synchronisation (vaura_*_generate instantiates CUDA graphs lazily inside the
- *     handle; graph launch is asynchronous too).
+ *   - every launch goes to the `stream` argument (a cudaStream_t passed as void*); nothing executes
+ *     on any other stream and there is no host synchronisation.  vaura_sampler_generate captures the
+ *     decode step into a CUDA graph (on a private capture-origin stream, so the legacy default stream
+ *     is usable as `stream`) and replays it asynchronously on `stream`.
  *   - return value: 0 = ok, otherwise one of VAURA_ERR_*; the message of the last error on the
  *     calling thread is returned by vaura_last_error().  Nothing throws across the ABI.
  *   - one host thread per handle; handles are independent (one process per GPU creates its own).

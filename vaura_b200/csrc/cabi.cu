@@ -38,6 +38,8 @@ struct vaura_sampler {
   vaura_sampler_dims d;
   vaura_sampler_weights w;
   cudaGraphExec_t graph_exec = nullptr;  // decode-step graph of the current generate() call
+  cudaStream_t capture_stream = nullptr; // capture origin only (the legacy default stream cannot be captured);
+                                         // nothing ever executes on it, graphs are launched on the caller's stream
 };
 
 extern "C" int vaura_version(void) { return 1; }
@@ -75,6 +77,8 @@ extern "C" int vaura_sampler_create(const vaura_sampler_dims* dims, const vaura_
   if (!s) return fail(VAURA_ERR_INVALID, "out of host memory");
   s->d = d;
   s->w = *weights;
+  cudaError_t ce = cudaStreamCreateWithFlags(&s->capture_stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) { delete s; return fail(VAURA_ERR_CUDA, "cudaStreamCreateWithFlags: %s", cudaGetErrorString(ce)); }
   *out = s;
   return VAURA_OK;
 }
@@ -82,6 +86,7 @@ extern "C" int vaura_sampler_create(const vaura_sampler_dims* dims, const vaura_
 extern "C" void vaura_sampler_destroy(vaura_sampler* s) {
   if (!s) return;
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
   delete s;
 }
 
@@ -237,18 +242,19 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   // decode steps: capture one step (reads its position from the device state) and replay it
   CUL(launch_set_state(ws.state, p->start_offset + 1, st));
   cudaGraph_t graph = nullptr;
-  CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  cudaStream_t cs = s->capture_stream;
+  CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
   g_capturing = true;
   g_capture_nodes = 0;
-  rc = transformer_pass(s, ws, p->sequence, p->batch, S, p->cond_rows, rows, 1, 0, ws.state, kvv, ws.logits, false, st);
+  rc = transformer_pass(s, ws, p->sequence, p->batch, S, p->cond_rows, rows, 1, 0, ws.state, kvv, ws.logits, false, cs);
   if (rc == VAURA_OK) {
     sa.state = ws.state;
-    cudaError_t e = launch_sample(sa, st);
+    cudaError_t e = launch_sample(sa, cs);
     if (e != cudaSuccess) rc = fail(VAURA_ERR_CUDA, "launch_sample: %s", cudaGetErrorString(e));
     LAUNCHED(1);
   }
   g_capturing = false;
-  cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  cudaError_t ce = cudaStreamEndCapture(cs, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
   if (ce != cudaSuccess) return fail(VAURA_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
   if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
