@@ -2,6 +2,7 @@
 // sequencing and CUDA-graph replay of the decode step.  No device memory is allocated here.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -314,7 +315,18 @@ struct vaura_codec {
   vaura_codec_dims d;
   const char* blob;
   std::vector<int64_t> off;
+  std::vector<int> taps;  // host copy of the tap-offset tables (same order as the device slot)
+  bool use_tc = true;     // tcgen05 implicit GEMM where the shape is supported, SIMT kernel otherwise
 };
+
+static int conv_dispatch(const vaura_codec* c, const ConvArgs& a, int tap_index, int B, cudaStream_t st) {
+  if (c->use_tc && conv_tc_supported(a.Cin, a.Cout, a.ntaps, a.nphase)) {
+    CUL(launch_conv_tc(a, c->taps.data() + tap_index, B, st));
+  } else {
+    CUL(launch_conv_gemm(a, B, st));
+  }
+  return VAURA_OK;
+}
 
 extern "C" int vaura_codec_create(const vaura_codec_dims* dims, const vaura_codec_weights* w, vaura_codec** out) {
   if (!dims || !w || !out || !w->blob || !w->offsets) return fail(VAURA_ERR_INVALID, "null argument");
@@ -329,6 +341,20 @@ extern "C" int vaura_codec_create(const vaura_codec_dims* dims, const vaura_code
   c->d = *dims;
   c->blob = (const char*)w->blob;
   c->off.assign(w->offsets, w->offsets + w->n_offsets);
+  for (int dil : {1, 3, 9})
+    for (int j = 0; j < 7; ++j) c->taps.push_back(j * dil - 3 * dil);
+  c->taps.push_back(0);
+  for (int j = 0; j < 7; ++j) c->taps.push_back(j - 3);
+  for (int i = 0; i < dims->n_blocks; ++i) {
+    const int s = dims->rates[i], pad = (s + 1) / 2;
+    if (s % 2) { delete c; return fail(VAURA_ERR_UNSUPPORTED, "odd upsampling rate %d", s); }
+    for (int r = 0; r < s; ++r) {
+      c->taps.push_back(0);
+      c->taps.push_back(r + pad >= s ? 1 : -1);
+    }
+  }
+  const char* env = getenv("VAURA_CODEC_SIMT");
+  c->use_tc = !(env && env[0] == '1');
   *out = c;
   return VAURA_OK;
 }
@@ -391,7 +417,9 @@ extern "C" int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t 
   a.in = ws.z; a.W = H(1); a.tap_off = taps_in; a.bias = F(2); a.alpha = F(3); a.residual = nullptr; a.out_raw = nullptr;
   a.out_act = ws.a0; a.Tin = T; a.Tq = T; a.Tout = T; a.Cin = d.latent_dim; a.Cout = d.decoder_dim; a.ntaps = 7;
   a.nphase = 1; a.ostride = 1;
-  CUL(launch_conv_gemm(a, B, st));
+  int rc = conv_dispatch(c, a, 22, B, st);
+  if (rc) return rc;
+  int ct_index = 29;
   __half* act_in = ws.a0;
   __half* act_out = ws.a1;
   int t = T;
@@ -403,8 +431,9 @@ extern "C" int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t 
     ct.in = act_in; ct.W = H(base + 1); ct.tap_off = taps_ct; ct.bias = F(base + 2); ct.alpha = F(base + 3);
     ct.out_raw = ws.x; ct.out_act = act_out; ct.Tin = t; ct.Tq = t; ct.Tout = t * s; ct.Cin = cin; ct.Cout = cout;
     ct.ntaps = 2; ct.nphase = s; ct.ostride = s;
-    CUL(launch_conv_gemm(ct, B, st));
+    if ((rc = conv_dispatch(c, ct, ct_index, B, st))) return rc;
     taps_ct += 2 * s;
+    ct_index += 2 * s;
     t *= s;
     for (int j = 0; j < 3; ++j) {
       const int rb = base + 3 + 6 * j;
@@ -412,14 +441,14 @@ extern "C" int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t 
       c7.in = act_out; c7.W = H(rb + 1); c7.tap_off = taps_k7[j]; c7.bias = F(rb + 2); c7.alpha = F(rb + 3);
       c7.out_act = ws.h; c7.Tin = t; c7.Tq = t; c7.Tout = t; c7.Cin = cout; c7.Cout = cout; c7.ntaps = 7; c7.nphase = 1;
       c7.ostride = 1;
-      CUL(launch_conv_gemm(c7, B, st));
+      if ((rc = conv_dispatch(c, c7, 7 * j, B, st))) return rc;
       // alpha of whatever consumes the block output next: next res unit, next block's snake, or the final snake
       const float* next_alpha = j < 2 ? F(rb + 6) : (i + 1 < d.n_blocks ? F(3 + 21 * (i + 1)) : F(tail));
       ConvArgs c1{};
       c1.in = ws.h; c1.W = H(rb + 4); c1.tap_off = taps_k1; c1.bias = F(rb + 5); c1.alpha = next_alpha; c1.residual = ws.x;
       c1.out_raw = j < 2 ? ws.x : nullptr; c1.out_act = act_out; c1.Tin = t; c1.Tq = t; c1.Tout = t; c1.Cin = cout;
       c1.Cout = cout; c1.ntaps = 1; c1.nphase = 1; c1.ostride = 1;
-      CUL(launch_conv_gemm(c1, B, st));
+      if ((rc = conv_dispatch(c, c1, 21, B, st))) return rc;
     }
     __half* tmp = act_in; act_in = act_out; act_out = tmp;
   }

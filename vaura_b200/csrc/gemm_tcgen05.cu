@@ -1,0 +1,347 @@
+// tcgen05 / TMEM / TMA GEMM for the dense contractions of the path (sm_100a only):
+//   D[m][n] = sum_tap sum_k A[m + off(tap)][k] * B[tap][n][k]        (both operands K-major, fp32 accumulate)
+// A = activations (rows = sequence rows, prefill positions, or codec time steps), B = weights.
+//   - batch >= 16 decode and prefill: QKV / wo / w1|w3 / w2 / heads projections of llama.py:228,:259,:176-177,:504
+//     with RoPE+KV-append, residual, SiLU*mul epilogues (bf16 operands)
+//   - codec: every WNConv1d / WNConvTranspose1d of the DAC decoder as an implicit GEMM (fp16 operands): the
+//     7 taps (or the 2 taps of a polyphase of the transposed conv) are extra K iterations whose A tile is the
+//     same TMA box shifted in time; out-of-range rows are zero-filled by TMA, which is the conv padding.
+//
+// One CTA computes one 128 x BLOCK_N tile:  warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread
+// tcgen05.mma issue, warps 2-5 = epilogue (tcgen05.ld 32 lanes each -> registers -> fused epilogue -> global).
+// smem ring of STAGES {A 128xBLOCK_K, B BLOCK_NxBLOCK_K} tiles in the 128B (or 64B) swizzled K-major layout
+// that TMA writes and the UMMA shared-memory descriptor reads; full/empty mbarriers; accumulator in TMEM.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vaura {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> CUDA error at the next API call) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  // load + wait in ONE asm statement so no consumer of r[] can be scheduled before the wait
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory matrix descriptor for a K-major tile whose rows are one swizzle atom wide
+// (BLOCK_K * 2 bytes == swizzle bytes): SBO = 8 rows * swizzle bytes, LBO unused, version 1 (sm_100).
+template <int SWIZZLE_BYTES>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  constexpr uint64_t layout = SWIZZLE_BYTES == 128 ? 2 : (SWIZZLE_BYTES == 64 ? 4 : 6);
+  constexpr uint64_t sbo = (8 * SWIZZLE_BYTES) >> 4;
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// instruction descriptor: fp32 accumulate, A/B both K-major, fmt 0 = f16, 1 = bf16
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int kTileM = 128;
+
+struct TcShape {
+  int ntaps, nphase, kblocks;  // K iterations = ntaps * kblocks (per phase)
+  int batch;
+  int tap_off[32];             // [nphase][ntaps] row shift of the A box
+};
+
+// ------------------------------------------------------------------------------------------------
+// epilogues: called once per (row, 16 consecutive columns)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float snake_eval(float v, float alpha) {
+  const float s = sinf(alpha * v);
+  return v + s * s / (alpha + 1e-9f);
+}
+
+struct EpiConv {
+  struct Params {
+    const float* bias;
+    const float* alpha;
+    const __half* residual;
+    __half* out_raw;
+    __half* out_act;
+    int Tq, Tout, Cout, ostride;
+  };
+  __device__ static void apply(const Params& p, int b, int phase, int m, int n0, float (&v)[16]) {
+    if (m >= p.Tq || n0 >= p.Cout) return;
+    const size_t base = ((size_t)b * p.Tout + (size_t)m * p.ostride + phase) * p.Cout + n0;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + i);
+      v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+    }
+    if (p.residual) {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(p.residual + base);
+      const uint4 r1 = *reinterpret_cast<const uint4*>(p.residual + base + 8);
+      const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[2 * i] += __low2float(h0[i]); v[2 * i + 1] += __high2float(h0[i]);
+        v[8 + 2 * i] += __low2float(h1[i]); v[8 + 2 * i + 1] += __high2float(h1[i]);
+      }
+    }
+    if (p.out_raw) {
+      uint4 o[2];
+      __half2* h = reinterpret_cast<__half2*>(o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      *reinterpret_cast<uint4*>(p.out_raw + base) = o[0];
+      *reinterpret_cast<uint4*>(p.out_raw + base + 8) = o[1];
+    }
+    if (p.out_act) {
+      uint4 o[2];
+      __half2* h = reinterpret_cast<__half2*>(o);
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 al = *reinterpret_cast<const float4*>(p.alpha + n0 + i);
+        h[i / 2] = __floats2half2_rn(snake_eval(v[i], al.x), snake_eval(v[i + 1], al.y));
+        h[i / 2 + 1] = __floats2half2_rn(snake_eval(v[i + 2], al.z), snake_eval(v[i + 3], al.w));
+      }
+      *reinterpret_cast<uint4*>(p.out_act + base) = o[0];
+      *reinterpret_cast<uint4*>(p.out_act + base + 8) = o[1];
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape g,
+               const typename Epi::Params ep) {
+  constexpr int SW = BLOCK_K * 2;
+  constexpr int A_BYTES = kTileM * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "stage buffers must stay 1024B aligned for the swizzle");
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N for M=128");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kTileM, n0 = blockIdx.y * BLOCK_N;
+  const int b = blockIdx.z / g.nphase, phase = blockIdx.z % g.nphase;
+  const int iters = g.ntaps * g.kblocks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        const int tap = it / g.kblocks, kb = it % g.kblocks;
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        tma_load_3d(sa, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
+        tma_load_3d(sa + A_BYTES, &tmB, &full[s], kb * BLOCK_K, n0, phase * g.ntaps + tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kTileM, BLOCK_N, FMT);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k)  // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
+          umma_bf16_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(tmem_full);    // accumulator complete
+    }
+  } else {
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
+      Epi::apply(ep, b, phase, m, n0 + c, v);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 3-D K-major map: dims {K, rows, outer}; box {block_k, box_rows, 1}; 16-bit elements
+static bool make_map(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, uint64_t outer, uint64_t row_stride_el,
+                     uint64_t outer_stride_el, int block_k, int box_rows, bool f16) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {K, rows, outer};
+  cuuint64_t strides[2] = {row_stride_el * 2, outer_stride_el * 2};
+  cuuint32_t box[3] = {(cuuint32_t)block_k, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  return fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
+            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi>
+static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcShape& g, const typename Epi::Params& ep,
+                             int m_tiles, int n_tiles, cudaStream_t st) {
+  constexpr int smem = STAGES * (kTileM * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+  auto kern = gemm_tc_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  kern<<<dim3(m_tiles, n_tiles, g.batch * g.nphase), 192, smem, st>>>(ta, tb, g, ep);
+  return cudaGetLastError();
+}
+
+bool conv_tc_supported(int Cin, int Cout, int ntaps, int nphase) {
+  if (Cin % 32 != 0 || Cout % 16 != 0 || ntaps * nphase > 32) return false;
+  const int bk = (Cin % 64 == 0) ? 64 : 32;
+  int bn = Cout;
+  if (bn > 256) bn = (Cout % 256 == 0) ? 256 : ((Cout % 192 == 0) ? 192 : 128);
+  if (Cout % bn != 0) return false;
+  const int ok[][2] = {{256, 64}, {192, 64}, {128, 64}, {96, 64}, {64, 64}, {32, 64}, {96, 32}, {32, 32}, {16, 32}};
+  for (auto& c : ok)
+    if (c[0] == bn && c[1] == bk) return true;
+  return false;
+}
+
+// codec conv as implicit GEMM (see ConvArgs in kernels.h)
+cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cudaStream_t st) {
+  const int bk = (a.Cin % 64 == 0) ? 64 : 32;
+  if (a.Cin % bk != 0 || a.Cout % 16 != 0 || a.ntaps * a.nphase > 32) return cudaErrorInvalidValue;
+  int bn = a.Cout;
+  if (bn > 256) bn = (a.Cout % 256 == 0) ? 256 : ((a.Cout % 192 == 0) ? 192 : 128);
+  if (a.Cout % bn != 0) return cudaErrorInvalidValue;
+  CUtensorMap ta, tb;
+  if (!make_map(&ta, a.in, a.Cin, a.Tin, B, a.Cin, (uint64_t)a.Tin * a.Cin, bk, kTileM, true)) return cudaErrorUnknown;
+  if (!make_map(&tb, a.W, a.Cin, a.Cout, (uint64_t)a.ntaps * a.nphase, a.Cin, (uint64_t)a.Cout * a.Cin, bk, bn, true))
+    return cudaErrorUnknown;
+  TcShape g{};
+  g.ntaps = a.ntaps; g.nphase = a.nphase; g.kblocks = a.Cin / bk; g.batch = B;
+  for (int i = 0; i < a.ntaps * a.nphase; ++i) g.tap_off[i] = tap_off_host[i];
+  EpiConv::Params ep{a.bias, a.alpha, a.residual, a.out_raw, a.out_act, a.Tq, a.Tout, a.Cout, a.ostride};
+  const int mt = (a.Tq + kTileM - 1) / kTileM, nt = a.Cout / bn;
+#define TC_CASE(BN, BK, ST) \
+  if (bn == BN && bk == BK) return launch_tc<BN, BK, ST, 0, EpiConv>(ta, tb, g, ep, mt, nt, st);
+  TC_CASE(256, 64, 4)
+  TC_CASE(192, 64, 4)
+  TC_CASE(128, 64, 6)
+  TC_CASE(96, 64, 6)
+  TC_CASE(64, 64, 6)
+  TC_CASE(32, 64, 6)
+  TC_CASE(96, 32, 8)
+  TC_CASE(32, 32, 8)
+  TC_CASE(16, 32, 8)
+#undef TC_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace vaura

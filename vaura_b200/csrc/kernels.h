@@ -76,6 +76,8 @@ cudaError_t launch_from_codes(const int32_t* codes, const __half* tables, __half
 cudaError_t launch_conv_gemm(const ConvArgs& a, int B, cudaStream_t st);
 cudaError_t launch_conv_out_tanh(const __half* in, const float* W, const float* bias, __half* wav, int B, int T, int C,
                                  cudaStream_t st);
+bool conv_tc_supported(int Cin, int Cout, int ntaps, int nphase);
+cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cudaStream_t st);
 cudaError_t init_decode_kernels();
 
 cudaError_t launch_embed(const EmbedArgs& a, int rows, cudaStream_t st);

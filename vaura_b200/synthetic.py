@@ -90,7 +90,7 @@ FULL_SAMPLER = SamplerDims()
 FULL_CODEC = CodecDims()
 # Small shapes for fast parity cases: same head_dim (96), same vocabulary.
 TINY_SAMPLER = SamplerDims(num_layers=2, d_model=384, nhead=4)
-TINY_CODEC = CodecDims(latent_dim=256, decoder_dim=256)
+TINY_CODEC = CodecDims(latent_dim=256, decoder_dim=512)
 
 
 def _gen(seed: int, key: str) -> torch.Generator:
