@@ -102,14 +102,15 @@ extern "C" int vaura_sampler_cond_project(vaura_sampler* s, const float* feats, 
 // ---- workspace layout (fp32act) ---------------------------------------------------------------------
 struct Workspace {
   StepState* state;
-  float *h, *q, *attn, *act, *logits;
+  float *h, *q, *attn, *act, *logits;                    // fp32act path
+  __nv_bfloat16 *xn_b, *q_b, *attn_b, *act_b;            // bf16 path (h and logits stay fp32)
   size_t bytes;
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static Workspace carve(const vaura_sampler_dims& d, int rows, int max_pos, void* base) {
-  Workspace w;
+static Workspace carve(const vaura_sampler_dims& d, int rows, int max_pos, int precision, void* base) {
+  Workspace w{};
   char* p = (char*)base;
   size_t off = 0;
   auto take = [&](size_t n) {
@@ -120,19 +121,32 @@ static Workspace carve(const vaura_sampler_dims& d, int rows, int max_pos, void*
   const size_t R = (size_t)rows * max_pos;
   w.state = (StepState*)take(sizeof(StepState));
   w.h = (float*)take(R * d.d_model * 4);
-  w.q = (float*)take(R * d.d_model * 4);
-  w.attn = (float*)take(R * d.d_model * 4);
-  w.act = (float*)take(R * d.ffn_dim * 4);
   w.logits = (float*)take((size_t)rows * d.num_codebooks * d.vocab * 4);
+  if (precision == VAURA_PRECISION_BF16) {
+    w.xn_b = (__nv_bfloat16*)take(R * d.d_model * 2);
+    w.q_b = (__nv_bfloat16*)take(R * d.d_model * 2);
+    w.attn_b = (__nv_bfloat16*)take(R * d.d_model * 2);
+    w.act_b = (__nv_bfloat16*)take(R * d.ffn_dim * 2);
+  } else {
+    w.q = (float*)take(R * d.d_model * 4);
+    w.attn = (float*)take(R * d.d_model * 4);
+    w.act = (float*)take(R * d.ffn_dim * 4);
+  }
   w.bytes = off;
   return w;
 }
 
+// AUTO: the tensor-core path needs at least one 16-row UMMA N/M granule of real work to pay off; below that the
+// decode step is a pure weight stream and the fp32-activation path gives bit-stable greedy tokens.
+static int resolve_precision(int precision, int rows) {
+  if (precision != VAURA_PRECISION_AUTO) return precision;
+  return rows >= 16 ? VAURA_PRECISION_BF16 : VAURA_PRECISION_FP32ACT;
+}
+
 extern "C" size_t vaura_sampler_workspace_bytes(const vaura_sampler* s, int32_t rows, int32_t max_positions,
                                                 int32_t precision) {
-  (void)precision;
   if (!s || rows <= 0 || max_positions <= 0) return 0;
-  return carve(s->d, rows, max_positions, nullptr).bytes;
+  return carve(s->d, rows, max_positions, resolve_precision(precision, rows), nullptr).bytes;
 }
 
 static KvView kv_view(const vaura_kv_cache* kv, int nhead) {
@@ -195,6 +209,66 @@ static int transformer_pass(const vaura_sampler* s, const Workspace& ws, const i
   return VAURA_OK;
 }
 
+// Same pass on the tensor-core path: bf16 activations, tcgen05 GEMMs with fused epilogues.
+static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, const int32_t* seq, int batch, int S,
+                                 const float* cond_rows, int rows, int npos, int pos0, const StepState* state,
+                                 const KvView& kv, float* logits_dst, bool logits_all, cudaStream_t st) {
+  const vaura_sampler_dims& d = s->d;
+  const vaura_sampler_weights& w = s->w;
+  const int R = rows * npos;
+  EmbedArgs e{};
+  e.seq = seq; e.cond_rows = cond_rows; e.tables = w.tok_tables; e.h = ws.h; e.state = state; e.pos0 = pos0;
+  e.npos = npos; e.batch = batch; e.K = d.num_codebooks; e.S = S; e.vocab = d.vocab; e.d_model = d.d_model;
+  e.cond_dim = d.cond_dim; e.cond_tokens = d.cond_tokens; e.atpvf = d.audio_tokens_per_video_frame;
+  CUL(launch_embed(e, R, st));
+  const size_t D = d.d_model, F = d.ffn_dim;
+  // narrow N tiles when there is a single M tile so the weight stream is spread over all SMs
+  const bool small = R <= 128;
+  for (int l = 0; l < d.num_layers; ++l) {
+    LinearTcArgs g{};
+    g.state = state; g.pos0 = pos0; g.npos = npos; g.R = R; g.layer = l; g.d_model = d.d_model; g.kv = kv; g.rope = w.rope;
+    CUL(launch_rmsnorm_bf16(ws.h, w.attn_norm + l * D, ws.xn_b, R, D, D, d.norm_eps, st));
+    g.A = ws.xn_b; g.lda = D; g.W = w.wqkv + (size_t)l * 3 * D * D; g.N = 3 * D; g.K = D; g.epi = EPI_QKV;
+    g.out_bf16 = ws.q_b; g.block_n = small ? 32 : 128;
+    CUL(launch_linear_tc(g, st));
+    AttnBf16Args a{};
+    a.q = ws.q_b; a.out = ws.attn_b; a.kv = kv; a.state = state; a.pos0 = pos0; a.npos = npos; a.layer = l;
+    a.d_model = d.d_model; a.scale = 1.0f / sqrtf((float)kHeadDim);
+    CUL(launch_attn_bf16(a, d.nhead, R, st));
+    g.A = ws.attn_b; g.lda = D; g.W = w.wo + (size_t)l * D * D; g.N = D; g.K = D; g.epi = EPI_RESID; g.out_f32 = ws.h;
+    g.ldo = D; g.block_n = small ? 16 : 128;
+    CUL(launch_linear_tc(g, st));
+    CUL(launch_rmsnorm_bf16(ws.h, w.ffn_norm + l * D, ws.xn_b, R, D, D, d.norm_eps, st));
+    g.A = ws.xn_b; g.lda = D; g.W = w.w13 + (size_t)l * 2 * F * D; g.N = 2 * F; g.K = D; g.epi = EPI_SWIGLU;
+    g.out_bf16 = ws.act_b; g.ldo = F; g.block_n = small ? 64 : 128;
+    CUL(launch_linear_tc(g, st));
+    g.A = ws.act_b; g.lda = F; g.W = w.w2 + (size_t)l * D * F; g.N = D; g.K = F; g.epi = EPI_RESID; g.out_f32 = ws.h;
+    g.ldo = D; g.block_n = small ? 16 : 128;
+    CUL(launch_linear_tc(g, st));
+  }
+  LinearTcArgs g{};
+  g.state = state; g.pos0 = pos0; g.npos = npos; g.d_model = d.d_model;
+  g.W = w.w_heads; g.N = d.num_codebooks * d.vocab; g.K = D; g.epi = EPI_STORE; g.out_f32 = logits_dst; g.ldo = g.N;
+  g.block_n = small ? 64 : 128;
+  if (logits_all) {
+    CUL(launch_rmsnorm_bf16(ws.h, w.final_norm, ws.xn_b, R, D, D, d.norm_eps, st));
+    g.A = ws.xn_b; g.lda = D; g.R = R; g.perm_S = npos; g.perm_V = d.vocab;
+  } else {  // only the last position of every sequence row feeds the heads
+    CUL(launch_rmsnorm_bf16(ws.h + (size_t)(npos - 1) * D, w.final_norm, ws.xn_b, rows, D, (size_t)npos * D, d.norm_eps, st));
+    g.A = ws.xn_b; g.lda = D; g.R = rows;
+  }
+  CUL(launch_linear_tc(g, st));
+  return VAURA_OK;
+}
+
+static int run_pass(int precision, const vaura_sampler* s, const Workspace& ws, const int32_t* seq, int batch, int S,
+                    const float* cond_rows, int rows, int npos, int pos0, const StepState* state, const KvView& kv,
+                    float* logits_dst, bool logits_all, cudaStream_t st) {
+  return precision == VAURA_PRECISION_BF16
+             ? transformer_pass_bf16(s, ws, seq, batch, S, cond_rows, rows, npos, pos0, state, kv, logits_dst, logits_all, st)
+             : transformer_pass(s, ws, seq, batch, S, cond_rows, rows, npos, pos0, state, kv, logits_dst, logits_all, st);
+}
+
 static int check_kv(const vaura_sampler* s, const vaura_kv_cache* kv, int want_dtype) {
   if (!kv || !kv->pages || !kv->page_table) return fail(VAURA_ERR_INVALID, "kv cache missing");
   if (kv->page_size != 16 && kv->page_size != 32) return fail(VAURA_ERR_INVALID, "page_size must be 16 or 32");
@@ -215,13 +289,14 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     return fail(VAURA_ERR_INVALID, "bad offsets [%d,%d) for S=%d", p->start_offset, p->end_offset, S);
   // sequence positions >= block_size overflow the RoPE table in the reference too (llama.py:493-497)
   if (S - 1 > d.block_size) return fail(VAURA_ERR_INVALID, "sequence of %d columns exceeds block_size %d", S, d.block_size);
-  int precision = p->precision == VAURA_PRECISION_AUTO ? VAURA_PRECISION_FP32ACT : p->precision;
-  if (precision != VAURA_PRECISION_FP32ACT) return fail(VAURA_ERR_UNSUPPORTED, "precision mode %d not built yet", precision);
-  int rc = check_kv(s, kv, VAURA_KV_F32);
-  if (rc) return rc;
   const int rows = p->batch * (p->use_cfg ? 2 : 1);
+  const int precision = resolve_precision(p->precision, rows);
+  if (precision != VAURA_PRECISION_FP32ACT && precision != VAURA_PRECISION_BF16)
+    return fail(VAURA_ERR_INVALID, "unknown precision mode %d", precision);
+  int rc = check_kv(s, kv, precision == VAURA_PRECISION_BF16 ? VAURA_KV_BF16 : VAURA_KV_F32);
+  if (rc) return rc;
   const int npre = p->start_offset;  // columns [0, start) are consumed by the first pass (prefill when > 1)
-  Workspace ws = carve(d, rows, npre, workspace);
+  Workspace ws = carve(d, rows, npre, precision, workspace);
   if (ws.bytes > workspace_bytes) return fail(VAURA_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
   cudaStream_t st = (cudaStream_t)stream;
   const KvView kvv = kv_view(kv, d.nhead);
@@ -233,7 +308,7 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   sa.top_p = p->top_p; sa.seed_lo = (uint32_t)p->seed; sa.seed_hi = (uint32_t)(p->seed >> 32);
 
   // first pass: positions [0, start) -> sample column start
-  rc = transformer_pass(s, ws, p->sequence, p->batch, S, p->cond_rows, rows, npre, 0, nullptr, kvv, ws.logits, false, st);
+  rc = run_pass(precision, s, ws, p->sequence, p->batch, S, p->cond_rows, rows, npre, 0, nullptr, kvv, ws.logits, false, st);
   if (rc) return rc;
   sa.state = nullptr; sa.offset = p->start_offset;
   CUL(launch_sample(sa, st));
@@ -247,7 +322,7 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
   g_capturing = true;
   g_capture_nodes = 0;
-  rc = transformer_pass(s, ws, p->sequence, p->batch, S, p->cond_rows, rows, 1, 0, ws.state, kvv, ws.logits, false, cs);
+  rc = run_pass(precision, s, ws, p->sequence, p->batch, S, p->cond_rows, rows, 1, 0, ws.state, kvv, ws.logits, false, cs);
   if (rc == VAURA_OK) {
     sa.state = ws.state;
     cudaError_t e = launch_sample(sa, cs);
@@ -276,15 +351,16 @@ extern "C" int vaura_sampler_forward(vaura_sampler* s, const int32_t* sequence, 
     return fail(VAURA_ERR_INVALID, "bad argument");
   const vaura_sampler_dims& d = s->d;
   if (S > d.block_size) return fail(VAURA_ERR_INVALID, "S=%d exceeds block_size %d (llama.py:493-497)", S, d.block_size);
-  if (precision == VAURA_PRECISION_AUTO) precision = VAURA_PRECISION_FP32ACT;
-  if (precision != VAURA_PRECISION_FP32ACT) return fail(VAURA_ERR_UNSUPPORTED, "precision mode %d not built yet", precision);
-  int rc = check_kv(s, kv, VAURA_KV_F32);
+  precision = resolve_precision(precision, rows);
+  if (precision != VAURA_PRECISION_FP32ACT && precision != VAURA_PRECISION_BF16)
+    return fail(VAURA_ERR_INVALID, "unknown precision mode %d", precision);
+  int rc = check_kv(s, kv, precision == VAURA_PRECISION_BF16 ? VAURA_KV_BF16 : VAURA_KV_F32);
   if (rc) return rc;
-  Workspace ws = carve(d, rows, S, workspace);
+  Workspace ws = carve(d, rows, S, precision, workspace);
   if (ws.bytes > workspace_bytes) return fail(VAURA_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
   // the heads GEMV stores straight into the reference layout [rows][K][S][V] (llama.py:504 torch.stack(dim=1))
-  return transformer_pass(s, ws, sequence, rows, S, cond_rows, rows, S, 0, nullptr, kv_view(kv, d.nhead), logits_out, true,
-                          (cudaStream_t)stream);
+  return run_pass(precision, s, ws, sequence, rows, S, cond_rows, rows, S, 0, nullptr, kv_view(kv, d.nhead), logits_out, true,
+                  (cudaStream_t)stream);
 }
 
 extern "C" int vaura_sample_logits(const float* logits, int32_t rows, int32_t K, int32_t V, int32_t use_cfg,

@@ -1,0 +1,123 @@
+// bf16-activation sampler path (VAURA_PRECISION_BF16, batch >= 16 and prefill): the projections run on
+// tcgen05 (gemm_tcgen05.cu); this file holds the two memory-bound stages between them.
+//   rmsnorm_bf16_kernel  llama.py:147-158, fp32 math, bf16 output (the GEMM's A operand)
+//   attn_bf16_kernel     llama.py:246-255 over the paged bf16 KV cache, fp32 softmax / accumulation
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vaura {
+
+__global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(const float* __restrict__ h, const float* __restrict__ w,
+                                                           __nv_bfloat16* __restrict__ out, int R, int D, size_t ldh, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= R) return;
+  const float* x = h + (size_t)r * ldh;
+  float ss = 0.f;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(x + c);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = warp_sum(ss);
+  const float rs = rsqrtf(ss / (float)D + eps);
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(x + c);
+    const float4 g = *reinterpret_cast<const float4*>(w + c);
+    uint2 o;
+    *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v.x * rs * g.x, v.y * rs * g.y);
+    *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v.z * rs * g.z, v.w * rs * g.w);
+    *reinterpret_cast<uint2*>(out + (size_t)r * D + c) = o;
+  }
+}
+
+cudaError_t launch_rmsnorm_bf16(const float* h, const float* w, void* out_bf16, int R, int D, size_t ldh, float eps,
+                                cudaStream_t st) {
+  rmsnorm_bf16_kernel<<<(R + 7) / 8, 256, 0, st>>>(h, w, reinterpret_cast<__nv_bfloat16*>(out_bf16), R, D, ldh, eps);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(128) attn_bf16_kernel(AttnBf16Args a) {
+  __shared__ float qs[kHeadDim];
+  __shared__ float sc[kMaxCtx];
+  __shared__ float red[4];
+  const int h = blockIdx.x, row = blockIdx.y;
+  const int b = row / a.npos, j = row % a.npos;
+  const int pos0 = a.state ? a.state->offset - a.npos : a.pos0;
+  const int p = pos0 + j, nctx = p + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __nv_bfloat16* kvp = reinterpret_cast<const __nv_bfloat16*>(a.kv.pages);
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(a.q);
+  if (tid < kHeadDim) qs[tid] = __bfloat162float(q[(size_t)row * a.d_model + h * kHeadDim + tid]);
+  __syncthreads();
+
+  // scores: 4 lanes per key position, 24 dims (48 bytes = 3 x 16B) each
+  const int g = tid >> 2, t = tid & 3;
+  float q24[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) q24[i] = qs[t * 24 + i];
+  const int nround = (nctx + 31) & ~31;
+  for (int jj = g; jj < nround; jj += 32) {
+    float s = 0.f;
+    if (jj < nctx) {
+      const uint4* kr = reinterpret_cast<const uint4*>(kvp + a.kv.row(a.layer, 0, b, jj, h) + t * 24);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const uint4 kk = kr[c];
+        const uint32_t w[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s = fmaf(q24[c * 8 + 2 * e], bf16_lo(w[e]), s);
+          s = fmaf(q24[c * 8 + 2 * e + 1], bf16_hi(w[e]), s);
+        }
+      }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (t == 0 && jj < nctx) sc[jj] = s * a.scale;
+  }
+  __syncthreads();
+
+  float m = -INFINITY;
+  for (int jj = tid; jj < nctx; jj += 128) m = fmaxf(m, sc[jj]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int jj = tid; jj < nctx; jj += 128) {
+    const float e = expf(sc[jj] - m);
+    sc[jj] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = red[0] + red[1] + red[2] + red[3];
+
+  // P.V: 48 threads x 2 dims; the 128 threads split the positions in 2 halves (threads 48..95 take odd ones)
+  __shared__ float part[2][kHeadDim];
+  if (tid < 96) {
+    const int half = tid / 48, d2 = (tid % 48) * 2;
+    float a0 = 0.f, a1 = 0.f;
+    for (int jj = half; jj < nctx; jj += 2) {
+      const uint32_t vv = *reinterpret_cast<const uint32_t*>(kvp + a.kv.row(a.layer, 1, b, jj, h) + d2);
+      a0 = fmaf(sc[jj], bf16_lo(vv), a0);
+      a1 = fmaf(sc[jj], bf16_hi(vv), a1);
+    }
+    part[half][d2] = a0;
+    part[half][d2 + 1] = a1;
+  }
+  __syncthreads();
+  if (tid < kHeadDim) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out);
+    o[(size_t)row * a.d_model + h * kHeadDim + tid] = __float2bfloat16_rn((part[0][tid] + part[1][tid]) / sum);
+  }
+}
+
+cudaError_t launch_attn_bf16(const AttnBf16Args& a, int nhead, int rows, cudaStream_t st) {
+  attn_bf16_kernel<<<dim3(nhead, rows), 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace vaura

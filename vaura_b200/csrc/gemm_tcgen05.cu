@@ -159,6 +159,74 @@ struct EpiConv {
   }
 };
 
+// ---- linear-layer epilogues of the bf16 sampler path (row = sequence row * npos + position) ---------------
+struct EpiLinear {
+  struct Params {
+    int mode;             // EPI_STORE / EPI_RESID / EPI_SWIGLU / EPI_QKV
+    int R, N;             // valid rows / output features
+    float* out_f32;       // STORE: [R][ldo] (or permuted), RESID: residual stream h [R][ldo]
+    __nv_bfloat16* out_bf16;  // SWIGLU: act [R][ldo]; QKV: q [R][d_model]
+    int ldo;
+    int perm_S, perm_V;   // STORE: see GemvArgs
+    const float* rope;
+    KvView kv;
+    const StepState* state;
+    int pos0, npos, layer, d_model;
+  };
+  __device__ static void apply(const Params& p, int /*b*/, int /*phase*/, int m, int n0, float (&v)[16]) {
+    if (m >= p.R || n0 >= p.N) return;
+    if (p.mode == EPI_STORE) {
+      size_t o = (size_t)m * p.ldo + n0;
+      if (p.perm_S > 0) {
+        const int bb = m / p.perm_S, j = m % p.perm_S, kk = n0 / p.perm_V;
+        o = (((size_t)bb * (p.N / p.perm_V) + kk) * p.perm_S + j) * p.perm_V + (n0 % p.perm_V);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(p.out_f32 + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else if (p.mode == EPI_RESID) {
+      float* o = p.out_f32 + (size_t)m * p.ldo + n0;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        float4 h = *reinterpret_cast<float4*>(o + i);
+        h.x += v[i]; h.y += v[i + 1]; h.z += v[i + 2]; h.w += v[i + 3];
+        *reinterpret_cast<float4*>(o + i) = h;
+      }
+    } else if (p.mode == EPI_SWIGLU) {
+      uint4 o;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a0 = v[4 * i], b0 = v[4 * i + 1], a1 = v[4 * i + 2], b1 = v[4 * i + 3];
+        h[i] = __floats2bfloat162_rn(a0 / (1.f + expf(-a0)) * b0, a1 / (1.f + expf(-a1)) * b1);
+      }
+      *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)m * p.ldo + (n0 >> 1)) = o;
+    } else {  // EPI_QKV
+      const int D = p.d_model, sec = n0 / D, within = n0 % D;
+      const int hd = within / kHeadDim, e = within % kHeadDim;
+      const int b = m / p.npos, j = m % p.npos;
+      const int pos = (p.state ? p.state->offset - p.npos : p.pos0) + j;
+      if (sec != 2) {
+        const float4* cs = reinterpret_cast<const float4*>(p.rope + ((size_t)pos * (kHeadDim / 2) + (e >> 1)) * 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // two (cos,sin) pairs per float4
+          const float4 c = cs[i];
+          const float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
+          v[4 * i] = x0 * c.x - x1 * c.y; v[4 * i + 1] = x1 * c.x + x0 * c.y;
+          v[4 * i + 2] = x2 * c.z - x3 * c.w; v[4 * i + 3] = x3 * c.z + x2 * c.w;
+        }
+      }
+      uint4 o[2];
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      __nv_bfloat16* dst = sec == 0 ? p.out_bf16 + (size_t)m * D + within
+                                    : reinterpret_cast<__nv_bfloat16*>(p.kv.pages) + p.kv.row(p.layer, sec - 1, b, pos, hd) + e;
+      *reinterpret_cast<uint4*>(dst) = o[0];
+      *reinterpret_cast<uint4*>(dst + 8) = o[1];
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -341,6 +409,28 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cu
   TC_CASE(32, 32, 8)
   TC_CASE(16, 32, 8)
 #undef TC_CASE
+  return cudaErrorInvalidValue;
+}
+
+// Linear layer of the bf16 sampler path: out = A[R][K] (bf16) x W[N][K]^T (bf16) with a fused epilogue.
+cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st) {
+  if (a.K % 64 != 0 || a.N % a.block_n != 0) return cudaErrorInvalidValue;
+  CUtensorMap ta, tb;
+  if (!make_map(&ta, a.A, a.K, a.R, 1, a.lda, (uint64_t)a.R * a.lda, 64, kTileM, false)) return cudaErrorUnknown;
+  if (!make_map(&tb, a.W, a.K, a.N, 1, a.K, (uint64_t)a.N * a.K, 64, a.block_n, false)) return cudaErrorUnknown;
+  TcShape g{};
+  g.ntaps = 1; g.nphase = 1; g.kblocks = a.K / 64; g.batch = 1;
+  EpiLinear::Params ep{};
+  ep.mode = a.epi; ep.R = a.R; ep.N = a.N; ep.out_f32 = a.out_f32; ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
+  ep.ldo = a.ldo; ep.perm_S = a.perm_S; ep.perm_V = a.perm_V; ep.rope = a.rope; ep.kv = a.kv; ep.state = a.state;
+  ep.pos0 = a.pos0; ep.npos = a.npos; ep.layer = a.layer; ep.d_model = a.d_model;
+  const int mt = (a.R + kTileM - 1) / kTileM, nt = a.N / a.block_n;
+  switch (a.block_n) {
+    case 16: return launch_tc<16, 64, 8, 1, EpiLinear>(ta, tb, g, ep, mt, nt, st);
+    case 32: return launch_tc<32, 64, 8, 1, EpiLinear>(ta, tb, g, ep, mt, nt, st);
+    case 64: return launch_tc<64, 64, 6, 1, EpiLinear>(ta, tb, g, ep, mt, nt, st);
+    case 128: return launch_tc<128, 64, 6, 1, EpiLinear>(ta, tb, g, ep, mt, nt, st);
+  }
   return cudaErrorInvalidValue;
 }
 

@@ -76,6 +76,30 @@ cudaError_t launch_from_codes(const int32_t* codes, const __half* tables, __half
 cudaError_t launch_conv_gemm(const ConvArgs& a, int B, cudaStream_t st);
 cudaError_t launch_conv_out_tanh(const __half* in, const float* W, const float* bias, __half* wav, int B, int T, int C,
                                  cudaStream_t st);
+struct LinearTcArgs {
+  const void* A;        // bf16 [R][lda]
+  const void* W;        // bf16 [N][K]
+  float* out_f32;
+  void* out_bf16;
+  const float* rope;
+  KvView kv;
+  const StepState* state;
+  int R, N, K, lda, ldo, block_n, epi;
+  int perm_S, perm_V, pos0, npos, layer, d_model;
+};
+cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st);
+// bf16 path helpers (decode_bf16.cu)
+cudaError_t launch_rmsnorm_bf16(const float* h, const float* w, void* out_bf16, int R, int D, size_t ldh, float eps, cudaStream_t st);
+struct AttnBf16Args {
+  const void* q;   // bf16 [rows*npos][d]
+  void* out;       // bf16 [rows*npos][d]
+  KvView kv;
+  const StepState* state;
+  int pos0, npos, layer, d_model;
+  float scale;
+};
+cudaError_t launch_attn_bf16(const AttnBf16Args& a, int nhead, int rows, cudaStream_t st);
+
 bool conv_tc_supported(int Cin, int Cout, int ntaps, int nphase);
 cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cudaStream_t st);
 cudaError_t init_decode_kernels();

@@ -21,6 +21,13 @@ from .weights import pack_sampler
 PAGE_SIZE = 32
 
 
+def resolve_precision(precision: int, rows: int) -> int:
+    """Same rule as csrc/cabi.cu: AUTO -> tcgen05/bf16 path from 16 sequence rows, fp32-activation path below."""
+    if precision != _cabi.PRECISION_AUTO:
+        return precision
+    return _cabi.PRECISION_BF16 if rows >= 16 else _cabi.PRECISION_FP32ACT
+
+
 class _CondEmbedder:
     """Stand-in for ``AVCLIPEmbedder`` exposing what callers read (vaura_model.py:790-793)."""
 
@@ -175,9 +182,10 @@ class Transformer(torch.nn.Module):
         seq = tgt.to(device=self.device, dtype=torch.int32).contiguous()
         logits = torch.empty(B, K, S, self.dims.d_codebook, dtype=torch.float32, device=self.device)
         h = self.handle()
+        precision = resolve_precision(precision, B)
         nbytes = lib.vaura_sampler_workspace_bytes(h, B, S, precision)
         ws = self._buffer("ws", nbytes)
-        kv = self._kv(B)
+        kv = self._kv(B, _cabi.KV_BF16 if precision == _cabi.PRECISION_BF16 else _cabi.KV_F32)
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream().cuda_stream
             _cabi.check(lib.vaura_sampler_forward(h, seq.data_ptr(), rows.data_ptr(), B, S, logits.data_ptr(), C.byref(kv),
@@ -195,9 +203,10 @@ class Transformer(torch.nn.Module):
         rows = B * (2 if use_cfg else 1)
         assert cond_rows.shape[0] == rows and cond_rows.is_contiguous()
         h = self.handle()
+        precision = resolve_precision(precision, rows)
         nbytes = lib.vaura_sampler_workspace_bytes(h, rows, max(start_offset, 1), precision)
         ws = self._buffer("ws", nbytes)
-        kv = self._kv(rows)
+        kv = self._kv(rows, _cabi.KV_BF16 if precision == _cabi.PRECISION_BF16 else _cabi.KV_F32)
         p = _cabi.GenerateParamsC(
             batch=B, use_cfg=int(use_cfg), timesteps=timesteps, start_offset=start_offset,
             end_offset=S if end_offset is None else end_offset, use_sampling=int(use_sampling), temp=float(temp),
