@@ -102,7 +102,8 @@ extern "C" int vaura_sampler_cond_project(vaura_sampler* s, const float* feats, 
 // ---- workspace layout (fp32act) ---------------------------------------------------------------------
 struct Workspace {
   StepState* state;
-  float *h, *q, *attn, *act, *logits;                    // fp32act path
+  unsigned long long* timing;
+  float *h, *q, *attn, *act, *logits, *attn_part;        // fp32act path
   __nv_bfloat16 *xn_b, *q_b, *attn_b, *act_b;            // bf16 path (h and logits stay fp32)
   size_t bytes;
 };
@@ -120,6 +121,7 @@ static Workspace carve(const vaura_sampler_dims& d, int rows, int max_pos, int p
   };
   const size_t R = (size_t)rows * max_pos;
   w.state = (StepState*)take(sizeof(StepState));
+  w.timing = (unsigned long long*)take(16384);  // debug: persistent-kernel phase timestamps (workspace bytes [256, 16640))
   w.h = (float*)take(R * d.d_model * 4);
   w.logits = (float*)take((size_t)rows * d.num_codebooks * d.vocab * 4);
   if (precision == VAURA_PRECISION_BF16) {
@@ -131,6 +133,7 @@ static Workspace carve(const vaura_sampler_dims& d, int rows, int max_pos, int p
     w.q = (float*)take(R * d.d_model * 4);
     w.attn = (float*)take(R * d.d_model * 4);
     w.act = (float*)take(R * d.ffn_dim * 4);
+    w.attn_part = (float*)take(persistent_attn_part_bytes(rows, d.nhead));
   }
   w.bytes = off;
   return w;
@@ -315,8 +318,26 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   const int nsteps = p->end_offset - (p->start_offset + 1);
   if (nsteps <= 0) return VAURA_OK;
 
-  // decode steps: capture one step (reads its position from the device state) and replay it
+  // decode steps
   CUL(launch_set_state(ws.state, p->start_offset + 1, st));
+  const char* no_persist = getenv("VAURA_NO_PERSISTENT");
+  if (precision == VAURA_PRECISION_FP32ACT && persistent_supported(rows, d.d_model, d.ffn_dim, kv->page_size) &&
+      !(no_persist && no_persist[0] == '1')) {
+    // rows <= 4: one persistent cooperative kernel per step (weights streamed through an smem ring by TMA)
+    PersistArgs pa{};
+    const vaura_sampler_weights& w = s->w;
+    pa.wqkv = w.wqkv; pa.wo = w.wo; pa.w13 = w.w13; pa.w2 = w.w2; pa.w_heads = w.w_heads; pa.attn_norm = w.attn_norm;
+    pa.ffn_norm = w.ffn_norm; pa.final_norm = w.final_norm; pa.tok_tables = w.tok_tables; pa.rope = w.rope;
+    pa.seq = p->sequence; pa.cond_rows = p->cond_rows; pa.h = ws.h; pa.q = ws.q; pa.act = ws.act; pa.logits = ws.logits;
+    pa.attn_part = ws.attn_part; pa.kv = kvv; pa.state = ws.state; pa.sample = sa; pa.sample.state = nullptr;
+    pa.L = d.num_layers; pa.D = d.d_model; pa.F = d.ffn_dim; pa.H = d.nhead; pa.Kc = K; pa.V = d.vocab; pa.S = S;
+    pa.batch = p->batch; pa.cond_dim = d.cond_dim; pa.cond_tokens = d.cond_tokens; pa.atpvf = d.audio_tokens_per_video_frame;
+    pa.eps = d.norm_eps; pa.scale = 1.0f / sqrtf((float)kHeadDim);
+    { const char* tm = getenv("VAURA_PERSIST_TIMING"); pa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
+    for (int i = 0; i < nsteps; ++i) CUL(launch_decode_persistent(pa, rows, st));
+    return VAURA_OK;
+  }
+  // otherwise: capture one step (reads its position from the device state) and replay it
   cudaGraph_t graph = nullptr;
   cudaStream_t cs = s->capture_stream;
   CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));

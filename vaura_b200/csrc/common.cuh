@@ -15,7 +15,9 @@ constexpr int kUnknown = -1;   // "not generated yet" marker (vaura_model.py:482
 struct StepState {
   int offset;    // column about to be sampled; the step consumes columns [offset - npos, offset)
   int done;      // arrival counter of the sampling kernel's CTAs
-  int pad[62];
+  unsigned epoch;    // persistent kernel: launches since the state was (re)initialised
+  unsigned barrier;  // persistent kernel: monotonically increasing device-wide barrier counter
+  int pad[60];
 };
 
 __device__ __forceinline__ float warp_sum(float v) {

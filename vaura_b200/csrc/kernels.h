@@ -104,6 +104,25 @@ bool conv_tc_supported(int Cin, int Cout, int ntaps, int nphase);
 cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cudaStream_t st);
 cudaError_t init_decode_kernels();
 
+// persistent decode-step kernel (decode_persistent.cu)
+struct PersistArgs {
+  const uint16_t *wqkv, *wo, *w13, *w2, *w_heads;
+  const float *attn_norm, *ffn_norm, *final_norm, *tok_tables, *rope;
+  const int32_t* seq;
+  const float* cond_rows;
+  float *h, *q, *act, *logits, *attn_part;
+  KvView kv;
+  StepState* state;
+  unsigned long long* timing;  // optional: phase timestamps (ns) of CTA 0
+  SampleArgs sample;
+  int L, D, F, H, Kc, V, S, batch, cond_dim, cond_tokens, atpvf, nslots, max_inflight;
+  float eps, scale;
+};
+
+bool persistent_supported(int rows, int D, int F, int page_size);
+size_t persistent_attn_part_bytes(int rows, int H);
+cudaError_t launch_decode_persistent(PersistArgs& a, int rows, cudaStream_t st);
+
 cudaError_t launch_embed(const EmbedArgs& a, int rows, cudaStream_t st);
 cudaError_t launch_gemv(int epi, bool norm, const GemvArgs& a, cudaStream_t st);
 cudaError_t launch_attn(const AttnArgs& a, int nhead, int rows, cudaStream_t st);
