@@ -36,3 +36,4 @@ for n, v in zip(names, per):
     print(f"  {n:8s} {v / L / 1e3:7.2f} us/layer")
 print("  tail: final-norm %.2f heads %.2f bar %.2f sample %.2f us" % tuple(x / 1e3 for x in tail))
 
+

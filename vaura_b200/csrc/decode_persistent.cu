@@ -4,10 +4,13 @@
 // wo+residual | RMSNorm+w1|w3+SiLU*mul | w2+residual} -> final norm + 9 heads -> CFG/sampling/write-back.
 // Every CTA owns a fixed contiguous block of output rows of every weight matrix, so its weight bytes for the
 // step are one fixed sequence of contiguous chunks.  A dedicated producer warp streams that sequence with
-// cp.async.bulk (TMA 1-D) into a ring of 18 KB shared-memory slots guarded by full/empty mbarriers; it never
-// waits for the dependency chain, so HBM keeps streaming while the 16 consumer warps sit in a grid barrier or in
-// the attention phase (the ring holds ~4.5 us of traffic per SM).  Consumers read weights and activations from
-// shared memory only; phases are separated by a device-wide barrier (one atomic + acquire spin per CTA).
+// cp.async.bulk (TMA 1-D) into two ~90 KB shared-memory slots (double buffer) guarded by full/empty mbarriers; it
+// never waits for the dependency chain, so HBM keeps streaming while the 15 consumer warps sit in a grid barrier or
+// in the attention phase.  A slot holds one "group" of up to 15 work items (one row pair per consumer warp; pairs
+// with K > 1536 are split along K over several warps), so ring synchronisation costs one mbarrier wait and one
+// arrive per group instead of per warp (mbarrier operations serialise at ~50 cycles each per SM).  Consumers read
+// weights and activations from shared memory only; phases are separated by a device-wide barrier (red.release +
+// ld.acquire spin per CTA).
 //
 // Replaces the same reference lines as decode_fp32.cu (llama.py:445-517 for one position) plus the sampling
 // stage of sampling.cu; arithmetic (fp32 accumulate order per row aside) is identical to gemv_kernel/attn_kernel.
@@ -22,7 +25,7 @@ namespace {
 constexpr int NW = 15;                     // consumer warps (+1 producer = 16 warps: 128 registers per thread)
 constexpr int kConsumers = NW * 32;        // 480
 constexpr int kThreadsP = kConsumers + 32;  // + producer warp
-constexpr int SLOT_BYTES = 18 * 1024;      // 3 row pairs of K=1536, or 1 row pair of K=4096
+constexpr int kMaxSplit = 4;               // a row pair with K > 1536 is split over up to 4 warps along K
 constexpr int ATT_STRIDE = 100;            // floats per attention partial: m, l, pad, pad, o[96]
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -63,6 +66,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(s_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
@@ -86,37 +92,56 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
   consumer_sync();
 }
 
-// dot products of one row pair (rows w0, w1 of K bf16 in smem) with NB activation rows (xs, permuted, smem).
-// All weight loads of a 192-chunk window are issued before the first FMA; every chunk is its own FMA chain.
+// explicit shared-memory loads: through generic pointers the compiler emits LD.E (generic), whose latency to the
+// shared window is several times that of LDS and sat on the critical path of every row pair
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// dot products of one row pair (rows at shared addresses w0, w1; K bf16 each) over chunks [c0, c1) with NB
+// activation rows (xs_addr: permuted fp32 rows in shared memory).  Loads of a 3-chunk window are issued before its FMAs.
 template <int NB>
-__device__ __forceinline__ void pair_dot(const uint4* __restrict__ w0, const uint4* __restrict__ w1,
-                                         const float* __restrict__ xs, int K, int lane, float (&acc0)[NB], float (&acc1)[NB]) {
-  const int K8 = K >> 3, halfK = K >> 1;
+__device__ __forceinline__ void pair_dot(uint32_t w0, uint32_t w1, uint32_t xs_addr, int K, int c0, int c1, int lane,
+                                         float (&acc0)[NB], float (&acc1)[NB]) {
 #pragma unroll
   for (int r = 0; r < NB; ++r) acc0[r] = acc1[r] = 0.f;
-  for (int base = 0; base < K8; base += 192) {
-    uint4 wa[6], wb[6];
+  for (int base = c0 + lane; base < c1; base += 96) {
+    uint4 wa[3], wb[3];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int c = base + lane + 32 * i;
-      if (c < K8) { wa[i] = w0[c]; wb[i] = w1[c]; }
+    for (int i = 0; i < 3; ++i) {
+      const int c = base + 32 * i;
+      if (c < c1) { wa[i] = lds_u4(w0 + 16 * c); wb[i] = lds_u4(w1 + 16 * c); }
     }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int c = base + lane + 32 * i;
-      if (c < K8) {
+    for (int r = 0; r < NB; ++r) {
+      float4 xl[3], xh[3];
 #pragma unroll
-        for (int r = 0; r < NB; ++r) {
-          const float4 xl = *reinterpret_cast<const float4*>(xs + (size_t)r * K + 4 * c);
-          const float4 xh = *reinterpret_cast<const float4*>(xs + (size_t)r * K + halfK + 4 * c);
-          float p0 = bf16_lo(wa[i].x) * xl.x, p1 = bf16_lo(wb[i].x) * xl.x;
-          p0 = fmaf(bf16_hi(wa[i].x), xl.y, p0); p1 = fmaf(bf16_hi(wb[i].x), xl.y, p1);
-          p0 = fmaf(bf16_lo(wa[i].y), xl.z, p0); p1 = fmaf(bf16_lo(wb[i].y), xl.z, p1);
-          p0 = fmaf(bf16_hi(wa[i].y), xl.w, p0); p1 = fmaf(bf16_hi(wb[i].y), xl.w, p1);
-          p0 = fmaf(bf16_lo(wa[i].z), xh.x, p0); p1 = fmaf(bf16_lo(wb[i].z), xh.x, p1);
-          p0 = fmaf(bf16_hi(wa[i].z), xh.y, p0); p1 = fmaf(bf16_hi(wb[i].z), xh.y, p1);
-          p0 = fmaf(bf16_lo(wa[i].w), xh.z, p0); p1 = fmaf(bf16_lo(wb[i].w), xh.z, p1);
-          p0 = fmaf(bf16_hi(wa[i].w), xh.w, p0); p1 = fmaf(bf16_hi(wb[i].w), xh.w, p1);
+      for (int i = 0; i < 3; ++i) {
+        const int c = base + 32 * i;
+        if (c < c1) {
+          xl[i] = lds_f4(xs_addr + 4 * (r * K + 4 * c));
+          xh[i] = lds_f4(xs_addr + 4 * (r * K + (K >> 1) + 4 * c));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int c = base + 32 * i;
+        if (c < c1) {
+          float p0 = bf16_lo(wa[i].x) * xl[i].x, p1 = bf16_lo(wb[i].x) * xl[i].x;
+          p0 = fmaf(bf16_hi(wa[i].x), xl[i].y, p0); p1 = fmaf(bf16_hi(wb[i].x), xl[i].y, p1);
+          p0 = fmaf(bf16_lo(wa[i].y), xl[i].z, p0); p1 = fmaf(bf16_lo(wb[i].y), xl[i].z, p1);
+          p0 = fmaf(bf16_hi(wa[i].y), xl[i].w, p0); p1 = fmaf(bf16_hi(wb[i].y), xl[i].w, p1);
+          p0 = fmaf(bf16_lo(wa[i].z), xh[i].x, p0); p1 = fmaf(bf16_lo(wb[i].z), xh[i].x, p1);
+          p0 = fmaf(bf16_hi(wa[i].z), xh[i].y, p0); p1 = fmaf(bf16_hi(wb[i].z), xh[i].y, p1);
+          p0 = fmaf(bf16_lo(wa[i].w), xh[i].z, p0); p1 = fmaf(bf16_lo(wb[i].w), xh[i].z, p1);
+          p0 = fmaf(bf16_hi(wa[i].w), xh[i].w, p0); p1 = fmaf(bf16_hi(wb[i].w), xh[i].w, p1);
           acc0[r] += p0; acc1[r] += p1;
         }
       }
@@ -125,6 +150,68 @@ __device__ __forceinline__ void pair_dot(const uint4* __restrict__ w0, const uin
 #pragma unroll
   for (int r = 0; r < NB; ++r) { acc0[r] = warp_sum(acc0[r]); acc1[r] = warp_sum(acc1[r]); }
 }
+
+__device__ __forceinline__ void pair_range(int pairs, int cta, int G, int& p0, int& p1) {
+  p0 = (int)(((unsigned)pairs * (unsigned)cta) / (unsigned)G);  // pairs * G < 2^31 for every supported shape
+  p1 = (int)(((unsigned)pairs * (unsigned)(cta + 1)) / (unsigned)G);
+}
+
+// Grouping of a CTA's row pairs of one phase: `splits` warps share a pair along K, a group holds at most
+// NW / splits pairs and at most slot_cap bytes, and the pairs are spread evenly over the groups.
+struct GroupPlan {
+  int splits, ngroups, base, rem;  // group g holds base + (g < rem) pairs
+  __device__ GroupPlan(int K, int npairs, int slot_cap) {
+    splits = (K + 1535) / 1536;
+    if (splits > kMaxSplit) splits = kMaxSplit;
+    int ppg = NW / splits;
+    const int cap = slot_cap / (4 * K);
+    if (ppg > cap) ppg = cap;
+    ngroups = (npairs + ppg - 1) / ppg;
+    base = ngroups ? npairs / ngroups : 0;
+    rem = ngroups ? npairs % ngroups : 0;
+  }
+};
+
+// The CTA's weight groups of one decode step in consumption order.
+struct WeightSched {
+  const PersistArgs& a;
+  int cta, G, l, ph, g, pp;
+  bool open;
+  GroupPlan gp;
+  const uint16_t* W;
+  int K;
+  __device__ WeightSched(const PersistArgs& a_, int cta_, int G_) : a(a_), cta(cta_), G(G_), l(0), ph(-1), g(0), pp(0), open(false), gp(1536, 0, 1 << 20), W(nullptr), K(0) {}
+  __device__ bool advance_phase() {
+    ++ph;
+    if (l < a.L && ph == 4) { ph = 0; ++l; }
+    if (l > a.L || (l == a.L && ph > 0)) return false;
+    const int D = a.D, F = a.F;
+    int pairs;
+    if (l == a.L) { W = a.w_heads; K = D; pairs = a.Kc * a.V / 2; }
+    else if (ph == 0) { W = a.wqkv + (size_t)l * 3 * D * D; K = D; pairs = 3 * D / 2; }
+    else if (ph == 1) { W = a.wo + (size_t)l * D * D; K = D; pairs = D / 2; }
+    else if (ph == 2) { W = a.w13 + (size_t)l * 2 * F * D; K = D; pairs = F; }
+    else { W = a.w2 + (size_t)l * D * F; K = F; pairs = D / 2; }
+    int p0, p1;
+    pair_range(pairs, cta, G, p0, p1);
+    gp = GroupPlan(K, p1 - p0, a.slot_cap);
+    g = 0;
+    pp = p0;
+    return true;
+  }
+  __device__ bool next(const uint16_t*& ptr, uint32_t& bytes) {
+    while (!open || g >= gp.ngroups) {
+      if (!advance_phase()) return false;
+      open = true;
+    }
+    const int n = gp.base + (g < gp.rem ? 1 : 0);
+    ptr = W + (size_t)pp * 2 * K;
+    bytes = (uint32_t)n * 4u * (uint32_t)K;
+    pp += n;
+    ++g;
+    return true;
+  }
+};
 
 constexpr int HOWN = 32;       // floats per row of this CTA's own slice of the residual stream
 constexpr int ATT_SCR = 4096;  // floats of attention scratch
@@ -136,33 +223,40 @@ struct Phase {
   int K, pairs, epi;
 };
 
-__device__ __forceinline__ void pair_range(int pairs, int cta, int G, int& p0, int& p1) {
-  p0 = (int)(((long long)pairs * cta) / G);
-  p1 = (int)(((long long)pairs * (cta + 1)) / G);
-}
 
 }  // namespace
 
 
-// Per-thread view of the CTA's shared-memory layout and ring position (kept small: it lives in local memory across
-// the __noinline__ phase functions, which keep the kernel's code footprint inside the instruction cache).
-struct Ctx {
-  uint8_t* slots;
-  float *xs, *scr, *hown, *rope_s, *red;
-  int* page_s;
-  uint64_t *full, *empty;
-  unsigned slot_ctr, pair_ctr;
-  int nslots, tid, warp, lane, cta, G, p, own0;
+// CTA-wide context at the start of dynamic shared memory.  The phase functions are __noinline__ (the kernel's code
+// must stay inside the instruction cache) and read everything they need from here with LDS: with 227 KB of the SM
+// carved out as shared memory there is almost no L1 left, so a by-reference kernel-parameter struct or a local-
+// memory context would turn every field access into an L2 round trip.
+struct SmemCtx {
+  PersistArgs a;
+  int slot_cap, slots_off, xs_off, scr_off, hown_off, rope_off, red_off, part_off, page_off, bar_off;
+  int cta, G, p, own0;
 };
+constexpr int kCtxBytes = 1024;
+static_assert(sizeof(SmemCtx) <= kCtxBytes, "SmemCtx must fit its reserved shared-memory block");
+
+#define VAURA_SMEM_VIEW()                                                                     \
+  extern __shared__ __align__(128) uint8_t smem[];                                            \
+  const SmemCtx& sc = *reinterpret_cast<const SmemCtx*>(smem);                                \
+  const PersistArgs& a = sc.a;                                                                \
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;                              \
+  float* xs = reinterpret_cast<float*>(smem + sc.xs_off);                                     \
+  float* red = reinterpret_cast<float*>(smem + sc.red_off);                                   \
+  float* part_s = reinterpret_cast<float*>(smem + sc.part_off);                               \
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + sc.bar_off);                            \
+  uint64_t* empty = full + 2;                                                                 \
+  (void)a; (void)tid; (void)warp; (void)lane; (void)xs; (void)red; (void)part_s; (void)full; (void)empty;
 
 // xs[r] = (x * rsqrt(mean(x^2)+eps)) * w, permuted.  Source: global h (through L2) or, for layer 0, the embedding
 // rows sitting unpermuted in xs (read into registers before the permuted overwrite; syncs in between).
 template <int NB>
-__device__ __noinline__ void stage_norm(const Ctx& c, const float* src_smem, const float* src_global, const float* w, int K,
-                                        float eps) {
-  const int tid = c.tid, lane = c.lane, warp = c.warp;
-  float* xs = c.xs;
-  float* red = c.red;
+__device__ __noinline__ void stage_norm(const float* src_smem, const float* src_global, const float* w, int K) {
+  VAURA_SMEM_VIEW();
+  const float eps = a.eps;
   for (int r = 0; r < NB; ++r) {
     float ss = 0.f;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -189,81 +283,120 @@ __device__ __noinline__ void stage_norm(const Ctx& c, const float* src_smem, con
   consumer_sync();
 }
 
-// GEMV phase over this CTA's row pairs; weights come from the smem ring, activations from xs
+// fused epilogue of one finished row pair (rows nn, nn+1), executed by lane r for activation row r
 template <int NB>
-__device__ __noinline__ void gemv_phase(const PersistArgs& a, Ctx& c, int K, int pairs, int epi, int layer) {
-  const int warp = c.warp, lane = c.lane, p = c.p, D = a.D, F = a.F;
-  const int pair_bytes = 4 * K, pps = SLOT_BYTES / pair_bytes;
-  unsigned slot_ctr = c.slot_ctr, pair_ctr = c.pair_ctr;
-  const int nslots = c.nslots;
-  const float* xs = c.xs;
+__device__ __forceinline__ void pair_epilogue(int epi, int layer, int pairs, int pair, int r, float y0, float y1) {
+  VAURA_SMEM_VIEW();
+  const int D = a.D, nn = 2 * pair;
+  const float* rope_s = reinterpret_cast<const float*>(smem + sc.rope_off);
+  const int* page_s = reinterpret_cast<const int*>(smem + sc.page_off);
+  if (epi == EPI_STORE) {
+    *reinterpret_cast<float2*>(a.logits + (size_t)r * (2 * pairs) + nn) = make_float2(y0, y1);
+  } else if (epi == EPI_RESID) {  // this CTA owns h[nn], h[nn+1]: the running value lives in smem
+    float* ho = reinterpret_cast<float*>(smem + sc.hown_off) + r * HOWN + (nn - 2 * sc.own0);
+    const float v0 = ho[0] + y0, v1 = ho[1] + y1;
+    ho[0] = v0; ho[1] = v1;
+    *reinterpret_cast<float2*>(a.h + (size_t)r * D + nn) = make_float2(v0, v1);
+  } else if (epi == EPI_SWIGLU) {
+    a.act[(size_t)r * a.F + pair] = y0 / (1.f + expf(-y0)) * y1;
+  } else {  // EPI_QKV: RoPE (llama.py:633-650) + KV append
+    const int sec = nn / D, within = nn % D, hd = within / kHeadDim, e = within % kHeadDim;
+    float o0 = y0, o1 = y1;
+    if (sec != 2) {
+      const float cs = rope_s[e], sn = rope_s[e + 1];
+      o0 = y0 * cs - y1 * sn;
+      o1 = y1 * cs + y0 * sn;
+    }
+    if (sec == 0) {
+      *reinterpret_cast<float2*>(a.q + (size_t)r * D + within) = make_float2(o0, o1);
+    } else {
+      const size_t row = ((((size_t)(layer * 2 + (sec - 1)) * a.kv.num_pages + page_s[r]) * a.kv.nhead + hd) *
+                              a.kv.page_size + (sc.p % a.kv.page_size)) * kHeadDim;
+      *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.kv.pages) + row + e) = make_float2(o0, o1);
+    }
+  }
+}
+
+// GEMV phase over this CTA's row pairs; weights come from the double-buffered smem slots, activations from xs
+template <int NB>
+__device__ __noinline__ unsigned gemv_phase(int K, int pairs, int epi, int layer, unsigned grp_ctr) {
+  VAURA_SMEM_VIEW();
+  const int pair_bytes = 4 * K, K8 = K >> 3;
   int p0, p1;
-  pair_range(pairs, c.cta, c.G, p0, p1);
-  for (int pp = p0; pp < p1; pp += pps) {
-    const int n = min(pps, p1 - pp);
-    const int s = slot_ctr % nslots;
-    const uint32_t par = (slot_ctr / nslots) & 1;
-    mb_wait(&c.full[s], par);
-    const uint8_t* sb = c.slots + (size_t)s * SLOT_BYTES;
-    for (int j = 0; j < n; ++j) {
-      if ((int)((pair_ctr + j) % NW) != warp) continue;
-      const int pair = pp + j, nn = 2 * pair;
-      const uint4* w0 = reinterpret_cast<const uint4*>(sb + (size_t)j * pair_bytes);
-      float acc0[NB], acc1[NB];
-      pair_dot<NB>(w0, w0 + (K >> 3), xs, K, lane, acc0, acc1);
+  pair_range(pairs, sc.cta, sc.G, p0, p1);
+  const GroupPlan gp(K, p1 - p0, sc.slot_cap);
+  int pp = p0;
+  for (int g = 0; g < gp.ngroups; ++g) {
+    const int n = gp.base + (g < gp.rem ? 1 : 0);
+    const int slot = grp_ctr & 1;
+    const uint32_t par = (grp_ctr >> 1) & 1;
+    if (tid == 0) mb_wait(&full[slot], par);
+    consumer_sync();
+    const uint8_t* sb = smem + sc.slots_off + (size_t)slot * sc.slot_cap;
+    const int item = warp;
+    const bool active = item < n * gp.splits;
+    const int j = item / gp.splits, seg = item % gp.splits;
+    float acc0[NB], acc1[NB];
+    if (active) {
+      const uint32_t w0 = s_u32(sb) + (uint32_t)(j * pair_bytes);
+      const int c0 = (K8 * seg) / gp.splits, c1 = (K8 * (seg + 1)) / gp.splits;
+      pair_dot<NB>(w0, w0 + 2 * K, s_u32(xs), K, c0, c1, lane, acc0, acc1);
+      if (gp.splits == 1) {
 #pragma unroll
-      for (int r = 0; r < NB; ++r) {
-        if (lane != r) continue;
-        const float y0 = acc0[r], y1 = acc1[r];
-        if (epi == EPI_STORE) {
-          *reinterpret_cast<float2*>(a.logits + (size_t)r * (2 * pairs) + nn) = make_float2(y0, y1);
-        } else if (epi == EPI_RESID) {  // this CTA owns h[nn], h[nn+1]: running value lives in smem
-          float* ho = c.hown + r * HOWN + (nn - 2 * c.own0);
-          const float v0 = ho[0] + y0, v1 = ho[1] + y1;
-          ho[0] = v0; ho[1] = v1;
-          *reinterpret_cast<float2*>(a.h + (size_t)r * D + nn) = make_float2(v0, v1);
-        } else if (epi == EPI_SWIGLU) {
-          a.act[(size_t)r * F + pair] = y0 / (1.f + expf(-y0)) * y1;
-        } else {  // EPI_QKV: RoPE (llama.py:633-650) + KV append
-          const int sec = nn / D, within = nn % D, hd = within / kHeadDim, e = within % kHeadDim;
-          float o0 = y0, o1 = y1;
-          if (sec != 2) {
-            const float cs = c.rope_s[e], sn = c.rope_s[e + 1];
-            o0 = y0 * cs - y1 * sn;
-            o1 = y1 * cs + y0 * sn;
+        for (int r = 0; r < NB; ++r)
+          if (lane == r) pair_epilogue<NB>(epi, layer, pairs, pp + j, r, acc0[r], acc1[r]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < NB; ++r)
+          if (lane == r) {
+            part_s[(item * NB + r) * 2] = acc0[r];
+            part_s[(item * NB + r) * 2 + 1] = acc1[r];
           }
-          if (sec == 0) {
-            *reinterpret_cast<float2*>(a.q + (size_t)r * D + within) = make_float2(o0, o1);
-          } else {
-            const size_t row = ((((size_t)(layer * 2 + (sec - 1)) * a.kv.num_pages + c.page_s[r]) * a.kv.nhead + hd) *
-                                    a.kv.page_size + (p % a.kv.page_size)) * kHeadDim;
-            *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.kv.pages) + row + e) = make_float2(o0, o1);
-          }
-        }
       }
     }
-    pair_ctr += n;
-    __syncwarp();
-    if (lane == 0) mb_arrive(&c.empty[s]);
-    ++slot_ctr;
+    if (gp.splits > 1) {
+      consumer_sync();
+      if (active && seg == 0 && lane < NB) {
+        float y0 = 0.f, y1 = 0.f;
+        for (int sgm = 0; sgm < gp.splits; ++sgm) {
+          y0 += part_s[((item + sgm) * NB + lane) * 2];
+          y1 += part_s[((item + sgm) * NB + lane) * 2 + 1];
+        }
+        pair_epilogue<NB>(epi, layer, pairs, pp + j, lane, y0, y1);
+      }
+    }
+    consumer_sync();  // every warp is done reading the slot (and part_s)
+    if (tid == 0) mb_arrive(&empty[slot]);
+    pp += n;
+    ++grp_ctr;
   }
-  c.slot_ctr = slot_ctr;
-  c.pair_ctr = pair_ctr;
+  return grp_ctr;
 }
 
 template <int NB>
 __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const PersistArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int Kmax = a.D > a.F ? a.D : a.F;
-  uint8_t* slots = smem;
-  float* xs = reinterpret_cast<float*>(smem + (size_t)a.nslots * SLOT_BYTES);  // [NB][Kmax] permuted activations
-  float* scr = xs + (size_t)NB * Kmax;                                          // attention scratch
-  float* hown = scr + ATT_SCR;                                                  // [NB][HOWN] own slice of h
-  float* rope_s = hown + NB * HOWN;                                             // [96] cos,sin of position p
-  float* red = rope_s + kHeadDim;                                               // [64]
-  int* page_s = reinterpret_cast<int*>(red + 64);                               // [8] KV page of position p per row
-  uint64_t* full = reinterpret_cast<uint64_t*>(page_s + 8);
-  uint64_t* empty = full + a.nslots;
+  // layout: [SmemCtx 1 KB][2 weight slots][xs][(attention scratch)][hown][rope][red][split-K partials][pages][mbarriers]
+  const bool scr_alias = (size_t)NB * Kmax >= ATT_SCR;  // scratch aliases xs (dead between the QKV phase and the combine)
+  const int slots_off = kCtxBytes;
+  const int xs_off = slots_off + 2 * a.slot_cap;
+  const int scr_off = scr_alias ? xs_off : xs_off + NB * Kmax * 4;
+  const int hown_off = xs_off + NB * Kmax * 4 + (scr_alias ? 0 : ATT_SCR * 4);
+  const int rope_off = hown_off + NB * HOWN * 4;
+  const int red_off = rope_off + kHeadDim * 4;
+  const int part_off = red_off + 64 * 4;
+  const int page_off = part_off + 128 * 4;
+  const int bar_off = page_off + 8 * 4;
+  uint8_t* slots = smem + slots_off;
+  float* xs = reinterpret_cast<float*>(smem + xs_off);
+  float* scr = reinterpret_cast<float*>(smem + scr_off);
+  float* hown = reinterpret_cast<float*>(smem + hown_off);
+  float* rope_s = reinterpret_cast<float*>(smem + rope_off);
+  float* part_s = reinterpret_cast<float*>(smem + part_off);
+  int* page_s = reinterpret_cast<int*>(smem + page_off);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + bar_off);
+  uint64_t* empty = full + 2;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, G = gridDim.x;
@@ -275,11 +408,19 @@ __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const Per
   unsigned bar_i = 0;
 
   if (tid == 0) {
-    for (int s = 0; s < a.nslots; ++s) {
+    for (int s = 0; s < 2; ++s) {
       mb_init(&full[s], 1);
-      mb_init(&empty[s], NW);
+      mb_init(&empty[s], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    SmemCtx& w = *reinterpret_cast<SmemCtx*>(smem);
+    w.a = a;
+    w.slot_cap = a.slot_cap; w.slots_off = slots_off; w.xs_off = xs_off; w.scr_off = scr_off; w.hown_off = hown_off;
+    w.rope_off = rope_off; w.red_off = red_off; w.part_off = part_off; w.page_off = page_off; w.bar_off = bar_off;
+    w.cta = cta; w.G = G; w.p = p;
+    int o0_, o1_;
+    pair_range(a.D / 2, cta, G, o0_, o1_);
+    w.own0 = o0_;
   }
   __syncthreads();
 
@@ -288,29 +429,25 @@ __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const Per
   // ============================== producer warp ==============================
   if (warp == NW) {
     if (lane == 0) {
-      unsigned slot_ctr = 0;
-      for (int l = 0; l <= a.L; ++l) {
-        const int nph = l < a.L ? 4 : 1;
-        for (int ph = 0; ph < nph; ++ph) {
-          Phase P;
-          if (l == a.L) P = {a.w_heads, D, head_pairs, EPI_STORE};
-          else if (ph == 0) P = {a.wqkv + (size_t)l * 3 * D * D, D, qkv_pairs, EPI_QKV};
-          else if (ph == 1) P = {a.wo + (size_t)l * D * D, D, d_pairs, EPI_RESID};
-          else if (ph == 2) P = {a.w13 + (size_t)l * 2 * F * D, D, f_pairs, EPI_SWIGLU};
-          else P = {a.w2 + (size_t)l * D * F, F, d_pairs, EPI_RESID};
-          const int pair_bytes = 4 * P.K, pps = SLOT_BYTES / pair_bytes;
-          int p0, p1;
-          pair_range(P.pairs, cta, G, p0, p1);
-          for (int pp = p0; pp < p1; pp += pps) {
-            const int n = min(pps, p1 - pp);
-            const int s = slot_ctr % a.nslots;
-            const uint32_t par = (slot_ctr / a.nslots) & 1;
-            mb_wait(&empty[s], par ^ 1);
-            mb_expect_tx(&full[s], (uint32_t)(n * pair_bytes));
-            bulk_g2s(slots + (size_t)s * SLOT_BYTES, P.W + (size_t)pp * 2 * P.K, (uint32_t)(n * pair_bytes), &full[s]);
-            ++slot_ctr;
-          }
-        }
+      // Two cursors walk the same schedule of (pointer, bytes) groups: `pf` runs kPrefetchAhead groups ahead and only
+      // warms L2 (cp.async.bulk.prefetch.L2), so HBM keeps streaming while both smem slots are full (grid barriers,
+      // attention, staging); `ld` fills the smem slots, mostly from L2.
+      const PersistArgs& as = reinterpret_cast<const SmemCtx*>(smem)->a;  // shared-memory copy (LDS, not local memory)
+      WeightSched ld(as, cta, G), pf(as, cta, G);
+      const uint16_t* ptr;
+      uint32_t bytes;
+      for (int i = 0; i < as.prefetch_ahead && pf.next(ptr, bytes); ++i) bulk_prefetch_l2(ptr, bytes);
+      unsigned grp_ctr = 0;
+      while (ld.next(ptr, bytes)) {
+        const int slot = grp_ctr & 1;
+        const uint32_t par = (grp_ctr >> 1) & 1;
+        const uint16_t* pptr;
+        uint32_t pbytes;
+        if (as.prefetch_ahead > 0 && pf.next(pptr, pbytes)) bulk_prefetch_l2(pptr, pbytes);
+        mb_wait(&empty[slot], par ^ 1);
+        mb_expect_tx(&full[slot], bytes);
+        bulk_g2s(slots + (size_t)slot * as.slot_cap, ptr, bytes, &full[slot]);
+        ++grp_ctr;
       }
     }
     return;
@@ -332,10 +469,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const Per
   if (tid < kHeadDim) rope_s[tid] = a.rope[(size_t)p * kHeadDim + tid];
   if (tid < NB) page_s[tid] = a.kv.page_table[tid * a.kv.max_pages_per_seq + p / a.kv.page_size];
 
-  Ctx c;
-  c.slots = slots; c.xs = xs; c.scr = scr; c.hown = hown; c.rope_s = rope_s; c.red = red; c.page_s = page_s;
-  c.full = full; c.empty = empty; c.slot_ctr = 0; c.pair_ctr = 0; c.nslots = a.nslots; c.tid = tid; c.warp = warp;
-  c.lane = lane; c.cta = cta; c.G = G; c.p = p; c.own0 = own0;
+  unsigned grp_ctr = 0;
 
   // ---- embedding (llama.py:455-472): every CTA builds the full rows in smem; owners keep/publish their slice ----
   {
@@ -368,10 +502,10 @@ __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const Per
   const int npages = p / a.kv.page_size + 1;
   for (int l = 0; l < a.L; ++l) {
     // ---------------- P1: attention_norm + wqkv + RoPE + KV append ----------------
-    if (l == 0) stage_norm<NB>(c, xs, nullptr, a.attn_norm, D, a.eps);
-    else stage_norm<NB>(c, nullptr, a.h, a.attn_norm + (size_t)l * D, D, a.eps);
+    if (l == 0) stage_norm<NB>(xs, nullptr, a.attn_norm, D);
+    else stage_norm<NB>(nullptr, a.h, a.attn_norm + (size_t)l * D, D);
     stamp();
-    gemv_phase<NB>(a, c, D, qkv_pairs, EPI_QKV, l);
+    grp_ctr = gemv_phase<NB>(D, qkv_pairs, EPI_QKV, l, grp_ctr);
     stamp();
     grid_barrier(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
     stamp();
@@ -448,38 +582,47 @@ __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const Per
 
     // ---------------- P3: combine partials -> xs, wo + residual ----------------
     for (int r = 0; r < NB; ++r) {
+      // per (head, page) weight exp(m - M) / sum_g exp(m_g - M) l_g, 8 lanes per head
+      float* wgt = part_s;  // [H*8] (H <= 16)
+      if (tid < a.H * (kMaxCtx / 32)) {
+        const int hh = tid >> 3, g = tid & 7;
+        const float* part = a.attn_part + (size_t)((r * a.H + hh) * (kMaxCtx / 32) + g) * ATT_STRIDE;
+        const float m = g < npages ? __ldcg(part) : -INFINITY;
+        const float lg = g < npages ? __ldcg(part + 1) : 0.f;
+        float M = m;
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 4));
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 2));
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 1));
+        const float e = g < npages ? expf(m - M) : 0.f;
+        float den = e * lg;
+        den += __shfl_xor_sync(0xffffffffu, den, 4);
+        den += __shfl_xor_sync(0xffffffffu, den, 2);
+        den += __shfl_xor_sync(0xffffffffu, den, 1);
+        wgt[tid] = e / den;
+      }
+      consumer_sync();
       for (int i = tid; i < D; i += kConsumers) {
         const int hh = i / kHeadDim, dd = i % kHeadDim;
-        const float* part = a.attn_part + (size_t)((r * a.H + hh) * (kMaxCtx / 32)) * ATT_STRIDE;
-        float mg[kMaxCtx / 32], M = -INFINITY;
+        const float* part = a.attn_part + (size_t)((r * a.H + hh) * (kMaxCtx / 32)) * ATT_STRIDE + 4 + dd;
+        float o = 0.f;
 #pragma unroll
-        for (int g = 0; g < kMaxCtx / 32; ++g) {
-          mg[g] = g < npages ? __ldcg(part + g * ATT_STRIDE) : -INFINITY;
-          M = fmaxf(M, mg[g]);
-        }
-        float num = 0.f, den = 0.f;
-#pragma unroll
-        for (int g = 0; g < kMaxCtx / 32; ++g) {
-          if (g < npages) {
-            const float wgt = expf(mg[g] - M);
-            num = fmaf(wgt, __ldcg(part + g * ATT_STRIDE + 4 + dd), num);
-            den = fmaf(wgt, __ldcg(part + g * ATT_STRIDE + 1), den);
-          }
-        }
-        xs[(size_t)r * D + perm_idx(i, D)] = num / den;
+        for (int g = 0; g < kMaxCtx / 32; ++g)
+          if (g < npages) o = fmaf(wgt[hh * 8 + g], __ldcg(part + g * ATT_STRIDE), o);
+        xs[(size_t)r * D + perm_idx(i, D)] = o;
       }
+      consumer_sync();
     }
     consumer_sync();
     stamp();
-    gemv_phase<NB>(a, c, D, d_pairs, EPI_RESID, l);
+    grp_ctr = gemv_phase<NB>(D, d_pairs, EPI_RESID, l, grp_ctr);
     stamp();
     grid_barrier(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
     stamp();
 
     // ---------------- P4: ffn_norm + w1|w3 + SiLU*mul ----------------
-    stage_norm<NB>(c, nullptr, a.h, a.ffn_norm + (size_t)l * D, D, a.eps);
+    stage_norm<NB>(nullptr, a.h, a.ffn_norm + (size_t)l * D, D);
     stamp();
-    gemv_phase<NB>(a, c, D, f_pairs, EPI_SWIGLU, l);
+    grp_ctr = gemv_phase<NB>(D, f_pairs, EPI_SWIGLU, l, grp_ctr);
     stamp();
     grid_barrier(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
     stamp();
@@ -492,16 +635,16 @@ __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const Per
       }
     consumer_sync();
     stamp();
-    gemv_phase<NB>(a, c, F, d_pairs, EPI_RESID, l);
+    grp_ctr = gemv_phase<NB>(F, d_pairs, EPI_RESID, l, grp_ctr);
     stamp();
     grid_barrier(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
     stamp();
   }
 
   // ---------------- final norm + heads ----------------
-  stage_norm<NB>(c, nullptr, a.h, a.final_norm, D, a.eps);
+  stage_norm<NB>(nullptr, a.h, a.final_norm, D);
   stamp();
-  gemv_phase<NB>(a, c, D, head_pairs, EPI_STORE, 0);
+  grp_ctr = gemv_phase<NB>(D, head_pairs, EPI_STORE, 0, grp_ctr);
   stamp();
   grid_barrier(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
   stamp();
@@ -509,7 +652,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const Per
   // ---------------- CFG / sampling / mask-fix / write-back: one warp per (clip, codebook) ----------------
   {
     const int nrows = a.sample.B * a.sample.K;
-    for (int u = cta + G * warp; u < nrows; u += G * NW) sample_row(a.sample, u / a.sample.K, u % a.sample.K, lane, offset);
+    const SampleArgs& sa = reinterpret_cast<const SmemCtx*>(smem)->a.sample;
+    for (int u = cta + G * warp; u < nrows; u += G * NW) sample_row(sa, u / sa.K, u % sa.K, lane, offset);
   }
   stamp();
   if (cta == 0 && tid == 0) {  // every CTA read offset/epoch before its first barrier arrival
@@ -521,19 +665,24 @@ __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const Per
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static size_t persist_smem(int NB, int D, int F, int& nslots) {
+static size_t persist_smem(int NB, int D, int F, int& slot_cap) {
   const int Kmax = D > F ? D : F;
-  const size_t fixed = (size_t)NB * Kmax * 4 + ATT_SCR * 4 + NB * HOWN * 4 + kHeadDim * 4 + 64 * 4 + 8 * 4 + 2 * 16 * 8 + 128;
+  const bool alias = (size_t)NB * Kmax >= (size_t)ATT_SCR;
+  const size_t fixed = kCtxBytes + (size_t)NB * Kmax * 4 + (alias ? 0 : ATT_SCR * 4) + NB * HOWN * 4 + kHeadDim * 4 + 64 * 4 +
+                       128 * 4 + 8 * 4 + 4 * 8 + 256;
   const size_t budget = 227 * 1024;
-  nslots = (int)((budget - fixed) / SLOT_BYTES);
-  if (nslots > 16) nslots = 16;
-  return fixed + (size_t)nslots * SLOT_BYTES;
+  size_t cap = (budget - fixed) / 2;
+  const size_t want = (size_t)NW * 4 * 1536;  // 15 row pairs of K=1536
+  if (cap > want) cap = want;
+  cap &= ~(size_t)1023;
+  slot_cap = (int)cap;
+  return fixed + 2 * cap;
 }
 
 bool persistent_supported(int rows, int D, int F, int page_size) {
   if (rows != 1 && rows != 2 && rows != 4) return false;
   if (page_size != 32) return false;
-  if (D % 16 || F % 16 || 4 * D > SLOT_BYTES || 4 * F > SLOT_BYTES) return false;
+  if (D % 16 || F % 16 || D > 4096 || F > 1536 * kMaxSplit) return false;
   if (D / 4 > kConsumers) return false;  // stage_norm covers a row with one float4 per thread
   if (2 * ((D / 2 + 131) / 132) > HOWN) return false;  // own slice of h per CTA (>= 132 SMs assumed)
   return true;
@@ -543,15 +692,14 @@ size_t persistent_attn_part_bytes(int rows, int H) { return (size_t)rows * H * (
 
 template <int NB>
 static cudaError_t launch_persist_t(PersistArgs& a, cudaStream_t st) {
-  int nslots = 0;
-  const size_t smem = persist_smem(NB, a.D, a.F, nslots);
-  if (nslots < 3) return cudaErrorInvalidValue;
-  a.nslots = nslots;
+  int slot_cap = 0;
+  const size_t smem = persist_smem(NB, a.D, a.F, slot_cap);
+  if (slot_cap < 4 * a.D || slot_cap < 4 * a.F) return cudaErrorInvalidValue;  // a slot must hold one row pair
+  a.slot_cap = slot_cap;
   {
-    const char* e = getenv("VAURA_PERSIST_INFLIGHT");
-    a.max_inflight = e ? atoi(e) : 4;
-    if (a.max_inflight < 1) a.max_inflight = 1;
-    if (a.max_inflight > nslots) a.max_inflight = nslots;
+    const char* e = getenv("VAURA_PERSIST_PREFETCH");
+    a.prefetch_ahead = e ? atoi(e) : 0;  // groups of L2 prefetch ahead of the smem fill (measured: no gain, off)
+    if (a.prefetch_ahead < 0) a.prefetch_ahead = 0;
   }
   static int grid = 0;
   if (!grid) {

@@ -115,7 +115,7 @@ struct PersistArgs {
   StepState* state;
   unsigned long long* timing;  // optional: phase timestamps (ns) of CTA 0
   SampleArgs sample;
-  int L, D, F, H, Kc, V, S, batch, cond_dim, cond_tokens, atpvf, nslots, max_inflight;
+  int L, D, F, H, Kc, V, S, batch, cond_dim, cond_tokens, atpvf, slot_cap, prefetch_ahead;
   float eps, scale;
 };
 
