@@ -227,41 +227,58 @@ def main():
     value = audio_per_step * args.steps / (ms / 1000.0)
     e2e = audio_per_step * args.steps / (ms_e2e / 1000.0)
 
-    # ---- roofline of the dominant kernel: the weight-streaming GEMV over w1|w3 (25.2 MB per launch) ------
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------
     peak, peak_src = load_peaks()
     rows = B * (2 if wl["cfg_scale"] > 1.0 else 1)
     d = FULL_SAMPLER
-    w13 = model.sampler.weights["w13"]
-    x = torch.randn(rows, d.d_model, device=dev)
-    y = torch.empty(rows, 2 * d.ffn_dim, device=dev)
     st = torch.cuda.current_stream().cuda_stream
-
-    def gemv_pass():
-        for l in range(d.num_layers):  # 24 different matrices = 604 MB > L2, nothing is re-read from cache
-            _cabi.check(lib.vaura_gemv_bf16w(w13[l].data_ptr(), x.data_ptr(), y.data_ptr(), 2 * d.ffn_dim, d.d_model,
-                                             rows, st), "vaura_gemv_bf16w")
-
-    for _ in range(3):
-        gemv_pass()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        gemv_pass()
-    e1.record()
-    torch.cuda.synchronize()
-    k_ms = e0.elapsed_time(e1) / (5 * d.num_layers)
-    alg_bytes = 2 * d.ffn_dim * d.d_model * 2 + rows * d.d_model * 4 + rows * 2 * d.ffn_dim * 4
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    step_bytes = sampler_step_bytes(d)
+    if rows <= 4:
+        # rows <= 4: the whole decode step is ONE persistent kernel (decode_step_persistent); timed through the
+        # token-only generate (CUDA events around 227 back-to-back launches of that kernel + 1 first pass)
+        def tokens_only_r():
+            model.generate(frames=feats_dev, clip_indices=clip_ids, _decode_audio=False, **kw)
+        tokens_only_r()
+        k_ms = timed(tokens_only_r, 3) / 3 / (T + 8)
+        kv_bytes = 24 * 2 * d.d_model * 4 * rows * (T + 8) / 2  # fp32 KV read, mean context (S/2 positions)
+        alg_bytes = step_bytes + kv_bytes
+        kname = f"decode_step_persistent<{rows}> (whole decode step: 24 layers + heads + sampling)"
+        key = f"decode_step_persistent_rows{rows}"
+    else:
+        # rows >= 16: tcgen05 linear over w1|w3 (25.2 MB of weights per launch), 24 different matrices back to back
+        w13 = model.sampler.weights["w13"]
+        x = torch.randn(rows, d.d_model, device=dev).to(torch.bfloat16)
+        y = torch.empty(rows, 2 * d.ffn_dim, device=dev)
+        bn = 64 if rows <= 128 else 128
+
+        def gemm_pass():
+            for l in range(d.num_layers):  # 604 MB of distinct weights > L2: nothing is re-read from cache
+                _cabi.check(lib.vaura_linear_bf16(x.data_ptr(), w13[l].data_ptr(), y.data_ptr(), rows, 2 * d.ffn_dim,
+                                                  d.d_model, bn, st), "vaura_linear_bf16")
+
+        for _ in range(3):
+            gemm_pass()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            gemm_pass()
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / (5 * d.num_layers)
+        alg_bytes = 2 * d.ffn_dim * d.d_model * 2 + rows * d.d_model * 2 + rows * 2 * d.ffn_dim * 4
+        kname = f"gemm_tc_kernel<{bn},64,...,EpiLinear> w1|w3 [8192x1536] bf16 x {rows} rows (tcgen05)"
+        key = f"gemm_tc_w13_rows{rows}"
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     if os.path.exists(prof):
-        traffic = json.load(open(prof)).get(f"gemv_w13_rows{rows}")
+        traffic = json.load(open(prof)).get(key)
 
     line = {
         "metric": "generated audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16 weights, fp32 activations/accumulate (codec fp16/fp32 accumulate)",
+        "vs_baseline": None, "dtype": ("bf16 weights, fp32 activations/accumulate" if rows < 16 else "bf16 weights+activations, fp32 accumulate (tcgen05)") + "; codec fp16, fp32 accumulate",
         "data": "synthetic",
         "config": {"workload": wl["name"], "per_gpu_batch": B, "tokens_per_clip": T, "decode_steps": T + 8,
                    "l2": "weights 1.39 GB per decode step >> 126 MB L2; no flush needed", "cfg_scale": wl["cfg_scale"],
@@ -269,7 +286,7 @@ def main():
         "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": feats_host.numel() * 4,
                 "d2h_bytes_per_step": wav_host.numel() * 2, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": f"gemv_kernel<SWIGLU-shaped> w1|w3 [8192x1536] bf16, {rows} rows", "bound": "hbm",
+        "roofline": {"kernel": kname, "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "us_per_launch": k_ms * 1e3, "algorithmic_bytes_per_launch": alg_bytes},
         "decode_step": {"p50_us": None, "weight_bytes": sampler_step_bytes(d)},

@@ -58,6 +58,12 @@ unsigned long long vaura_launch_count(void);
  * (What nn.Linear does at llama.py:228/:259/:176-177/:504 for one position.)  N even, K % 8 == 0. */
 int vaura_gemv_bf16w(const uint16_t* W, const float* x, float* y, int32_t N, int32_t K, int32_t R, void* stream);
 
+/* tcgen05 linear layer, the dominant kernel of the bf16 (rows >= 16 / prefill) path, as a stand-alone op:
+ * y[r][n] = sum_k A[r][k] * W[n][k]; A bf16 [R][K], W bf16 [N][K], y f32 [R][N]; fp32 accumulate in TMEM.
+ * K % 64 == 0, N % block_n == 0, block_n in {16, 32, 64, 128}. */
+int vaura_linear_bf16(const uint16_t* A, const uint16_t* W, float* y, int32_t R, int32_t N, int32_t K, int32_t block_n,
+                      void* stream);
+
 /* ---- AR transformer ("sampler"), replaces models/modules/sampler/llama.py:286-586 -------------- */
 typedef struct {
   int32_t num_layers;    /* 24 */

@@ -228,3 +228,26 @@ def test_bf16_path_with_cfg_and_prompt_prefill(tiny_model, tiny_oracle):
     ref = lg[B:] + (lg[:B] - lg[B:]) * 2.5
     mine = out["_logits"][Tp + 1:].cpu().permute(1, 2, 0, 3)
     assert rel_err(mine, ref[:, :, Tp:]) < 2 * BF16_LOGIT_TOL  # CFG amplifies the error by ~cfg_scale
+
+
+def test_standalone_ops_match_torch_fp32():
+    """Op-level entry points of the C ABI (the kernels bench.py times for the roofline)."""
+    import ctypes as C
+
+    lib = _cabi.load()
+    g = torch.Generator().manual_seed(1)
+    st = torch.cuda.current_stream().cuda_stream
+    for R, N, K in ((1, 4608, 1536), (4, 1536, 4096), (7, 64, 384)):
+        W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
+        x = torch.randn(R, K, generator=g).cuda()
+        y = torch.empty(R, N, device="cuda")
+        _cabi.check(lib.vaura_gemv_bf16w(W.data_ptr(), x.data_ptr(), y.data_ptr(), N, K, R, st), "gemv")
+        ref = x.double() @ W.double().t()
+        assert float((y.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+    for R, N, K, bn in ((64, 8192, 1536, 64), (200, 1536, 4096, 128), (16, 1152, 384, 32)):
+        W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
+        A = torch.randn(R, K, generator=g).to(torch.bfloat16).cuda()
+        y = torch.empty(R, N, device="cuda")
+        _cabi.check(lib.vaura_linear_bf16(A.data_ptr(), W.data_ptr(), y.data_ptr(), R, N, K, bn, st), "linear")
+        ref = A.double() @ W.double().t()  # bf16 operands, fp32 accumulate: only summation-order error remains
+        assert float((y.double() - ref).abs().max() / ref.abs().max()) < 1e-5

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_lib", "libvaura_b200.so")
 
 EXPORTS = [
-    "vaura_version", "vaura_arch", "vaura_last_error", "vaura_launch_count", "vaura_gemv_bf16w",
+    "vaura_version", "vaura_arch", "vaura_last_error", "vaura_launch_count", "vaura_gemv_bf16w", "vaura_linear_bf16",
     "vaura_sampler_create", "vaura_sampler_destroy", "vaura_sampler_cond_project",
     "vaura_sampler_workspace_bytes", "vaura_sampler_generate", "vaura_sampler_forward", "vaura_sample_logits",
     "vaura_codec_create", "vaura_codec_destroy", "vaura_codec_workspace_bytes", "vaura_codec_decode",
@@ -71,6 +71,8 @@ def load():
     lib.vaura_last_error.restype = C.c_char_p
     lib.vaura_launch_count.restype = C.c_ulonglong
     lib.vaura_gemv_bf16w.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.vaura_linear_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_void_p]
     lib.vaura_sampler_create.argtypes = [C.POINTER(SamplerDimsC), C.POINTER(SamplerWeightsC), C.POINTER(C.c_void_p)]
     lib.vaura_sampler_destroy.argtypes = [C.c_void_p]
     lib.vaura_sampler_destroy.restype = None

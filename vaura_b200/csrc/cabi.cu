@@ -48,6 +48,17 @@ extern "C" const char* vaura_arch(void) { return "sm_100a"; }
 extern "C" const char* vaura_last_error(void) { return g_err; }
 extern "C" unsigned long long vaura_launch_count(void) { return g_launches; }
 
+extern "C" int vaura_linear_bf16(const uint16_t* A, const uint16_t* W, float* y, int32_t R, int32_t N, int32_t K,
+                                 int32_t block_n, void* stream) {
+  if (!A || !W || !y || R <= 0 || N <= 0 || K <= 0 || (K % 64) || block_n <= 0 || (N % block_n))
+    return fail(VAURA_ERR_INVALID, "bad argument");
+  LinearTcArgs g{};
+  g.A = A; g.lda = K; g.W = W; g.N = N; g.K = K; g.R = R; g.epi = EPI_STORE; g.out_f32 = y; g.ldo = N; g.block_n = block_n;
+  g.npos = 1;
+  CUL(launch_linear_tc(g, (cudaStream_t)stream));
+  return VAURA_OK;
+}
+
 extern "C" int vaura_gemv_bf16w(const uint16_t* W, const float* x, float* y, int32_t N, int32_t K, int32_t R, void* stream) {
   if (!W || !x || !y || N <= 0 || K <= 0 || R <= 0 || (N & 1) || (K & 7)) return fail(VAURA_ERR_INVALID, "bad argument");
   CU(init_decode_kernels());

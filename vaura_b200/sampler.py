@@ -157,11 +157,19 @@ class Transformer(torch.nn.Module):
         rows, tv, cin = memory.shape
         if cin != self.dims.cond_in:
             raise ValueError(f"conditioning width {cin} != {self.dims.cond_in}")
+        if tv > self.dims.cond_tokens:
+            raise ValueError(f"{tv} visual tokens > {self.dims.cond_tokens}: the conditioning table is built for at most "
+                             f"{self.dims.cond_tokens} rows plus the empty_video_emb row")
         out = torch.empty(rows, tv + 1, self.dims.cond_dim, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream().cuda_stream
             _cabi.check(lib.vaura_sampler_cond_project(self.handle(), memory.data_ptr(), rows, tv, out.data_ptr(), st),
                         "vaura_sampler_cond_project")
+        if tv < self.dims.cond_tokens:
+            # fewer visual tokens than table rows (short last window): positions whose frame index is >= Tv read
+            # empty_video_emb (llama.py:569-572), so rows [Tv, cond_tokens] all hold that vector
+            pad = out[:, tv:].expand(rows, self.dims.cond_tokens + 1 - tv, self.dims.cond_dim)
+            out = torch.cat([out[:, :tv], pad], dim=1).contiguous()
         return out
 
     def forward(self, tgt: torch.Tensor, memory: torch.Tensor, use_conditioning: bool = True, tgt_mask=None,
@@ -176,8 +184,6 @@ class Transformer(torch.nn.Module):
         B, K, S = tgt.shape
         if self.audio_tokens_per_video_frame is None:
             self._set_audio_tokens_per_video_frame(S, memory.shape[1])
-        if memory.shape[1] != self.dims.cond_tokens:
-            raise ValueError(f"expected {self.dims.cond_tokens} visual tokens, got {memory.shape[1]}")
         rows = self.cond_rows(memory)
         seq = tgt.to(device=self.device, dtype=torch.int32).contiguous()
         logits = torch.empty(B, K, S, self.dims.d_codebook, dtype=torch.float32, device=self.device)
