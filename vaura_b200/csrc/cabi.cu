@@ -54,7 +54,7 @@ extern "C" int vaura_linear_bf16(const uint16_t* A, const uint16_t* W, float* y,
     return fail(VAURA_ERR_INVALID, "bad argument");
   LinearTcArgs g{};
   g.A = A; g.lda = K; g.W = W; g.N = N; g.K = K; g.R = R; g.epi = EPI_STORE; g.out_f32 = y; g.ldo = N; g.block_n = block_n;
-  g.npos = 1;
+  g.npos = 1; g.ksplit = 1; g.pdl = 0;
   CUL(launch_linear_tc(g, (cudaStream_t)stream));
   return VAURA_OK;
 }
@@ -238,37 +238,50 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
   const size_t D = d.d_model, F = d.ffn_dim;
   // narrow N tiles when there is a single M tile so the weight stream is spread over all SMs
   const bool small = R <= 128;
+  const char* nopdl = getenv("VAURA_NO_PDL");
+  // Programmatic dependent launch is OFF by default: measured on B200 it gave no step-time gain, and an explicit
+  // griddepcontrol.launch_dependents inside the GEMM made dependents observe stale activations.
+  // VAURA_PDL_MODE bits: 1 attribute+wait, 2 GEMM trigger after its wait, 4 weight prefetch before the wait,
+  // 8 trigger in the small kernels.
+  int pdl = 0;
+  (void)nopdl;
+  { const char* m = getenv("VAURA_PDL_MODE"); if (m) pdl = atoi(m); }
+  const char* nosplit = getenv("VAURA_NO_SPLITK");
+  const bool splitk = small && !(nosplit && nosplit[0] == '1');
   for (int l = 0; l < d.num_layers; ++l) {
     LinearTcArgs g{};
     g.state = state; g.pos0 = pos0; g.npos = npos; g.R = R; g.layer = l; g.d_model = d.d_model; g.kv = kv; g.rope = w.rope;
-    CUL(launch_rmsnorm_bf16(ws.h, w.attn_norm + l * D, ws.xn_b, R, D, D, d.norm_eps, st));
+    g.pdl = pdl;
+    CUL(launch_rmsnorm_bf16(ws.h, w.attn_norm + l * D, ws.xn_b, R, D, D, d.norm_eps, pdl, st));
     g.A = ws.xn_b; g.lda = D; g.W = w.wqkv + (size_t)l * 3 * D * D; g.N = 3 * D; g.K = D; g.epi = EPI_QKV;
     g.out_bf16 = ws.q_b; g.block_n = small ? 32 : 128;
     CUL(launch_linear_tc(g, st));
     AttnBf16Args a{};
     a.q = ws.q_b; a.out = ws.attn_b; a.kv = kv; a.state = state; a.pos0 = pos0; a.npos = npos; a.layer = l;
-    a.d_model = d.d_model; a.scale = 1.0f / sqrtf((float)kHeadDim);
+    a.d_model = d.d_model; a.scale = 1.0f / sqrtf((float)kHeadDim); a.pdl = pdl;
     CUL(launch_attn_bf16(a, d.nhead, R, st));
     g.A = ws.attn_b; g.lda = D; g.W = w.wo + (size_t)l * D * D; g.N = D; g.K = D; g.epi = EPI_RESID; g.out_f32 = ws.h;
-    g.ldo = D; g.block_n = small ? 16 : 128;
+    g.ldo = D; g.block_n = splitk ? 64 : (small ? 16 : 128); g.ksplit = splitk ? 6 : 1;
     CUL(launch_linear_tc(g, st));
-    CUL(launch_rmsnorm_bf16(ws.h, w.ffn_norm + l * D, ws.xn_b, R, D, D, d.norm_eps, st));
+    g.ksplit = 1;
+    CUL(launch_rmsnorm_bf16(ws.h, w.ffn_norm + l * D, ws.xn_b, R, D, D, d.norm_eps, pdl, st));
     g.A = ws.xn_b; g.lda = D; g.W = w.w13 + (size_t)l * 2 * F * D; g.N = 2 * F; g.K = D; g.epi = EPI_SWIGLU;
     g.out_bf16 = ws.act_b; g.ldo = F; g.block_n = small ? 64 : 128;
     CUL(launch_linear_tc(g, st));
     g.A = ws.act_b; g.lda = F; g.W = w.w2 + (size_t)l * D * F; g.N = D; g.K = F; g.epi = EPI_RESID; g.out_f32 = ws.h;
-    g.ldo = D; g.block_n = small ? 16 : 128;
+    g.ldo = D; g.block_n = splitk ? 64 : (small ? 16 : 128); g.ksplit = splitk ? 8 : 1;
     CUL(launch_linear_tc(g, st));
+    g.ksplit = 1;
   }
   LinearTcArgs g{};
-  g.state = state; g.pos0 = pos0; g.npos = npos; g.d_model = d.d_model;
+  g.state = state; g.pos0 = pos0; g.npos = npos; g.d_model = d.d_model; g.pdl = pdl;
   g.W = w.w_heads; g.N = d.num_codebooks * d.vocab; g.K = D; g.epi = EPI_STORE; g.out_f32 = logits_dst; g.ldo = g.N;
   g.block_n = small ? 64 : 128;
   if (logits_all) {
-    CUL(launch_rmsnorm_bf16(ws.h, w.final_norm, ws.xn_b, R, D, D, d.norm_eps, st));
+    CUL(launch_rmsnorm_bf16(ws.h, w.final_norm, ws.xn_b, R, D, D, d.norm_eps, pdl, st));
     g.A = ws.xn_b; g.lda = D; g.R = R; g.perm_S = npos; g.perm_V = d.vocab;
   } else {  // only the last position of every sequence row feeds the heads
-    CUL(launch_rmsnorm_bf16(ws.h + (size_t)(npos - 1) * D, w.final_norm, ws.xn_b, rows, D, (size_t)npos * D, d.norm_eps, st));
+    CUL(launch_rmsnorm_bf16(ws.h + (size_t)(npos - 1) * D, w.final_norm, ws.xn_b, rows, D, (size_t)npos * D, d.norm_eps, pdl, st));
     g.A = ws.xn_b; g.lda = D; g.R = rows;
   }
   CUL(launch_linear_tc(g, st));

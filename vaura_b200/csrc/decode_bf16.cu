@@ -7,39 +7,77 @@
 
 namespace vaura {
 
-__global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(const float* __restrict__ h, const float* __restrict__ w,
-                                                           __nv_bfloat16* __restrict__ out, int R, int D, size_t ldh, float eps) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + warp;
-  if (r >= R) return;
+// one CTA per row, one float4 per thread: a single L2 round trip instead of a serial loop per warp
+__global__ void __launch_bounds__(512) rmsnorm_bf16_kernel(const float* __restrict__ h, const float* __restrict__ w,
+                                                           __nv_bfloat16* __restrict__ out, int R, int D, size_t ldh, float eps,
+                                                           int pdl) {
+  if (pdl) {  // programmatic dependent launch: wait for the producer of h, then let our consumer start its prologue
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (pdl & 8) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+  __shared__ float red[16];
+  const int r = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* x = h + (size_t)r * ldh;
+  const int n4 = D >> 2;
+  float4 v[2];
   float ss = 0.f;
-  for (int c = lane * 4; c < D; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(x + c);
-    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = tid + i * blockDim.x;
+    v[i] = c < n4 ? *reinterpret_cast<const float4*>(x + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
   }
   ss = warp_sum(ss);
-  const float rs = rsqrtf(ss / (float)D + eps);
-  for (int c = lane * 4; c < D; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(x + c);
-    const float4 g = *reinterpret_cast<const float4*>(w + c);
-    uint2 o;
-    *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v.x * rs * g.x, v.y * rs * g.y);
-    *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v.z * rs * g.z, v.w * rs * g.w);
-    *reinterpret_cast<uint2*>(out + (size_t)r * D + c) = o;
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float rs = rsqrtf(tot / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = tid + i * blockDim.x;
+    if (c < n4) {
+      const float4 g = *reinterpret_cast<const float4*>(w + 4 * c);
+      uint2 o;
+      *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v[i].x * rs * g.x, v[i].y * rs * g.y);
+      *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v[i].z * rs * g.z, v[i].w * rs * g.w);
+      *reinterpret_cast<uint2*>(out + (size_t)r * D + 4 * c) = o;
+    }
   }
 }
 
-cudaError_t launch_rmsnorm_bf16(const float* h, const float* w, void* out_bf16, int R, int D, size_t ldh, float eps,
+static cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st, cudaLaunchAttribute* attr, int pdl) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cfg;
+}
+
+cudaError_t launch_rmsnorm_bf16(const float* h, const float* w, void* out_bf16, int R, int D, size_t ldh, float eps, int pdl,
                                 cudaStream_t st) {
-  rmsnorm_bf16_kernel<<<(R + 7) / 8, 256, 0, st>>>(h, w, reinterpret_cast<__nv_bfloat16*>(out_bf16), R, D, ldh, eps);
-  return cudaGetLastError();
+  cudaLaunchAttribute attr[1];
+  int threads = ((D / 4 + 1) / 2 + 31) / 32 * 32;  // two float4 per thread
+  if (threads > 512) threads = 512;
+  if (threads < 32) threads = 32;
+  if (D % 4 != 0 || D / 4 > 2 * threads) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg = pdl_config(dim3(R), dim3(threads), 0, st, attr, pdl);
+  return cudaLaunchKernelEx(&cfg, rmsnorm_bf16_kernel, h, w, reinterpret_cast<__nv_bfloat16*>(out_bf16), R, D, ldh, eps, pdl);
 }
 
 __global__ void __launch_bounds__(128) attn_bf16_kernel(AttnBf16Args a) {
   __shared__ float qs[kHeadDim];
   __shared__ float sc[kMaxCtx];
   __shared__ float red[4];
+  if (a.pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (a.pdl & 8) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   const int h = blockIdx.x, row = blockIdx.y;
   const int b = row / a.npos, j = row % a.npos;
   const int pos0 = a.state ? a.state->offset - a.npos : a.pos0;
@@ -116,8 +154,9 @@ __global__ void __launch_bounds__(128) attn_bf16_kernel(AttnBf16Args a) {
 }
 
 cudaError_t launch_attn_bf16(const AttnBf16Args& a, int nhead, int rows, cudaStream_t st) {
-  attn_bf16_kernel<<<dim3(nhead, rows), 128, 0, st>>>(a);
-  return cudaGetLastError();
+  cudaLaunchAttribute attr[1];
+  cudaLaunchConfig_t cfg = pdl_config(dim3(nhead, rows), dim3(128), 0, st, attr, a.pdl);
+  return cudaLaunchKernelEx(&cfg, attn_bf16_kernel, a);
 }
 
 }  // namespace vaura

@@ -102,6 +102,9 @@ constexpr int kTileM = 128;
 struct TcShape {
   int ntaps, nphase, kblocks;  // K iterations = ntaps * kblocks (per phase)
   int batch;
+  int ksplit;                  // split-K factor (linear layers with an accumulating epilogue); grid.z = batch*nphase*ksplit
+  int pdl;                     // launched with programmatic stream serialization: weights may be fetched before the
+                               // prerequisite grid has finished, everything else waits on griddepcontrol
   int tap_off[32];             // [nphase][ntaps] row shift of the A box
 };
 
@@ -177,6 +180,7 @@ struct EpiLinear {
     KvView kv;
     const StepState* state;
     int pos0, npos, layer, d_model;
+    int atomic;
   };
   __device__ static void apply(const Params& p, int /*b*/, int /*phase*/, int m, int n0, float (&v)[16]) {
     if (m >= p.R || n0 >= p.N) return;
@@ -190,11 +194,19 @@ struct EpiLinear {
       for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(p.out_f32 + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     } else if (p.mode == EPI_RESID) {
       float* o = p.out_f32 + (size_t)m * p.ldo + n0;
+      if (p.atomic) {  // split-K partial: accumulate into the fp32 residual stream with vector reductions
 #pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        float4 h = *reinterpret_cast<float4*>(o + i);
-        h.x += v[i]; h.y += v[i + 1]; h.z += v[i + 2]; h.w += v[i + 3];
-        *reinterpret_cast<float4*>(o + i) = h;
+        for (int i = 0; i < 16; i += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]),
+                       "f"(v[i + 3])
+                       : "memory");
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          float4 h = *reinterpret_cast<float4*>(o + i);
+          h.x += v[i]; h.y += v[i + 1]; h.z += v[i + 2]; h.w += v[i + 3];
+          *reinterpret_cast<float4*>(o + i) = h;
+        }
       }
     } else if (p.mode == EPI_SWIGLU) {
       uint4 o;
@@ -235,15 +247,16 @@ struct EpiLinear {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape g,
                const typename Epi::Params ep) {
   constexpr int SW = BLOCK_K * 2;
-  constexpr int A_BYTES = kTileM * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  static_assert(TILE_M == 64 || TILE_M == 128, "UMMA M for cta_group::1");
+  constexpr int A_BYTES = TILE_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "stage buffers must stay 1024B aligned for the swizzle");
-  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N for M=128");
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -253,9 +266,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kTileM, n0 = blockIdx.y * BLOCK_N;
-  const int b = blockIdx.z / g.nphase, phase = blockIdx.z % g.nphase;
-  const int iters = g.ntaps * g.kblocks;
+  const int m0 = blockIdx.x * TILE_M, n0 = blockIdx.y * BLOCK_N;
+  const int split = blockIdx.z % g.ksplit, zz = blockIdx.z / g.ksplit;
+  const int b = zz / g.nphase, phase = zz % g.nphase;
+  const int total_iters = g.ntaps * g.kblocks;
+  const int it_begin = (total_iters * split) / g.ksplit, it_end = (total_iters * (split + 1)) / g.ksplit;
+  const int iters = it_end - it_begin;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -276,22 +292,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // NOTE: triggering the dependent grid BEFORE this grid's own griddepcontrol.wait was measured to break the chain
+  // (the dependent's wait then no longer covers our prerequisite); the trigger is issued after the wait, below.
+
   if (warp == 0) {
     if (lane == 0) {
+      // weights (operand B) do not depend on the previous kernel: fill the first ring pass before waiting for it
+      const int pre = (g.pdl & 4) ? min(iters, STAGES) : 0;
+      for (int it = 0; it < pre; ++it) {
+        const int gi = it_begin + it, tap = gi / g.kblocks, kb = gi % g.kblocks;
+        mbar_expect_tx(&full[it], STAGE_BYTES);
+        tma_load_3d(smem + it * STAGE_BYTES + A_BYTES, &tmB, &full[it], kb * BLOCK_K, n0, phase * g.ntaps + tap);
+      }
+      if (g.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int it = 0; it < iters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], STAGE_BYTES);
-        const int tap = it / g.kblocks, kb = it % g.kblocks;
+        const int gi = it_begin + it, tap = gi / g.kblocks, kb = gi % g.kblocks;
         uint8_t* sa = smem + s * STAGE_BYTES;
+        if (it >= pre) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          tma_load_3d(sa + A_BYTES, &tmB, &full[s], kb * BLOCK_K, n0, phase * g.ntaps + tap);
+        }
         tma_load_3d(sa, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
-        tma_load_3d(sa + A_BYTES, &tmB, &full[s], kb * BLOCK_K, n0, phase * g.ntaps + tap);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kTileM, BLOCK_N, FMT);
+      constexpr uint32_t idesc = make_idesc(TILE_M, BLOCK_N, FMT);
       for (int it = 0; it < iters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -307,15 +336,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(tmem_full);    // accumulator complete
     }
   } else {
+    if (g.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // our prerequisite has completed: the dependent grid may now start its prologue and weight prefetch
+    if (g.pdl & 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     mbar_wait(tmem_full, 0);
     tcgen05_fence_after();
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    const int m = m0 + q * 32 + lane;
+    // M=128: accumulator row i sits in lane i.  M=64: rows 16q..16q+15 sit in lanes 32q..32q+15 (half-filled quadrants)
+    const int m = TILE_M == 128 ? m0 + q * 32 + lane : m0 + q * 16 + lane;
+    const bool row_ok = TILE_M == 128 || lane < 16;
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N; c += 16) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
-      Epi::apply(ep, b, phase, m, n0 + c, v);
+      if (row_ok) Epi::apply(ep, b, phase, m, n0 + c, v);
     }
   }
   tcgen05_fence_before();
@@ -359,21 +393,30 @@ static bool make_map(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128>
 static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcShape& g, const typename Epi::Params& ep,
                              int m_tiles, int n_tiles, cudaStream_t st) {
-  constexpr int smem = STAGES * (kTileM * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
-  auto kern = gemm_tc_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi>;
+  constexpr int smem = STAGES * (TILE_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "stage ring exceeds shared memory");
+  auto kern = gemm_tc_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, TILE_M>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  kern<<<dim3(m_tiles, n_tiles, g.batch * g.nphase), 192, smem, st>>>(ta, tb, g, ep);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(m_tiles, n_tiles, g.batch * g.nphase * g.ksplit);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr1[1];
+  attr1[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr1[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr1;
+  cfg.numAttrs = g.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, g, ep);
 }
-
 bool conv_tc_supported(int Cin, int Cout, int ntaps, int nphase) {
   if (Cin % 32 != 0 || Cout % 16 != 0 || ntaps * nphase > 32) return false;
   const int bk = (Cin % 64 == 0) ? 64 : 32;
@@ -398,7 +441,7 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cu
   if (!make_map(&tb, a.W, a.Cin, a.Cout, (uint64_t)a.ntaps * a.nphase, a.Cin, (uint64_t)a.Cout * a.Cin, bk, bn, true))
     return cudaErrorUnknown;
   TcShape g{};
-  g.ntaps = a.ntaps; g.nphase = a.nphase; g.kblocks = a.Cin / bk; g.batch = B;
+  g.ntaps = a.ntaps; g.nphase = a.nphase; g.kblocks = a.Cin / bk; g.batch = B; g.ksplit = 1; g.pdl = 0;
   for (int i = 0; i < a.ntaps * a.nphase; ++i) g.tap_off[i] = tap_off_host[i];
   EpiConv::Params ep{a.bias, a.alpha, a.residual, a.out_raw, a.out_act, a.Tq, a.Tout, a.Cout, a.ostride};
   const int mt = (a.Tq + kTileM - 1) / kTileM, nt = a.Cout / bn;
@@ -420,16 +463,30 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cu
 // Linear layer of the bf16 sampler path: out = A[R][K] (bf16) x W[N][K]^T (bf16) with a fused epilogue.
 cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st) {
   if (a.K % 64 != 0 || a.N % a.block_n != 0) return cudaErrorInvalidValue;
+  // up to 64 rows: UMMA M=64 halves the activation tile, so twice as many weight bytes fit in flight per SM
+  const int tile_m = a.R <= 64 ? 64 : kTileM;
   CUtensorMap ta, tb;
-  if (!make_map(&ta, a.A, a.K, a.R, 1, a.lda, (uint64_t)a.R * a.lda, 64, kTileM, false)) return cudaErrorUnknown;
+  if (!make_map(&ta, a.A, a.K, a.R, 1, a.lda, (uint64_t)a.R * a.lda, 64, tile_m, false)) return cudaErrorUnknown;
   if (!make_map(&tb, a.W, a.K, a.N, 1, a.K, (uint64_t)a.N * a.K, 64, a.block_n, false)) return cudaErrorUnknown;
   TcShape g{};
   g.ntaps = 1; g.nphase = 1; g.kblocks = a.K / 64; g.batch = 1;
+  g.ksplit = (a.epi == EPI_RESID && a.ksplit > 1) ? a.ksplit : 1;
+  if (g.ksplit > g.kblocks) g.ksplit = g.kblocks;
+  g.pdl = a.pdl;
   EpiLinear::Params ep{};
   ep.mode = a.epi; ep.R = a.R; ep.N = a.N; ep.out_f32 = a.out_f32; ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
   ep.ldo = a.ldo; ep.perm_S = a.perm_S; ep.perm_V = a.perm_V; ep.rope = a.rope; ep.kv = a.kv; ep.state = a.state;
-  ep.pos0 = a.pos0; ep.npos = a.npos; ep.layer = a.layer; ep.d_model = a.d_model;
-  const int mt = (a.R + kTileM - 1) / kTileM, nt = a.N / a.block_n;
+  ep.pos0 = a.pos0; ep.npos = a.npos; ep.layer = a.layer; ep.d_model = a.d_model; ep.atomic = g.ksplit > 1;
+  const int mt = (a.R + tile_m - 1) / tile_m, nt = a.N / a.block_n;
+  if (tile_m == 64) {
+    switch (a.block_n) {
+      case 16: return launch_tc<16, 64, 12, 1, EpiLinear, 64>(ta, tb, g, ep, mt, nt, st);
+      case 32: return launch_tc<32, 64, 12, 1, EpiLinear, 64>(ta, tb, g, ep, mt, nt, st);
+      case 64: return launch_tc<64, 64, 12, 1, EpiLinear, 64>(ta, tb, g, ep, mt, nt, st);
+      case 128: return launch_tc<128, 64, 8, 1, EpiLinear, 64>(ta, tb, g, ep, mt, nt, st);
+    }
+    return cudaErrorInvalidValue;
+  }
   switch (a.block_n) {
     case 16: return launch_tc<16, 64, 8, 1, EpiLinear>(ta, tb, g, ep, mt, nt, st);
     case 32: return launch_tc<32, 64, 8, 1, EpiLinear>(ta, tb, g, ep, mt, nt, st);

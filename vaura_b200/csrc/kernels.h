@@ -86,10 +86,13 @@ struct LinearTcArgs {
   const StepState* state;
   int R, N, K, lda, ldo, block_n, epi;
   int perm_S, perm_V, pos0, npos, layer, d_model;
+  int ksplit;  // EPI_RESID only: split K over this many CTAs, partials reduced with red.global.add
+  int pdl;     // programmatic dependent launch (see TcShape::pdl)
 };
 cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st);
 // bf16 path helpers (decode_bf16.cu)
-cudaError_t launch_rmsnorm_bf16(const float* h, const float* w, void* out_bf16, int R, int D, size_t ldh, float eps, cudaStream_t st);
+cudaError_t launch_rmsnorm_bf16(const float* h, const float* w, void* out_bf16, int R, int D, size_t ldh, float eps, int pdl,
+                                cudaStream_t st);
 struct AttnBf16Args {
   const void* q;   // bf16 [rows*npos][d]
   void* out;       // bf16 [rows*npos][d]
@@ -97,6 +100,7 @@ struct AttnBf16Args {
   const StepState* state;
   int pos0, npos, layer, d_model;
   float scale;
+  int pdl;
 };
 cudaError_t launch_attn_bf16(const AttnBf16Args& a, int nhead, int rows, cudaStream_t st);
 
