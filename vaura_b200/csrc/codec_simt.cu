@@ -36,9 +36,9 @@ cudaError_t launch_from_codes(const int32_t* codes, const __half* tables, __half
   return cudaGetLastError();
 }
 
-__device__ __forceinline__ float snake_f(float v, float alpha) {
-  const float s = sinf(alpha * v);
-  return v + s * s / (alpha + 1e-9f);
+__device__ __forceinline__ float snake_f(float v, float alpha, float inv_alpha) {
+  const float s = __sinf(alpha * v);
+  return fmaf(s * s, inv_alpha, v);
 }
 
 constexpr int TM = 64, TN = 64, TK = 16;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(ConvArgs a) {
       float v = acc[i][j] + a.bias[co];
       if (a.residual) v += __half2float(a.residual[base + co]);
       if (a.out_raw) a.out_raw[base + co] = __float2half_rn(v);
-      if (a.out_act) a.out_act[base + co] = __float2half_rn(snake_f(v, a.alpha[co]));
+      if (a.out_act) a.out_act[base + co] = __float2half_rn(snake_f(v, a.alpha[co], a.alpha[a.Cout + co]));
     }
   }
 }

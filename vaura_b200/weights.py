@@ -137,6 +137,11 @@ def pack_codec(sd: Dict[str, torch.Tensor], dims: CodecDims, device):
     def f(t):
         parts.append(t.to(torch.float32).contiguous())
 
+    def snake(alpha):
+        """[C] alpha followed by [C] 1/(alpha + 1e-9): the epilogues multiply instead of dividing."""
+        al = alpha.reshape(-1).to(torch.float32)
+        parts.append(torch.cat([al, (al + 1e-9).reciprocal()]).contiguous())
+
     n = len(dims.decoder_rates)
     tables = []
     for k in range(dims.n_codebooks):
@@ -153,20 +158,20 @@ def pack_codec(sd: Dict[str, torch.Tensor], dims: CodecDims, device):
     tap_tables += [j - 3 for j in range(7)]
     for i, s in enumerate(dims.decoder_rates):
         p = f"decoder.model.{i + 1}.block"
-        f(sd[f"{p}.0.alpha"].reshape(-1))
+        snake(sd[f"{p}.0.alpha"])
         wt, offs = convt_polyphase(_conv_w(sd, f"{p}.1"), s)
         h(wt)
         tap_tables += offs
         f(sd[f"{p}.1.bias"])
         for j in range(3):
             q = f"{p}.{2 + j}.block"
-            f(sd[f"{q}.0.alpha"].reshape(-1))
+            snake(sd[f"{q}.0.alpha"])
             h(_conv_w(sd, f"{q}.1").permute(2, 0, 1))
             f(sd[f"{q}.1.bias"])
-            f(sd[f"{q}.2.alpha"].reshape(-1))
+            snake(sd[f"{q}.2.alpha"])
             h(_conv_w(sd, f"{q}.3").permute(2, 0, 1))
             f(sd[f"{q}.3.bias"])
-    f(sd[f"decoder.model.{n + 1}.alpha"].reshape(-1))
+    snake(sd[f"decoder.model.{n + 1}.alpha"])
     f(_conv_w(sd, f"decoder.model.{n + 2}")[0].t())  # (1,Cl,7) -> [7][Cl] fp32
     f(sd[f"decoder.model.{n + 2}.bias"])
     parts.append(torch.tensor(tap_tables, dtype=torch.int32))
