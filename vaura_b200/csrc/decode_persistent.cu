@@ -3,14 +3,13 @@
 // One CTA per SM runs the WHOLE decode step: embedding -> 24 x {RMSNorm+QKV+RoPE+KV append | paged attention |
 // wo+residual | RMSNorm+w1|w3+SiLU*mul | w2+residual} -> final norm + 9 heads -> CFG/sampling/write-back.
 // Every CTA owns a fixed contiguous block of output rows of every weight matrix, so its weight bytes for the
-// step are one fixed sequence of contiguous chunks.  A dedicated producer warp streams that sequence with
-// cp.async.bulk (TMA 1-D) into two ~90 KB shared-memory slots (double buffer) guarded by full/empty mbarriers; it
-// never waits for the dependency chain, so HBM keeps streaming while the 15 consumer warps sit in a grid barrier or
-// in the attention phase.  A slot holds one "group" of up to 15 work items (one row pair per consumer warp; pairs
-// with K > 1536 are split along K over several warps), so ring synchronisation costs one mbarrier wait and one
-// arrive per group instead of per warp (mbarrier operations serialise at ~50 cycles each per SM).  Consumers read
-// weights and activations from shared memory only; phases are separated by a device-wide barrier (red.release +
-// ld.acquire spin per CTA).
+// step are one fixed sequence of contiguous chunks, streamed with cp.async.bulk (TMA 1-D) into two ~96 KB
+// shared-memory slots (double buffer) whose arrival is tracked by one mbarrier each.  A slot holds one "group" of up
+// to 16 work items (one row pair per warp; pairs with K > 2048 are split along K over two warps).  All 16 warps
+// compute; when a group is finished (CTA-wide named barrier) thread 0 immediately issues the copy of the group after
+// next into the slot that just became free, so the copy of group g+1 is always in flight while group g is consumed
+// and during grid barriers / attention / staging.  The warps read weights and activations from shared memory only;
+// phases are separated by a device-wide barrier (red.release + ld.acquire spin per CTA).
 //
 // Replaces the same reference lines as decode_fp32.cu (llama.py:445-517 for one position) plus the sampling
 // stage of sampling.cu; arithmetic (fp32 accumulate order per row aside) is identical to gemv_kernel/attn_kernel.
@@ -22,9 +21,10 @@ namespace vaura {
 
 namespace {
 
-constexpr int NW = 15;                     // consumer warps (+1 producer = 16 warps: 128 registers per thread)
-constexpr int kConsumers = NW * 32;        // 480
-constexpr int kThreadsP = kConsumers + 32;  // + producer warp
+constexpr int NW = 16;                     // warps per CTA (512 threads -> 128 registers per thread); all of them compute,
+                                           // thread 0 also issues the weight copies
+constexpr int kConsumers = NW * 32;        // 512
+constexpr int kThreadsP = kConsumers;
 constexpr int kMaxSplit = 4;               // a row pair with K > 1536 is split over up to 4 warps along K
 constexpr int ATT_STRIDE = 100;            // floats per attention partial: m, l, pad, pad, o[96]
 
@@ -161,7 +161,7 @@ __device__ __forceinline__ void pair_range(int pairs, int cta, int G, int& p0, i
 struct GroupPlan {
   int splits, ngroups, base, rem;  // group g holds base + (g < rem) pairs
   __device__ GroupPlan(int K, int npairs, int slot_cap) {
-    splits = (K + 1535) / 1536;
+    splits = (K + 2047) / 2048;
     if (splits > kMaxSplit) splits = kMaxSplit;
     int ppg = NW / splits;
     const int cap = slot_cap / (4 * K);
@@ -174,14 +174,14 @@ struct GroupPlan {
 
 // The CTA's weight groups of one decode step in consumption order.
 struct WeightSched {
-  const PersistArgs& a;
-  int cta, G, l, ph, g, pp;
-  bool open;
-  GroupPlan gp;
+  int cta, G, l, ph, g, pp, open;
+  int gp_ngroups, gp_base, gp_rem;
   const uint16_t* W;
   int K;
-  __device__ WeightSched(const PersistArgs& a_, int cta_, int G_) : a(a_), cta(cta_), G(G_), l(0), ph(-1), g(0), pp(0), open(false), gp(1536, 0, 1 << 20), W(nullptr), K(0) {}
-  __device__ bool advance_phase() {
+  __device__ void init(int cta_, int G_) {
+    cta = cta_; G = G_; l = 0; ph = -1; g = 0; pp = 0; open = 0; gp_ngroups = 0; gp_base = 0; gp_rem = 0; W = nullptr; K = 0;
+  }
+  __device__ bool advance_phase(const PersistArgs& a) {
     ++ph;
     if (l < a.L && ph == 4) { ph = 0; ++l; }
     if (l > a.L || (l == a.L && ph > 0)) return false;
@@ -194,17 +194,18 @@ struct WeightSched {
     else { W = a.w2 + (size_t)l * D * F; K = F; pairs = D / 2; }
     int p0, p1;
     pair_range(pairs, cta, G, p0, p1);
-    gp = GroupPlan(K, p1 - p0, a.slot_cap);
+    const GroupPlan gp(K, p1 - p0, a.slot_cap);
+    gp_ngroups = gp.ngroups; gp_base = gp.base; gp_rem = gp.rem;
     g = 0;
     pp = p0;
     return true;
   }
-  __device__ bool next(const uint16_t*& ptr, uint32_t& bytes) {
-    while (!open || g >= gp.ngroups) {
-      if (!advance_phase()) return false;
-      open = true;
+  __device__ bool next(const PersistArgs& a, const uint16_t*& ptr, uint32_t& bytes) {
+    while (!open || g >= gp_ngroups) {
+      if (!advance_phase(a)) return false;
+      open = 1;
     }
-    const int n = gp.base + (g < gp.rem ? 1 : 0);
+    const int n = gp_base + (g < gp_rem ? 1 : 0);
     ptr = W + (size_t)pp * 2 * K;
     bytes = (uint32_t)n * 4u * (uint32_t)K;
     pp += n;
@@ -233,10 +234,12 @@ struct Phase {
 // memory context would turn every field access into an L2 round trip.
 struct SmemCtx {
   PersistArgs a;
+  WeightSched sched;   // load cursor, touched by thread 0 only
+  unsigned issued;     // groups whose copy has been issued
   int slot_cap, slots_off, xs_off, scr_off, hown_off, rope_off, red_off, part_off, page_off, bar_off;
   int cta, G, p, own0;
 };
-constexpr int kCtxBytes = 1024;
+constexpr int kCtxBytes = 1024;  // PersistArgs + schedule cursor + layout offsets
 static_assert(sizeof(SmemCtx) <= kCtxBytes, "SmemCtx must fit its reserved shared-memory block");
 
 #define VAURA_SMEM_VIEW()                                                                     \
@@ -248,8 +251,21 @@ static_assert(sizeof(SmemCtx) <= kCtxBytes, "SmemCtx must fit its reserved share
   float* red = reinterpret_cast<float*>(smem + sc.red_off);                                   \
   float* part_s = reinterpret_cast<float*>(smem + sc.part_off);                               \
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + sc.bar_off);                            \
-  uint64_t* empty = full + 2;                                                                 \
-  (void)a; (void)tid; (void)warp; (void)lane; (void)xs; (void)red; (void)part_s; (void)full; (void)empty;
+  (void)a; (void)tid; (void)warp; (void)lane; (void)xs; (void)red; (void)part_s; (void)full;
+
+// thread 0: issue the bulk copy of the next group of the schedule into slot (issued & 1)
+__device__ __forceinline__ void issue_next_group() {
+  extern __shared__ __align__(128) uint8_t smem[];
+  SmemCtx& w = *reinterpret_cast<SmemCtx*>(smem);
+  const uint16_t* ptr;
+  uint32_t bytes;
+  if (!w.sched.next(w.a, ptr, bytes)) return;
+  const int slot = w.issued & 1;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + w.bar_off);
+  mb_expect_tx(&full[slot], bytes);
+  bulk_g2s(smem + w.slots_off + (size_t)slot * w.slot_cap, ptr, bytes, &full[slot]);
+  ++w.issued;
+}
 
 // xs[r] = (x * rsqrt(mean(x^2)+eps)) * w, permuted.  Source: global h (through L2) or, for layer 0, the embedding
 // rows sitting unpermuted in xs (read into registers before the permuted overwrite; syncs in between).
@@ -365,8 +381,8 @@ __device__ __noinline__ unsigned gemv_phase(int K, int pairs, int epi, int layer
         pair_epilogue<NB>(epi, layer, pairs, pp + j, lane, y0, y1);
       }
     }
-    consumer_sync();  // every warp is done reading the slot (and part_s)
-    if (tid == 0) mb_arrive(&empty[slot]);
+    consumer_sync();  // every warp is done reading the slot (and part_s): refill it with the group after next
+    if (tid == 0) issue_next_group();
     pp += n;
     ++grp_ctr;
   }
@@ -396,7 +412,6 @@ __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const Per
   float* part_s = reinterpret_cast<float*>(smem + part_off);
   int* page_s = reinterpret_cast<int*>(smem + page_off);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + bar_off);
-  uint64_t* empty = full + 2;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, G = gridDim.x;
@@ -408,10 +423,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const Per
   unsigned bar_i = 0;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mb_init(&full[s], 1);
-      mb_init(&empty[s], 1);
-    }
+    for (int s = 0; s < 2; ++s) mb_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     SmemCtx& w = *reinterpret_cast<SmemCtx*>(smem);
     w.a = a;
@@ -421,39 +433,15 @@ __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const Per
     int o0_, o1_;
     pair_range(a.D / 2, cta, G, o0_, o1_);
     w.own0 = o0_;
+    w.sched.init(cta, G);
+    w.issued = 0;
+    issue_next_group();  // both slots start filling before the embedding / first norm
+    issue_next_group();
   }
   __syncthreads();
 
   const int qkv_pairs = 3 * D / 2, d_pairs = D / 2, f_pairs = F, head_pairs = a.Kc * a.V / 2;
 
-  // ============================== producer warp ==============================
-  if (warp == NW) {
-    if (lane == 0) {
-      // Two cursors walk the same schedule of (pointer, bytes) groups: `pf` runs kPrefetchAhead groups ahead and only
-      // warms L2 (cp.async.bulk.prefetch.L2), so HBM keeps streaming while both smem slots are full (grid barriers,
-      // attention, staging); `ld` fills the smem slots, mostly from L2.
-      const PersistArgs& as = reinterpret_cast<const SmemCtx*>(smem)->a;  // shared-memory copy (LDS, not local memory)
-      WeightSched ld(as, cta, G), pf(as, cta, G);
-      const uint16_t* ptr;
-      uint32_t bytes;
-      for (int i = 0; i < as.prefetch_ahead && pf.next(ptr, bytes); ++i) bulk_prefetch_l2(ptr, bytes);
-      unsigned grp_ctr = 0;
-      while (ld.next(ptr, bytes)) {
-        const int slot = grp_ctr & 1;
-        const uint32_t par = (grp_ctr >> 1) & 1;
-        const uint16_t* pptr;
-        uint32_t pbytes;
-        if (as.prefetch_ahead > 0 && pf.next(pptr, pbytes)) bulk_prefetch_l2(pptr, pbytes);
-        mb_wait(&empty[slot], par ^ 1);
-        mb_expect_tx(&full[slot], bytes);
-        bulk_g2s(slots + (size_t)slot * as.slot_cap, ptr, bytes, &full[slot]);
-        ++grp_ctr;
-      }
-    }
-    return;
-  }
-
-  // ============================== consumer warps ==============================
   int own0, own1;  // this CTA's slice of the residual stream (features [2*own0, 2*own1))
   pair_range(d_pairs, cta, G, own0, own1);
 
@@ -672,7 +660,7 @@ static size_t persist_smem(int NB, int D, int F, int& slot_cap) {
                        128 * 4 + 8 * 4 + 4 * 8 + 256;
   const size_t budget = 227 * 1024;
   size_t cap = (budget - fixed) / 2;
-  const size_t want = (size_t)NW * 4 * 1536;  // 15 row pairs of K=1536
+  const size_t want = (size_t)NW * 4 * 1536;  // 16 row pairs of K=1536
   if (cap > want) cap = want;
   cap &= ~(size_t)1023;
   slot_cap = (int)cap;
