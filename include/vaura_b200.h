@@ -96,6 +96,14 @@ typedef struct {
   const float* fc1;         /* [cond_dim][cond_in]  cls_embeddings.projection.fc1.weight           */
   const float* fc2;         /* [cond_dim][cond_dim] cls_embeddings.projection.fc2.weight           */
   const float* empty_video_emb; /* [cond_dim] (llama.py:336-338) */
+  /* Optional second copy of the five matrices in K-block-major order for the tensor-core persistent decode kernel
+   * (rows <= 2): X_t[l][kb][n][64] = X[l][n][64*kb .. 64*kb+63], so the [rows x 64] tile a CTA fetches per K block is
+   * one contiguous chunk.  NULL disables that kernel (the SIMT persistent kernel is used instead). */
+  const uint16_t* wqkv_t;
+  const uint16_t* wo_t;
+  const uint16_t* w13_t;
+  const uint16_t* w2_t;
+  const uint16_t* w_heads_t;
 } vaura_sampler_weights;
 
 /* Paged KV cache, caller-owned.  Element (layer l, kv in {0=K,1=V}, sequence b, position p, head h, dim e):

@@ -351,6 +351,7 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     PersistArgs pa{};
     const vaura_sampler_weights& w = s->w;
     pa.wqkv = w.wqkv; pa.wo = w.wo; pa.w13 = w.w13; pa.w2 = w.w2; pa.w_heads = w.w_heads; pa.attn_norm = w.attn_norm;
+    pa.wqkv_t = w.wqkv_t; pa.wo_t = w.wo_t; pa.w13_t = w.w13_t; pa.w2_t = w.w2_t; pa.w_heads_t = w.w_heads_t;
     pa.ffn_norm = w.ffn_norm; pa.final_norm = w.final_norm; pa.tok_tables = w.tok_tables; pa.rope = w.rope;
     pa.seq = p->sequence; pa.cond_rows = p->cond_rows; pa.h = ws.h; pa.q = ws.q; pa.act = ws.act; pa.logits = ws.logits;
     pa.attn_part = ws.attn_part; pa.kv = kvv; pa.state = ws.state; pa.sample = sa; pa.sample.state = nullptr;
@@ -358,7 +359,19 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     pa.batch = p->batch; pa.cond_dim = d.cond_dim; pa.cond_tokens = d.cond_tokens; pa.atpvf = d.audio_tokens_per_video_frame;
     pa.eps = d.norm_eps; pa.scale = 1.0f / sqrtf((float)kHeadDim);
     { const char* tm = getenv("VAURA_PERSIST_TIMING"); pa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
-    for (int i = 0; i < nsteps; ++i) CUL(launch_decode_persistent(pa, rows, st));
+    int sms = 0, dev = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // The tensor-core variant (decode_persistent_tc.cu) is parity-green but measured slower than the SIMT variant on
+    // B200 (1.07 vs 0.80 ms per step at one row: its phases are bound by the number of tiny tcgen05.mma / TMA
+    // operations per K block); it is opt-in until the work partition is changed.
+    const char* tc = getenv("VAURA_PERSIST_TC");
+    const bool use_tc = (tc && tc[0] == '1') && w.wqkv_t && w.wo_t && w.w13_t && w.w2_t && w.w_heads_t &&
+                        persistent_tc_supported(rows, d.d_model, d.ffn_dim, kv->page_size, K * d.vocab / 2, d.ffn_dim, sms);
+    for (int i = 0; i < nsteps; ++i) {
+      if (use_tc) CUL(launch_decode_persistent_tc(pa, rows, st));
+      else CUL(launch_decode_persistent(pa, rows, st));
+    }
     return VAURA_OK;
   }
   // otherwise: capture one step (reads its position from the device state) and replay it

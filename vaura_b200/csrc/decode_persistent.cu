@@ -691,7 +691,7 @@ static cudaError_t launch_persist_t(PersistArgs& a, cudaStream_t st) {
   }
   static int grid = 0;
   if (!grid) {
-    cudaError_t e = cudaFuncSetAttribute(decode_step_persistent<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(decode_step_persistent<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0, occ = 0;
     cudaGetDevice(&dev);

@@ -111,6 +111,7 @@ cudaError_t init_decode_kernels();
 // persistent decode-step kernel (decode_persistent.cu)
 struct PersistArgs {
   const uint16_t *wqkv, *wo, *w13, *w2, *w_heads;
+  const uint16_t *wqkv_t, *wo_t, *w13_t, *w2_t, *w_heads_t;  // K-block-major copies (tensor-core variant)
   const float *attn_norm, *ffn_norm, *final_norm, *tok_tables, *rope;
   const int32_t* seq;
   const float* cond_rows;
@@ -126,6 +127,9 @@ struct PersistArgs {
 bool persistent_supported(int rows, int D, int F, int page_size);
 size_t persistent_attn_part_bytes(int rows, int H);
 cudaError_t launch_decode_persistent(PersistArgs& a, int rows, cudaStream_t st);
+// tensor-core variant (decode_persistent_tc.cu)
+bool persistent_tc_supported(int rows, int D, int F, int page_size, int head_pairs, int f_pairs, int sms);
+cudaError_t launch_decode_persistent_tc(PersistArgs& a, int rows, cudaStream_t st);
 
 cudaError_t launch_embed(const EmbedArgs& a, int rows, cudaStream_t st);
 cudaError_t launch_gemv(int epi, bool norm, const GemvArgs& a, cudaStream_t st);
