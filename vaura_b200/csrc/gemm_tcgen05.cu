@@ -252,13 +252,17 @@ struct EpiLinear {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128>
+// KSUB: 64-wide K blocks per pipeline stage.  The single-thread producer / MMA loops pay ~0.25 us of serialized
+// mbarrier-wait + fence + commit latency per stage; with thin tiles (decode: 64 rows x 32-64 weight rows) that
+// latency, not bandwidth, bounded the mainloop, so linear layers put 4 K blocks (16 UMMAs) behind each barrier.
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128, int KSUB = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape g,
                const typename Epi::Params ep) {
   constexpr int SW = BLOCK_K * 2;
   static_assert(TILE_M == 64 || TILE_M == 128, "UMMA M for cta_group::1");
-  constexpr int A_BYTES = TILE_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int A_BYTES = TILE_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, SUB_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE_BYTES = KSUB * SUB_BYTES;
   constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "stage buffers must stay 1024B aligned for the swizzle");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
@@ -274,9 +278,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m0 = blockIdx.x * TILE_M, n0 = blockIdx.y * BLOCK_N;
   const int split = blockIdx.z % g.ksplit, zz = blockIdx.z / g.ksplit;
   const int b = zz / g.nphase, phase = zz % g.nphase;
-  const int total_iters = g.ntaps * g.kblocks;
-  const int it_begin = (total_iters * split) / g.ksplit, it_end = (total_iters * (split + 1)) / g.ksplit;
-  const int iters = it_end - it_begin;
+  // units = (tap, K block) pairs; a stage covers up to KSUB consecutive units (KSUB > 1 only with a single tap)
+  const int total_units = g.ntaps * g.kblocks;
+  const int u_begin = (total_units * split) / g.ksplit, u_end = (total_units * (split + 1)) / g.ksplit;
+  const int iters = (u_end - u_begin + KSUB - 1) / KSUB;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -305,22 +310,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // weights (operand B) do not depend on the previous kernel: fill the first ring pass before waiting for it
       const int pre = (g.pdl & 4) ? min(iters, STAGES) : 0;
       for (int it = 0; it < pre; ++it) {
-        const int gi = it_begin + it, tap = gi / g.kblocks, kb = gi % g.kblocks;
-        mbar_expect_tx(&full[it], STAGE_BYTES);
-        tma_load_3d(smem + it * STAGE_BYTES + A_BYTES, &tmB, &full[it], kb * BLOCK_K, n0, phase * g.ntaps + tap);
+        const int u0 = u_begin + it * KSUB, nsub = min(KSUB, u_end - u0);
+        mbar_expect_tx(&full[it], nsub * SUB_BYTES);
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int gi = u0 + sub, tap = gi / g.kblocks, kb = gi % g.kblocks;
+          tma_load_3d(smem + it * STAGE_BYTES + sub * SUB_BYTES + A_BYTES, &tmB, &full[it], kb * BLOCK_K, n0, phase * g.ntaps + tap);
+        }
       }
       if (g.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int it = 0; it < iters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        const int gi = it_begin + it, tap = gi / g.kblocks, kb = gi % g.kblocks;
-        uint8_t* sa = smem + s * STAGE_BYTES;
+        const int u0 = u_begin + it * KSUB, nsub = min(KSUB, u_end - u0);
+        uint8_t* ss = smem + s * STAGE_BYTES;
         if (it >= pre) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], STAGE_BYTES);
-          tma_load_3d(sa + A_BYTES, &tmB, &full[s], kb * BLOCK_K, n0, phase * g.ntaps + tap);
+          mbar_expect_tx(&full[s], nsub * SUB_BYTES);
         }
-        tma_load_3d(sa, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int gi = u0 + sub, tap = gi / g.kblocks, kb = gi % g.kblocks;
+          uint8_t* sa = ss + sub * SUB_BYTES;
+          if (it >= pre) tma_load_3d(sa + A_BYTES, &tmB, &full[s], kb * BLOCK_K, n0, phase * g.ntaps + tap);
+          tma_load_3d(sa, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -331,11 +343,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[s], ph);
         tcgen05_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
+        const int nsub = min(KSUB, u_end - (u_begin + it * KSUB));
+        for (int sub = 0; sub < nsub; ++sub) {
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES + sub * SUB_BYTES);
+          const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k)  // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
-          umma_bf16_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          for (int k = 0; k < BLOCK_K / 16; ++k)  // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
+            umma_bf16_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | sub | k) != 0);
+        }
         umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
       }
       umma_commit(tmem_full);    // accumulator complete
@@ -401,12 +416,13 @@ static bool make_map(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128, int KSUB = 1>
 static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcShape& g, const typename Epi::Params& ep,
                              int m_tiles, int n_tiles, cudaStream_t st) {
-  constexpr int smem = STAGES * (TILE_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+  constexpr int smem = STAGES * KSUB * (TILE_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
   static_assert(smem <= 227 * 1024, "stage ring exceeds shared memory");
-  auto kern = gemm_tc_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, TILE_M>;
+  if (KSUB > 1 && g.ntaps != 1) return cudaErrorInvalidValue;
+  auto kern = gemm_tc_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, TILE_M, KSUB>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -488,10 +504,10 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st) {
   const int mt = (a.R + tile_m - 1) / tile_m, nt = a.N / a.block_n;
   if (tile_m == 64) {
     switch (a.block_n) {
-      case 16: return launch_tc<16, 64, 12, 1, EpiLinear, 64>(ta, tb, g, ep, mt, nt, st);
-      case 32: return launch_tc<32, 64, 12, 1, EpiLinear, 64>(ta, tb, g, ep, mt, nt, st);
-      case 64: return launch_tc<64, 64, 12, 1, EpiLinear, 64>(ta, tb, g, ep, mt, nt, st);
-      case 128: return launch_tc<128, 64, 8, 1, EpiLinear, 64>(ta, tb, g, ep, mt, nt, st);
+      case 16: return launch_tc<16, 64, 4, 1, EpiLinear, 64, 4>(ta, tb, g, ep, mt, nt, st);
+      case 32: return launch_tc<32, 64, 4, 1, EpiLinear, 64, 4>(ta, tb, g, ep, mt, nt, st);
+      case 64: return launch_tc<64, 64, 3, 1, EpiLinear, 64, 4>(ta, tb, g, ep, mt, nt, st);
+      case 128: return launch_tc<128, 64, 2, 1, EpiLinear, 64, 4>(ta, tb, g, ep, mt, nt, st);
     }
     return cudaErrorInvalidValue;
   }
