@@ -174,7 +174,7 @@ def main():
     lib = _cabi.load()
     wl = WORKLOADS[args.workload]
     B, T = wl["batch"], wl["T"]
-    model = build_model(FULL_SAMPLER, FULL_CODEC)
+    model = build_model(FULL_SAMPLER, FULL_CODEC, device=str(dev))
     model.seed = 1234
     kw = dict(max_new_tokens=T, use_sampling=wl["use_sampling"], temp=wl["temp"], top_k=wl["top_k"], top_p=0.0,
               cfg_scale=wl["cfg_scale"], prompt_is_encoded=True)

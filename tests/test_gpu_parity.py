@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def build_model(sdims, cdims, seed=0):
+def build_model(sdims, cdims, seed=0, device="cuda:0"):
     cfg = dict(
         use_visual_conditioning=True,
         feature_extractor_config={"target": "models.modules.feature_extractors.avclip.motionformer.MotionFormer",
@@ -34,7 +34,7 @@ def build_model(sdims, cdims, seed=0):
         flatten_vis_feats=True,
     )
     m = VAURAModel(**cfg)
-    m.load_state_dict(make_checkpoint_state_dict(sdims, cdims, seed), device="cuda:0")
+    m.load_state_dict(make_checkpoint_state_dict(sdims, cdims, seed), device=device)
     m.eval()
     m.sampler.audio_tokens_per_video_frame = 7
     return m
