@@ -115,6 +115,7 @@ struct Workspace {
   StepState* state;
   unsigned long long* timing;
   float *h, *q, *attn, *act, *logits, *attn_part;        // fp32act path
+  long long* xfix;                                       // fp32act path, cluster decode kernel (rows <= 2)
   __nv_bfloat16 *xn_b, *q_b, *attn_b, *act_b;            // bf16 path (h and logits stay fp32)
   size_t bytes;
 };
@@ -145,6 +146,7 @@ static Workspace carve(const vaura_sampler_dims& d, int rows, int max_pos, int p
     w.attn = (float*)take(R * d.d_model * 4);
     w.act = (float*)take(R * d.ffn_dim * 4);
     w.attn_part = (float*)take(persistent_attn_part_bytes(rows, d.nhead));
+    w.xfix = (long long*)take(cluster_xfix_bytes(rows <= 2 ? rows : 1));
   }
   w.bytes = off;
   return w;
@@ -368,8 +370,19 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     const char* tc = getenv("VAURA_PERSIST_TC");
     const bool use_tc = (tc && tc[0] == '1') && w.wqkv_t && w.wo_t && w.w13_t && w.w2_t && w.w_heads_t &&
                         persistent_tc_supported(rows, d.d_model, d.ffn_dim, kv->page_size, K * d.vocab / 2, d.ffn_dim, sms);
+    // rows <= 2: cluster variant (decode_cluster.cu) when the per-CTA weight streams were packed
+    const char* nocl = getenv("VAURA_NO_CLUSTER");
+    const bool use_cluster = !use_tc && w.wstream && !(nocl && nocl[0] == '1') &&
+                             cluster_supported(rows, d.num_layers, d.d_model, d.ffn_dim, d.nhead, K * d.vocab, kv->page_size,
+                                               d.cond_dim, S);
+    if (use_cluster) {
+      pa.wstream = w.wstream;
+      pa.xfix = ws.xfix;
+      CU(cudaMemsetAsync(ws.xfix, 0, cluster_xfix_bytes(rows), st));
+    }
     for (int i = 0; i < nsteps; ++i) {
-      if (use_tc) CUL(launch_decode_persistent_tc(pa, rows, st));
+      if (use_cluster) CUL(launch_decode_cluster(pa, rows, st));
+      else if (use_tc) CUL(launch_decode_persistent_tc(pa, rows, st));
       else CUL(launch_decode_persistent(pa, rows, st));
     }
     return VAURA_OK;

@@ -1,0 +1,842 @@
+// Cluster-persistent decode-step kernel for the HBM-bound small-batch regime (rows <= 2, fp32-exact activations).
+//
+// 32 clusters x 4 CTAs (one CTA per SM, 128 SMs; a B200 co-schedules at most 15 clusters of 8 but 33 of 4, see
+// profiles/probes/cluster_occ.cu) run the WHOLE decode step.  Attention head h is served by the two clusters 2h, 2h+1:
+// both compute q|k|v and the attention of head h (same bytes, read from HBM once and from L2 the second time) so that
+// no attention data ever crosses a cluster; everything else is partitioned without overlap:
+//
+//   layer l:  x -> [RMSNorm . wqkv rows of head h, K split over the 4 CTAs] -> DSMEM reduce-scatter + RoPE + KV append
+//               + all-gather -> attention of head h (positions split over the CTAs, partials combined through DSMEM)
+//               -> wo[768s + 192r .. +192, head h]  -> 64-bit fixed-point red.add into the residual    | grid barrier
+//             x -> [RMSNorm . w1|w3 of 32 hidden units per CTA] -> SiLU*mul -> DSMEM all-gather of the cluster's 128
+//               -> w2[384r .. +384, units of the cluster] -> fixed-point red.add                         | grid barrier
+//
+// so a layer costs two device-wide barriers (the kernel it replaces, decode_persistent.cu, needs five) and four
+// cluster-local ones.  The residual stream lives in three rotating [rows][1536] buffers of 2^-32 fixed-point int64:
+// integer adds commute, so the result does not depend on the order in which the clusters arrive (bit-reproducible);
+// each phase reads buffer n, accumulates into n+1 and clears n+2.
+//
+// Weights: a producer thread copies the CTA's weights with cp.async.bulk into a ring of 12 KB shared-memory slots; a
+// slot holds two 16x16 bf16 tiles for each of the 12 compute warps, stored in the register order of the
+// mma.sync.m16n8k16 A fragment (one conflict-free LDS.128 per tile per lane).  The bytes come from two strictly
+// sequential streams (vaura_b200/weights.py: pack_cluster_stream): the q|k|v stream shared by the two clusters of a
+// head and the CTA's private stream.  Slots are grouped into units of 3 or 4 with one full/empty mbarrier pair each
+// (13 units = 45 slots per layer); the producer runs ahead of the consumers through barriers, attention and staging.
+//
+// Arithmetic: activations stay fp32-exact.  An fp32 value is split into three bf16 terms (hi, mid, lo; 8+8+8 mantissa
+// bits) that occupy three of the eight B-operand columns of mma.sync.m16n8k16 (two sequence rows use six); products of
+// bf16 values are exact in fp32 and the tensor core accumulates in fp32, so the result equals an fp32 dot product up
+// to summation order.  The three column sums are added in the epilogue.
+//
+// Replaces the same reference lines as decode_persistent.cu (llama.py:445-517 for one position, vaura_model.py:775-827).
+#include <cstdlib>
+
+#include "sampling.cuh"
+
+namespace vaura {
+
+namespace {
+
+constexpr int CW = 12;                     // compute warps
+constexpr int kCT = CW * 32;               // 384 compute threads
+constexpr int kThreadsC = kCT + 32;        // + one producer warp
+constexpr int CL = 4;                      // CTAs per cluster
+constexpr int NCL = 32;                    // clusters; head = cluster / 2
+constexpr int SLOT = 12288;                // ring slot: 12 warps x 2 tiles x 512 B
+constexpr int DM = 1536, FF = 4096, NHEAD = 16;
+constexpr int QROWS = 3 * kHeadDim;        // 288 q|k|v rows of one head (18 row tiles); K slice per CTA = 384 (24 k-tiles)
+constexpr int QOWN = QROWS / CL;           // 72 rows reduced by each CTA
+constexpr int HROWS = 288;                 // heads rows per cluster (9 * 1024 / 32)
+constexpr int HOWN = HROWS / CL;           // 72
+constexpr int HU = FF / NCL;               // 128 hidden units per cluster
+constexpr int HUC = HU / CL;               // 32 hidden units per CTA
+constexpr int WO_ROWS = 192;               // wo rows per CTA: [768 s + 192 r, +192)
+constexpr int W2_ROWS = DM / CL;           // 384 w2 rows per CTA
+constexpr int UNITS_PER_LAYER = 13;        // 6 qkv (3 slots) + 1 wo (3) + 4 w13 (4) + 2 w2 (4) = 45 slots
+constexpr int QKV_SLOTS = 18, PRIV_SLOTS = 27, HEAD_SLOTS = 18;
+constexpr int HEAD_UNITS = 6;
+constexpr int MAXIT = 5;                   // attention items (positions) per warp: 4 CTAs x 12 warps x 5 = 240 old positions
+constexpr int WP_STRIDE = 100;             // floats per attention partial: m, l, pad, pad, o[96]
+constexpr float kFixScale = 4294967296.0f; // residual stream fixed point: 2^-32
+constexpr float kFixInv = 2.3283064365386963e-10f;
+
+template <int NB>
+struct Lay {
+  static constexpr int nslot = NB == 1 ? 15 : 14;
+  static constexpr int ring = 0;
+  static constexpr int bx = ring + nslot * SLOT;            // B fragments of the normed residual [96 k-tiles][32][2] u32
+  static constexpr int bs = bx + 96 * 256;                  // B fragments of attn out (6 k-tiles) / hidden (8 k-tiles)
+  static constexpr int ra = bs + 8 * 256;                   // alias group A (CTA-local scratch):
+  static constexpr int ra_bytes = CW * NB * WP_STRIDE * 4;  //   attention partials of the 12 warps [12][NB][100]
+  static constexpr int halves = ra;                         //   qkv / heads K halves [2][288][NB] f32
+  static constexpr int rs_recv = ra + 2 * QROWS * NB * 4;   //   reduce-scatter target [4][72][NB] f32 (remote-written)
+  static constexpr int rb = ra + ra_bytes;                  // attention partials of the 4 CTAs [4][NB][100] (remote-written)
+  static constexpr int rb_bytes = CL * NB * WP_STRIDE * 4;
+  static constexpr int qkv = rb + rb_bytes;                 // [NB][288] f32 (remote-written all-gather)
+  static constexpr int hrecv = qkv + NB * QROWS * 4;        // [NB][128] f32 (remote-written all-gather)
+  static constexpr int xown = hrecv + NB * HU * 4;          // [NB][384] f32: this CTA's rows of the phase input
+  static constexpr int red = xown + NB * W2_ROWS * 4;       // [12][NB] f32
+  static constexpr int rope = red + 128;                    // [96] f32
+  static constexpr int bars = rope + kHeadDim * 4;          // full[13], empty[13], cbar
+  static constexpr int sargs = bars + 32 * 8;               // SampleArgs copy
+  static constexpr int total = sargs + 256;
+  static_assert(2 * QROWS * NB * 4 + CL * QOWN * NB * 4 <= ra_bytes, "qkv halves + reduce-scatter target fit alias group A");
+  static_assert(CW * 64 * NB * 4 <= ra_bytes, "w13 partials fit alias group A");
+  static_assert(sizeof(SampleArgs) <= 256, "SampleArgs copy");
+  static_assert(total <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mb_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mb_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mb_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t now_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr uint64_t kSpinTimeoutNs = 2000000000ull;  // a protocol bug traps (-> CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
+  if (mb_try_wait(bar, parity)) return;
+  const uint64_t t0 = now_ns();
+  while (!mb_try_wait(bar, parity))
+    if (now_ns() - t0 > kSpinTimeoutNs) __trap();
+}
+__device__ __forceinline__ void mb_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mb_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = now_ns();
+  while (!mb_try_wait_cluster(bar, parity))
+    if (now_ns() - t0 > kSpinTimeoutNs) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// device-wide barrier among the compute threads of all CTAs (co-resident: one CTA per SM, checked at launch)
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  consumer_sync();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    if ((int)(ld_acquire(counter) - target) < 0) {
+      const uint64_t t0 = now_ns();
+      while ((int)(ld_acquire(counter) - target) < 0)
+        if (now_ns() - t0 > kSpinTimeoutNs) __trap();
+    }
+  }
+  consumer_sync();
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void hw_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// cluster-wide barrier of the compute threads: bar.sync orders this CTA's DSMEM stores before the remote arrivals
+// (release at cluster scope); every compute thread then waits on the CTA's own mbarrier (acquire at cluster scope)
+__device__ __forceinline__ void cluster_barrier(uint32_t cbar, uint32_t& phase) {
+  consumer_sync();
+  if (threadIdx.x < CL) {
+    const uint32_t remote = mapa_u32(cbar, threadIdx.x);
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  }
+  mb_wait_cluster(cbar, phase);
+  phase ^= 1u;
+}
+
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint4& a, const uint2& b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y));
+}
+
+__device__ __forceinline__ long long f2fix(float v) { return __float2ll_rn(v * kFixScale); }
+__device__ __forceinline__ float fix2f(long long v) { return __ll2float_rn(v) * kFixInv; }
+__device__ __forceinline__ void red_add_fix(long long* p, long long v) {
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// fp32 -> (hi, mid, lo) bf16 bit patterns with hi + mid + lo == v exactly (round-to-nearest residuals)
+__device__ __forceinline__ void split3(float v, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(h);
+  const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(m);
+  const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+  hi = __bfloat16_as_ushort(h); mid = __bfloat16_as_ushort(m); lo = __bfloat16_as_ushort(l);
+}
+// B-fragment address (bytes from the fragment array base) of element (k, column n): mma.m16n8k16 .col B operand,
+// lane = n*4 + (k%8)/2, register (k%16)/8, half k%2
+__device__ __forceinline__ uint32_t bfrag_off(int k, int n) {
+  const int kk = k & 15;
+  return (uint32_t)(((k >> 4) * 32 + n * 4 + ((kk & 7) >> 1)) * 8 + (kk >> 3) * 4 + (kk & 1) * 2);
+}
+// stage the pair (v0, v1) = elements (k, k+1), k even, of sequence row b into B fragments (three split columns)
+__device__ __forceinline__ void stage_pair(uint8_t* base, int k, int b, float v0, float v1) {
+  uint32_t h0, m0, l0, h1, m1, l1;
+  split3(v0, h0, m0, l0);
+  split3(v1, h1, m1, l1);
+  *reinterpret_cast<uint32_t*>(base + bfrag_off(k, 3 * b + 0)) = h0 | (h1 << 16);
+  *reinterpret_cast<uint32_t*>(base + bfrag_off(k, 3 * b + 1)) = m0 | (m1 << 16);
+  *reinterpret_cast<uint32_t*>(base + bfrag_off(k, 3 * b + 2)) = l0 | (l1 << 16);
+}
+__device__ __forceinline__ void stage_one(uint8_t* base, int k, int b, float v) {
+  uint32_t h, m, l;
+  split3(v, h, m, l);
+  *reinterpret_cast<uint16_t*>(base + bfrag_off(k, 3 * b + 0)) = (uint16_t)h;
+  *reinterpret_cast<uint16_t*>(base + bfrag_off(k, 3 * b + 1)) = (uint16_t)m;
+  *reinterpret_cast<uint16_t*>(base + bfrag_off(k, 3 * b + 2)) = (uint16_t)l;
+}
+
+// accumulator fragment (rows g, g+8; columns 2t, 2t+1) -> out[half][b] = sum of the three split columns of sequence
+// row b, valid in all four lanes of the quad
+template <int NB>
+__device__ __forceinline__ void quad_reduce(const float (&c)[4], int tq, float (&out)[2][NB]) {
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const float ca = c[2 * hf], cb = c[2 * hf + 1];
+    float s0 = tq == 0 ? ca + cb : (tq == 1 ? ca : 0.f);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    out[hf][0] = s0;
+    if (NB == 2) {
+      float s1 = tq == 1 ? cb : (tq == 2 ? ca + cb : 0.f);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      out[hf][NB - 1] = s1;
+    }
+  }
+}
+
+}  // namespace
+
+template <int NB>
+__global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid_constant__ PersistArgs a) {
+  using LY = Lay<NB>;
+  constexpr int NSLOT = LY::nslot;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x, G = gridDim.x;
+  const int rank = (int)cluster_rank();
+  const int cl = cta / CL;                // cluster
+  const int head = cl >> 1, sh = cl & 1;  // attention head, which half of the wo rows
+  const uint32_t sbase = s_u32(smem);
+  const uint32_t full0 = sbase + LY::bars, empty0 = full0 + UNITS_PER_LAYER * 8, cbar = empty0 + UNITS_PER_LAYER * 8;
+  const int L = a.L;
+
+  if (tid == 0) {
+    for (int i = 0; i < UNITS_PER_LAYER; ++i) { mb_init(full0 + 8 * i, 1); mb_init(empty0 + 8 * i, CW); }
+    mb_init(cbar, CL);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *reinterpret_cast<SampleArgs*>(smem + LY::sargs) = a.sample;
+  }
+  // zero the B-fragment arrays once: the unused columns must stay zero
+  for (int i = tid; i < (96 + 8) * 256 / 16; i += kThreadsC)
+    reinterpret_cast<uint4*>(smem + LY::bx)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  hw_cluster_sync();  // every CTA of the cluster has initialised its barriers before any remote arrive / store
+
+  if (warp == CW) {
+    // ------------------------------- producer: the CTA's two weight streams -------------------------------
+    if (lane == 0) {
+      uint64_t pol_first, pol_last;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+      // q|k|v stream of (head, rank): read by this CTA and by its twin in the other cluster of the head
+      const uint8_t* qsrc = a.wstream + (size_t)(head * CL + rank) * L * QKV_SLOTS * SLOT;
+      const uint8_t* psrc = a.wstream + (size_t)NHEAD * CL * L * QKV_SLOTS * SLOT +
+                            (size_t)cta * ((size_t)L * PRIV_SLOTS + HEAD_SLOTS) * SLOT;
+      const int nq_layers = UNITS_PER_LAYER * L, NQ = nq_layers + HEAD_UNITS;
+      int rel = 0;       // units whose release by the 12 compute warps has been observed (in order)
+      int freed = 0;     // ring slots of those units
+      int issued = 0;    // ring slots handed to the copy engine so far
+      int wslot = 0;     // ring position of the next slot
+      for (int q = 0; q < NQ; ++q) {
+        const int i = q < nq_layers ? q % UNITS_PER_LAYER : q - nq_layers;
+        const bool is_q = q < nq_layers && i < 6;
+        const int n = (q >= nq_layers || i < 7) ? 3 : 4;
+        while (issued + n - freed > NSLOT) {
+          const int ri = rel < nq_layers ? rel % UNITS_PER_LAYER : rel - nq_layers;
+          const int ru = rel < nq_layers ? rel / UNITS_PER_LAYER : L;
+          mb_wait(empty0 + 8 * ri, ru & 1);
+          freed += (rel >= nq_layers || ri < 7) ? 3 : 4;
+          ++rel;
+        }
+        mb_expect_tx(full0 + 8 * i, (uint32_t)n * SLOT);
+        for (int s = 0; s < n; ++s) {
+          if (is_q) { bulk_g2s(sbase + LY::ring + wslot * SLOT, qsrc, SLOT, full0 + 8 * i, pol_last); qsrc += SLOT; }
+          else { bulk_g2s(sbase + LY::ring + wslot * SLOT, psrc, SLOT, full0 + 8 * i, pol_first); psrc += SLOT; }
+          wslot = wslot + 1 == NSLOT ? 0 : wslot + 1;
+        }
+        issued += n;
+      }
+    }
+  } else {
+    // ------------------------------------------- compute warps -------------------------------------------
+    const int gq = lane >> 2, tq = lane & 3;
+    const int offset = a.state->offset;
+    const unsigned epoch = a.state->epoch;
+    const int p = offset - 1;  // position fed by this step
+    const unsigned nbar = (unsigned)(2 * L + 1);
+    unsigned bar_i = 0;
+    uint32_t cphase = 0;
+    int rslot = 0;  // ring position of the next slot to consume
+    float* red = reinterpret_cast<float*>(smem + LY::red);
+    float* rope_s = reinterpret_cast<float*>(smem + LY::rope);
+    float* xown = reinterpret_cast<float*>(smem + LY::xown);
+    float* qkv_s = reinterpret_cast<float*>(smem + LY::qkv);
+    const uint32_t aring = sbase + LY::ring + warp * 1024 + lane * 16;
+    const uint32_t abx = sbase + LY::bx + lane * 8, abs_ = sbase + LY::bs + lane * 8;
+    // address of tile t of the s-th slot after the ring cursor
+    auto tile_addr = [&](int s, int t) {
+      int sl = rslot + s;
+      if (sl >= NSLOT) sl -= NSLOT;
+      return aring + sl * SLOT + t * 512;
+    };
+    auto advance = [&](int n) { rslot += n; if (rslot >= NSLOT) rslot -= NSLOT; };
+
+    int stamp_i = 0;
+    auto stamp = [&]() {
+      if (a.timing && cta == 0 && tid == 0) a.timing[stamp_i] = now_ns();
+      ++stamp_i;
+    };
+    stamp();
+
+    if (tid < kHeadDim) rope_s[tid] = a.rope[(size_t)p * kHeadDim + tid];
+
+    // attention work split: old positions [0, p) in four chunks, one per CTA; warp w takes items w, w+12, ...
+    const int chunk = (p + CL - 1) / CL;
+    const int j0 = rank * chunk, j1 = min(p, j0 + chunk);
+    int koff[MAXIT][NB];
+    bool kvalid[MAXIT];
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int j = j0 + warp + CW * it;
+      kvalid[it] = j < j1;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const int page = kvalid[it] ? a.kv.page_table[b * a.kv.max_pages_per_seq + j / a.kv.page_size] : 0;
+        koff[it][b] = ((page * a.kv.nhead + head) * a.kv.page_size + (j % a.kv.page_size)) * kHeadDim + 4 * lane;
+      }
+    }
+    const size_t kv_half = (size_t)a.kv.num_pages * a.kv.nhead * a.kv.page_size * kHeadDim;  // floats of K (or V) per layer
+    const bool new_warp = rank == CL - 1 && warp == CW - 1;  // takes the position written by this step
+    const float* kvbase = reinterpret_cast<const float*>(a.kv.pages);
+    constexpr bool kEarlyV = NB == 1;  // two rows: V is fetched after the QKV phase (register budget)
+
+    // x = phase input; loads 4 consecutive features per thread and sequence row, stages x * norm_w as B fragments,
+    // keeps rows [own0, own0 + ownn) for the residual add, leaves rstd in rstd[]
+    float rstd[NB];
+    auto stage_x = [&](auto load4, const float* norm_w, int own0, int ownn) {
+      float ss[NB];
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(norm_w) + tid);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float4 v = load4(b);
+        ss[b] = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        if (4 * tid >= own0 && 4 * tid < own0 + ownn) *reinterpret_cast<float4*>(xown + b * W2_ROWS + (4 * tid - own0)) = v;
+        stage_pair(smem + LY::bx, 4 * tid, b, v.x * g4.x, v.y * g4.y);
+        stage_pair(smem + LY::bx, 4 * tid + 2, b, v.z * g4.z, v.w * g4.w);
+        ss[b] = warp_sum(ss[b]);
+        if (lane == 0) red[warp * NB + b] = ss[b];
+      }
+      consumer_sync();
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < CW; ++w) tot += red[w * NB + b];
+        rstd[b] = rsqrtf(tot / (float)DM + a.eps);
+      }
+    };
+    auto load_fix = [&](const long long* buf) {
+      return [=](int b) {
+        const longlong2 u0 = __ldcg(reinterpret_cast<const longlong2*>(buf + (size_t)b * DM + 4 * tid));
+        const longlong2 u1 = __ldcg(reinterpret_cast<const longlong2*>(buf + (size_t)b * DM + 4 * tid) + 1);
+        return make_float4(fix2f(u0.x), fix2f(u0.y), fix2f(u1.x), fix2f(u1.y));
+      };
+    };
+    // embedding (llama.py:455-472): conditioning row | sum of the 9 folded token tables
+    auto load_embed = [&](int b) {
+      const int C = a.cond_dim, TD = DM - C, i = 4 * tid;
+      if (i < C) {
+        int vrow = p / a.atpvf;
+        if (vrow > a.cond_tokens) vrow = a.cond_tokens;
+        return __ldg(reinterpret_cast<const float4*>(a.cond_rows + ((size_t)b * (a.cond_tokens + 1) + vrow) * C + i));
+      }
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int bt = b % a.batch;
+      for (int k = 0; k < a.Kc; ++k) {
+        const int tok = a.seq[((size_t)bt * a.Kc + k) * a.S + p];
+        const float4 t = __ldg(reinterpret_cast<const float4*>(a.tok_tables + ((size_t)k * (a.V + 1) + tok) * TD + (i - C)));
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+      }
+      return v;
+    };
+    auto xbuf = [&](int n) { return a.xfix + (size_t)(n % 3) * NB * DM; };  // rotating residual buffers
+    auto clear_slice = [&](long long* buf) {  // this CTA's share of the buffer the phase after next accumulates into
+      if (tid < NB * DM / (CL * NCL)) buf[cta * (NB * DM / (CL * NCL)) + tid] = 0;
+    };
+    // output rows [row0 + 16 rt, +16) of a residual phase: add the partial (and, where `carry`, the phase input)
+    auto resid_add = [&](const float (&acc)[4], long long* dst, int row0, int rt, bool carry) {
+      float o[2][NB];
+      quad_reduce<NB>(acc, tq, o);
+      if (tq < NB) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int rl = 16 * rt + gq + 8 * hf;
+          float v = tq == 0 ? o[hf][0] : o[hf][NB - 1];
+          if (carry) v += xown[tq * W2_ROWS + rl];
+          red_add_fix(dst + (size_t)tq * DM + row0 + rl, f2fix(v));
+        }
+      }
+    };
+    // K-split GEMV of 288 rows (18 row tiles) x this CTA's 384 features: 6 units of 3 slots; warp (rh, kq) owns row
+    // tiles 3rh..3rh+2 and k-tiles 12kq..12kq+11.  Leaves the cluster-reduced rows [72 rank, +72) in rs_recv[4][72][NB]
+    auto ksplit_288 = [&](int use) {
+      const int rh = warp >> 1, kq = warp & 1;
+      float* halves = reinterpret_cast<float*>(smem + LY::halves);
+#pragma unroll
+      for (int rt = 0; rt < 3; ++rt) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int hk = 0; hk < 2; ++hk) {
+          const int u = 2 * rt + hk;
+          uint2 bq[6];
+#pragma unroll
+          for (int kk = 0; kk < 6; ++kk) bq[kk] = lds_u2(abx + (24 * rank + 12 * kq + 6 * hk + kk) * 256);
+          mb_wait(full0 + 8 * u, (uint32_t)use & 1u);
+          uint4 A[6];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
+#pragma unroll
+          for (int j = 0; j < 6; ++j) mma16816(acc, A[j], bq[j]);
+          __syncwarp();
+          if (lane == 0) mb_arrive(empty0 + 8 * u);
+          advance(3);
+        }
+        float o[2][NB];
+        quad_reduce<NB>(acc, tq, o);
+        if (tq < NB) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf)
+            halves[(kq * QROWS + 16 * (3 * rh + rt) + gq + 8 * hf) * NB + tq] = tq == 0 ? o[hf][0] : o[hf][NB - 1];
+        }
+      }
+      consumer_sync();
+      // reduce-scatter: row i goes to CTA i / 72
+      for (int e = tid; e < QROWS * NB; e += kCT) {
+        const int i = e / NB, b = e % NB;
+        const float v = halves[e] + halves[QROWS * NB + e];
+        st_cluster_f32(mapa_u32(sbase + LY::rs_recv + ((rank * QOWN + i % QOWN) * NB + b) * 4, i / QOWN), v);
+      }
+      cluster_barrier(cbar, cphase);
+    };
+
+    for (int l = 0; l < L; ++l) {
+      const uint32_t par = (uint32_t)l & 1u;
+      long long* x_in = xbuf(2 * l);
+      long long* x_mid = xbuf(2 * l + 1);
+      long long* x_out = xbuf(2 * l + 2);
+
+      // ---- K/V rows of this head's old positions: issued now, consumed after the QKV exchange ----
+      float4 kreg[MAXIT][NB], vreg[MAXIT][NB];
+      const float* kl = kvbase + (size_t)l * 2 * kv_half;
+#pragma unroll
+      for (int it = 0; it < MAXIT; ++it)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          kreg[it][b] = make_float4(0.f, 0.f, 0.f, 0.f);
+          vreg[it][b] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kvalid[it] && lane < 24) {
+            kreg[it][b] = __ldcg(reinterpret_cast<const float4*>(kl + koff[it][b]));
+            if (kEarlyV) vreg[it][b] = __ldcg(reinterpret_cast<const float4*>(kl + kv_half + koff[it][b]));
+          }
+        }
+
+      // ================= attention block: RMSNorm . wqkv rows of head `head`, K split over the 4 CTAs =================
+      clear_slice(x_out);
+      if (l == 0) stage_x(load_embed, a.attn_norm, 768 * sh + WO_ROWS * rank, WO_ROWS);
+      else stage_x(load_fix(x_in), a.attn_norm + (size_t)l * DM, 768 * sh + WO_ROWS * rank, WO_ROWS);
+      stamp();
+      ksplit_288(l);
+      {
+        // owner of 72 rows: sum the 4 K slices, apply rstd and RoPE (llama.py:633-650), append K/V, all-gather
+        const bool own = tid < QOWN * NB;
+        float y = 0.f;
+        if (own) {
+          const int ii = tid / NB, b = tid % NB;
+          const float* rr = reinterpret_cast<const float*>(smem + LY::rs_recv);
+#pragma unroll
+          for (int s = 0; s < CL; ++s) y += rr[(s * QOWN + ii) * NB + b];
+          y *= rstd[b];
+        }
+        const float other = __shfl_xor_sync(0xffffffffu, y, NB);  // partner of the RoPE pair (rows 2m, 2m+1)
+        if (own) {
+          const int ii = tid / NB, b = tid % NB;
+          const int i = rank * QOWN + ii, sec = i / kHeadDim, e = i % kHeadDim;
+          float o = y;
+          if (sec != 2) {
+            const float cs = rope_s[e & ~1], sn = rope_s[(e & ~1) + 1];
+            o = (e & 1) ? y * cs + other * sn : y * cs - other * sn;
+          }
+          if (sec != 0 && sh == 0) {  // the twin cluster computes the same values: one of them appends
+            const int page = a.kv.page_table[b * a.kv.max_pages_per_seq + p / a.kv.page_size];
+            float* dstp = reinterpret_cast<float*>(a.kv.pages) + (size_t)l * 2 * kv_half + (size_t)(sec - 1) * kv_half +
+                          ((size_t)(page * a.kv.nhead + head) * a.kv.page_size + (p % a.kv.page_size)) * kHeadDim + e;
+            *dstp = o;
+          }
+          const uint32_t local = sbase + LY::qkv + (b * QROWS + i) * 4;
+#pragma unroll
+          for (int s = 0; s < CL; ++s) st_cluster_f32(mapa_u32(local, s), o);
+        }
+        cluster_barrier(cbar, cphase);
+      }
+      stamp();
+
+      // ================= attention of head `head`: positions split over the CTAs =================
+      {
+        if (!kEarlyV) {
+#pragma unroll
+          for (int it = 0; it < MAXIT; ++it)
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+              if (kvalid[it] && lane < 24) vreg[it][b] = __ldcg(reinterpret_cast<const float4*>(kl + kv_half + koff[it][b]));
+        }
+        float* wp = reinterpret_cast<float*>(smem + LY::ra);  // [12][NB][100]
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const float4 q4 = lane < 24 ? *reinterpret_cast<const float4*>(qkv_s + b * QROWS + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float sc[MAXIT + 1];
+#pragma unroll
+          for (int it = 0; it < MAXIT; ++it) {
+            const float4 k4 = kreg[it][b];
+            const float d = warp_sum(k4.x * q4.x + k4.y * q4.y + k4.z * q4.z + k4.w * q4.w);
+            sc[it] = kvalid[it] ? d * a.scale : -INFINITY;
+          }
+          float4 vn = make_float4(0.f, 0.f, 0.f, 0.f);
+          sc[MAXIT] = -INFINITY;
+          if (new_warp) {
+            float4 kn = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < 24) {
+              kn = *reinterpret_cast<const float4*>(qkv_s + b * QROWS + kHeadDim + 4 * lane);
+              vn = *reinterpret_cast<const float4*>(qkv_s + b * QROWS + 2 * kHeadDim + 4 * lane);
+            }
+            sc[MAXIT] = warp_sum(kn.x * q4.x + kn.y * q4.y + kn.z * q4.z + kn.w * q4.w) * a.scale;
+          }
+          float m = sc[MAXIT];
+#pragma unroll
+          for (int it = 0; it < MAXIT; ++it) m = fmaxf(m, sc[it]);
+          float lsum = 0.f;
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m > -INFINITY) {
+#pragma unroll
+            for (int it = 0; it <= MAXIT; ++it) {
+              const float e = sc[it] > -INFINITY ? expf(sc[it] - m) : 0.f;
+              const float4 v4 = it < MAXIT ? vreg[it < MAXIT ? it : 0][b] : vn;
+              lsum += e;
+              o.x = fmaf(e, v4.x, o.x); o.y = fmaf(e, v4.y, o.y); o.z = fmaf(e, v4.z, o.z); o.w = fmaf(e, v4.w, o.w);
+            }
+          }
+          float* w = wp + (warp * NB + b) * WP_STRIDE;
+          if (lane == 0) { w[0] = m; w[1] = lsum; }
+          if (lane < 24) *reinterpret_cast<float4*>(w + 4 + 4 * lane) = o;
+        }
+        consumer_sync();
+        // CTA partial -> every CTA of the cluster
+        if (tid < kHeadDim * NB) {
+          const int b = tid / kHeadDim, d = tid % kHeadDim;
+          float M = -INFINITY;
+#pragma unroll
+          for (int w = 0; w < CW; ++w) M = fmaxf(M, wp[(w * NB + b) * WP_STRIDE]);
+          float Ls = 0.f, O = 0.f;
+          if (M > -INFINITY) {
+#pragma unroll
+            for (int w = 0; w < CW; ++w) {
+              const float mw = wp[(w * NB + b) * WP_STRIDE];
+              const float f = mw > -INFINITY ? expf(mw - M) : 0.f;
+              Ls = fmaf(f, wp[(w * NB + b) * WP_STRIDE + 1], Ls);
+              O = fmaf(f, wp[(w * NB + b) * WP_STRIDE + 4 + d], O);
+            }
+          }
+          const uint32_t local = sbase + LY::rb + ((rank * NB + b) * WP_STRIDE) * 4;
+#pragma unroll
+          for (int s = 0; s < CL; ++s) {
+            const uint32_t rbase = mapa_u32(local, s);
+            st_cluster_f32(rbase + (4 + d) * 4, O);
+            if (d == 0) { st_cluster_f32(rbase, M); st_cluster_f32(rbase + 4, Ls); }
+          }
+        }
+        cluster_barrier(cbar, cphase);
+        if (tid < kHeadDim * NB) {
+          const int b = tid / kHeadDim, d = tid % kHeadDim;
+          const float* ar = reinterpret_cast<const float*>(smem + LY::rb);
+          float M = -INFINITY;
+#pragma unroll
+          for (int s = 0; s < CL; ++s) M = fmaxf(M, ar[(s * NB + b) * WP_STRIDE]);
+          float den = 0.f, O = 0.f;
+#pragma unroll
+          for (int s = 0; s < CL; ++s) {
+            const float ms = ar[(s * NB + b) * WP_STRIDE];
+            const float f = ms > -INFINITY ? expf(ms - M) : 0.f;
+            den = fmaf(f, ar[(s * NB + b) * WP_STRIDE + 1], den);
+            O = fmaf(f, ar[(s * NB + b) * WP_STRIDE + 4 + d], O);
+          }
+          stage_one(smem + LY::bs, d, b, O / den);
+        }
+        consumer_sync();
+      }
+      stamp();
+
+      // ============ wo[768 sh + 192 rank .. +192, head]; warp w owns row tile w; residual into x_mid ============
+      {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        mb_wait(full0 + 8 * 6, par);
+        uint4 A[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
+#pragma unroll
+        for (int j = 0; j < 6; ++j) mma16816(acc, A[j], lds_u2(abs_ + j * 256));
+        __syncwarp();
+        if (lane == 0) mb_arrive(empty0 + 8 * 6);
+        advance(3);
+        resid_add(acc, x_mid, 768 * sh + WO_ROWS * rank, warp, head == 0);
+      }
+      stamp();
+      grid_barrier(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
+      stamp();
+
+      // ============ MLP: RMSNorm . w1|w3 of this CTA's 32 hidden units (K split over the 12 warps) ============
+      clear_slice(x_in);
+      stage_x(load_fix(x_mid), a.ffn_norm + (size_t)l * DM, W2_ROWS * rank, W2_ROWS);
+      stamp();
+      {
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[r][e] = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint2 b0 = lds_u2(abx + (8 * warp + 2 * u) * 256), b1 = lds_u2(abx + (8 * warp + 2 * u + 1) * 256);
+          mb_wait(full0 + 8 * (7 + u), par);
+          uint4 A[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mma16816(acc[j & 3], A[j], (j >> 2) ? b1 : b0);
+          __syncwarp();
+          if (lane == 0) mb_arrive(empty0 + 8 * (7 + u));
+          advance(4);
+        }
+        float* part = reinterpret_cast<float*>(smem + LY::ra);  // [12][64][NB]
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float o[2][NB];
+          quad_reduce<NB>(acc[r], tq, o);
+          if (tq < NB) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+              part[(warp * 64 + 16 * r + gq + 8 * hf) * NB + tq] = tq == 0 ? o[hf][0] : o[hf][NB - 1];
+          }
+        }
+        consumer_sync();
+        if (tid < HUC * NB) {  // hidden unit u of this CTA: rows 16R+g (w1) and 16R+8+g (w3), R = u / 8, g = u % 8
+          const int u = tid / NB, b = tid % NB;
+          const int r1 = 16 * (u >> 3) + (u & 7), r3 = r1 + 8;
+          float y1 = 0.f, y3 = 0.f;
+#pragma unroll
+          for (int w = 0; w < CW; ++w) { y1 += part[(w * 64 + r1) * NB + b]; y3 += part[(w * 64 + r3) * NB + b]; }
+          y1 *= rstd[b]; y3 *= rstd[b];
+          const float hv = y1 / (1.f + expf(-y1)) * y3;
+          const uint32_t local = sbase + LY::hrecv + (b * HU + rank * HUC + u) * 4;
+#pragma unroll
+          for (int s = 0; s < CL; ++s) st_cluster_f32(mapa_u32(local, s), hv);
+        }
+        cluster_barrier(cbar, cphase);
+        if (tid < HU * NB / 2) {
+          const int b = tid / (HU / 2), k = 2 * (tid % (HU / 2));
+          const float2 v = *reinterpret_cast<const float2*>(smem + LY::hrecv + (b * HU + k) * 4);
+          stage_pair(smem + LY::bs, k, b, v.x, v.y);
+        }
+        consumer_sync();
+      }
+      stamp();
+      // ==== w2[384 rank .. +384, hidden units of the cluster]; warp w owns row tiles 2w, 2w+1; residual into x_out ====
+      {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          mb_wait(full0 + 8 * (11 + u), par);
+          uint4 A[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mma16816(acc, A[j], lds_u2(abs_ + j * 256));
+          __syncwarp();
+          if (lane == 0) mb_arrive(empty0 + 8 * (11 + u));
+          advance(4);
+          resid_add(acc, x_out, W2_ROWS * rank, 2 * warp + u, cl == 0);
+        }
+      }
+      stamp();
+      grid_barrier(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
+      stamp();
+    }
+
+    // ============ final norm + heads: the cluster owns rows [288 cl, +288), K split over its CTAs ============
+    {
+      stage_x(load_fix(xbuf(2 * L)), a.final_norm, 0, 0);
+      ksplit_288(L);
+      if (tid < HOWN * NB) {
+        const int ii = tid / NB, b = tid % NB;
+        const float* rr = reinterpret_cast<const float*>(smem + LY::rs_recv);
+        float y = 0.f;
+#pragma unroll
+        for (int s = 0; s < CL; ++s) y += rr[(s * HOWN + ii) * NB + b];
+        a.logits[(size_t)b * (a.Kc * a.V) + cl * HROWS + rank * HOWN + ii] = y * rstd[b];
+      }
+      stamp();
+      grid_barrier(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
+      stamp();
+    }
+
+    // ============ CFG / sampling / mask-fix / write-back: one warp per (clip, codebook) ============
+    {
+      const SampleArgs& sa = *reinterpret_cast<const SampleArgs*>(smem + LY::sargs);
+      const int nrows = sa.B * sa.K;
+      for (int u = cta + G * warp; u < nrows; u += G * CW) sample_row(sa, u / sa.K, u % sa.K, lane, offset);
+    }
+    stamp();
+    if (cta == 0 && tid == 0) {  // every CTA read offset/epoch before its first barrier arrival
+      a.state->offset = offset + 1;
+      a.state->epoch = epoch + 1;
+    }
+  }
+  __syncwarp();
+  hw_cluster_sync();  // no CTA exits while a peer may still address its shared memory
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+size_t cluster_stream_bytes(int L) {
+  return ((size_t)NHEAD * CL * L * QKV_SLOTS + (size_t)NCL * CL * ((size_t)L * PRIV_SLOTS + HEAD_SLOTS)) * SLOT;
+}
+
+bool cluster_supported(int rows, int L, int D, int F, int H, int head_rows, int page_size, int cond_dim, int max_ctx) {
+  if (rows != 1 && rows != 2) return false;
+  if (D != DM || F != FF || H != NHEAD || head_rows != NCL * HROWS) return false;
+  if (page_size != 32 || L < 1) return false;
+  if (cond_dim % 4 || cond_dim <= 0 || cond_dim >= DM) return false;
+  if ((max_ctx + CL - 1) / CL > MAXIT * CW) return false;  // attention items per warp
+  return true;
+}
+
+size_t cluster_xfix_bytes(int rows) { return (size_t)3 * rows * DM * sizeof(long long); }
+
+template <int NB>
+static cudaError_t launch_cluster_t(const PersistArgs& a, cudaStream_t st) {
+  static int mode = 0;  // 0 = not initialised, 1 = cooperative + cluster, 2 = cluster only
+  constexpr int smem = Lay<NB>::total;
+  if (!mode) {
+    cudaError_t e = cudaFuncSetAttribute(decode_step_cluster<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(CL * NCL); qc.blockDim = dim3(kThreadsC); qc.dynamicSmemBytes = smem;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa; qc.numAttrs = 1;
+    int nclusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&nclusters, decode_step_cluster<NB>, &qc);
+    if (e != cudaSuccess) return e;
+    if (nclusters < NCL) return cudaErrorCooperativeLaunchTooLarge;  // all clusters must be co-resident (device-wide barriers)
+    mode = 1;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(CL * NCL); cfg.blockDim = dim3(kThreadsC); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = mode == 1 ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_step_cluster<NB>, a);
+  if (e != cudaSuccess && mode == 1) {
+    // cooperative + cluster launch rejected by this driver: co-residency is still guaranteed by the occupancy query
+    // above (32 clusters of one CTA per SM on an otherwise idle device), so launch with the cluster attribute alone
+    (void)cudaGetLastError();
+    mode = 2;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, decode_step_cluster<NB>, a);
+  }
+  return e;
+}
+
+cudaError_t launch_decode_cluster(const PersistArgs& a, int rows, cudaStream_t st) {
+  switch (rows) {
+    case 1: return launch_cluster_t<1>(a, st);
+    case 2: return launch_cluster_t<2>(a, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace vaura
