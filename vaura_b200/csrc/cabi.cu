@@ -361,6 +361,7 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     pa.batch = p->batch; pa.cond_dim = d.cond_dim; pa.cond_tokens = d.cond_tokens; pa.atpvf = d.audio_tokens_per_video_frame;
     pa.eps = d.norm_eps; pa.scale = 1.0f / sqrtf((float)kHeadDim);
     { const char* tm = getenv("VAURA_PERSIST_TIMING"); pa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
+    { const char* tc = getenv("VAURA_TIMING_CTA"); pa.timing_cta = tc ? atoi(tc) : 0; }
     int sms = 0, dev = 0;
     CU(cudaGetDevice(&dev));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -378,6 +379,8 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     if (use_cluster) {
       pa.wstream = w.wstream;
       pa.xfix = ws.xfix;
+      { const char* rl = getenv("VAURA_CLUSTER_RING"); pa.prefetch_ahead = rl ? atoi(rl) : 0; }
+      { const char* pc = getenv("VAURA_CLUSTER_PACE"); pa.pace_cycles = pc ? atoi(pc) : 0; }
       CU(cudaMemsetAsync(ws.xfix, 0, cluster_xfix_bytes(rows), st));
     }
     for (int i = 0; i < nsteps; ++i) {

@@ -123,18 +123,20 @@ __device__ __forceinline__ uint64_t now_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-constexpr uint64_t kSpinTimeoutNs = 2000000000ull;  // a protocol bug traps (-> CUDA error) instead of hanging the GPU
+// Spin waits poll without reading %globaltimer (a read costs on the order of a microsecond and would quantise every
+// wait); the timeout that turns a protocol bug into a trap (-> CUDA error) instead of a hung GPU counts SM cycles.
+constexpr long long kSpinTimeoutCycles = 4000000000ll;  // ~2 s
 __device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
   if (mb_try_wait(bar, parity)) return;
-  const uint64_t t0 = now_ns();
+  const long long t0 = clock64();
   while (!mb_try_wait(bar, parity))
-    if (now_ns() - t0 > kSpinTimeoutNs) __trap();
+    if (clock64() - t0 > kSpinTimeoutCycles) __trap();
 }
 __device__ __forceinline__ void mb_wait_cluster(uint32_t bar, uint32_t parity) {
   if (mb_try_wait_cluster(bar, parity)) return;
-  const uint64_t t0 = now_ns();
+  const long long t0 = clock64();
   while (!mb_try_wait_cluster(bar, parity))
-    if (now_ns() - t0 > kSpinTimeoutNs) __trap();
+    if (clock64() - t0 > kSpinTimeoutCycles) __trap();
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
   asm volatile(
@@ -154,9 +156,9 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     if ((int)(ld_acquire(counter) - target) < 0) {
-      const uint64_t t0 = now_ns();
+      const long long t0 = clock64();
       while ((int)(ld_acquire(counter) - target) < 0)
-        if (now_ns() - t0 > kSpinTimeoutNs) __trap();
+        if (clock64() - t0 > kSpinTimeoutCycles) __trap();
     }
   }
   consumer_sync();
@@ -307,11 +309,14 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       int freed = 0;     // ring slots of those units
       int issued = 0;    // ring slots handed to the copy engine so far
       int wslot = 0;     // ring position of the next slot
+      const long long pace = a.pace_cycles;
+      long long next_issue = 0;
+      const int ring_limit = a.prefetch_ahead >= 4 && a.prefetch_ahead < NSLOT ? a.prefetch_ahead : NSLOT;  // experiment knob
       for (int q = 0; q < NQ; ++q) {
         const int i = q < nq_layers ? q % UNITS_PER_LAYER : q - nq_layers;
         const bool is_q = q < nq_layers && i < 6;
         const int n = (q >= nq_layers || i < 7) ? 3 : 4;
-        while (issued + n - freed > NSLOT) {
+        while (issued + n - freed > ring_limit) {
           const int ri = rel < nq_layers ? rel % UNITS_PER_LAYER : rel - nq_layers;
           const int ru = rel < nq_layers ? rel / UNITS_PER_LAYER : L;
           mb_wait(empty0 + 8 * ri, ru & 1);
@@ -320,6 +325,11 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
         }
         mb_expect_tx(full0 + 8 * i, (uint32_t)n * SLOT);
         for (int s = 0; s < n; ++s) {
+          if (pace) {
+            long long now = clock64();
+            while (now < next_issue) now = clock64();
+            next_issue = now + pace;
+          }
           if (is_q) { bulk_g2s(sbase + LY::ring + wslot * SLOT, qsrc, SLOT, full0 + 8 * i, pol_last); qsrc += SLOT; }
           else { bulk_g2s(sbase + LY::ring + wslot * SLOT, psrc, SLOT, full0 + 8 * i, pol_first); psrc += SLOT; }
           wslot = wslot + 1 == NSLOT ? 0 : wslot + 1;
@@ -353,10 +363,12 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 
     int stamp_i = 0;
     auto stamp = [&]() {
-      if (a.timing && cta == 0 && tid == 0) a.timing[stamp_i] = now_ns();
+      if (a.timing && cta == a.timing_cta && tid == 0) a.timing[stamp_i] = now_ns();
       ++stamp_i;
     };
     stamp();
+    bool dbg = false;  // fine-grained stamps of one layer (profiles/cluster_timing.py)
+    auto dstamp = [&](int k) { if (dbg) a.timing[256 + k] = now_ns(); };
 
     if (tid < kHeadDim) rope_s[tid] = a.rope[(size_t)p * kHeadDim + tid];
 
@@ -461,7 +473,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           uint2 bq[6];
 #pragma unroll
           for (int kk = 0; kk < 6; ++kk) bq[kk] = lds_u2(abx + (24 * rank + 12 * kq + 6 * hk + kk) * 256);
+          dstamp(2 * u);
           mb_wait(full0 + 8 * u, (uint32_t)use & 1u);
+          dstamp(2 * u + 1);
           uint4 A[6];
 #pragma unroll
           for (int j = 0; j < 6; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
@@ -479,18 +493,23 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
             halves[(kq * QROWS + 16 * (3 * rh + rt) + gq + 8 * hf) * NB + tq] = tq == 0 ? o[hf][0] : o[hf][NB - 1];
         }
       }
+      dstamp(12);
       consumer_sync();
+      dstamp(13);
       // reduce-scatter: row i goes to CTA i / 72
       for (int e = tid; e < QROWS * NB; e += kCT) {
         const int i = e / NB, b = e % NB;
         const float v = halves[e] + halves[QROWS * NB + e];
         st_cluster_f32(mapa_u32(sbase + LY::rs_recv + ((rank * QOWN + i % QOWN) * NB + b) * 4, i / QOWN), v);
       }
+      dstamp(14);
       cluster_barrier(cbar, cphase);
+      dstamp(15);
     };
 
     for (int l = 0; l < L; ++l) {
       const uint32_t par = (uint32_t)l & 1u;
+      dbg = a.timing && cta == a.timing_cta && tid == 0 && l == L / 2;
       long long* x_in = xbuf(2 * l);
       long long* x_mid = xbuf(2 * l + 1);
       long long* x_out = xbuf(2 * l + 2);
@@ -546,7 +565,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 #pragma unroll
           for (int s = 0; s < CL; ++s) st_cluster_f32(mapa_u32(local, s), o);
         }
+        dstamp(16);
         cluster_barrier(cbar, cphase);
+        dstamp(17);
       }
       stamp();
 
@@ -598,6 +619,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           if (lane == 0) { w[0] = m; w[1] = lsum; }
           if (lane < 24) *reinterpret_cast<float4*>(w + 4 + 4 * lane) = o;
         }
+        dstamp(18);
         consumer_sync();
         // CTA partial -> every CTA of the cluster
         if (tid < kHeadDim * NB) {
@@ -623,7 +645,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
             if (d == 0) { st_cluster_f32(rbase, M); st_cluster_f32(rbase + 4, Ls); }
           }
         }
+        dstamp(19);
         cluster_barrier(cbar, cphase);
+        dstamp(20);
         if (tid < kHeadDim * NB) {
           const int b = tid / kHeadDim, d = tid % kHeadDim;
           const float* ar = reinterpret_cast<const float*>(smem + LY::rb);
@@ -647,7 +671,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       // ============ wo[768 sh + 192 rank .. +192, head]; warp w owns row tile w; residual into x_mid ============
       {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        dstamp(21);
         mb_wait(full0 + 8 * 6, par);
+        dstamp(22);
         uint4 A[6];
 #pragma unroll
         for (int j = 0; j < 6; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
@@ -675,7 +701,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const uint2 b0 = lds_u2(abx + (8 * warp + 2 * u) * 256), b1 = lds_u2(abx + (8 * warp + 2 * u + 1) * 256);
+          dstamp(24 + 2 * u);
           mb_wait(full0 + 8 * (7 + u), par);
+          dstamp(25 + 2 * u);
           uint4 A[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
@@ -696,7 +724,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
               part[(warp * 64 + 16 * r + gq + 8 * hf) * NB + tq] = tq == 0 ? o[hf][0] : o[hf][NB - 1];
           }
         }
+        dstamp(32);
         consumer_sync();
+        dstamp(33);
         if (tid < HUC * NB) {  // hidden unit u of this CTA: rows 16R+g (w1) and 16R+8+g (w3), R = u / 8, g = u % 8
           const int u = tid / NB, b = tid % NB;
           const int r1 = 16 * (u >> 3) + (u & 7), r3 = r1 + 8;
@@ -709,7 +739,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 #pragma unroll
           for (int s = 0; s < CL; ++s) st_cluster_f32(mapa_u32(local, s), hv);
         }
+        dstamp(34);
         cluster_barrier(cbar, cphase);
+        dstamp(35);
         if (tid < HU * NB / 2) {
           const int b = tid / (HU / 2), k = 2 * (tid % (HU / 2));
           const float2 v = *reinterpret_cast<const float2*>(smem + LY::hrecv + (b * HU + k) * 4);
@@ -723,7 +755,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          dstamp(36 + 2 * u);
           mb_wait(full0 + 8 * (11 + u), par);
+          dstamp(37 + 2 * u);
           uint4 A[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
@@ -740,6 +774,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       stamp();
     }
 
+    dbg = false;
     // ============ final norm + heads: the cluster owns rows [288 cl, +288), K split over its CTAs ============
     {
       stage_x(load_fix(xbuf(2 * L)), a.final_norm, 0, 0);

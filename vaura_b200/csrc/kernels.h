@@ -120,7 +120,9 @@ struct PersistArgs {
   float *h, *q, *act, *logits, *attn_part;
   KvView kv;
   StepState* state;
-  unsigned long long* timing;  // optional: phase timestamps (ns) of CTA 0
+  unsigned long long* timing;  // optional: phase timestamps (ns) of CTA `timing_cta`
+  int timing_cta;
+  int pace_cycles;  // cluster variant: minimum SM cycles between two 12 KB weight copies of a CTA (0 = unpaced)
   SampleArgs sample;
   int L, D, F, H, Kc, V, S, batch, cond_dim, cond_tokens, atpvf, slot_cap, prefetch_ahead;
   float eps, scale;
