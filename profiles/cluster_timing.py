@@ -27,7 +27,7 @@ torch.cuda.synchronize()
 print(f"generate {T} tokens: {ev[0].elapsed_time(ev[1]):.2f} ms -> {ev[0].elapsed_time(ev[1]) / (T + 8) * 1e3:.1f} us per step (incl. first pass)")
 ws = m.sampler._buffers["ws"]
 t = ws[256:256 + 16384].cpu().numpy().view(np.uint64).astype(np.int64)
-names = ["stage1", "qkv+xchg", "attn", "wo", "bar1", "stage2", "w13+xchg", "w2", "bar2"]
+names = ["stage1", "qkv+xchg", "attn", "wo", "stage2", "w13+xchg", "w2"]
 L = FULL_SAMPLER.num_layers
 per = np.zeros(len(names))
 idx = 1
@@ -45,10 +45,10 @@ print("  tail: norm+heads %.2f bar %.2f sample %.2f us" % tuple(x / 1e3 for x in
 d = t[256:256 + 40]
 labels = {0: "qkv u0 wait", 1: "qkv u0 got", 2: "u1 wait", 3: "u1 got", 4: "u2 wait", 5: "u2 got", 6: "u3 wait", 7: "u3 got",
           8: "u4 wait", 9: "u4 got", 10: "u5 wait", 11: "u5 got", 12: "halves written", 13: "cta sync", 14: "rs pushed",
-          15: "cluster bar 1", 16: "owner + ag pushed", 17: "cluster bar 2", 18: "attn warp partials", 19: "attn cta pushed",
-          20: "cluster bar 3", 21: "wo wait", 22: "wo got", 24: "w13 u0 wait", 25: "u0 got", 26: "u1 wait", 27: "u1 got",
+          15: "xchg 1 done", 16: "rope/qkv written", 17: "cta sync", 18: "attn warp partials", 19: "attn cta pushed",
+          20: "xchg 2 done", 21: "wo wait", 22: "wo got", 24: "w13 u0 wait", 25: "u0 got", 26: "u1 wait", 27: "u1 got",
           28: "u2 wait", 29: "u2 got", 30: "u3 wait", 31: "u3 got", 32: "part written", 33: "cta sync", 34: "h pushed",
-          35: "cluster bar 4", 36: "w2 u0 wait", 37: "u0 got", 38: "w2 u1 wait", 39: "u1 got"}
+          35: "xchg 3 done", 36: "w2 u0 wait", 37: "u0 got", 38: "w2 u1 wait", 39: "u1 got"}
 base = d[0]
 print("layer %d detail (us since first qkv wait):" % (L // 2))
 prev = base

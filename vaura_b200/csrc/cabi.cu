@@ -146,7 +146,7 @@ static Workspace carve(const vaura_sampler_dims& d, int rows, int max_pos, int p
     w.attn = (float*)take(R * d.d_model * 4);
     w.act = (float*)take(R * d.ffn_dim * 4);
     w.attn_part = (float*)take(persistent_attn_part_bytes(rows, d.nhead));
-    w.xfix = (long long*)take(cluster_xfix_bytes(rows <= 2 ? rows : 1));
+    w.xfix = (long long*)take(cluster_xfix_bytes(rows <= 2 ? rows : 1, d.num_layers));
   }
   w.bytes = off;
   return w;
@@ -381,7 +381,7 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
       pa.xfix = ws.xfix;
       { const char* rl = getenv("VAURA_CLUSTER_RING"); pa.prefetch_ahead = rl ? atoi(rl) : 0; }
       { const char* pc = getenv("VAURA_CLUSTER_PACE"); pa.pace_cycles = pc ? atoi(pc) : 0; }
-      CU(cudaMemsetAsync(ws.xfix, 0, cluster_xfix_bytes(rows), st));
+      CU(cudaMemsetAsync(ws.xfix, 0, cluster_xfix_bytes(rows, d.num_layers), st));
     }
     for (int i = 0; i < nsteps; ++i) {
       if (use_cluster) CUL(launch_decode_cluster(pa, rows, st));

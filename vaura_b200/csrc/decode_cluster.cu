@@ -11,10 +11,17 @@
 //             x -> [RMSNorm . w1|w3 of 32 hidden units per CTA] -> SiLU*mul -> DSMEM all-gather of the cluster's 128
 //               -> w2[384r .. +384, units of the cluster] -> fixed-point red.add                         | grid barrier
 //
-// so a layer costs two device-wide barriers (the kernel it replaces, decode_persistent.cu, needs five) and four
-// cluster-local ones.  The residual stream lives in three rotating [rows][1536] buffers of 2^-32 fixed-point int64:
-// integer adds commute, so the result does not depend on the order in which the clusters arrive (bit-reproducible);
-// each phase reads buffer n, accumulates into n+1 and clears n+2.
+// Synchronisation.  Measured on B200 (profiles/probes/dsmem_latency.cu): while cp.async.bulk copies are in flight, any
+// release/acquire barrier - DSMEM mbarrier arrive, barrier.cluster, or a global red.release/ld.acquire counter - costs
+// ~1.5 us instead of 0.35 us (the fence waits for the outstanding copies), whereas fence-free mechanisms keep their idle
+// latency.  So this kernel has NO barrier between the phases of a step:
+//   * cluster exchanges use st.async (remote shared-memory store that completes transaction bytes on the destination's
+//     mbarrier; 0.24 us with or without streaming); two mbarriers alternate because a peer can be one exchange ahead;
+//   * the residual stream is self-validating: every phase output is a fresh [rows][1536] buffer of int64 words holding
+//     (2^-32 fixed-point sum << 6) + number of contributions, accumulated with red.global.add.u64.  A reader spins on
+//     its own four words until the count says every cluster has contributed.  Integer adds commute, so the value does
+//     not depend on arrival order (bit-reproducible).  The 48 buffers of a step are cleared after the step's only
+//     device-wide barrier (logits complete -> sampling).
 //
 // Weights: a producer thread copies the CTA's weights with cp.async.bulk into a ring of 12 KB shared-memory slots; a
 // slot holds two 16x16 bf16 tiles for each of the 12 compute warps, stored in the register order of the
@@ -66,21 +73,21 @@ struct Lay {
   static constexpr int ring = 0;
   static constexpr int bx = ring + nslot * SLOT;            // B fragments of the normed residual [96 k-tiles][32][2] u32
   static constexpr int bs = bx + 96 * 256;                  // B fragments of attn out (6 k-tiles) / hidden (8 k-tiles)
-  static constexpr int ra = bs + 8 * 256;                   // alias group A (CTA-local scratch):
-  static constexpr int ra_bytes = CW * NB * WP_STRIDE * 4;  //   attention partials of the 12 warps [12][NB][100]
-  static constexpr int halves = ra;                         //   qkv / heads K halves [2][288][NB] f32
-  static constexpr int rs_recv = ra + 2 * QROWS * NB * 4;   //   reduce-scatter target [4][72][NB] f32 (remote-written)
-  static constexpr int rb = ra + ra_bytes;                  // attention partials of the 4 CTAs [4][NB][100] (remote-written)
-  static constexpr int rb_bytes = CL * NB * WP_STRIDE * 4;
-  static constexpr int qkv = rb + rb_bytes;                 // [NB][288] f32 (remote-written all-gather)
+  static constexpr int ra = bs + 8 * 256;                   // alias group A:
+  static constexpr int halves = ra;                         //   qkv / heads K halves of this CTA [2][NB][288] f32
+  static constexpr int qrecv = ra + 2 * QROWS * NB * 4;     //   all-to-all target [4 src][NB][288] f32 (remote-written)
+  static constexpr int ra_bytes = (2 + CL) * QROWS * NB * 4;//   also: attention partials of the 12 warps [12][NB][100], w13 partials
+  static constexpr int rb = ra + ra_bytes;                  // attention partials of the 4 CTAs [4][NB][100] (remote-written);
+  static constexpr int rb_bytes = CL * NB * WP_STRIDE * 4;  //   also the heads reduce-scatter target [4 src][NB][72]
+  static constexpr int qkv = rb + rb_bytes;                 // [NB][288] f32: q|k|v of the head after RoPE
   static constexpr int hrecv = qkv + NB * QROWS * 4;        // [NB][128] f32 (remote-written all-gather)
   static constexpr int xown = hrecv + NB * HU * 4;          // [NB][384] f32: this CTA's rows of the phase input
   static constexpr int red = xown + NB * W2_ROWS * 4;       // [12][NB] f32
   static constexpr int rope = red + 128;                    // [96] f32
-  static constexpr int bars = rope + kHeadDim * 4;          // full[13], empty[13], cbar
+  static constexpr int bars = rope + kHeadDim * 4;          // full[13], empty[13], xbar[2]
   static constexpr int sargs = bars + 32 * 8;               // SampleArgs copy
   static constexpr int total = sargs + 256;
-  static_assert(2 * QROWS * NB * 4 + CL * QOWN * NB * 4 <= ra_bytes, "qkv halves + reduce-scatter target fit alias group A");
+  static_assert(CW * NB * WP_STRIDE * 4 <= ra_bytes, "attention warp partials fit alias group A");
   static_assert(CW * 64 * NB * 4 <= ra_bytes, "w13 partials fit alias group A");
   static_assert(sizeof(SampleArgs) <= 256, "SampleArgs copy");
   static_assert(total <= 227 * 1024, "shared memory budget");
@@ -107,17 +114,6 @@ __device__ __forceinline__ bool mb_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ bool mb_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 __device__ __forceinline__ uint64_t now_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -130,12 +126,6 @@ __device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
   if (mb_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mb_try_wait(bar, parity))
-    if (clock64() - t0 > kSpinTimeoutCycles) __trap();
-}
-__device__ __forceinline__ void mb_wait_cluster(uint32_t bar, uint32_t parity) {
-  if (mb_try_wait_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mb_try_wait_cluster(bar, parity))
     if (clock64() - t0 > kSpinTimeoutCycles) __trap();
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
@@ -173,24 +163,16 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
 __device__ __forceinline__ void hw_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// cluster-wide barrier of the compute threads: bar.sync orders this CTA's DSMEM stores before the remote arrivals
-// (release at cluster scope); every compute thread then waits on the CTA's own mbarrier (acquire at cluster scope)
-__device__ __forceinline__ void cluster_barrier(uint32_t cbar, uint32_t& phase) {
-  consumer_sync();
-  if (threadIdx.x < CL) {
-    const uint32_t remote = mapa_u32(cbar, threadIdx.x);
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-  }
-  mb_wait_cluster(cbar, phase);
-  phase ^= 1u;
+// remote shared-memory store of 16 bytes that completes 16 transaction bytes on the mbarrier `rbar` of the destination
+// CTA (both addresses from mapa): data and completion travel together, no fence involved
+__device__ __forceinline__ void st_async_f4(uint32_t raddr, float4 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(raddr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rbar)
+               : "memory");
 }
-
 __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -208,8 +190,14 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint4& a, const ui
       : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y));
 }
 
-__device__ __forceinline__ long long f2fix(float v) { return __float2ll_rn(v * kFixScale); }
-__device__ __forceinline__ float fix2f(long long v) { return __ll2float_rn(v) * kFixInv; }
+// residual word = (2^-32 fixed-point value << 6) + contribution count
+constexpr int kCntBits = 6;
+__device__ __forceinline__ long long f2fix(float v) { return __float2ll_rn(v * kFixScale) * (1ll << kCntBits) + 1; }
+__device__ __forceinline__ float fix2f(long long w) { return __ll2float_rn(w >> kCntBits) * kFixInv; }
+__device__ __forceinline__ void ld_relaxed_x4(const long long* p, long long (&w)[4]) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(p + 2) : "memory");
+}
 __device__ __forceinline__ void red_add_fix(long long* p, long long v) {
   asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -279,12 +267,13 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
   const int cl = cta / CL;                // cluster
   const int head = cl >> 1, sh = cl & 1;  // attention head, which half of the wo rows
   const uint32_t sbase = s_u32(smem);
-  const uint32_t full0 = sbase + LY::bars, empty0 = full0 + UNITS_PER_LAYER * 8, cbar = empty0 + UNITS_PER_LAYER * 8;
+  const uint32_t full0 = sbase + LY::bars, empty0 = full0 + UNITS_PER_LAYER * 8, xbar = empty0 + UNITS_PER_LAYER * 8;
   const int L = a.L;
 
   if (tid == 0) {
     for (int i = 0; i < UNITS_PER_LAYER; ++i) { mb_init(full0 + 8 * i, 1); mb_init(empty0 + 8 * i, CW); }
-    mb_init(cbar, CL);
+    mb_init(xbar, 1);
+    mb_init(xbar + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     *reinterpret_cast<SampleArgs*>(smem + LY::sargs) = a.sample;
   }
@@ -343,14 +332,13 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
     const int offset = a.state->offset;
     const unsigned epoch = a.state->epoch;
     const int p = offset - 1;  // position fed by this step
-    const unsigned nbar = (unsigned)(2 * L + 1);
-    unsigned bar_i = 0;
-    uint32_t cphase = 0;
-    int rslot = 0;  // ring position of the next slot to consume
+    uint32_t xc = 0;           // cluster exchanges done so far: exchange xc uses xbar[xc & 1], parity (xc >> 1) & 1
+    int rslot = 0;             // ring position of the next slot to consume
     float* red = reinterpret_cast<float*>(smem + LY::red);
     float* rope_s = reinterpret_cast<float*>(smem + LY::rope);
     float* xown = reinterpret_cast<float*>(smem + LY::xown);
     float* qkv_s = reinterpret_cast<float*>(smem + LY::qkv);
+    float* halves = reinterpret_cast<float*>(smem + LY::halves);
     const uint32_t aring = sbase + LY::ring + warp * 1024 + lane * 16;
     const uint32_t abx = sbase + LY::bx + lane * 8, abs_ = sbase + LY::bs + lane * 8;
     // address of tile t of the s-th slot after the ring cursor
@@ -360,6 +348,12 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       return aring + sl * SLOT + t * 512;
     };
     auto advance = [&](int n) { rslot += n; if (rslot >= NSLOT) rslot -= NSLOT; };
+    // exchange protocol: every CTA of the cluster receives `bytes` in total through st.async
+    auto xarm = [&](uint32_t bytes) { if (tid == 0) mb_expect_tx(xbar + 8 * (xc & 1), bytes); };
+    auto xpush = [&](uint32_t local_addr, int dst, float4 v) {
+      st_async_f4(mapa_u32(local_addr, dst), v, mapa_u32(xbar + 8 * (xc & 1), dst));
+    };
+    auto xwait = [&]() { mb_wait(xbar + 8 * (xc & 1), (xc >> 1) & 1u); ++xc; };
 
     int stamp_i = 0;
     auto stamp = [&]() {
@@ -417,11 +411,21 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
         rstd[b] = rsqrtf(tot / (float)DM + a.eps);
       }
     };
-    auto load_fix = [&](const long long* buf) {
+    // phase output n (1..2L) lives in residual buffer n; a word is complete when its count reaches `expect`
+    auto xbuf = [&](int n) { return a.xfix + (size_t)n * NB * DM; };
+    auto load_fix = [&](const long long* buf, int expect) {
       return [=](int b) {
-        const longlong2 u0 = __ldcg(reinterpret_cast<const longlong2*>(buf + (size_t)b * DM + 4 * tid));
-        const longlong2 u1 = __ldcg(reinterpret_cast<const longlong2*>(buf + (size_t)b * DM + 4 * tid) + 1);
-        return make_float4(fix2f(u0.x), fix2f(u0.y), fix2f(u1.x), fix2f(u1.y));
+        const long long* src = buf + (size_t)b * DM + 4 * tid;
+        long long w[4];
+        ld_relaxed_x4(src, w);
+        if (((w[0] & w[1] & w[2] & w[3]) & 63) != expect || ((w[0] | w[1] | w[2] | w[3]) & 63) != expect) {
+          const long long t0 = clock64();
+          do {
+            ld_relaxed_x4(src, w);
+            if (clock64() - t0 > kSpinTimeoutCycles) __trap();
+          } while (((w[0] & w[1] & w[2] & w[3]) & 63) != expect || ((w[0] | w[1] | w[2] | w[3]) & 63) != expect);
+        }
+        return make_float4(fix2f(w[0]), fix2f(w[1]), fix2f(w[2]), fix2f(w[3]));
       };
     };
     // embedding (llama.py:455-472): conditioning row | sum of the 9 folded token tables
@@ -441,10 +445,6 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       }
       return v;
     };
-    auto xbuf = [&](int n) { return a.xfix + (size_t)(n % 3) * NB * DM; };  // rotating residual buffers
-    auto clear_slice = [&](long long* buf) {  // this CTA's share of the buffer the phase after next accumulates into
-      if (tid < NB * DM / (CL * NCL)) buf[cta * (NB * DM / (CL * NCL)) + tid] = 0;
-    };
     // output rows [row0 + 16 rt, +16) of a residual phase: add the partial (and, where `carry`, the phase input)
     auto resid_add = [&](const float (&acc)[4], long long* dst, int row0, int rt, bool carry) {
       float o[2][NB];
@@ -460,13 +460,12 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       }
     };
     // K-split GEMV of 288 rows (18 row tiles) x this CTA's 384 features: 6 units of 3 slots; warp (rh, kq) owns row
-    // tiles 3rh..3rh+2 and k-tiles 12kq..12kq+11.  Leaves the cluster-reduced rows [72 rank, +72) in rs_recv[4][72][NB]
+    // tiles 3rh..3rh+2 and k-tiles 12kq..12kq+11.  Leaves halves[kq][b][row]
     auto ksplit_288 = [&](int use) {
       const int rh = warp >> 1, kq = warp & 1;
-      float* halves = reinterpret_cast<float*>(smem + LY::halves);
 #pragma unroll
       for (int rt = 0; rt < 3; ++rt) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int hk = 0; hk < 2; ++hk) {
           const int u = 2 * rt + hk;
@@ -480,37 +479,27 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 #pragma unroll
           for (int j = 0; j < 6; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
 #pragma unroll
-          for (int j = 0; j < 6; ++j) mma16816(acc, A[j], bq[j]);
+          for (int j = 0; j < 6; j += 2) { mma16816(acc0, A[j], bq[j]); mma16816(acc1, A[j + 1], bq[j + 1]); }
           __syncwarp();
           if (lane == 0) mb_arrive(empty0 + 8 * u);
           advance(3);
         }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc0[e] += acc1[e];
         float o[2][NB];
-        quad_reduce<NB>(acc, tq, o);
+        quad_reduce<NB>(acc0, tq, o);
         if (tq < NB) {
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf)
-            halves[(kq * QROWS + 16 * (3 * rh + rt) + gq + 8 * hf) * NB + tq] = tq == 0 ? o[hf][0] : o[hf][NB - 1];
+            halves[(kq * NB + tq) * QROWS + 16 * (3 * rh + rt) + gq + 8 * hf] = tq == 0 ? o[hf][0] : o[hf][NB - 1];
         }
       }
       dstamp(12);
-      consumer_sync();
-      dstamp(13);
-      // reduce-scatter: row i goes to CTA i / 72
-      for (int e = tid; e < QROWS * NB; e += kCT) {
-        const int i = e / NB, b = e % NB;
-        const float v = halves[e] + halves[QROWS * NB + e];
-        st_cluster_f32(mapa_u32(sbase + LY::rs_recv + ((rank * QOWN + i % QOWN) * NB + b) * 4, i / QOWN), v);
-      }
-      dstamp(14);
-      cluster_barrier(cbar, cphase);
-      dstamp(15);
     };
 
     for (int l = 0; l < L; ++l) {
       const uint32_t par = (uint32_t)l & 1u;
       dbg = a.timing && cta == a.timing_cta && tid == 0 && l == L / 2;
-      long long* x_in = xbuf(2 * l);
       long long* x_mid = xbuf(2 * l + 1);
       long long* x_out = xbuf(2 * l + 2);
 
@@ -530,43 +519,51 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
         }
 
       // ================= attention block: RMSNorm . wqkv rows of head `head`, K split over the 4 CTAs =================
-      clear_slice(x_out);
       if (l == 0) stage_x(load_embed, a.attn_norm, 768 * sh + WO_ROWS * rank, WO_ROWS);
-      else stage_x(load_fix(x_in), a.attn_norm + (size_t)l * DM, 768 * sh + WO_ROWS * rank, WO_ROWS);
+      else stage_x(load_fix(xbuf(2 * l), NCL), a.attn_norm + (size_t)l * DM, 768 * sh + WO_ROWS * rank, WO_ROWS);
       stamp();
       ksplit_288(l);
       {
-        // owner of 72 rows: sum the 4 K slices, apply rstd and RoPE (llama.py:633-650), append K/V, all-gather
-        const bool own = tid < QOWN * NB;
-        float y = 0.f;
-        if (own) {
-          const int ii = tid / NB, b = tid % NB;
-          const float* rr = reinterpret_cast<const float*>(smem + LY::rs_recv);
+        // all-to-all: every CTA receives the K-slice sums of all four CTAs, [src][b][288]
+        xarm(CL * NB * QROWS * 4);
+        consumer_sync();
+        dstamp(13);
+        if (tid < NB * QROWS / 4) {
+          const float4 h0 = *reinterpret_cast<const float4*>(halves + 4 * tid);
+          const float4 h1 = *reinterpret_cast<const float4*>(halves + NB * QROWS + 4 * tid);
+          const float4 v = make_float4(h0.x + h1.x, h0.y + h1.y, h0.z + h1.z, h0.w + h1.w);
+          const uint32_t local = sbase + LY::qrecv + (rank * NB * QROWS + 4 * tid) * 4;
 #pragma unroll
-          for (int s = 0; s < CL; ++s) y += rr[(s * QOWN + ii) * NB + b];
-          y *= rstd[b];
+          for (int s = 0; s < CL; ++s) xpush(local, s, v);
         }
-        const float other = __shfl_xor_sync(0xffffffffu, y, NB);  // partner of the RoPE pair (rows 2m, 2m+1)
-        if (own) {
-          const int ii = tid / NB, b = tid % NB;
-          const int i = rank * QOWN + ii, sec = i / kHeadDim, e = i % kHeadDim;
+        dstamp(14);
+        xwait();
+        dstamp(15);
+        // every CTA: sum the 4 K slices, apply rstd and RoPE (llama.py:633-650); rows [72 rank, +72) append K/V
+        const float* qr = reinterpret_cast<const float*>(smem + LY::qrecv);
+        for (int e = tid; e < NB * QROWS; e += kCT) {  // 288 (or 576) is a multiple of 32: whole warps
+          const int b = e / QROWS, i = e % QROWS;
+          float y = 0.f;
+#pragma unroll
+          for (int s = 0; s < CL; ++s) y += qr[s * NB * QROWS + e];
+          y *= rstd[b];
+          const float other = __shfl_xor_sync(0xffffffffu, y, 1);  // partner of the RoPE pair (rows 2m, 2m+1)
+          const int sec = i / kHeadDim, d = i % kHeadDim;
           float o = y;
           if (sec != 2) {
-            const float cs = rope_s[e & ~1], sn = rope_s[(e & ~1) + 1];
-            o = (e & 1) ? y * cs + other * sn : y * cs - other * sn;
+            const float cs = rope_s[d & ~1], sn = rope_s[(d & ~1) + 1];
+            o = (d & 1) ? y * cs + other * sn : y * cs - other * sn;
           }
-          if (sec != 0 && sh == 0) {  // the twin cluster computes the same values: one of them appends
+          if (sec != 0 && sh == 0 && i / QOWN == rank) {  // the twin cluster computes the same values: one CTA appends
             const int page = a.kv.page_table[b * a.kv.max_pages_per_seq + p / a.kv.page_size];
             float* dstp = reinterpret_cast<float*>(a.kv.pages) + (size_t)l * 2 * kv_half + (size_t)(sec - 1) * kv_half +
-                          ((size_t)(page * a.kv.nhead + head) * a.kv.page_size + (p % a.kv.page_size)) * kHeadDim + e;
+                          ((size_t)(page * a.kv.nhead + head) * a.kv.page_size + (p % a.kv.page_size)) * kHeadDim + d;
             *dstp = o;
           }
-          const uint32_t local = sbase + LY::qkv + (b * QROWS + i) * 4;
-#pragma unroll
-          for (int s = 0; s < CL; ++s) st_cluster_f32(mapa_u32(local, s), o);
+          qkv_s[e] = o;
         }
         dstamp(16);
-        cluster_barrier(cbar, cphase);
+        consumer_sync();
         dstamp(17);
       }
       stamp();
@@ -588,19 +585,23 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 #pragma unroll
           for (int it = 0; it < MAXIT; ++it) {
             const float4 k4 = kreg[it][b];
-            const float d = warp_sum(k4.x * q4.x + k4.y * q4.y + k4.z * q4.z + k4.w * q4.w);
-            sc[it] = kvalid[it] ? d * a.scale : -INFINITY;
+            sc[it] = k4.x * q4.x + k4.y * q4.y + k4.z * q4.z + k4.w * q4.w;
           }
           float4 vn = make_float4(0.f, 0.f, 0.f, 0.f);
-          sc[MAXIT] = -INFINITY;
-          if (new_warp) {
-            float4 kn = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < 24) {
-              kn = *reinterpret_cast<const float4*>(qkv_s + b * QROWS + kHeadDim + 4 * lane);
-              vn = *reinterpret_cast<const float4*>(qkv_s + b * QROWS + 2 * kHeadDim + 4 * lane);
-            }
-            sc[MAXIT] = warp_sum(kn.x * q4.x + kn.y * q4.y + kn.z * q4.z + kn.w * q4.w) * a.scale;
+          sc[MAXIT] = 0.f;
+          if (new_warp && lane < 24) {
+            const float4 kn = *reinterpret_cast<const float4*>(qkv_s + b * QROWS + kHeadDim + 4 * lane);
+            vn = *reinterpret_cast<const float4*>(qkv_s + b * QROWS + 2 * kHeadDim + 4 * lane);
+            sc[MAXIT] = kn.x * q4.x + kn.y * q4.y + kn.z * q4.z + kn.w * q4.w;
           }
+          // six independent butterfly reductions, interleaved
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int it = 0; it <= MAXIT; ++it) sc[it] += __shfl_xor_sync(0xffffffffu, sc[it], o);
+#pragma unroll
+          for (int it = 0; it < MAXIT; ++it) sc[it] = kvalid[it] ? sc[it] * a.scale : -INFINITY;
+          sc[MAXIT] = new_warp ? sc[MAXIT] * a.scale : -INFINITY;
           float m = sc[MAXIT];
 #pragma unroll
           for (int it = 0; it < MAXIT; ++it) m = fmaxf(m, sc[it]);
@@ -619,34 +620,33 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           if (lane == 0) { w[0] = m; w[1] = lsum; }
           if (lane < 24) *reinterpret_cast<float4*>(w + 4 + 4 * lane) = o;
         }
+        xarm(CL * NB * WP_STRIDE * 4);
         dstamp(18);
         consumer_sync();
-        // CTA partial -> every CTA of the cluster
-        if (tid < kHeadDim * NB) {
-          const int b = tid / kHeadDim, d = tid % kHeadDim;
+        // CTA partial (m, l, -, -, o[96]) -> every CTA of the cluster, 25 float4 per sequence row
+        if (tid < 25 * NB) {
+          const int b = tid / 25, c4 = tid % 25;
           float M = -INFINITY;
 #pragma unroll
           for (int w = 0; w < CW; ++w) M = fmaxf(M, wp[(w * NB + b) * WP_STRIDE]);
-          float Ls = 0.f, O = 0.f;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           if (M > -INFINITY) {
 #pragma unroll
             for (int w = 0; w < CW; ++w) {
-              const float mw = wp[(w * NB + b) * WP_STRIDE];
-              const float f = mw > -INFINITY ? expf(mw - M) : 0.f;
-              Ls = fmaf(f, wp[(w * NB + b) * WP_STRIDE + 1], Ls);
-              O = fmaf(f, wp[(w * NB + b) * WP_STRIDE + 4 + d], O);
+              const float* rec = wp + (w * NB + b) * WP_STRIDE;
+              const float f = rec[0] > -INFINITY ? expf(rec[0] - M) : 0.f;
+              const float4 v = *reinterpret_cast<const float4*>(rec + 4 * c4);
+              if (c4 == 0) acc.y = fmaf(f, v.y, acc.y);
+              else { acc.x = fmaf(f, v.x, acc.x); acc.y = fmaf(f, v.y, acc.y); acc.z = fmaf(f, v.z, acc.z); acc.w = fmaf(f, v.w, acc.w); }
             }
           }
-          const uint32_t local = sbase + LY::rb + ((rank * NB + b) * WP_STRIDE) * 4;
+          if (c4 == 0) acc.x = M;
+          const uint32_t local = sbase + LY::rb + ((rank * NB + b) * WP_STRIDE + 4 * c4) * 4;
 #pragma unroll
-          for (int s = 0; s < CL; ++s) {
-            const uint32_t rbase = mapa_u32(local, s);
-            st_cluster_f32(rbase + (4 + d) * 4, O);
-            if (d == 0) { st_cluster_f32(rbase, M); st_cluster_f32(rbase + 4, Ls); }
-          }
+          for (int s = 0; s < CL; ++s) xpush(local, s, acc);
         }
         dstamp(19);
-        cluster_barrier(cbar, cphase);
+        xwait();
         dstamp(20);
         if (tid < kHeadDim * NB) {
           const int b = tid / kHeadDim, d = tid % kHeadDim;
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 
       // ============ wo[768 sh + 192 rank .. +192, head]; warp w owns row tile w; residual into x_mid ============
       {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
         dstamp(21);
         mb_wait(full0 + 8 * 6, par);
         dstamp(22);
@@ -678,19 +678,18 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 #pragma unroll
         for (int j = 0; j < 6; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
 #pragma unroll
-        for (int j = 0; j < 6; ++j) mma16816(acc, A[j], lds_u2(abs_ + j * 256));
+        for (int j = 0; j < 6; j += 2) { mma16816(acc0, A[j], lds_u2(abs_ + j * 256)); mma16816(acc1, A[j + 1], lds_u2(abs_ + (j + 1) * 256)); }
         __syncwarp();
         if (lane == 0) mb_arrive(empty0 + 8 * 6);
         advance(3);
-        resid_add(acc, x_mid, 768 * sh + WO_ROWS * rank, warp, head == 0);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc0[e] += acc1[e];
+        resid_add(acc0, x_mid, 768 * sh + WO_ROWS * rank, warp, head == 0);
       }
-      stamp();
-      grid_barrier(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
       stamp();
 
       // ============ MLP: RMSNorm . w1|w3 of this CTA's 32 hidden units (K split over the 12 warps) ============
-      clear_slice(x_in);
-      stage_x(load_fix(x_mid), a.ffn_norm + (size_t)l * DM, W2_ROWS * rank, W2_ROWS);
+      stage_x(load_fix(x_mid, NHEAD), a.ffn_norm + (size_t)l * DM, W2_ROWS * rank, W2_ROWS);
       stamp();
       {
         float acc[4][4];
@@ -713,7 +712,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           if (lane == 0) mb_arrive(empty0 + 8 * (7 + u));
           advance(4);
         }
-        float* part = reinterpret_cast<float*>(smem + LY::ra);  // [12][64][NB]
+        float* part = reinterpret_cast<float*>(smem + LY::ra);  // [12][NB][64]
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           float o[2][NB];
@@ -721,26 +720,33 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           if (tq < NB) {
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf)
-              part[(warp * 64 + 16 * r + gq + 8 * hf) * NB + tq] = tq == 0 ? o[hf][0] : o[hf][NB - 1];
+              part[(warp * NB + tq) * 64 + 16 * r + gq + 8 * hf] = tq == 0 ? o[hf][0] : o[hf][NB - 1];
           }
         }
+        xarm(CL * NB * HUC * 4);
         dstamp(32);
         consumer_sync();
         dstamp(33);
-        if (tid < HUC * NB) {  // hidden unit u of this CTA: rows 16R+g (w1) and 16R+8+g (w3), R = u / 8, g = u % 8
-          const int u = tid / NB, b = tid % NB;
-          const int r1 = 16 * (u >> 3) + (u & 7), r3 = r1 + 8;
-          float y1 = 0.f, y3 = 0.f;
+        if (tid < HUC * NB / 4) {  // 4 hidden units per thread: unit u -> rows 16R+g (w1) and 16R+8+g (w3), R = u / 8, g = u % 8
+          const int b = tid / (HUC / 4), u0 = 4 * (tid % (HUC / 4));
+          const int r1 = 16 * (u0 >> 3) + (u0 & 7);
+          float4 y1 = make_float4(0.f, 0.f, 0.f, 0.f), y3 = y1;
 #pragma unroll
-          for (int w = 0; w < CW; ++w) { y1 += part[(w * 64 + r1) * NB + b]; y3 += part[(w * 64 + r3) * NB + b]; }
-          y1 *= rstd[b]; y3 *= rstd[b];
-          const float hv = y1 / (1.f + expf(-y1)) * y3;
-          const uint32_t local = sbase + LY::hrecv + (b * HU + rank * HUC + u) * 4;
+          for (int w = 0; w < CW; ++w) {
+            const float4 p1 = *reinterpret_cast<const float4*>(part + (w * NB + b) * 64 + r1);
+            const float4 p3 = *reinterpret_cast<const float4*>(part + (w * NB + b) * 64 + r1 + 8);
+            y1.x += p1.x; y1.y += p1.y; y1.z += p1.z; y1.w += p1.w;
+            y3.x += p3.x; y3.y += p3.y; y3.z += p3.z; y3.w += p3.w;
+          }
+          const float rs = rstd[b];
+          auto swiglu = [&](float g1, float g3) { g1 *= rs; g3 *= rs; return g1 / (1.f + expf(-g1)) * g3; };
+          const float4 hv = make_float4(swiglu(y1.x, y3.x), swiglu(y1.y, y3.y), swiglu(y1.z, y3.z), swiglu(y1.w, y3.w));
+          const uint32_t local = sbase + LY::hrecv + (b * HU + rank * HUC + u0) * 4;
 #pragma unroll
-          for (int s = 0; s < CL; ++s) st_cluster_f32(mapa_u32(local, s), hv);
+          for (int s = 0; s < CL; ++s) xpush(local, s, hv);
         }
         dstamp(34);
-        cluster_barrier(cbar, cphase);
+        xwait();
         dstamp(35);
         if (tid < HU * NB / 2) {
           const int b = tid / (HU / 2), k = 2 * (tid % (HU / 2));
@@ -754,7 +760,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
           dstamp(36 + 2 * u);
           mb_wait(full0 + 8 * (11 + u), par);
           dstamp(37 + 2 * u);
@@ -762,34 +768,52 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 #pragma unroll
           for (int j = 0; j < 8; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
 #pragma unroll
-          for (int j = 0; j < 8; ++j) mma16816(acc, A[j], lds_u2(abs_ + j * 256));
+          for (int j = 0; j < 8; j += 2) { mma16816(acc0, A[j], lds_u2(abs_ + j * 256)); mma16816(acc1, A[j + 1], lds_u2(abs_ + (j + 1) * 256)); }
           __syncwarp();
           if (lane == 0) mb_arrive(empty0 + 8 * (11 + u));
           advance(4);
-          resid_add(acc, x_out, W2_ROWS * rank, 2 * warp + u, cl == 0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc0[e] += acc1[e];
+          resid_add(acc0, x_out, W2_ROWS * rank, 2 * warp + u, cl == 0);
         }
       }
-      stamp();
-      grid_barrier(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
       stamp();
     }
 
     dbg = false;
     // ============ final norm + heads: the cluster owns rows [288 cl, +288), K split over its CTAs ============
     {
-      stage_x(load_fix(xbuf(2 * L)), a.final_norm, 0, 0);
+      stage_x(load_fix(xbuf(2 * L), NCL), a.final_norm, 0, 0);
       ksplit_288(L);
+      // reduce-scatter: rows [72 dst, +72) of every sequence row go to CTA dst, [src][b][72]
+      xarm(CL * NB * HOWN * 4);
+      consumer_sync();
+      if (tid < NB * QROWS / 4) {
+        const int b = (4 * tid) / QROWS, i = (4 * tid) % QROWS;
+        const float4 h0 = *reinterpret_cast<const float4*>(halves + 4 * tid);
+        const float4 h1 = *reinterpret_cast<const float4*>(halves + NB * QROWS + 4 * tid);
+        const float4 v = make_float4(h0.x + h1.x, h0.y + h1.y, h0.z + h1.z, h0.w + h1.w);
+        xpush(sbase + LY::rb + ((rank * NB + b) * HOWN + i % HOWN) * 4, i / HOWN, v);
+      }
+      xwait();
       if (tid < HOWN * NB) {
-        const int ii = tid / NB, b = tid % NB;
-        const float* rr = reinterpret_cast<const float*>(smem + LY::rs_recv);
+        const int b = tid / HOWN, ii = tid % HOWN;
+        const float* rr = reinterpret_cast<const float*>(smem + LY::rb);
         float y = 0.f;
 #pragma unroll
-        for (int s = 0; s < CL; ++s) y += rr[(s * HOWN + ii) * NB + b];
+        for (int s = 0; s < CL; ++s) y += rr[(s * NB + b) * HOWN + ii];
         a.logits[(size_t)b * (a.Kc * a.V) + cl * HROWS + rank * HOWN + ii] = y * rstd[b];
       }
       stamp();
-      grid_barrier(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
+      // the step's only device-wide barrier: logits complete, every CTA is done reading the residual buffers
+      grid_barrier(&a.state->barrier, (epoch + 1) * (unsigned)G);
       stamp();
+    }
+    // clear the residual buffers of this step for the next one (the last reader is past the barrier)
+    {
+      constexpr int per_cta = NB * DM / (CL * NCL);
+      for (int i = tid; i < 2 * L * per_cta; i += kCT)
+        a.xfix[(size_t)NB * DM + (size_t)(i / per_cta) * NB * DM + cta * per_cta + i % per_cta] = 0;
     }
 
     // ============ CFG / sampling / mask-fix / write-back: one warp per (clip, codebook) ============
@@ -824,7 +848,7 @@ bool cluster_supported(int rows, int L, int D, int F, int H, int head_rows, int 
   return true;
 }
 
-size_t cluster_xfix_bytes(int rows) { return (size_t)3 * rows * DM * sizeof(long long); }
+size_t cluster_xfix_bytes(int rows, int L) { return (size_t)(2 * L + 1) * rows * DM * sizeof(long long); }
 
 template <int NB>
 static cudaError_t launch_cluster_t(const PersistArgs& a, cudaStream_t st) {

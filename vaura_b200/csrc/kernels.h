@@ -113,7 +113,7 @@ struct PersistArgs {
   const uint16_t *wqkv, *wo, *w13, *w2, *w_heads;
   const uint16_t *wqkv_t, *wo_t, *w13_t, *w2_t, *w_heads_t;  // K-block-major copies (tensor-core variant)
   const uint8_t* wstream;       // fragment-ordered weight streams (cluster variant, decode_cluster.cu)
-  long long* xfix;              // cluster variant: three rotating fixed-point residual buffers [3][rows][D]
+  long long* xfix;              // cluster variant: residual buffers [2L+1][rows][D] (word = fixed-point sum << 6 | count)
   const float *attn_norm, *ffn_norm, *final_norm, *tok_tables, *rope;
   const int32_t* seq;
   const float* cond_rows;
@@ -138,7 +138,7 @@ cudaError_t launch_decode_persistent_tc(PersistArgs& a, int rows, cudaStream_t s
 // cluster variant (decode_cluster.cu): 32 clusters x 4 CTAs, mma.sync from fragment-ordered weight streams
 bool cluster_supported(int rows, int L, int D, int F, int H, int head_rows, int page_size, int cond_dim, int max_ctx);
 size_t cluster_stream_bytes(int L);
-size_t cluster_xfix_bytes(int rows);
+size_t cluster_xfix_bytes(int rows, int L);
 cudaError_t launch_decode_cluster(const PersistArgs& a, int rows, cudaStream_t st);
 
 cudaError_t launch_embed(const EmbedArgs& a, int rows, cudaStream_t st);
