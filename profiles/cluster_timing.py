@@ -42,16 +42,17 @@ for n, v in zip(names, per):
     print(f"  {n:9s} {v / L / 1e3:7.2f} us/layer")
 print("  tail: norm+heads %.2f bar %.2f sample %.2f us" % tuple(x / 1e3 for x in tail))
 
-d = t[256:256 + 40]
+d = t[256:256 + 48]
 labels = {0: "qkv u0 wait", 1: "qkv u0 got", 2: "u1 wait", 3: "u1 got", 4: "u2 wait", 5: "u2 got", 6: "u3 wait", 7: "u3 got",
           8: "u4 wait", 9: "u4 got", 10: "u5 wait", 11: "u5 got", 12: "halves written", 13: "cta sync", 14: "rs pushed",
           15: "xchg 1 done", 16: "rope/qkv written", 17: "cta sync", 18: "attn warp partials", 19: "attn cta pushed",
           20: "xchg 2 done", 21: "wo wait", 22: "wo got", 24: "w13 u0 wait", 25: "u0 got", 26: "u1 wait", 27: "u1 got",
           28: "u2 wait", 29: "u2 got", 30: "u3 wait", 31: "u3 got", 32: "part written", 33: "cta sync", 34: "h pushed",
-          35: "xchg 3 done", 36: "w2 u0 wait", 37: "u0 got", 38: "w2 u1 wait", 39: "u1 got"}
+          35: "xchg 3 done", 41: "wo adds issued, arrived", 42: "counter barrier done", 43: "x_mid words complete", 36: "w2 u0 wait", 37: "u0 got", 38: "w2 u1 wait", 39: "u1 got"}
 base = d[0]
 print("layer %d detail (us since first qkv wait):" % (L // 2))
 prev = base
-for k in sorted(labels):
+order = list(range(0, 23)) + [41, 42, 43] + list(range(24, 40))
+for k in [o for o in order if o in labels]:
     print(f"  {labels[k]:22s} {(d[k] - base) / 1e3:7.2f}  (+{(d[k] - prev) / 1e3:.2f})")
     prev = d[k]

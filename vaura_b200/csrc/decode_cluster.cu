@@ -69,11 +69,12 @@ constexpr float kFixInv = 2.3283064365386963e-10f;
 
 template <int NB>
 struct Lay {
-  static constexpr int nslot = NB == 1 ? 15 : 14;
+  static constexpr int nslot = NB == 1 ? 17 : 15;
+  static constexpr int bkt = 96 * NB;                       // bytes of one k-tile of B fragments: 3 NB columns x 4 lanes x 8 B
   static constexpr int ring = 0;
-  static constexpr int bx = ring + nslot * SLOT;            // B fragments of the normed residual [96 k-tiles][32][2] u32
-  static constexpr int bs = bx + 96 * 256;                  // B fragments of attn out (6 k-tiles) / hidden (8 k-tiles)
-  static constexpr int ra = bs + 8 * 256;                   // alias group A:
+  static constexpr int bx = ring + nslot * SLOT;            // B fragments of the normed residual [96 k-tiles][3 NB cols][4][2] u32
+  static constexpr int bs = bx + 96 * bkt;                  // B fragments of attn out (6 k-tiles) / hidden (8 k-tiles)
+  static constexpr int ra = bs + 8 * bkt;                   // alias group A:
   static constexpr int halves = ra;                         //   qkv / heads K halves of this CTA [2][NB][288] f32
   static constexpr int qrecv = ra + 2 * QROWS * NB * 4;     //   all-to-all target [4 src][NB][288] f32 (remote-written)
   static constexpr int ra_bytes = (2 + CL) * QROWS * NB * 4;//   also: attention partials of the 12 warps [12][NB][100], w13 partials
@@ -82,8 +83,8 @@ struct Lay {
   static constexpr int qkv = rb + rb_bytes;                 // [NB][288] f32: q|k|v of the head after RoPE
   static constexpr int hrecv = qkv + NB * QROWS * 4;        // [NB][128] f32 (remote-written all-gather)
   static constexpr int xown = hrecv + NB * HU * 4;          // [NB][384] f32: this CTA's rows of the phase input
-  static constexpr int red = xown + NB * W2_ROWS * 4;       // [12][NB] f32
-  static constexpr int rope = red + 128;                    // [96] f32
+  static constexpr int red = xown + NB * W2_ROWS * 4;       // [12][NB] f32 sums of squares, [16 + 12*NB] score maxima
+  static constexpr int rope = red + 256;                    // [96] f32
   static constexpr int bars = rope + kHeadDim * 4;          // full[13], empty[13], xbar[2]
   static constexpr int sargs = bars + 32 * 8;               // SampleArgs copy
   static constexpr int total = sargs + 256;
@@ -153,6 +154,26 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
   }
   consumer_sync();
 }
+// fence-free arrival / wait on the device-wide counter (probe: 0.45 us with or without streaming).  It only tells that
+// every CTA has ISSUED its residual adds; completeness of the data is checked on the words themselves.
+__device__ __forceinline__ void grid_arrive_relaxed(unsigned* counter) {
+  consumer_sync();
+  if (threadIdx.x == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+__device__ __forceinline__ void grid_wait_relaxed(unsigned* counter, unsigned target) {
+  if (threadIdx.x == 0) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if ((int)(v - target) < 0) {
+      const long long t0 = clock64();
+      do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (clock64() - t0 > kSpinTimeoutCycles) __trap();
+      } while ((int)(v - target) < 0);
+    }
+  }
+  consumer_sync();
+}
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -171,6 +192,16 @@ __device__ __forceinline__ void hw_cluster_sync() {
 __device__ __forceinline__ void st_async_f4(uint32_t raddr, float4 v, uint32_t rbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(raddr),
                "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rbar)
+               : "memory");
+}
+// issued where written (asm volatile): the compiler must not sink the K/V prefetch to its first use
+__device__ __forceinline__ float4 ldg_cg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_async_f1(uint32_t raddr, float v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(raddr), "f"(v), "r"(rbar)
                : "memory");
 }
 __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
@@ -212,45 +243,43 @@ __device__ __forceinline__ void split3(float v, uint32_t& hi, uint32_t& mid, uin
   hi = __bfloat16_as_ushort(h); mid = __bfloat16_as_ushort(m); lo = __bfloat16_as_ushort(l);
 }
 // B-fragment address (bytes from the fragment array base) of element (k, column n): mma.m16n8k16 .col B operand,
-// lane = n*4 + (k%8)/2, register (k%16)/8, half k%2
+// lane = n*4 + (k%8)/2, register (k%16)/8, half k%2.  Only the 3 NB live columns are stored (12 NB lanes per k-tile);
+// the other lanes feed zeros.
+template <int NB>
 __device__ __forceinline__ uint32_t bfrag_off(int k, int n) {
   const int kk = k & 15;
-  return (uint32_t)(((k >> 4) * 32 + n * 4 + ((kk & 7) >> 1)) * 8 + (kk >> 3) * 4 + (kk & 1) * 2);
+  return (uint32_t)(((k >> 4) * 12 * NB + n * 4 + ((kk & 7) >> 1)) * 8 + (kk >> 3) * 4 + (kk & 1) * 2);
 }
 // stage the pair (v0, v1) = elements (k, k+1), k even, of sequence row b into B fragments (three split columns)
+template <int NB>
 __device__ __forceinline__ void stage_pair(uint8_t* base, int k, int b, float v0, float v1) {
   uint32_t h0, m0, l0, h1, m1, l1;
   split3(v0, h0, m0, l0);
   split3(v1, h1, m1, l1);
-  *reinterpret_cast<uint32_t*>(base + bfrag_off(k, 3 * b + 0)) = h0 | (h1 << 16);
-  *reinterpret_cast<uint32_t*>(base + bfrag_off(k, 3 * b + 1)) = m0 | (m1 << 16);
-  *reinterpret_cast<uint32_t*>(base + bfrag_off(k, 3 * b + 2)) = l0 | (l1 << 16);
+  *reinterpret_cast<uint32_t*>(base + bfrag_off<NB>(k, 3 * b + 0)) = h0 | (h1 << 16);
+  *reinterpret_cast<uint32_t*>(base + bfrag_off<NB>(k, 3 * b + 1)) = m0 | (m1 << 16);
+  *reinterpret_cast<uint32_t*>(base + bfrag_off<NB>(k, 3 * b + 2)) = l0 | (l1 << 16);
 }
+template <int NB>
 __device__ __forceinline__ void stage_one(uint8_t* base, int k, int b, float v) {
   uint32_t h, m, l;
   split3(v, h, m, l);
-  *reinterpret_cast<uint16_t*>(base + bfrag_off(k, 3 * b + 0)) = (uint16_t)h;
-  *reinterpret_cast<uint16_t*>(base + bfrag_off(k, 3 * b + 1)) = (uint16_t)m;
-  *reinterpret_cast<uint16_t*>(base + bfrag_off(k, 3 * b + 2)) = (uint16_t)l;
+  *reinterpret_cast<uint16_t*>(base + bfrag_off<NB>(k, 3 * b + 0)) = (uint16_t)h;
+  *reinterpret_cast<uint16_t*>(base + bfrag_off<NB>(k, 3 * b + 1)) = (uint16_t)m;
+  *reinterpret_cast<uint16_t*>(base + bfrag_off<NB>(k, 3 * b + 2)) = (uint16_t)l;
 }
 
-// accumulator fragment (rows g, g+8; columns 2t, 2t+1) -> out[half][b] = sum of the three split columns of sequence
-// row b, valid in all four lanes of the quad
+// accumulator fragment (rows g, g+8; columns 2t, 2t+1) -> out[half] = sum of the three split columns of sequence row
+// tq (columns 3tq..3tq+2), valid in the lanes tq < NB: row 0 = cols 0,1 (lane tq 0) + col 2 (lane tq 1, c[even]);
+// row 1 = col 3 (lane tq 1, c[odd]) + cols 4,5 (lane tq 2).  One shuffle per half.
 template <int NB>
-__device__ __forceinline__ void quad_reduce(const float (&c)[4], int tq, float (&out)[2][NB]) {
+__device__ __forceinline__ void quad_reduce(const float (&c)[4], int tq, float (&out)[2]) {
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) {
     const float ca = c[2 * hf], cb = c[2 * hf + 1];
-    float s0 = tq == 0 ? ca + cb : (tq == 1 ? ca : 0.f);
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-    out[hf][0] = s0;
-    if (NB == 2) {
-      float s1 = tq == 1 ? cb : (tq == 2 ? ca + cb : 0.f);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      out[hf][NB - 1] = s1;
-    }
+    const float send = tq == 1 ? ca : ca + cb;
+    const float recv = __shfl_down_sync(0xffffffffu, send, 1);
+    out[hf] = (tq == 0 ? ca + cb : cb) + recv;
   }
 }
 
@@ -277,9 +306,6 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     *reinterpret_cast<SampleArgs*>(smem + LY::sargs) = a.sample;
   }
-  // zero the B-fragment arrays once: the unused columns must stay zero
-  for (int i = tid; i < (96 + 8) * 256 / 16; i += kThreadsC)
-    reinterpret_cast<uint4*>(smem + LY::bx)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   hw_cluster_sync();  // every CTA of the cluster has initialised its barriers before any remote arrive / store
 
@@ -332,6 +358,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
     const int offset = a.state->offset;
     const unsigned epoch = a.state->epoch;
     const int p = offset - 1;  // position fed by this step
+    const unsigned nbar = (unsigned)(2 * L + 1);
+    unsigned bar_i = 0;
     uint32_t xc = 0;           // cluster exchanges done so far: exchange xc uses xbar[xc & 1], parity (xc >> 1) & 1
     int rslot = 0;             // ring position of the next slot to consume
     float* red = reinterpret_cast<float*>(smem + LY::red);
@@ -341,6 +369,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
     float* halves = reinterpret_cast<float*>(smem + LY::halves);
     const uint32_t aring = sbase + LY::ring + warp * 1024 + lane * 16;
     const uint32_t abx = sbase + LY::bx + lane * 8, abs_ = sbase + LY::bs + lane * 8;
+    const bool blive = lane < 12 * NB;  // lanes that hold a live B column
+    auto ldb = [&](uint32_t base, int kt) { return blive ? lds_u2(base + kt * LY::bkt) : make_uint2(0u, 0u); };
     // address of tile t of the s-th slot after the ring cursor
     auto tile_addr = [&](int s, int t) {
       int sl = rslot + s;
@@ -384,7 +414,6 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
     const size_t kv_half = (size_t)a.kv.num_pages * a.kv.nhead * a.kv.page_size * kHeadDim;  // floats of K (or V) per layer
     const bool new_warp = rank == CL - 1 && warp == CW - 1;  // takes the position written by this step
     const float* kvbase = reinterpret_cast<const float*>(a.kv.pages);
-    constexpr bool kEarlyV = NB == 1;  // two rows: V is fetched after the QKV phase (register budget)
 
     // x = phase input; loads 4 consecutive features per thread and sequence row, stages x * norm_w as B fragments,
     // keeps rows [own0, own0 + ownn) for the residual add, leaves rstd in rstd[]
@@ -395,10 +424,11 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
         const float4 v = load4(b);
+        dstamp(43);
         ss[b] = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
         if (4 * tid >= own0 && 4 * tid < own0 + ownn) *reinterpret_cast<float4*>(xown + b * W2_ROWS + (4 * tid - own0)) = v;
-        stage_pair(smem + LY::bx, 4 * tid, b, v.x * g4.x, v.y * g4.y);
-        stage_pair(smem + LY::bx, 4 * tid + 2, b, v.z * g4.z, v.w * g4.w);
+        stage_pair<NB>(smem + LY::bx, 4 * tid, b, v.x * g4.x, v.y * g4.y);
+        stage_pair<NB>(smem + LY::bx, 4 * tid + 2, b, v.z * g4.z, v.w * g4.w);
         ss[b] = warp_sum(ss[b]);
         if (lane == 0) red[warp * NB + b] = ss[b];
       }
@@ -447,13 +477,13 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
     };
     // output rows [row0 + 16 rt, +16) of a residual phase: add the partial (and, where `carry`, the phase input)
     auto resid_add = [&](const float (&acc)[4], long long* dst, int row0, int rt, bool carry) {
-      float o[2][NB];
+      float o[2];
       quad_reduce<NB>(acc, tq, o);
       if (tq < NB) {
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const int rl = 16 * rt + gq + 8 * hf;
-          float v = tq == 0 ? o[hf][0] : o[hf][NB - 1];
+          float v = o[hf];
           if (carry) v += xown[tq * W2_ROWS + rl];
           red_add_fix(dst + (size_t)tq * DM + row0 + rl, f2fix(v));
         }
@@ -471,7 +501,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           const int u = 2 * rt + hk;
           uint2 bq[6];
 #pragma unroll
-          for (int kk = 0; kk < 6; ++kk) bq[kk] = lds_u2(abx + (24 * rank + 12 * kq + 6 * hk + kk) * 256);
+          for (int kk = 0; kk < 6; ++kk) bq[kk] = ldb(abx, 24 * rank + 12 * kq + 6 * hk + kk);
           dstamp(2 * u);
           mb_wait(full0 + 8 * u, (uint32_t)use & 1u);
           dstamp(2 * u + 1);
@@ -486,12 +516,11 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc0[e] += acc1[e];
-        float o[2][NB];
+        float o[2];
         quad_reduce<NB>(acc0, tq, o);
         if (tq < NB) {
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf)
-            halves[(kq * NB + tq) * QROWS + 16 * (3 * rh + rt) + gq + 8 * hf] = tq == 0 ? o[hf][0] : o[hf][NB - 1];
+          for (int hf = 0; hf < 2; ++hf) halves[(kq * NB + tq) * QROWS + 16 * (3 * rh + rt) + gq + 8 * hf] = o[hf];
         }
       }
       dstamp(12);
@@ -513,8 +542,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           kreg[it][b] = make_float4(0.f, 0.f, 0.f, 0.f);
           vreg[it][b] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (kvalid[it] && lane < 24) {
-            kreg[it][b] = __ldcg(reinterpret_cast<const float4*>(kl + koff[it][b]));
-            if (kEarlyV) vreg[it][b] = __ldcg(reinterpret_cast<const float4*>(kl + kv_half + koff[it][b]));
+            kreg[it][b] = ldg_cg_f4(kl + koff[it][b]);
           }
         }
 
@@ -523,6 +551,12 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       else stage_x(load_fix(xbuf(2 * l), NCL), a.attn_norm + (size_t)l * DM, 768 * sh + WO_ROWS * rank, WO_ROWS);
       stamp();
       ksplit_288(l);
+      // V rows: issued after the QKV MMAs (register budget), consumed after the exchange and the score pass
+#pragma unroll
+      for (int it = 0; it < MAXIT; ++it)
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+          if (kvalid[it] && lane < 24) vreg[it][b] = ldg_cg_f4(kl + kv_half + koff[it][b]);
       {
         // all-to-all: every CTA receives the K-slice sums of all four CTAs, [src][b][288]
         xarm(CL * NB * QROWS * 4);
@@ -570,14 +604,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 
       // ================= attention of head `head`: positions split over the CTAs =================
       {
-        if (!kEarlyV) {
-#pragma unroll
-          for (int it = 0; it < MAXIT; ++it)
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-              if (kvalid[it] && lane < 24) vreg[it][b] = __ldcg(reinterpret_cast<const float4*>(kl + kv_half + koff[it][b]));
-        }
         float* wp = reinterpret_cast<float*>(smem + LY::ra);  // [12][NB][100]
+        float scs[NB][MAXIT + 1];
+        float4 vnew[NB];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
           const float4 q4 = lane < 24 ? *reinterpret_cast<const float4*>(qkv_s + b * QROWS + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -587,11 +616,11 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
             const float4 k4 = kreg[it][b];
             sc[it] = k4.x * q4.x + k4.y * q4.y + k4.z * q4.z + k4.w * q4.w;
           }
-          float4 vn = make_float4(0.f, 0.f, 0.f, 0.f);
+          vnew[b] = make_float4(0.f, 0.f, 0.f, 0.f);
           sc[MAXIT] = 0.f;
           if (new_warp && lane < 24) {
             const float4 kn = *reinterpret_cast<const float4*>(qkv_s + b * QROWS + kHeadDim + 4 * lane);
-            vn = *reinterpret_cast<const float4*>(qkv_s + b * QROWS + 2 * kHeadDim + 4 * lane);
+            vnew[b] = *reinterpret_cast<const float4*>(qkv_s + b * QROWS + 2 * kHeadDim + 4 * lane);
             sc[MAXIT] = kn.x * q4.x + kn.y * q4.y + kn.z * q4.z + kn.w * q4.w;
           }
           // six independent butterfly reductions, interleaved
@@ -605,42 +634,44 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           float m = sc[MAXIT];
 #pragma unroll
           for (int it = 0; it < MAXIT; ++it) m = fmaxf(m, sc[it]);
+          if (lane == 0) red[16 + warp * NB + b] = m;
+#pragma unroll
+          for (int it = 0; it <= MAXIT; ++it) scs[b][it] = sc[it];
+        }
+        consumer_sync();
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          float M = red[16 + b];
+#pragma unroll
+          for (int w = 1; w < CW; ++w) M = fmaxf(M, red[16 + w * NB + b]);  // max over the CTA's positions (-inf if it has none)
           float lsum = 0.f;
           float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m > -INFINITY) {
+          if (M > -INFINITY) {
 #pragma unroll
             for (int it = 0; it <= MAXIT; ++it) {
-              const float e = sc[it] > -INFINITY ? expf(sc[it] - m) : 0.f;
-              const float4 v4 = it < MAXIT ? vreg[it < MAXIT ? it : 0][b] : vn;
+              const float e = scs[b][it] > -INFINITY ? __expf(scs[b][it] - M) : 0.f;
+              const float4 v4 = it < MAXIT ? vreg[it < MAXIT ? it : 0][b] : vnew[b];
               lsum += e;
               o.x = fmaf(e, v4.x, o.x); o.y = fmaf(e, v4.y, o.y); o.z = fmaf(e, v4.z, o.z); o.w = fmaf(e, v4.w, o.w);
             }
           }
           float* w = wp + (warp * NB + b) * WP_STRIDE;
-          if (lane == 0) { w[0] = m; w[1] = lsum; }
+          if (lane == 0) { w[0] = M; w[1] = lsum; }
           if (lane < 24) *reinterpret_cast<float4*>(w + 4 + 4 * lane) = o;
         }
         xarm(CL * NB * WP_STRIDE * 4);
         dstamp(18);
         consumer_sync();
-        // CTA partial (m, l, -, -, o[96]) -> every CTA of the cluster, 25 float4 per sequence row
+        // CTA partial (M, l, -, -, o[96]) -> every CTA of the cluster, 25 float4 per sequence row
         if (tid < 25 * NB) {
           const int b = tid / 25, c4 = tid % 25;
-          float M = -INFINITY;
-#pragma unroll
-          for (int w = 0; w < CW; ++w) M = fmaxf(M, wp[(w * NB + b) * WP_STRIDE]);
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (M > -INFINITY) {
 #pragma unroll
-            for (int w = 0; w < CW; ++w) {
-              const float* rec = wp + (w * NB + b) * WP_STRIDE;
-              const float f = rec[0] > -INFINITY ? expf(rec[0] - M) : 0.f;
-              const float4 v = *reinterpret_cast<const float4*>(rec + 4 * c4);
-              if (c4 == 0) acc.y = fmaf(f, v.y, acc.y);
-              else { acc.x = fmaf(f, v.x, acc.x); acc.y = fmaf(f, v.y, acc.y); acc.z = fmaf(f, v.z, acc.z); acc.w = fmaf(f, v.w, acc.w); }
-            }
+          for (int w = 0; w < CW; ++w) {
+            const float4 v = *reinterpret_cast<const float4*>(wp + (w * NB + b) * WP_STRIDE + 4 * c4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
           }
-          if (c4 == 0) acc.x = M;
+          if (c4 == 0) { acc.x = wp[b * WP_STRIDE]; acc.z = 0.f; acc.w = 0.f; }  // every warp stored the same M
           const uint32_t local = sbase + LY::rb + ((rank * NB + b) * WP_STRIDE + 4 * c4) * 4;
 #pragma unroll
           for (int s = 0; s < CL; ++s) xpush(local, s, acc);
@@ -662,7 +693,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
             den = fmaf(f, ar[(s * NB + b) * WP_STRIDE + 1], den);
             O = fmaf(f, ar[(s * NB + b) * WP_STRIDE + 4 + d], O);
           }
-          stage_one(smem + LY::bs, d, b, O / den);
+          stage_one<NB>(smem + LY::bs, d, b, O / den);
         }
         consumer_sync();
       }
@@ -678,7 +709,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 #pragma unroll
         for (int j = 0; j < 6; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
 #pragma unroll
-        for (int j = 0; j < 6; j += 2) { mma16816(acc0, A[j], lds_u2(abs_ + j * 256)); mma16816(acc1, A[j + 1], lds_u2(abs_ + (j + 1) * 256)); }
+        for (int j = 0; j < 6; j += 2) { mma16816(acc0, A[j], ldb(abs_, j)); mma16816(acc1, A[j + 1], ldb(abs_, j + 1)); }
         __syncwarp();
         if (lane == 0) mb_arrive(empty0 + 8 * 6);
         advance(3);
@@ -686,7 +717,11 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
         for (int e = 0; e < 4; ++e) acc0[e] += acc1[e];
         resid_add(acc0, x_mid, 768 * sh + WO_ROWS * rank, warp, head == 0);
       }
+      grid_arrive_relaxed(&a.state->barrier);
       stamp();
+      dstamp(41);
+      grid_wait_relaxed(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
+      dstamp(42);
 
       // ============ MLP: RMSNorm . w1|w3 of this CTA's 32 hidden units (K split over the 12 warps) ============
       stage_x(load_fix(x_mid, NHEAD), a.ffn_norm + (size_t)l * DM, W2_ROWS * rank, W2_ROWS);
@@ -699,7 +734,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           for (int e = 0; e < 4; ++e) acc[r][e] = 0.f;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const uint2 b0 = lds_u2(abx + (8 * warp + 2 * u) * 256), b1 = lds_u2(abx + (8 * warp + 2 * u + 1) * 256);
+          const uint2 b0 = ldb(abx, 8 * warp + 2 * u), b1 = ldb(abx, 8 * warp + 2 * u + 1);
           dstamp(24 + 2 * u);
           mb_wait(full0 + 8 * (7 + u), par);
           dstamp(25 + 2 * u);
@@ -715,35 +750,28 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
         float* part = reinterpret_cast<float*>(smem + LY::ra);  // [12][NB][64]
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          float o[2][NB];
+          float o[2];
           quad_reduce<NB>(acc[r], tq, o);
           if (tq < NB) {
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf)
-              part[(warp * NB + tq) * 64 + 16 * r + gq + 8 * hf] = tq == 0 ? o[hf][0] : o[hf][NB - 1];
+            for (int hf = 0; hf < 2; ++hf) part[(warp * NB + tq) * 64 + 16 * r + gq + 8 * hf] = o[hf];
           }
         }
         xarm(CL * NB * HUC * 4);
         dstamp(32);
         consumer_sync();
         dstamp(33);
-        if (tid < HUC * NB / 4) {  // 4 hidden units per thread: unit u -> rows 16R+g (w1) and 16R+8+g (w3), R = u / 8, g = u % 8
-          const int b = tid / (HUC / 4), u0 = 4 * (tid % (HUC / 4));
-          const int r1 = 16 * (u0 >> 3) + (u0 & 7);
-          float4 y1 = make_float4(0.f, 0.f, 0.f, 0.f), y3 = y1;
+        if (tid < HUC * NB) {  // hidden unit u of this CTA: rows 16R+g (w1) and 16R+8+g (w3), R = u / 8, g = u % 8
+          const int b = tid / HUC, u = tid % HUC;
+          const int r1 = 16 * (u >> 3) + (u & 7);
+          float y1 = 0.f, y3 = 0.f;
 #pragma unroll
-          for (int w = 0; w < CW; ++w) {
-            const float4 p1 = *reinterpret_cast<const float4*>(part + (w * NB + b) * 64 + r1);
-            const float4 p3 = *reinterpret_cast<const float4*>(part + (w * NB + b) * 64 + r1 + 8);
-            y1.x += p1.x; y1.y += p1.y; y1.z += p1.z; y1.w += p1.w;
-            y3.x += p3.x; y3.y += p3.y; y3.z += p3.z; y3.w += p3.w;
-          }
-          const float rs = rstd[b];
-          auto swiglu = [&](float g1, float g3) { g1 *= rs; g3 *= rs; return g1 / (1.f + expf(-g1)) * g3; };
-          const float4 hv = make_float4(swiglu(y1.x, y3.x), swiglu(y1.y, y3.y), swiglu(y1.z, y3.z), swiglu(y1.w, y3.w));
-          const uint32_t local = sbase + LY::hrecv + (b * HU + rank * HUC + u0) * 4;
+          for (int w = 0; w < CW; ++w) { y1 += part[(w * NB + b) * 64 + r1]; y3 += part[(w * NB + b) * 64 + r1 + 8]; }
+          y1 *= rstd[b]; y3 *= rstd[b];
+          const float hv = y1 / (1.f + expf(-y1)) * y3;
+          const uint32_t local = sbase + LY::hrecv + (b * HU + rank * HUC + u) * 4;
 #pragma unroll
-          for (int s = 0; s < CL; ++s) xpush(local, s, hv);
+          for (int s = 0; s < CL; ++s) st_async_f1(mapa_u32(local, s), hv, mapa_u32(xbar + 8 * (xc & 1), s));
         }
         dstamp(34);
         xwait();
@@ -751,7 +779,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
         if (tid < HU * NB / 2) {
           const int b = tid / (HU / 2), k = 2 * (tid % (HU / 2));
           const float2 v = *reinterpret_cast<const float2*>(smem + LY::hrecv + (b * HU + k) * 4);
-          stage_pair(smem + LY::bs, k, b, v.x, v.y);
+          stage_pair<NB>(smem + LY::bs, k, b, v.x, v.y);
         }
         consumer_sync();
       }
@@ -768,7 +796,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 #pragma unroll
           for (int j = 0; j < 8; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) { mma16816(acc0, A[j], lds_u2(abs_ + j * 256)); mma16816(acc1, A[j + 1], lds_u2(abs_ + (j + 1) * 256)); }
+          for (int j = 0; j < 8; j += 2) { mma16816(acc0, A[j], ldb(abs_, j)); mma16816(acc1, A[j + 1], ldb(abs_, j + 1)); }
           __syncwarp();
           if (lane == 0) mb_arrive(empty0 + 8 * (11 + u));
           advance(4);
@@ -777,7 +805,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           resid_add(acc0, x_out, W2_ROWS * rank, 2 * warp + u, cl == 0);
         }
       }
+      grid_arrive_relaxed(&a.state->barrier);
       stamp();
+      grid_wait_relaxed(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
     }
 
     dbg = false;
@@ -806,7 +836,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       }
       stamp();
       // the step's only device-wide barrier: logits complete, every CTA is done reading the residual buffers
-      grid_barrier(&a.state->barrier, (epoch + 1) * (unsigned)G);
+      grid_barrier(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
       stamp();
     }
     // clear the residual buffers of this step for the next one (the last reader is past the barrier)
