@@ -168,6 +168,16 @@ def test_full_size_greedy_matches_reference_golden():
         assert torch.equal(o4, r4)
     else:
         assert (o4 == r4).float().mean().item() > 0.9
+    # two sequence rows take the cluster decode kernel's NB = 2 instance: 1 clip + CFG, and 2 clips without
+    for nclip, cfg in ((1, 3.0), (2, 1.0)):
+        f = make_avclip_features(nclip, 91 + nclip)
+        o = m.generate(frames=f.cuda(), max_new_tokens=24, use_sampling=False, prompt_is_encoded=True, cfg_scale=cfg,
+                       return_sampled_indices=True, _decode_audio=False, _return_logits=True)
+        r, lg = vo.generate_tokens(oracle, f.reshape(nclip, 32, 768), max_new_tokens=24, cfg_scale=cfg, collect_logits=True)
+        assert rel_err(o["_logits"][1:].cpu(), lg) < 2e-5
+        gaps = torch.topk(lg, 2, dim=-1).values
+        if float((gaps[..., 0] - gaps[..., 1]).min()) > 1e-3:
+            assert torch.equal(o["sampled_indices"].cpu(), r)
 
 
 # ---- tensor-core (bf16 activation) path ------------------------------------------------------------------

@@ -380,7 +380,7 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
       pa.wstream = w.wstream;
       pa.xfix = ws.xfix;
       { const char* rl = getenv("VAURA_CLUSTER_RING"); pa.prefetch_ahead = rl ? atoi(rl) : 0; }
-      { const char* pc = getenv("VAURA_CLUSTER_PACE"); pa.pace_cycles = pc ? atoi(pc) : 0; }
+      { const char* pc = getenv("VAURA_CLUSTER_L2_AHEAD"); pa.pace_cycles = pc ? atoi(pc) : -1; }
       CU(cudaMemsetAsync(ws.xfix, 0, cluster_xfix_bytes(rows, d.num_layers), st));
     }
     for (int i = 0; i < nsteps; ++i) {

@@ -122,7 +122,7 @@ struct PersistArgs {
   StepState* state;
   unsigned long long* timing;  // optional: phase timestamps (ns) of CTA `timing_cta`
   int timing_cta;
-  int pace_cycles;  // cluster variant: minimum SM cycles between two 12 KB weight copies of a CTA (0 = unpaced)
+  int pace_cycles;  // cluster variant: units of L2 prefetch ahead of the shared-memory fill (< 0: default)
   SampleArgs sample;
   int L, D, F, H, Kc, V, S, batch, cond_dim, cond_tokens, atpvf, slot_cap, prefetch_ahead;
   float eps, scale;
