@@ -14,14 +14,17 @@ from vaura_b200.synthetic import FULL_CODEC, FULL_SAMPLER, make_avclip_features 
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 120
+MODE = sys.argv[3] if len(sys.argv) > 3 else "topk"
+SKW = {"topk": dict(use_sampling=True, top_k=128), "argmax": dict(use_sampling=False), "nofilter": dict(use_sampling=True, top_k=0),
+       "topp": dict(use_sampling=True, top_k=0, top_p=0.9)}[MODE]
 m = build_model(FULL_SAMPLER, FULL_CODEC)
 feats = make_avclip_features(B, 2).cuda()
 for _ in range(2):
-    m.generate(frames=feats, max_new_tokens=T, use_sampling=True, top_k=128, prompt_is_encoded=True, _decode_audio=False)
+    m.generate(frames=feats, max_new_tokens=T, prompt_is_encoded=True, **SKW, _decode_audio=False)
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 ev[0].record()
-m.generate(frames=feats, max_new_tokens=T, use_sampling=True, top_k=128, prompt_is_encoded=True, _decode_audio=False)
+m.generate(frames=feats, max_new_tokens=T, prompt_is_encoded=True, **SKW, _decode_audio=False)
 ev[1].record()
 torch.cuda.synchronize()
 print(f"generate {T} tokens: {ev[0].elapsed_time(ev[1]):.2f} ms -> {ev[0].elapsed_time(ev[1]) / (T + 8) * 1e3:.1f} us per step (incl. first pass)")
