@@ -87,7 +87,8 @@ struct Lay {
   static constexpr int rope = red + 256;                    // [96] f32
   static constexpr int bars = rope + kHeadDim * 4;          // full[13], empty[13], xbar[2]
   static constexpr int sargs = bars + 32 * 8;               // SampleArgs copy
-  static constexpr int total = sargs + 256;
+  static constexpr int kofft = sargs + 256;                 // [12 warps][MAXIT][NB] int: K/V row offsets of a warp's positions
+  static constexpr int total = kofft + CW * MAXIT * NB * 4;
   static_assert(CW * NB * WP_STRIDE * 4 <= ra_bytes, "attention warp partials fit alias group A");
   static_assert(CW * 64 * NB * 4 <= ra_bytes, "w13 partials fit alias group A");
   static_assert(sizeof(SampleArgs) <= 256, "SampleArgs copy");
@@ -288,7 +289,8 @@ __device__ __forceinline__ void quad_reduce(const float (&c)[4], int tq, float (
 
 }  // namespace
 
-template <int NB>
+// TM: phase timestamps of one CTA (profiles/cluster_timing.py); the production instance carries none of that code
+template <int NB, bool TM>
 __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid_constant__ PersistArgs a) {
   using LY = Lay<NB>;
   constexpr int NSLOT = LY::nslot;
@@ -396,30 +398,35 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 
     int stamp_i = 0;
     auto stamp = [&]() {
-      if (a.timing && cta == a.timing_cta && tid == 0) a.timing[stamp_i] = now_ns();
-      ++stamp_i;
+      if (TM) {
+        if (cta == a.timing_cta && tid == 0) a.timing[stamp_i] = now_ns();
+        ++stamp_i;
+      }
     };
     stamp();
     bool dbg = false;  // fine-grained stamps of one layer (profiles/cluster_timing.py)
-    auto dstamp = [&](int k) { if (dbg) a.timing[256 + k] = now_ns(); };
+    auto dstamp = [&](int k) { if (TM && dbg) a.timing[256 + k] = now_ns(); };
 
     if (tid < kHeadDim) rope_s[tid] = a.rope[(size_t)p * kHeadDim + tid];
 
     // attention work split: old positions [0, p) in four chunks, one per CTA; warp w takes items w, w+12, ...
     const int chunk = (p + CL - 1) / CL;
     const int j0 = rank * chunk, j1 = min(p, j0 + chunk);
-    int koff[MAXIT][NB];
-    bool kvalid[MAXIT];
+    // row offsets live in shared memory (one table per warp), validity in a bit mask: registers are the scarce resource
+    int* kofft = reinterpret_cast<int*>(smem + LY::kofft) + warp * MAXIT * NB;
+    unsigned kvmask = 0;
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
       const int j = j0 + warp + CW * it;
-      kvalid[it] = j < j1;
-#pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        const int page = kvalid[it] ? a.kv.page_table[b * a.kv.max_pages_per_seq + j / a.kv.page_size] : 0;
-        koff[it][b] = ((page * a.kv.nhead + head) * a.kv.page_size + (j % a.kv.page_size)) * kHeadDim + 4 * lane;
+      if (j < j1) kvmask |= 1u << it;
+      if (lane < NB) {
+        const int page = j < j1 ? a.kv.page_table[lane * a.kv.max_pages_per_seq + j / a.kv.page_size] : 0;
+        kofft[it * NB + lane] = ((page * a.kv.nhead + head) * a.kv.page_size + (j % a.kv.page_size)) * kHeadDim;
       }
     }
+    __syncwarp();
+    auto kvalid_ = [&](int it) { return (kvmask >> it) & 1u; };
+    auto koff_ = [&](int it, int b) { return kofft[it * NB + b] + 4 * lane; };
     const size_t kv_half = (size_t)a.kv.num_pages * a.kv.nhead * a.kv.page_size * kHeadDim;  // floats of K (or V) per layer
     const bool new_warp = rank == CL - 1 && warp == CW - 1;  // takes the position written by this step
     const float* kvbase = reinterpret_cast<const float*>(a.kv.pages);
@@ -535,9 +542,10 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       dstamp(12);
     };
 
+    constexpr bool kLate = NB > 1;  // two sequence rows: K/V registers are filled late (see below)
     for (int l = 0; l < L; ++l) {
       const uint32_t par = (uint32_t)l & 1u;
-      dbg = a.timing && cta == a.timing_cta && tid == 0 && l == L / 2;
+      if (TM) dbg = cta == a.timing_cta && tid == 0 && l == L / 2;
       long long* x_mid = xbuf(2 * l + 1);
       long long* x_out = xbuf(2 * l + 2);
 
@@ -548,11 +556,13 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       for (int it = 0; it < MAXIT; ++it)
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          kreg[it][b] = make_float4(0.f, 0.f, 0.f, 0.f);
-          vreg[it][b] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kvalid[it] && lane < 24) {
-            kreg[it][b] = ldg_cg_f4(kl + koff[it][b]);
-            if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(kl + kv_half + koff[it][b]));  // V row: 3 lines
+          if (!kLate) kreg[it][b] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kvalid_(it) && lane < 24) {
+            if (!kLate) kreg[it][b] = ldg_cg_f4(kl + koff_(it, b));
+            if ((lane & 7) == 0) {  // three 128-byte lines per row
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(kl + kv_half + koff_(it, b)));
+              if (kLate) asm volatile("prefetch.global.L2 [%0];" ::"l"(kl + koff_(it, b)));
+            }
           }
         }
 
@@ -561,12 +571,17 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       else stage_x(load_fix(xbuf(2 * l), NCL), a.attn_norm + (size_t)l * DM, 768 * sh + WO_ROWS * rank, WO_ROWS);
       stamp();
       ksplit_288(l);
-      // V rows: issued after the QKV MMAs (register budget), consumed after the exchange and the score pass
+      // One sequence row: K was fetched at the top of the layer, V is fetched now and hidden behind the exchange.
+      // Two rows: the rows were prefetched into L2 at the top; K is fetched now, V after the score pass when the K
+      // registers are dead (a spilled register costs an L2 round trip on this path).
 #pragma unroll
       for (int it = 0; it < MAXIT; ++it)
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
-          if (kvalid[it] && lane < 24) vreg[it][b] = ldg_cg_f4(kl + kv_half + koff[it][b]);
+        for (int b = 0; b < NB; ++b) {
+          const bool live = kvalid_(it) && lane < 24;
+          if (kLate) kreg[it][b] = live ? ldg_cg_f4(kl + koff_(it, b)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          else vreg[it][b] = live ? ldg_cg_f4(kl + kv_half + koff_(it, b)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       {
         // all-to-all: every CTA receives the K-slice sums of all four CTAs, [src][b][288]
         xarm(CL * NB * QROWS * 4);
@@ -590,7 +605,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           float y = 0.f;
 #pragma unroll
           for (int s = 0; s < CL; ++s) y += qr[s * NB * QROWS + e];
-          y *= rstd[b];
+          y *= b ? rstd[NB - 1] : rstd[0];  // no runtime-indexed register array
           const float other = __shfl_xor_sync(0xffffffffu, y, 1);  // partner of the RoPE pair (rows 2m, 2m+1)
           const int sec = i / kHeadDim, d = i % kHeadDim;
           float o = y;
@@ -639,7 +654,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 #pragma unroll
             for (int it = 0; it <= MAXIT; ++it) sc[it] += __shfl_xor_sync(0xffffffffu, sc[it], o);
 #pragma unroll
-          for (int it = 0; it < MAXIT; ++it) sc[it] = kvalid[it] ? sc[it] * a.scale : -INFINITY;
+          for (int it = 0; it < MAXIT; ++it) sc[it] = kvalid_(it) ? sc[it] * a.scale : -INFINITY;
           sc[MAXIT] = new_warp ? sc[MAXIT] * a.scale : -INFINITY;
           float m = sc[MAXIT];
 #pragma unroll
@@ -647,6 +662,13 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           if (lane == 0) red[16 + warp * NB + b] = m;
 #pragma unroll
           for (int it = 0; it <= MAXIT; ++it) scs[b][it] = sc[it];
+        }
+        if (kLate) {
+#pragma unroll
+          for (int it = 0; it < MAXIT; ++it)
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+              vreg[it][b] = kvalid_(it) && lane < 24 ? ldg_cg_f4(kl + kv_half + koff_(it, b)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         consumer_sync();
 #pragma unroll
@@ -777,7 +799,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           float y1 = 0.f, y3 = 0.f;
 #pragma unroll
           for (int w = 0; w < CW; ++w) { y1 += part[(w * NB + b) * 64 + r1]; y3 += part[(w * NB + b) * 64 + r1 + 8]; }
-          y1 *= rstd[b]; y3 *= rstd[b];
+          const float rs = b ? rstd[NB - 1] : rstd[0];
+          y1 *= rs; y3 *= rs;
           const float hv = y1 / (1.f + expf(-y1)) * y3;
           const uint32_t local = sbase + LY::hrecv + (b * HU + rank * HUC + u) * 4;
 #pragma unroll
@@ -842,7 +865,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
         float y = 0.f;
 #pragma unroll
         for (int s = 0; s < CL; ++s) y += rr[(s * NB + b) * HOWN + ii];
-        a.logits[(size_t)b * (a.Kc * a.V) + cl * HROWS + rank * HOWN + ii] = y * rstd[b];
+        a.logits[(size_t)b * (a.Kc * a.V) + cl * HROWS + rank * HOWN + ii] = y * (b ? rstd[NB - 1] : rstd[0]);
       }
       stamp();
       // the step's only device-wide barrier: logits complete, every CTA is done reading the residual buffers
@@ -890,12 +913,12 @@ bool cluster_supported(int rows, int L, int D, int F, int H, int head_rows, int 
 
 size_t cluster_xfix_bytes(int rows, int L) { return (size_t)(2 * L + 1) * rows * DM * sizeof(long long); }
 
-template <int NB>
+template <int NB, bool TM>
 static cudaError_t launch_cluster_t(const PersistArgs& a, cudaStream_t st) {
   static int mode = 0;  // 0 = not initialised, 1 = cooperative + cluster, 2 = cluster only
   constexpr int smem = Lay<NB>::total;
   if (!mode) {
-    cudaError_t e = cudaFuncSetAttribute(decode_step_cluster<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(decode_step_cluster<NB, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t qc{};
     qc.gridDim = dim3(CL * NCL); qc.blockDim = dim3(kThreadsC); qc.dynamicSmemBytes = smem;
@@ -904,7 +927,7 @@ static cudaError_t launch_cluster_t(const PersistArgs& a, cudaStream_t st) {
     qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
     qc.attrs = qa; qc.numAttrs = 1;
     int nclusters = 0;
-    e = cudaOccupancyMaxActiveClusters(&nclusters, decode_step_cluster<NB>, &qc);
+    e = cudaOccupancyMaxActiveClusters(&nclusters, decode_step_cluster<NB, TM>, &qc);
     if (e != cudaSuccess) return e;
     if (nclusters < NCL) return cudaErrorCooperativeLaunchTooLarge;  // all clusters must be co-resident (device-wide barriers)
     mode = 1;
@@ -918,22 +941,23 @@ static cudaError_t launch_cluster_t(const PersistArgs& a, cudaStream_t st) {
   at[1].val.cooperative = 1;
   cfg.attrs = at;
   cfg.numAttrs = mode == 1 ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_step_cluster<NB>, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_step_cluster<NB, TM>, a);
   if (e != cudaSuccess && mode == 1) {
     // cooperative + cluster launch rejected by this driver: co-residency is still guaranteed by the occupancy query
     // above (32 clusters of one CTA per SM on an otherwise idle device), so launch with the cluster attribute alone
     (void)cudaGetLastError();
     mode = 2;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, decode_step_cluster<NB>, a);
+    e = cudaLaunchKernelEx(&cfg, decode_step_cluster<NB, TM>, a);
   }
   return e;
 }
 
 cudaError_t launch_decode_cluster(const PersistArgs& a, int rows, cudaStream_t st) {
+  const bool tm = a.timing != nullptr;
   switch (rows) {
-    case 1: return launch_cluster_t<1>(a, st);
-    case 2: return launch_cluster_t<2>(a, st);
+    case 1: return tm ? launch_cluster_t<1, true>(a, st) : launch_cluster_t<1, false>(a, st);
+    case 2: return tm ? launch_cluster_t<2, true>(a, st) : launch_cluster_t<2, false>(a, st);
   }
   return cudaErrorInvalidValue;
 }
