@@ -236,16 +236,18 @@ def main():
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     step_bytes = sampler_step_bytes(d)
     if rows <= 4:
-        # rows <= 4: the whole decode step is ONE persistent kernel (decode_step_persistent); timed through the
-        # token-only generate (CUDA events around 227 back-to-back launches of that kernel + 1 first pass)
+        # rows <= 4: the whole decode step is ONE persistent kernel (rows <= 2: decode_step_cluster, 32 clusters x 4
+        # CTAs; rows 3-4: decode_step_persistent); timed through the token-only generate (CUDA events around 227
+        # back-to-back launches of that kernel + 1 first pass)
         def tokens_only_r():
             model.generate(frames=feats_dev, clip_indices=clip_ids, _decode_audio=False, **kw)
         tokens_only_r()
         k_ms = timed(tokens_only_r, 3) / 3 / (T + 8)
         kv_bytes = 24 * 2 * d.d_model * 4 * rows * (T + 8) / 2  # fp32 KV read, mean context (S/2 positions)
         alg_bytes = step_bytes + kv_bytes
-        kname = f"decode_step_persistent<{rows}> (whole decode step: 24 layers + heads + sampling)"
-        key = f"decode_step_persistent_rows{rows}"
+        kern = "decode_step_cluster" if rows <= 2 else "decode_step_persistent"
+        kname = f"{kern}<{rows}> (whole decode step: 24 layers + heads + sampling)"
+        key = f"{kern}_rows{rows}"
     else:
         # rows >= 16: tcgen05 linear over w1|w3 (25.2 MB of weights per launch), 24 different matrices back to back
         w13 = model.sampler.weights["w13"]

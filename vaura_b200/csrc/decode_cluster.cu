@@ -930,7 +930,10 @@ static cudaError_t launch_cluster_t(const PersistArgs& a, cudaStream_t st) {
     e = cudaOccupancyMaxActiveClusters(&nclusters, decode_step_cluster<NB, TM>, &qc);
     if (e != cudaSuccess) return e;
     if (nclusters < NCL) return cudaErrorCooperativeLaunchTooLarge;  // all clusters must be co-resident (device-wide barriers)
-    mode = 1;
+    // VAURA_CLUSTER_NOCOOP=1: skip the cooperative attribute (Nsight Compute's kernel replay rejects cooperative
+    // cluster launches); co-residency is already established by the occupancy query above
+    const char* nc = getenv("VAURA_CLUSTER_NOCOOP");
+    mode = (nc && nc[0] == '1') ? 2 : 1;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(CL * NCL); cfg.blockDim = dim3(kThreadsC); cfg.dynamicSmemBytes = smem; cfg.stream = st;
