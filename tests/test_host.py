@@ -177,3 +177,39 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+# ---- weight streams of the cluster-persistent decode kernel (weights.py: pack_cluster_stream) --------------------
+STREAM_SHAPES = {"qkv": (4608, 1536), "wo": (1536, 1536), "w13": (8192, 1536), "w2": (1536, 4096), "heads": (9216, 1536)}
+
+
+@pytest.mark.parametrize("phase", sorted(STREAM_SHAPES))
+def test_cluster_stream_index_is_a_bijection(phase):
+    """Every weight element appears exactly once in the streams (q|k|v once for the two clusters of a head)."""
+    from vaura_b200.weights import CLUSTER_PHASE_SLOTS, CLUSTER_SLOT_ELEMS, cluster_stream_index
+
+    rows, cols = STREAM_SHAPES[phase]
+    idx = cluster_stream_index(phase)
+    groups = 16 if phase == "qkv" else 32
+    assert idx.shape == (groups, 4, CLUSTER_PHASE_SLOTS[phase], 12, 2, 32, 8)
+    assert idx.numel() == rows * cols and idx.numel() == groups * 4 * CLUSTER_PHASE_SLOTS[phase] * CLUSTER_SLOT_ELEMS
+    counts = torch.bincount(idx.reshape(-1), minlength=rows * cols)
+    assert int(counts.min()) == 1 and int(counts.max()) == 1
+
+
+def test_cluster_stream_tile_is_an_mma_a_fragment():
+    """A 512-byte tile holds a 16 x 16 block in mma.m16n8k16 A-fragment order: lane 4g+t owns rows g, g+8 and k 2t, 2t+1,
+    2t+8, 2t+9; the warp/slot map is the one csrc/decode_cluster.cu consumes (wo: warp w = row tile w, tile j = k-tile j)."""
+    from vaura_b200.weights import cluster_stream_index
+
+    idx = cluster_stream_index("wo")  # [cluster][rank][slot][warp][tile][lane][e]
+    cl, r, slot, w, t = 5, 2, 1, 7, 1
+    tile = idx[cl, r, slot, w, t]  # [32][8] flat indices into wo (1536 x 1536)
+    row0 = 768 * (cl % 2) + 192 * r + 16 * w
+    col0 = 96 * (cl // 2) + 16 * (2 * slot + t)
+    for lane in (0, 5, 31):
+        g, tq = lane // 4, lane % 4
+        want = [(g, 2 * tq), (g, 2 * tq + 1), (g + 8, 2 * tq), (g + 8, 2 * tq + 1),
+                (g, 2 * tq + 8), (g, 2 * tq + 9), (g + 8, 2 * tq + 8), (g + 8, 2 * tq + 9)]
+        got = [(int(v) // 1536 - row0, int(v) % 1536 - col0) for v in tile[lane]]
+        assert got == want
