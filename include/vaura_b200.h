@@ -106,8 +106,8 @@ typedef struct {
   const uint16_t* w_heads_t;
   /* Optional third copy for the cluster-persistent decode kernel (rows <= 2; csrc/decode_cluster.cu), as 12288-byte
    * slots of 16x16 bf16 tiles in mma.m16n8k16 A-fragment register order, in consumption order:
-   *   [16 heads][4 ranks][L][18 slots]           q|k|v rows of a head, K split over the 4 CTAs of a cluster
-   *   [128 CTAs][L x (3 wo + 16 w13 + 8 w2) + 18 heads slots]
+   *   [16 heads][4 ranks][L][18 q|k|v + 6 wo slots]   shared by the two clusters that serve a head
+   *   [128 CTAs][L x (16 w13 + 8 w2) + 18 heads slots]
    * (vaura_b200/weights.py: pack_cluster_stream documents the exact index map).  NULL disables that kernel. */
   const uint8_t* wstream;
 } vaura_sampler_weights;

@@ -190,7 +190,7 @@ def test_cluster_stream_index_is_a_bijection(phase):
 
     rows, cols = STREAM_SHAPES[phase]
     idx = cluster_stream_index(phase)
-    groups = 16 if phase == "qkv" else 32
+    groups = 16 if phase in ("qkv", "wo") else 32
     assert idx.shape == (groups, 4, CLUSTER_PHASE_SLOTS[phase], 12, 2, 32, 8)
     assert idx.numel() == rows * cols and idx.numel() == groups * 4 * CLUSTER_PHASE_SLOTS[phase] * CLUSTER_SLOT_ELEMS
     counts = torch.bincount(idx.reshape(-1), minlength=rows * cols)
@@ -199,14 +199,16 @@ def test_cluster_stream_index_is_a_bijection(phase):
 
 def test_cluster_stream_tile_is_an_mma_a_fragment():
     """A 512-byte tile holds a 16 x 16 block in mma.m16n8k16 A-fragment order: lane 4g+t owns rows g, g+8 and k 2t, 2t+1,
-    2t+8, 2t+9; the warp/slot map is the one csrc/decode_cluster.cu consumes (wo: warp w = row tile w, tile j = k-tile j)."""
+    2t+8, 2t+9; the warp/slot map is the one csrc/decode_cluster.cu consumes (wo: warp w = row tiles 2w, 2w+1; slots 0-2 hold
+    k-tiles 0-2 of the head, slots 3-5 k-tiles 3-5)."""
     from vaura_b200.weights import cluster_stream_index
 
-    idx = cluster_stream_index("wo")  # [cluster][rank][slot][warp][tile][lane][e]
-    cl, r, slot, w, t = 5, 2, 1, 7, 1
-    tile = idx[cl, r, slot, w, t]  # [32][8] flat indices into wo (1536 x 1536)
-    row0 = 768 * (cl % 2) + 192 * r + 16 * w
-    col0 = 96 * (cl // 2) + 16 * (2 * slot + t)
+    idx = cluster_stream_index("wo")  # [head][rank][slot][warp][tile][lane][e]
+    h, r, slot, w, t = 5, 2, 4, 7, 1
+    tile = idx[h, r, slot, w, t]  # [32][8] flat indices into wo (1536 x 1536)
+    jj = 2 * (slot % 3) + t
+    row0 = 384 * r + 16 * (2 * w + jj // 3)
+    col0 = 96 * h + 16 * (3 * (slot // 3) + jj % 3)
     for lane in (0, 5, 31):
         g, tq = lane // 4, lane % 4
         want = [(g, 2 * tq), (g, 2 * tq + 1), (g + 8, 2 * tq), (g + 8, 2 * tq + 1),

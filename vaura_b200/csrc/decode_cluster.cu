@@ -37,6 +37,7 @@
 //
 // Replaces the same reference lines as decode_persistent.cu (llama.py:445-517 for one position, vaura_model.py:775-827).
 #include <cstdlib>
+#include <type_traits>
 
 #include "sampling.cuh"
 
@@ -57,10 +58,9 @@ constexpr int HROWS = 288;                 // heads rows per cluster (9 * 1024 /
 constexpr int HOWN = HROWS / CL;           // 72
 constexpr int HU = FF / NCL;               // 128 hidden units per cluster
 constexpr int HUC = HU / CL;               // 32 hidden units per CTA
-constexpr int WO_ROWS = 192;               // wo rows per CTA: [768 s + 192 r, +192)
-constexpr int W2_ROWS = DM / CL;           // 384 w2 rows per CTA
-constexpr int UNITS_PER_LAYER = 13;        // 6 qkv (3 slots) + 1 wo (3) + 4 w13 (4) + 2 w2 (4) = 45 slots
-constexpr int QKV_SLOTS = 18, PRIV_SLOTS = 27, HEAD_SLOTS = 18;
+constexpr int W2_ROWS = DM / CL;           // 384 wo / w2 rows per CTA
+constexpr int SH_SLOTS = 24;               // shared stream per layer: 18 q|k|v + 6 wo slots (two k halves of 3)
+constexpr int PRIV_SLOTS = 24, HEAD_SLOTS = 18;  // private stream per layer: 16 w1|w3 + 8 w2 slots; heads at the end
 constexpr int HEAD_UNITS = 6;
 constexpr int MAXIT = 5;                   // attention items (positions) per warp: 4 CTAs x 12 warps x 5 = 240 old positions
 constexpr int WP_STRIDE = 100;             // floats per attention partial: m, l, pad, pad, o[96]
@@ -70,6 +70,7 @@ constexpr float kFixInv = 2.3283064365386963e-10f;
 template <int NB>
 struct Lay {
   static constexpr int nslot = NB == 1 ? 17 : 15;
+  static constexpr int upl = 12 + NB;                       // units per layer: 6 qkv + NB wo (3 slots each) + 4 w13 + 2 w2 (4 slots each)
   static constexpr int bkt = 96 * NB;                       // bytes of one k-tile of B fragments: 3 NB columns x 4 lanes x 8 B
   static constexpr int ring = 0;
   static constexpr int bx = ring + nslot * SLOT;            // B fragments of the normed residual [96 k-tiles][3 NB cols][4][2] u32
@@ -85,10 +86,10 @@ struct Lay {
   static constexpr int xown = hrecv + NB * HU * 4;          // [NB][384] f32: this CTA's rows of the phase input
   static constexpr int red = xown + NB * W2_ROWS * 4;       // [12][NB] f32 sums of squares, [16 + 12*NB] score maxima
   static constexpr int rope = red + 256;                    // [96] f32
-  static constexpr int bars = rope + kHeadDim * 4;          // full[13], empty[13], xbar[2]
+  static constexpr int bars = rope + kHeadDim * 4;          // full[upl], empty[upl], xbar[2]
   static constexpr int sargs = bars + 32 * 8;               // SampleArgs copy
-  static constexpr int kofft = sargs + 256;                 // [12 warps][MAXIT][NB] int: K/V row offsets of a warp's positions
-  static constexpr int total = kofft + CW * MAXIT * NB * 4;
+  static constexpr int kofft = sargs + 256;                 // [12 warps][MAXIT] int: K/V row offsets of a warp's positions
+  static constexpr int total = kofft + CW * MAXIT * 4;
   static_assert(CW * NB * WP_STRIDE * 4 <= ra_bytes, "attention warp partials fit alias group A");
   static_assert(CW * 64 * NB * 4 <= ra_bytes, "w13 partials fit alias group A");
   static_assert(sizeof(SampleArgs) <= 256, "SampleArgs copy");
@@ -294,18 +295,23 @@ template <int NB, bool TM>
 __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid_constant__ PersistArgs a) {
   using LY = Lay<NB>;
   constexpr int NSLOT = LY::nslot;
+  constexpr int UPL = LY::upl;          // units per layer: 6 qkv + NB wo + 4 w13 + 2 w2
+  constexpr int U_WO = 6, U_W13 = 6 + NB, U_W2 = 10 + NB;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, G = gridDim.x;
   const int rank = (int)cluster_rank();
   const int cl = cta / CL;                // cluster
-  const int head = cl >> 1, sh = cl & 1;  // attention head, which half of the wo rows
+  const int head = cl >> 1, sh = cl & 1;  // attention head; which of the head's two clusters
+  // The attention block (q|k|v, attention, wo) works on ONE sequence row per cluster: with two rows the two clusters of
+  // a head take one row each (and the full wo K range), with one row both compute the row and split the wo K range.
+  const int ab = NB == 1 ? 0 : sh;
   const uint32_t sbase = s_u32(smem);
-  const uint32_t full0 = sbase + LY::bars, empty0 = full0 + UNITS_PER_LAYER * 8, xbar = empty0 + UNITS_PER_LAYER * 8;
+  const uint32_t full0 = sbase + LY::bars, empty0 = full0 + UPL * 8, xbar = empty0 + UPL * 8;
   const int L = a.L;
 
   if (tid == 0) {
-    for (int i = 0; i < UNITS_PER_LAYER; ++i) { mb_init(full0 + 8 * i, 1); mb_init(empty0 + 8 * i, CW); }
+    for (int i = 0; i < UPL; ++i) { mb_init(full0 + 8 * i, 1); mb_init(empty0 + 8 * i, CW); }
     mb_init(xbar, 1);
     mb_init(xbar + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -320,44 +326,55 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       uint64_t pol_first, pol_last;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
-      // q|k|v stream of (head, rank): read by this CTA and by its twin in the other cluster of the head
-      const uint8_t* qsrc = a.wstream + (size_t)(head * CL + rank) * L * QKV_SLOTS * SLOT;
-      const uint8_t* psrc = a.wstream + (size_t)NHEAD * CL * L * QKV_SLOTS * SLOT +
+      // shared stream of (head, rank): read by this CTA and by its twin in the other cluster of the head
+      const uint8_t* shared = a.wstream + (size_t)(head * CL + rank) * L * SH_SLOTS * SLOT;
+      const uint8_t* priv = a.wstream + (size_t)NHEAD * CL * L * SH_SLOTS * SLOT +
                             (size_t)cta * ((size_t)L * PRIV_SLOTS + HEAD_SLOTS) * SLOT;
-      const int nq_layers = UNITS_PER_LAYER * L, NQ = nq_layers + HEAD_UNITS;
+      const int nq_layers = UPL * L, NQ = nq_layers + HEAD_UNITS;
+      // unit q of the step: barrier index, slots, source, L2 policy
+      auto unit = [&](int q, int& i, int& n, const uint8_t*& src, bool& is_shared) {
+        if (q >= nq_layers) { i = q - nq_layers; n = 3; src = priv + ((size_t)L * PRIV_SLOTS + 3 * i) * SLOT; is_shared = false; return; }
+        const int l = q / UPL;
+        i = q % UPL;
+        if (i < U_WO) { n = 3; src = shared + ((size_t)l * SH_SLOTS + 3 * i) * SLOT; is_shared = true; }
+        else if (i < U_W13) { n = 3; src = shared + ((size_t)l * SH_SLOTS + 18 + 3 * (NB == 1 ? sh : i - U_WO)) * SLOT; is_shared = true; }
+        else if (i < U_W2) { n = 4; src = priv + ((size_t)l * PRIV_SLOTS + 4 * (i - U_W13)) * SLOT; is_shared = false; }
+        else { n = 4; src = priv + ((size_t)l * PRIV_SLOTS + 16 + 4 * (i - U_W2)) * SLOT; is_shared = false; }
+      };
       int rel = 0;       // units whose release by the 12 compute warps has been observed (in order)
       int freed = 0;     // ring slots of those units
       int issued = 0;    // ring slots handed to the copy engine so far
       int wslot = 0;     // ring position of the next slot
       const int ring_limit = a.prefetch_ahead >= 4 && a.prefetch_ahead < NSLOT ? a.prefetch_ahead : NSLOT;  // experiment knob
-      // L2 prefetch cursor: runs `ahead` units in front of the shared-memory fill so that HBM keeps streaming while the
-      // ring is full and a refill after a burst comes from L2 (latency ~0.5 us instead of ~2 us from loaded HBM)
-      const int ahead = a.pace_cycles >= 0 ? a.pace_cycles : 1;  // measured: 1 unit is best, deeper prefetch slows the residual exchange
+      // L2 prefetch cursor: runs `ahead` units in front of the shared-memory fill so that a refill after a burst comes
+      // from L2 (measured: 1 unit is best, deeper prefetch slows the residual exchange)
+      const int ahead = a.pace_cycles >= 0 ? a.pace_cycles : 1;
       int pq = 0;
-      const uint8_t *pf_q = qsrc, *pf_p = psrc;
-      auto unit_slots = [&](int q) { const int i = q < nq_layers ? q % UNITS_PER_LAYER : 0; return (q >= nq_layers || i < 7) ? 3 : 4; };
-      auto unit_is_q = [&](int q) { return q < nq_layers && q % UNITS_PER_LAYER < 6; };
       for (int q = 0; q < NQ; ++q) {
-        const int i = q < nq_layers ? q % UNITS_PER_LAYER : q - nq_layers;
-        const bool is_q = unit_is_q(q);
-        const int n = unit_slots(q);
+        int i, n;
+        const uint8_t* src;
+        bool is_shared;
+        unit(q, i, n, src, is_shared);
         while (pq < NQ && pq <= q + ahead) {
-          const uint32_t bytes = (uint32_t)unit_slots(pq) * SLOT;
-          if (unit_is_q(pq)) { if (pq > q) bulk_prefetch_l2(pf_q, bytes); pf_q += bytes; }
-          else { if (pq > q) bulk_prefetch_l2(pf_p, bytes); pf_p += bytes; }
+          int pi, pn;
+          const uint8_t* psrc;
+          bool ps;
+          unit(pq, pi, pn, psrc, ps);
+          if (pq > q) bulk_prefetch_l2(psrc, (uint32_t)pn * SLOT);
           ++pq;
         }
         while (issued + n - freed > ring_limit) {
-          const int ri = rel < nq_layers ? rel % UNITS_PER_LAYER : rel - nq_layers;
-          const int ru = rel < nq_layers ? rel / UNITS_PER_LAYER : L;
-          mb_wait(empty0 + 8 * ri, ru & 1);
-          freed += unit_slots(rel);
+          int ri, rn;
+          const uint8_t* rsrc;
+          bool rs;
+          unit(rel, ri, rn, rsrc, rs);
+          mb_wait(empty0 + 8 * ri, (uint32_t)(rel < nq_layers ? rel / UPL : L) & 1u);
+          freed += rn;
           ++rel;
         }
         mb_expect_tx(full0 + 8 * i, (uint32_t)n * SLOT);
         for (int s = 0; s < n; ++s) {
-          if (is_q) { bulk_g2s(sbase + LY::ring + wslot * SLOT, qsrc, SLOT, full0 + 8 * i, pol_last); qsrc += SLOT; }
-          else { bulk_g2s(sbase + LY::ring + wslot * SLOT, psrc, SLOT, full0 + 8 * i, pol_first); psrc += SLOT; }
+          bulk_g2s(sbase + LY::ring + wslot * SLOT, src + (size_t)s * SLOT, SLOT, full0 + 8 * i, is_shared ? pol_last : pol_first);
           wslot = wslot + 1 == NSLOT ? 0 : wslot + 1;
         }
         issued += n;
@@ -380,8 +397,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
     float* halves = reinterpret_cast<float*>(smem + LY::halves);
     const uint32_t aring = sbase + LY::ring + warp * 1024 + lane * 16;
     const uint32_t abx = sbase + LY::bx + lane * 8, abs_ = sbase + LY::bs + lane * 8;
-    const bool blive = lane < 12 * NB;  // lanes that hold a live B column
-    auto ldb = [&](uint32_t base, int kt) { return blive ? lds_u2(base + kt * LY::bkt) : make_uint2(0u, 0u); };
+    // B fragments of R sequence rows: 3R live columns = 12R lanes, 96R bytes per k-tile
+    auto ldb = [&](uint32_t base, int kt, int R) { return lane < 12 * R ? lds_u2(base + kt * 96 * R) : make_uint2(0u, 0u); };
     // address of tile t of the s-th slot after the ring cursor
     auto tile_addr = [&](int s, int t) {
       int sl = rslot + s;
@@ -389,6 +406,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       return aring + sl * SLOT + t * 512;
     };
     auto advance = [&](int n) { rslot += n; if (rslot >= NSLOT) rslot -= NSLOT; };
+    auto release = [&](int i) { __syncwarp(); if (lane == 0) mb_arrive(empty0 + 8 * i); };
     // exchange protocol: every CTA of the cluster receives `bytes` in total through st.async
     auto xarm = [&](uint32_t bytes) { if (tid == 0) mb_expect_tx(xbar + 8 * (xc & 1), bytes); };
     auto xpush = [&](uint32_t local_addr, int dst, float4 v) {
@@ -410,51 +428,53 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
     if (tid < kHeadDim) rope_s[tid] = a.rope[(size_t)p * kHeadDim + tid];
 
     // attention work split: old positions [0, p) in four chunks, one per CTA; warp w takes items w, w+12, ...
+    // row offsets live in shared memory (one table per warp), validity in a bit mask: registers are the scarce resource
     const int chunk = (p + CL - 1) / CL;
     const int j0 = rank * chunk, j1 = min(p, j0 + chunk);
-    // row offsets live in shared memory (one table per warp), validity in a bit mask: registers are the scarce resource
-    int* kofft = reinterpret_cast<int*>(smem + LY::kofft) + warp * MAXIT * NB;
+    int* kofft = reinterpret_cast<int*>(smem + LY::kofft) + warp * MAXIT;
     unsigned kvmask = 0;
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
       const int j = j0 + warp + CW * it;
       if (j < j1) kvmask |= 1u << it;
-      if (lane < NB) {
-        const int page = j < j1 ? a.kv.page_table[lane * a.kv.max_pages_per_seq + j / a.kv.page_size] : 0;
-        kofft[it * NB + lane] = ((page * a.kv.nhead + head) * a.kv.page_size + (j % a.kv.page_size)) * kHeadDim;
+      if (lane == 0) {
+        const int page = j < j1 ? a.kv.page_table[ab * a.kv.max_pages_per_seq + j / a.kv.page_size] : 0;
+        kofft[it] = ((page * a.kv.nhead + head) * a.kv.page_size + (j % a.kv.page_size)) * kHeadDim;
       }
     }
     __syncwarp();
-    auto kvalid_ = [&](int it) { return (kvmask >> it) & 1u; };
-    auto koff_ = [&](int it, int b) { return kofft[it * NB + b] + 4 * lane; };
+    auto kvalid = [&](int it) { return ((kvmask >> it) & 1u) && lane < 24; };
+    auto koff = [&](int it) { return kofft[it] + 4 * lane; };
     const size_t kv_half = (size_t)a.kv.num_pages * a.kv.nhead * a.kv.page_size * kHeadDim;  // floats of K (or V) per layer
     const bool new_warp = rank == CL - 1 && warp == CW - 1;  // takes the position written by this step
     const float* kvbase = reinterpret_cast<const float*>(a.kv.pages);
 
-    // x = phase input; loads 4 consecutive features per thread and sequence row, stages x * norm_w as B fragments,
-    // keeps rows [own0, own0 + ownn) for the residual add, leaves rstd in rstd[]
+    // ---- staging: x -> B fragments of x * norm_w (three bf16 split columns per row), sum of squares -> rstd ----
+    // every thread owns 4 consecutive features; `own0`: first of the 384 rows this CTA carries into the residual add
     float rstd[NB];
-    auto stage_x = [&](auto load4, const float* norm_w, int own0, int ownn) {
-      float ss[NB];
+    auto stage_rows = [&](auto load4, const float* norm_w, auto rows_tag, int row0) {  // rows [row0, row0 + R)
+      constexpr int R = decltype(rows_tag)::value;
+      float ss[R];
       const float4 g4 = __ldg(reinterpret_cast<const float4*>(norm_w) + tid);
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        const float4 v = load4(b);
+      for (int b = 0; b < R; ++b) {
+        const float4 v = load4(row0 + b);
         dstamp(43);
         ss[b] = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        if (4 * tid >= own0 && 4 * tid < own0 + ownn) *reinterpret_cast<float4*>(xown + b * W2_ROWS + (4 * tid - own0)) = v;
-        stage_pair<NB>(smem + LY::bx, 4 * tid, b, v.x * g4.x, v.y * g4.y);
-        stage_pair<NB>(smem + LY::bx, 4 * tid + 2, b, v.z * g4.z, v.w * g4.w);
+        if (4 * tid >= W2_ROWS * rank && 4 * tid < W2_ROWS * (rank + 1))
+          *reinterpret_cast<float4*>(xown + (row0 + b) * W2_ROWS + (4 * tid - W2_ROWS * rank)) = v;
+        stage_pair<R>(smem + LY::bx, 4 * tid, b, v.x * g4.x, v.y * g4.y);
+        stage_pair<R>(smem + LY::bx, 4 * tid + 2, b, v.z * g4.z, v.w * g4.w);
         ss[b] = warp_sum(ss[b]);
         if (lane == 0) red[warp * NB + b] = ss[b];
       }
       consumer_sync();
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
+      for (int b = 0; b < R; ++b) {
         float tot = 0.f;
 #pragma unroll
         for (int w = 0; w < CW; ++w) tot += red[w * NB + b];
-        rstd[b] = rsqrtf(tot / (float)DM + a.eps);
+        rstd[R == NB ? b : 0] = rsqrtf(tot / (float)DM + a.eps);
       }
     };
     // phase output n (1..2L) lives in residual buffer n; a word is complete when its count reaches `expect`
@@ -491,23 +511,26 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       }
       return v;
     };
-    // output rows [row0 + 16 rt, +16) of a residual phase: add the partial (and, where `carry`, the phase input)
-    auto resid_add = [&](const float (&acc)[4], long long* dst, int row0, int rt, bool carry) {
+    // output rows [384 rank + 16 rt, +16) of a residual phase, R sequence rows starting at row0: add the partial (and,
+    // where `carry`, the phase input)
+    auto resid_add = [&](const float (&acc)[4], long long* dst, int rt, bool carry, auto rows_tag, int row0) {
+      constexpr int R = decltype(rows_tag)::value;
       float o[2];
-      quad_reduce<NB>(acc, tq, o);
-      if (tq < NB) {
+      quad_reduce<R>(acc, tq, o);
+      if (tq < R) {
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const int rl = 16 * rt + gq + 8 * hf;
           float v = o[hf];
-          if (carry) v += xown[tq * W2_ROWS + rl];
-          red_add_fix(dst + (size_t)tq * DM + row0 + rl, f2fix(v));
+          if (carry) v += xown[(row0 + tq) * W2_ROWS + rl];
+          red_add_fix(dst + (size_t)(row0 + tq) * DM + W2_ROWS * rank + rl, f2fix(v));
         }
       }
     };
-    // K-split GEMV of 288 rows (18 row tiles) x this CTA's 384 features: 6 units of 3 slots; warp (rh, kq) owns row
-    // tiles 3rh..3rh+2 and k-tiles 12kq..12kq+11.  Leaves halves[kq][b][row]
-    auto ksplit_288 = [&](int use) {
+    // K-split GEMV of 288 rows (18 row tiles) x this CTA's 384 features for R sequence rows: 6 units of 3 slots; warp
+    // (rh, kq) owns row tiles 3rh..3rh+2 and k-tiles 12kq..12kq+11.  Leaves halves[kq][b][row]
+    auto ksplit_288 = [&](int use, auto rows_tag) {
+      constexpr int R = decltype(rows_tag)::value;
       const int rh = warp >> 1, kq = warp & 1;
 #pragma unroll
       for (int rt = 0; rt < 3; ++rt) {
@@ -517,7 +540,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           const int u = 2 * rt + hk;
           uint2 bq[6];
 #pragma unroll
-          for (int kk = 0; kk < 6; ++kk) bq[kk] = ldb(abx, 24 * rank + 12 * kq + 6 * hk + kk);
+          for (int kk = 0; kk < 6; ++kk) bq[kk] = ldb(abx, 24 * rank + 12 * kq + 6 * hk + kk, R);
           dstamp(2 * u);
           mb_wait(full0 + 8 * u, (uint32_t)use & 1u);
           dstamp(2 * u + 1);
@@ -526,72 +549,61 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           for (int j = 0; j < 6; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
 #pragma unroll
           for (int j = 0; j < 6; j += 2) { mma16816(acc0, A[j], bq[j]); mma16816(acc1, A[j + 1], bq[j + 1]); }
-          __syncwarp();
-          if (lane == 0) mb_arrive(empty0 + 8 * u);
+          release(u);
           advance(3);
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc0[e] += acc1[e];
         float o[2];
-        quad_reduce<NB>(acc0, tq, o);
-        if (tq < NB) {
+        quad_reduce<R>(acc0, tq, o);
+        if (tq < R) {
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) halves[(kq * NB + tq) * QROWS + 16 * (3 * rh + rt) + gq + 8 * hf] = o[hf];
+          for (int hf = 0; hf < 2; ++hf) halves[(kq * R + tq) * QROWS + 16 * (3 * rh + rt) + gq + 8 * hf] = o[hf];
         }
       }
       dstamp(12);
     };
+    using One = std::integral_constant<int, 1>;
+    using All = std::integral_constant<int, NB>;
 
-    constexpr bool kLate = NB > 1;  // two sequence rows: K/V registers are filled late (see below)
     for (int l = 0; l < L; ++l) {
       const uint32_t par = (uint32_t)l & 1u;
       if (TM) dbg = cta == a.timing_cta && tid == 0 && l == L / 2;
       long long* x_mid = xbuf(2 * l + 1);
       long long* x_out = xbuf(2 * l + 2);
 
-      // ---- K/V rows of this head's old positions: issued now, consumed after the QKV exchange ----
-      float4 kreg[MAXIT][NB], vreg[MAXIT][NB];
+      // ---- K rows of this head's old positions (sequence row ab): issued now, consumed after the QKV exchange; the V
+      //      rows are only pulled into L2 for now (three 128-byte lines per row) ----
+      float4 kreg[MAXIT], vreg[MAXIT];
       const float* kl = kvbase + (size_t)l * 2 * kv_half;
 #pragma unroll
-      for (int it = 0; it < MAXIT; ++it)
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          if (!kLate) kreg[it][b] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kvalid_(it) && lane < 24) {
-            if (!kLate) kreg[it][b] = ldg_cg_f4(kl + koff_(it, b));
-            if ((lane & 7) == 0) {  // three 128-byte lines per row
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(kl + kv_half + koff_(it, b)));
-              if (kLate) asm volatile("prefetch.global.L2 [%0];" ::"l"(kl + koff_(it, b)));
-            }
-          }
+      for (int it = 0; it < MAXIT; ++it) {
+        kreg[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kvalid(it)) {
+          kreg[it] = ldg_cg_f4(kl + koff(it));
+          if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(kl + kv_half + koff(it)));
         }
+      }
 
-      // ================= attention block: RMSNorm . wqkv rows of head `head`, K split over the 4 CTAs =================
-      if (l == 0) stage_x(load_embed, a.attn_norm, 768 * sh + WO_ROWS * rank, WO_ROWS);
-      else stage_x(load_fix(xbuf(2 * l), NCL), a.attn_norm + (size_t)l * DM, 768 * sh + WO_ROWS * rank, WO_ROWS);
+      // ================= attention block, sequence row ab: RMSNorm . wqkv rows of the head, K split over the 4 CTAs =================
+      if (l == 0) stage_rows(load_embed, a.attn_norm, One{}, ab);
+      else stage_rows(load_fix(xbuf(2 * l), NCL), a.attn_norm + (size_t)l * DM, One{}, ab);
+      const float rstd_a = rstd[0];
       stamp();
-      ksplit_288(l);
-      // One sequence row: K was fetched at the top of the layer, V is fetched now and hidden behind the exchange.
-      // Two rows: the rows were prefetched into L2 at the top; K is fetched now, V after the score pass when the K
-      // registers are dead (a spilled register costs an L2 round trip on this path).
+      ksplit_288(l, One{});
+      // V rows: issued after the QKV MMAs (register budget), hidden behind the exchange and the score pass
 #pragma unroll
-      for (int it = 0; it < MAXIT; ++it)
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          const bool live = kvalid_(it) && lane < 24;
-          if (kLate) kreg[it][b] = live ? ldg_cg_f4(kl + koff_(it, b)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          else vreg[it][b] = live ? ldg_cg_f4(kl + kv_half + koff_(it, b)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      for (int it = 0; it < MAXIT; ++it) vreg[it] = kvalid(it) ? ldg_cg_f4(kl + kv_half + koff(it)) : make_float4(0.f, 0.f, 0.f, 0.f);
       {
-        // all-to-all: every CTA receives the K-slice sums of all four CTAs, [src][b][288]
-        xarm(CL * NB * QROWS * 4);
+        // all-to-all: every CTA receives the K-slice sums of all four CTAs, [src][288]
+        xarm(CL * QROWS * 4);
         consumer_sync();
         dstamp(13);
-        if (tid < NB * QROWS / 4) {
+        if (tid < QROWS / 4) {
           const float4 h0 = *reinterpret_cast<const float4*>(halves + 4 * tid);
-          const float4 h1 = *reinterpret_cast<const float4*>(halves + NB * QROWS + 4 * tid);
+          const float4 h1 = *reinterpret_cast<const float4*>(halves + QROWS + 4 * tid);
           const float4 v = make_float4(h0.x + h1.x, h0.y + h1.y, h0.z + h1.z, h0.w + h1.w);
-          const uint32_t local = sbase + LY::qrecv + (rank * NB * QROWS + 4 * tid) * 4;
+          const uint32_t local = sbase + LY::qrecv + (rank * QROWS + 4 * tid) * 4;
 #pragma unroll
           for (int s = 0; s < CL; ++s) xpush(local, s, v);
         }
@@ -600,12 +612,12 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
         dstamp(15);
         // every CTA: sum the 4 K slices, apply rstd and RoPE (llama.py:633-650); rows [72 rank, +72) append K/V
         const float* qr = reinterpret_cast<const float*>(smem + LY::qrecv);
-        for (int e = tid; e < NB * QROWS; e += kCT) {  // 288 (or 576) is a multiple of 32: whole warps
-          const int b = e / QROWS, i = e % QROWS;
+        if (tid < QROWS) {  // 288 = 9 whole warps
+          const int i = tid;
           float y = 0.f;
 #pragma unroll
-          for (int s = 0; s < CL; ++s) y += qr[s * NB * QROWS + e];
-          y *= b ? rstd[NB - 1] : rstd[0];  // no runtime-indexed register array
+          for (int s = 0; s < CL; ++s) y += qr[s * QROWS + i];
+          y *= rstd_a;
           const float other = __shfl_xor_sync(0xffffffffu, y, 1);  // partner of the RoPE pair (rows 2m, 2m+1)
           const int sec = i / kHeadDim, d = i % kHeadDim;
           float o = y;
@@ -613,13 +625,14 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
             const float cs = rope_s[d & ~1], sn = rope_s[(d & ~1) + 1];
             o = (d & 1) ? y * cs + other * sn : y * cs - other * sn;
           }
-          if (sec != 0 && sh == 0 && i / QOWN == rank) {  // the twin cluster computes the same values: one CTA appends
-            const int page = a.kv.page_table[b * a.kv.max_pages_per_seq + p / a.kv.page_size];
+          // one sequence row: the twin cluster computes the same values, cluster 2h appends; two rows: each its own
+          if (sec != 0 && (NB > 1 || sh == 0) && i / QOWN == rank) {
+            const int page = a.kv.page_table[ab * a.kv.max_pages_per_seq + p / a.kv.page_size];
             float* dstp = reinterpret_cast<float*>(a.kv.pages) + (size_t)l * 2 * kv_half + (size_t)(sec - 1) * kv_half +
                           ((size_t)(page * a.kv.nhead + head) * a.kv.page_size + (p % a.kv.page_size)) * kHeadDim + d;
             *dstp = o;
           }
-          qkv_s[e] = o;
+          qkv_s[i] = o;
         }
         dstamp(16);
         consumer_sync();
@@ -627,127 +640,121 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       }
       stamp();
 
-      // ================= attention of head `head`: positions split over the CTAs =================
+      // ================= attention of the head, sequence row ab: positions split over the CTAs =================
       {
-        float* wp = reinterpret_cast<float*>(smem + LY::ra);  // [12][NB][100]
-        float scs[NB][MAXIT + 1];
-        float4 vnew[NB];
+        float* wp = reinterpret_cast<float*>(smem + LY::ra);  // [12][100]
+        const float4 q4 = lane < 24 ? *reinterpret_cast<const float4*>(qkv_s + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float sc[MAXIT + 1];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          const float4 q4 = lane < 24 ? *reinterpret_cast<const float4*>(qkv_s + b * QROWS + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float sc[MAXIT + 1];
-#pragma unroll
-          for (int it = 0; it < MAXIT; ++it) {
-            const float4 k4 = kreg[it][b];
-            sc[it] = k4.x * q4.x + k4.y * q4.y + k4.z * q4.z + k4.w * q4.w;
-          }
-          vnew[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-          sc[MAXIT] = 0.f;
-          if (new_warp && lane < 24) {
-            const float4 kn = *reinterpret_cast<const float4*>(qkv_s + b * QROWS + kHeadDim + 4 * lane);
-            vnew[b] = *reinterpret_cast<const float4*>(qkv_s + b * QROWS + 2 * kHeadDim + 4 * lane);
-            sc[MAXIT] = kn.x * q4.x + kn.y * q4.y + kn.z * q4.z + kn.w * q4.w;
-          }
-          // six independent butterfly reductions, interleaved
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int it = 0; it <= MAXIT; ++it) sc[it] += __shfl_xor_sync(0xffffffffu, sc[it], o);
-#pragma unroll
-          for (int it = 0; it < MAXIT; ++it) sc[it] = kvalid_(it) ? sc[it] * a.scale : -INFINITY;
-          sc[MAXIT] = new_warp ? sc[MAXIT] * a.scale : -INFINITY;
-          float m = sc[MAXIT];
-#pragma unroll
-          for (int it = 0; it < MAXIT; ++it) m = fmaxf(m, sc[it]);
-          if (lane == 0) red[16 + warp * NB + b] = m;
-#pragma unroll
-          for (int it = 0; it <= MAXIT; ++it) scs[b][it] = sc[it];
+        for (int it = 0; it < MAXIT; ++it) {
+          const float4 k4 = kreg[it];
+          sc[it] = k4.x * q4.x + k4.y * q4.y + k4.z * q4.z + k4.w * q4.w;
         }
-        if (kLate) {
-#pragma unroll
-          for (int it = 0; it < MAXIT; ++it)
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-              vreg[it][b] = kvalid_(it) && lane < 24 ? ldg_cg_f4(kl + kv_half + koff_(it, b)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 vnew = make_float4(0.f, 0.f, 0.f, 0.f);
+        sc[MAXIT] = 0.f;
+        if (new_warp && lane < 24) {
+          const float4 kn = *reinterpret_cast<const float4*>(qkv_s + kHeadDim + 4 * lane);
+          vnew = *reinterpret_cast<const float4*>(qkv_s + 2 * kHeadDim + 4 * lane);
+          sc[MAXIT] = kn.x * q4.x + kn.y * q4.y + kn.z * q4.z + kn.w * q4.w;
         }
+        // six independent butterfly reductions, interleaved
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int it = 0; it <= MAXIT; ++it) sc[it] += __shfl_xor_sync(0xffffffffu, sc[it], o);
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) sc[it] = ((kvmask >> it) & 1u) ? sc[it] * a.scale : -INFINITY;
+        sc[MAXIT] = new_warp ? sc[MAXIT] * a.scale : -INFINITY;
+        float m = sc[MAXIT];
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) m = fmaxf(m, sc[it]);
+        if (lane == 0) red[16 + warp] = m;
         consumer_sync();
+        float M = red[16];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          float M = red[16 + b];
+        for (int w = 1; w < CW; ++w) M = fmaxf(M, red[16 + w]);  // max over the CTA's positions (-inf if it has none)
+        float lsum = 0.f;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (M > -INFINITY) {
 #pragma unroll
-          for (int w = 1; w < CW; ++w) M = fmaxf(M, red[16 + w * NB + b]);  // max over the CTA's positions (-inf if it has none)
-          float lsum = 0.f;
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (M > -INFINITY) {
-#pragma unroll
-            for (int it = 0; it <= MAXIT; ++it) {
-              const float e = scs[b][it] > -INFINITY ? __expf(scs[b][it] - M) : 0.f;
-              const float4 v4 = it < MAXIT ? vreg[it < MAXIT ? it : 0][b] : vnew[b];
-              lsum += e;
-              o.x = fmaf(e, v4.x, o.x); o.y = fmaf(e, v4.y, o.y); o.z = fmaf(e, v4.z, o.z); o.w = fmaf(e, v4.w, o.w);
-            }
+          for (int it = 0; it <= MAXIT; ++it) {
+            const float e = sc[it] > -INFINITY ? __expf(sc[it] - M) : 0.f;
+            const float4 v4 = it < MAXIT ? vreg[it < MAXIT ? it : 0] : vnew;
+            lsum += e;
+            o.x = fmaf(e, v4.x, o.x); o.y = fmaf(e, v4.y, o.y); o.z = fmaf(e, v4.z, o.z); o.w = fmaf(e, v4.w, o.w);
           }
-          float* w = wp + (warp * NB + b) * WP_STRIDE;
+        }
+        {
+          float* w = wp + warp * WP_STRIDE;
           if (lane == 0) { w[0] = M; w[1] = lsum; }
           if (lane < 24) *reinterpret_cast<float4*>(w + 4 + 4 * lane) = o;
         }
-        xarm(CL * NB * WP_STRIDE * 4);
+        xarm(CL * WP_STRIDE * 4);
         dstamp(18);
         consumer_sync();
-        // CTA partial (M, l, -, -, o[96]) -> every CTA of the cluster, 25 float4 per sequence row
-        if (tid < 25 * NB) {
-          const int b = tid / 25, c4 = tid % 25;
+        // CTA partial (M, l, -, -, o[96]) -> every CTA of the cluster, 25 float4
+        if (tid < 25) {
+          const int c4 = tid;
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int w = 0; w < CW; ++w) {
-            const float4 v = *reinterpret_cast<const float4*>(wp + (w * NB + b) * WP_STRIDE + 4 * c4);
+            const float4 v = *reinterpret_cast<const float4*>(wp + w * WP_STRIDE + 4 * c4);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
           }
-          if (c4 == 0) { acc.x = wp[b * WP_STRIDE]; acc.z = 0.f; acc.w = 0.f; }  // every warp stored the same M
-          const uint32_t local = sbase + LY::rb + ((rank * NB + b) * WP_STRIDE + 4 * c4) * 4;
+          if (c4 == 0) { acc.x = wp[0]; acc.z = 0.f; acc.w = 0.f; }  // every warp stored the same M
+          const uint32_t local = sbase + LY::rb + (rank * WP_STRIDE + 4 * c4) * 4;
 #pragma unroll
           for (int s = 0; s < CL; ++s) xpush(local, s, acc);
         }
         dstamp(19);
         xwait();
         dstamp(20);
-        if (tid < kHeadDim * NB) {
-          const int b = tid / kHeadDim, d = tid % kHeadDim;
+        if (tid < kHeadDim) {
+          const int d = tid;
           const float* ar = reinterpret_cast<const float*>(smem + LY::rb);
-          float M = -INFINITY;
+          float Mx = -INFINITY;
 #pragma unroll
-          for (int s = 0; s < CL; ++s) M = fmaxf(M, ar[(s * NB + b) * WP_STRIDE]);
+          for (int s = 0; s < CL; ++s) Mx = fmaxf(Mx, ar[s * WP_STRIDE]);
           float den = 0.f, O = 0.f;
 #pragma unroll
           for (int s = 0; s < CL; ++s) {
-            const float ms = ar[(s * NB + b) * WP_STRIDE];
-            const float f = ms > -INFINITY ? expf(ms - M) : 0.f;
-            den = fmaf(f, ar[(s * NB + b) * WP_STRIDE + 1], den);
-            O = fmaf(f, ar[(s * NB + b) * WP_STRIDE + 4 + d], O);
+            const float ms = ar[s * WP_STRIDE];
+            const float f = ms > -INFINITY ? expf(ms - Mx) : 0.f;
+            den = fmaf(f, ar[s * WP_STRIDE + 1], den);
+            O = fmaf(f, ar[s * WP_STRIDE + 4 + d], O);
           }
-          stage_one<NB>(smem + LY::bs, d, b, O / den);
+          stage_one<1>(smem + LY::bs, d, 0, O / den);
         }
         consumer_sync();
       }
       stamp();
 
-      // ============ wo[768 sh + 192 rank .. +192, head]; warp w owns row tile w; residual into x_mid ============
+      // ==== wo[384 rank .. +384, head] for row ab; warp w owns row tiles 2w, 2w+1; one row: this cluster's half of the
+      //      head's 96 features (k-tiles 3sh..3sh+2), two rows: all six k-tiles in two units; residual into x_mid ====
       {
-        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-        dstamp(21);
-        mb_wait(full0 + 8 * 6, par);
-        dstamp(22);
-        uint4 A[6];
+        float acc[2][4];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int j = 0; j < 6; j += 2) { mma16816(acc0, A[j], ldb(abs_, j)); mma16816(acc1, A[j + 1], ldb(abs_, j + 1)); }
-        __syncwarp();
-        if (lane == 0) mb_arrive(empty0 + 8 * 6);
-        advance(3);
+          for (int e = 0; e < 4; ++e) acc[r][e] = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc0[e] += acc1[e];
-        resid_add(acc0, x_mid, 768 * sh + WO_ROWS * rank, warp, head == 0);
+        for (int u = 0; u < NB; ++u) {
+          const int kh = NB == 1 ? sh : u;  // k half held by this unit
+          dstamp(21);
+          mb_wait(full0 + 8 * (U_WO + u), par);
+          dstamp(22);
+          uint4 A[6];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
+#pragma unroll
+          for (int j = 0; j < 6; ++j) mma16816(acc[j / 3], A[j], ldb(abs_, 3 * kh + j % 3, 1));
+          release(U_WO + u);
+          advance(3);
+        }
+        // the phase input is carried by one cluster per sequence row: cluster 0 (one row), the head-0 clusters (two rows)
+        const bool carry = NB == 1 ? cl == 0 : head == 0;
+        resid_add(acc[0], x_mid, 2 * warp, carry, One{}, ab);
+        resid_add(acc[1], x_mid, 2 * warp + 1, carry, One{}, ab);
       }
       grid_arrive_relaxed(&a.state->barrier);
       stamp();
@@ -755,8 +762,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
       grid_wait_relaxed(&a.state->barrier, (epoch * nbar + (++bar_i)) * (unsigned)G);
       dstamp(42);
 
-      // ============ MLP: RMSNorm . w1|w3 of this CTA's 32 hidden units (K split over the 12 warps) ============
-      stage_x(load_fix(x_mid, NHEAD), a.ffn_norm + (size_t)l * DM, W2_ROWS * rank, W2_ROWS);
+      // ============ MLP, all rows: RMSNorm . w1|w3 of this CTA's 32 hidden units (K split over the 12 warps) ============
+      stage_rows(load_fix(x_mid, NB == 1 ? NCL : NHEAD), a.ffn_norm + (size_t)l * DM, All{}, 0);
       stamp();
       {
         float acc[4][4];
@@ -766,17 +773,16 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           for (int e = 0; e < 4; ++e) acc[r][e] = 0.f;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const uint2 b0 = ldb(abx, 8 * warp + 2 * u), b1 = ldb(abx, 8 * warp + 2 * u + 1);
+          const uint2 b0 = ldb(abx, 8 * warp + 2 * u, NB), b1 = ldb(abx, 8 * warp + 2 * u + 1, NB);
           dstamp(24 + 2 * u);
-          mb_wait(full0 + 8 * (7 + u), par);
+          mb_wait(full0 + 8 * (U_W13 + u), par);
           dstamp(25 + 2 * u);
           uint4 A[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
 #pragma unroll
           for (int j = 0; j < 8; ++j) mma16816(acc[j & 3], A[j], (j >> 2) ? b1 : b0);
-          __syncwarp();
-          if (lane == 0) mb_arrive(empty0 + 8 * (7 + u));
+          release(U_W13 + u);
           advance(4);
         }
         float* part = reinterpret_cast<float*>(smem + LY::ra);  // [12][NB][64]
@@ -799,7 +805,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           float y1 = 0.f, y3 = 0.f;
 #pragma unroll
           for (int w = 0; w < CW; ++w) { y1 += part[(w * NB + b) * 64 + r1]; y3 += part[(w * NB + b) * 64 + r1 + 8]; }
-          const float rs = b ? rstd[NB - 1] : rstd[0];
+          const float rs = b ? rstd[NB - 1] : rstd[0];  // no runtime-indexed register array
           y1 *= rs; y3 *= rs;
           const float hv = y1 / (1.f + expf(-y1)) * y3;
           const uint32_t local = sbase + LY::hrecv + (b * HU + rank * HUC + u) * 4;
@@ -823,19 +829,18 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
         for (int u = 0; u < 2; ++u) {
           float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
           dstamp(36 + 2 * u);
-          mb_wait(full0 + 8 * (11 + u), par);
+          mb_wait(full0 + 8 * (U_W2 + u), par);
           dstamp(37 + 2 * u);
           uint4 A[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) A[j] = lds_u4(tile_addr(j >> 1, j & 1));
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) { mma16816(acc0, A[j], ldb(abs_, j)); mma16816(acc1, A[j + 1], ldb(abs_, j + 1)); }
-          __syncwarp();
-          if (lane == 0) mb_arrive(empty0 + 8 * (11 + u));
+          for (int j = 0; j < 8; j += 2) { mma16816(acc0, A[j], ldb(abs_, j, NB)); mma16816(acc1, A[j + 1], ldb(abs_, j + 1, NB)); }
+          release(U_W2 + u);
           advance(4);
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc0[e] += acc1[e];
-          resid_add(acc0, x_out, W2_ROWS * rank, 2 * warp + u, cl == 0);
+          resid_add(acc0, x_out, 2 * warp + u, cl == 0, All{}, 0);
         }
       }
       grid_arrive_relaxed(&a.state->barrier);
@@ -846,8 +851,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
     dbg = false;
     // ============ final norm + heads: the cluster owns rows [288 cl, +288), K split over its CTAs ============
     {
-      stage_x(load_fix(xbuf(2 * L), NCL), a.final_norm, 0, 0);
-      ksplit_288(L);
+      stage_rows(load_fix(xbuf(2 * L), NCL), a.final_norm, All{}, 0);
+      ksplit_288(L, All{});
       // reduce-scatter: rows [72 dst, +72) of every sequence row go to CTA dst, [src][b][72]
       xarm(CL * NB * HOWN * 4);
       consumer_sync();
@@ -899,7 +904,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 // host side
 // ------------------------------------------------------------------------------------------------
 size_t cluster_stream_bytes(int L) {
-  return ((size_t)NHEAD * CL * L * QKV_SLOTS + (size_t)NCL * CL * ((size_t)L * PRIV_SLOTS + HEAD_SLOTS)) * SLOT;
+  return ((size_t)NHEAD * CL * L * SH_SLOTS + (size_t)NCL * CL * ((size_t)L * PRIV_SLOTS + HEAD_SLOTS)) * SLOT;
 }
 
 bool cluster_supported(int rows, int L, int D, int F, int H, int head_rows, int page_size, int cond_dim, int max_ctx) {

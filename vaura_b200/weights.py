@@ -109,18 +109,20 @@ def pack_sampler(sd: Dict[str, torch.Tensor], dims: SamplerDims, device) -> Dict
 
 # ---- weight streams of the cluster-persistent decode kernel (csrc/decode_cluster.cu) ---------------------------
 # 32 clusters (cl) x 4 CTAs (r); head h = cl // 2, s = cl % 2.  Bytes, in 12288-byte slots:
-#   [16 heads][4 ranks][L][18 slots]                 q|k|v stream, shared by the CTAs (2h, r) and (2h+1, r)
-#   [128 CTAs][L x (wo 3 | w13 16 | w2 8) | heads 18]  private streams
+#   [16 heads][4 ranks][L][qkv 18 | wo 6]          shared streams, read by the CTAs (2h, r) and (2h+1, r)
+#   [128 CTAs][L x (w13 16 | w2 8) | heads 18]       private streams
 # slot = [warp w: 12][tile t: 2][lane: 32][e: 8] bf16.  A tile is 16 rows x 16 k in mma.m16n8k16 A-fragment order:
 # lane = 4*gq + tq holds rows frow = gq + 8*((e>>1)&1), k fk = 2*tq + (e&1) + 8*(e>>2).  With j = 2*slot + t the tile
 # (row-tile R, k-tile Kt) a warp owns and the source element of local (row lr = 16R + frow, k lk = 16Kt + fk) are:
 #   qkv   R = 3*(w//2) + j//12, Kt = 12*(w%2) + j%12   row (lr//96)*d + 96h + lr%96        col 384r + lk
-#   wo    R = w,                Kt = j                 row 768s + 192r + lr                col 96h + lk
+#   wo    slots 0-2: k-half 0, slots 3-5: k-half 1 of the head's 96 features (one sequence row: cluster s reads half s;
+#         two rows: every cluster reads both halves for its own row); within a half jj = 2*(slot%3) + t:
+#         R = 2w + jj//3, Kt = 3*(slot//3) + jj%3      row 384r + lr                       col 96h + lk
 #   w13   R = j%4,              Kt = 8w + j//4         row 2*(128cl + 32r + 8R + frow%8) + frow//8 (interleaved w1|w3), col lk
 #   w2    R = 2w + j//8,        Kt = j%8               row 384r + lr                       col 128cl + lk
 #   heads R = 3*(w//2) + j//12, Kt = 12*(w%2) + j%12   row 288cl + lr                      col 384r + lk
 CLUSTER_SLOT_ELEMS = 12 * 2 * 32 * 8
-CLUSTER_PHASE_SLOTS = {"qkv": 18, "wo": 3, "w13": 16, "w2": 8, "heads": 18}
+CLUSTER_PHASE_SLOTS = {"qkv": 18, "wo": 6, "w13": 16, "w2": 8, "heads": 18}
 
 
 def cluster_stream_supported(dims: SamplerDims) -> bool:
@@ -130,9 +132,9 @@ def cluster_stream_supported(dims: SamplerDims) -> bool:
 
 def cluster_stream_index(phase: str, device="cpu") -> torch.Tensor:
     """Flat source index (into the row-major matrix of the phase) of every stream element:
-    int64 [groups][4 ranks][slots][12 warps][2 tiles][32 lanes][8]; groups = 16 heads (qkv) or 32 clusters."""
+    int64 [groups][4 ranks][slots][12 warps][2 tiles][32 lanes][8]; groups = 16 heads (qkv, wo) or 32 clusters."""
     G = CLUSTER_PHASE_SLOTS[phase]
-    NG = 16 if phase == "qkv" else 32
+    NG = 16 if phase in ("qkv", "wo") else 32
     ar = lambda n: torch.arange(n, device=device)
     c = ar(NG).view(NG, 1, 1, 1, 1, 1, 1)
     r = ar(4).view(1, 4, 1, 1, 1, 1, 1)
@@ -147,7 +149,8 @@ def cluster_stream_index(phase: str, device="cpu") -> torch.Tensor:
     if phase in ("qkv", "heads"):
         R, Kt = 3 * (w // 2) + j // 12, 12 * (w % 2) + j % 12
     elif phase == "wo":
-        R, Kt = w, j
+        jj = 2 * (g % 3) + t
+        R, Kt = 2 * w + jj // 3, 3 * (g // 3) + jj % 3
     elif phase == "w2":
         R, Kt = 2 * w + j // 8, j % 8
     else:  # w13
@@ -156,7 +159,7 @@ def cluster_stream_index(phase: str, device="cpu") -> torch.Tensor:
     if phase == "qkv":
         row, col, ld = (lr // 96) * 1536 + 96 * c + lr % 96, 384 * r + lk, 1536
     elif phase == "wo":
-        row, col, ld = 768 * (c % 2) + 192 * r + lr, 96 * (c // 2) + lk, 1536
+        row, col, ld = 384 * r + lr, 96 * c + lk, 1536
     elif phase == "w13":
         row, col, ld = 2 * (128 * c + 32 * r + 8 * R + frow % 8) + frow // 8, lk, 1536
     elif phase == "w2":
@@ -168,29 +171,32 @@ def cluster_stream_index(phase: str, device="cpu") -> torch.Tensor:
 
 
 def pack_cluster_stream(packed: Dict[str, torch.Tensor], dims: SamplerDims) -> torch.Tensor:
-    """-> flat uint8 tensor: the q|k|v streams followed by the 128 private streams (include/vaura_b200.h: wstream)."""
+    """-> flat uint8 tensor: the 64 shared streams followed by the 128 private streams (include/vaura_b200.h: wstream)."""
     assert cluster_stream_supported(dims)
     L = dims.num_layers
     dev = packed["wqkv"].device
     SE = CLUSTER_SLOT_ELEMS
-    nq = 64 * L * 18 * SE
-    per_priv = (L * 27 + 18) * SE
-    out = torch.empty(nq + 128 * per_priv, dtype=torch.bfloat16, device=dev)
-    qv = out[:nq].view(64, L, 18 * SE)
-    pv = out[nq:].view(128, per_priv)
-    idx = cluster_stream_index("qkv", dev).view(64, -1)
+    nsh = 64 * L * 24 * SE
+    per_priv = (L * 24 + 18) * SE
+    out = torch.empty(nsh + 128 * per_priv, dtype=torch.bfloat16, device=dev)
+    sv = out[:nsh].view(64, L, 24 * SE)
+    pv = out[nsh:].view(128, per_priv)
+    iq = cluster_stream_index("qkv", dev).view(64, -1)
+    io = cluster_stream_index("wo", dev).view(64, -1)
     for l in range(L):
-        qv[:, l] = packed["wqkv"][l].reshape(-1)[idx]
+        sv[:, l, :18 * SE] = packed["wqkv"][l].reshape(-1)[iq]
+        sv[:, l, 18 * SE:] = packed["wo"][l].reshape(-1)[io]
+    del iq, io
     off = 0
-    for phase in ("wo", "w13", "w2"):
+    for phase in ("w13", "w2"):
         idx = cluster_stream_index(phase, dev).view(128, -1)
         n = idx.shape[1]
         for l in range(L):
-            pv[:, l * 27 * SE + off:l * 27 * SE + off + n] = packed[phase][l].reshape(-1)[idx]
+            pv[:, l * 24 * SE + off:l * 24 * SE + off + n] = packed[phase][l].reshape(-1)[idx]
         off += n
-    assert off == 27 * SE
+    assert off == 24 * SE
     idx = cluster_stream_index("heads", dev).view(128, -1)
-    pv[:, L * 27 * SE:] = packed["w_heads"].reshape(-1)[idx]
+    pv[:, L * 24 * SE:] = packed["w_heads"].reshape(-1)[idx]
     return out.view(torch.uint8)
 
 
