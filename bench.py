@@ -38,6 +38,9 @@ WORKLOADS = {
     # BASELINE.json configs[0]/[2]: batch-1 low latency
     "b1": dict(batch=1, T=220, use_sampling=True, top_k=128, temp=1.0, cfg_scale=1.0,
                name="one 2.56 s clip, batch 1, top-k 128 sampling"),
+    # the reference's own generate settings (configs/generate_vgg.yaml: cfg_scale 6.0) at batch 1: two sequence rows
+    "b1_cfg": dict(batch=1, T=220, use_sampling=True, top_k=128, temp=1.0, cfg_scale=6.0,
+                   name="one 2.56 s clip, batch 1, top-k 128 sampling, classifier-free guidance 6.0 (2 sequence rows)"),
 }
 
 

@@ -336,19 +336,33 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   sa.use_sampling = p->use_sampling; sa.top_k = p->top_k; sa.cfg_scale = p->cfg_scale; sa.temp = p->temp;
   sa.top_p = p->top_p; sa.seed_lo = (uint32_t)p->seed; sa.seed_hi = (uint32_t)(p->seed >> 32);
 
-  // first pass: positions [0, start) -> sample column start
-  rc = run_pass(precision, s, ws, p->sequence, p->batch, S, p->cond_rows, rows, npre, 0, nullptr, kvv, ws.logits, false, st);
-  if (rc) return rc;
-  sa.state = nullptr; sa.offset = p->start_offset;
-  CUL(launch_sample(sa, st));
-  const int nsteps = p->end_offset - (p->start_offset + 1);
-  if (nsteps <= 0) return VAURA_OK;
+  const char* no_persist = getenv("VAURA_NO_PERSISTENT");
+  const bool persist = precision == VAURA_PRECISION_FP32ACT && persistent_supported(rows, d.d_model, d.ffn_dim, kv->page_size) &&
+                       !(no_persist && no_persist[0] == '1');
+  // rows <= 2: cluster variant (decode_cluster.cu) when the weight streams were packed.  Without a prompt it also runs
+  // the first position (a decode step with an empty KV cache), so the whole clip is one kernel per column.
+  const char* nocl = getenv("VAURA_NO_CLUSTER");
+  const char* ptc = getenv("VAURA_PERSIST_TC");
+  const bool use_cluster = persist && s->w.wstream && !(nocl && nocl[0] == '1') && !(ptc && ptc[0] == '1') &&
+                           cluster_supported(rows, d.num_layers, d.d_model, d.ffn_dim, d.nhead, K * d.vocab, kv->page_size,
+                                             d.cond_dim, S);
+  const bool cluster_first = use_cluster && npre == 1;
+  int nsteps = p->end_offset - (p->start_offset + 1);
+  if (!cluster_first) {
+    // first pass: positions [0, start) -> sample column start
+    rc = run_pass(precision, s, ws, p->sequence, p->batch, S, p->cond_rows, rows, npre, 0, nullptr, kvv, ws.logits, false, st);
+    if (rc) return rc;
+    sa.state = nullptr; sa.offset = p->start_offset;
+    CUL(launch_sample(sa, st));
+    if (nsteps <= 0) return VAURA_OK;
+    CUL(launch_set_state(ws.state, p->start_offset + 1, st));
+  } else {
+    CUL(launch_set_state(ws.state, p->start_offset, st));
+    nsteps += 1;
+  }
 
   // decode steps
-  CUL(launch_set_state(ws.state, p->start_offset + 1, st));
-  const char* no_persist = getenv("VAURA_NO_PERSISTENT");
-  if (precision == VAURA_PRECISION_FP32ACT && persistent_supported(rows, d.d_model, d.ffn_dim, kv->page_size) &&
-      !(no_persist && no_persist[0] == '1')) {
+  if (persist) {
     // rows <= 4: one persistent cooperative kernel per step (weights streamed through an smem ring by TMA)
     PersistArgs pa{};
     const vaura_sampler_weights& w = s->w;
@@ -371,11 +385,6 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     const char* tc = getenv("VAURA_PERSIST_TC");
     const bool use_tc = (tc && tc[0] == '1') && w.wqkv_t && w.wo_t && w.w13_t && w.w2_t && w.w_heads_t &&
                         persistent_tc_supported(rows, d.d_model, d.ffn_dim, kv->page_size, K * d.vocab / 2, d.ffn_dim, sms);
-    // rows <= 2: cluster variant (decode_cluster.cu) when the per-CTA weight streams were packed
-    const char* nocl = getenv("VAURA_NO_CLUSTER");
-    const bool use_cluster = !use_tc && w.wstream && !(nocl && nocl[0] == '1') &&
-                             cluster_supported(rows, d.num_layers, d.d_model, d.ffn_dim, d.nhead, K * d.vocab, kv->page_size,
-                                               d.cond_dim, S);
     if (use_cluster) {
       pa.wstream = w.wstream;
       pa.xfix = ws.xfix;
