@@ -178,6 +178,20 @@ def test_full_size_greedy_matches_reference_golden():
         gaps = torch.topk(lg, 2, dim=-1).values
         if float((gaps[..., 0] - gaps[..., 1]).min()) > 1e-3:
             assert torch.equal(o["sampled_indices"].cpu(), r)
+    # a prompt makes the first pass a multi-position prefill (multi-kernel path); the cluster kernel then continues on the
+    # KV cache those kernels wrote, with classifier-free guidance on top (the reference's generate settings)
+    g2 = torch.Generator().manual_seed(5)
+    prompt = torch.randint(0, 1024, (1, 9, 10), generator=g2)
+    f = make_avclip_features(1, 95)
+    o = m.generate(frames=f.cuda(), audio=prompt.cuda(), max_new_tokens=26, use_sampling=False, prompt_is_encoded=True,
+                   cfg_scale=6.0, return_sampled_indices=True, _decode_audio=False, _return_logits=True)
+    r, lg = vo.generate_tokens(oracle, f.reshape(1, 32, 768), prompt=prompt, max_new_tokens=26, cfg_scale=6.0,
+                               collect_logits=True)
+    start = prompt.shape[-1] + 1
+    assert rel_err(o["_logits"][start:].cpu(), lg) < 2e-5
+    gaps = torch.topk(lg, 2, dim=-1).values
+    if float((gaps[..., 0] - gaps[..., 1]).min()) > 1e-3:
+        assert torch.equal(o["sampled_indices"].cpu(), r)
 
 
 # ---- tensor-core (bf16 activation) path ------------------------------------------------------------------

@@ -13,6 +13,8 @@
 // that TMA writes and the UMMA shared-memory descriptor reads; full/empty mbarriers; accumulator in TMEM.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -383,6 +385,142 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// persistent variant (codec convs): one CTA per SM walks the (m, n, batch*phase) tiles; the accumulator is double
+// buffered in TMEM so the epilogue of tile i (bias + residual + Snake + two fp16 stores per element, the long pole of
+// the narrow layers) overlaps the TMA / MMA mainloop of tile i+1, and barrier init / TMEM allocation / launch happen
+// once per layer instead of once per 128-row tile.  Same tile arithmetic as gemm_tc_kernel (KSUB = 1, no split-K).
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape g,
+                          const typename Epi::Params ep, const int m_tiles, const int n_tiles) {
+  constexpr int SW = BLOCK_K * 2;
+  constexpr int TILE_M = kTileM;
+  constexpr int A_BYTES = TILE_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int ACC_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;  // per accumulator buffer
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "stage buffers must stay 1024B aligned for the swizzle");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;   // [2] accumulator buffer written
+  uint64_t* tempty = tfull + 2;       // [2] accumulator buffer drained by the 8 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int iters = g.ntaps * g.kblocks;
+  const int zdim = g.batch * g.nphase;
+  const int ntiles = m_tiles * n_tiles * zdim;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (m0, n0, batch, phase); m fastest so that neighbouring CTAs share the weight tile in L2
+  auto tile_coords = [&](int t, int& m0, int& n0, int& b, int& phase) {
+    m0 = (t % m_tiles) * TILE_M;
+    const int r = t / m_tiles;
+    n0 = (r % n_tiles) * BLOCK_N;
+    const int zz = r / n_tiles;
+    b = zz / g.nphase;
+    phase = zz % g.nphase;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int git = 0;  // ring iterations since the kernel started
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int m0, n0, b, phase;
+        tile_coords(t, m0, n0, b, phase);
+        for (int it = 0; it < iters; ++it, ++git) {
+          const int s = git % STAGES;
+          const uint32_t ph = (git / STAGES) & 1;
+          const int tap = it / g.kblocks, kb = it % g.kblocks;
+          uint8_t* ss = smem + s * STAGE_BYTES;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          tma_load_3d(ss + A_BYTES, &tmB, &full[s], kb * BLOCK_K, n0, phase * g.ntaps + tap);
+          tma_load_3d(ss, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE_M, BLOCK_N, FMT);
+      int git = 0, tc = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
+        const int ab = tc & 1;
+        mbar_wait(&tempty[ab], ((tc >> 1) & 1) ^ 1);  // the epilogue has drained this buffer (first use passes)
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + ab * ACC_COLS;
+        for (int it = 0; it < iters; ++it, ++git) {
+          const int s = git % STAGES;
+          const uint32_t ph = (git / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) umma_bf16_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[ab]);
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    constexpr int kChunks = BLOCK_N / 16, kHalf = (kChunks + 1) / 2;
+    const int c_begin = (warp - 2) < 4 ? 0 : kHalf * 16, c_end = (warp - 2) < 4 ? kHalf * 16 : BLOCK_N;
+    int tc = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
+      int m0, n0, b, phase;
+      tile_coords(t, m0, n0, b, phase);
+      const int ab = tc & 1;
+      mbar_wait(&tfull[ab], (tc >> 1) & 1);
+      tcgen05_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const uint32_t tacc = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; c += 16) {
+        float v[16];
+        tmem_ld16(tacc + c, v);
+        Epi::apply(ep, b, phase, m, n0 + c, v);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[ab])) : "memory");
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -441,6 +579,25 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const
   cfg.numAttrs = g.pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, g, ep);
 }
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi>
+static cudaError_t launch_tc_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const TcShape& g,
+                                        const typename Epi::Params& ep, int m_tiles, int n_tiles, cudaStream_t st) {
+  constexpr int smem = STAGES * (kTileM * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "stage ring exceeds shared memory");
+  auto kern = gemm_tc_persistent_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi>;
+  static int sms = 0;
+  if (!sms) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int ntiles = m_tiles * n_tiles * g.batch * g.nphase;
+  kern<<<dim3(ntiles < sms ? ntiles : sms), dim3(kGemmThreads), smem, st>>>(ta, tb, g, ep, m_tiles, n_tiles);
+  return cudaGetLastError();
+}
+
 bool conv_tc_supported(int Cin, int Cout, int ntaps, int nphase) {
   if (Cin % 32 != 0 || Cout % 16 != 0 || ntaps * nphase > 32) return false;
   const int bk = (Cin % 64 == 0) ? 64 : 32;
@@ -469,8 +626,13 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cu
   for (int i = 0; i < a.ntaps * a.nphase; ++i) g.tap_off[i] = tap_off_host[i];
   EpiConv::Params ep{a.bias, a.alpha, a.residual, a.out_raw, a.out_act, a.Tq, a.Tout, a.Cout, a.ostride};
   const int mt = (a.Tq + kTileM - 1) / kTileM, nt = a.Cout / bn;
-#define TC_CASE(BN, BK, ST) \
-  if (bn == BN && bk == BK) return launch_tc<BN, BK, ST, 0, EpiConv>(ta, tb, g, ep, mt, nt, st);
+  // persistent tile loop (double-buffered TMEM accumulator) unless VAURA_CONV_PERSISTENT=0
+  static int persistent = -1;
+  if (persistent < 0) { const char* e = getenv("VAURA_CONV_PERSISTENT"); persistent = !(e && e[0] == '0'); }
+#define TC_CASE(BN, BK, ST)                                                                                    \
+  if (bn == BN && bk == BK)                                                                                    \
+    return persistent ? launch_tc_persistent<BN, BK, ST, 0, EpiConv>(ta, tb, g, ep, mt, nt, st)                \
+                      : launch_tc<BN, BK, ST, 0, EpiConv>(ta, tb, g, ep, mt, nt, st);
   TC_CASE(256, 64, 4)
   TC_CASE(192, 64, 4)
   TC_CASE(128, 64, 6)
