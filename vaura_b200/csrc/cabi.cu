@@ -250,6 +250,13 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
   { const char* m = getenv("VAURA_PDL_MODE"); if (m) pdl = atoi(m); }
   const char* nosplit = getenv("VAURA_NO_SPLITK");
   const bool splitk = small && !(nosplit && nosplit[0] == '1');
+  // tuning knobs of the two residual GEMMs (N tile, split-K factor)
+  static int wo_bn = 0, wo_ks = 0, w2_bn = 0, w2_ks = 0;
+  if (!wo_bn) {
+    auto envi = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
+    wo_bn = envi("VAURA_WO_BN", 64); wo_ks = envi("VAURA_WO_KSPLIT", 6);
+    w2_bn = envi("VAURA_W2_BN", 64); w2_ks = envi("VAURA_W2_KSPLIT", 6);  // 24 x 6 = 144 CTAs: one wave (8 -> 192 CTAs was 6 % slower)
+  }
   for (int l = 0; l < d.num_layers; ++l) {
     LinearTcArgs g{};
     g.state = state; g.pos0 = pos0; g.npos = npos; g.R = R; g.layer = l; g.d_model = d.d_model; g.kv = kv; g.rope = w.rope;
@@ -263,7 +270,7 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
     a.d_model = d.d_model; a.scale = 1.0f / sqrtf((float)kHeadDim); a.pdl = pdl;
     CUL(launch_attn_bf16(a, d.nhead, R, st));
     g.A = ws.attn_b; g.lda = D; g.W = w.wo + (size_t)l * D * D; g.N = D; g.K = D; g.epi = EPI_RESID; g.out_f32 = ws.h;
-    g.ldo = D; g.block_n = splitk ? 64 : (small ? 16 : 128); g.ksplit = splitk ? 6 : 1;
+    g.ldo = D; g.block_n = splitk ? wo_bn : (small ? 16 : 128); g.ksplit = splitk ? wo_ks : 1;
     CUL(launch_linear_tc(g, st));
     g.ksplit = 1;
     CUL(launch_rmsnorm_bf16(ws.h, w.ffn_norm + l * D, ws.xn_b, R, D, D, d.norm_eps, pdl, st));
@@ -271,7 +278,7 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
     g.out_bf16 = ws.act_b; g.ldo = F; g.block_n = small ? 64 : 128;
     CUL(launch_linear_tc(g, st));
     g.A = ws.act_b; g.lda = F; g.W = w.w2 + (size_t)l * D * F; g.N = D; g.K = F; g.epi = EPI_RESID; g.out_f32 = ws.h;
-    g.ldo = D; g.block_n = splitk ? 64 : (small ? 16 : 128); g.ksplit = splitk ? 8 : 1;
+    g.ldo = D; g.block_n = splitk ? w2_bn : (small ? 16 : 128); g.ksplit = splitk ? w2_ks : 1;
     CUL(launch_linear_tc(g, st));
     g.ksplit = 1;
   }
