@@ -248,6 +248,23 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
   int pdl = 0;
   (void)nopdl;
   { const char* m = getenv("VAURA_PDL_MODE"); if (m) pdl = atoi(m); }
+  // rows <= 64, one new position per row (graph-replayed decode step): one cooperative kernel for all layers + heads
+  {
+    static int fused_on = -1;
+    if (fused_on < 0) { const char* e = getenv("VAURA_FUSED_STEP"); fused_on = !(e && e[0] == '0'); }
+    if (fused_on && npos == 1 && !logits_all && state && fused_step_supported(R, d.d_model, d.ffn_dim, d.num_codebooks * d.vocab)) {
+      FusedStepArgs fa{};
+      fa.attn_norm = w.attn_norm; fa.ffn_norm = w.ffn_norm; fa.final_norm = w.final_norm; fa.rope = w.rope;
+      fa.h = ws.h; fa.xn = ws.xn_b; fa.q = ws.q_b; fa.attn = ws.attn_b; fa.act = ws.act_b; fa.logits = logits_dst;
+      fa.kv = kv; fa.state = const_cast<StepState*>(state);
+      fa.R = R; fa.L = d.num_layers; fa.D = d.d_model; fa.F = d.ffn_dim; fa.H = d.nhead; fa.NH = d.num_codebooks * d.vocab;
+      fa.wo_ksplit = 6; fa.w2_ksplit = 6;
+      fa.eps = d.norm_eps; fa.scale = 1.0f / sqrtf((float)kHeadDim);
+      { const char* tm = getenv("VAURA_PERSIST_TIMING"); fa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
+      CUL(launch_decode_fused_bf16(fa, w.wqkv, w.wo, w.w13, w.w2, w.w_heads, st));
+      return VAURA_OK;
+    }
+  }
   const char* nosplit = getenv("VAURA_NO_SPLITK");
   const bool splitk = small && !(nosplit && nosplit[0] == '1');
   // tuning knobs of the two residual GEMMs (N tile, split-K factor)

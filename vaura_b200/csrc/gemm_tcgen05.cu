@@ -521,6 +521,373 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused decode step of the bf16 path for up to 64 sequence rows (one new position per row): ONE cooperative kernel runs
+// the 24 layers + final norm + heads that transformer_pass_bf16 issues as 170 launches.  Each phase is the same tile
+// arithmetic as the stand-alone kernels (rmsnorm_bf16_kernel, gemm_tc_kernel with UMMA M = 64 and 4 K blocks per stage,
+// attn_bf16_kernel restated per warp); phases are separated by a device-wide barrier instead of a kernel boundary, so the
+// ~4 us of launch + prologue (barrier init, TMEM allocation, tensor-map fetch, pipeline fill from a cold start) per kernel
+// is paid once per step.  Every GEMM phase has at most one tile per CTA (144 / 128 tiles on 148 SMs).
+// Cross-CTA data (h, xn, q, K/V, attention output, SwiGLU output) is read with L2 loads or TMA after the barrier's
+// acquire; a proxy fence orders the generic-proxy stores of the previous phase before the async-proxy (TMA) reads.
+// ------------------------------------------------------------------------------------------------
+namespace fused {
+constexpr int kStages = 3, kKsub = 4, kBlockK = 64, kTileM64 = 64;
+constexpr int kABytes = kTileM64 * kBlockK * 2;           // 8 KB activation sub-tile
+constexpr int kBMax = 64 * kBlockK * 2;                   // 8 KB weight sub-tile (BN = 64; BN = 32 uses half of it)
+constexpr int kSubBytes = kABytes + kBMax, kStageBytes = kKsub * kSubBytes;  // 64 KB per stage
+constexpr int kAttnScratch = 10 * (kHeadDim + kMaxCtx) * 4;                  // per-warp q + scores
+constexpr int kSmem = kStages * kStageBytes + 256 + kAttnScratch + 1024;
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// device-wide barrier: no bulk copy is in flight when a CTA arrives (its mainloop has drained), so the release /
+// acquire pair costs its idle latency (~0.75 us, profiles/r01_probe_sync_latency_under_tma.txt)
+__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned target) {
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    if ((int)(ld_acquire_u32(counter) - target) < 0) {
+      const long long t0 = clock64();
+      while ((int)(ld_acquire_u32(counter) - target) < 0)
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+  }
+  __syncthreads();
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+}  // namespace fused
+
+// per-CTA pipeline state that survives across the GEMM tiles of a step
+struct FusedPipe {
+  uint8_t* smem;
+  uint64_t *full, *empty, *tmem_full;
+  uint32_t tmem_base;
+  int git;     // ring iterations so far (identical in the producer and the MMA thread)
+  int tiles;   // accumulator uses so far (epilogue warps)
+};
+
+// one 64 x BN output tile: A = activations [64 x K] (map tmA, rows 0..63), B = weight rows [n0, n0 + BN) of layer `layer`
+// (map tmB), K blocks [kb0, kb1); warp 0 = TMA, warp 1 = MMA issue, warps 2-9 = epilogue
+template <int BN>
+__device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap* tmA, const CUtensorMap* tmB, int layer, int n0,
+                                                int kb0, int kb1, const EpiLinear::Params& ep) {
+  using namespace fused;
+  constexpr int B_BYTES = BN * kBlockK * 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int iters = (kb1 - kb0 + kKsub - 1) / kKsub;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int gi = pp.git + it, s = gi % kStages;
+        const uint32_t ph = (gi / kStages) & 1;
+        const int u0 = kb0 + it * kKsub, nsub = min(kKsub, kb1 - u0);
+        uint8_t* ss = pp.smem + s * kStageBytes;
+        mbar_wait(&pp.empty[s], ph ^ 1);
+        mbar_expect_tx(&pp.full[s], nsub * (kABytes + B_BYTES));
+        for (int sub = 0; sub < nsub; ++sub) {
+          uint8_t* sa = ss + sub * kSubBytes;
+          tma_load_3d(sa + kABytes, tmB, &pp.full[s], (u0 + sub) * kBlockK, n0, layer);
+          tma_load_3d(sa, tmA, &pp.full[s], (u0 + sub) * kBlockK, 0, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kTileM64, BN, 1);
+      for (int it = 0; it < iters; ++it) {
+        const int gi = pp.git + it, s = gi % kStages;
+        const uint32_t ph = (gi / kStages) & 1;
+        mbar_wait(&pp.full[s], ph);
+        tcgen05_fence_after();
+        const int nsub = min(kKsub, kb1 - (kb0 + it * kKsub));
+        for (int sub = 0; sub < nsub; ++sub) {
+          const uint32_t a_addr = smem_u32(pp.smem + s * kStageBytes + sub * kSubBytes);
+          const uint64_t adesc = make_smem_desc<128>(a_addr), bdesc = make_smem_desc<128>(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) umma_bf16_f16(pp.tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | sub | k) != 0);
+        }
+        umma_commit(&pp.empty[s]);
+      }
+      umma_commit(pp.tmem_full);
+    }
+  } else {
+    mbar_wait(pp.tmem_full, pp.tiles & 1);
+    tcgen05_fence_after();
+    const int q = warp & 3;
+    const int m = q * 16 + lane;  // UMMA M = 64: rows 16q..16q+15 sit in lanes 32q..32q+15
+    const bool row_ok = lane < 16;
+    constexpr int kChunks = BN / 16, kHalf = (kChunks + 1) / 2;
+    const int c_begin = (warp - 2) < 4 ? 0 : kHalf * 16, c_end = (warp - 2) < 4 ? kHalf * 16 : BN;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 16) {
+      float v[16];
+      tmem_ld16(pp.tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
+      if (row_ok) EpiLinear::apply(ep, 0, 0, m, n0 + c, v);
+    }
+    tcgen05_fence_before();
+  }
+  pp.git += iters;
+  pp.tiles += 1;
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_constant__ CUtensorMap tm_attn,
+                       const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wqkv,
+                       const __grid_constant__ CUtensorMap tm_wo, const __grid_constant__ CUtensorMap tm_w13,
+                       const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_heads,
+                       const FusedStepArgs a) {
+  using namespace fused;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  FusedPipe pp;
+  pp.smem = smem;
+  pp.full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  pp.empty = pp.full + kStages;
+  pp.tmem_full = pp.empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pp.tmem_full + 1);
+  float* scratch = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
+  pp.git = 0;
+  pp.tiles = 0;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x, G = gridDim.x;
+  const int R = a.R, D = a.D, F = a.F;
+  const unsigned epoch = a.state->epoch;
+  const int p = a.state->offset - 1;  // position fed by this step
+  const unsigned nbar = (unsigned)(7 * a.L + 1);
+  unsigned bi = 0;
+  int stamp_i = 0;
+  auto stamp = [&]() {  // optional phase timestamps of CTA 0 (profiles/fused_timing.py)
+    if (a.timing && cta == 0 && tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.timing[stamp_i] = t;
+    }
+    ++stamp_i;
+  };
+  auto sync_all = [&]() { stamp(); grid_sync(&a.state->barrier, (epoch * nbar + (++bi)) * (unsigned)G); stamp(); };
+
+  if (warp == 0 && lane == 0) {
+    const CUtensorMap* maps[8] = {&tm_xn, &tm_attn, &tm_act, &tm_wqkv, &tm_wo, &tm_w13, &tm_w2, &tm_heads};
+    for (int i = 0; i < 8; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(maps[i]) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&pp.full[s], 1);
+      mbar_init(&pp.empty[s], 1);
+    }
+    mbar_init(pp.tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  pp.tmem_base = *tmem_slot;
+
+  // ---- RMSNorm of the residual row `cta` (llama.py:147-158): fp32 math, bf16 output = the next GEMM's A operand ----
+  auto rmsnorm_phase = [&](const float* w) {
+    if (cta < R) {
+      float* red = scratch;
+      const float* x = a.h + (size_t)cta * D;
+      const int n4 = D >> 2;
+      float4 v[2];
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = tid + i * kGemmThreads;
+        v[i] = c < n4 ? __ldcg(reinterpret_cast<const float4*>(x) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) red[warp] = ss;
+      __syncthreads();
+      float tot = 0.f;
+      for (int i = 0; i < kGemmThreads / 32; ++i) tot += red[i];
+      const float rs = rsqrtf(tot / (float)D + a.eps);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = tid + i * kGemmThreads;
+        if (c < n4) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(w) + c);
+          uint2 o;
+          *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v[i].x * rs * g.x, v[i].y * rs * g.y);
+          *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v[i].z * rs * g.z, v[i].w * rs * g.w);
+          *reinterpret_cast<uint2*>(a.xn + (size_t)cta * D + 4 * c) = o;
+        }
+      }
+    }
+  };
+
+  // ---- attention (llama.py:246-255): one warp per (row, head) over the paged bf16 cache, fp32 softmax.  The loads of
+  //      32 key rows (scores) / 16 value rows (P.V) are issued before their arithmetic so ~6 KB per warp is in flight ----
+  auto attention_phase = [&](int layer) {
+    float* qs = scratch + warp * (kHeadDim + kMaxCtx);
+    float* sc = qs + kHeadDim;
+    const __nv_bfloat16* kvp = reinterpret_cast<const __nv_bfloat16*>(a.kv.pages);
+    const int nctx = p + 1, psz = a.kv.page_size;
+    const size_t page_stride = (size_t)a.kv.nhead * psz * kHeadDim;
+    for (int item = warp * G + cta; item < R * a.H; item += G * (kGemmThreads / 32)) {  // CTA-fastest: every SM gets ~7 items
+      const int row = item / a.H, hd = item % a.H;
+      // the sequence row's pages (<= 16 for 256 positions of 16); lane i holds page i
+      const int mypage = lane < a.kv.max_pages_per_seq ? a.kv.page_table[row * a.kv.max_pages_per_seq + lane] : 0;
+      auto row_ptr = [&](int kvsel, int jj) {
+        const int page = __shfl_sync(0xffffffffu, mypage, jj / psz);
+        return kvp + ((size_t)(layer * 2 + kvsel) * a.kv.num_pages + page) * page_stride + ((size_t)hd * psz + jj % psz) * kHeadDim;
+      };
+      __syncwarp();
+      for (int d = lane; d < kHeadDim; d += 32)
+        qs[d] = __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(a.q) + (size_t)row * D + hd * kHeadDim + d)));
+      __syncwarp();
+      // scores: 4 lanes per key position; lane t takes the 16-byte chunks t, t+4, t+8 of the 192-byte row, so one load
+      // instruction reads 64 contiguous bytes per row (whole sectors); 4 x 8 positions per iteration
+      const int g = lane >> 2, t = lane & 3;
+      float q24[24];
+#pragma unroll
+      for (int i = 0; i < 24; ++i) q24[i] = qs[(4 * (i >> 3) + t) * 8 + (i & 7)];
+      float mx = -INFINITY;
+      for (int j0 = 0; j0 < nctx; j0 += 32) {
+        uint4 kk[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = min(j0 + 8 * u + g, nctx - 1);  // clamp: every lane takes part in the page shuffle
+          const uint4* kr = reinterpret_cast<const uint4*>(row_ptr(0, jj)) + t;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) kk[u][c] = __ldcg(kr + 4 * c);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = j0 + 8 * u + g;
+          float sdot = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const uint32_t w[4] = {kk[u][c].x, kk[u][c].y, kk[u][c].z, kk[u][c].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              sdot = fmaf(q24[c * 8 + 2 * e], bf16_lo(w[e]), sdot);
+              sdot = fmaf(q24[c * 8 + 2 * e + 1], bf16_hi(w[e]), sdot);
+            }
+          }
+          sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+          sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+          if (jj < nctx) {
+            sdot *= a.scale;
+            if (t == 0) sc[jj] = sdot;
+            mx = fmaxf(mx, sdot);
+          }
+        }
+      }
+      mx = warp_max(mx);
+      __syncwarp();
+      float sum = 0.f;
+      for (int jj = lane; jj < nctx; jj += 32) {
+        const float e = expf(sc[jj] - mx);
+        sc[jj] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      __syncwarp();
+      // P.V: lanes 0-11 take the even positions, lanes 12-23 the odd ones, 8 dims (one 16-byte load) each; 32 positions
+      // (16 loads per lane, 6 KB per warp) per iteration; the two halves are added at the end
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+      const int half = lane >= 12 ? 1 : 0, dl = lane < 24 ? lane - 12 * half : 0;
+      for (int j0 = 0; j0 < nctx; j0 += 32) {
+        uint4 vv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          vv[u] = __ldcg(reinterpret_cast<const uint4*>(row_ptr(1, min(j0 + 2 * u + half, nctx - 1)) + 8 * dl));
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int jj = j0 + 2 * u + half;
+          const float pj = (jj < nctx && lane < 24) ? sc[jj] : 0.f;
+          const uint32_t w[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            o[2 * e] = fmaf(pj, bf16_lo(w[e]), o[2 * e]);
+            o[2 * e + 1] = fmaf(pj, bf16_hi(w[e]), o[2 * e + 1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += __shfl_down_sync(0xffffffffu, o[i], 12);
+      if (lane < 12) {
+        const float inv = 1.f / sum;
+        uint4 ov;
+        *reinterpret_cast<__nv_bfloat162*>(&ov.x) = __floats2bfloat162_rn(o[0] * inv, o[1] * inv);
+        *reinterpret_cast<__nv_bfloat162*>(&ov.y) = __floats2bfloat162_rn(o[2] * inv, o[3] * inv);
+        *reinterpret_cast<__nv_bfloat162*>(&ov.z) = __floats2bfloat162_rn(o[4] * inv, o[5] * inv);
+        *reinterpret_cast<__nv_bfloat162*>(&ov.w) = __floats2bfloat162_rn(o[6] * inv, o[7] * inv);
+        *reinterpret_cast<uint4*>(a.attn + (size_t)row * D + hd * kHeadDim + 8 * lane) = ov;
+      }
+    }
+  };
+
+  EpiLinear::Params ep{};
+  ep.R = R; ep.rope = a.rope; ep.kv = a.kv; ep.state = a.state; ep.pos0 = 0; ep.npos = 1; ep.d_model = D;
+  ep.perm_S = 0; ep.perm_V = 0;
+
+  for (int l = 0; l < a.L; ++l) {
+    rmsnorm_phase(a.attn_norm + (size_t)l * D);
+    sync_all();
+    // wqkv: 144 tiles of 32 output features, RoPE + KV append + bf16 q in the epilogue
+    if (cta < 3 * D / 32) {
+      ep.mode = EPI_QKV; ep.N = 3 * D; ep.out_bf16 = a.q; ep.out_f32 = nullptr; ep.ldo = D; ep.layer = l; ep.atomic = 0;
+      fused_gemm_tile<32>(pp, &tm_xn, &tm_wqkv, l, cta * 32, 0, D / kBlockK, ep);
+    }
+    sync_all();
+    attention_phase(l);
+    sync_all();
+    // wo + residual: 24 N tiles x wo_ksplit K slices, fp32 vector reductions into h
+    {
+      const int nt = D / 64, tiles = nt * a.wo_ksplit;
+      if (cta < tiles) {
+        const int split = cta / nt, kb = D / kBlockK;
+        ep.mode = EPI_RESID; ep.N = D; ep.out_f32 = a.h; ep.ldo = D; ep.atomic = 1;
+        fused_gemm_tile<64>(pp, &tm_attn, &tm_wo, l, (cta % nt) * 64, kb * split / a.wo_ksplit, kb * (split + 1) / a.wo_ksplit, ep);
+      }
+    }
+    sync_all();
+    rmsnorm_phase(a.ffn_norm + (size_t)l * D);
+    sync_all();
+    // w1|w3 (rows interleaved) + SiLU * mul: 128 tiles of 64 rows = 32 hidden units
+    if (cta < 2 * F / 64) {
+      ep.mode = EPI_SWIGLU; ep.N = 2 * F; ep.out_bf16 = a.act; ep.ldo = F; ep.atomic = 0;
+      fused_gemm_tile<64>(pp, &tm_xn, &tm_w13, l, cta * 64, 0, D / kBlockK, ep);
+    }
+    sync_all();
+    // w2 + residual
+    {
+      const int nt = D / 64, tiles = nt * a.w2_ksplit;
+      if (cta < tiles) {
+        const int split = cta / nt, kb = F / kBlockK;
+        ep.mode = EPI_RESID; ep.N = D; ep.out_f32 = a.h; ep.ldo = D; ep.atomic = 1;
+        fused_gemm_tile<64>(pp, &tm_act, &tm_w2, l, (cta % nt) * 64, kb * split / a.w2_ksplit, kb * (split + 1) / a.w2_ksplit, ep);
+      }
+    }
+    sync_all();
+  }
+  rmsnorm_phase(a.final_norm);
+  sync_all();
+  // heads: NH / 64 tiles (144 for 9 x 1024), plain fp32 store
+  for (int t = cta; t < a.NH / 64; t += G) {
+    ep.mode = EPI_STORE; ep.N = a.NH; ep.out_f32 = a.logits; ep.ldo = a.NH; ep.atomic = 0;
+    fused_gemm_tile<64>(pp, &tm_xn, &tm_heads, 0, t * 64, 0, D / kBlockK, ep);
+    __syncthreads();  // the accumulator is single-buffered: drain it before the next tile's MMAs
+  }
+  if (cta == 0 && tid == 0) a.state->epoch = epoch + 1;  // every CTA read the epoch before its first barrier arrival
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pp.tmem_base), "r"(64));
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -644,6 +1011,51 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cu
   TC_CASE(16, 32, 8)
 #undef TC_CASE
   return cudaErrorInvalidValue;
+}
+
+// Fused decode step (decode_step_fused_bf16): tensor maps are rebuilt per call (they are baked into the captured graph node)
+bool fused_step_supported(int R, int D, int F, int NH) {
+  return R >= 1 && R <= 64 && D % 64 == 0 && F % 64 == 0 && NH % 64 == 0 && (3 * D) % 32 == 0 && D / 4 <= 2 * kGemmThreads;
+}
+
+cudaError_t launch_decode_fused_bf16(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
+                                     const void* w_heads, cudaStream_t st) {
+  if (!fused_step_supported(a.R, a.D, a.F, a.NH)) return cudaErrorInvalidValue;
+  static int sms = 0;
+  if (!sms) {
+    cudaError_t e = cudaFuncSetAttribute(decode_step_fused_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::kSmem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_step_fused_bf16, kGemmThreads, fused::kSmem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) { sms = 0; return cudaErrorLaunchOutOfResources; }
+  }
+  const int need = a.D / 64 * (a.wo_ksplit > a.w2_ksplit ? a.wo_ksplit : a.w2_ksplit);
+  if (3 * a.D / 32 > sms || 2 * a.F / 64 > sms || need > sms) return cudaErrorInvalidValue;  // one tile per CTA per phase
+  const uint64_t D = a.D, F = a.F, L = a.L;
+  CUtensorMap m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads;
+  bool ok = make_map(&m_xn, a.xn, D, a.R, 1, D, (uint64_t)a.R * D, 64, 64, false) &&
+            make_map(&m_attn, a.attn, D, a.R, 1, D, (uint64_t)a.R * D, 64, 64, false) &&
+            make_map(&m_act, a.act, F, a.R, 1, F, (uint64_t)a.R * F, 64, 64, false) &&
+            make_map(&m_wqkv, wqkv, D, 3 * D, L, D, 3 * D * D, 64, 32, false) &&
+            make_map(&m_wo, wo, D, D, L, D, D * D, 64, 64, false) &&
+            make_map(&m_w13, w13, D, 2 * F, L, D, 2 * F * D, 64, 64, false) &&
+            make_map(&m_w2, w2, F, D, L, F, D * F, 64, 64, false) &&
+            make_map(&m_heads, w_heads, D, a.NH, 1, D, (uint64_t)a.NH * D, 64, 64, false);
+  if (!ok) return cudaErrorUnknown;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(sms);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = fused::kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, decode_step_fused_bf16, m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads, a);
 }
 
 // Linear layer of the bf16 sampler path: out = A[R][K] (bf16) x W[N][K]^T (bf16) with a fused epilogue.

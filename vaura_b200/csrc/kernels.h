@@ -104,6 +104,24 @@ struct AttnBf16Args {
 };
 cudaError_t launch_attn_bf16(const AttnBf16Args& a, int nhead, int rows, cudaStream_t st);
 
+// fused decode step of the bf16 path, rows <= 64 (gemm_tcgen05.cu: decode_step_fused_bf16)
+struct FusedStepArgs {
+  const float *attn_norm, *ffn_norm, *final_norm, *rope;
+  float* h;                  // [R][D] residual stream (written by embed_kernel before this kernel)
+  __nv_bfloat16 *xn, *q, *attn, *act;  // [R][D], [R][D], [R][D], [R][F]
+  float* logits;             // [R][NH]
+  KvView kv;                 // bf16 pages
+  StepState* state;
+  int R, L, D, F, H, NH;     // rows, layers, d_model, ffn, heads, K*V logits per row
+  int wo_ksplit, w2_ksplit;
+  float eps, scale;
+  unsigned long long* timing;  // optional: timestamps (ns) of CTA 0 before / after every device-wide barrier
+};
+
+bool fused_step_supported(int R, int D, int F, int NH);
+cudaError_t launch_decode_fused_bf16(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
+                                     const void* w_heads, cudaStream_t st);
+
 bool conv_tc_supported(int Cin, int Cout, int ntaps, int nphase);
 cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cudaStream_t st);
 cudaError_t init_decode_kernels();
