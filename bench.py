@@ -251,8 +251,20 @@ def main():
         kern = "decode_step_cluster" if rows <= 2 else "decode_step_persistent"
         kname = f"{kern}<{rows}> (whole decode step: 24 layers + heads + sampling)"
         key = f"{kern}_rows{rows}"
+    elif rows <= 64:
+        # rows 16..64: the whole decode step is ONE cooperative kernel (decode_step_fused_bf16: rmsnorm, tcgen05 GEMM tiles,
+        # attention, device-wide barriers between phases); timed through the token-only generate, which is 228 x (embed
+        # kernel + that kernel + sampling kernel) back to back
+        def tokens_only_r():
+            model.generate(frames=feats_dev, clip_indices=clip_ids, _decode_audio=False, **kw)
+        tokens_only_r()
+        k_ms = timed(tokens_only_r, 3) / 3 / (T + 8)
+        kv_bytes = 24 * 2 * d.d_model * 2 * rows * (T + 8) / 2  # bf16 KV read, mean context (S/2 positions)
+        alg_bytes = step_bytes + kv_bytes
+        kname = f"decode_step_fused_bf16 ({rows} rows: 24 layers + heads in one launch; embed + sampling kernels included in the time)"
+        key = f"decode_step_fused_bf16_rows{rows}"
     else:
-        # rows >= 16: tcgen05 linear over w1|w3 (25.2 MB of weights per launch), 24 different matrices back to back
+        # rows > 64: tcgen05 linear over w1|w3 (25.2 MB of weights per launch), 24 different matrices back to back
         w13 = model.sampler.weights["w13"]
         x = torch.randn(rows, d.d_model, device=dev).to(torch.bfloat16)
         y = torch.empty(rows, 2 * d.ffn_dim, device=dev)
