@@ -235,6 +235,22 @@ def test_bf16_path_generate_batch16(tiny_model, tiny_oracle):
         assert torch.equal(o32["sampled_indices"].cpu(), r32)
 
 
+def test_bf16_path_full_size_fused_step():
+    """Full-size model, 24 sequence rows: the fused cooperative decode-step kernel (decode_step_fused_bf16) with every GEMM
+    phase at its real tile count (144 / 128 tiles on 148 SMs), teacher-forced against the fp32 oracle on our own tokens."""
+    B, T = 24, 6
+    m = build_model(FULL_SAMPLER, FULL_CODEC)
+    oracle = vo.SamplerOracle(make_sampler_state_dict(FULL_SAMPLER, 0), FULL_SAMPLER)
+    feats = make_avclip_features(B, 33)
+    out = m.generate(frames=feats.cuda(), max_new_tokens=T, use_sampling=False, prompt_is_encoded=True,
+                     return_sampled_indices=True, check=True, _return_logits=True, _decode_audio=False)
+    codes = out["sampled_indices"].cpu()
+    seq, _ = vo.build_pattern_sequence(codes, 1024)
+    ref = oracle.forward_full(seq[..., :-1], feats.reshape(B, 32, 768))
+    mine = out["_logits"][1:].cpu().permute(1, 2, 0, 3)
+    assert rel_err(mine, ref) < BF16_LOGIT_TOL
+
+
 def test_bf16_path_with_cfg_and_prompt_prefill(tiny_model, tiny_oracle):
     B, T, Tp = 8, 30, 11  # 16 rows with CFG; prompt -> prefill of 12 columns on the tensor-core path
     feats = make_avclip_features(B, 33)
