@@ -724,8 +724,10 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     }
   };
 
-  // ---- attention (llama.py:246-255): one warp per (row, head) over the paged bf16 cache, fp32 softmax.  The loads of
-  //      32 key rows (scores) / 16 value rows (P.V) are issued before their arithmetic so ~6 KB per warp is in flight ----
+  // ---- attention (llama.py:246-255): one warp per (row, head) over the paged bf16 cache, fp32 softmax.  Positions are
+  //      walked 32 at a time as two 16-position runs, each inside one page (page size 16 or 32): two page look-ups
+  //      (shuffles) and two base addresses per iteration, every load a constant offset from them; the 12 key loads /
+  //      16 value loads of an iteration are issued before their arithmetic (6 KB per warp in flight) ----
   auto attention_phase = [&](int layer) {
     float* qs = scratch + warp * (kHeadDim + kMaxCtx);
     float* sc = qs + kHeadDim;
@@ -736,29 +738,32 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       const int row = item / a.H, hd = item % a.H;
       // the sequence row's pages (<= 16 for 256 positions of 16); lane i holds page i
       const int mypage = lane < a.kv.max_pages_per_seq ? a.kv.page_table[row * a.kv.max_pages_per_seq + lane] : 0;
-      auto row_ptr = [&](int kvsel, int jj) {
-        const int page = __shfl_sync(0xffffffffu, mypage, jj / psz);
-        return kvp + ((size_t)(layer * 2 + kvsel) * a.kv.num_pages + page) * page_stride + ((size_t)hd * psz + jj % psz) * kHeadDim;
+      // first row of the 16-position run that starts at position j (j % 16 == 0), K (kvsel 0) or V (1)
+      auto run_ptr = [&](int kvsel, int j) {
+        const int page = __shfl_sync(0xffffffffu, mypage, j / psz);
+        return kvp + ((size_t)(layer * 2 + kvsel) * a.kv.num_pages + page) * page_stride + ((size_t)hd * psz + j % psz) * kHeadDim;
       };
       __syncwarp();
       for (int d = lane; d < kHeadDim; d += 32)
         qs[d] = __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(a.q) + (size_t)row * D + hd * kHeadDim + d)));
       __syncwarp();
-      // scores: 4 lanes per key position; lane t takes the 16-byte chunks t, t+4, t+8 of the 192-byte row, so one load
-      // instruction reads 64 contiguous bytes per row (whole sectors); 4 x 8 positions per iteration
+      // scores: 4 lanes per key position; lane t takes the 16-byte chunks t, t+4, t+8 of the 192-byte row (one load
+      // instruction reads 64 contiguous bytes per row); 4 x 8 positions per iteration
       const int g = lane >> 2, t = lane & 3;
       float q24[24];
 #pragma unroll
       for (int i = 0; i < 24; ++i) q24[i] = qs[(4 * (i >> 3) + t) * 8 + (i & 7)];
       float mx = -INFINITY;
       for (int j0 = 0; j0 < nctx; j0 += 32) {
+        const bool two = j0 + 16 < nctx;
+        const uint4* runA = reinterpret_cast<const uint4*>(run_ptr(0, j0));
+        const uint4* runB = reinterpret_cast<const uint4*>(run_ptr(0, two ? j0 + 16 : j0));
         uint4 kk[4][3];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int jj = min(j0 + 8 * u + g, nctx - 1);  // clamp: every lane takes part in the page shuffle
-          const uint4* kr = reinterpret_cast<const uint4*>(row_ptr(0, jj)) + t;
+          const uint4* kr = ((u < 2 || !two) ? runA : runB) + ((8 * (u & 1) + g) * 12 + t);  // row (8u + g) % 16 of the run
 #pragma unroll
-          for (int c = 0; c < 3; ++c) kk[u][c] = __ldcg(kr + 4 * c);
+          for (int c = 0; c < 3; ++c) kk[u][c] = __ldcg(kr + 4 * c);  // rows past nctx stay inside the page: read, not used
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -785,28 +790,30 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       mx = warp_max(mx);
       __syncwarp();
       float sum = 0.f;
-      for (int jj = lane; jj < nctx; jj += 32) {
-        const float e = expf(sc[jj] - mx);
+      for (int jj = lane; jj < ((nctx + 31) & ~31); jj += 32) {  // positions past the context get probability 0
+        const float e = jj < nctx ? expf(sc[jj] - mx) : 0.f;
         sc[jj] = e;
         sum += e;
       }
       sum = warp_sum(sum);
       __syncwarp();
-      // P.V: lanes 0-11 take the even positions, lanes 12-23 the odd ones, 8 dims (one 16-byte load) each; 32 positions
-      // (16 loads per lane, 6 KB per warp) per iteration; the two halves are added at the end
+      // P.V: lanes 0-11 take the even positions, lanes 12-23 the odd ones, 8 dims (one 16-byte load) each
       float o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = 0.f;
       const int half = lane >= 12 ? 1 : 0, dl = lane < 24 ? lane - 12 * half : 0;
       for (int j0 = 0; j0 < nctx; j0 += 32) {
+        const bool two = j0 + 16 < nctx;
+        const uint4* runA = reinterpret_cast<const uint4*>(run_ptr(1, j0)) + half * 12 + dl;
+        const uint4* runB = reinterpret_cast<const uint4*>(run_ptr(1, two ? j0 + 16 : j0)) + half * 12 + dl;
         uint4 vv[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
-          vv[u] = __ldcg(reinterpret_cast<const uint4*>(row_ptr(1, min(j0 + 2 * u + half, nctx - 1)) + 8 * dl));
+        for (int u = 0; u < 16; ++u)  // row 2 (u % 8) + half of the run; rows past the context may hold anything (NaN bit patterns)
+          vv[u] = j0 + 2 * u + half < nctx ? __ldcg((u < 8 ? runA : runB) + (u & 7) * 24) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const int jj = j0 + 2 * u + half;
-          const float pj = (jj < nctx && lane < 24) ? sc[jj] : 0.f;
+          const float pj = (u < 8 || two) ? sc[jj] : 0.f;
           const uint32_t w[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
