@@ -261,6 +261,7 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
       fa.wo_ksplit = 6; fa.w2_ksplit = 6;
       fa.eps = d.norm_eps; fa.scale = 1.0f / sqrtf((float)kHeadDim);
       { const char* tm = getenv("VAURA_PERSIST_TIMING"); fa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
+      { const char* tc = getenv("VAURA_TIMING_CTA"); fa.timing_cta = tc ? atoi(tc) : 0; }
       CUL(launch_decode_fused_bf16(fa, w.wqkv, w.wo, w.w13, w.w2, w.w_heads, st));
       return VAURA_OK;
     }

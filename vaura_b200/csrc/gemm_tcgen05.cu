@@ -662,7 +662,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   unsigned bi = 0;
   int stamp_i = 0;
   auto stamp = [&]() {  // optional phase timestamps of CTA 0 (profiles/fused_timing.py)
-    if (a.timing && cta == 0 && tid == 0) {
+    if (a.timing && cta == a.timing_cta && tid == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       a.timing[stamp_i] = t;

@@ -115,7 +115,8 @@ struct FusedStepArgs {
   int R, L, D, F, H, NH;     // rows, layers, d_model, ffn, heads, K*V logits per row
   int wo_ksplit, w2_ksplit;
   float eps, scale;
-  unsigned long long* timing;  // optional: timestamps (ns) of CTA 0 before / after every device-wide barrier
+  unsigned long long* timing;  // optional: timestamps (ns) of CTA `timing_cta` before / after every device-wide barrier
+  int timing_cta;
 };
 
 bool fused_step_supported(int R, int D, int F, int NH);
