@@ -228,7 +228,8 @@ static int transformer_pass(const vaura_sampler* s, const Workspace& ws, const i
 // Same pass on the tensor-core path: bf16 activations, tcgen05 GEMMs with fused epilogues.
 static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, const int32_t* seq, int batch, int S,
                                  const float* cond_rows, int rows, int npos, int pos0, const StepState* state,
-                                 const KvView& kv, float* logits_dst, bool logits_all, cudaStream_t st) {
+                                 const KvView& kv, float* logits_dst, bool logits_all, cudaStream_t st,
+                                 const SampleArgs* fuse_sample = nullptr, bool* sampled = nullptr) {
   const vaura_sampler_dims& d = s->d;
   const vaura_sampler_weights& w = s->w;
   const int R = rows * npos;
@@ -236,6 +237,36 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
   e.seq = seq; e.cond_rows = cond_rows; e.tables = w.tok_tables; e.h = ws.h; e.state = state; e.pos0 = pos0;
   e.npos = npos; e.batch = batch; e.K = d.num_codebooks; e.S = S; e.vocab = d.vocab; e.d_model = d.d_model;
   e.cond_dim = d.cond_dim; e.cond_tokens = d.cond_tokens; e.atpvf = d.audio_tokens_per_video_frame;
+  // rows <= 64, one new position per row (graph-replayed decode step): one cooperative kernel for all layers + heads
+  // and, when the caller hands in the sampling arguments, for the embedding and the sampling stage as well
+  {
+    static int fused_on = -1, fuse_io_on = -1;
+    if (fused_on < 0) { const char* ev = getenv("VAURA_FUSED_STEP"); fused_on = !(ev && ev[0] == '0'); }
+    if (fuse_io_on < 0) { const char* ev = getenv("VAURA_FUSED_IO"); fuse_io_on = !(ev && ev[0] == '0'); }
+    if (fused_on && npos == 1 && !logits_all && state && fused_step_supported(R, d.d_model, d.ffn_dim, d.num_codebooks * d.vocab)) {
+      const bool io = fuse_io_on && fuse_sample && sampled && d.cond_dim % 4 == 0 && (d.d_model - d.cond_dim) % 4 == 0;
+      if (!io) CUL(launch_embed(e, R, st));
+      FusedStepArgs fa{};
+      fa.attn_norm = w.attn_norm; fa.ffn_norm = w.ffn_norm; fa.final_norm = w.final_norm; fa.rope = w.rope;
+      fa.h = ws.h; fa.xn = ws.xn_b; fa.q = ws.q_b; fa.attn = ws.attn_b; fa.act = ws.act_b; fa.logits = logits_dst;
+      fa.kv = kv; fa.state = const_cast<StepState*>(state);
+      fa.R = R; fa.L = d.num_layers; fa.D = d.d_model; fa.F = d.ffn_dim; fa.H = d.nhead; fa.NH = d.num_codebooks * d.vocab;
+      fa.wo_ksplit = 6; fa.w2_ksplit = 6;
+      fa.eps = d.norm_eps; fa.scale = 1.0f / sqrtf((float)kHeadDim);
+      { const char* tm = getenv("VAURA_PERSIST_TIMING"); fa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
+      { const char* tc = getenv("VAURA_TIMING_CTA"); fa.timing_cta = tc ? atoi(tc) : 0; }
+      fa.fuse_io = io ? 1 : 0;
+      if (io) {
+        fa.seq = seq; fa.cond_rows = cond_rows; fa.tables = w.tok_tables; fa.batch = batch; fa.Kc = d.num_codebooks; fa.S = S;
+        fa.vocab = d.vocab; fa.cond_dim = d.cond_dim; fa.cond_tokens = d.cond_tokens; fa.atpvf = d.audio_tokens_per_video_frame;
+        fa.sample = *fuse_sample;
+        fa.sample.state = nullptr;
+        *sampled = true;
+      }
+      CUL(launch_decode_fused_bf16(fa, w.wqkv, w.wo, w.w13, w.w2, w.w_heads, st));
+      return VAURA_OK;
+    }
+  }
   CUL(launch_embed(e, R, st));
   const size_t D = d.d_model, F = d.ffn_dim;
   // narrow N tiles when there is a single M tile so the weight stream is spread over all SMs
@@ -248,24 +279,6 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
   int pdl = 0;
   (void)nopdl;
   { const char* m = getenv("VAURA_PDL_MODE"); if (m) pdl = atoi(m); }
-  // rows <= 64, one new position per row (graph-replayed decode step): one cooperative kernel for all layers + heads
-  {
-    static int fused_on = -1;
-    if (fused_on < 0) { const char* e = getenv("VAURA_FUSED_STEP"); fused_on = !(e && e[0] == '0'); }
-    if (fused_on && npos == 1 && !logits_all && state && fused_step_supported(R, d.d_model, d.ffn_dim, d.num_codebooks * d.vocab)) {
-      FusedStepArgs fa{};
-      fa.attn_norm = w.attn_norm; fa.ffn_norm = w.ffn_norm; fa.final_norm = w.final_norm; fa.rope = w.rope;
-      fa.h = ws.h; fa.xn = ws.xn_b; fa.q = ws.q_b; fa.attn = ws.attn_b; fa.act = ws.act_b; fa.logits = logits_dst;
-      fa.kv = kv; fa.state = const_cast<StepState*>(state);
-      fa.R = R; fa.L = d.num_layers; fa.D = d.d_model; fa.F = d.ffn_dim; fa.H = d.nhead; fa.NH = d.num_codebooks * d.vocab;
-      fa.wo_ksplit = 6; fa.w2_ksplit = 6;
-      fa.eps = d.norm_eps; fa.scale = 1.0f / sqrtf((float)kHeadDim);
-      { const char* tm = getenv("VAURA_PERSIST_TIMING"); fa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
-      { const char* tc = getenv("VAURA_TIMING_CTA"); fa.timing_cta = tc ? atoi(tc) : 0; }
-      CUL(launch_decode_fused_bf16(fa, w.wqkv, w.wo, w.w13, w.w2, w.w_heads, st));
-      return VAURA_OK;
-    }
-  }
   const char* nosplit = getenv("VAURA_NO_SPLITK");
   const bool splitk = small && !(nosplit && nosplit[0] == '1');
   // tuning knobs of the two residual GEMMs (N tile, split-K factor)
@@ -317,9 +330,11 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
 
 static int run_pass(int precision, const vaura_sampler* s, const Workspace& ws, const int32_t* seq, int batch, int S,
                     const float* cond_rows, int rows, int npos, int pos0, const StepState* state, const KvView& kv,
-                    float* logits_dst, bool logits_all, cudaStream_t st) {
+                    float* logits_dst, bool logits_all, cudaStream_t st, const SampleArgs* fuse_sample = nullptr,
+                    bool* sampled = nullptr) {
   return precision == VAURA_PRECISION_BF16
-             ? transformer_pass_bf16(s, ws, seq, batch, S, cond_rows, rows, npos, pos0, state, kv, logits_dst, logits_all, st)
+             ? transformer_pass_bf16(s, ws, seq, batch, S, cond_rows, rows, npos, pos0, state, kv, logits_dst, logits_all, st,
+                                     fuse_sample, sampled)
              : transformer_pass(s, ws, seq, batch, S, cond_rows, rows, npos, pos0, state, kv, logits_dst, logits_all, st);
 }
 
@@ -430,8 +445,10 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
   g_capturing = true;
   g_capture_nodes = 0;
-  rc = run_pass(precision, s, ws, p->sequence, p->batch, S, p->cond_rows, rows, 1, 0, ws.state, kvv, ws.logits, false, cs);
-  if (rc == VAURA_OK) {
+  bool sampled = false;  // the fused bf16 step kernel also samples and advances the loop state
+  rc = run_pass(precision, s, ws, p->sequence, p->batch, S, p->cond_rows, rows, 1, 0, ws.state, kvv, ws.logits, false, cs, &sa,
+                &sampled);
+  if (rc == VAURA_OK && !sampled) {
     sa.state = ws.state;
     cudaError_t e = launch_sample(sa, cs);
     if (e != cudaSuccess) rc = fail(VAURA_ERR_CUDA, "launch_sample: %s", cudaGetErrorString(e));

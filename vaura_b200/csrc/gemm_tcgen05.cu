@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "sampling.cuh"
 
 namespace vaura {
 
@@ -639,7 +640,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
                        const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wqkv,
                        const __grid_constant__ CUtensorMap tm_wo, const __grid_constant__ CUtensorMap tm_w13,
                        const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_heads,
-                       const FusedStepArgs a) {
+                       const __grid_constant__ FusedStepArgs a) {
   using namespace fused;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -657,8 +658,9 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   const int cta = blockIdx.x, G = gridDim.x;
   const int R = a.R, D = a.D, F = a.F;
   const unsigned epoch = a.state->epoch;
-  const int p = a.state->offset - 1;  // position fed by this step
-  const unsigned nbar = (unsigned)(7 * a.L + 1);
+  const int offset = a.state->offset;
+  const int p = offset - 1;  // position fed by this step
+  const unsigned nbar = (unsigned)(7 * a.L + 1 + (a.fuse_io ? 1 : 0));
   unsigned bi = 0;
   int stamp_i = 0;
   auto stamp = [&]() {  // optional phase timestamps of CTA 0 (profiles/fused_timing.py)
@@ -690,18 +692,40 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   tcgen05_fence_after();
   pp.tmem_base = *tmem_slot;
 
-  // ---- RMSNorm of the residual row `cta` (llama.py:147-158): fp32 math, bf16 output = the next GEMM's A operand ----
-  auto rmsnorm_phase = [&](const float* w) {
+  // ---- RMSNorm of the residual row `cta` (llama.py:147-158): fp32 math, bf16 output = the next GEMM's A operand.
+  //      embed = true (first phase of a step with fuse_io): the row is built here from the conditioning row and the 9
+  //      folded token tables (llama.py:455-472, what embed_kernel does) and stored to h on the way ----
+  auto rmsnorm_phase = [&](const float* w, bool embed) {
     if (cta < R) {
       float* red = scratch;
-      const float* x = a.h + (size_t)cta * D;
+      float* hrow = a.h + (size_t)cta * D;
       const int n4 = D >> 2;
       float4 v[2];
       float ss = 0.f;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int c = tid + i * kGemmThreads;
-        v[i] = c < n4 ? __ldcg(reinterpret_cast<const float4*>(x) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < n4) {
+          if (!embed) {
+            v[i] = __ldcg(reinterpret_cast<const float4*>(hrow) + c);
+          } else {
+            const int C = a.cond_dim, TD = D - C, f = 4 * c;
+            if (f < C) {
+              int vrow = p / a.atpvf;
+              if (vrow > a.cond_tokens) vrow = a.cond_tokens;  // >= Tv -> empty_video_emb row (llama.py:569-572)
+              v[i] = __ldg(reinterpret_cast<const float4*>(a.cond_rows + ((size_t)cta * (a.cond_tokens + 1) + vrow) * C + f));
+            } else {
+              const int bt = cta % a.batch;  // CFG halves share the token sequence (vaura_model.py:795)
+              for (int k = 0; k < a.Kc; ++k) {  // python sum() adds the codebooks in order (llama.py:455-460)
+                const int tok = a.seq[((size_t)bt * a.Kc + k) * a.S + p];
+                const float4 tv = __ldg(reinterpret_cast<const float4*>(a.tables + ((size_t)k * (a.vocab + 1) + tok) * TD + (f - C)));
+                v[i].x += tv.x; v[i].y += tv.y; v[i].z += tv.z; v[i].w += tv.w;
+              }
+            }
+            reinterpret_cast<float4*>(hrow)[c] = v[i];
+          }
+        }
         ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
       }
       ss = warp_sum(ss);
@@ -841,7 +865,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   ep.perm_S = 0; ep.perm_V = 0;
 
   for (int l = 0; l < a.L; ++l) {
-    rmsnorm_phase(a.attn_norm + (size_t)l * D);
+    rmsnorm_phase(a.attn_norm + (size_t)l * D, l == 0 && a.fuse_io);
     sync_all();
     // wqkv: 144 tiles of 32 output features, RoPE + KV append + bf16 q in the epilogue
     if (cta < 3 * D / 32) {
@@ -861,7 +885,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       }
     }
     sync_all();
-    rmsnorm_phase(a.ffn_norm + (size_t)l * D);
+    rmsnorm_phase(a.ffn_norm + (size_t)l * D, false);
     sync_all();
     // w1|w3 (rows interleaved) + SiLU * mul: 128 tiles of 64 rows = 32 hidden units
     if (cta < 2 * F / 64) {
@@ -880,7 +904,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     }
     sync_all();
   }
-  rmsnorm_phase(a.final_norm);
+  rmsnorm_phase(a.final_norm, false);
   sync_all();
   // heads: NH / 64 tiles (144 for 9 x 1024), plain fp32 store
   for (int t = cta; t < a.NH / 64; t += G) {
@@ -888,7 +912,16 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     fused_gemm_tile<64>(pp, &tm_xn, &tm_heads, 0, t * 64, 0, D / kBlockK, ep);
     __syncthreads();  // the accumulator is single-buffered: drain it before the next tile's MMAs
   }
-  if (cta == 0 && tid == 0) a.state->epoch = epoch + 1;  // every CTA read the epoch before its first barrier arrival
+  if (a.fuse_io) {
+    // CFG / sampling / mask-fix / write-back (vaura_model.py:775-827, what sample_kernel does): one warp per (clip, codebook)
+    sync_all();
+    const int nrows = a.sample.B * a.sample.K;
+    for (int u = warp * G + cta; u < nrows; u += G * (kGemmThreads / 32)) sample_row(a.sample, u / a.sample.K, u % a.sample.K, lane, offset);
+  }
+  if (cta == 0 && tid == 0) {  // every CTA read offset / epoch before its first barrier arrival
+    a.state->epoch = epoch + 1;
+    if (a.fuse_io) a.state->offset = offset + 1;
+  }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pp.tmem_base), "r"(64));

@@ -117,6 +117,13 @@ struct FusedStepArgs {
   float eps, scale;
   unsigned long long* timing;  // optional: timestamps (ns) of CTA `timing_cta` before / after every device-wide barrier
   int timing_cta;
+  // fuse_io: the kernel also builds the embedding rows (first phase) and samples / writes back the tokens (last phase)
+  int fuse_io;
+  const int32_t* seq;       // [B][K][S]
+  const float* cond_rows;   // [rows][cond_tokens+1][cond_dim]
+  const float* tables;      // [K][V+1][d - cond_dim]
+  int batch, Kc, S, vocab, cond_dim, cond_tokens, atpvf;
+  SampleArgs sample;        // state = nullptr: the column comes from this kernel's own state read
 };
 
 bool fused_step_supported(int R, int D, int F, int NH);
