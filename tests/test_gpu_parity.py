@@ -270,6 +270,23 @@ def test_bf16_path_with_cfg_and_prompt_prefill(tiny_model, tiny_oracle):
     assert rel_err(mine, ref[:, :, Tp:]) < 2 * BF16_LOGIT_TOL  # CFG amplifies the error by ~cfg_scale
 
 
+def test_bf16_path_128_row_fused_step(tiny_model, tiny_oracle):
+    """48 clips with CFG = 96 sequence rows: the fused decode-step kernel's 128-row instance (UMMA M = 128)."""
+    B, T = 48, 12
+    feats = make_avclip_features(B, 41)
+    out = tiny_model.generate(frames=feats.cuda(), max_new_tokens=T, use_sampling=False, prompt_is_encoded=True,
+                              return_sampled_indices=True, cfg_scale=2.0, check=True, _return_logits=True,
+                              _decode_audio=False)
+    codes = out["sampled_indices"].cpu()
+    seq, _ = vo.build_pattern_sequence(codes, 1024)
+    f = feats.reshape(B, 32, 768)
+    fa = torch.cat([f, torch.zeros_like(f) + tiny_oracle.uncond], 0)
+    lg = tiny_oracle.forward_full(seq[..., :-1].repeat(2, 1, 1), fa)
+    ref = lg[B:] + (lg[:B] - lg[B:]) * 2.0
+    mine = out["_logits"][1:].cpu().permute(1, 2, 0, 3)
+    assert rel_err(mine, ref) < 2 * BF16_LOGIT_TOL  # CFG amplifies the error by ~cfg_scale
+
+
 def test_standalone_ops_match_torch_fp32():
     """Op-level entry points of the C ABI (the kernels bench.py times for the roofline)."""
     import ctypes as C

@@ -532,12 +532,20 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 // acquire; a proxy fence orders the generic-proxy stores of the previous phase before the async-proxy (TMA) reads.
 // ------------------------------------------------------------------------------------------------
 namespace fused {
-constexpr int kStages = 3, kKsub = 4, kBlockK = 64, kTileM64 = 64;
-constexpr int kABytes = kTileM64 * kBlockK * 2;           // 8 KB activation sub-tile
+constexpr int kKsub = 4, kBlockK = 64;
 constexpr int kBMax = 64 * kBlockK * 2;                   // 8 KB weight sub-tile (BN = 64; BN = 32 uses half of it)
-constexpr int kSubBytes = kABytes + kBMax, kStageBytes = kKsub * kSubBytes;  // 64 KB per stage
+// TM = UMMA M = rows of the activation tile: 64 (up to 64 sequence rows) or 128 (up to 128, e.g. 64 clips with CFG)
+template <int TM>
+struct Geo {
+  static constexpr int kABytes = TM * kBlockK * 2;                 // 8 / 16 KB activation sub-tile
+  static constexpr int kSubBytes = kABytes + kBMax;
+  static constexpr int kStageBytes = kKsub * kSubBytes;            // 64 / 96 KB per stage
+  static constexpr int kStages = TM == 64 ? 3 : 2;                 // 192 KB of ring either way
+  static constexpr int kRing = kStages * kStageBytes;
+};
 constexpr int kAttnScratch = 10 * (kHeadDim + kMaxCtx) * 4;                  // per-warp q + scores
-constexpr int kSmem = kStages * kStageBytes + 256 + kAttnScratch + 1024;
+constexpr int kSmem = 3 * 65536 + 256 + kAttnScratch + 1024;
+static_assert(Geo<64>::kRing == 3 * 65536 && Geo<128>::kRing == 3 * 65536, "ring size");
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -573,10 +581,12 @@ struct FusedPipe {
 
 // one 64 x BN output tile: A = activations [64 x K] (map tmA, rows 0..63), B = weight rows [n0, n0 + BN) of layer `layer`
 // (map tmB), K blocks [kb0, kb1); warp 0 = TMA, warp 1 = MMA issue, warps 2-9 = epilogue
-template <int BN>
+template <int BN, int TM>
 __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap* tmA, const CUtensorMap* tmB, int layer, int n0,
                                                 int kb0, int kb1, const EpiLinear::Params& ep) {
   using namespace fused;
+  using GE = Geo<TM>;
+  constexpr int kStages = GE::kStages, kStageBytes = GE::kStageBytes, kSubBytes = GE::kSubBytes, kABytes = GE::kABytes;
   constexpr int B_BYTES = BN * kBlockK * 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int iters = (kb1 - kb0 + kKsub - 1) / kKsub;
@@ -598,7 +608,7 @@ __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kTileM64, BN, 1);
+      constexpr uint32_t idesc = make_idesc(TM, BN, 1);
       for (int it = 0; it < iters; ++it) {
         const int gi = pp.git + it, s = gi % kStages;
         const uint32_t ph = (gi / kStages) & 1;
@@ -619,8 +629,9 @@ __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap
     mbar_wait(pp.tmem_full, pp.tiles & 1);
     tcgen05_fence_after();
     const int q = warp & 3;
-    const int m = q * 16 + lane;  // UMMA M = 64: rows 16q..16q+15 sit in lanes 32q..32q+15
-    const bool row_ok = lane < 16;
+    // UMMA M = 128: accumulator row i sits in lane i; M = 64: rows 16q..16q+15 sit in lanes 32q..32q+15
+    const int m = TM == 128 ? q * 32 + lane : q * 16 + lane;
+    const bool row_ok = TM == 128 || lane < 16;
     constexpr int kChunks = BN / 16, kHalf = (kChunks + 1) / 2;
     const int c_begin = (warp - 2) < 4 ? 0 : kHalf * 16, c_end = (warp - 2) < 4 ? kHalf * 16 : BN;
 #pragma unroll 1
@@ -635,6 +646,7 @@ __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap
   pp.tiles += 1;
 }
 
+template <int TM>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_constant__ CUtensorMap tm_attn,
                        const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wqkv,
@@ -642,6 +654,8 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
                        const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_heads,
                        const __grid_constant__ FusedStepArgs a) {
   using namespace fused;
+  using GE = Geo<TM>;
+  constexpr int kStages = GE::kStages, kStageBytes = GE::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   FusedPipe pp;
@@ -870,7 +884,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     // wqkv: 144 tiles of 32 output features, RoPE + KV append + bf16 q in the epilogue
     if (cta < 3 * D / 32) {
       ep.mode = EPI_QKV; ep.N = 3 * D; ep.out_bf16 = a.q; ep.out_f32 = nullptr; ep.ldo = D; ep.layer = l; ep.atomic = 0;
-      fused_gemm_tile<32>(pp, &tm_xn, &tm_wqkv, l, cta * 32, 0, D / kBlockK, ep);
+      fused_gemm_tile<32, TM>(pp, &tm_xn, &tm_wqkv, l, cta * 32, 0, D / kBlockK, ep);
     }
     sync_all();
     attention_phase(l);
@@ -881,7 +895,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       if (cta < tiles) {
         const int split = cta / nt, kb = D / kBlockK;
         ep.mode = EPI_RESID; ep.N = D; ep.out_f32 = a.h; ep.ldo = D; ep.atomic = 1;
-        fused_gemm_tile<64>(pp, &tm_attn, &tm_wo, l, (cta % nt) * 64, kb * split / a.wo_ksplit, kb * (split + 1) / a.wo_ksplit, ep);
+        fused_gemm_tile<64, TM>(pp, &tm_attn, &tm_wo, l, (cta % nt) * 64, kb * split / a.wo_ksplit, kb * (split + 1) / a.wo_ksplit, ep);
       }
     }
     sync_all();
@@ -890,7 +904,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     // w1|w3 (rows interleaved) + SiLU * mul: 128 tiles of 64 rows = 32 hidden units
     if (cta < 2 * F / 64) {
       ep.mode = EPI_SWIGLU; ep.N = 2 * F; ep.out_bf16 = a.act; ep.ldo = F; ep.atomic = 0;
-      fused_gemm_tile<64>(pp, &tm_xn, &tm_w13, l, cta * 64, 0, D / kBlockK, ep);
+      fused_gemm_tile<64, TM>(pp, &tm_xn, &tm_w13, l, cta * 64, 0, D / kBlockK, ep);
     }
     sync_all();
     // w2 + residual
@@ -899,7 +913,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       if (cta < tiles) {
         const int split = cta / nt, kb = F / kBlockK;
         ep.mode = EPI_RESID; ep.N = D; ep.out_f32 = a.h; ep.ldo = D; ep.atomic = 1;
-        fused_gemm_tile<64>(pp, &tm_act, &tm_w2, l, (cta % nt) * 64, kb * split / a.w2_ksplit, kb * (split + 1) / a.w2_ksplit, ep);
+        fused_gemm_tile<64, TM>(pp, &tm_act, &tm_w2, l, (cta % nt) * 64, kb * split / a.w2_ksplit, kb * (split + 1) / a.w2_ksplit, ep);
       }
     }
     sync_all();
@@ -909,7 +923,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   // heads: NH / 64 tiles (144 for 9 x 1024), plain fp32 store
   for (int t = cta; t < a.NH / 64; t += G) {
     ep.mode = EPI_STORE; ep.N = a.NH; ep.out_f32 = a.logits; ep.ldo = a.NH; ep.atomic = 0;
-    fused_gemm_tile<64>(pp, &tm_xn, &tm_heads, 0, t * 64, 0, D / kBlockK, ep);
+    fused_gemm_tile<64, TM>(pp, &tm_xn, &tm_heads, 0, t * 64, 0, D / kBlockK, ep);
     __syncthreads();  // the accumulator is single-buffered: drain it before the next tile's MMAs
   }
   if (a.fuse_io) {
@@ -1055,30 +1069,31 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cu
 
 // Fused decode step (decode_step_fused_bf16): tensor maps are rebuilt per call (they are baked into the captured graph node)
 bool fused_step_supported(int R, int D, int F, int NH) {
-  return R >= 1 && R <= 64 && D % 64 == 0 && F % 64 == 0 && NH % 64 == 0 && (3 * D) % 32 == 0 && D / 4 <= 2 * kGemmThreads;
+  return R >= 1 && R <= 128 && D % 64 == 0 && F % 64 == 0 && NH % 64 == 0 && (3 * D) % 32 == 0 && D / 4 <= 2 * kGemmThreads;
 }
 
-cudaError_t launch_decode_fused_bf16(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
-                                     const void* w_heads, cudaStream_t st) {
-  if (!fused_step_supported(a.R, a.D, a.F, a.NH)) return cudaErrorInvalidValue;
+template <int TM>
+static cudaError_t launch_decode_fused_t(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
+                                         const void* w_heads, cudaStream_t st) {
   static int sms = 0;
   if (!sms) {
-    cudaError_t e = cudaFuncSetAttribute(decode_step_fused_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(decode_step_fused_bf16<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::kSmem);
     if (e != cudaSuccess) return e;
     int dev = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_step_fused_bf16, kGemmThreads, fused::kSmem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_step_fused_bf16<TM>, kGemmThreads, fused::kSmem);
     if (e != cudaSuccess) return e;
     if (occ < 1) { sms = 0; return cudaErrorLaunchOutOfResources; }
   }
   const int need = a.D / 64 * (a.wo_ksplit > a.w2_ksplit ? a.wo_ksplit : a.w2_ksplit);
-  if (3 * a.D / 32 > sms || 2 * a.F / 64 > sms || need > sms) return cudaErrorInvalidValue;  // one tile per CTA per phase
+  // one tile per CTA per phase, one residual row per CTA in the norm phases
+  if (3 * a.D / 32 > sms || 2 * a.F / 64 > sms || need > sms || a.R > sms) return cudaErrorInvalidValue;
   const uint64_t D = a.D, F = a.F, L = a.L;
   CUtensorMap m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads;
-  bool ok = make_map(&m_xn, a.xn, D, a.R, 1, D, (uint64_t)a.R * D, 64, 64, false) &&
-            make_map(&m_attn, a.attn, D, a.R, 1, D, (uint64_t)a.R * D, 64, 64, false) &&
-            make_map(&m_act, a.act, F, a.R, 1, F, (uint64_t)a.R * F, 64, 64, false) &&
+  bool ok = make_map(&m_xn, a.xn, D, a.R, 1, D, (uint64_t)a.R * D, 64, TM, false) &&
+            make_map(&m_attn, a.attn, D, a.R, 1, D, (uint64_t)a.R * D, 64, TM, false) &&
+            make_map(&m_act, a.act, F, a.R, 1, F, (uint64_t)a.R * F, 64, TM, false) &&
             make_map(&m_wqkv, wqkv, D, 3 * D, L, D, 3 * D * D, 64, 32, false) &&
             make_map(&m_wo, wo, D, D, L, D, D * D, 64, 64, false) &&
             make_map(&m_w13, w13, D, 2 * F, L, D, 2 * F * D, 64, 64, false) &&
@@ -1095,7 +1110,14 @@ cudaError_t launch_decode_fused_bf16(const FusedStepArgs& a, const void* wqkv, c
   at[0].val.cooperative = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, decode_step_fused_bf16, m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads, a);
+  return cudaLaunchKernelEx(&cfg, decode_step_fused_bf16<TM>, m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads, a);
+}
+
+cudaError_t launch_decode_fused_bf16(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
+                                     const void* w_heads, cudaStream_t st) {
+  if (!fused_step_supported(a.R, a.D, a.F, a.NH)) return cudaErrorInvalidValue;
+  return a.R <= 64 ? launch_decode_fused_t<64>(a, wqkv, wo, w13, w2, w_heads, st)
+                   : launch_decode_fused_t<128>(a, wqkv, wo, w13, w2, w_heads, st);
 }
 
 // Linear layer of the bf16 sampler path: out = A[R][K] (bf16) x W[N][K]^T (bf16) with a fused epilogue.
