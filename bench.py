@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the V-AURA generation hot path (BASELINE.json metric: generated audio-sec/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload b64|b1|b1_long] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload b64|b64_cfg|b1|b1_cfg] [--impl reference]
 
 One "step" = one pass of the hot path over one batch of synthetic clips: VAURAModel.generate(...)
 (228 device-side decode steps + sampling + codec decode) on `batch` clips of 2.56 s.  Under torchrun
