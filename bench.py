@@ -315,6 +315,20 @@ def main():
     tokens_only()
     ms_tok = timed(tokens_only, 2) / 2
     line["decode_step"]["mean_us"] = ms_tok * 1e3 / (T + 8)
+    # p50 of the step-to-step latency: the step kernels (decode_step_cluster, decode_step_fused_bf16) stamp %globaltimer at
+    # the start of the launch that samples column `offset` into the workspace (csrc/cabi.cu: ws.timing + 1024)
+    try:
+        import numpy as np
+        ws_buf = model.sampler._buffers["ws"]
+        S = T + 9
+        st_ns = ws_buf[256 + 8 * 1024:256 + 8 * (1024 + S)].cpu().numpy().view(np.uint64).astype(np.int64)
+        d_ns = np.diff(st_ns[2:S])
+        d_ns = d_ns[(d_ns > 0) & (d_ns < 10**8)]
+        if d_ns.size >= 100:
+            line["decode_step"]["p50_us"] = float(np.median(d_ns)) / 1e3
+            line["decode_step"]["p99_us"] = float(np.percentile(d_ns, 99)) / 1e3
+    except Exception:  # paths without a persistent step kernel leave no stamps
+        pass
     line["decode_step"]["hbm_frac_of_measured"] = (sampler_step_bytes(d) / (ms_tok * 1e-3 / (T + 8)) / 1e9) / peak
     line["codec"] = {"ms_per_batch": ms / args.steps - ms_tok, "gflop_per_clip": codec_flops(FULL_CODEC, T) / 1e9}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

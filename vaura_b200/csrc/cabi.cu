@@ -254,6 +254,7 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
       fa.wo_ksplit = 6; fa.w2_ksplit = 6;
       fa.eps = d.norm_eps; fa.scale = 1.0f / sqrtf((float)kHeadDim);
       { const char* tm = getenv("VAURA_PERSIST_TIMING"); fa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
+      fa.step_times = ws.timing + 1024;
       { const char* tc = getenv("VAURA_TIMING_CTA"); fa.timing_cta = tc ? atoi(tc) : 0; }
       fa.fuse_io = io ? 1 : 0;
       if (io) {
@@ -415,6 +416,7 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     pa.batch = p->batch; pa.cond_dim = d.cond_dim; pa.cond_tokens = d.cond_tokens; pa.atpvf = d.audio_tokens_per_video_frame;
     pa.eps = d.norm_eps; pa.scale = 1.0f / sqrtf((float)kHeadDim);
     { const char* tm = getenv("VAURA_PERSIST_TIMING"); pa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
+    pa.step_times = ws.timing + 1024;  // workspace bytes [256 + 8192, ...): one timestamp per generated column
     { const char* tc = getenv("VAURA_TIMING_CTA"); pa.timing_cta = tc ? atoi(tc) : 0; }
     int sms = 0, dev = 0;
     CU(cudaGetDevice(&dev));

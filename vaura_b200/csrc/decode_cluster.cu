@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
     const int offset = a.state->offset;
     const unsigned epoch = a.state->epoch;
     const int p = offset - 1;  // position fed by this step
+    if (cta == 0 && tid == 0 && a.step_times) a.step_times[offset] = now_ns();  // step-to-step latency (bench.py: p50)
     const unsigned nbar = (unsigned)(2 * L + 1);
     unsigned bar_i = 0;
     uint32_t xc = 0;           // cluster exchanges done so far: exchange xc uses xbar[xc & 1], parity (xc >> 1) & 1

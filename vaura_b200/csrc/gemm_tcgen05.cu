@@ -674,6 +674,11 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   const unsigned epoch = a.state->epoch;
   const int offset = a.state->offset;
   const int p = offset - 1;  // position fed by this step
+  if (cta == 0 && tid == 0 && a.step_times) {  // step-to-step latency (bench.py: p50)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.step_times[offset] = t;
+  }
   const unsigned nbar = (unsigned)(7 * a.L + 1 + (a.fuse_io ? 1 : 0));
   unsigned bi = 0;
   int stamp_i = 0;

@@ -116,6 +116,7 @@ struct FusedStepArgs {
   int wo_ksplit, w2_ksplit;
   float eps, scale;
   unsigned long long* timing;  // optional: timestamps (ns) of CTA `timing_cta` before / after every device-wide barrier
+  unsigned long long* step_times;  // [kMaxCtx + 16]: %globaltimer at the start of the launch that samples column `offset`
   int timing_cta;
   // fuse_io: the kernel also builds the embedding rows (first phase) and samples / writes back the tokens (last phase)
   int fuse_io;
@@ -147,6 +148,7 @@ struct PersistArgs {
   KvView kv;
   StepState* state;
   unsigned long long* timing;  // optional: phase timestamps (ns) of CTA `timing_cta`
+  unsigned long long* step_times;  // [kMaxCtx + 16]: %globaltimer at the start of the launch that samples column `offset`
   int timing_cta;
   int pace_cycles;  // cluster variant: units of L2 prefetch ahead of the shared-memory fill (< 0: default)
   SampleArgs sample;
