@@ -12,7 +12,7 @@ torch.manual_seed(0)
 for rows in (1, 64):
     logits = torch.randn(rows, 9, 1024, device="cuda") * 2.0
     for name, kw in (("argmax", dict(use_sampling=False)), ("no filter", dict(use_sampling=True, top_k=0)),
-                     ("top-k 128", dict(use_sampling=True, top_k=128)), ("top-p 0.9", dict(use_sampling=True, top_p=0.9))):
+                     ("top-k 256", dict(use_sampling=True, top_k=256)), ("top-p 0.9", dict(use_sampling=True, top_p=0.9))):
         for _ in range(5):
             sample_logits(logits, **kw)
         torch.cuda.synchronize()

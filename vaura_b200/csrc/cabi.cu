@@ -384,9 +384,12 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   // the first position (a decode step with an empty KV cache), so the whole clip is one kernel per column.
   const char* nocl = getenv("VAURA_NO_CLUSTER");
   const char* ptc = getenv("VAURA_PERSIST_TC");
+  const char* ptm = getenv("VAURA_PERSIST_TIMING");
+  const bool phase_timing = ptm && ptm[0] == '1';
   const bool use_cluster = persist && s->w.wstream && !(nocl && nocl[0] == '1') && !(ptc && ptc[0] == '1') &&
                            cluster_supported(rows, d.num_layers, d.d_model, d.ffn_dim, d.nhead, K * d.vocab, kv->page_size,
-                                             d.cond_dim, S);
+                                             d.cond_dim, S) &&
+                           cluster_launchable(rows, phase_timing);
   const bool cluster_first = use_cluster && npre == 1;
   int nsteps = p->end_offset - (p->start_offset + 1);
   if (!cluster_first) {

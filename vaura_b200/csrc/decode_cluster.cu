@@ -919,27 +919,41 @@ bool cluster_supported(int rows, int L, int D, int F, int H, int head_rows, int 
 
 size_t cluster_xfix_bytes(int rows, int L) { return (size_t)(2 * L + 1) * rows * DM * sizeof(long long); }
 
+// One-time set-up of an instantiation: opt into the large dynamic shared memory window and check that all 32 clusters
+// of 4 CTAs can be co-resident (the kernel's device-wide barriers need that). Returns 0 when the device cannot hold
+// them (fewer SMs visible than 128, MIG slice, MPS partition), else 1 (cooperative + cluster) or 2 (cluster only).
+template <int NB, bool TM>
+static int cluster_mode(cudaError_t* err) {
+  static int mode = -1;  // -1 = not probed yet
+  if (mode >= 0) { *err = mode ? cudaSuccess : cudaErrorCooperativeLaunchTooLarge; return mode; }
+  constexpr int smem = Lay<NB>::total;
+  cudaError_t e = cudaFuncSetAttribute(decode_step_cluster<NB, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { *err = e; (void)cudaGetLastError(); return mode = 0; }
+  cudaLaunchConfig_t qc{};
+  qc.gridDim = dim3(CL * NCL); qc.blockDim = dim3(kThreadsC); qc.dynamicSmemBytes = smem;
+  cudaLaunchAttribute qa[1];
+  qa[0].id = cudaLaunchAttributeClusterDimension;
+  qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+  qc.attrs = qa; qc.numAttrs = 1;
+  int nclusters = 0;
+  e = cudaOccupancyMaxActiveClusters(&nclusters, decode_step_cluster<NB, TM>, &qc);
+  if (e != cudaSuccess) { *err = e; (void)cudaGetLastError(); return mode = 0; }
+  if (nclusters < NCL) { *err = cudaErrorCooperativeLaunchTooLarge; return mode = 0; }
+  // VAURA_CLUSTER_NOCOOP=1: skip the cooperative attribute (Nsight Compute's kernel replay rejects cooperative
+  // cluster launches); co-residency is already established by the occupancy query above
+  const char* nc = getenv("VAURA_CLUSTER_NOCOOP");
+  *err = cudaSuccess;
+  return mode = (nc && nc[0] == '1') ? 2 : 1;
+}
+
 template <int NB, bool TM>
 static cudaError_t launch_cluster_t(const PersistArgs& a, cudaStream_t st) {
-  static int mode = 0;  // 0 = not initialised, 1 = cooperative + cluster, 2 = cluster only
   constexpr int smem = Lay<NB>::total;
+  static int mode = 0;
   if (!mode) {
-    cudaError_t e = cudaFuncSetAttribute(decode_step_cluster<NB, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t qc{};
-    qc.gridDim = dim3(CL * NCL); qc.blockDim = dim3(kThreadsC); qc.dynamicSmemBytes = smem;
-    cudaLaunchAttribute qa[1];
-    qa[0].id = cudaLaunchAttributeClusterDimension;
-    qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-    qc.attrs = qa; qc.numAttrs = 1;
-    int nclusters = 0;
-    e = cudaOccupancyMaxActiveClusters(&nclusters, decode_step_cluster<NB, TM>, &qc);
-    if (e != cudaSuccess) return e;
-    if (nclusters < NCL) return cudaErrorCooperativeLaunchTooLarge;  // all clusters must be co-resident (device-wide barriers)
-    // VAURA_CLUSTER_NOCOOP=1: skip the cooperative attribute (Nsight Compute's kernel replay rejects cooperative
-    // cluster launches); co-residency is already established by the occupancy query above
-    const char* nc = getenv("VAURA_CLUSTER_NOCOOP");
-    mode = (nc && nc[0] == '1') ? 2 : 1;
+    cudaError_t e;
+    mode = cluster_mode<NB, TM>(&e);
+    if (!mode) return e;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(CL * NCL); cfg.blockDim = dim3(kThreadsC); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -960,6 +974,15 @@ static cudaError_t launch_cluster_t(const PersistArgs& a, cudaStream_t st) {
     e = cudaLaunchKernelEx(&cfg, decode_step_cluster<NB, TM>, a);
   }
   return e;
+}
+
+bool cluster_launchable(int rows, bool timing) {
+  cudaError_t e;
+  switch (rows) {
+    case 1: return (timing ? cluster_mode<1, true>(&e) : cluster_mode<1, false>(&e)) != 0;
+    case 2: return (timing ? cluster_mode<2, true>(&e) : cluster_mode<2, false>(&e)) != 0;
+  }
+  return false;
 }
 
 cudaError_t launch_decode_cluster(const PersistArgs& a, int rows, cudaStream_t st) {

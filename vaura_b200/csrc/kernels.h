@@ -167,6 +167,9 @@ cudaError_t launch_decode_persistent_tc(PersistArgs& a, int rows, cudaStream_t s
 bool cluster_supported(int rows, int L, int D, int F, int H, int head_rows, int page_size, int cond_dim, int max_ctx);
 size_t cluster_stream_bytes(int L);
 size_t cluster_xfix_bytes(int rows, int L);
+// false when this device cannot keep all 32 clusters of 4 co-resident (fewer than 128 SMs visible): the caller then
+// uses decode_step_persistent instead
+bool cluster_launchable(int rows, bool timing);
 cudaError_t launch_decode_cluster(const PersistArgs& a, int rows, cudaStream_t st);
 
 cudaError_t launch_embed(const EmbedArgs& a, int rows, cudaStream_t st);
