@@ -435,6 +435,7 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
       pa.xfix = ws.xfix;
       { const char* rl = getenv("VAURA_CLUSTER_RING"); pa.prefetch_ahead = rl ? atoi(rl) : 0; }
       { const char* pc = getenv("VAURA_CLUSTER_L2_AHEAD"); pa.pace_cycles = pc ? atoi(pc) : -1; }
+      { const char* tu = getenv("VAURA_CLUSTER_TAIL_UNITS"); pa.tail_units = tu ? atoi(tu) : 0; }
       CU(cudaMemsetAsync(ws.xfix, 0, cluster_xfix_bytes(rows, d.num_layers), st));
     }
     for (int i = 0; i < nsteps; ++i) {

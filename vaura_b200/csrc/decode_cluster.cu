@@ -379,6 +379,15 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
         }
         issued += n;
       }
+      // HBM idles from here to the end of the step (device barrier, sampling, launch gap): pull the head of the next
+      // step's streams into L2 meanwhile
+      for (int q = 0; q < a.tail_units && q < nq_layers; ++q) {
+        int i, n;
+        const uint8_t* src;
+        bool is_shared;
+        unit(q, i, n, src, is_shared);
+        bulk_prefetch_l2(src, (uint32_t)n * SLOT);
+      }
     }
   } else {
     // ------------------------------------------- compute warps -------------------------------------------

@@ -151,6 +151,7 @@ struct PersistArgs {
   unsigned long long* step_times;  // [kMaxCtx + 16]: %globaltimer at the start of the launch that samples column `offset`
   int timing_cta;
   int pace_cycles;  // cluster variant: units of L2 prefetch ahead of the shared-memory fill (< 0: default)
+  int tail_units;   // cluster variant: units of the NEXT step's stream head prefetched into L2 during the sampling tail
   SampleArgs sample;
   int L, D, F, H, Kc, V, S, batch, cond_dim, cond_tokens, atpvf, slot_cap, prefetch_ahead;
   float eps, scale;
