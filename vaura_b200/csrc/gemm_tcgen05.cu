@@ -53,6 +53,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (t - t0 > 2000000000ull) __trap();  // 2 s
   }
 }
+// plain (1-D) bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
@@ -545,7 +556,12 @@ struct Geo {
   static constexpr int kRing = kStages * kStageBytes;
 };
 constexpr int kAttnScratch = 10 * (kHeadDim + kMaxCtx) * 4;                  // per-warp q + scores
-constexpr int kSmem = 3 * 65536 + 256 + kAttnScratch + 1024;
+// attention staging: every warp owns kAttnSlots slots of one 16-position run of K or V rows (16 x 192 B) inside the idle
+// GEMM ring, each with its own mbarrier
+constexpr int kAttnSlots = 6, kRunBytes = 16 * kHeadDim * 2;
+constexpr int kAttnBars = 10 * kAttnSlots * 8;
+constexpr int kSmem = 3 * 65536 + 256 + kAttnScratch + 512 + 1024;
+static_assert(10 * kAttnSlots * kRunBytes <= 3 * 65536 && kAttnBars <= 512, "attention staging fits the GEMM ring");
 static_assert(Geo<64>::kRing == 3 * 65536 && Geo<128>::kRing == 3 * 65536, "ring size");
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -665,6 +681,8 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   pp.tmem_full = pp.empty + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pp.tmem_full + 1);
   float* scratch = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
+  uint64_t* attn_bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + 256 + kAttnScratch);
+  unsigned acopies = 0;  // K/V runs this warp has staged so far in the launch (slot = n % kAttnSlots, phase = n / kAttnSlots)
   pp.git = 0;
   pp.tiles = 0;
 
@@ -700,6 +718,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       mbar_init(&pp.empty[s], 1);
     }
     mbar_init(pp.tmem_full, 1);
+    for (int i = 0; i < 10 * kAttnSlots; ++i) mbar_init(&attn_bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -767,31 +786,66 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     }
   };
 
-  // ---- attention (llama.py:246-255): one warp per (row, head) over the paged bf16 cache, fp32 softmax.  Positions are
-  //      walked 32 at a time as two 16-position runs, each inside one page (page size 16 or 32): two page look-ups
-  //      (shuffles) and two base addresses per iteration, every load a constant offset from them; the 12 key loads /
-  //      16 value loads of an iteration are issued before their arithmetic (6 KB per warp in flight) ----
+  // ---- attention (llama.py:246-255): one warp per (row, head) over the paged bf16 cache, fp32 softmax.  A 16-position
+  //      run of K or V rows of one head is contiguous inside its page (3 KB): the warp stages the runs of its items -
+  //      all K runs, then all V runs, then the next item - with one bulk copy each into a private ring of kAttnSlots
+  //      slots in the idle GEMM ring, so up to 18 KB per warp are in flight independent of registers and the V rows
+  //      (and the next item's K rows) stream in while the scores are computed.  Positions are consumed 32 at a time.
   auto attention_phase = [&](int layer) {
     float* qs = scratch + warp * (kHeadDim + kMaxCtx);
     float* sc = qs + kHeadDim;
     const __nv_bfloat16* kvp = reinterpret_cast<const __nv_bfloat16*>(a.kv.pages);
     const int nctx = p + 1, psz = a.kv.page_size;
     const size_t page_stride = (size_t)a.kv.nhead * psz * kHeadDim;
-    for (int item = warp * G + cta; item < R * a.H; item += G * (kGemmThreads / 32)) {  // CTA-fastest: every SM gets ~7 items
+    const int item_stride = G * (kGemmThreads / 32), item0 = warp * G + cta;  // CTA-fastest: every SM gets ~7 items
+    const int nitems = item0 < R * a.H ? (R * a.H - item0 + item_stride - 1) / item_stride : 0;  // <= 2 (R <= 128)
+    const int nr = (nctx + 15) >> 4, total = nitems * 2 * nr;
+    // the page tables of the warp's items: lane i holds page i (<= 16 pages for 256 positions of 16)
+    int pg[2] = {0, 0};
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (i < nitems && lane < a.kv.max_pages_per_seq)
+        pg[i] = a.kv.page_table[((item0 + i * item_stride) / a.H) * a.kv.max_pages_per_seq + lane];
+    uint8_t* stage = smem + warp * (kAttnSlots * kRunBytes);
+    uint64_t* abar = attn_bars + warp * kAttnSlots;
+    const unsigned abase = acopies;
+    int issued = 0, consumed = 0;
+    // stage copy number `issued` of the phase: item issued / 2nr, K runs 0..nr-1 then V runs 0..nr-1
+    auto issue_one = [&]() {
+      const int it = issued / (2 * nr), rem = issued - it * 2 * nr, kvsel = rem >= nr ? 1 : 0, j = (rem - kvsel * nr) * 16;
+      const int hd = (item0 + it * item_stride) % a.H;
+      const int page = __shfl_sync(0xffffffffu, it ? pg[1] : pg[0], j / psz);
+      const __nv_bfloat16* src =
+          kvp + ((size_t)(layer * 2 + kvsel) * a.kv.num_pages + page) * page_stride + ((size_t)hd * psz + j % psz) * kHeadDim;
+      const int slot = (int)(acopies % kAttnSlots);
+      if (lane == 0) {
+        mbar_expect_tx(&abar[slot], kRunBytes);
+        bulk_load_1d(stage + slot * kRunBytes, src, kRunBytes, &abar[slot]);
+      }
+      ++acopies;
+      ++issued;
+    };
+    auto refill = [&]() {
+      __syncwarp();  // every lane is done reading the slots counted in `consumed`
+      while (issued < total && issued - consumed < kAttnSlots) issue_one();
+    };
+    // wait for copy c of the phase and return its slot
+    auto staged = [&](int c) -> const uint8_t* {
+      const unsigned n = abase + (unsigned)c;
+      mbar_wait(&abar[n % kAttnSlots], (n / kAttnSlots) & 1u);
+      return stage + (n % kAttnSlots) * kRunBytes;
+    };
+    refill();
+    for (int it = 0; it < nitems; ++it) {
+      const int item = item0 + it * item_stride;
       const int row = item / a.H, hd = item % a.H;
-      // the sequence row's pages (<= 16 for 256 positions of 16); lane i holds page i
-      const int mypage = lane < a.kv.max_pages_per_seq ? a.kv.page_table[row * a.kv.max_pages_per_seq + lane] : 0;
-      // first row of the 16-position run that starts at position j (j % 16 == 0), K (kvsel 0) or V (1)
-      auto run_ptr = [&](int kvsel, int j) {
-        const int page = __shfl_sync(0xffffffffu, mypage, j / psz);
-        return kvp + ((size_t)(layer * 2 + kvsel) * a.kv.num_pages + page) * page_stride + ((size_t)hd * psz + j % psz) * kHeadDim;
-      };
+      const int cK = it * 2 * nr, cV = cK + nr;
       __syncwarp();
       for (int d = lane; d < kHeadDim; d += 32)
         qs[d] = __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(a.q) + (size_t)row * D + hd * kHeadDim + d)));
       __syncwarp();
-      // scores: 4 lanes per key position; lane t takes the 16-byte chunks t, t+4, t+8 of the 192-byte row (one load
-      // instruction reads 64 contiguous bytes per row); 4 x 8 positions per iteration
+      // scores: 4 lanes per key position; lane t takes the 16-byte chunks t, t+4, t+8 of the 192-byte row (conflict-free:
+      // a quarter warp reads two rows x four chunks); 4 x 8 positions per iteration
       const int g = lane >> 2, t = lane & 3;
       float q24[24];
 #pragma unroll
@@ -799,22 +853,17 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       float mx = -INFINITY;
       for (int j0 = 0; j0 < nctx; j0 += 32) {
         const bool two = j0 + 16 < nctx;
-        const uint4* runA = reinterpret_cast<const uint4*>(run_ptr(0, j0));
-        const uint4* runB = reinterpret_cast<const uint4*>(run_ptr(0, two ? j0 + 16 : j0));
-        uint4 kk[4][3];
+        const uint8_t* runA = staged(cK + (j0 >> 4));
+        const uint8_t* runB = two ? staged(cK + (j0 >> 4) + 1) : runA;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const uint4* kr = ((u < 2 || !two) ? runA : runB) + ((8 * (u & 1) + g) * 12 + t);  // row (8u + g) % 16 of the run
-#pragma unroll
-          for (int c = 0; c < 3; ++c) kk[u][c] = __ldcg(kr + 4 * c);  // rows past nctx stay inside the page: read, not used
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
+          const uint8_t* kr = ((u < 2 || !two) ? runA : runB) + ((8 * (u & 1) + g) * 12 + t) * 16;  // row (8u + g) % 16 of the run
           const int jj = j0 + 8 * u + g;
           float sdot = 0.f;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const uint32_t w[4] = {kk[u][c].x, kk[u][c].y, kk[u][c].z, kk[u][c].w};
+            const uint4 kk = lds_u4(kr + 64 * c);  // rows past nctx hold whatever the page holds: read, not used
+            const uint32_t w[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               sdot = fmaf(q24[c * 8 + 2 * e], bf16_lo(w[e]), sdot);
@@ -829,6 +878,8 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
             mx = fmaxf(mx, sdot);
           }
         }
+        consumed += two ? 2 : 1;
+        refill();
       }
       mx = warp_max(mx);
       __syncwarp();
@@ -840,30 +891,30 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       }
       sum = warp_sum(sum);
       __syncwarp();
-      // P.V: lanes 0-11 take the even positions, lanes 12-23 the odd ones, 8 dims (one 16-byte load) each
+      // P.V: lanes 0-11 take the even positions, lanes 12-23 the odd ones, 8 dims (one 16-byte chunk) each
       float o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = 0.f;
       const int half = lane >= 12 ? 1 : 0, dl = lane < 24 ? lane - 12 * half : 0;
       for (int j0 = 0; j0 < nctx; j0 += 32) {
         const bool two = j0 + 16 < nctx;
-        const uint4* runA = reinterpret_cast<const uint4*>(run_ptr(1, j0)) + half * 12 + dl;
-        const uint4* runB = reinterpret_cast<const uint4*>(run_ptr(1, two ? j0 + 16 : j0)) + half * 12 + dl;
-        uint4 vv[16];
+        const uint8_t* runA = staged(cV + (j0 >> 4)) + (half * 12 + dl) * 16;
+        const uint8_t* runB = two ? staged(cV + (j0 >> 4) + 1) + (half * 12 + dl) * 16 : runA;
 #pragma unroll
-        for (int u = 0; u < 16; ++u)  // row 2 (u % 8) + half of the run; rows past the context may hold anything (NaN bit patterns)
-          vv[u] = j0 + 2 * u + half < nctx ? __ldcg((u < 8 ? runA : runB) + (u & 7) * 24) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < 16; ++u) {  // row 2 (u % 8) + half of the run; rows past the context may hold anything (NaN bit patterns)
           const int jj = j0 + 2 * u + half;
-          const float pj = (u < 8 || two) ? sc[jj] : 0.f;
-          const uint32_t w[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+          const bool live = jj < nctx && (u < 8 || two);
+          const uint4 vv = live ? lds_u4((u < 8 ? runA : runB) + (u & 7) * 24 * 16) : make_uint4(0u, 0u, 0u, 0u);
+          const float pj = live ? sc[jj] : 0.f;
+          const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             o[2 * e] = fmaf(pj, bf16_lo(w[e]), o[2 * e]);
             o[2 * e + 1] = fmaf(pj, bf16_hi(w[e]), o[2 * e + 1]);
           }
         }
+        consumed += two ? 2 : 1;
+        refill();
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += __shfl_down_sync(0xffffffffu, o[i], 12);
