@@ -21,20 +21,19 @@ torch.cuda.synchronize()
 ws = m.sampler._buffers["ws"]
 t = ws[256:256 + 16384].cpu().numpy().view(np.uint64).astype(np.int64)
 L = FULL_SAMPLER.num_layers
-# stamps: 2 per barrier (before, after); 7 barriers per layer
-names = ["rms1", "qkv", "attn", "wo", "rms2", "w13", "w2"]
-work = np.zeros(7)
-bar = np.zeros(7)
-prev = None
-idx = 0
-t0 = t[0]
+# stamps: 2 per barrier (before, after); one barrier after the first norm, then 5 per layer.  "work" is thread 0's
+# (the TMA producer's) time from the previous barrier to its arrival; the rest of the CTA's phase shows up as wait.
+names = ["qkv", "attn", "wo+rms", "w13", "w2+rms"]
+work = np.zeros(5)
+bar = np.zeros(5)
+idx = 2  # skip the barrier after the first norm
+t0 = t[1]
 for l in range(L):
-    for i in range(7):
+    for i in range(5):
         before, after = t[idx], t[idx + 1]
-        start = t[idx - 1] if idx > 0 else before
-        work[i] += before - start
+        work[i] += before - t[idx - 1]
         bar[i] += after - before
         idx += 2
-print(f"layers total {(t[idx - 1] - t0) / 1e3:.1f} us at position {T + 7}; first stamp = first barrier arrival")
+print(f"layers total {(t[idx - 1] - t0) / 1e3:.1f} us at position {T + 7}")
 for n, w, b in zip(names, work, bar):
-    print(f"  {n:5s} work {w / L / 1e3:6.2f} us   barrier wait {b / L / 1e3:6.2f} us   (per layer, CTA 0)")
+    print(f"  {n:7s} work {w / L / 1e3:6.2f} us   barrier wait {b / L / 1e3:6.2f} us   phase {(w + b) / L / 1e3:6.2f} us (per layer, CTA {os.environ.get('VAURA_TIMING_CTA', '0')})")

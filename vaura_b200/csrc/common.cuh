@@ -17,7 +17,9 @@ struct StepState {
   int done;      // arrival counter of the sampling kernel's CTAs
   unsigned epoch;    // persistent kernel: launches since the state was (re)initialised
   unsigned barrier;  // persistent kernel: monotonically increasing device-wide barrier counter
-  int pad[60];
+  int pad0[28];
+  unsigned tiles_done;  // fused step kernel: split-K tiles finished (own 128-byte line; see decode_step_fused_bf16)
+  int pad1[31];
 };
 
 __device__ __forceinline__ float warp_sum(float v) {

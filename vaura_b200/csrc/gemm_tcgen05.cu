@@ -697,7 +697,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     a.step_times[offset] = t;
   }
-  const unsigned nbar = (unsigned)(7 * a.L + 1 + (a.fuse_io ? 1 : 0));
+  const unsigned nbar = (unsigned)(5 * a.L + 1 + (a.fuse_io ? 1 : 0));
   unsigned bi = 0;
   int stamp_i = 0;
   auto stamp = [&]() {  // optional phase timestamps of CTA 0 (profiles/fused_timing.py)
@@ -934,9 +934,29 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   ep.R = R; ep.rope = a.rope; ep.kv = a.kv; ep.state = a.state; ep.pos0 = 0; ep.npos = 1; ep.d_model = D;
   ep.perm_S = 0; ep.perm_V = 0;
 
+  // The RMSNorm after a split-K GEMM (wo, w2) needs every tile's reductions, the GEMM after it needs every row's norm:
+  // instead of two device-wide barriers the tile CTAs count themselves on state->tiles_done (release) and only the R
+  // CTAs that normalise a row wait for the count (acquire); the one barrier that follows covers both.
+  const unsigned tiles_wo = (unsigned)(D / 64 * a.wo_ksplit), tiles_w2 = (unsigned)(D / 64 * a.w2_ksplit);
+  const unsigned tiles_base = epoch * (unsigned)a.L * (tiles_wo + tiles_w2);
+  unsigned tiles_seen = 0;
+  auto tiles_arrive = [&]() {
+    __syncthreads();
+    if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&a.state->tiles_done) : "memory");
+  };
+  auto tiles_wait = [&]() {
+    if (tid == 0) {
+      const unsigned target = tiles_base + tiles_seen;
+      const long long t0 = clock64();
+      while ((int)(ld_acquire_u32(&a.state->tiles_done) - target) < 0)
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+    __syncthreads();
+  };
+
+  rmsnorm_phase(a.attn_norm, a.fuse_io);
+  sync_all();
   for (int l = 0; l < a.L; ++l) {
-    rmsnorm_phase(a.attn_norm + (size_t)l * D, l == 0 && a.fuse_io);
-    sync_all();
     // wqkv: 144 tiles of 32 output features, RoPE + KV append + bf16 q in the epilogue
     if (cta < 3 * D / 32) {
       ep.mode = EPI_QKV; ep.N = 3 * D; ep.out_bf16 = a.q; ep.out_f32 = nullptr; ep.ldo = D; ep.layer = l; ep.atomic = 0;
@@ -945,17 +965,21 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     sync_all();
     attention_phase(l);
     sync_all();
-    // wo + residual: 24 N tiles x wo_ksplit K slices, fp32 vector reductions into h
+    // wo + residual: 24 N tiles x wo_ksplit K slices, fp32 vector reductions into h; then the FFN norm of the rows
     {
-      const int nt = D / 64, tiles = nt * a.wo_ksplit;
-      if (cta < tiles) {
+      const int nt = D / 64;
+      if (cta < (int)tiles_wo) {
         const int split = cta / nt, kb = D / kBlockK;
         ep.mode = EPI_RESID; ep.N = D; ep.out_f32 = a.h; ep.ldo = D; ep.atomic = 1;
         fused_gemm_tile<64, TM>(pp, &tm_attn, &tm_wo, l, (cta % nt) * 64, kb * split / a.wo_ksplit, kb * (split + 1) / a.wo_ksplit, ep);
+        tiles_arrive();
+      }
+      tiles_seen += tiles_wo;
+      if (cta < R) {
+        tiles_wait();
+        rmsnorm_phase(a.ffn_norm + (size_t)l * D, false);
       }
     }
-    sync_all();
-    rmsnorm_phase(a.ffn_norm + (size_t)l * D, false);
     sync_all();
     // w1|w3 (rows interleaved) + SiLU * mul: 128 tiles of 64 rows = 32 hidden units
     if (cta < 2 * F / 64) {
@@ -963,19 +987,23 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       fused_gemm_tile<64, TM>(pp, &tm_xn, &tm_w13, l, cta * 64, 0, D / kBlockK, ep);
     }
     sync_all();
-    // w2 + residual
+    // w2 + residual; then the next layer's attention norm (the final norm after the last layer)
     {
-      const int nt = D / 64, tiles = nt * a.w2_ksplit;
-      if (cta < tiles) {
+      const int nt = D / 64;
+      if (cta < (int)tiles_w2) {
         const int split = cta / nt, kb = F / kBlockK;
         ep.mode = EPI_RESID; ep.N = D; ep.out_f32 = a.h; ep.ldo = D; ep.atomic = 1;
         fused_gemm_tile<64, TM>(pp, &tm_act, &tm_w2, l, (cta % nt) * 64, kb * split / a.w2_ksplit, kb * (split + 1) / a.w2_ksplit, ep);
+        tiles_arrive();
+      }
+      tiles_seen += tiles_w2;
+      if (cta < R) {
+        tiles_wait();
+        rmsnorm_phase(l + 1 < a.L ? a.attn_norm + (size_t)(l + 1) * D : a.final_norm, false);
       }
     }
     sync_all();
   }
-  rmsnorm_phase(a.final_norm, false);
-  sync_all();
   // heads: NH / 64 tiles (144 for 9 x 1024), plain fp32 store
   for (int t = cta; t < a.NH / 64; t += G) {
     ep.mode = EPI_STORE; ep.N = a.NH; ep.out_f32 = a.logits; ep.ldo = a.NH; ep.atomic = 0;
@@ -1145,6 +1173,8 @@ static cudaError_t launch_decode_fused_t(const FusedStepArgs& a, const void* wqk
   const int need = a.D / 64 * (a.wo_ksplit > a.w2_ksplit ? a.wo_ksplit : a.w2_ksplit);
   // one tile per CTA per phase, one residual row per CTA in the norm phases
   if (3 * a.D / 32 > sms || 2 * a.F / 64 > sms || need > sms || a.R > sms) return cudaErrorInvalidValue;
+  // attention phase: at most two (row, head) items per warp, lane i holds page i, 16-position runs inside a page
+  if (a.R * a.H > 2 * sms * (kGemmThreads / 32) || a.kv.max_pages_per_seq > 32 || a.kv.page_size % 16) return cudaErrorInvalidValue;
   const uint64_t D = a.D, F = a.F, L = a.L;
   CUtensorMap m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads;
   bool ok = make_map(&m_xn, a.xn, D, a.R, 1, D, (uint64_t)a.R * D, 64, TM, false) &&

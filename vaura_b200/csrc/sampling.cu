@@ -46,6 +46,7 @@ __global__ void set_state_kernel(StepState* s, int offset) {
   s->done = 0;
   s->epoch = 0;
   s->barrier = 0;
+  s->tiles_done = 0;
 }
 
 cudaError_t launch_set_state(StepState* s, int offset, cudaStream_t st) {
