@@ -37,3 +37,7 @@ for l in range(L):
 print(f"layers total {(t[idx - 1] - t0) / 1e3:.1f} us at position {T + 7}")
 for n, w, b in zip(names, work, bar):
     print(f"  {n:7s} work {w / L / 1e3:6.2f} us   barrier wait {b / L / 1e3:6.2f} us   phase {(w + b) / L / 1e3:6.2f} us (per layer, CTA {os.environ.get('VAURA_TIMING_CTA', '0')})")
+a = t[900:908]
+if a[0] and a[7] > a[0]:
+    lab = ["page table + first copies issued", "q loaded", "first K run landed", "scores done", "softmax done", "first V run landed", "P.V done"]
+    print("attention sub-phases of warp 0, last layer (us): " + ", ".join(f"{n} {(a[i + 1] - a[i]) / 1e3:.2f}" for i, n in enumerate(lab)))

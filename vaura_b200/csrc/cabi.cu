@@ -341,7 +341,12 @@ static int run_pass(int precision, const vaura_sampler* s, const Workspace& ws, 
 
 static int check_kv(const vaura_sampler* s, const vaura_kv_cache* kv, int want_dtype) {
   if (!kv || !kv->pages || !kv->page_table) return fail(VAURA_ERR_INVALID, "kv cache missing");
-  if (kv->page_size != 16 && kv->page_size != 32) return fail(VAURA_ERR_INVALID, "page_size must be 16 or 32");
+  {
+    const char* ap = getenv("VAURA_ANY_PAGE");  // experiment: any power-of-two page >= 16 on the bf16 path
+    const bool pow2 = kv->page_size >= 16 && !(kv->page_size & (kv->page_size - 1));
+    if (kv->page_size != 16 && kv->page_size != 32 && !(ap && ap[0] == '1' && pow2))
+      return fail(VAURA_ERR_INVALID, "page_size must be 16 or 32");
+  }
   if (kv->max_pages_per_seq * kv->page_size < s->d.block_size)
     return fail(VAURA_ERR_INVALID, "page table covers %d positions < block_size %d", kv->max_pages_per_seq * kv->page_size,
                 s->d.block_size);

@@ -682,7 +682,6 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pp.tmem_full + 1);
   float* scratch = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
   uint64_t* attn_bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + 256 + kAttnScratch);
-  unsigned acopies = 0;  // K/V runs this warp has staged so far in the launch (slot = n % kAttnSlots, phase = n / kAttnSlots)
   pp.git = 0;
   pp.tiles = 0;
 
@@ -791,58 +790,88 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   //      all K runs, then all V runs, then the next item - with one bulk copy each into a private ring of kAttnSlots
   //      slots in the idle GEMM ring, so up to 18 KB per warp are in flight independent of registers and the V rows
   //      (and the next item's K rows) stream in while the scores are computed.  Positions are consumed 32 at a time.
+  // the warp's items and their page tables do not change during the launch: lane i holds page i (<= 16 pages for 256
+  // positions of 16)
+  const int att_item_stride = G * (kGemmThreads / 32), att_item0 = warp * G + cta;  // CTA-fastest: every SM gets ~7 items
+  const int att_nitems = att_item0 < R * a.H ? (R * a.H - att_item0 + att_item_stride - 1) / att_item_stride : 0;  // <= 2
+  int att_pg[2] = {0, 0}, att_row[2] = {0, 0}, att_hd[2] = {0, 0};
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    if (i < att_nitems) {
+      const int item = att_item0 + i * att_item_stride;
+      att_row[i] = item / a.H;
+      att_hd[i] = item % a.H;
+      if (lane < a.kv.max_pages_per_seq) att_pg[i] = a.kv.page_table[att_row[i] * a.kv.max_pages_per_seq + lane];
+    }
+  int att_slot = 0;         // ring position of the next copy to issue (kernel lifetime)
+  int att_rslot = 0;        // ring position of the next copy to consume
+  unsigned att_rphase = 0;  // bit s = parity of the phase the consumer waits for on slot s
   auto attention_phase = [&](int layer) {
     float* qs = scratch + warp * (kHeadDim + kMaxCtx);
     float* sc = qs + kHeadDim;
     const __nv_bfloat16* kvp = reinterpret_cast<const __nv_bfloat16*>(a.kv.pages);
-    const int nctx = p + 1, psz = a.kv.page_size;
+    const int nctx = p + 1, psz = a.kv.page_size, psh = 31 - __clz(psz);
     const size_t page_stride = (size_t)a.kv.nhead * psz * kHeadDim;
-    const int item_stride = G * (kGemmThreads / 32), item0 = warp * G + cta;  // CTA-fastest: every SM gets ~7 items
-    const int nitems = item0 < R * a.H ? (R * a.H - item0 + item_stride - 1) / item_stride : 0;  // <= 2 (R <= 128)
+    const int nitems = att_nitems;
     const int nr = (nctx + 15) >> 4, total = nitems * 2 * nr;
-    // the page tables of the warp's items: lane i holds page i (<= 16 pages for 256 positions of 16)
-    int pg[2] = {0, 0};
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-      if (i < nitems && lane < a.kv.max_pages_per_seq)
-        pg[i] = a.kv.page_table[((item0 + i * item_stride) / a.H) * a.kv.max_pages_per_seq + lane];
     uint8_t* stage = smem + warp * (kAttnSlots * kRunBytes);
     uint64_t* abar = attn_bars + warp * kAttnSlots;
-    const unsigned abase = acopies;
+    // q of the first item: requested before anything else so that its latency overlaps the first copies
+    unsigned short qraw[3] = {0, 0, 0};
+    if (nitems)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        qraw[i] = __ldcg(reinterpret_cast<const unsigned short*>(a.q) + (size_t)att_row[0] * D + att_hd[0] * kHeadDim + lane + 32 * i);
     int issued = 0, consumed = 0;
-    // stage copy number `issued` of the phase: item issued / 2nr, K runs 0..nr-1 then V runs 0..nr-1
-    auto issue_one = [&]() {
-      const int it = issued / (2 * nr), rem = issued - it * 2 * nr, kvsel = rem >= nr ? 1 : 0, j = (rem - kvsel * nr) * 16;
-      const int hd = (item0 + it * item_stride) % a.H;
-      const int page = __shfl_sync(0xffffffffu, it ? pg[1] : pg[0], j / psz);
-      const __nv_bfloat16* src =
-          kvp + ((size_t)(layer * 2 + kvsel) * a.kv.num_pages + page) * page_stride + ((size_t)hd * psz + j % psz) * kHeadDim;
-      const int slot = (int)(acopies % kAttnSlots);
-      if (lane == 0) {
-        mbar_expect_tx(&abar[slot], kRunBytes);
-        bulk_load_1d(stage + slot * kRunBytes, src, kRunBytes, &abar[slot]);
+    int astamp_i = 0;
+    auto astamp = [&]() {  // sub-phase timestamps of (timing CTA, thread 0) in the last layer: timing[900 ...]
+      if (a.timing && cta == a.timing_cta && tid == 0 && layer == a.L - 1) {
+        unsigned long long tt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+        a.timing[900 + astamp_i] = tt;
       }
-      ++acopies;
+      ++astamp_i;
+    };
+    astamp();
+    // issue cursor: item, K (0) / V (1), run; copies go out in consumption order (all K runs, all V runs, next item)
+    int c_it = 0, c_kv = 0, c_run = 0;
+    auto issue_one = [&]() {
+      const int j = c_run * 16;
+      const int page = __shfl_sync(0xffffffffu, c_it ? att_pg[1] : att_pg[0], j >> psh);
+      const int hd = c_it ? att_hd[1] : att_hd[0];
+      const __nv_bfloat16* src = kvp + ((size_t)(layer * 2 + c_kv) * a.kv.num_pages + page) * page_stride +
+                                 ((size_t)hd * psz + (j & (psz - 1))) * kHeadDim;
+      if (lane == 0) {
+        mbar_expect_tx(&abar[att_slot], kRunBytes);
+        bulk_load_1d(stage + att_slot * kRunBytes, src, kRunBytes, &abar[att_slot]);
+      }
+      att_slot = att_slot + 1 == kAttnSlots ? 0 : att_slot + 1;
       ++issued;
+      if (++c_run == nr) { c_run = 0; if (++c_kv == 2) { c_kv = 0; ++c_it; } }
     };
     auto refill = [&]() {
       __syncwarp();  // every lane is done reading the slots counted in `consumed`
       while (issued < total && issued - consumed < kAttnSlots) issue_one();
     };
-    // wait for copy c of the phase and return its slot
-    auto staged = [&](int c) -> const uint8_t* {
-      const unsigned n = abase + (unsigned)c;
-      mbar_wait(&abar[n % kAttnSlots], (n / kAttnSlots) & 1u);
-      return stage + (n % kAttnSlots) * kRunBytes;
+    // wait for the next copy in consumption order and return its slot
+    auto staged = [&]() -> const uint8_t* {
+      const int sl = att_rslot;
+      mbar_wait(&abar[sl], (att_rphase >> sl) & 1u);
+      att_rphase ^= 1u << sl;
+      att_rslot = sl + 1 == kAttnSlots ? 0 : sl + 1;
+      return stage + sl * kRunBytes;
     };
     refill();
+    astamp();
     for (int it = 0; it < nitems; ++it) {
-      const int item = item0 + it * item_stride;
-      const int row = item / a.H, hd = item % a.H;
-      const int cK = it * 2 * nr, cV = cK + nr;
+      const int row = it ? att_row[1] : att_row[0], hd = it ? att_hd[1] : att_hd[0];
       __syncwarp();
-      for (int d = lane; d < kHeadDim; d += 32)
-        qs[d] = __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(a.q) + (size_t)row * D + hd * kHeadDim + d)));
+      if (it)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          qraw[i] = __ldcg(reinterpret_cast<const unsigned short*>(a.q) + (size_t)row * D + hd * kHeadDim + lane + 32 * i);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) qs[lane + 32 * i] = __bfloat162float(__ushort_as_bfloat16(qraw[i]));
       __syncwarp();
       // scores: 4 lanes per key position; lane t takes the 16-byte chunks t, t+4, t+8 of the 192-byte row (conflict-free:
       // a quarter warp reads two rows x four chunks); 4 x 8 positions per iteration
@@ -851,71 +880,106 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
 #pragma unroll
       for (int i = 0; i < 24; ++i) q24[i] = qs[(4 * (i >> 3) + t) * 8 + (i & 7)];
       float mx = -INFINITY;
+      astamp();
       for (int j0 = 0; j0 < nctx; j0 += 32) {
         const bool two = j0 + 16 < nctx;
-        const uint8_t* runA = staged(cK + (j0 >> 4));
-        const uint8_t* runB = two ? staged(cK + (j0 >> 4) + 1) : runA;
+        const uint8_t* runA = staged();
+        if (j0 == 0) astamp();
+        const uint8_t* runB = two ? staged() : runA;
+        // two rows per half (rows g and 8 + g of run A, then of run B): six independent 8-term chains in flight
+        float sd[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          if (h2 == 1 && !two) break;
+          const uint8_t* kr = (h2 ? runB : runA) + (g * 12 + t) * 16;
+          uint4 kk[2][3];
+#pragma unroll
+          for (int u2 = 0; u2 < 2; ++u2)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) kk[u2][c] = lds_u4(kr + u2 * (8 * 12 * 16) + 64 * c);  // rows past nctx: read, not used
+          float ps[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int u2 = 0; u2 < 2; ++u2)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const uint32_t w = e == 0 ? kk[u2][c].x : e == 1 ? kk[u2][c].y : e == 2 ? kk[u2][c].z : kk[u2][c].w;
+                ps[u2][c] = fmaf(q24[c * 8 + 2 * e], bf16_lo(w), ps[u2][c]);
+                ps[u2][c] = fmaf(q24[c * 8 + 2 * e + 1], bf16_hi(w), ps[u2][c]);
+              }
+          sd[2 * h2] = (ps[0][0] + ps[0][1]) + ps[0][2];
+          sd[2 * h2 + 1] = (ps[1][0] + ps[1][1]) + ps[1][2];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sd[u] += __shfl_xor_sync(0xffffffffu, sd[u], 2);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sd[u] += __shfl_xor_sync(0xffffffffu, sd[u], 1);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const uint8_t* kr = ((u < 2 || !two) ? runA : runB) + ((8 * (u & 1) + g) * 12 + t) * 16;  // row (8u + g) % 16 of the run
           const int jj = j0 + 8 * u + g;
-          float sdot = 0.f;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const uint4 kk = lds_u4(kr + 64 * c);  // rows past nctx hold whatever the page holds: read, not used
-            const uint32_t w[4] = {kk.x, kk.y, kk.z, kk.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              sdot = fmaf(q24[c * 8 + 2 * e], bf16_lo(w[e]), sdot);
-              sdot = fmaf(q24[c * 8 + 2 * e + 1], bf16_hi(w[e]), sdot);
-            }
-          }
-          sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-          sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
           if (jj < nctx) {
-            sdot *= a.scale;
-            if (t == 0) sc[jj] = sdot;
-            mx = fmaxf(mx, sdot);
+            const float sv = sd[u] * a.scale;
+            if (t == 0) sc[jj] = sv;
+            mx = fmaxf(mx, sv);
           }
         }
         consumed += two ? 2 : 1;
         refill();
       }
+      astamp();
       mx = warp_max(mx);
       __syncwarp();
       float sum = 0.f;
       for (int jj = lane; jj < ((nctx + 31) & ~31); jj += 32) {  // positions past the context get probability 0
         const float e = jj < nctx ? expf(sc[jj] - mx) : 0.f;
-        sc[jj] = e;
+        __syncwarp();
+        // within a block of 32 positions: even positions first, then odd ones (what a P.V lane reads is contiguous)
+        sc[(jj & ~31) + (lane & 1) * 16 + (lane >> 1)] = e;
         sum += e;
       }
       sum = warp_sum(sum);
       __syncwarp();
-      // P.V: lanes 0-11 take the even positions, lanes 12-23 the odd ones, 8 dims (one 16-byte chunk) each
+      // P.V: lanes 0-11 take the even positions, lanes 12-23 the odd ones, 8 dims (one 16-byte chunk) each; eight
+      // independent accumulators, eight value rows in flight
       float o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = 0.f;
       const int half = lane >= 12 ? 1 : 0, dl = lane < 24 ? lane - 12 * half : 0;
+      astamp();
       for (int j0 = 0; j0 < nctx; j0 += 32) {
         const bool two = j0 + 16 < nctx;
-        const uint8_t* runA = staged(cV + (j0 >> 4)) + (half * 12 + dl) * 16;
-        const uint8_t* runB = two ? staged(cV + (j0 >> 4) + 1) + (half * 12 + dl) * 16 : runA;
+        const uint8_t* runA = staged() + (half * 12 + dl) * 16;
+        if (j0 == 0) astamp();
+        const uint8_t* runB = two ? staged() + (half * 12 + dl) * 16 : runA;
+        float pj[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {  // row 2 (u % 8) + half of the run; rows past the context may hold anything (NaN bit patterns)
-          const int jj = j0 + 2 * u + half;
-          const bool live = jj < nctx && (u < 8 || two);
-          const uint4 vv = live ? lds_u4((u < 8 ? runA : runB) + (u & 7) * 24 * 16) : make_uint4(0u, 0u, 0u, 0u);
-          const float pj = live ? sc[jj] : 0.f;
-          const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+        for (int i = 0; i < 4; ++i) {
+          const uint4 pv = lds_u4(sc + j0 + half * 16 + 4 * i);
+          pj[4 * i] = __uint_as_float(pv.x); pj[4 * i + 1] = __uint_as_float(pv.y);
+          pj[4 * i + 2] = __uint_as_float(pv.z); pj[4 * i + 3] = __uint_as_float(pv.w);
+        }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            o[2 * e] = fmaf(pj, bf16_lo(w[e]), o[2 * e]);
-            o[2 * e + 1] = fmaf(pj, bf16_hi(w[e]), o[2 * e + 1]);
+        for (int b8 = 0; b8 < 2; ++b8) {
+          if (b8 == 1 && !two) break;
+          const uint8_t* rb = b8 ? runB : runA;
+          uint4 vv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)  // row 2 i + half of the run; rows past the context may hold anything (NaN bit patterns)
+            vv[i] = j0 + 16 * b8 + 2 * i + half < nctx ? lds_u4(rb + i * 24 * 16) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float pw = pj[8 * b8 + i];
+            o[0] = fmaf(pw, bf16_lo(vv[i].x), o[0]); o[1] = fmaf(pw, bf16_hi(vv[i].x), o[1]);
+            o[2] = fmaf(pw, bf16_lo(vv[i].y), o[2]); o[3] = fmaf(pw, bf16_hi(vv[i].y), o[3]);
+            o[4] = fmaf(pw, bf16_lo(vv[i].z), o[4]); o[5] = fmaf(pw, bf16_hi(vv[i].z), o[5]);
+            o[6] = fmaf(pw, bf16_lo(vv[i].w), o[6]); o[7] = fmaf(pw, bf16_hi(vv[i].w), o[7]);
           }
         }
         consumed += two ? 2 : 1;
         refill();
       }
+      astamp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += __shfl_down_sync(0xffffffffu, o[i], 12);
       if (lane < 12) {
@@ -1174,7 +1238,9 @@ static cudaError_t launch_decode_fused_t(const FusedStepArgs& a, const void* wqk
   // one tile per CTA per phase, one residual row per CTA in the norm phases
   if (3 * a.D / 32 > sms || 2 * a.F / 64 > sms || need > sms || a.R > sms) return cudaErrorInvalidValue;
   // attention phase: at most two (row, head) items per warp, lane i holds page i, 16-position runs inside a page
-  if (a.R * a.H > 2 * sms * (kGemmThreads / 32) || a.kv.max_pages_per_seq > 32 || a.kv.page_size % 16) return cudaErrorInvalidValue;
+  if (a.R * a.H > 2 * sms * (kGemmThreads / 32) || a.kv.max_pages_per_seq > 32 || a.kv.page_size < 16 ||
+      (a.kv.page_size & (a.kv.page_size - 1)))
+    return cudaErrorInvalidValue;
   const uint64_t D = a.D, F = a.F, L = a.L;
   CUtensorMap m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads;
   bool ok = make_map(&m_xn, a.xn, D, a.R, 1, D, (uint64_t)a.R * D, 64, TM, false) &&

@@ -8,6 +8,7 @@ arithmetic happens in ``libvaura_b200.so``; torch only owns device buffers and t
 from __future__ import annotations
 
 import ctypes as C
+import os
 from math import ceil
 from types import SimpleNamespace
 from typing import Dict, Optional
@@ -18,7 +19,7 @@ from . import _cabi
 from .synthetic import SamplerDims, find_multiple
 from .weights import pack_sampler
 
-PAGE_SIZE = 32
+PAGE_SIZE = int(os.environ.get("VAURA_PAGE_SIZE", "32"))
 
 
 def resolve_precision(precision: int, rows: int) -> int:
