@@ -41,3 +41,10 @@ a = t[900:908]
 if a[0] and a[7] > a[0]:
     lab = ["page table + first copies issued", "q loaded", "first K run landed", "scores done", "softmax done", "first V run landed", "P.V done"]
     print("attention sub-phases of warp 0, last layer (us): " + ", ".join(f"{n} {(a[i + 1] - a[i]) / 1e3:.2f}" for i, n in enumerate(lab)))
+for name, base in (("wqkv", 910), ("w1|w3", 940)):
+    d = t[base:base + 27]
+    if d[26]:
+        rel = lambda v: (v - d[26]) / 1e3
+        print(f"{name} tile of the last layer, us after the producer's entry: loads issued " + " ".join(f"{rel(v):.2f}" for v in d[0:6]) +
+              " | landed " + " ".join(f"{rel(v):.2f}" for v in d[8:14]) + " | MMAs issued " + " ".join(f"{rel(v):.2f}" for v in d[16:22]) +
+              f" | accumulator complete {rel(d[24]):.2f} | epilogue done {rel(d[25]):.2f}")

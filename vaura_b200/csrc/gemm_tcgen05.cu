@@ -53,6 +53,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (t - t0 > 2000000000ull) __trap();  // 2 s
   }
 }
+// warp-uniform variants (see umma_bf16_f16_elect): every lane executes, one elected lane issues
+__device__ __forceinline__ void mbar_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_elect(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_elect(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // plain (1-D) bulk copy global -> shared, completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -63,6 +89,13 @@ __device__ __forceinline__ uint4 lds_u4(const void* p) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
   return v;
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
@@ -79,6 +112,26 @@ __device__ __forceinline__ void umma_bf16_f16(uint32_t tmem_d, uint64_t adesc, u
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// Warp-uniform variants: EVERY lane of a converged warp executes the statement with identical operands and one elected
+// lane issues.  Inside `if (lane == 0)` the compiler cannot prove uniformity and wraps each tcgen05.mma / bulk copy in
+// an ELECT + R2UR.BROADCAST loop (~80 cycles per instruction, measured 41 ns per MMA); with uniform control flow the
+// operands are plain uniform registers.
+__device__ __forceinline__ void umma_bf16_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -545,6 +598,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 // ------------------------------------------------------------------------------------------------
 namespace fused {
 constexpr int kKsub = 4, kBlockK = 64;
+constexpr int kAccCols = 64;  // TMEM columns of the accumulator (BN <= 64)
 constexpr int kBMax = 64 * kBlockK * 2;                   // 8 KB weight sub-tile (BN = 64; BN = 32 uses half of it)
 // TM = UMMA M = rows of the activation tile: 64 (up to 64 sequence rows) or 128 (up to 128, e.g. 64 clips with CFG)
 template <int TM>
@@ -599,51 +653,73 @@ struct FusedPipe {
 // (map tmB), K blocks [kb0, kb1); warp 0 = TMA, warp 1 = MMA issue, warps 2-9 = epilogue
 template <int BN, int TM>
 __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap* tmA, const CUtensorMap* tmB, int layer, int n0,
-                                                int kb0, int kb1, const EpiLinear::Params& ep) {
+                                                int kb0, int kb1, const EpiLinear::Params& ep,
+                                                unsigned long long* dbg = nullptr) {
+  // dbg (profiles/fused_timing.py): [0..7] stage loads issued, [8..15] stage landed, [16..23] stage MMAs issued,
+  // [24] accumulator complete, [25] epilogue done, [26] entry
+  auto dstamp = [&](int i) {
+    if (dbg) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      dbg[i] = t;
+    }
+  };
   using namespace fused;
   using GE = Geo<TM>;
   constexpr int kStages = GE::kStages, kStageBytes = GE::kStageBytes, kSubBytes = GE::kSubBytes, kABytes = GE::kABytes;
   constexpr int B_BYTES = BN * kBlockK * 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int iters = (kb1 - kb0 + kKsub - 1) / kKsub;
+  const int rot = blockIdx.x % iters;
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int gi = pp.git + it, s = gi % kStages;
-        const uint32_t ph = (gi / kStages) & 1;
-        const int u0 = kb0 + it * kKsub, nsub = min(kKsub, kb1 - u0);
-        uint8_t* ss = pp.smem + s * kStageBytes;
-        mbar_wait(&pp.empty[s], ph ^ 1);
-        mbar_expect_tx(&pp.full[s], nsub * (kABytes + B_BYTES));
-        for (int sub = 0; sub < nsub; ++sub) {
-          uint8_t* sa = ss + sub * kSubBytes;
-          tma_load_3d(sa + kABytes, tmB, &pp.full[s], (u0 + sub) * kBlockK, n0, layer);
-          tma_load_3d(sa, tmA, &pp.full[s], (u0 + sub) * kBlockK, 0, 0);
-        }
-      }
+    // the whole warp walks the stages (uniform control flow); one elected lane issues the copies
+    if (dbg && lane == 0) dstamp(26);
+    for (int it = 0; it < iters; ++it) {
+      const int gi = pp.git + it, s = gi % kStages;
+      const uint32_t ph = (gi / kStages) & 1;
+      // K groups are visited in a CTA-dependent rotation (neutral in measurements, kept: the CTAs of a phase read the
+      // same activation matrix, this keeps them from asking the same L2 lines at the same time)
+      const int grp = (it + rot) % iters;
+      const int u0 = kb0 + grp * kKsub;
+      uint8_t* ss = pp.smem + s * kStageBytes;
+      mbar_wait(&pp.empty[s], ph ^ 1);
+      // one box per operand covers the stage's kKsub K blocks (a copy instruction costs the issuing thread ~0.13 us
+      // whatever its size, profiles/probes/tma_rate.cu); a box that runs past kb1 or past K still delivers its full
+      // byte count
+      mbar_expect_tx_elect(&pp.full[s], kKsub * (kABytes + B_BYTES));
+      tma_load_4d_elect(ss + kKsub * kABytes, tmB, &pp.full[s], 0, n0, u0, layer);
+      tma_load_4d_elect(ss, tmA, &pp.full[s], 0, 0, u0, 0);
+      if (dbg && lane == 0 && it < 8) dstamp(it);
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TM, BN, 1);
-      for (int it = 0; it < iters; ++it) {
-        const int gi = pp.git + it, s = gi % kStages;
-        const uint32_t ph = (gi / kStages) & 1;
-        mbar_wait(&pp.full[s], ph);
-        tcgen05_fence_after();
-        const int nsub = min(kKsub, kb1 - (kb0 + it * kKsub));
-        for (int sub = 0; sub < nsub; ++sub) {
-          const uint32_t a_addr = smem_u32(pp.smem + s * kStageBytes + sub * kSubBytes);
-          const uint64_t adesc = make_smem_desc<128>(a_addr), bdesc = make_smem_desc<128>(a_addr + kABytes);
+    // the whole warp walks the stages (uniform control flow); one elected lane issues the MMAs and the commits
+    constexpr uint32_t idesc = make_idesc(TM, BN, 1);
+    for (int it = 0; it < iters; ++it) {
+      const int gi = pp.git + it, s = gi % kStages;
+      const uint32_t ph = (gi / kStages) & 1;
+      mbar_wait(&pp.full[s], ph);
+      tcgen05_fence_after();
+      if (dbg && lane == 0 && it < 8) dstamp(8 + it);
+      const int nsub = min(kKsub, kb1 - (kb0 + (it + rot) % iters * kKsub));
+      for (int sub = 0; sub < nsub; ++sub) {
+        // stage layout: kKsub activation sub-tiles, then kKsub weight sub-tiles (each [rows x 128 B], 128B-swizzled)
+        const uint32_t st_addr = smem_u32(pp.smem + s * kStageBytes);
+        const uint64_t adesc = make_smem_desc<128>(st_addr + sub * kABytes),
+                       bdesc = make_smem_desc<128>(st_addr + kKsub * kABytes + sub * B_BYTES);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) umma_bf16_f16(pp.tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | sub | k) != 0);
-        }
-        umma_commit(&pp.empty[s]);
+        for (int k = 0; k < kBlockK / 16; ++k)
+          umma_bf16_f16_elect(pp.tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | sub | k) != 0);
       }
-      umma_commit(pp.tmem_full);
+      umma_commit_elect(&pp.empty[s]);
+      if (dbg && lane == 0 && it < 8) dstamp(16 + it);
     }
+    umma_commit_elect(pp.tmem_full);
+    __syncwarp();
   } else {
     mbar_wait(pp.tmem_full, pp.tiles & 1);
     tcgen05_fence_after();
+    if (warp == 2 && lane == 0) dstamp(24);
     const int q = warp & 3;
     // UMMA M = 128: accumulator row i sits in lane i; M = 64: rows 16q..16q+15 sit in lanes 32q..32q+15
     const int m = TM == 128 ? q * 32 + lane : q * 16 + lane;
@@ -657,6 +733,7 @@ __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap
       if (row_ok) EpiLinear::apply(ep, 0, 0, m, n0 + c, v);
     }
     tcgen05_fence_before();
+    if (warp == 2 && lane == 0) dstamp(25);
   }
   pp.git += iters;
   pp.tiles += 1;
@@ -721,7 +798,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kAccCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tcgen05_fence_before();
@@ -841,10 +918,8 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       const int hd = c_it ? att_hd[1] : att_hd[0];
       const __nv_bfloat16* src = kvp + ((size_t)(layer * 2 + c_kv) * a.kv.num_pages + page) * page_stride +
                                  ((size_t)hd * psz + (j & (psz - 1))) * kHeadDim;
-      if (lane == 0) {
-        mbar_expect_tx(&abar[att_slot], kRunBytes);
-        bulk_load_1d(stage + att_slot * kRunBytes, src, kRunBytes, &abar[att_slot]);
-      }
+      mbar_expect_tx_elect(&abar[att_slot], kRunBytes);
+      bulk_load_1d_elect(stage + att_slot * kRunBytes, src, kRunBytes, &abar[att_slot]);
       att_slot = att_slot + 1 == kAttnSlots ? 0 : att_slot + 1;
       ++issued;
       if (++c_run == nr) { c_run = 0; if (++c_kv == 2) { c_kv = 0; ++c_it; } }
@@ -1018,13 +1093,42 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     __syncthreads();
   };
 
+  // ---- L2 prefetch of the weight tile this CTA multiplies in the NEXT GEMM phase.  A GEMM phase is short (one tile per
+  //      CTA) and its ring holds about half of the tile's operands, so weight bytes that come from HBM cost two memory
+  //      round trips per phase; requested one phase ahead they are L2 hits when the tile runs, and HBM works in the
+  //      background of a phase instead of on its critical path.  Issued by warp 2 (an epilogue warp, idle until the
+  //      accumulator is complete): one request per weight row segment. ----
+  auto prefetch_rows = [&](const __nv_bfloat16* w, size_t row0, int nrows, size_t ld, size_t col0, int ncols) {
+    if (warp != 2 || !a.l2_prefetch) return;
+    for (int r = lane; r < nrows; r += 32)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(w + (row0 + r) * ld + col0), "r"(ncols * 2) : "memory");
+  };
+  auto prefetch_wqkv = [&](int l) {
+    if (cta < 3 * D / 32) prefetch_rows(a.w_qkv, (size_t)l * 3 * D + cta * 32, 32, D, 0, D);
+  };
+  auto prefetch_splitk = [&](const __nv_bfloat16* w, int l, int K, int ksplit) {  // wo / w2 tile of this CTA
+    const int nt = D / 64;
+    if (cta >= nt * ksplit) return;
+    const int split = cta / nt, kb = K / kBlockK, k0 = kb * split / ksplit, k1 = kb * (split + 1) / ksplit;
+    prefetch_rows(w, (size_t)l * D + (cta % nt) * 64, 64, K, (size_t)k0 * kBlockK, (k1 - k0) * kBlockK);
+  };
+  auto prefetch_w13 = [&](int l) {
+    if (cta < 2 * F / 64) prefetch_rows(a.w_13, (size_t)l * 2 * F + cta * 64, 64, D, 0, D);
+  };
+  auto prefetch_heads = [&]() {
+    for (int t = cta; t < a.NH / 64; t += G) prefetch_rows(a.w_heads, (size_t)t * 64, 64, D, 0, D);
+  };
+
+  prefetch_wqkv(0);
   rmsnorm_phase(a.attn_norm, a.fuse_io);
   sync_all();
   for (int l = 0; l < a.L; ++l) {
     // wqkv: 144 tiles of 32 output features, RoPE + KV append + bf16 q in the epilogue
+    prefetch_splitk(a.w_o, l, D, a.wo_ksplit);
     if (cta < 3 * D / 32) {
       ep.mode = EPI_QKV; ep.N = 3 * D; ep.out_bf16 = a.q; ep.out_f32 = nullptr; ep.ldo = D; ep.layer = l; ep.atomic = 0;
-      fused_gemm_tile<32, TM>(pp, &tm_xn, &tm_wqkv, l, cta * 32, 0, D / kBlockK, ep);
+      fused_gemm_tile<32, TM>(pp, &tm_xn, &tm_wqkv, l, cta * 32, 0, D / kBlockK, ep,
+                              a.timing && cta == a.timing_cta && l == a.L - 1 ? a.timing + 910 : nullptr);
     }
     sync_all();
     attention_phase(l);
@@ -1032,6 +1136,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     // wo + residual: 24 N tiles x wo_ksplit K slices, fp32 vector reductions into h; then the FFN norm of the rows
     {
       const int nt = D / 64;
+      prefetch_w13(l);
       if (cta < (int)tiles_wo) {
         const int split = cta / nt, kb = D / kBlockK;
         ep.mode = EPI_RESID; ep.N = D; ep.out_f32 = a.h; ep.ldo = D; ep.atomic = 1;
@@ -1046,14 +1151,17 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     }
     sync_all();
     // w1|w3 (rows interleaved) + SiLU * mul: 128 tiles of 64 rows = 32 hidden units
+    prefetch_splitk(a.w_2, l, F, a.w2_ksplit);
     if (cta < 2 * F / 64) {
       ep.mode = EPI_SWIGLU; ep.N = 2 * F; ep.out_bf16 = a.act; ep.ldo = F; ep.atomic = 0;
-      fused_gemm_tile<64, TM>(pp, &tm_xn, &tm_w13, l, cta * 64, 0, D / kBlockK, ep);
+      fused_gemm_tile<64, TM>(pp, &tm_xn, &tm_w13, l, cta * 64, 0, D / kBlockK, ep,
+                              a.timing && cta == a.timing_cta && l == a.L - 1 ? a.timing + 940 : nullptr);
     }
     sync_all();
     // w2 + residual; then the next layer's attention norm (the final norm after the last layer)
     {
       const int nt = D / 64;
+      if (l + 1 < a.L) prefetch_wqkv(l + 1); else prefetch_heads();
       if (cta < (int)tiles_w2) {
         const int split = cta / nt, kb = F / kBlockK;
         ep.mode = EPI_RESID; ep.N = D; ep.out_f32 = a.h; ep.ldo = D; ep.atomic = 1;
@@ -1086,7 +1194,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pp.tmem_base), "r"(64));
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pp.tmem_base), "r"(kAccCols));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1121,6 +1229,20 @@ static bool make_map(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows
   return fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// [outer][rows][K] bf16 seen as (64, rows, K / 64, outer): one box = nblk K blocks of box_rows rows, landing in shared
+// memory as nblk consecutive 128B-swizzled [box_rows x 64] sub-tiles
+static bool make_map_kblocks(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, uint64_t outer, uint64_t row_stride_el,
+                             uint64_t outer_stride_el, int box_rows, int nblk) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || K % 64) return false;
+  cuuint64_t dims[4] = {64, rows, K / 64, outer};
+  cuuint64_t strides[3] = {row_stride_el * 2, 64 * 2, outer_stride_el * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, (cuuint32_t)nblk, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128, int KSUB = 1>
@@ -1243,14 +1365,15 @@ static cudaError_t launch_decode_fused_t(const FusedStepArgs& a, const void* wqk
     return cudaErrorInvalidValue;
   const uint64_t D = a.D, F = a.F, L = a.L;
   CUtensorMap m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads;
-  bool ok = make_map(&m_xn, a.xn, D, a.R, 1, D, (uint64_t)a.R * D, 64, TM, false) &&
-            make_map(&m_attn, a.attn, D, a.R, 1, D, (uint64_t)a.R * D, 64, TM, false) &&
-            make_map(&m_act, a.act, F, a.R, 1, F, (uint64_t)a.R * F, 64, TM, false) &&
-            make_map(&m_wqkv, wqkv, D, 3 * D, L, D, 3 * D * D, 64, 32, false) &&
-            make_map(&m_wo, wo, D, D, L, D, D * D, 64, 64, false) &&
-            make_map(&m_w13, w13, D, 2 * F, L, D, 2 * F * D, 64, 64, false) &&
-            make_map(&m_w2, w2, F, D, L, F, D * F, 64, 64, false) &&
-            make_map(&m_heads, w_heads, D, a.NH, 1, D, (uint64_t)a.NH * D, 64, 64, false);
+  constexpr int KS = fused::kKsub;
+  bool ok = make_map_kblocks(&m_xn, a.xn, D, a.R, 1, D, (uint64_t)a.R * D, TM, KS) &&
+            make_map_kblocks(&m_attn, a.attn, D, a.R, 1, D, (uint64_t)a.R * D, TM, KS) &&
+            make_map_kblocks(&m_act, a.act, F, a.R, 1, F, (uint64_t)a.R * F, TM, KS) &&
+            make_map_kblocks(&m_wqkv, wqkv, D, 3 * D, L, D, 3 * D * D, 32, KS) &&
+            make_map_kblocks(&m_wo, wo, D, D, L, D, D * D, 64, KS) &&
+            make_map_kblocks(&m_w13, w13, D, 2 * F, L, D, 2 * F * D, 64, KS) &&
+            make_map_kblocks(&m_w2, w2, F, D, L, F, D * F, 64, KS) &&
+            make_map_kblocks(&m_heads, w_heads, D, a.NH, 1, D, (uint64_t)a.NH * D, 64, KS);
   if (!ok) return cudaErrorUnknown;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(sms);
@@ -1262,14 +1385,25 @@ static cudaError_t launch_decode_fused_t(const FusedStepArgs& a, const void* wqk
   at[0].val.cooperative = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, decode_step_fused_bf16<TM>, m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads, a);
+  FusedStepArgs b = a;
+  b.w_qkv = static_cast<const __nv_bfloat16*>(wqkv);
+  b.w_o = static_cast<const __nv_bfloat16*>(wo);
+  b.w_13 = static_cast<const __nv_bfloat16*>(w13);
+  b.w_2 = static_cast<const __nv_bfloat16*>(w2);
+  b.w_heads = static_cast<const __nv_bfloat16*>(w_heads);
+  {
+    const char* pf = getenv("VAURA_FUSED_L2_PREFETCH");
+    b.l2_prefetch = pf ? atoi(pf) : 1;
+  }
+  return cudaLaunchKernelEx(&cfg, decode_step_fused_bf16<TM>, m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads, b);
 }
 
 cudaError_t launch_decode_fused_bf16(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
                                      const void* w_heads, cudaStream_t st) {
   if (!fused_step_supported(a.R, a.D, a.F, a.NH)) return cudaErrorInvalidValue;
-  return a.R <= 64 ? launch_decode_fused_t<64>(a, wqkv, wo, w13, w2, w_heads, st)
-                   : launch_decode_fused_t<128>(a, wqkv, wo, w13, w2, w_heads, st);
+  const char* tm = getenv("VAURA_FUSED_TM128");  // experiment: UMMA M = 128 also for <= 64 rows
+  return a.R <= 64 && !(tm && tm[0] == '1') ? launch_decode_fused_t<64>(a, wqkv, wo, w13, w2, w_heads, st)
+                                            : launch_decode_fused_t<128>(a, wqkv, wo, w13, w2, w_heads, st);
 }
 
 // Linear layer of the bf16 sampler path: out = A[R][K] (bf16) x W[N][K]^T (bf16) with a fused epilogue.

@@ -115,6 +115,9 @@ struct FusedStepArgs {
   int R, L, D, F, H, NH;     // rows, layers, d_model, ffn, heads, K*V logits per row
   int wo_ksplit, w2_ksplit;
   float eps, scale;
+  // raw weight pointers (the GEMM operands themselves go through tensor maps): L2 prefetch of the next phase's tile
+  const __nv_bfloat16 *w_qkv, *w_o, *w_13, *w_2, *w_heads;
+  int l2_prefetch;  // 0 = off
   unsigned long long* timing;  // optional: timestamps (ns) of CTA `timing_cta` before / after every device-wide barrier
   unsigned long long* step_times;  // [kMaxCtx + 16]: %globaltimer at the start of the launch that samples column `offset`
   int timing_cta;
