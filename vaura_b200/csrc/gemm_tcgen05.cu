@@ -127,6 +127,19 @@ __device__ __forceinline__ void umma_bf16_f16_elect(uint32_t tmem_d, uint64_t ad
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// same, the shared-memory descriptors given by their low words (the 14-bit address field); the high word of a
+// 128B-swizzled K-major descriptor is a constant
+__device__ __forceinline__ void umma_bf16_f16_elect_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "n"(0x40004040)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"
@@ -154,7 +167,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // UMMA shared-memory matrix descriptor for a K-major tile whose rows are one swizzle atom wide
 // (BLOCK_K * 2 bytes == swizzle bytes): SBO = 8 rows * swizzle bytes, LBO unused, version 1 (sm_100).
 template <int SWIZZLE_BYTES>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+__host__ __device__ constexpr uint64_t make_smem_desc(uint32_t smem_addr) {
   constexpr uint64_t layout = SWIZZLE_BYTES == 128 ? 2 : (SWIZZLE_BYTES == 64 ? 4 : 6);
   constexpr uint64_t sbo = (8 * SWIZZLE_BYTES) >> 4;
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (sbo << 32) | (1ull << 46) | (layout << 61);
@@ -702,14 +715,24 @@ __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap
       tcgen05_fence_after();
       if (dbg && lane == 0 && it < 8) dstamp(8 + it);
       const int nsub = min(kKsub, kb1 - (kb0 + (it + rot) % iters * kKsub));
-      for (int sub = 0; sub < nsub; ++sub) {
-        // stage layout: kKsub activation sub-tiles, then kKsub weight sub-tiles (each [rows x 128 B], 128B-swizzled)
-        const uint32_t st_addr = smem_u32(pp.smem + s * kStageBytes);
-        const uint64_t adesc = make_smem_desc<128>(st_addr + sub * kABytes),
-                       bdesc = make_smem_desc<128>(st_addr + kKsub * kABytes + sub * B_BYTES);
+      // stage layout: kKsub activation sub-tiles, then kKsub weight sub-tiles (each [rows x 128 B], 128B-swizzled);
+      // descriptors differ only in their 14-bit address field: +2 per 32-byte K step inside the swizzle atom
+      const uint32_t st_addr = smem_u32(pp.smem + s * kStageBytes);
+      static_assert((make_smem_desc<128>(0) >> 32) == 0x40004040ull, "descriptor high word");
+      const uint32_t a_lo = (st_addr & 0x3FFFF) >> 4, b_lo = ((st_addr + kKsub * kABytes) & 0x3FFFF) >> 4;
+      if (nsub == kKsub) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)
-          umma_bf16_f16_elect(pp.tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | sub | k) != 0);
+        for (int sub = 0; sub < kKsub; ++sub)
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16_f16_elect_lo(pp.tmem_base, a_lo + sub * (kABytes >> 4) + 2 * k, b_lo + sub * (B_BYTES >> 4) + 2 * k, idesc,
+                                   (it | sub | k) != 0);
+      } else {
+        for (int sub = 0; sub < nsub; ++sub)
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16_f16_elect_lo(pp.tmem_base, a_lo + sub * (kABytes >> 4) + 2 * k, b_lo + sub * (B_BYTES >> 4) + 2 * k, idesc,
+                                   (it | sub | k) != 0);
       }
       umma_commit_elect(&pp.empty[s]);
       if (dbg && lane == 0 && it < 8) dstamp(16 + it);
