@@ -140,6 +140,28 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
+// Warp-uniform variants for the producer warp: every lane executes the statement with identical operands and one
+// elected lane issues.  Inside `if (lane == 0)` the compiler wraps every copy instruction in an ELECT + R2UR loop
+// (~0.13 us per copy of the issuing thread's time, profiles/probes/tma_rate.cu).
+__device__ __forceinline__ void mb_expect_tx_e(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_e(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n\t}" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2_e(const void* src, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.prefetch.L2.global [%0], %1;\n\t}" ::"l"(src), "r"(bytes)
+      : "memory");
+}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -322,7 +344,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
 
   if (warp == CW) {
     // ------------------------------- producer: the CTA's two weight streams -------------------------------
-    if (lane == 0) {
+    // (all 32 lanes walk the loop with identical values; one elected lane issues each copy)
+    {
       uint64_t pol_first, pol_last;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
@@ -360,7 +383,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           const uint8_t* psrc;
           bool ps;
           unit(pq, pi, pn, psrc, ps);
-          if (pq > q) bulk_prefetch_l2(psrc, (uint32_t)pn * SLOT);
+          if (pq > q) bulk_prefetch_l2_e(psrc, (uint32_t)pn * SLOT);
           ++pq;
         }
         while (issued + n - freed > ring_limit) {
@@ -372,10 +395,14 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
           freed += rn;
           ++rel;
         }
-        mb_expect_tx(full0 + 8 * i, (uint32_t)n * SLOT);
-        for (int s = 0; s < n; ++s) {
-          bulk_g2s(sbase + LY::ring + wslot * SLOT, src + (size_t)s * SLOT, SLOT, full0 + 8 * i, is_shared ? pol_last : pol_first);
-          wslot = wslot + 1 == NSLOT ? 0 : wslot + 1;
+        mb_expect_tx_e(full0 + 8 * i, (uint32_t)n * SLOT);
+        {  // the unit's slots are contiguous in the stream and in the ring up to the wrap: one copy, two at the wrap
+          const int n1 = min(n, NSLOT - wslot);
+          bulk_g2s_e(sbase + LY::ring + wslot * SLOT, src, (uint32_t)n1 * SLOT, full0 + 8 * i, is_shared ? pol_last : pol_first);
+          if (n1 < n)
+            bulk_g2s_e(sbase + LY::ring, src + (size_t)n1 * SLOT, (uint32_t)(n - n1) * SLOT, full0 + 8 * i,
+                       is_shared ? pol_last : pol_first);
+          wslot = wslot + n >= NSLOT ? wslot + n - NSLOT : wslot + n;
         }
         issued += n;
       }
@@ -386,7 +413,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
         const uint8_t* src;
         bool is_shared;
         unit(q, i, n, src, is_shared);
-        bulk_prefetch_l2(src, (uint32_t)n * SLOT);
+        bulk_prefetch_l2_e(src, (uint32_t)n * SLOT);
       }
     }
   } else {
