@@ -70,6 +70,15 @@ __device__ __forceinline__ void bulk_load_1d_elect(void* dst, const void* src, u
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_elect(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d_elect(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"
@@ -524,47 +533,47 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     phase = zz % g.nphase;
   };
 
+  // warps 0 and 1 run their loops with all 32 lanes (uniform control flow) and one elected lane issues: inside
+  // `if (lane == 0)` every tensor copy / MMA costs an ELECT + R2UR loop (~0.13 us per copy, ~41 ns per MMA)
   if (warp == 0) {
-    if (lane == 0) {
-      int git = 0;  // ring iterations since the kernel started
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        int m0, n0, b, phase;
-        tile_coords(t, m0, n0, b, phase);
-        for (int it = 0; it < iters; ++it, ++git) {
-          const int s = git % STAGES;
-          const uint32_t ph = (git / STAGES) & 1;
-          const int tap = it / g.kblocks, kb = it % g.kblocks;
-          uint8_t* ss = smem + s * STAGE_BYTES;
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], STAGE_BYTES);
-          tma_load_3d(ss + A_BYTES, &tmB, &full[s], kb * BLOCK_K, n0, phase * g.ntaps + tap);
-          tma_load_3d(ss, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
-        }
+    int git = 0;  // ring iterations since the kernel started
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int m0, n0, b, phase;
+      tile_coords(t, m0, n0, b, phase);
+      for (int it = 0; it < iters; ++it, ++git) {
+        const int s = git % STAGES;
+        const uint32_t ph = (git / STAGES) & 1;
+        const int tap = it / g.kblocks, kb = it % g.kblocks;
+        uint8_t* ss = smem + s * STAGE_BYTES;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx_elect(&full[s], STAGE_BYTES);
+        tma_load_3d_elect(ss + A_BYTES, &tmB, &full[s], kb * BLOCK_K, n0, phase * g.ntaps + tap);
+        tma_load_3d_elect(ss, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_M, BLOCK_N, FMT);
-      int git = 0, tc = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
-        const int ab = tc & 1;
-        mbar_wait(&tempty[ab], ((tc >> 1) & 1) ^ 1);  // the epilogue has drained this buffer (first use passes)
+    constexpr uint32_t idesc = make_idesc(TILE_M, BLOCK_N, FMT);
+    int git = 0, tc = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
+      const int ab = tc & 1;
+      mbar_wait(&tempty[ab], ((tc >> 1) & 1) ^ 1);  // the epilogue has drained this buffer (first use passes)
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + ab * ACC_COLS;
+      for (int it = 0; it < iters; ++it, ++git) {
+        const int s = git % STAGES;
+        const uint32_t ph = (git / STAGES) & 1;
+        mbar_wait(&full[s], ph);
         tcgen05_fence_after();
-        const uint32_t tacc = tmem_base + ab * ACC_COLS;
-        for (int it = 0; it < iters; ++it, ++git) {
-          const int s = git % STAGES;
-          const uint32_t ph = (git / STAGES) & 1;
-          mbar_wait(&full[s], ph);
-          tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-          const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) umma_bf16_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
-          umma_commit(&empty[s]);
-        }
-        umma_commit(&tfull[ab]);
+        for (int k = 0; k < BLOCK_K / 16; ++k) umma_bf16_f16_elect(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        umma_commit_elect(&empty[s]);
       }
+      umma_commit_elect(&tfull[ab]);
     }
+    __syncwarp();
   } else {
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
     constexpr int kChunks = BLOCK_N / 16, kHalf = (kChunks + 1) / 2;
