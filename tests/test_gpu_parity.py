@@ -287,6 +287,27 @@ def test_bf16_path_128_row_fused_step(tiny_model, tiny_oracle):
     assert rel_err(mine, ref) < 2 * BF16_LOGIT_TOL  # CFG amplifies the error by ~cfg_scale
 
 
+def test_bf16_fused_step_with_16_position_pages(tiny_model, tiny_oracle, monkeypatch):
+    """K/V pages of 16 positions (the other page size the C ABI accepts): one staged attention run per page, a long
+    enough clip for runs in several pages; teacher-forced against the fp32 oracle on our own tokens."""
+    import vaura_b200.sampler as vs
+
+    monkeypatch.setattr(vs, "PAGE_SIZE", 16)
+    tiny_model.sampler._buffers.clear()  # page tables are cached per row count
+    B, T = 20, 40
+    feats = make_avclip_features(B, 57)
+    try:
+        out = tiny_model.generate(frames=feats.cuda(), max_new_tokens=T, use_sampling=False, prompt_is_encoded=True,
+                                  return_sampled_indices=True, check=True, _return_logits=True, _decode_audio=False)
+    finally:
+        tiny_model.sampler._buffers.clear()
+    codes = out["sampled_indices"].cpu()
+    seq, _ = vo.build_pattern_sequence(codes, 1024)
+    ref = tiny_oracle.forward_full(seq[..., :-1], feats.reshape(B, 32, 768))
+    mine = out["_logits"][1:].cpu().permute(1, 2, 0, 3)
+    assert rel_err(mine, ref) < BF16_LOGIT_TOL
+
+
 def test_standalone_ops_match_torch_fp32():
     """Op-level entry points of the C ABI (the kernels bench.py times for the roofline)."""
     import ctypes as C

@@ -76,3 +76,19 @@ def test_sampling_distribution_chi_square():
         chi2 = float((((counts[keep] - exp) ** 2) / exp)[big].sum())
         dof = int(big.sum()) - 1
         assert chi2 < dof + 5 * (2 * dof) ** 0.5 + 10, (kw, chi2, dof)
+
+
+def test_top_k_keeps_ties_of_the_kth_value():
+    """utils/utils.py:139-160 masks `probs < k-th value`: every tie of the k-th largest survives.  Exercises the radix
+    select's early exit (a candidate that keeps exactly k values) and its full-length path (ties: no such candidate)."""
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(4, 9, 1024, generator=g) * 2
+    logits[0] = 0.25                                   # all equal: every value ties with the k-th
+    logits[1, :, 100:140] = logits[1].max() + 1.0      # 40 equal maxima, k = 16 cuts through them
+    for k in (1, 16, 256, 1023):
+        _, probs = sample_logits(logits.cuda(), temp=1.0, top_k=k, return_probs=True)
+        ref = vo.filtered_probs(logits.reshape(-1, 1024), 1.0, k, 0.0).reshape(4, 9, 1024)
+        assert torch.equal(probs.cpu() > 0, ref > 0), k
+        assert torch.allclose(probs.cpu(), ref.float(), atol=2e-7), k
+    _, probs = sample_logits(logits.cuda(), temp=1.0, top_k=16, return_probs=True)
+    assert int((probs[0, 0] > 0).sum()) == 1024 and int((probs[1, 0] > 0).sum()) == 40
