@@ -477,13 +477,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // the narrow layers) overlaps the TMA / MMA mainloop of tile i+1, and barrier init / TMEM allocation / launch happen
 // once per layer instead of once per 128-row tile.  Same tile arithmetic as gemm_tc_kernel (KSUB = 1, no split-K).
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi>
+// KSUB > 1: a stage holds KSUB K blocks of each operand (KSUB activation sub-tiles, then KSUB weight sub-tiles), loaded by
+// ONE 4-D tensor box per operand (maps from make_map_kblocks) - for channel counts that force a narrow K block (Cin = 96:
+// 32-wide blocks) the copies and barrier round trips per tap drop from 3 to 1.
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int KSUB = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape g,
                           const typename Epi::Params ep, const int m_tiles, const int n_tiles) {
   constexpr int SW = BLOCK_K * 2;
   constexpr int TILE_M = kTileM;
-  constexpr int A_BYTES = TILE_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int A_BYTES = TILE_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, STAGE_BYTES = KSUB * (A_BYTES + B_BYTES);
   constexpr int ACC_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;  // per accumulator buffer
   constexpr int TMEM_COLS = 2 * ACC_COLS;
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "stage buffers must stay 1024B aligned for the swizzle");
@@ -497,7 +500,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int iters = g.ntaps * g.kblocks;
+  const int kgroups = g.kblocks / KSUB;  // stages per tap
+  const int iters = g.ntaps * kgroups;
   const int zdim = g.batch * g.nphase;
   const int ntiles = m_tiles * n_tiles * zdim;
 
@@ -543,12 +547,17 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       for (int it = 0; it < iters; ++it, ++git) {
         const int s = git % STAGES;
         const uint32_t ph = (git / STAGES) & 1;
-        const int tap = it / g.kblocks, kb = it % g.kblocks;
+        const int tap = it / kgroups, kb = it % kgroups;
         uint8_t* ss = smem + s * STAGE_BYTES;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx_elect(&full[s], STAGE_BYTES);
-        tma_load_3d_elect(ss + A_BYTES, &tmB, &full[s], kb * BLOCK_K, n0, phase * g.ntaps + tap);
-        tma_load_3d_elect(ss, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
+        if (KSUB == 1) {
+          tma_load_3d_elect(ss + A_BYTES, &tmB, &full[s], kb * BLOCK_K, n0, phase * g.ntaps + tap);
+          tma_load_3d_elect(ss, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
+        } else {
+          tma_load_4d_elect(ss + KSUB * A_BYTES, &tmB, &full[s], 0, n0, kb * KSUB, phase * g.ntaps + tap);
+          tma_load_4d_elect(ss, &tmA, &full[s], 0, m0 + g.tap_off[phase * g.ntaps + tap], kb * KSUB, b);
+        }
       }
     }
     __syncwarp();
@@ -566,9 +575,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         mbar_wait(&full[s], ph);
         tcgen05_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) umma_bf16_f16_elect(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        for (int sub = 0; sub < KSUB; ++sub) {
+          const uint64_t adesc = make_smem_desc<SW>(a_addr + sub * A_BYTES),
+                         bdesc = make_smem_desc<SW>(a_addr + KSUB * A_BYTES + sub * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_bf16_f16_elect(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | sub | k) != 0);
+        }
         umma_commit_elect(&empty[s]);
       }
       umma_commit_elect(&tfull[ab]);
@@ -1266,15 +1280,16 @@ static bool make_map(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows
 // [outer][rows][K] bf16 seen as (64, rows, K / 64, outer): one box = nblk K blocks of box_rows rows, landing in shared
 // memory as nblk consecutive 128B-swizzled [box_rows x 64] sub-tiles
 static bool make_map_kblocks(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, uint64_t outer, uint64_t row_stride_el,
-                             uint64_t outer_stride_el, int box_rows, int nblk) {
+                             uint64_t outer_stride_el, int box_rows, int nblk, int block_k = 64, bool f16 = false) {
   EncodeTiledFn fn = encode_fn();
-  if (!fn || K % 64) return false;
-  cuuint64_t dims[4] = {64, rows, K / 64, outer};
-  cuuint64_t strides[3] = {row_stride_el * 2, 64 * 2, outer_stride_el * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, (cuuint32_t)nblk, 1};
+  if (!fn || K % block_k || (block_k != 64 && block_k != 32)) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)block_k, rows, K / block_k, outer};
+  cuuint64_t strides[3] = {row_stride_el * 2, (cuuint64_t)block_k * 2, outer_stride_el * 2};
+  cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)box_rows, (cuuint32_t)nblk, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128, int KSUB = 1>
@@ -1302,12 +1317,13 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const
   cfg.numAttrs = g.pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, g, ep);
 }
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int KSUB = 1>
 static cudaError_t launch_tc_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const TcShape& g,
                                         const typename Epi::Params& ep, int m_tiles, int n_tiles, cudaStream_t st) {
-  constexpr int smem = STAGES * (kTileM * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+  constexpr int smem = STAGES * KSUB * (kTileM * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
   static_assert(smem <= 227 * 1024, "stage ring exceeds shared memory");
-  auto kern = gemm_tc_persistent_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi>;
+  if (g.kblocks % KSUB) return cudaErrorInvalidValue;
+  auto kern = gemm_tc_persistent_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, KSUB>;
   static int sms = 0;
   if (!sms) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1350,8 +1366,19 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cu
   EpiConv::Params ep{a.bias, a.alpha, a.residual, a.out_raw, a.out_act, a.Tq, a.Tout, a.Cout, a.ostride};
   const int mt = (a.Tq + kTileM - 1) / kTileM, nt = a.Cout / bn;
   // persistent tile loop (double-buffered TMEM accumulator) unless VAURA_CONV_PERSISTENT=0
-  static int persistent = -1;
+  static int persistent = -1, ksub3 = -1;
   if (persistent < 0) { const char* e = getenv("VAURA_CONV_PERSISTENT"); persistent = !(e && e[0] == '0'); }
+  if (ksub3 < 0) { const char* e = getenv("VAURA_CONV_KSUB"); ksub3 = !(e && e[0] == '0'); }
+  // 96 input channels = three 32-wide K blocks per tap: one stage (one tensor box per operand) per tap
+  if (persistent && ksub3 && bk == 32 && a.Cin == 96 && (bn == 96 || bn == 32 || bn == 16)) {
+    CUtensorMap ta4, tb4;
+    if (!make_map_kblocks(&ta4, a.in, a.Cin, a.Tin, B, a.Cin, (uint64_t)a.Tin * a.Cin, kTileM, 3, 32, true) ||
+        !make_map_kblocks(&tb4, a.W, a.Cin, a.Cout, (uint64_t)a.ntaps * a.nphase, a.Cin, (uint64_t)a.Cout * a.Cin, bn, 3, 32, true))
+      return cudaErrorUnknown;
+    if (bn == 96) return launch_tc_persistent<96, 32, 4, 0, EpiConv, 3>(ta4, tb4, g, ep, mt, nt, st);
+    if (bn == 32) return launch_tc_persistent<32, 32, 4, 0, EpiConv, 3>(ta4, tb4, g, ep, mt, nt, st);
+    return launch_tc_persistent<16, 32, 4, 0, EpiConv, 3>(ta4, tb4, g, ep, mt, nt, st);
+  }
 #define TC_CASE(BN, BK, ST)                                                                                    \
   if (bn == BN && bk == BK)                                                                                    \
     return persistent ? launch_tc_persistent<BN, BK, ST, 0, EpiConv>(ta, tb, g, ep, mt, nt, st)                \
