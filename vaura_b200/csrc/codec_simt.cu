@@ -120,35 +120,69 @@ cudaError_t launch_conv_gemm(const ConvArgs& a, int B, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// final conv (C -> 1, k=7, pad 3) + tanh; weights fp32 [7][C]
+// final conv (C -> 1, k=7, pad 3) + tanh; weights fp32 [7][C].
+// One warp walks kOutPerWarp consecutive outputs of a clip: lane l holds channels [4l, 4l+4) (C <= 128: one coalesced
+// 8-byte load per lane per input row), every input row feeds the seven outputs it overlaps through seven rotating
+// partial sums, and the output that has seen its last row is reduced across the warp and written.  The input is read
+// once, row-contiguously (the per-output version read every row seven times through strided 16-byte pieces).
+constexpr int kOutPerWarp = 128;
 __global__ void __launch_bounds__(256) conv_out_tanh_kernel(const __half* __restrict__ in, const float* __restrict__ W,
                                                             const float* __restrict__ bias, __half* __restrict__ wav, int T,
                                                             int C) {
-  extern __shared__ float ws[];  // [7][C]
-  for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) ws[i] = W[i];
-  __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-  if (t >= T) return;
-  float s = bias[0];
-  for (int j = 0; j < 7; ++j) {
-    const int ti = t + j - 3;
-    if (ti < 0 || ti >= T) continue;
-    const uint4* p = reinterpret_cast<const uint4*>(in + ((size_t)b * T + ti) * C);
-    for (int c8 = 0; c8 < C / 8; ++c8) {
-      const uint4 raw = p[c8];
-      const __half2* h = reinterpret_cast<const __half2*>(&raw);
-      const float* w = ws + j * C + c8 * 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int t0 = (blockIdx.x * (blockDim.x >> 5) + warp) * kOutPerWarp;
+  if (t0 >= T) return;
+  const int t1 = min(t0 + kOutPerWarp, T);
+  const bool live = 4 * lane < C;
+  float w[7][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) s = fmaf(__low2float(h[e]), w[2 * e], fmaf(__high2float(h[e]), w[2 * e + 1], s));
+  for (int j = 0; j < 7; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) w[j][e] = live ? W[j * C + 4 * lane + e] : 0.f;
+  const float b0 = bias[0];
+  const __half* base = in + (size_t)b * T * C + 4 * lane;
+  // acc[j]: partial sum of output (r - j + 3) after row r has been added, i.e. acc[0] is the youngest output
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  constexpr int U = 8;  // rows in flight
+  for (int r0 = t0 - 3; r0 < t1 + 3; r0 += U) {
+    uint2 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + u;
+      raw[u] = (live && r >= 0 && r < T && r < t1 + 3) ? __ldg(reinterpret_cast<const uint2*>(base + (size_t)r * C)) : make_uint2(0u, 0u);
     }
+    float done[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const __half2 h0 = *reinterpret_cast<const __half2*>(&raw[u].x), h1 = *reinterpret_cast<const __half2*>(&raw[u].y);
+      const float x0 = __low2float(h0), x1 = __high2float(h0), x2 = __low2float(h1), x3 = __high2float(h1);
+      // row r is tap j of output r - j + 3: the oldest live output (tap 6) completes with this row
+#pragma unroll
+      for (int j = 0; j < 7; ++j) acc[j] = fmaf(x0, w[j][0], fmaf(x1, w[j][1], fmaf(x2, w[j][2], fmaf(x3, w[j][3], acc[j]))));
+      done[u] = acc[6];
+#pragma unroll
+      for (int j = 6; j > 0; --j) acc[j] = acc[j - 1];
+      acc[0] = 0.f;
+    }
+    // the U outputs completed by these rows: U interleaved butterfly reductions, lane u writes output r0 + u - 3
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u) done[u] += __shfl_xor_sync(0xffffffffu, done[u], o);
+    float mine = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) mine = lane == u ? done[u] : mine;
+    const int t = r0 + lane - 3;
+    if (lane < U && t >= t0 && t < t1) wav[(size_t)b * T + t] = __float2half_rn(tanhf(mine + b0));
   }
-  wav[(size_t)b * T + t] = __float2half_rn(tanhf(s));
 }
 
 cudaError_t launch_conv_out_tanh(const __half* in, const float* W, const float* bias, __half* wav, int B, int T, int C,
                                  cudaStream_t st) {
-  if (C % 8 != 0) return cudaErrorInvalidValue;
-  conv_out_tanh_kernel<<<dim3((T + 255) / 256, B), 256, 7 * C * sizeof(float), st>>>(in, W, bias, wav, T, C);
+  if (C % 8 != 0 || C > 128) return cudaErrorInvalidValue;
+  const int warps = (T + kOutPerWarp - 1) / kOutPerWarp;
+  conv_out_tanh_kernel<<<dim3((warps + 7) / 8, B), 256, 0, st>>>(in, W, bias, wav, T, C);
   return cudaGetLastError();
 }
 
