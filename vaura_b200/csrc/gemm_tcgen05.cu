@@ -218,7 +218,21 @@ struct EpiConv {
     __half* out_act;
     int Tq, Tout, Cout, ostride;
   };
+  // the 16 residual values of a chunk (zeros when the layer has none): the persistent kernel requests them before it
+  // waits for the accumulator, so that their latency overlaps the tile's MMAs
+  __device__ static void load_residual(const Params& p, int b, int phase, int m, int n0, uint4& r0, uint4& r1) {
+    r0 = r1 = make_uint4(0u, 0u, 0u, 0u);
+    if (!p.residual || m >= p.Tq || n0 >= p.Cout) return;
+    const size_t base = ((size_t)b * p.Tout + (size_t)m * p.ostride + phase) * p.Cout + n0;
+    r0 = *reinterpret_cast<const uint4*>(p.residual + base);
+    r1 = *reinterpret_cast<const uint4*>(p.residual + base + 8);
+  }
   __device__ static void apply(const Params& p, int b, int phase, int m, int n0, float (&v)[16]) {
+    uint4 r0, r1;
+    load_residual(p, b, phase, m, n0, r0, r1);
+    apply(p, b, phase, m, n0, v, r0, r1);
+  }
+  __device__ static void apply(const Params& p, int b, int phase, int m, int n0, float (&v)[16], const uint4& r0, const uint4& r1) {
     if (m >= p.Tq || n0 >= p.Cout) return;
     const size_t base = ((size_t)b * p.Tout + (size_t)m * p.ostride + phase) * p.Cout + n0;
 #pragma unroll
@@ -227,8 +241,6 @@ struct EpiConv {
       v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
     }
     if (p.residual) {
-      const uint4 r0 = *reinterpret_cast<const uint4*>(p.residual + base);
-      const uint4 r1 = *reinterpret_cast<const uint4*>(p.residual + base + 8);
       const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
       const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
 #pragma unroll
@@ -597,15 +609,25 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       int m0, n0, b, phase;
       tile_coords(t, m0, n0, b, phase);
       const int ab = tc & 1;
+      const int m = m0 + q * 32 + lane;
+      // residual rows of this warp's chunks: in flight while the tile's MMAs run
+      uint4 res[kHalf][2];
+#pragma unroll
+      for (int i = 0; i < kHalf; ++i) {
+        const int c = c_begin + 16 * i;
+        if (c < c_end) Epi::load_residual(ep, b, phase, m, n0 + c, res[i][0], res[i][1]);
+      }
       mbar_wait(&tfull[ab], (tc >> 1) & 1);
       tcgen05_fence_after();
-      const int m = m0 + q * 32 + lane;
       const uint32_t tacc = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c = c_begin; c < c_end; c += 16) {
-        float v[16];
-        tmem_ld16(tacc + c, v);
-        Epi::apply(ep, b, phase, m, n0 + c, v);
+#pragma unroll
+      for (int i = 0; i < kHalf; ++i) {
+        const int c = c_begin + 16 * i;
+        if (c < c_end) {
+          float v[16];
+          tmem_ld16(tacc + c, v);
+          Epi::apply(ep, b, phase, m, n0 + c, v, res[i][0], res[i][1]);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
