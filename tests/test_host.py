@@ -215,3 +215,20 @@ def test_cluster_stream_tile_is_an_mma_a_fragment():
                 (g, 2 * tq + 8), (g, 2 * tq + 9), (g + 8, 2 * tq + 8), (g + 8, 2 * tq + 9)]
         got = [(int(v) // 1536 - row0, int(v) % 1536 - col0) for v in tile[lane]]
         assert got == want
+
+
+def test_precision_rule_and_environment_override(monkeypatch):
+    """AUTO: fp32 activations below 16 sequence rows, bf16 from 16 (same rule as csrc/cabi.cu); VAURA_PRECISION overrides
+    AUTO only, an explicit precision always wins."""
+    from vaura_b200 import _cabi
+    from vaura_b200.sampler import resolve_precision
+
+    monkeypatch.delenv("VAURA_PRECISION", raising=False)
+    assert resolve_precision(_cabi.PRECISION_AUTO, 1) == _cabi.PRECISION_FP32ACT
+    assert resolve_precision(_cabi.PRECISION_AUTO, 15) == _cabi.PRECISION_FP32ACT
+    assert resolve_precision(_cabi.PRECISION_AUTO, 16) == _cabi.PRECISION_BF16
+    monkeypatch.setenv("VAURA_PRECISION", "bf16")
+    assert resolve_precision(_cabi.PRECISION_AUTO, 4) == _cabi.PRECISION_BF16
+    assert resolve_precision(_cabi.PRECISION_FP32ACT, 4) == _cabi.PRECISION_FP32ACT
+    monkeypatch.setenv("VAURA_PRECISION", "fp32")
+    assert resolve_precision(_cabi.PRECISION_AUTO, 64) == _cabi.PRECISION_FP32ACT

@@ -23,9 +23,16 @@ PAGE_SIZE = int(os.environ.get("VAURA_PAGE_SIZE", "32"))
 
 
 def resolve_precision(precision: int, rows: int) -> int:
-    """Same rule as csrc/cabi.cu: AUTO -> tcgen05/bf16 path from 16 sequence rows, fp32-activation path below."""
+    """Same rule as csrc/cabi.cu: AUTO -> tcgen05/bf16 path from 16 sequence rows, fp32-activation path below.
+
+    ``VAURA_PRECISION=bf16|fp32`` overrides AUTO: at 3...15 rows the bf16 path (one fused kernel per step, ~1.0-1.1 ms)
+    is 1.2-3x faster than the fp32-activation paths (1.2-2.9 ms, profiles/scripts/rows_sweep.py) at bf16 tolerance
+    instead of bit-exact greedy tokens; at 1-2 rows the fp32-activation cluster kernel is both exact and 3x faster."""
     if precision != _cabi.PRECISION_AUTO:
         return precision
+    env = os.environ.get("VAURA_PRECISION", "").lower()
+    if env in ("bf16", "fp32"):
+        return _cabi.PRECISION_BF16 if env == "bf16" else _cabi.PRECISION_FP32ACT
     return _cabi.PRECISION_BF16 if rows >= 16 else _cabi.PRECISION_FP32ACT
 
 
