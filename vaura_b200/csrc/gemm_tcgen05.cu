@@ -320,7 +320,9 @@ struct EpiLinear {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float a0 = v[4 * i], b0 = v[4 * i + 1], a1 = v[4 * i + 2], b1 = v[4 * i + 3];
-        h[i] = __floats2bfloat162_rn(a0 / (1.f + expf(-a0)) * b0, a1 / (1.f + expf(-a1)) * b1);
+        // SiLU(a) * b; fast division / exponential: the result is rounded to bf16 (the IEEE division's out-of-line slow
+        // path is a branch per quotient, which serialises the eight of a chunk)
+        h[i] = __floats2bfloat162_rn(__fdividef(a0, 1.f + __expf(-a0)) * b0, __fdividef(a1, 1.f + __expf(-a1)) * b1);
       }
       *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)m * p.ldo + (n0 >> 1)) = o;
     } else {  // EPI_QKV
@@ -1138,7 +1140,8 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   };
 
   EpiLinear::Params ep{};
-  ep.R = R; ep.rope = a.rope; ep.kv = a.kv; ep.state = a.state; ep.pos0 = 0; ep.npos = 1; ep.d_model = D;
+  // the position is known here: no dependent load of state->offset in front of the RoPE / KV-append epilogue
+  ep.R = R; ep.rope = a.rope; ep.kv = a.kv; ep.state = nullptr; ep.pos0 = p; ep.npos = 1; ep.d_model = D;
   ep.perm_S = 0; ep.perm_V = 0;
 
   // The RMSNorm after a split-K GEMM (wo, w2) needs every tile's reductions, the GEMM after it needs every row's norm:
