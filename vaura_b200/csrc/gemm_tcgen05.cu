@@ -288,6 +288,47 @@ struct EpiLinear {
     int pos0, npos, layer, d_model;
     int atomic;
   };
+  // what the RoPE / KV-append epilogue of one 16-column chunk reads from global memory besides the accumulator: eight
+  // (cos, sin) pairs and the destination row in the paged cache.  The fused step kernel requests them before it waits for
+  // the accumulator (their L2 latency overlaps the tile's MMAs).
+  struct QkvPre {
+    float4 cs[4];
+    size_t dst;  // element offset into q (section 0) or the K/V pages (sections 1, 2)
+  };
+  __device__ static void prefetch_qkv(const Params& p, int m, int n0, QkvPre& q) {
+    const int D = p.d_model, sec = n0 / D, within = n0 % D;
+    const int hd = within / kHeadDim, e = within % kHeadDim;
+    const int b = m / p.npos, j = m % p.npos;
+    const int pos = (p.state ? p.state->offset - p.npos : p.pos0) + j;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q.cs[i] = make_float4(1.f, 0.f, 1.f, 0.f);
+    q.dst = 0;
+    if (m >= p.R || n0 >= p.N) return;
+    if (sec != 2) {
+      const float4* cs = reinterpret_cast<const float4*>(p.rope + ((size_t)pos * (kHeadDim / 2) + (e >> 1)) * 2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q.cs[i] = cs[i];
+    }
+    q.dst = sec == 0 ? (size_t)m * D + within : p.kv.row(p.layer, sec - 1, b, pos, hd) + e;
+  }
+  __device__ static void apply_qkv(const Params& p, int m, int n0, float (&v)[16], const QkvPre& q) {
+    if (m >= p.R || n0 >= p.N) return;
+    const int sec = n0 / p.d_model;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // two (cos,sin) pairs per float4; identity for the V section
+      const float4 c = q.cs[i];
+      const float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
+      v[4 * i] = x0 * c.x - x1 * c.y; v[4 * i + 1] = x1 * c.x + x0 * c.y;
+      v[4 * i + 2] = x2 * c.z - x3 * c.w; v[4 * i + 3] = x3 * c.z + x2 * c.w;
+    }
+    uint4 o[2];
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    __nv_bfloat16* dst = (sec == 0 ? p.out_bf16 : reinterpret_cast<__nv_bfloat16*>(p.kv.pages)) + q.dst;
+    *reinterpret_cast<uint4*>(dst) = o[0];
+    *reinterpret_cast<uint4*>(dst + 8) = o[1];
+  }
   __device__ static void apply(const Params& p, int /*b*/, int /*phase*/, int m, int n0, float (&v)[16]) {
     if (m >= p.R || n0 >= p.N) return;
     if (p.mode == EPI_STORE) {
@@ -787,20 +828,27 @@ __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap
     umma_commit_elect(pp.tmem_full);
     __syncwarp();
   } else {
-    mbar_wait(pp.tmem_full, pp.tiles & 1);
-    tcgen05_fence_after();
-    if (warp == 2 && lane == 0) dstamp(24);
     const int q = warp & 3;
     // UMMA M = 128: accumulator row i sits in lane i; M = 64: rows 16q..16q+15 sit in lanes 32q..32q+15
     const int m = TM == 128 ? q * 32 + lane : q * 16 + lane;
     const bool row_ok = TM == 128 || lane < 16;
     constexpr int kChunks = BN / 16, kHalf = (kChunks + 1) / 2;
     const int c_begin = (warp - 2) < 4 ? 0 : kHalf * 16, c_end = (warp - 2) < 4 ? kHalf * 16 : BN;
+    // wqkv tiles (BN = 32: one chunk per warp): RoPE pairs and the cache row are requested before the accumulator wait
+    const bool qkv_pre = BN == 32 && ep.mode == EPI_QKV;
+    EpiLinear::QkvPre pre;
+    if (qkv_pre && row_ok) EpiLinear::prefetch_qkv(ep, m, n0 + c_begin, pre);
+    mbar_wait(pp.tmem_full, pp.tiles & 1);
+    tcgen05_fence_after();
+    if (warp == 2 && lane == 0) dstamp(24);
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 16) {
       float v[16];
       tmem_ld16(pp.tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
-      if (row_ok) EpiLinear::apply(ep, 0, 0, m, n0 + c, v);
+      if (row_ok) {
+        if (qkv_pre) EpiLinear::apply_qkv(ep, m, n0 + c, v, pre);
+        else EpiLinear::apply(ep, 0, 0, m, n0 + c, v);
+      }
     }
     tcgen05_fence_before();
     if (warp == 2 && lane == 0) dstamp(25);
