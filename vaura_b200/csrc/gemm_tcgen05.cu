@@ -932,8 +932,14 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       float* red = scratch;
       float* hrow = a.h + (size_t)cta * D;
       const int n4 = D >> 2;
-      float4 v[2];
+      float4 v[2], gw[2];
       float ss = 0.f;
+      // the norm weights do not depend on the row: requested first, in flight together with the row
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = tid + i * kGemmThreads;
+        gw[i] = c < n4 ? __ldg(reinterpret_cast<const float4*>(w) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int c = tid + i * kGemmThreads;
@@ -970,7 +976,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       for (int i = 0; i < 2; ++i) {
         const int c = tid + i * kGemmThreads;
         if (c < n4) {
-          const float4 g = __ldg(reinterpret_cast<const float4*>(w) + c);
+          const float4 g = gw[i];
           uint2 o;
           *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v[i].x * rs * g.x, v[i].y * rs * g.y);
           *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v[i].z * rs * g.z, v[i].w * rs * g.w);
