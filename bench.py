@@ -1,17 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the V-AURA generation hot path (BASELINE.json metric: generated audio-sec/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload b64|b64_cfg|b1|b1_cfg] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload b64|b64_cfg|b1|b1_cfg|long_b1|dataset]
+                    [--impl reference] [--no-sub] [--no-cpu-baseline]
 
 One "step" = one pass of the hot path over one batch of synthetic clips: VAURAModel.generate(...)
 (228 device-side decode steps + sampling + codec decode) on `batch` clips of 2.56 s.  Under torchrun
-every rank runs the same per-GPU workload on its own clips (data parallel, weak scaling, no collective
-in the timed path; the final waveform gather is outside the hot loop).
+every rank runs the same per-GPU workload on its own clips (data parallel, weak scaling); the one exchange
+step of the path - the NCCL all-gather of the fp16 waveforms - is inside the timed region of every
+step at N > 1.
 
 Printed JSON (rank 0, one line): value = whole-job audio-seconds per second with inputs resident in HBM;
 e2e = the same through the public API with pinned host inputs and the waveform read back to the host;
-roofline = the dominant kernel timed alone with CUDA events against MEASURED_PEAKS.json;
-cpu_baseline = the oracle port of the reference's algorithm timed on this box's host cores.
+roofline = the dominant kernel (one launch = one decode step) timed with CUDA events against MEASURED_PEAKS.json;
+cpu_baseline = the oracle port of the reference's algorithm (no KV cache, fp32) run for one whole clip on this box's
+host cores.  At N = 1 the default workload also carries sub-records for the other halves of BASELINE's metric:
+`b1` (one clip, batch 1), `b64_cfg` (128 sequence rows) and `long_b1` (10.24 s clip by overlapping windows, config 3).
+
+`--workload dataset` is BASELINE config 4 in miniature: `driver.generate_dataset` over --clips-per-gpu x N clips
+sharded by clip index, ending in the waveform all-gather, all inside the timed region.
+
+`--impl reference` times the reference's own algorithm on the host cores: ONE real 2.56 s clip end to end (228
+full-prefix forwards, llama.py:445-517 re-run per step as vaura_model.py:502-547 does, then the CPU codec decode),
+cut into K consecutive slices that are reported as the K steps.
 """
 from __future__ import annotations
 
@@ -41,6 +52,12 @@ WORKLOADS = {
     # the reference's own generate settings (configs/generate_vgg.yaml: cfg_scale 6.0) at batch 1: two sequence rows
     "b1_cfg": dict(batch=1, T=220, use_sampling=True, top_k=128, temp=1.0, cfg_scale=6.0,
                    name="one 2.56 s clip, batch 1, top-k 128 sampling, classifier-free guidance 6.0 (2 sequence rows)"),
+    # BASELINE.json configs[2]: one 10.24 s clip, batch 1, overlapping 2.56 s windows (scripts/generate.py:327-370)
+    "long_b1": dict(batch=1, T=220, use_sampling=True, top_k=128, temp=1.0, cfg_scale=1.0, duration=10.24,
+                    name="one 10.24 s clip, batch 1, 13 overlapping 2.56 s windows (stride 0.64 s), top-k 128 sampling"),
+    # BASELINE.json configs[3] in miniature: clips sharded over the ranks by index + waveform all-gather
+    "dataset": dict(batch=64, T=220, use_sampling=True, top_k=128, temp=1.0, cfg_scale=1.0,
+                    name="synthetic clip set sharded data-parallel by clip index, batch 64 per GPU, NCCL waveform all-gather"),
 }
 
 
@@ -94,33 +111,82 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_sample(threads: int):
-    """Reference algorithm on host cores: the reference has no KV cache and re-runs the whole prefix every
-    step (models/vaura_model.py:502-547).  Bounded sample: the oracle's full-prefix forward
-    (oracle/vaura_oracle.py: forward_full, restating llama.py:445-517) at prefix lengths 1/76/152/228,
-    integrated piecewise-linearly over the 228 steps of one 2.56 s clip (B=1, fp32)."""
-    from oracle import vaura_oracle as vo
-    from vaura_b200.synthetic import FULL_SAMPLER, make_avclip_features, make_sampler_state_dict
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (oracle port; /root/reference does not exist on the GPU box)
+# ---------------------------------------------------------------------------------------------------------------------
+class CpuReferenceClip:
+    """One real 2.56 s clip, B = 1, greedy, exactly as the reference executes it: no KV cache, every step re-runs the
+    whole prefix through the 24 layers in fp32 (models/vaura_model.py:502-547 -> llama.py:445-517, restated by
+    oracle/vaura_oracle.py: forward_full), the mask-fix and write-back of :536-544, then the codec decode on the CPU
+    (models/modules/dac/model.py:41-48, restated by oracle/dac_oracle.py).  `run_steps` advances the loop so that the
+    caller can cut the clip into timed slices."""
 
-    torch.set_num_threads(threads)
-    oracle = vo.SamplerOracle(make_sampler_state_dict(FULL_SAMPLER, 0), FULL_SAMPLER)
-    feats = make_avclip_features(1, 1).reshape(1, 32, 768)
-    g = torch.Generator().manual_seed(0)
-    seq = torch.randint(0, 1024, (1, 9, 229), generator=g)
-    with torch.no_grad():
-        oracle.forward_full(seq[..., :8], feats)  # warm-up
-        pts = []
-        for n in (1, 76, 152, 228):
-            t0 = time.perf_counter()
-            oracle.forward_full(seq[..., :n], feats)
-            pts.append((n, time.perf_counter() - t0))
-    total = 0.0
-    for (n0, t0), (n1, t1) in zip(pts[:-1], pts[1:]):
-        for n in range(n0, n1):
-            total += t0 + (t1 - t0) * (n - n0) / (n1 - n0)
-    total += pts[-1][1]
-    audio = 220 * AUDIO_SEC_PER_TOKEN
-    return audio / total, total, pts
+    def __init__(self, threads: int):
+        from oracle import vaura_oracle as vo
+        from oracle.dac_oracle import DacDecodeOracle
+        from vaura_b200.synthetic import (FULL_CODEC, FULL_SAMPLER, make_avclip_features, make_codec_state_dict,
+                                          make_sampler_state_dict)
+
+        torch.set_num_threads(threads)
+        self.vo = vo
+        self.oracle = vo.SamplerOracle(make_sampler_state_dict(FULL_SAMPLER, 0), FULL_SAMPLER)
+        self.codec = DacDecodeOracle(make_codec_state_dict(FULL_CODEC, 100), FULL_CODEC)
+        self.feats = make_avclip_features(1, 1).reshape(1, 32, 768)
+        self.T = 220
+        codes = torch.full((1, 9, self.T), vo.UNKNOWN, dtype=torch.long)
+        self.seq, self.mask = vo.build_pattern_sequence(codes, 1024)
+        self.S = self.seq.shape[-1]
+        self.offset = 1
+        self.total_steps = self.S - 1
+
+    def warm(self, n: int):
+        with torch.no_grad():
+            for _ in range(max(1, n)):
+                self.oracle.forward_full(torch.full((1, 9, 8), 1024, dtype=torch.long), self.feats)
+
+    def run_steps(self, n: int) -> int:
+        done = 0
+        with torch.no_grad():
+            while done < n and self.offset < self.S:
+                o = self.offset
+                logits = self.oracle.forward_full(self.seq[..., :o], self.feats)[:, :, -1]  # last position only is used
+                nxt = torch.argmax(logits, dim=-1)
+                nxt[:, ~self.mask[:, o]] = 1024
+                cur = self.seq[..., o]
+                self.seq[..., o] = torch.where(cur == self.vo.UNKNOWN, nxt, cur)
+                self.offset += 1
+                done += 1
+        return done
+
+    def decode_audio(self):
+        with torch.no_grad():
+            return self.codec.decode(self.vo.revert_pattern_sequence(self.seq, self.T))
+
+
+def cpu_reference_clip(threads: int, slices: int, warmup: int):
+    """-> (audio-s/s, total seconds, per-slice seconds, codec seconds)."""
+    clip = CpuReferenceClip(threads)
+    clip.warm(warmup)
+    slices = max(1, min(slices, clip.total_steps))
+    per, t_slices = [], []
+    base, extra = divmod(clip.total_steps, slices)
+    t_all = time.perf_counter()
+    codec_s = 0.0
+    for i in range(slices):
+        t0 = time.perf_counter()
+        clip.run_steps(base + (1 if i < extra else 0))
+        if i == slices - 1:
+            tc = time.perf_counter()
+            wav = clip.decode_audio()
+            codec_s = time.perf_counter() - tc
+            assert wav.shape == (1, 1, 220 * 512)
+        t_slices.append(time.perf_counter() - t0)
+    total = time.perf_counter() - t_all
+    return 220 * AUDIO_SEC_PER_TOKEN / total, total, t_slices, codec_s
+
+
+CPU_SAMPLE = ("oracle port of the reference's own loop, one whole 2.56 s clip, B=1, greedy, fp32: 228 full-prefix forwards "
+              "(no KV cache, vaura_model.py:502-547) + CPU codec decode; measured, not extrapolated")
 
 
 def run_reference(args, rank, world):
@@ -128,24 +194,26 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     wl = WORKLOADS[args.workload]
-    vals = []
-    for _ in range(max(1, args.steps)):
-        v, total, pts = cpu_reference_sample(threads)
-        vals.append(v)
-    value = sum(vals) / len(vals)
+    steps = max(1, args.steps)
+    value, total, t_slices, codec_s = cpu_reference_clip(threads, steps, args.warmup)
     line = {
         "impl": "reference", "metric": "generated audio-sec/sec", "value": value, "unit": "audio-s/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * 220 * AUDIO_SEC_PER_TOKEN / value,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "note": "CPU reference algorithm, throughput per clip is batch-independent"},
-        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                         "sample": "oracle port of the reference's no-KV-cache loop: full-prefix forwards at prefix "
-                                   "1/76/152/228 integrated over 228 steps, B=1, fp32"},
+        "config": {"workload": wl["name"],
+                   "note": "CPU reference algorithm: per-clip cost is batch-independent on the host cores, so one clip is the "
+                           "bounded sample; the K steps are K consecutive slices of its 228 decode iterations (the last one "
+                           "includes the codec decode)",
+                   "clip_seconds": total, "codec_seconds": codec_s, "slices": len(t_slices)},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": CPU_SAMPLE},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,6 +222,8 @@ def main():
     ap.add_argument("--workload", default="b64", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the b1 / b64_cfg / long_b1 sub-records")
+    ap.add_argument("--clips-per-gpu", type=int, default=128, help="dataset workload: clips per rank and step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -162,11 +232,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import numpy as np
     import torch.distributed as dist
 
-    from tests.test_gpu_parity import build_model
     from vaura_b200 import _cabi
-    from vaura_b200.synthetic import FULL_CODEC, FULL_SAMPLER, make_avclip_features
+    from vaura_b200.driver import gather_waveforms, generate_dataset, generate_long
+    from vaura_b200.synthetic import FULL_CODEC, FULL_SAMPLER, build_model, make_avclip_features
     from vaura_b200.weights import codec_flops, sampler_step_bytes
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU path"
@@ -177,47 +248,229 @@ def main():
     lib = _cabi.load()
     wl = WORKLOADS[args.workload]
     B, T = wl["batch"], wl["T"]
+    d = FULL_SAMPLER
     model = build_model(FULL_SAMPLER, FULL_CODEC, device=str(dev))
     model.seed = 1234
-    kw = dict(max_new_tokens=T, use_sampling=wl["use_sampling"], temp=wl["temp"], top_k=wl["top_k"], top_p=0.0,
-              cfg_scale=wl["cfg_scale"], prompt_is_encoded=True)
-    # rank r owns clips [r*B, (r+1)*B) of every step; features depend only on the clip index
-    feats_host = make_avclip_features(B, 2 + rank).pin_memory()
-    feats_dev = feats_host.to(dev)
-    clip_ids = torch.arange(rank * B, (rank + 1) * B, dtype=torch.int32)
-    wav_host = torch.empty(B, 1, T * 512, dtype=torch.float16).pin_memory()
+    peak, peak_src = load_peaks()
+    step_bytes = sampler_step_bytes(d)
+    traffic_tab = {}
+    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof):
+        traffic_tab = json.load(open(prof))
 
-    def step_resident():
-        return model.generate(frames=feats_dev, clip_indices=clip_ids, **kw)["generated_audio"]
-
-    def step_e2e():
-        f = feats_host.to(dev, non_blocking=True)
-        wav = model.generate(frames=f, clip_indices=clip_ids, **kw)["generated_audio"]
-        wav_host.copy_(wav, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return wav_host
+    def gen_kw(w):
+        return dict(max_new_tokens=w["T"], use_sampling=w["use_sampling"], temp=w["temp"], top_k=w["top_k"], top_p=0.0,
+                    cfg_scale=w["cfg_scale"], prompt_is_encoded=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
+    def timed(fn, steps, collective=True):
+        """CUDA-event time of `steps` calls, barrier + synchronize on both sides, max over ranks."""
+        if collective:
+            barrier()
+        else:
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        barrier()
+        if collective:
+            barrier()
+        else:
+            torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
+        if world > 1 and collective:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def step_latency(S):
+        """p50 / p99 of the step-to-step latency from the %globaltimer stamp every step kernel (decode_step_cluster,
+        decode_step_fused_bf16) leaves at the start of the launch that samples column `offset` (csrc/cabi.cu)."""
+        try:
+            ws_buf = model.sampler._buffers["ws"]
+            st_ns = ws_buf[256 + 8 * 1024:256 + 8 * (1024 + S)].cpu().numpy().view(np.uint64).astype(np.int64)
+            d_ns = np.diff(st_ns[2:S])
+            d_ns = d_ns[(d_ns > 0) & (d_ns < 10**8)]
+            if d_ns.size >= 50:
+                return float(np.median(d_ns)) / 1e3, float(np.percentile(d_ns, 99)) / 1e3
+        except Exception:  # paths without a persistent step kernel leave no stamps
+            pass
+        return None, None
+
+    def decode_roofline(w, feats, ids):
+        """The dominant kernel of a 2.56 s workload is the decode step (one launch = one generated column over all
+        sequence rows).  Timed through the token-only generate: CUDA events around 228 back-to-back launches (the first
+        one is the first-pass kernels), on torch's current stream, which is the stream the C ABI launches on."""
+        rows = w["batch"] * (2 if w["cfg_scale"] > 1.0 else 1)
+        kw = gen_kw(w)
+        sampling = bool(w["use_sampling"]) and w["temp"] > 0
+
+        def tokens_only():
+            model.generate(frames=feats, clip_indices=ids, _decode_audio=False, **kw)
+        tokens_only()
+        ms_tok = timed(tokens_only, 3, collective=False) / 3
+        nsteps = w["T"] + 8
+        k_ms = ms_tok / nsteps
+        bf16 = rows >= 16 or (rows >= 3 and sampling)
+        kv_el = 2 if bf16 else 4
+        kv_bytes = d.num_layers * 2 * d.d_model * kv_el * rows * nsteps / 2  # K/V read at the mean context (S/2 positions)
+        alg = step_bytes + kv_bytes
+        if bf16:
+            tm = 64 if rows <= 64 else 128
+            kname = (f"decode_step_fused_bf16<{tm}> ({rows} sequence rows; one launch = embedding + 24 layers + heads + "
+                     f"CFG/sampling/write-back of one column)")
+            key = f"decode_step_fused_bf16_rows{rows}"
+        elif rows <= 2:
+            kname = f"decode_step_cluster<{rows}> (one launch = the whole decode step: 24 layers + heads + sampling)"
+            key = f"decode_step_cluster_rows{rows}"
+        else:
+            kname = f"fp32-activation decode step at {rows} rows (decode_step_persistent / graph of GEMV kernels)"
+            key = f"decode_step_persistent_rows{rows}"
+        p50, p99 = step_latency(w["T"] + 9)
+        ach = alg / (k_ms * 1e-3) / 1e9
+        roof = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic_tab.get(key), "peak_source": peak_src, "us_per_launch": k_ms * 1e3,
+                "algorithmic_bytes_per_launch": alg,
+                "algorithmic_bytes": f"weights {step_bytes} + K/V read {int(kv_bytes)} (24 layers x 2 x 1536 x {kv_el} B x "
+                                     f"{rows} rows x mean context {nsteps // 2})"}
+        step = {"p50_us": p50, "p99_us": p99, "mean_us": k_ms * 1e3, "weight_bytes": step_bytes,
+                "weights_only_hbm_frac_of_measured": (step_bytes / (k_ms * 1e-3) / 1e9) / peak}
+        return roof, step, ms_tok
+
+    clocks = ClockSampler(local_rank)
+    line = None
+
+    # ---- dataset workload (BASELINE config 4 in miniature) ----------------------------------------------------------
+    if args.workload == "dataset":
+        per_gpu = args.clips_per_gpu
+        n_items = per_gpu * world
+        kw = gen_kw(wl)
+        failed = []
+        feat_cache = {}
+
+        def gen_batch(ids):
+            key = (int(ids[0]), int(ids[-1]))
+            if key not in feat_cache:  # features depend only on the clip index (seed = clip index, SURVEY §8d config 4)
+                feat_cache[key] = torch.stack([make_avclip_features(1, 100000 + int(c))[0] for c in ids]).to(dev)
+            return model.generate(frames=feat_cache[key], clip_indices=ids, **kw)["generated_audio"]
+
+        def step():
+            return generate_dataset(gen_batch, n_items, B, rank, world, gather=True, failed=failed)
+
+        for _ in range(max(args.warmup, 1)):
+            out = step()
+        assert out.shape == (n_items, 1, T * 512), out.shape
+        if rank == 0:
+            clocks.start()
+        l0 = lib.vaura_launch_count()
+        ms = timed(step, args.steps)
+        launches = lib.vaura_launch_count() - l0
+        clk = clocks.stop() if rank == 0 else None
+        # the exchange step alone
+        local = out[rank * per_gpu:(rank + 1) * per_gpu].contiguous()
+        gather_ms = timed(lambda: gather_waveforms(local, n_items, rank, world), 5) / 5 if world > 1 else 0.0
+        audio = n_items * T * AUDIO_SEC_PER_TOKEN
+        value = audio * args.steps / (ms / 1000.0)
+        line = {
+            "metric": "generated audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 1), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 weights+activations, fp32 accumulate (tcgen05); codec fp16, fp32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "clips": n_items, "clips_per_gpu": per_gpu, "per_gpu_batch": B,
+                       "parallelism": f"dp{world}: contiguous clip-index shards, full weight replica per GPU, one NCCL "
+                                      "all_gather_into_tensor of the fp16 waveforms per step (inside the timed region)",
+                       "l2": "weights 1.39 GB per decode step >> 126 MB L2; no flush needed"},
+            "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": per_gpu * 32 * 768 * 4,
+                    "d2h_bytes_per_step": 0, "note": "features are made on the host per clip index and copied once (cached "
+                                                      "across steps); the gathered waveforms stay on the device"},
+            "gpu_launches": int(launches),
+            "gather": {"ms": gather_ms, "bytes_per_rank": int(local.numel() * 2), "bytes_total": int(out.numel() * 2),
+                       "algbw_GBps": (out.numel() * 2 / 1e9) / (gather_ms / 1e3) if gather_ms > 0 else None},
+            "failed_clips": failed, "clocks": clk,
+        }
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- long clip workload (BASELINE config 3) -------------------------------------------------------------------------
+    def long_clip_record(steps):
+        w = WORKLOADS["long_b1"]
+        duration = w["duration"]
+        feats = make_avclip_features(1, 3, segments=16).to(dev)  # 16 segments of AVCLIP features (10.24 s of video)
+        kw = dict(use_sampling=True, temp=w["temp"], top_k=w["top_k"], top_p=0.0, cfg_scale=w["cfg_scale"])
+
+        def run():
+            return generate_long(model, feats, duration, **kw)
+        out = run()
+        n_tok = out["sampled_indices"].shape[-1]
+        ms = timed(run, steps, collective=False) / steps
+        ms_tok = timed(lambda: generate_long(model, feats, duration, decode_audio=False, **kw), steps, collective=False) / steps
+        # one window's prefill alone: prompt of 165 tokens -> first pass over 166 columns + the first sampled column
+        from vaura_b200.driver import chunk_schedule
+        sched = chunk_schedule(duration)
+        pl = sched[1]["prompt_len"]
+        prompt = out["sampled_indices"][:, :, :pl].contiguous()
+        sel = feats[:, torch.tensor(sched[1]["positions"], device=dev) % feats.shape[1]]
+
+        def prefill_only():  # stops after the first sampled column (_end_offset): first pass over the prompt columns only
+            model.generate(frames=sel, audio=prompt, max_new_tokens=sched[1]["max_gen_len"], prompt_is_encoded=True,
+                           _decode_audio=False, _end_offset=pl + 2, **kw)
+        prefill_only()
+        ms_pre = timed(prefill_only, 5, collective=False) / 5
+        audio = n_tok * AUDIO_SEC_PER_TOKEN
+        return {"workload": w["name"], "value": audio / (ms / 1e3), "unit": "audio-s/s", "ms_per_clip": ms,
+                "ms_tokens_only": ms_tok, "tokens": int(n_tok), "windows": len(sched),
+                "prefill_positions": pl + 1, "prefill_ms_per_window": ms_pre,
+                "prefill_note": "generate() with the window's prompt, stopped after the first sampled column: host glue + "
+                                "the first pass over the prompt columns + one sampling launch"}
+
+    if args.workload == "long_b1":
+        for _ in range(max(args.warmup, 1)):
+            pass
+        if rank == 0:
+            clocks.start()
+        rec = long_clip_record(max(args.steps, 1))
+        clk = clocks.stop() if rank == 0 else None
+        line = {"metric": "generated audio-sec/sec", "value": rec["value"] * world, "unit": "audio-s/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": rec["ms_per_clip"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16 weights, fp32 activations/accumulate; codec fp16",
+                "data": "synthetic", "config": {"workload": rec["workload"], "parallelism": f"dp{world} replicas"},
+                "long_b1": rec, "clocks": clk}
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- 2.56 s workloads (b64 default) -------------------------------------------------------------------------------
+    kw = gen_kw(wl)
+    # rank r owns clips [r*B, (r+1)*B) of every step; features depend only on the clip index
+    feats_host = make_avclip_features(B, 2 + rank).pin_memory()
+    feats_dev = feats_host.to(dev)
+    clip_ids = torch.arange(rank * B, (rank + 1) * B, dtype=torch.int32)
+    wav_host = torch.empty(B * world, 1, T * 512, dtype=torch.float16).pin_memory()
+    n_items = B * world
+
+    def step_resident():
+        wav = model.generate(frames=feats_dev, clip_indices=clip_ids, **kw)["generated_audio"]
+        return gather_waveforms(wav, n_items, rank, world)  # identity at N = 1; NCCL all-gather otherwise
+
+    def step_e2e():
+        f = feats_host.to(dev, non_blocking=True)
+        wav = model.generate(frames=f, clip_indices=clip_ids, **kw)["generated_audio"]
+        wav = gather_waveforms(wav, n_items, rank, world)
+        wav_host.copy_(wav, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return wav_host
+
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     l0 = lib.vaura_launch_count()
@@ -229,115 +482,63 @@ def main():
     audio_per_step = B * T * AUDIO_SEC_PER_TOKEN * world
     value = audio_per_step * args.steps / (ms / 1000.0)
     e2e = audio_per_step * args.steps / (ms_e2e / 1000.0)
+    gather_ms = None
+    if world > 1:
+        wav_local = model.generate(frames=feats_dev, clip_indices=clip_ids, **kw)["generated_audio"]
+        gather_ms = timed(lambda: gather_waveforms(wav_local, n_items, rank, world), 5) / 5
 
-    # ---- roofline of the dominant kernel ------------------------------------------------------------------
-    peak, peak_src = load_peaks()
+    roof, step_rec, ms_tok = decode_roofline(wl, feats_dev, clip_ids)
     rows = B * (2 if wl["cfg_scale"] > 1.0 else 1)
-    d = FULL_SAMPLER
-    st = torch.cuda.current_stream().cuda_stream
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    step_bytes = sampler_step_bytes(d)
-    if rows <= 4:
-        # rows <= 4: the whole decode step is ONE persistent kernel (rows <= 2: decode_step_cluster, 32 clusters x 4
-        # CTAs; rows 3-4: decode_step_persistent); timed through the token-only generate (CUDA events around 227
-        # back-to-back launches of that kernel + 1 first pass)
-        def tokens_only_r():
-            model.generate(frames=feats_dev, clip_indices=clip_ids, _decode_audio=False, **kw)
-        tokens_only_r()
-        k_ms = timed(tokens_only_r, 3) / 3 / (T + 8)
-        kv_bytes = 24 * 2 * d.d_model * 4 * rows * (T + 8) / 2  # fp32 KV read, mean context (S/2 positions)
-        alg_bytes = step_bytes + kv_bytes
-        kern = "decode_step_cluster" if rows <= 2 else "decode_step_persistent"
-        kname = f"{kern}<{rows}> (whole decode step: 24 layers + heads + sampling)"
-        key = f"{kern}_rows{rows}"
-    elif rows <= 64:
-        # rows 16..64: the whole decode step is ONE cooperative kernel (decode_step_fused_bf16: rmsnorm, tcgen05 GEMM tiles,
-        # attention, device-wide barriers between phases); timed through the token-only generate, which is 228 x (embed
-        # kernel + that kernel + sampling kernel) back to back
-        def tokens_only_r():
-            model.generate(frames=feats_dev, clip_indices=clip_ids, _decode_audio=False, **kw)
-        tokens_only_r()
-        k_ms = timed(tokens_only_r, 3) / 3 / (T + 8)
-        kv_bytes = 24 * 2 * d.d_model * 2 * rows * (T + 8) / 2  # bf16 KV read, mean context (S/2 positions)
-        alg_bytes = step_bytes + kv_bytes
-        kname = f"decode_step_fused_bf16 ({rows} rows: 24 layers + heads in one launch; embed + sampling kernels included in the time)"
-        key = f"decode_step_fused_bf16_rows{rows}"
-    else:
-        # rows > 64: tcgen05 linear over w1|w3 (25.2 MB of weights per launch), 24 different matrices back to back
-        w13 = model.sampler.weights["w13"]
-        x = torch.randn(rows, d.d_model, device=dev).to(torch.bfloat16)
-        y = torch.empty(rows, 2 * d.ffn_dim, device=dev)
-        bn = 64 if rows <= 128 else 128
-
-        def gemm_pass():
-            for l in range(d.num_layers):  # 604 MB of distinct weights > L2: nothing is re-read from cache
-                _cabi.check(lib.vaura_linear_bf16(x.data_ptr(), w13[l].data_ptr(), y.data_ptr(), rows, 2 * d.ffn_dim,
-                                                  d.d_model, bn, st), "vaura_linear_bf16")
-
-        for _ in range(3):
-            gemm_pass()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            gemm_pass()
-        e1.record()
-        torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / (5 * d.num_layers)
-        alg_bytes = 2 * d.ffn_dim * d.d_model * 2 + rows * d.d_model * 2 + rows * 2 * d.ffn_dim * 4
-        kname = f"gemm_tc_kernel<{bn},64,...,EpiLinear> w1|w3 [8192x1536] bf16 x {rows} rows (tcgen05)"
-        key = f"gemm_tc_w13_rows{rows}"
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    if os.path.exists(prof):
-        traffic = json.load(open(prof)).get(key)
-
     line = {
         "metric": "generated audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": ("bf16 weights, fp32 activations/accumulate" if rows < 16 else "bf16 weights+activations, fp32 accumulate (tcgen05)") + "; codec fp16, fp32 accumulate",
+        "vs_baseline": None,
+        "dtype": ("bf16 weights+activations, fp32 accumulate (tcgen05)" if rows >= 3 else "bf16 weights, fp32 activations/accumulate")
+                 + "; codec fp16, fp32 accumulate",
         "data": "synthetic",
         "config": {"workload": wl["name"], "per_gpu_batch": B, "tokens_per_clip": T, "decode_steps": T + 8,
                    "l2": "weights 1.39 GB per decode step >> 126 MB L2; no flush needed", "cfg_scale": wl["cfg_scale"],
-                   "parallelism": f"dp{world} (clips sharded, no collective in the hot loop)"},
+                   "parallelism": f"dp{world} (clips sharded by index, no collective in the decode loop; NCCL all-gather of the "
+                                  "fp16 waveforms at the end of every step)" if world > 1 else "dp1"},
         "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": feats_host.numel() * 4,
                 "d2h_bytes_per_step": wav_host.numel() * 2, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": kname, "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "us_per_launch": k_ms * 1e3, "algorithmic_bytes_per_launch": alg_bytes},
-        "decode_step": {"p50_us": None, "weight_bytes": sampler_step_bytes(d)},
+        "roofline": roof,
+        "decode_step": step_rec,
         "clocks": clk,
+        "codec": {"ms_per_batch": ms / args.steps - ms_tok - (gather_ms or 0.0), "gflop_per_clip": codec_flops(FULL_CODEC, T) / 1e9},
     }
-    # decode-step latency: tokens only, no codec
-    def tokens_only():
-        model.generate(frames=feats_dev, clip_indices=clip_ids, _decode_audio=False, **kw)
-    tokens_only()
-    ms_tok = timed(tokens_only, 2) / 2
-    line["decode_step"]["mean_us"] = ms_tok * 1e3 / (T + 8)
-    # p50 of the step-to-step latency: the step kernels (decode_step_cluster, decode_step_fused_bf16) stamp %globaltimer at
-    # the start of the launch that samples column `offset` into the workspace (csrc/cabi.cu: ws.timing + 1024)
-    try:
-        import numpy as np
-        ws_buf = model.sampler._buffers["ws"]
-        S = T + 9
-        st_ns = ws_buf[256 + 8 * 1024:256 + 8 * (1024 + S)].cpu().numpy().view(np.uint64).astype(np.int64)
-        d_ns = np.diff(st_ns[2:S])
-        d_ns = d_ns[(d_ns > 0) & (d_ns < 10**8)]
-        if d_ns.size >= 100:
-            line["decode_step"]["p50_us"] = float(np.median(d_ns)) / 1e3
-            line["decode_step"]["p99_us"] = float(np.percentile(d_ns, 99)) / 1e3
-    except Exception:  # paths without a persistent step kernel leave no stamps
-        pass
-    line["decode_step"]["hbm_frac_of_measured"] = (sampler_step_bytes(d) / (ms_tok * 1e-3 / (T + 8)) / 1e9) / peak
-    line["codec"] = {"ms_per_batch": ms / args.steps - ms_tok, "gflop_per_clip": codec_flops(FULL_CODEC, T) / 1e9}
+    if gather_ms is not None:
+        line["gather"] = {"ms": gather_ms, "bytes_per_rank": int(B * T * 512 * 2), "bytes_total": int(n_items * T * 512 * 2)}
+
+    # ---- the other halves of BASELINE's metric, N = 1 only (the driver runs the default line) --------------------------
+    if world == 1 and not args.no_sub and args.workload == "b64":
+        sub_steps = 3
+        for name in ("b1", "b64_cfg"):
+            w = WORKLOADS[name]
+            fh = make_avclip_features(w["batch"], 2).pin_memory()
+            ids = torch.arange(w["batch"], dtype=torch.int32)
+            wh = torch.empty(w["batch"], 1, w["T"] * 512, dtype=torch.float16).pin_memory()
+            kws = gen_kw(w)
+
+            def e2e_step():
+                f = fh.to(dev, non_blocking=True)
+                wv = model.generate(frames=f, clip_indices=ids, **kws)["generated_audio"]
+                wh.copy_(wv, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            for _ in range(3):
+                e2e_step()
+            ms_s = timed(e2e_step, sub_steps, collective=False) / sub_steps
+            r, s, _ = decode_roofline(w, fh.to(dev), ids)
+            line[name] = {"workload": w["name"], "e2e": w["batch"] * w["T"] * AUDIO_SEC_PER_TOKEN / (ms_s / 1e3),
+                          "unit": "audio-s/s", "ms_per_step": ms_s, "roofline": r, "decode_step": s}
+        line["long_b1"] = long_clip_record(2)
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, total, pts = cpu_reference_sample(threads)
+        v, total, t_slices, codec_s = cpu_reference_clip(threads, 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                                "sample": "oracle port of the reference's no-KV-cache loop: full-prefix forwards at "
-                                          "prefix 1/76/152/228 integrated over 228 steps, B=1, fp32; "
-                                          f"{total:.1f} s per clip"}
+                                "sample": CPU_SAMPLE + f"; {total:.1f} s per clip (codec {codec_s:.1f} s)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

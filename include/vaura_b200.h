@@ -34,7 +34,8 @@ extern "C" {
 #define VAURA_ERR_CUDA 3         /* CUDA runtime error; message has the cudaError string */
 #define VAURA_ERR_WORKSPACE 4    /* caller-provided workspace too small */
 
-#define VAURA_PRECISION_AUTO 0
+#define VAURA_PRECISION_AUTO 0    /* BF16 from 16 sequence rows, and from 3 rows when the call samples (top-k / top-p /
+                                     temperature: no bit-exactness contract); FP32ACT otherwise (greedy, rows <= 2) */
 #define VAURA_PRECISION_FP32ACT 1 /* bf16 weights, fp32 activations + fp32 KV, CUDA-core FMA (HBM-bound small batch) */
 #define VAURA_PRECISION_BF16 2    /* bf16 weights + bf16 activations/KV, tcgen05 GEMMs, fp32 accumulate */
 
@@ -152,13 +153,17 @@ typedef struct {
   int32_t top_k;         /* used when top_p <= 0 and top_k > 0 */
   float top_p;           /* > 0 takes precedence over top_k (vaura_model.py:818-823) */
   float cfg_scale;
-  uint64_t seed;         /* Philox key; counter = (clip_id, offset, codebook, 0) */
+  uint64_t seed;         /* Philox key; counter = (clip_id, offset, codebook, stream_id) */
   const int32_t* clip_ids; /* device [B] or NULL (=> 0..B-1) */
   int32_t* sequence;     /* device [B][K][S] int32, in/out; -1 = not generated yet (vaura_model.py:482) */
   const float* cond_rows;/* device [rows][cond_tokens+1][cond_dim] from vaura_sampler_cond_project */
   float* logits_out;     /* optional device [S][B][K][V] post-CFG logits, entry [offset] = the logits that
                             produced column offset; NULL to skip */
   int32_t precision;     /* VAURA_PRECISION_* */
+  uint32_t stream_id;    /* 4th Philox counter word.  Calls that would otherwise repeat (seed, clip id, column,
+                            codebook) - the windows of a chunked long clip, successive batches without clip ids -
+                            pass different values so that they do not draw the same uniforms (the reference's
+                            torch.multinomial advances a global generator, utils/utils.py:139-160) */
 } vaura_generate_params;
 
 int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_params* p, const vaura_kv_cache* kv,

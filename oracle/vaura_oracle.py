@@ -263,10 +263,10 @@ def philox4x32_10(counter: Tuple[int, int, int, int], key: Tuple[int, int]) -> T
     return c0, c1, c2, c3
 
 
-def philox_uniform(seed: int, clip_id: int, step: int, codebook: int) -> float:
-    """u in [0,1): counter = (clip_id, step, codebook, 0), key = (seed lo, seed hi); first word,
+def philox_uniform(seed: int, clip_id: int, step: int, codebook: int, stream_id: int = 0) -> float:
+    """u in [0,1): counter = (clip_id, step, codebook, stream_id), key = (seed lo, seed hi); first word,
     top 24 bits."""
-    r = philox4x32_10((clip_id & 0xFFFFFFFF, step & 0xFFFFFFFF, codebook & 0xFFFFFFFF, 0),
+    r = philox4x32_10((clip_id & 0xFFFFFFFF, step & 0xFFFFFFFF, codebook & 0xFFFFFFFF, stream_id & 0xFFFFFFFF),
                       (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
     return (r[0] >> 8) * (1.0 / 16777216.0)
 
@@ -297,6 +297,7 @@ def generate_tokens(
     seed: int = 0,
     clip_ids: Optional[List[int]] = None,
     collect_logits: bool = False,
+    stream_id: int = 0,
 ):
     """KV-cached restatement of VAURAModel.generate up to out_codes (vaura_model.py:455-572).
 
@@ -341,7 +342,7 @@ def generate_tokens(
             nxt = torch.empty((B, K), dtype=torch.long)
             for b in range(B):
                 for k in range(K):
-                    u01 = philox_uniform(seed, clip_ids[b], offset, k)
+                    u01 = philox_uniform(seed, clip_ids[b], offset, k, stream_id)
                     nxt[b, k] = inverse_cdf_draw(probs[b, k], u01)
         else:
             nxt = torch.argmax(logits, dim=-1)  # vaura_model.py:825

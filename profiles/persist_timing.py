@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from tests.test_gpu_parity import build_model  # noqa: E402
+from vaura_b200.synthetic import build_model  # noqa: E402
 from vaura_b200.synthetic import FULL_CODEC, FULL_SAMPLER, make_avclip_features  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1

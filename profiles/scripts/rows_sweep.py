@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from tests.test_gpu_parity import build_model  # noqa: E402
+from vaura_b200.synthetic import build_model  # noqa: E402
 from vaura_b200 import _cabi  # noqa: E402
 from vaura_b200.synthetic import FULL_CODEC, FULL_SAMPLER, make_avclip_features  # noqa: E402
 

@@ -77,7 +77,7 @@ def test_chunked_long_clip_matches_oracle():
     """BASELINE config 3 shape on the tiny model: overlapping windows with prompt carry-over; greedy tokens must equal
     the oracle run through the same schedule."""
     from oracle import vaura_oracle as vo
-    from tests.test_gpu_parity import build_model
+    from vaura_b200.synthetic import build_model
     from vaura_b200.driver import generate_long
     from vaura_b200.synthetic import TINY_CODEC, TINY_SAMPLER, make_avclip_features, make_sampler_state_dict
 
@@ -104,3 +104,45 @@ def test_chunked_long_clip_matches_oracle():
     else:
         assert (toks == ref).float().mean() > 0.9
     assert out["generated_audio"].shape == (B, 1, toks.shape[-1] * 512)
+
+
+# ---- NCCL: sharded generation == single-GPU generation, bit for bit (needs 2 GPUs; gpurun --gpus 2) -------------------
+def _real_generate_fn(device):
+    from vaura_b200 import _cabi
+    from vaura_b200.synthetic import TINY_CODEC, TINY_SAMPLER, build_model, make_avclip_features
+
+    model = build_model(TINY_SAMPLER, TINY_CODEC, device=device)
+    model.seed = 77
+
+    def gen(ids):
+        # features and Philox counters are keyed by the clip index; the fp32-activation path is deterministic per row
+        feats = torch.stack([make_avclip_features(1, 5000 + int(c))[0] for c in ids]).to(device)
+        return model.generate(frames=feats, clip_indices=ids, max_new_tokens=16, use_sampling=True, top_k=64,
+                              prompt_is_encoded=True, _precision=_cabi.PRECISION_FP32ACT)["generated_audio"]
+    return gen
+
+
+def _nccl_worker(rank, world, port, n_items, batch, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    full = generate_dataset(_real_generate_fn(f"cuda:{rank}"), n_items, batch, rank, world, gather=True)
+    torch.cuda.synchronize()
+    torch.save(full.cpu(), os.path.join(out_dir, f"nccl_r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_nccl_sharded_generation_equals_single_gpu(tmp_path):
+    """BASELINE config 4 on hardware, in miniature: clips sharded over 2 ranks by index, real model, NCCL all-gather of the
+    fp16 waveforms; every rank must end up with exactly the waveforms one GPU produces alone."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    n_items, batch = 11, 4
+    ref = generate_dataset(_real_generate_fn("cuda:0"), n_items, batch, 0, 1).cpu()
+    assert ref.shape == (n_items, 1, 16 * 512) and ref.dtype == torch.float16
+    world = 2
+    mp.spawn(_nccl_worker, args=(world, _free_port(), n_items, batch, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = torch.load(os.path.join(tmp_path, f"nccl_r{r}.pt"))
+        assert got.shape == ref.shape and torch.equal(got, ref), r

@@ -1,0 +1,185 @@
+"""Full-clip parity of the headline path (run on the B200 box: pytest -m gpu).
+
+`bench.py` measures 64 clips x 228 decode steps through `decode_step_fused_bf16`; these tests run exactly that
+configuration (full-size model, 220 tokens, 8 K/V pages per sequence) and compare every one of the 228 steps with the
+fp32 CPU oracle, teacher-forced on the tokens the GPU produced (models/vaura_model.py:502-547, llama.py:445-517).
+north star: per-step logits within 1e-2 relative error in bf16 (relative to max |logit| of the step) and
+>= 99 % token agreement over the full clip.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vaura_oracle as vo
+from vaura_b200 import _cabi
+from vaura_b200.synthetic import (FULL_CODEC, FULL_SAMPLER, build_model, make_avclip_features, make_sampler_state_dict)
+
+pytestmark = pytest.mark.gpu
+BF16_LOGIT_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def full_model():
+    return build_model(FULL_SAMPLER, FULL_CODEC)
+
+
+@pytest.fixture(scope="module")
+def full_oracle():
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    return vo.SamplerOracle(make_sampler_state_dict(FULL_SAMPLER, 0), FULL_SAMPLER)
+
+
+def _teacher_forced(oracle, seq, feats, cfg_scale, chunk=8):
+    """Oracle logits (B,K,S-1,V) for the columns of `seq` (post-CFG when cfg_scale > 1), in chunks of clips."""
+    out = []
+    for b0 in range(0, seq.shape[0], chunk):
+        s, f = seq[b0:b0 + chunk, :, :-1], feats[b0:b0 + chunk]
+        if cfg_scale > 1.0:
+            fa = torch.cat([f, torch.zeros_like(f) + oracle.uncond], 0)
+            lg = oracle.forward_full(s.repeat(2, 1, 1), fa)
+            n = s.shape[0]
+            out.append(lg[n:] + (lg[:n] - lg[n:]) * cfg_scale)
+        else:
+            out.append(oracle.forward_full(s, f))
+    return torch.cat(out, 0)
+
+
+def _check_full_clip(model, oracle, B, cfg_scale, feat_seed, check_clips, tol):
+    T = 220
+    feats = make_avclip_features(B, feat_seed)
+    out = model.generate(frames=feats.cuda(), max_new_tokens=T, use_sampling=False, prompt_is_encoded=True,
+                         return_sampled_indices=True, check=True, cfg_scale=cfg_scale, _return_logits=True,
+                         _decode_audio=False)
+    codes = out["sampled_indices"].cpu()
+    assert codes.shape == (B, 9, T) and int(codes.min()) >= 0 and int(codes.max()) < 1024
+    seq, _ = vo.build_pattern_sequence(codes, 1024)
+    sel = list(check_clips)
+    mine = out["_logits"][1:, sel].cpu().permute(1, 2, 0, 3)  # (S-1,b,K,V) -> (b,K,S-1,V)
+    ref = _teacher_forced(oracle, seq[sel], feats[sel].reshape(len(sel), 32, 768), cfg_scale)
+    assert mine.shape == ref.shape == (len(sel), 9, T + 8, 1024)
+    # per-step error relative to the step's max |logit| (every position, every clip checked)
+    step_max = ref.abs().amax(dim=(1, 3))                       # (b, S-1)
+    err = (mine - ref).abs().amax(dim=(1, 3)) / step_max        # (b, S-1)
+    worst = int(err.argmax())
+    wb, wp = worst // err.shape[1], worst % err.shape[1]
+    print(f"[full clip B={B} cfg={cfg_scale}] max per-step logit error {float(err.max()):.3e} at clip {sel[wb]} "
+          f"position {wp}; mean {float(err.mean()):.3e}; at page boundaries "
+          f"{[round(float(err[:, p].max()), 5) for p in (31, 32, 63, 64, 127, 128, 223, 224, 227)]}")
+    assert float(err.max()) < tol, (float(err.max()), sel[wb], wp)
+    # argmax agreement with the oracle on the same inputs: >= 99 % over the clip, 100 % where the top-2 gap is clear.
+    # Only valid pattern cells count (the others are overwritten with the special id, vaura_model.py:536-537).
+    mask = vo.pattern_mask(9, T)[:, 1:]                         # (K, S-1): column s = position s-1 ... uses s = 1..S-1
+    agree = mine.argmax(-1) == ref.argmax(-1)                   # (b,K,S-1)
+    valid = mask[None].expand_as(agree)
+    rate = float(agree[valid].float().mean())
+    top2 = torch.topk(ref, 2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 2 * tol * step_max[:, None, :]
+    print(f"[full clip B={B} cfg={cfg_scale}] argmax agreement {rate:.4f} over {int(valid.sum())} cells; "
+          f"clear-gap cells {int((clear & valid).sum())}")
+    assert rate >= 0.99, rate
+    assert bool(agree[clear & valid].all())
+    return codes
+
+
+def test_fused_bf16_step_full_clip_64_rows(full_model, full_oracle):
+    """BASELINE config 2 shape: 64 clips, 228 steps through decode_step_fused_bf16<64>, all 8 K/V pages, positions >= 224
+    (empty_video_emb rows)."""
+    _check_full_clip(full_model, full_oracle, B=64, cfg_scale=1.0, feat_seed=2, check_clips=range(0, 64, 4),
+                     tol=BF16_LOGIT_TOL)
+
+
+def test_fused_bf16_step_full_clip_128_rows_cfg(full_model, full_oracle):
+    """64 clips with classifier-free guidance = 128 sequence rows: decode_step_fused_bf16<128>.  The CFG combine
+    u + (c - u) * s (vaura_model.py:810-813) amplifies the bf16 error of both halves, hence 2 x the tolerance at s = 2."""
+    _check_full_clip(full_model, full_oracle, B=64, cfg_scale=2.0, feat_seed=3, check_clips=range(1, 64, 8),
+                     tol=2 * BF16_LOGIT_TOL)
+
+
+def test_fp32_path_unselected_seed_full_clip(full_model, full_oracle):
+    """The greedy goldens were made from feature seeds re-drawn until no step had a near-tie (oracle/make_golden.py:73-106).
+    This is a seed nobody selected: B = 1, fp32-activation path (decode_step_cluster), free-running against the oracle's
+    KV-cached loop.  north star: bit-exact while the oracle's top-2 gap stays clear, >= 99 % agreement over the clip."""
+    T = 220
+    feats = make_avclip_features(1, 424242)
+    out = full_model.generate(frames=feats.cuda(), max_new_tokens=T, use_sampling=False, prompt_is_encoded=True,
+                              return_sampled_indices=True, check=True, _return_logits=True, _decode_audio=False)
+    codes = out["sampled_indices"].cpu()
+    ref, lg = vo.generate_tokens(full_oracle, feats.reshape(1, 32, 768), max_new_tokens=T, collect_logits=True)
+    top2 = torch.topk(lg, 2, dim=-1).values                     # (steps,1,K,V) -> gaps (steps,1,K)
+    gap = (top2[..., 0] - top2[..., 1])
+    mask = vo.pattern_mask(9, T)[:, 1:].t()[:, None, :]         # (steps,1,K)
+    gap = torch.where(mask, gap, torch.full_like(gap, 1e9))
+    first_tie = int((gap.amin(dim=(1, 2)) < 1e-4).float().argmax()) if bool((gap < 1e-4).any()) else T + 8
+    seq_m, _ = vo.build_pattern_sequence(codes, 1024)
+    seq_r, _ = vo.build_pattern_sequence(ref, 1024)
+    rate = float((codes == ref).float().mean())
+    print(f"[unselected seed] min top-2 gap {float(gap.min()):.3e}, first near-tie step {first_tie}, agreement {rate:.4f}")
+    assert torch.equal(seq_m[..., :first_tie + 1], seq_r[..., :first_tie + 1])
+    assert rate >= 0.99 or first_tie < T + 8
+    if first_tie >= 64:
+        assert torch.equal(seq_m[..., :65], seq_r[..., :65])
+    # teacher-forced on our own tokens the logits agree to fp32 tolerance whatever the ties did
+    tf = full_oracle.forward_full(seq_m[..., :-1], feats.reshape(1, 32, 768))
+    mine = out["_logits"][1:].cpu().permute(1, 2, 0, 3)
+    assert float((mine - tf).abs().max() / tf.abs().max()) < 2e-5
+
+
+def test_fp32_checkpoint_weights_are_bf16_quantised():
+    """The transformer matrices are stored in bf16 on every path.  The synthetic weights used elsewhere are
+    bf16-representable, which makes that lossless; a real fp32 checkpoint is not.  This measures the cost on weights that
+    are NOT representable: logits within bf16 tolerance of the fp32-weight oracle, tokens mostly equal."""
+    from vaura_b200.synthetic import TINY_CODEC, TINY_SAMPLER, make_checkpoint_state_dict
+
+    sd = make_checkpoint_state_dict(TINY_SAMPLER, TINY_CODEC, 7)
+    g = torch.Generator().manual_seed(11)
+    for k in list(sd):
+        if k.startswith("sampler.") and sd[k].dtype == torch.float32 and sd[k].dim() >= 2:
+            sd[k] = sd[k] * (1.0 + 3e-3 * torch.randn(sd[k].shape, generator=g))  # no longer bf16-representable
+    assert not torch.equal(sd["sampler.layers.0.attention.wqkv.weight"],
+                           sd["sampler.layers.0.attention.wqkv.weight"].to(torch.bfloat16).float())
+    m = build_model(TINY_SAMPLER, TINY_CODEC)
+    m.load_state_dict(sd, device="cuda:0")
+    oracle = vo.SamplerOracle({k[len("sampler."):]: v for k, v in sd.items() if k.startswith("sampler.")}, TINY_SAMPLER)
+    B, T = 2, 40
+    feats = make_avclip_features(B, 77)
+    out = m.generate(frames=feats.cuda(), max_new_tokens=T, use_sampling=False, prompt_is_encoded=True,
+                     return_sampled_indices=True, _return_logits=True, _decode_audio=False,
+                     _precision=_cabi.PRECISION_FP32ACT)
+    codes = out["sampled_indices"].cpu()
+    seq, _ = vo.build_pattern_sequence(codes, 1024)
+    ref = oracle.forward_full(seq[..., :-1], feats.reshape(B, 32, 768))
+    mine = out["_logits"][1:].cpu().permute(1, 2, 0, 3)
+    err = float((mine - ref).abs().max() / ref.abs().max())
+    agree = float((mine.argmax(-1) == ref.argmax(-1)).float().mean())
+    print(f"[bf16-quantised fp32 weights] logit error {err:.3e} of max |logit|, argmax agreement {agree:.4f}")
+    assert err < BF16_LOGIT_TOL and agree >= 0.95
+
+
+def test_philox_stream_id_separates_calls():
+    """Two calls with the same seed, clip ids and columns draw different uniforms when their stream ids differ (the windows
+    of generate_long, successive batches without clip ids) and identical ones when they are equal."""
+    from vaura_b200.synthetic import TINY_CODEC, TINY_SAMPLER
+
+    m = build_model(TINY_SAMPLER, TINY_CODEC)
+    feats = make_avclip_features(2, 5).cuda()
+    ids = torch.tensor([3, 4])
+    kw = dict(frames=feats, max_new_tokens=16, top_k=64, return_sampled_indices=True, _decode_audio=False,
+              prompt_is_encoded=True)
+    a = m.generate(clip_indices=ids, **kw)["sampled_indices"]
+    b = m.generate(clip_indices=ids, **kw)["sampled_indices"]
+    c = m.generate(clip_indices=ids, _stream_id=1, **kw)["sampled_indices"]
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    # without clip ids consecutive calls take consecutive streams (the reference's global generator advances too)
+    d = m.generate(**kw)["sampled_indices"]
+    e = m.generate(**kw)["sampled_indices"]
+    assert not torch.equal(d, e)
+    # the device draw equals the oracle's Philox inverse-CDF with the same 4-word counter
+    from vaura_b200.sampler import sample_logits
+    g = torch.Generator().manual_seed(1)
+    logits = torch.randn(1, 9, 1024, generator=g)
+    # (vaura_sample_logits is stream 0; the generate path above covers the other streams)
+    toks, probs = sample_logits(logits.cuda(), temp=1.0, top_k=32, seed=7, offset=3, return_probs=True)
+    u = vo.philox_uniform(7, 0, 3, 0, stream_id=0)
+    assert vo.inverse_cdf_draw(probs[0, 0].cpu().numpy(), u) == int(toks[0, 0])

@@ -9,35 +9,11 @@ import torch
 from oracle import vaura_oracle as vo
 from oracle.dac_oracle import DacDecodeOracle
 from vaura_b200 import VAURAModel, _cabi
-from vaura_b200.synthetic import (FULL_CODEC, FULL_SAMPLER, TINY_CODEC, TINY_SAMPLER, make_avclip_features,
-                                  make_checkpoint_state_dict, make_codec_state_dict, make_sampler_state_dict)
+from vaura_b200.synthetic import (FULL_CODEC, FULL_SAMPLER, TINY_CODEC, TINY_SAMPLER, build_model, make_avclip_features,
+                                  make_codec_state_dict, make_sampler_state_dict)
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-
-
-def build_model(sdims, cdims, seed=0, device="cuda:0"):
-    cfg = dict(
-        use_visual_conditioning=True,
-        feature_extractor_config={"target": "models.modules.feature_extractors.avclip.motionformer.MotionFormer",
-                                  "params": {}},
-        audio_encoder_config={"target": "models.modules.dac.model.DacModelWrapper",
-                              "params": {"model_sr": 44100, "dims": cdims}},
-        sampler_config={"target": "models.modules.sampler.llama.Transformer",
-                        "params": dict(num_layers=sdims.num_layers, d_model=sdims.d_model, d_codebook=sdims.d_codebook,
-                                       nhead=sdims.nhead, num_codebooks=sdims.num_codebooks,
-                                       block_size_audio=sdims.block_size, block_size_video=64,
-                                       cond_feature_channel_scaler=sdims.cond_feature_channel_scaler)},
-        visual_bridge_config={"target": "torch.nn.Identity"},
-        pattern_provider_config={"target": "models.modules.misc.codebook_patterns.DelayedPatternProvider",
-                                 "params": {"n_q": sdims.num_codebooks}},
-        flatten_vis_feats=True,
-    )
-    m = VAURAModel(**cfg)
-    m.load_state_dict(make_checkpoint_state_dict(sdims, cdims, seed), device=device)
-    m.eval()
-    m.sampler.audio_tokens_per_video_frame = 7
-    return m
 
 
 @pytest.fixture(scope="module")

@@ -232,3 +232,86 @@ def test_precision_rule_and_environment_override(monkeypatch):
     assert resolve_precision(_cabi.PRECISION_FP32ACT, 4) == _cabi.PRECISION_FP32ACT
     monkeypatch.setenv("VAURA_PRECISION", "fp32")
     assert resolve_precision(_cabi.PRECISION_AUTO, 64) == _cabi.PRECISION_FP32ACT
+
+
+# ---- boundary: checkpoints, pickers, audio_tokens_per_video_frame --------------------------------------------------
+def test_lightning_checkpoint_split_and_hparams(tmp_path):
+    """A Lightning-style .ckpt (state_dict with the reference's prefixes + hyper_parameters) is split the way
+    VAURAModel.load_from_checkpoint consumes it (scripts/generate.py:209-211)."""
+    from vaura_b200.codec import DacModelWrapper
+    from vaura_b200.synthetic import make_checkpoint_state_dict
+    from vaura_b200.weights import load_lightning_checkpoint
+
+    sd = make_checkpoint_state_dict(TINY_SAMPLER, TINY_CODEC, 0)
+    sd["visual_feature_extractor.dummy"] = torch.zeros(1)
+    sd["loss_weight"] = torch.ones(1)
+    path = tmp_path / "epoch=3-val_loss=1.25.ckpt"
+    torch.save({"state_dict": sd, "hyper_parameters": {"batch_size": 2}, "epoch": 3}, path)
+    parts, hp = load_lightning_checkpoint(str(path))
+    assert hp == {"batch_size": 2}
+    assert set(parts) == {"sampler", "codec", "feature_extractor", "other"}
+    assert "layers.0.attention.wqkv.weight" in parts["sampler"] and "decoder.model.0.weight_v" in parts["codec"]
+    assert list(parts["feature_extractor"]) == ["dummy"] and list(parts["other"]) == ["loss_weight"]
+    # codec shape parameters are read off the state dict when the YAML gives only model_sr
+    assert DacModelWrapper.dims_from_state_dict(parts["codec"], 44100) == TINY_CODEC
+
+
+def test_checkpoint_pickers(tmp_path):
+    import time as _t
+
+    for name in ("epoch=1-val_loss=2.50.ckpt", "epoch=7-val_loss=1.75.ckpt", "epoch=9-val_loss=1.80.ckpt"):
+        (tmp_path / name).write_bytes(b"x")
+        _t.sleep(0.01)
+    assert vcfg.get_file_with_best_val_loss(tmp_path).name == "epoch=7-val_loss=1.75.ckpt"
+    assert vcfg.get_latest_file(tmp_path, "*.ckpt").name == "epoch=9-val_loss=1.80.ckpt"
+    only = tmp_path / "single"
+    only.mkdir()
+    (only / "last.ckpt").write_bytes(b"x")
+    assert vcfg.get_file_with_best_val_loss(only).name == "last.ckpt"
+    with pytest.raises(AssertionError):
+        vcfg.get_file_with_best_val_loss(tmp_path / "single", "*.pt")
+
+
+def test_audio_tokens_per_video_frame_must_be_positive():
+    """llama.py:544-553 derives ceil((Ta - K) / Tv); without a prompt that is ceil(-8/32) = 0, which the kernels would
+    divide by.  The host mirror raises instead of forwarding it (the reference fails on the host as well)."""
+    from vaura_b200.sampler import Transformer
+
+    t = Transformer(num_layers=2, d_model=384, nhead=4, num_codebooks=9, block_size_audio=256, cond_feature_channel_scaler=3)
+    t.codebook_pattern = "DelayedPatternProvider"
+    with pytest.raises(ValueError):
+        t._set_audio_tokens_per_video_frame(1, 32)
+    with pytest.raises(ValueError):
+        t._set_audio_tokens_per_video_frame(5, 4)
+    t._set_audio_tokens_per_video_frame(9 + 220, 32)
+    assert t.audio_tokens_per_video_frame == 7
+    t.weights = {"wqkv": torch.zeros(1)}
+    t.audio_tokens_per_video_frame = 0
+    with pytest.raises(ValueError):
+        t.handle()
+
+
+def test_precision_rule_takes_sampling_calls_from_three_rows(monkeypatch):
+    from vaura_b200.sampler import resolve_precision
+
+    monkeypatch.delenv("VAURA_PRECISION", raising=False)
+    for rows, sampling, want in ((1, True, _cabi.PRECISION_FP32ACT), (2, True, _cabi.PRECISION_FP32ACT),
+                                 (3, True, _cabi.PRECISION_BF16), (15, True, _cabi.PRECISION_BF16),
+                                 (3, False, _cabi.PRECISION_FP32ACT), (15, False, _cabi.PRECISION_FP32ACT),
+                                 (16, False, _cabi.PRECISION_BF16)):
+        assert resolve_precision(_cabi.PRECISION_AUTO, rows, sampling) == want, (rows, sampling)
+
+
+def test_generate_dataset_isolates_failures():
+    """scripts/generate.py:386-389: one clip that raises does not end the run; it is reported and left silent."""
+    from vaura_b200.driver import generate_dataset
+
+    def gen(ids):
+        if 5 in ids.tolist():
+            raise RuntimeError("decode error")
+        return ids.to(torch.float16).view(-1, 1, 1).expand(-1, 1, 4).contiguous()
+
+    failed = []
+    out = generate_dataset(gen, 9, 4, 0, 1, failed=failed)
+    assert failed == [5] and out.shape == (9, 1, 4)
+    assert out[:, 0, 0].tolist() == [0, 1, 2, 3, 4, 0, 6, 7, 8]

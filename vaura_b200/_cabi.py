@@ -41,7 +41,8 @@ class GenerateParamsC(C.Structure):
                 ("start_offset", C.c_int32), ("end_offset", C.c_int32), ("use_sampling", C.c_int32),
                 ("temp", C.c_float), ("top_k", C.c_int32), ("top_p", C.c_float), ("cfg_scale", C.c_float),
                 ("seed", C.c_uint64), ("clip_ids", C.c_void_p), ("sequence", C.c_void_p),
-                ("cond_rows", C.c_void_p), ("logits_out", C.c_void_p), ("precision", C.c_int32)]
+                ("cond_rows", C.c_void_p), ("logits_out", C.c_void_p), ("precision", C.c_int32),
+                ("stream_id", C.c_uint32)]
 
 
 class CodecDimsC(C.Structure):

@@ -25,6 +25,9 @@ class DacModelWrapper(torch.nn.Module):
         super().__init__()
         assert model_sr in MODEL_SR, "Invalid model samplerate"
         self.model_sr = model_sr
+        if isinstance(dims, dict):  # YAML-borne dims (hparams.yaml cannot carry a dataclass)
+            dims = CodecDims(**{k: tuple(v) if isinstance(v, list) else v for k, v in dims.items()})
+        self._dims_given = dims is not None
         self.dims = dims or CodecDims(sample_rate=model_sr)
         self._blob = None
         self._offsets = None
@@ -42,8 +45,32 @@ class DacModelWrapper(torch.nn.Module):
     def half(self):  # the compute path already stores fp16 (vaura_model.py:92)
         return self
 
+    @staticmethod
+    def dims_from_state_dict(sd, sample_rate: int) -> CodecDims:
+        """Shape parameters read off a dac state dict (the reference gets them from the downloaded model's metadata,
+        models/modules/dac/model.py:23-25): conv_in (decoder_dim, latent, 7), ConvTranspose1d kernels (Cin, Cout, 2*rate),
+        one quantizer entry per codebook."""
+        def shape(key):
+            for suffix in (".weight_v", ".weight"):
+                if key + suffix in sd:
+                    return tuple(sd[key + suffix].shape)
+            raise KeyError(key)
+        decoder_dim, latent, _ = shape("decoder.model.0")
+        rates, i = [], 1
+        while any(k.startswith(f"decoder.model.{i}.block.1.") for k in sd):
+            rates.append(shape(f"decoder.model.{i}.block.1")[2] // 2)
+            i += 1
+        n_q = 0
+        while f"quantizer.quantizers.{n_q}.codebook.weight" in sd:
+            n_q += 1
+        size, cdim = sd["quantizer.quantizers.0.codebook.weight"].shape
+        return CodecDims(latent_dim=latent, decoder_dim=decoder_dim, decoder_rates=tuple(rates), n_codebooks=n_q,
+                         codebook_size=size, codebook_dim=cdim, sample_rate=sample_rate)
+
     def load_state_dict(self, state_dict, strict: bool = True, device=None):
         device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if not self._dims_given:
+            self.dims = self.dims_from_state_dict(state_dict, self.model_sr)
         self._blob, self._offsets = pack_codec(state_dict, self.dims, device)
         self._destroy()
         return torch.nn.modules.module._IncompatibleKeys([], [])
@@ -81,7 +108,11 @@ class DacModelWrapper(torch.nn.Module):
         raise NotImplementedError("DAC encode (wav -> codes) is outside the built hot path (SURVEY §8f row 3)")
 
     @torch.no_grad()
-    def decode(self, codes: tp.Union[torch.Tensor, tp.List[tp.Tuple[torch.Tensor, tp.Any]]], max_batch: int = 16):
+    def decode(self, codes: tp.Union[torch.Tensor, tp.List[tp.Tuple[torch.Tensor, tp.Any]]], max_batch: int = 16,
+               validate: bool = True):
+        """``validate``: range-check the codes on the host first (F.embedding raises IndexError in the reference); it
+        costs a device->host synchronisation, so ``VAURAModel.generate`` - whose codes come from the sampling stage and
+        are in range by construction - turns it off.  The kernel clamps indices either way (no out-of-bounds read)."""
         if type(codes) == list:  # EnCodec-style frames (models/modules/dac/model.py:43-44)
             codes = codes[0][0]
         lib = _cabi.load()
@@ -90,7 +121,7 @@ class DacModelWrapper(torch.nn.Module):
         B, Kc, T = codes.shape
         if Kc != self.dims.n_codebooks:
             raise ValueError(f"expected {self.dims.n_codebooks} codebooks, got {Kc}")
-        if codes.numel() and (int(codes.min()) < 0 or int(codes.max()) >= self.dims.codebook_size):
+        if validate and codes.numel() and (int(codes.min()) < 0 or int(codes.max()) >= self.dims.codebook_size):
             raise IndexError("codec code out of range")  # F.embedding would raise in the reference
         hop = self.dims.hop_length
         wav = torch.empty(B, 1, T * hop, dtype=torch.float16, device=dev)

@@ -145,3 +145,33 @@ def load_config(path: str, overrides: Optional[List[str]] = None, base_dir: Opti
     if overrides:
         cfg = merge(cfg, from_dotlist(overrides))
     return resolve(cfg, base_dir=base_dir or os.getcwd())
+
+
+# ---- checkpoint pickers of the generate driver (reference utils/utils.py:25-45) -----------------------------------
+def get_latest_file(path, pattern: str = "*"):
+    """Newest file (ctime) under ``path`` matching ``pattern``."""
+    from pathlib import Path
+
+    files = list(Path(path).glob(pattern))
+    if not files:
+        raise FileNotFoundError(f"No files found in {path} with pattern {pattern}")
+    return max(files, key=lambda x: x.stat().st_ctime)
+
+
+def get_file_with_best_val_loss(path, pattern: str = "*.ckpt"):
+    """The checkpoint whose file name carries the lowest ``val_loss=<float>`` (Lightning's ModelCheckpoint naming);
+    a directory with a single checkpoint returns it whatever its name."""
+    from pathlib import Path
+
+    ckpts = sorted(Path(path).glob(pattern))
+    assert len(ckpts) > 0, f"No files found in {path} with pattern {pattern}"
+    if len(ckpts) == 1:
+        return ckpts[0]
+    best, best_loss = None, float("inf")
+    for f in ckpts:
+        m = re.search(r"val_loss=([0-9]+(?:\.[0-9]+)?)", f.name)
+        if m and float(m.group(1)) < best_loss:
+            best, best_loss = f, float(m.group(1))
+    if best is None:
+        raise FileNotFoundError(f"no checkpoint name under {path} carries val_loss=<float>")
+    return best

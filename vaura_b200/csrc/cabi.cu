@@ -22,9 +22,11 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-static unsigned long long g_launches = 0;  // kernels launched (see vaura_launch_count)
-static unsigned long long g_capture_nodes = 0;
-static bool g_capturing = false;
+// kernels launched (see vaura_launch_count).  One host thread drives a handle (include/vaura_b200.h); the capture flags are
+// per thread so that two threads driving two handles do not see each other's capture.
+static unsigned long long g_launches = 0;
+static thread_local unsigned long long g_capture_nodes = 0;
+static thread_local bool g_capturing = false;
 #define LAUNCHED(n) do { if (g_capturing) g_capture_nodes += (n); else g_launches += (n); } while (0)
 
 #define CU(expr)                                                                                   \
@@ -35,10 +37,22 @@ static bool g_capturing = false;
 
 #define CUL(expr) do { CU(expr); LAUNCHED(1); } while (0)
 
+// Everything a captured decode-step graph bakes in: pointers, shapes and sampling parameters.  A generate() call whose key
+// equals the cached one replays the instantiated graph instead of capturing, instantiating and re-encoding tensor maps.
+struct GraphKey {
+  vaura_generate_params p;
+  vaura_kv_cache kv;
+  void* workspace;
+  int precision, device;
+  bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+
 struct vaura_sampler {
   vaura_sampler_dims d;
   vaura_sampler_weights w;
-  cudaGraphExec_t graph_exec = nullptr;  // decode-step graph of the current generate() call
+  cudaGraphExec_t graph_exec = nullptr;  // decode-step graph of the last generate() call that captured one
+  GraphKey graph_key;                    // valid when graph_exec != nullptr
+  unsigned long long graph_nodes = 0;    // kernel nodes of graph_exec
   cudaStream_t capture_stream = nullptr; // capture origin only (the legacy default stream cannot be captured);
                                          // nothing ever executes on it, graphs are launched on the caller's stream
 };
@@ -80,6 +94,11 @@ extern "C" int vaura_sampler_create(const vaura_sampler_dims* dims, const vaura_
   if (d.vocab != 1024) return fail(VAURA_ERR_UNSUPPORTED, "vocab %d unsupported (sampling kernel is built for 1024)", d.vocab);
   if (d.num_codebooks < 1 || d.num_codebooks > 16) return fail(VAURA_ERR_UNSUPPORTED, "num_codebooks must be 1..16");
   if (d.block_size > kMaxCtx) return fail(VAURA_ERR_UNSUPPORTED, "block_size > %d", kMaxCtx);
+  // every embedding path divides the position by audio_tokens_per_video_frame (llama.py:555-586); the reference raises on
+  // the host for a non-positive value
+  if (d.audio_tokens_per_video_frame < 1)
+    return fail(VAURA_ERR_INVALID, "audio_tokens_per_video_frame = %d must be >= 1", d.audio_tokens_per_video_frame);
+  if (d.cond_tokens < 1 || d.cond_dim < 4 || d.cond_in < 1) return fail(VAURA_ERR_INVALID, "bad conditioning shape");
   int dev = 0, major = 0;
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
@@ -154,15 +173,22 @@ static Workspace carve(const vaura_sampler_dims& d, int rows, int max_pos, int p
 
 // AUTO: the tensor-core path needs at least one 16-row UMMA N/M granule of real work to pay off; below that the
 // decode step is a pure weight stream and the fp32-activation path gives bit-stable greedy tokens.
-static int resolve_precision(int precision, int rows) {
+// From 3 rows the fused bf16 step kernel (~1 ms) is faster than the fp32-activation paths (1.2-2.9 ms at 3..15 rows,
+// profiles/scripts/rows_sweep.py); a call that samples has no bit-exactness contract, so AUTO takes it there as well.
+static int resolve_precision(int precision, int rows, bool sampling) {
   if (precision != VAURA_PRECISION_AUTO) return precision;
-  return rows >= 16 ? VAURA_PRECISION_BF16 : VAURA_PRECISION_FP32ACT;
+  return (rows >= 16 || (rows >= 3 && sampling)) ? VAURA_PRECISION_BF16 : VAURA_PRECISION_FP32ACT;
 }
 
 extern "C" size_t vaura_sampler_workspace_bytes(const vaura_sampler* s, int32_t rows, int32_t max_positions,
                                                 int32_t precision) {
   if (!s || rows <= 0 || max_positions <= 0) return 0;
-  return carve(s->d, rows, max_positions, resolve_precision(precision, rows), nullptr).bytes;
+  if (precision == VAURA_PRECISION_AUTO) {  // the mode depends on the call (sampling or not): enough for either
+    const size_t a = carve(s->d, rows, max_positions, VAURA_PRECISION_BF16, nullptr).bytes;
+    const size_t b = carve(s->d, rows, max_positions, VAURA_PRECISION_FP32ACT, nullptr).bytes;
+    return a > b ? a : b;
+  }
+  return carve(s->d, rows, max_positions, precision, nullptr).bytes;
 }
 
 static KvView kv_view(const vaura_kv_cache* kv, int nhead) {
@@ -365,7 +391,7 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   // sequence positions >= block_size overflow the RoPE table in the reference too (llama.py:493-497)
   if (S - 1 > d.block_size) return fail(VAURA_ERR_INVALID, "sequence of %d columns exceeds block_size %d", S, d.block_size);
   const int rows = p->batch * (p->use_cfg ? 2 : 1);
-  const int precision = resolve_precision(p->precision, rows);
+  const int precision = resolve_precision(p->precision, rows, p->use_sampling && p->temp > 0.f);
   if (precision != VAURA_PRECISION_FP32ACT && precision != VAURA_PRECISION_BF16)
     return fail(VAURA_ERR_INVALID, "unknown precision mode %d", precision);
   int rc = check_kv(s, kv, precision == VAURA_PRECISION_BF16 ? VAURA_KV_BF16 : VAURA_KV_F32);
@@ -381,6 +407,7 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   sa.B = p->batch; sa.K = K; sa.V = d.vocab; sa.S = S; sa.T = p->timesteps; sa.use_cfg = p->use_cfg;
   sa.use_sampling = p->use_sampling; sa.top_k = p->top_k; sa.cfg_scale = p->cfg_scale; sa.temp = p->temp;
   sa.top_p = p->top_p; sa.seed_lo = (uint32_t)p->seed; sa.seed_hi = (uint32_t)(p->seed >> 32);
+  sa.stream_id = p->stream_id;
 
   const char* no_persist = getenv("VAURA_NO_PERSISTENT");
   const bool persist = precision == VAURA_PRECISION_FP32ACT && persistent_supported(rows, d.d_model, d.ffn_dim, kv->page_size) &&
@@ -450,7 +477,19 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     }
     return VAURA_OK;
   }
-  // otherwise: capture one step (reads its position from the device state) and replay it
+  // otherwise: capture one step (reads its position from the device state) and replay it; a call with the same pointers,
+  // shapes and sampling parameters as the last one replays the graph instantiated then
+  GraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.p = *p; key.kv = *kv; key.workspace = workspace; key.precision = precision;
+  cudaGetDevice(&key.device);
+  if (s->graph_exec && s->graph_key == key) {
+    for (int i = 0; i < nsteps; ++i) {
+      CU(cudaGraphLaunch(s->graph_exec, st));
+      g_launches += s->graph_nodes;
+    }
+    return VAURA_OK;
+  }
   cudaGraph_t graph = nullptr;
   cudaStream_t cs = s->capture_stream;
   CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
@@ -473,9 +512,11 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   ce = cudaGraphInstantiate(&s->graph_exec, graph, 0);
   cudaGraphDestroy(graph);
   if (ce != cudaSuccess) return fail(VAURA_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+  s->graph_key = key;
+  s->graph_nodes = g_capture_nodes;
   for (int i = 0; i < nsteps; ++i) {
     CU(cudaGraphLaunch(s->graph_exec, st));
-    g_launches += g_capture_nodes;
+    g_launches += s->graph_nodes;
   }
   return VAURA_OK;
 }
@@ -487,7 +528,7 @@ extern "C" int vaura_sampler_forward(vaura_sampler* s, const int32_t* sequence, 
     return fail(VAURA_ERR_INVALID, "bad argument");
   const vaura_sampler_dims& d = s->d;
   if (S > d.block_size) return fail(VAURA_ERR_INVALID, "S=%d exceeds block_size %d (llama.py:493-497)", S, d.block_size);
-  precision = resolve_precision(precision, rows);
+  precision = resolve_precision(precision, rows, false);
   if (precision != VAURA_PRECISION_FP32ACT && precision != VAURA_PRECISION_BF16)
     return fail(VAURA_ERR_INVALID, "unknown precision mode %d", precision);
   int rc = check_kv(s, kv, precision == VAURA_PRECISION_BF16 ? VAURA_KV_BF16 : VAURA_KV_F32);
@@ -510,6 +551,7 @@ extern "C" int vaura_sample_logits(const float* logits, int32_t rows, int32_t K,
   sa.B = rows; sa.K = K; sa.V = V; sa.S = 0; sa.T = 0; sa.use_cfg = use_cfg; sa.use_sampling = use_sampling;
   sa.top_k = top_k; sa.cfg_scale = cfg_scale; sa.temp = temp; sa.top_p = top_p; sa.seed_lo = (uint32_t)seed;
   sa.seed_hi = (uint32_t)(seed >> 32);
+  sa.stream_id = 0;
   CUL(launch_sample(sa, (cudaStream_t)stream));
   return VAURA_OK;
 }

@@ -17,7 +17,10 @@ __global__ void __launch_bounds__(256) from_codes_kernel(const int32_t* __restri
                                                          __half* __restrict__ z, int Kc, int T, int Vc, int latent) {
   const int t = blockIdx.x, b = blockIdx.y;
   __shared__ int code[16];
-  if (threadIdx.x < Kc) code[threadIdx.x] = codes[((size_t)b * Kc + threadIdx.x) * T + t];
+  if (threadIdx.x < Kc) {  // clamped: an out-of-range code never reads outside the table (the host mirror raises on it)
+    const int c = codes[((size_t)b * Kc + threadIdx.x) * T + t];
+    code[threadIdx.x] = c < 0 ? 0 : (c >= Vc ? Vc - 1 : c);
+  }
   __syncthreads();
   for (int c = threadIdx.x * 2; c < latent; c += blockDim.x * 2) {
     float s0 = 0.f, s1 = 0.f;

@@ -58,7 +58,7 @@ struct KvView {
   }
 };
 
-// Philox4x32-10 (Salmon et al., SC'11).  counter = (clip_id, offset, codebook, 0), key = seed.
+// Philox4x32-10 (Salmon et al., SC'11).  counter = (clip_id, offset, codebook, stream_id), key = seed.
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll

@@ -57,6 +57,7 @@ struct SampleArgs {
   int use_cfg, use_sampling, top_k;
   float cfg_scale, temp, top_p;
   uint32_t seed_lo, seed_hi;
+  uint32_t stream_id;    // 4th Philox counter word: distinguishes calls that reuse (clip id, column, codebook)
 };
 
 struct ConvArgs {

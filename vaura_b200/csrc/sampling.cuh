@@ -134,7 +134,7 @@ static __device__ __noinline__ void sample_row(const SampleArgs& a, int b, int k
   } else {
     // the draw's uniform first: its ten dependent Philox rounds overlap the softmax arithmetic
     const int clip = a.clip_ids ? a.clip_ids[b] : b;
-    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)clip, (uint32_t)offset, (uint32_t)k, 0u),
+    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)clip, (uint32_t)offset, (uint32_t)k, a.stream_id),
                                     make_uint2(a.seed_lo, a.seed_hi));
     const float u01 = (float)(rnd.x >> 8) * (1.0f / 16777216.0f);
     // softmax(logits / temp)  (vaura_model.py:817); sums run as four interleaved chains per lane

@@ -44,12 +44,15 @@ def generate_long(model, frames: torch.Tensor, duration: float, stride: float = 
     """frames: per-segment visual input (B, n_segments, ...), e.g. AVCLIP features (B, S, 8, 768)."""
     all_tokens, prompt_tokens = [], None
     stride_tokens = int(COMPRESSION_MODEL_FRAME_RATE * stride)
-    for ch in chunk_schedule(duration, stride, model_max_duration, vfps):
+    stream0 = int(gen_kwargs.pop("_stream_id", 0) or 0)
+    for wi, ch in enumerate(chunk_schedule(duration, stride, model_max_duration, vfps)):
         pos = torch.tensor(ch["positions"], device=frames.device) % frames.shape[1]
         selected = frames[:, pos]
+        # every window restarts at column 0 with the same clip ids: the window index goes into the Philox counter so
+        # that overlapping windows do not draw the same uniforms for the same columns
         item = model.generate(frames=selected, audio=prompt_tokens, max_new_tokens=ch["max_gen_len"],
                               return_sampled_indices=True, remove_prompts=False, prompt_is_encoded=True,
-                              _decode_audio=False, **gen_kwargs)
+                              _decode_audio=False, _stream_id=stream0 + wi, **gen_kwargs)
         gen_tokens = item["sampled_indices"]
         all_tokens.append(gen_tokens if prompt_tokens is None else gen_tokens[:, :, prompt_tokens.shape[-1]:])
         prompt_tokens = gen_tokens[:, :, stride_tokens:]
@@ -82,21 +85,48 @@ def gather_waveforms(local: torch.Tensor, n_items: int, rank: int, world: int, g
 
 @torch.no_grad()
 def generate_dataset(generate_batch: Callable[[torch.Tensor], torch.Tensor], n_items: int, batch_size: int, rank: int = 0,
-                     world: int = 1, gather: bool = True, group=None):
+                     world: int = 1, gather: bool = True, group=None, failed: Optional[List[int]] = None):
     """Data-parallel generation of ``n_items`` clips.  ``generate_batch(clip_ids int32 (b,)) -> waveforms (b,1,L)``
     must depend only on the clip ids (features and the Philox counters are keyed by clip id), which makes the
     result independent of ``world`` and ``batch_size``.  Returns all waveforms in clip order (every rank) when
-    ``gather`` is set, else this rank's block."""
+    ``gather`` is set, else this rank's block.
+
+    Failure isolation (scripts/generate.py:386-389 wraps every clip in try/except, prints and goes on): a batch that
+    raises is retried clip by clip; a clip that still raises is reported in ``failed`` (its global index is appended
+    when a list is passed) and its waveform is left zero, so one bad input does not end a 15k-clip run."""
     lo, hi = shard_range(n_items, rank, world)
-    blocks = []
+    blocks: List[Optional[torch.Tensor]] = []
+    missing: List[Tuple[int, int]] = []  # (block position, clip id) of clips that failed
     for b0 in range(lo, hi, batch_size):
         ids = torch.arange(b0, min(hi, b0 + batch_size), dtype=torch.int32)
-        blocks.append(generate_batch(ids))
-    if blocks:
+        try:
+            blocks.append(generate_batch(ids))
+            continue
+        except Exception as e:  # noqa: BLE001 - the reference driver catches everything per clip as well
+            print(f"[generate_dataset] rank {rank}: batch {b0}..{int(ids[-1])} failed ({type(e).__name__}: {e}); "
+                  f"retrying clip by clip", flush=True)
+        for cid in ids.tolist():
+            try:
+                blocks.append(generate_batch(torch.tensor([cid], dtype=torch.int32)))
+            except Exception as e:  # noqa: BLE001
+                print(f"[generate_dataset] rank {rank}: clip {cid} failed ({type(e).__name__}: {e})", flush=True)
+                missing.append((len(blocks), cid))
+                blocks.append(None)
+                if failed is not None:
+                    failed.append(cid)
+    good = [b for b in blocks if b is not None]
+    if good:
+        for pos, _ in missing:
+            blocks[pos] = torch.zeros_like(good[0][:1])
         local = torch.cat(blocks, dim=0)
-    else:  # rank beyond the data: learn the waveform shape from a peer-independent dry value
+    elif blocks:  # every clip of the shard failed: the waveform shape is learnt from the peers below
         local = None
+    else:  # rank beyond the data
+        local = None
+    n_failed_here = len(missing)
     if not gather or world == 1:
+        if local is None and blocks:
+            raise RuntimeError(f"all {len(blocks)} clips of rank {rank} failed")
         return local
     import torch.distributed as dist
 
@@ -105,7 +135,7 @@ def generate_dataset(generate_batch: Callable[[torch.Tensor], torch.Tensor], n_i
                         device=local.device if local is not None else _default_device())
     dist.all_reduce(meta, op=dist.ReduceOp.MAX, group=group)
     if local is None:
-        local = torch.zeros(0, 1, int(meta.item()), dtype=torch.float16, device=meta.device)
+        local = torch.zeros(n_failed_here, 1, int(meta.item()), dtype=torch.float16, device=meta.device)
     return gather_waveforms(local, n_items, rank, world, group)
 
 

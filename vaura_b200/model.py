@@ -55,7 +55,12 @@ class VAURAModel(torch.nn.Module):
             self.sampler.codebook_pattern = self.pattern_provider.__class__.__name__
         self.apply_per_video_frame_mask = apply_per_video_frame_mask
         self.return_attention_weights = return_attention_weights
-        self.seed = 0  # Philox key of the device sampler; per-draw counter = (clip id, column, codebook)
+        # Philox key of the device sampler; per-draw counter = (clip id, column, codebook, stream id).  Calls without
+        # clip_indices take consecutive stream ids (the reference's torch.multinomial advances a global generator, so
+        # two calls never repeat their draws either); calls with clip_indices use stream 0 unless `_stream_id` is given,
+        # which makes a clip's tokens a function of (seed, clip id) alone - independent of batching and of the GPU count.
+        self.seed = 0
+        self._auto_stream = 0
 
     # vaura_model.py:690-697
     def _update_sampler_config(self, sampler_config: dict) -> dict:
@@ -122,7 +127,8 @@ class VAURAModel(torch.nn.Module):
                  return_attention_weights: bool = False, return_sampled_indices: bool = False, check: bool = False,
                  use_sampling: bool = True, temp: float = 1.0, top_k: int = 256, top_p: float = 0.0,
                  remove_prompts: bool = False, prompt_is_encoded: bool = False, cfg_scale: float = 1.0,
-                 _return_logits: bool = False, _precision: int = _cabi.PRECISION_AUTO, _decode_audio: bool = True) -> dict:
+                 _return_logits: bool = False, _precision: int = _cabi.PRECISION_AUTO, _decode_audio: bool = True,
+                 _stream_id: Optional[int] = None, _end_offset: Optional[int] = None) -> dict:
         assert not self.training, "do not use generation in training mode"  # vaura_model.py:437
         if return_attention_weights:
             # the reference sampler returns None weights and then indexes them (llama.py:539, vaura_model.py:528)
@@ -165,10 +171,15 @@ class VAURAModel(torch.nn.Module):
         ids = None
         if clip_indices is not None:
             ids = torch.as_tensor(clip_indices).to(device=dev, dtype=torch.int32).contiguous()
+        if _stream_id is None:
+            _stream_id = 0
+            if clip_indices is None:
+                _stream_id = self._auto_stream
+                self._auto_stream += 1
         self.sampler.generate_tokens(seq32, cond_rows, timesteps=max_new_tokens, start_offset=start_offset_sequence,
                                      use_cfg=use_cfg, cfg_scale=cfg_scale, use_sampling=use_sampling, temp=temp,
                                      top_k=top_k, top_p=top_p, seed=self.seed, clip_ids=ids, logits_out=logits_out,
-                                     precision=_precision)
+                                     precision=_precision, stream_id=_stream_id, end_offset=_end_offset)
         gen_sequence = seq32.to(torch.long)
         if check:
             # vaura_model.py:550-558 (these force a device->host sync, as they do in the reference)
@@ -180,7 +191,9 @@ class VAURAModel(torch.nn.Module):
         generated_item: Dict[str, Any] = {}
         if _decode_audio:
             sampled_frames = [(out_codes[..., : self.num_codebooks, :], None)]
-            generated_item["generated_audio"] = self.audio_encoder.decode(sampled_frames)
+            # the tokens were written by the sampling stage (always < vocab; the special id only sits in the pattern cells
+            # that revert_pattern_sequence drops): no host-synchronising range check needed
+            generated_item["generated_audio"] = self.audio_encoder.decode(sampled_frames, validate=False)
         else:
             generated_item["generated_audio"] = None
         generated_item["s_attn_weights"] = None

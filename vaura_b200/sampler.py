@@ -22,18 +22,19 @@ from .weights import pack_sampler
 PAGE_SIZE = int(os.environ.get("VAURA_PAGE_SIZE", "32"))
 
 
-def resolve_precision(precision: int, rows: int) -> int:
-    """Same rule as csrc/cabi.cu: AUTO -> tcgen05/bf16 path from 16 sequence rows, fp32-activation path below.
+def resolve_precision(precision: int, rows: int, sampling: bool = False) -> int:
+    """Same rule as csrc/cabi.cu: AUTO -> tcgen05/bf16 path from 16 sequence rows, and from 3 rows when the call samples
+    (top-k / top-p / temperature draws have no bit-exactness contract); fp32-activation path otherwise.
 
-    ``VAURA_PRECISION=bf16|fp32`` overrides AUTO: at 3...15 rows the bf16 path (one fused kernel per step, ~1.0-1.1 ms)
-    is 1.2-3x faster than the fp32-activation paths (1.2-2.9 ms, profiles/scripts/rows_sweep.py) at bf16 tolerance
-    instead of bit-exact greedy tokens; at 1-2 rows the fp32-activation cluster kernel is both exact and 3x faster."""
+    At 3...15 rows the bf16 path (one fused kernel per step, ~1 ms) is 1.2-3x faster than the fp32-activation paths
+    (1.2-2.9 ms, profiles/scripts/rows_sweep.py) at bf16 tolerance instead of bit-exact greedy tokens; at 1-2 rows the
+    fp32-activation cluster kernel is both exact and 3x faster.  ``VAURA_PRECISION=bf16|fp32`` overrides AUTO."""
     if precision != _cabi.PRECISION_AUTO:
         return precision
     env = os.environ.get("VAURA_PRECISION", "").lower()
     if env in ("bf16", "fp32"):
         return _cabi.PRECISION_BF16 if env == "bf16" else _cabi.PRECISION_FP32ACT
-    return _cabi.PRECISION_BF16 if rows >= 16 else _cabi.PRECISION_FP32ACT
+    return _cabi.PRECISION_BF16 if (rows >= 16 or (rows >= 3 and sampling)) else _cabi.PRECISION_FP32ACT
 
 
 class _CondEmbedder:
@@ -84,7 +85,13 @@ class Transformer(torch.nn.Module):
         # llama.py:544-553
         pat = (self.codebook_pattern or "delayed").lower()
         Ta = Ta - self.num_codebooks if "delayed" in pat else Ta - 1
-        self.audio_tokens_per_video_frame = ceil(Ta / Tv)
+        atpvf = ceil(Ta / Tv)
+        if atpvf < 1:
+            # the reference goes on to `range(0, Ta, 0)` / a negative stride and raises on the host (llama.py:555-586);
+            # the kernels divide the position by this value
+            raise ValueError(f"audio_tokens_per_video_frame = ceil({Ta} / {Tv}) = {atpvf} must be >= 1: set "
+                             "sampler.audio_tokens_per_video_frame explicitly (scripts/generate.py:216 sets 7)")
+        self.audio_tokens_per_video_frame = atpvf
 
     def load_state_dict(self, state_dict, strict: bool = True, device=None):
         device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -116,6 +123,8 @@ class Transformer(torch.nn.Module):
             raise RuntimeError("sampler weights are not loaded (load_state_dict / load_from_checkpoint first)")
         if self.audio_tokens_per_video_frame is None:
             raise RuntimeError("sampler.audio_tokens_per_video_frame is not set (scripts/generate.py:216 sets 7)")
+        if int(self.audio_tokens_per_video_frame) < 1:
+            raise ValueError(f"sampler.audio_tokens_per_video_frame = {self.audio_tokens_per_video_frame} must be >= 1")
         if self._handle is not None and self._handle_atpvf == self.audio_tokens_per_video_frame:
             return self._handle
         self._destroy()
@@ -209,7 +218,8 @@ class Transformer(torch.nn.Module):
     def generate_tokens(self, sequence: torch.Tensor, cond_rows: torch.Tensor, timesteps: int, start_offset: int,
                         use_cfg: bool, cfg_scale: float, use_sampling: bool, temp: float, top_k: int, top_p: float,
                         seed: int = 0, clip_ids: Optional[torch.Tensor] = None, logits_out: Optional[torch.Tensor] = None,
-                        end_offset: Optional[int] = None, precision: int = _cabi.PRECISION_AUTO) -> torch.Tensor:
+                        end_offset: Optional[int] = None, precision: int = _cabi.PRECISION_AUTO,
+                        stream_id: int = 0) -> torch.Tensor:
         """Run the fused decode loop in place on ``sequence`` (B,K,S) int32 (-1 = to be generated)."""
         lib = _cabi.load()
         assert sequence.dtype == torch.int32 and sequence.is_contiguous() and sequence.device == self.device
@@ -217,7 +227,7 @@ class Transformer(torch.nn.Module):
         rows = B * (2 if use_cfg else 1)
         assert cond_rows.shape[0] == rows and cond_rows.is_contiguous()
         h = self.handle()
-        precision = resolve_precision(precision, rows)
+        precision = resolve_precision(precision, rows, bool(use_sampling) and float(temp) > 0.0)
         nbytes = lib.vaura_sampler_workspace_bytes(h, rows, max(start_offset, 1), precision)
         ws = self._buffer("ws", nbytes)
         kv = self._kv(rows, _cabi.KV_BF16 if precision == _cabi.PRECISION_BF16 else _cabi.KV_F32)
@@ -227,7 +237,7 @@ class Transformer(torch.nn.Module):
             top_k=int(top_k), top_p=float(top_p), cfg_scale=float(cfg_scale), seed=int(seed) & (2 ** 64 - 1),
             clip_ids=clip_ids.data_ptr() if clip_ids is not None else None, sequence=sequence.data_ptr(),
             cond_rows=cond_rows.data_ptr(), logits_out=logits_out.data_ptr() if logits_out is not None else None,
-            precision=precision)
+            precision=precision, stream_id=int(stream_id) & 0xFFFFFFFF)
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream().cuda_stream
             _cabi.check(lib.vaura_sampler_generate(h, C.byref(p), C.byref(kv), ws.data_ptr(), ws.numel(), st),

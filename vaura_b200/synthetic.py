@@ -212,3 +212,32 @@ def make_avclip_features(batch: int, seed: int, segments: int = 4, tokens_per_se
     return torch.stack([
         _randn(seed, f"avclip.{b}", (segments, tokens_per_segment, width)) for b in range(batch)
     ])
+
+
+def build_model(sdims: SamplerDims = FULL_SAMPLER, cdims: CodecDims = FULL_CODEC, seed: int = 0, device="cuda:0"):
+    """``VAURAModel`` of the named shape with the synthetic weights above, built through the same constructor
+    keywords an experiment's ``hparams.yaml`` carries (reference ``target:`` strings; vaura_model.py:28-48) and put
+    in the state ``scripts/generate.py:212-216`` leaves it in (eval mode, 7 audio tokens per video frame)."""
+    from .model import VAURAModel
+
+    cfg = dict(
+        use_visual_conditioning=True,
+        feature_extractor_config={"target": "models.modules.feature_extractors.avclip.motionformer.MotionFormer",
+                                  "params": {}},
+        audio_encoder_config={"target": "models.modules.dac.model.DacModelWrapper",
+                              "params": {"model_sr": 44100, "dims": cdims}},
+        sampler_config={"target": "models.modules.sampler.llama.Transformer",
+                        "params": dict(num_layers=sdims.num_layers, d_model=sdims.d_model, d_codebook=sdims.d_codebook,
+                                       nhead=sdims.nhead, num_codebooks=sdims.num_codebooks,
+                                       block_size_audio=sdims.block_size, block_size_video=64,
+                                       cond_feature_channel_scaler=sdims.cond_feature_channel_scaler)},
+        visual_bridge_config={"target": "torch.nn.Identity"},
+        pattern_provider_config={"target": "models.modules.misc.codebook_patterns.DelayedPatternProvider",
+                                 "params": {"n_q": sdims.num_codebooks}},
+        flatten_vis_feats=True,
+    )
+    m = VAURAModel(**cfg)
+    m.load_state_dict(make_checkpoint_state_dict(sdims, cdims, seed), device=device)
+    m.eval()
+    m.sampler.audio_tokens_per_video_frame = 7
+    return m
