@@ -136,6 +136,7 @@ struct Workspace {
   float *h, *q, *attn, *act, *logits, *attn_part;        // fp32act path
   long long* xfix;                                       // fp32act path, cluster decode kernel (rows <= 2)
   __nv_bfloat16 *xn_b, *q_b, *attn_b, *act_b;            // bf16 path (h and logits stay fp32)
+  __nv_bfloat16 *x3, *act3;                              // fp32act path, tensor-core prefill: operands as three bf16 terms
   size_t bytes;
 };
 
@@ -166,6 +167,10 @@ static Workspace carve(const vaura_sampler_dims& d, int rows, int max_pos, int p
     w.act = (float*)take(R * d.ffn_dim * 4);
     w.attn_part = (float*)take(persistent_attn_part_bytes(rows, d.nhead));
     w.xfix = (long long*)take(cluster_xfix_bytes(rows <= 2 ? rows : 1, d.num_layers));
+    if (R >= 16) {  // multi-position passes (prefill, teacher-forced forward) run their GEMMs on the tensor cores
+      w.x3 = (__nv_bfloat16*)take(R * 3 * d.d_model * 2);
+      w.act3 = (__nv_bfloat16*)take(R * 3 * d.ffn_dim * 2);
+    }
   }
   w.bytes = off;
   return w;
@@ -202,6 +207,10 @@ static KvView kv_view(const vaura_kv_cache* kv, int nhead) {
   return v;
 }
 
+static int transformer_pass_tc3(const vaura_sampler* s, const Workspace& ws, const int32_t* seq, int batch, int S,
+                                const float* cond_rows, int rows, int npos, int pos0, const StepState* state,
+                                const KvView& kv, float* logits_dst, bool logits_all, cudaStream_t st);
+
 // One transformer pass over `npos` new positions per sequence row (fp32act path).
 //   state != nullptr: positions come from the device-resident loop state (graph replay);
 //   otherwise pos0 is the first new position.
@@ -213,6 +222,12 @@ static int transformer_pass(const vaura_sampler* s, const Workspace& ws, const i
   const vaura_sampler_dims& d = s->d;
   const vaura_sampler_weights& w = s->w;
   const int R = rows * npos;
+  {
+    static int tc3 = -1;  // VAURA_PREFILL_TC=0: keep multi-position passes on the GEMV kernels
+    if (tc3 < 0) { const char* ev = getenv("VAURA_PREFILL_TC"); tc3 = !(ev && ev[0] == '0'); }
+    if (tc3 && npos > 1 && R >= 16 && ws.x3 && d.d_model % 64 == 0 && d.ffn_dim % 64 == 0)
+      return transformer_pass_tc3(s, ws, seq, batch, S, cond_rows, rows, npos, pos0, state, kv, logits_dst, logits_all, st);
+  }
   EmbedArgs e{};
   e.seq = seq; e.cond_rows = cond_rows; e.tables = w.tok_tables; e.h = ws.h; e.state = state; e.pos0 = pos0;
   e.npos = npos; e.batch = batch; e.K = d.num_codebooks; e.S = S; e.vocab = d.vocab; e.d_model = d.d_model;
@@ -248,6 +263,70 @@ static int transformer_pass(const vaura_sampler* s, const Workspace& ws, const i
   if (logits_all) { g.x = ws.h; g.ldx = D; g.R = R; g.perm_S = npos; g.perm_V = d.vocab; }
   else { g.x = ws.h + (size_t)(npos - 1) * D; g.ldx = (size_t)npos * D; g.R = rows; }
   CUL(launch_gemv(EPI_STORE, true, g, st));
+  return VAURA_OK;
+}
+
+// The fp32-activation pass over many positions (prompt prefill of a chunked long clip, teacher-forced forward) with the four
+// projections of a layer on the tensor cores: every fp32 A operand is split into three bf16 terms (x = t1 + t2 + t3 to 24
+// significant bits, common.cuh: split3) laid side by side along K, the bf16 weights are multiplied with each term
+// (LinearTcArgs::w_k re-reads their K blocks) and tcgen05 accumulates in fp32 - the products are the fp32 products, only
+// the summation order differs from gemv_kernel.  The weights are read once per pass instead of once per 8 rows
+// (launch_gemv_nb: ceil(166 / 8) = 21 passes for a 166-position prompt).  KV cache, q, attention and the residual stream
+// stay fp32, so the decode steps that follow continue bit-compatibly.  No split-K: every output element has one owner
+// and the result is deterministic.
+static int transformer_pass_tc3(const vaura_sampler* s, const Workspace& ws, const int32_t* seq, int batch, int S,
+                                const float* cond_rows, int rows, int npos, int pos0, const StepState* state,
+                                const KvView& kv, float* logits_dst, bool logits_all, cudaStream_t st) {
+  const vaura_sampler_dims& d = s->d;
+  const vaura_sampler_weights& w = s->w;
+  const int R = rows * npos;
+  EmbedArgs e{};
+  e.seq = seq; e.cond_rows = cond_rows; e.tables = w.tok_tables; e.h = ws.h; e.state = state; e.pos0 = pos0;
+  e.npos = npos; e.batch = batch; e.K = d.num_codebooks; e.S = S; e.vocab = d.vocab; e.d_model = d.d_model;
+  e.cond_dim = d.cond_dim; e.cond_tokens = d.cond_tokens; e.atpvf = d.audio_tokens_per_video_frame;
+  CUL(launch_embed(e, R, st));
+  const size_t D = d.d_model, F = d.ffn_dim;
+  // N tiles: enough CTAs to cover the SMs with ceil(R / 128) row tiles
+  const int mt = (R + 127) / 128;
+  auto pick_bn = [&](int N) { for (int bn : {128, 64, 32}) if (N % bn == 0 && (N / bn) * mt >= 96) return bn; return N % 32 == 0 ? 32 : 16; };
+  for (int l = 0; l < d.num_layers; ++l) {
+    LinearTcArgs g{};
+    g.state = state; g.pos0 = pos0; g.npos = npos; g.R = R; g.layer = l; g.d_model = d.d_model; g.kv = kv; g.rope = w.rope;
+    g.ksplit = 1; g.pdl = 0;
+    CUL(launch_rmsnorm_split3(ws.h, w.attn_norm + l * D, ws.x3, R, (int)D, D, d.norm_eps, st));
+    g.A = ws.x3; g.lda = 3 * D; g.K = 3 * D; g.w_k = D; g.W = w.wqkv + (size_t)l * 3 * D * D; g.N = 3 * D; g.epi = EPI_QKV_F32;
+    g.out_f32 = ws.q; g.ldo = D; g.block_n = pick_bn(3 * D);
+    CUL(launch_linear_tc(g, st));
+    AttnArgs a{};
+    a.q = ws.q; a.out = ws.attn; a.out3 = reinterpret_cast<uint16_t*>(ws.x3); a.kv = kv; a.state = state; a.pos0 = pos0;
+    a.npos = npos; a.layer = l; a.d_model = d.d_model; a.scale = 1.0f / sqrtf((float)kHeadDim);
+    CUL(launch_attn(a, d.nhead, R, st));
+    g.A = ws.x3; g.lda = 3 * D; g.K = 3 * D; g.w_k = D; g.W = w.wo + (size_t)l * D * D; g.N = D; g.epi = EPI_RESID;
+    g.out_f32 = ws.h; g.ldo = D; g.block_n = pick_bn(D);
+    CUL(launch_linear_tc(g, st));
+    CUL(launch_rmsnorm_split3(ws.h, w.ffn_norm + l * D, ws.x3, R, (int)D, D, d.norm_eps, st));
+    g.A = ws.x3; g.lda = 3 * D; g.K = 3 * D; g.w_k = D; g.W = w.w13 + (size_t)l * 2 * F * D; g.N = 2 * F; g.epi = EPI_SWIGLU_SPLIT3;
+    g.out_bf16 = ws.act3; g.ldo = 3 * F; g.aux = (int)F; g.block_n = pick_bn(2 * F);
+    CUL(launch_linear_tc(g, st));
+    g.A = ws.act3; g.lda = 3 * F; g.K = 3 * F; g.w_k = F; g.W = w.w2 + (size_t)l * D * F; g.N = D; g.epi = EPI_RESID;
+    g.out_f32 = ws.h; g.ldo = D; g.block_n = pick_bn(D);
+    CUL(launch_linear_tc(g, st));
+  }
+  if (logits_all) {  // every position feeds the heads: the logits land in the reference layout [rows][K][S][V] (llama.py:504)
+    LinearTcArgs g{};
+    g.state = state; g.pos0 = pos0; g.npos = npos; g.d_model = d.d_model; g.ksplit = 1;
+    CUL(launch_rmsnorm_split3(ws.h, w.final_norm, ws.x3, R, (int)D, D, d.norm_eps, st));
+    g.A = ws.x3; g.lda = 3 * D; g.K = 3 * D; g.w_k = D; g.W = w.w_heads; g.N = d.num_codebooks * d.vocab; g.R = R;
+    g.epi = EPI_STORE; g.out_f32 = logits_dst; g.ldo = g.N; g.perm_S = npos; g.perm_V = d.vocab; g.block_n = 128;
+    if (g.N % 128) return fail(VAURA_ERR_UNSUPPORTED, "heads width %d is not a multiple of 128", g.N);
+    CUL(launch_linear_tc(g, st));
+  } else {  // only the last position of every sequence row feeds the heads: a few rows, the weight-streaming GEMV
+    GemvArgs g{};
+    g.state = state; g.pos0 = pos0; g.npos = npos; g.layer = 0; g.d_model = d.d_model; g.eps = d.norm_eps;
+    g.W = w.w_heads; g.norm_w = w.final_norm; g.N = d.num_codebooks * d.vocab; g.K = D; g.ldo = g.N; g.out = logits_dst;
+    g.x = ws.h + (size_t)(npos - 1) * D; g.ldx = (size_t)npos * D; g.R = rows;
+    CUL(launch_gemv(EPI_STORE, true, g, st));
+  }
   return VAURA_OK;
 }
 

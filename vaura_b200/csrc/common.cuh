@@ -37,6 +37,15 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
+// x = t1 + t2 + t3 with bf16 terms: 3 x 8 significant bits cover the 24 of an fp32, so bf16 x bf16 products of the terms
+// accumulated in fp32 reproduce the fp32 product (what decode_cluster.cu does with mma.sync, here for tcgen05 prefill)
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& t1, __nv_bfloat16& t2, __nv_bfloat16& t3) {
+  t1 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(t1);
+  t2 = __float2bfloat16_rn(r1);
+  t3 = __float2bfloat16_rn(r1 - __bfloat162float(t2));
+}
+
 // 16-byte streaming load: weights are read exactly once per step, keep them out of L1.
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
   uint4 r;

@@ -46,6 +46,53 @@ __global__ void __launch_bounds__(512) rmsnorm_bf16_kernel(const float* __restri
   }
 }
 
+// RMSNorm in fp32 with the GEMV path's operation order ((x * rs) * w, llama.py:157-158), output as three bf16 terms
+// side by side: out3[r][0:D] | [D:2D] | [2D:3D]
+__global__ void __launch_bounds__(512) rmsnorm_split3_kernel(const float* __restrict__ h, const float* __restrict__ w,
+                                                             __nv_bfloat16* __restrict__ out3, int D, size_t ldh, float eps) {
+  __shared__ float red[16];
+  const int r = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* x = h + (size_t)r * ldh;
+  const int n4 = D >> 2;
+  float4 v[2];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = tid + i * blockDim.x;
+    v[i] = c < n4 ? *reinterpret_cast<const float4*>(x + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float rs = rsqrtf(tot / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = tid + i * blockDim.x;
+    if (c < n4) {
+      const float4 g = *reinterpret_cast<const float4*>(w + 4 * c);
+      const float y[4] = {v[i].x * rs * g.x, v[i].y * rs * g.y, v[i].z * rs * g.z, v[i].w * rs * g.w};
+      __nv_bfloat16 t[3][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split3(y[e], t[0][e], t[1][e], t[2][e]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        *reinterpret_cast<uint2*>(out3 + (size_t)r * 3 * D + (size_t)k * D + 4 * c) = *reinterpret_cast<const uint2*>(t[k]);
+    }
+  }
+}
+
+cudaError_t launch_rmsnorm_split3(const float* h, const float* w, void* out3, int R, int D, size_t ldh, float eps, cudaStream_t st) {
+  int threads = ((D / 4 + 1) / 2 + 31) / 32 * 32;  // two float4 per thread
+  if (threads > 512) threads = 512;
+  if (threads < 32) threads = 32;
+  if (D % 4 != 0 || D / 4 > 2 * threads) return cudaErrorInvalidValue;
+  rmsnorm_split3_kernel<<<R, threads, 0, st>>>(h, w, reinterpret_cast<__nv_bfloat16*>(out3), D, ldh, eps);
+  return cudaGetLastError();
+}
+
 static cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st, cudaLaunchAttribute* attr, int pdl) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;

@@ -306,11 +306,130 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnArgs a) {
       a3 = fmaf(sc[jj + 3], kvp[a.kv.row(a.layer, 1, b, jj + 3, h) + tid], a3);
     }
     for (; jj < nctx; ++jj) a0 = fmaf(sc[jj], kvp[a.kv.row(a.layer, 1, b, jj, h) + tid], a0);
-    a.out[(size_t)row * a.d_model + h * kHeadDim + tid] = ((a0 + a1) + (a2 + a3)) / sum;
+    const float o = ((a0 + a1) + (a2 + a3)) / sum;
+    a.out[(size_t)row * a.d_model + h * kHeadDim + tid] = o;
+    if (a.out3) {  // the wo GEMM of the tensor-core prefill reads the row as three bf16 terms
+      __nv_bfloat16 t1, t2, t3;
+      split3(o, t1, t2, t3);
+      __nv_bfloat16* o3 = reinterpret_cast<__nv_bfloat16*>(a.out3) + (size_t)row * 3 * a.d_model + h * kHeadDim + tid;
+      o3[0] = t1; o3[a.d_model] = t2; o3[2 * a.d_model] = t3;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// causal attention of a multi-position pass (prompt prefill, teacher-forced forward) over the paged fp32 KV cache:
+// one CTA per (head, 32 consecutive query positions of one sequence).  Keys / values are staged 32 positions at a time
+// in shared memory and shared by the 32 queries (attn_kernel re-reads the whole context per query: 166 x the K/V
+// traffic for a 166-position prompt); flash-style online softmax in fp32 (llama.py:246-255, scale 1/sqrt(96)).
+// Warp w owns queries 4w..4w+3: scores with lane = key (K rows padded to 97 floats: conflict-free), P.V with lane =
+// output dims lane, lane + 32, lane + 64.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPfQ = 32, kPfK = 32, kPfThreads = 256;
+__global__ void __launch_bounds__(kPfThreads) attn_prefill_kernel(AttnArgs a) {
+  __shared__ float qs[kPfQ][kHeadDim];
+  __shared__ float ks[kPfK][kHeadDim + 1];
+  __shared__ float vs[kPfK][kHeadDim];
+  __shared__ float ps[kPfThreads / 32][kPfK][4];
+  const int h = blockIdx.x, j0 = blockIdx.y * kPfQ, b = blockIdx.z;
+  const int pos0 = a.state ? a.state->offset - a.npos : a.pos0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nq = min(kPfQ, a.npos - j0);
+  const float* kvp = reinterpret_cast<const float*>(a.kv.pages);
+  for (int i = tid; i < kPfQ * (kHeadDim / 4); i += kPfThreads) {
+    const int qi = i / (kHeadDim / 4), c = i % (kHeadDim / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (qi < nq) v = *reinterpret_cast<const float4*>(a.q + (size_t)(b * a.npos + j0 + qi) * a.d_model + h * kHeadDim + 4 * c);
+    *reinterpret_cast<float4*>(&qs[qi][4 * c]) = v;
+  }
+  float m[4], l[4], acc[4][3];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { m[u] = -INFINITY; l[u] = 0.f; acc[u][0] = acc[u][1] = acc[u][2] = 0.f; }
+  const int last_pos = pos0 + j0 + nq - 1;  // last key any query of this block may see
+  for (int k0 = 0; k0 <= last_pos; k0 += kPfK) {
+    __syncthreads();  // previous tile consumed (and qs written, first iteration)
+    {  // stage 32 key / value rows: 8 threads per position, 3 float4 each
+      const int r = tid >> 3, c = tid & 7, pos = k0 + r;
+      if (pos <= last_pos) {
+        const float4* kr = reinterpret_cast<const float4*>(kvp + a.kv.row(a.layer, 0, b, pos, h));
+        const float4* vr = reinterpret_cast<const float4*>(kvp + a.kv.row(a.layer, 1, b, pos, h));
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float4 kk = kr[c + 8 * i], vv = vr[c + 8 * i];
+          float* kd = &ks[r][4 * (c + 8 * i)];
+          kd[0] = kk.x; kd[1] = kk.y; kd[2] = kk.z; kd[3] = kk.w;
+          *reinterpret_cast<float4*>(&vs[r][4 * (c + 8 * i)]) = vv;
+        }
+      }
+    }
+    __syncthreads();
+    // scores of this warp's 4 queries against key k0 + lane
+    float sc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int kpos = k0 + lane;
+#pragma unroll 4
+    for (int d4 = 0; d4 < kHeadDim / 4; ++d4) {
+      const float k0v = ks[lane][4 * d4], k1v = ks[lane][4 * d4 + 1], k2v = ks[lane][4 * d4 + 2], k3v = ks[lane][4 * d4 + 3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 qv = *reinterpret_cast<const float4*>(&qs[4 * warp + u][4 * d4]);
+        sc[u] = fmaf(qv.x, k0v, sc[u]); sc[u] = fmaf(qv.y, k1v, sc[u]);
+        sc[u] = fmaf(qv.z, k2v, sc[u]); sc[u] = fmaf(qv.w, k3v, sc[u]);
+      }
+    }
+    float corr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int qpos = pos0 + j0 + 4 * warp + u;
+      const bool ok = kpos <= qpos && 4 * warp + u < nq;
+      const float sv = ok ? sc[u] * a.scale : -INFINITY;
+      const float mn = fmaxf(m[u], warp_max(sv));
+      const float pe = ok ? expf(sv - mn) : 0.f;           // mn is finite whenever ok (the key itself is visible)
+      corr[u] = m[u] == -INFINITY ? 0.f : expf(m[u] - mn);  // no key seen yet: nothing to rescale
+      if (mn == -INFINITY) corr[u] = 0.f;
+      l[u] = l[u] * corr[u] + warp_sum(pe);
+      m[u] = mn;
+      ps[warp][lane][u] = pe;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc[u][0] *= corr[u]; acc[u][1] *= corr[u]; acc[u][2] *= corr[u]; }
+    const int nk = min(kPfK, last_pos - k0 + 1);
+    for (int j = 0; j < nk; ++j) {
+      const float4 pv = *reinterpret_cast<const float4*>(&ps[warp][j][0]);
+      const float v0 = vs[j][lane], v1 = vs[j][lane + 32], v2 = vs[j][lane + 64];
+      acc[0][0] = fmaf(pv.x, v0, acc[0][0]); acc[0][1] = fmaf(pv.x, v1, acc[0][1]); acc[0][2] = fmaf(pv.x, v2, acc[0][2]);
+      acc[1][0] = fmaf(pv.y, v0, acc[1][0]); acc[1][1] = fmaf(pv.y, v1, acc[1][1]); acc[1][2] = fmaf(pv.y, v2, acc[1][2]);
+      acc[2][0] = fmaf(pv.z, v0, acc[2][0]); acc[2][1] = fmaf(pv.z, v1, acc[2][1]); acc[2][2] = fmaf(pv.z, v2, acc[2][2]);
+      acc[3][0] = fmaf(pv.w, v0, acc[3][0]); acc[3][1] = fmaf(pv.w, v1, acc[3][1]); acc[3][2] = fmaf(pv.w, v2, acc[3][2]);
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int qi = 4 * warp + u;
+    if (qi >= nq) continue;
+    const size_t row = (size_t)b * a.npos + j0 + qi;
+    const float inv = 1.f / l[u];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float o = acc[u][i] * inv;
+      const int col = h * kHeadDim + lane + 32 * i;
+      a.out[row * a.d_model + col] = o;
+      if (a.out3) {
+        __nv_bfloat16 t1, t2, t3;
+        split3(o, t1, t2, t3);
+        __nv_bfloat16* o3 = reinterpret_cast<__nv_bfloat16*>(a.out3) + row * 3 * a.d_model + col;
+        o3[0] = t1; o3[a.d_model] = t2; o3[2 * a.d_model] = t3;
+      }
+    }
   }
 }
 
 cudaError_t launch_attn(const AttnArgs& a, int nhead, int rows, cudaStream_t st) {
+  if (a.npos >= 16 && rows % a.npos == 0) {  // multi-position pass: keys / values shared by 32 queries per CTA
+    attn_prefill_kernel<<<dim3(nhead, (a.npos + kPfQ - 1) / kPfQ, rows / a.npos), kPfThreads, 0, st>>>(a);
+    return cudaGetLastError();
+  }
   attn_kernel<<<dim3(nhead, rows), 128, 0, st>>>(a);
   return cudaGetLastError();
 }

@@ -195,6 +195,8 @@ struct TcShape {
   int ksplit;                  // split-K factor (linear layers with an accumulating epilogue); grid.z = batch*nphase*ksplit
   int pdl;                     // launched with programmatic stream serialization: weights may be fetched before the
                                // prerequisite grid has finished, everything else waits on griddepcontrol
+  int bwrap;                   // > 0: operand B has only this many K blocks; block kb of the K loop reads block kb % bwrap
+                               // (A = several bf16 terms of a split fp32 operand side by side, see LinearTcArgs::w_k)
   int tap_off[32];             // [nphase][ntaps] row shift of the A box
 };
 
@@ -287,6 +289,7 @@ struct EpiLinear {
     const StepState* state;
     int pos0, npos, layer, d_model;
     int atomic;
+    int aux;              // EPI_SWIGLU_SPLIT3: F
   };
   // what the RoPE / KV-append epilogue of one 16-column chunk reads from global memory besides the accumulator: eight
   // (cos, sin) pairs and the destination row in the paged cache.  The fused step kernel requests them before it waits for
@@ -366,6 +369,38 @@ struct EpiLinear {
         h[i] = __floats2bfloat162_rn(__fdividef(a0, 1.f + __expf(-a0)) * b0, __fdividef(a1, 1.f + __expf(-a1)) * b1);
       }
       *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)m * p.ldo + (n0 >> 1)) = o;
+    } else if (p.mode == EPI_SWIGLU_SPLIT3) {
+      // fp32-activation prefill: exact SiLU (same expression as gemv_kernel<EPI_SWIGLU>), the 8 results of the chunk stored as
+      // three bf16 terms at [m][j], [m][F + j], [m][2F + j]
+      __nv_bfloat16 t[3][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a0 = v[2 * i], b0 = v[2 * i + 1];
+        split3(a0 / (1.f + expf(-a0)) * b0, t[0][i], t[1][i], t[2][i]);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)m * p.ldo + (size_t)k * p.aux + (n0 >> 1)) = *reinterpret_cast<const uint4*>(t[k]);
+    } else if (p.mode == EPI_QKV_F32) {
+      // RoPE (llama.py:633-650), q -> fp32 [R][d], K/V -> fp32 pages (what gemv_kernel<EPI_QKV> writes)
+      const int D = p.d_model, sec = n0 / D, within = n0 % D;
+      const int hd = within / kHeadDim, e = within % kHeadDim;
+      const int b = m / p.npos, j = m % p.npos;
+      const int pos = (p.state ? p.state->offset - p.npos : p.pos0) + j;
+      if (sec != 2) {
+        const float4* cs = reinterpret_cast<const float4*>(p.rope + ((size_t)pos * (kHeadDim / 2) + (e >> 1)) * 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 c = cs[i];
+          const float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
+          v[4 * i] = x0 * c.x - x1 * c.y; v[4 * i + 1] = x1 * c.x + x0 * c.y;
+          v[4 * i + 2] = x2 * c.z - x3 * c.w; v[4 * i + 3] = x3 * c.z + x2 * c.w;
+        }
+      }
+      float* dst = sec == 0 ? p.out_f32 + (size_t)m * D + within
+                            : reinterpret_cast<float*>(p.kv.pages) + p.kv.row(p.layer, sec - 1, b, pos, hd) + e;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     } else {  // EPI_QKV
       const int D = p.d_model, sec = n0 / D, within = n0 % D;
       const int hd = within / kHeadDim, e = within % kHeadDim;
@@ -449,56 +484,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // NOTE: triggering the dependent grid BEFORE this grid's own griddepcontrol.wait was measured to break the chain
   // (the dependent's wait then no longer covers our prerequisite); the trigger is issued after the wait, below.
 
+  // warps 0 and 1 walk their loops with all 32 lanes (uniform control flow) and one elected lane issues: inside
+  // `if (lane == 0)` every tensor copy / MMA costs an ELECT + R2UR loop (~0.13 us per copy, ~41 ns per MMA; measured
+  // 0.54 us per 64-wide K block on the prefill GEMMs before this change)
   if (warp == 0) {
-    if (lane == 0) {
-      // weights (operand B) do not depend on the previous kernel: fill the first ring pass before waiting for it
-      const int pre = (g.pdl & 4) ? min(iters, STAGES) : 0;
-      for (int it = 0; it < pre; ++it) {
-        const int u0 = u_begin + it * KSUB, nsub = min(KSUB, u_end - u0);
-        mbar_expect_tx(&full[it], nsub * SUB_BYTES);
-        for (int sub = 0; sub < nsub; ++sub) {
-          const int gi = u0 + sub, tap = gi / g.kblocks, kb = gi % g.kblocks;
-          tma_load_3d(smem + it * STAGE_BYTES + sub * SUB_BYTES + A_BYTES, &tmB, &full[it], kb * BLOCK_K, n0, phase * g.ntaps + tap);
-        }
-      }
-      if (g.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        const int u0 = u_begin + it * KSUB, nsub = min(KSUB, u_end - u0);
-        uint8_t* ss = smem + s * STAGE_BYTES;
-        if (it >= pre) {
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], nsub * SUB_BYTES);
-        }
-        for (int sub = 0; sub < nsub; ++sub) {
-          const int gi = u0 + sub, tap = gi / g.kblocks, kb = gi % g.kblocks;
-          uint8_t* sa = ss + sub * SUB_BYTES;
-          if (it >= pre) tma_load_3d(sa + A_BYTES, &tmB, &full[s], kb * BLOCK_K, n0, phase * g.ntaps + tap);
-          tma_load_3d(sa, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
-        }
+    // weights (operand B) do not depend on the previous kernel: fill the first ring pass before waiting for it
+    const int pre = (g.pdl & 4) ? min(iters, STAGES) : 0;
+    for (int it = 0; it < pre; ++it) {
+      const int u0 = u_begin + it * KSUB, nsub = min(KSUB, u_end - u0);
+      mbar_expect_tx_elect(&full[it], nsub * SUB_BYTES);
+      for (int sub = 0; sub < nsub; ++sub) {
+        const int gi = u0 + sub, tap = gi / g.kblocks, kb = gi % g.kblocks;
+        const int kbB = g.bwrap ? kb % g.bwrap : kb;
+        tma_load_3d_elect(smem + it * STAGE_BYTES + sub * SUB_BYTES + A_BYTES, &tmB, &full[it], kbB * BLOCK_K, n0, phase * g.ntaps + tap);
       }
     }
+    if (g.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      const int u0 = u_begin + it * KSUB, nsub = min(KSUB, u_end - u0);
+      uint8_t* ss = smem + s * STAGE_BYTES;
+      if (it >= pre) {
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx_elect(&full[s], nsub * SUB_BYTES);
+      }
+      for (int sub = 0; sub < nsub; ++sub) {
+        const int gi = u0 + sub, tap = gi / g.kblocks, kb = gi % g.kblocks;
+        const int kbB = g.bwrap ? kb % g.bwrap : kb;
+        uint8_t* sa = ss + sub * SUB_BYTES;
+        if (it >= pre) tma_load_3d_elect(sa + A_BYTES, &tmB, &full[s], kbB * BLOCK_K, n0, phase * g.ntaps + tap);
+        tma_load_3d_elect(sa, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
+      }
+    }
+    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_M, BLOCK_N, FMT);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        tcgen05_fence_after();
-        const int nsub = min(KSUB, u_end - (u_begin + it * KSUB));
-        for (int sub = 0; sub < nsub; ++sub) {
-          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES + sub * SUB_BYTES);
-          const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
+    constexpr uint32_t idesc = make_idesc(TILE_M, BLOCK_N, FMT);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      tcgen05_fence_after();
+      const int nsub = min(KSUB, u_end - (u_begin + it * KSUB));
+      for (int sub = 0; sub < nsub; ++sub) {
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES + sub * SUB_BYTES);
+        const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k)  // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
-            umma_bf16_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | sub | k) != 0);
-        }
-        umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+        for (int k = 0; k < BLOCK_K / 16; ++k)  // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
+          umma_bf16_f16_elect(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | sub | k) != 0);
       }
-      umma_commit(tmem_full);    // accumulator complete
+      umma_commit_elect(&empty[s]);  // frees the smem slot once these MMAs have read it
     }
+    umma_commit_elect(tmem_full);    // accumulator complete
+    __syncwarp();
   } else {
     if (g.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     // our prerequisite has completed: the dependent grid may now start its prologue and weight prefetch
@@ -1547,13 +1585,16 @@ cudaError_t launch_decode_fused_bf16(const FusedStepArgs& a, const void* wqkv, c
 // Linear layer of the bf16 sampler path: out = A[R][K] (bf16) x W[N][K]^T (bf16) with a fused epilogue.
 cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st) {
   if (a.K % 64 != 0 || a.N % a.block_n != 0) return cudaErrorInvalidValue;
+  const int wk = a.w_k > 0 ? a.w_k : a.K;  // K extent of W (A may hold several bf16 terms side by side)
+  if (wk % 64 != 0 || a.K % wk != 0) return cudaErrorInvalidValue;
   // up to 64 rows: UMMA M=64 halves the activation tile, so twice as many weight bytes fit in flight per SM
   const int tile_m = a.R <= 64 ? 64 : kTileM;
   CUtensorMap ta, tb;
   if (!make_map(&ta, a.A, a.K, a.R, 1, a.lda, (uint64_t)a.R * a.lda, 64, tile_m, false)) return cudaErrorUnknown;
-  if (!make_map(&tb, a.W, a.K, a.N, 1, a.K, (uint64_t)a.N * a.K, 64, a.block_n, false)) return cudaErrorUnknown;
+  if (!make_map(&tb, a.W, wk, a.N, 1, wk, (uint64_t)a.N * wk, 64, a.block_n, false)) return cudaErrorUnknown;
   TcShape g{};
   g.ntaps = 1; g.nphase = 1; g.kblocks = a.K / 64; g.batch = 1;
+  g.bwrap = wk != a.K ? wk / 64 : 0;
   g.ksplit = (a.epi == EPI_RESID && a.ksplit > 1) ? a.ksplit : 1;
   if (g.ksplit > g.kblocks) g.ksplit = g.kblocks;
   g.pdl = a.pdl;
@@ -1561,6 +1602,7 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st) {
   ep.mode = a.epi; ep.R = a.R; ep.N = a.N; ep.out_f32 = a.out_f32; ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
   ep.ldo = a.ldo; ep.perm_S = a.perm_S; ep.perm_V = a.perm_V; ep.rope = a.rope; ep.kv = a.kv; ep.state = a.state;
   ep.pos0 = a.pos0; ep.npos = a.npos; ep.layer = a.layer; ep.d_model = a.d_model; ep.atomic = g.ksplit > 1;
+  ep.aux = a.aux;
   const int mt = (a.R + tile_m - 1) / tile_m, nt = a.N / a.block_n;
   if (tile_m == 64) {
     switch (a.block_n) {

@@ -7,7 +7,11 @@
 
 namespace vaura {
 
-enum { EPI_STORE = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_QKV = 3 };
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_QKV = 3,
+       // fp32-activation prefill on the tensor cores (A operand = fp32 activations split into three bf16 terms):
+       EPI_QKV_F32 = 4,        // RoPE, q -> fp32 [R][d], K/V -> fp32 pages
+       EPI_SWIGLU_SPLIT3 = 5   // silu(w1 x) * w3 x in fp32, stored as three bf16 terms [R][3F] (the next GEMM's A operand)
+};
 
 struct EmbedArgs {
   const int32_t* seq;       // [B][K][S]
@@ -37,6 +41,7 @@ struct GemvArgs {
 struct AttnArgs {
   const float* q;   // [rows*npos][d]
   float* out;       // [rows*npos][d]
+  uint16_t* out3;   // optional: the same rows as three bf16 terms [rows*npos][3 d] (hi | mid | lo), see split3()
   KvView kv;
   const StepState* state;
   int pos0, npos;
@@ -89,6 +94,9 @@ struct LinearTcArgs {
   int perm_S, perm_V, pos0, npos, layer, d_model;
   int ksplit;  // EPI_RESID only: split K over this many CTAs, partials reduced with red.global.add
   int pdl;     // programmatic dependent launch (see TcShape::pdl)
+  int w_k;     // 0: W is [N][K].  > 0: W is [N][w_k] and A is [R][K] with K a multiple of w_k: the K blocks of W are
+               // re-read for every w_k-wide section of A (A = the bf16 terms of a split fp32 operand side by side)
+  int aux;     // EPI_SWIGLU_SPLIT3: F (distance between the three terms of one output element)
 };
 cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st);
 // bf16 path helpers (decode_bf16.cu)
@@ -104,6 +112,8 @@ struct AttnBf16Args {
   int pdl;
 };
 cudaError_t launch_attn_bf16(const AttnBf16Args& a, int nhead, int rows, cudaStream_t st);
+// fp32 -> three bf16 terms (x = t1 + t2 + t3 to 24 significant bits): the A operand of the fp32-equivalent tensor-core GEMMs
+cudaError_t launch_rmsnorm_split3(const float* h, const float* w, void* out3, int R, int D, size_t ldh, float eps, cudaStream_t st);
 
 // fused decode step of the bf16 path, rows <= 64 (gemm_tcgen05.cu: decode_step_fused_bf16)
 struct FusedStepArgs {
