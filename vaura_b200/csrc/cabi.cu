@@ -137,6 +137,7 @@ struct Workspace {
   long long* xfix;                                       // fp32act path, cluster decode kernel (rows <= 2)
   __nv_bfloat16 *xn_b, *q_b, *attn_b, *act_b;            // bf16 path (h and logits stay fp32)
   __nv_bfloat16 *x3, *act3;                              // fp32act path, tensor-core prefill: operands as three bf16 terms
+  char* f2;                                              // bf16 path, decode_step_fused2: h_t | q_t | ssq_part | w2_part | w2_cnt
   size_t bytes;
 };
 
@@ -161,6 +162,7 @@ static Workspace carve(const vaura_sampler_dims& d, int rows, int max_pos, int p
     w.q_b = (__nv_bfloat16*)take(R * d.d_model * 2);
     w.attn_b = (__nv_bfloat16*)take(R * d.d_model * 2);
     w.act_b = (__nv_bfloat16*)take(R * d.ffn_dim * 2);
+    w.f2 = (char*)take(fused2_workspace_bytes(d.d_model));
   } else {
     w.q = (float*)take(R * d.d_model * 4);
     w.attn = (float*)take(R * d.d_model * 4);
@@ -286,9 +288,14 @@ static int transformer_pass_tc3(const vaura_sampler* s, const Workspace& ws, con
   e.cond_dim = d.cond_dim; e.cond_tokens = d.cond_tokens; e.atpvf = d.audio_tokens_per_video_frame;
   CUL(launch_embed(e, R, st));
   const size_t D = d.d_model, F = d.ffn_dim;
-  // N tiles: enough CTAs to cover the SMs with ceil(R / 128) row tiles
-  const int mt = (R + 127) / 128;
-  auto pick_bn = [&](int N) { for (int bn : {128, 64, 32}) if (N % bn == 0 && (N / bn) * mt >= 96) return bn; return N % 32 == 0 ? 32 : 16; };
+  // N tiles.  Every CTA streams its whole row tile of A (three terms) once, so the L2 -> SM traffic of a GEMM is
+  // (tiles) x (3 x 128 + BN) x K x 2 bytes: wide tiles for the wide matrices (wqkv, w1|w3: measured L2-bound with narrow
+  // ones), 64-wide tiles for the two 1536-wide ones so that they still cover 48 SMs.
+  auto pick_bn = [&](int N) {
+    if (N >= 4096 && N % 256 == 0) return 256;
+    if (N >= 2048 && N % 128 == 0) return 128;
+    return N % 64 == 0 ? 64 : 32;
+  };
   for (int l = 0; l < d.num_layers; ++l) {
     LinearTcArgs g{};
     g.state = state; g.pos0 = pos0; g.npos = npos; g.R = R; g.layer = l; g.d_model = d.d_model; g.kv = kv; g.rope = w.rope;
@@ -317,8 +324,8 @@ static int transformer_pass_tc3(const vaura_sampler* s, const Workspace& ws, con
     g.state = state; g.pos0 = pos0; g.npos = npos; g.d_model = d.d_model; g.ksplit = 1;
     CUL(launch_rmsnorm_split3(ws.h, w.final_norm, ws.x3, R, (int)D, D, d.norm_eps, st));
     g.A = ws.x3; g.lda = 3 * D; g.K = 3 * D; g.w_k = D; g.W = w.w_heads; g.N = d.num_codebooks * d.vocab; g.R = R;
-    g.epi = EPI_STORE; g.out_f32 = logits_dst; g.ldo = g.N; g.perm_S = npos; g.perm_V = d.vocab; g.block_n = 128;
-    if (g.N % 128) return fail(VAURA_ERR_UNSUPPORTED, "heads width %d is not a multiple of 128", g.N);
+    g.epi = EPI_STORE; g.out_f32 = logits_dst; g.ldo = g.N; g.perm_S = npos; g.perm_V = d.vocab; g.block_n = pick_bn(g.N);
+    if (g.N % g.block_n) return fail(VAURA_ERR_UNSUPPORTED, "heads width %d is not a multiple of %d", g.N, g.block_n);
     CUL(launch_linear_tc(g, st));
   } else {  // only the last position of every sequence row feeds the heads: a few rows, the weight-streaming GEMV
     GemvArgs g{};
@@ -350,6 +357,39 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
     if (fuse_io_on < 0) { const char* ev = getenv("VAURA_FUSED_IO"); fuse_io_on = !(ev && ev[0] == '0'); }
     if (fused_on && npos == 1 && !logits_all && state && fused_step_supported(R, d.d_model, d.ffn_dim, d.num_codebooks * d.vocab)) {
       const bool io = fuse_io_on && fuse_sample && sampled && d.cond_dim % 4 == 0 && (d.d_model - d.cond_dim) % 4 == 0;
+      // second design (decode_fused2.cu): swap-AB tiles, K split inside CTA pairs, norms folded into their neighbours
+      static int fused2_on = -1;
+      if (fused2_on < 0) { const char* ev = getenv("VAURA_FUSED2"); fused2_on = !(ev && ev[0] == '0'); }
+      int sms2 = 0, dev2 = 0;
+      cudaGetDevice(&dev2);
+      cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, dev2);
+      if (fused2_on && io && ws.f2 &&
+          fused2_supported(R, d.num_layers, d.d_model, d.ffn_dim, d.nhead, d.num_codebooks * d.vocab, sms2 & ~1, kv.page_size,
+                           kv.max_pages_per_seq)) {
+        Fused2Args fa{};
+        const size_t Dm = d.d_model;
+        char* fp = ws.f2;
+        fa.h_t = (float*)fp; fp += Dm * 64 * 4;
+        fa.q_t = (__nv_bfloat16*)fp; fp += Dm * 64 * 2;
+        fa.ssq_part = (float*)fp; fp += 64 * 64 * 4;
+        fa.w2_part = (float*)fp; fp += (Dm / 64) * 3 * 2 * 32 * 64 * 4;
+        fa.w2_cnt = (unsigned*)fp;
+        fa.attn_norm = w.attn_norm; fa.ffn_norm = w.ffn_norm; fa.final_norm = w.final_norm; fa.rope = w.rope;
+        fa.hb = ws.xn_b; fa.attn = ws.attn_b; fa.act = ws.act_b; fa.logits = logits_dst;
+        fa.kv = kv; fa.state = const_cast<StepState*>(state);
+        fa.R = R; fa.L = d.num_layers; fa.D = d.d_model; fa.F = d.ffn_dim; fa.H = d.nhead; fa.NH = d.num_codebooks * d.vocab;
+        fa.eps = d.norm_eps; fa.scale = 1.0f / sqrtf((float)kHeadDim);
+        { const char* tm = getenv("VAURA_PERSIST_TIMING"); fa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
+        fa.step_times = ws.timing + 1024;
+        { const char* tc = getenv("VAURA_TIMING_CTA"); fa.timing_cta = tc ? atoi(tc) : 0; }
+        fa.seq = seq; fa.cond_rows = cond_rows; fa.tables = w.tok_tables; fa.batch = batch; fa.Kc = d.num_codebooks; fa.S = S;
+        fa.vocab = d.vocab; fa.cond_dim = d.cond_dim; fa.cond_tokens = d.cond_tokens; fa.atpvf = d.audio_tokens_per_video_frame;
+        fa.sample = *fuse_sample;
+        fa.sample.state = nullptr;
+        *sampled = true;
+        CUL(launch_decode_fused2(fa, w.wqkv, w.wo, w.w13, w.w2, w.w_heads, st));
+        return VAURA_OK;
+      }
       if (!io) CUL(launch_embed(e, R, st));
       FusedStepArgs fa{};
       fa.attn_norm = w.attn_norm; fa.ffn_norm = w.ffn_norm; fa.final_norm = w.final_norm; fa.rope = w.rope;
@@ -556,6 +596,8 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     }
     return VAURA_OK;
   }
+  if (precision == VAURA_PRECISION_BF16 && ws.f2)  // decode_step_fused2: arrival counters of the w2 K thirds start at 0
+    CU(cudaMemsetAsync(ws.f2 + fused2_workspace_bytes(d.d_model) - 1024, 0, 1024, st));
   // otherwise: capture one step (reads its position from the device state) and replay it; a call with the same pointers,
   // shapes and sampling parameters as the last one replays the graph instantiated then
   GraphKey key;

@@ -1,0 +1,959 @@
+// Fused decode step of the bf16 path for up to 64 sequence rows, second design (round 2): one cooperative kernel per
+// generated column, 148 CTAs in 74 clusters of two.  What changed against decode_step_fused_bf16 (gemm_tcgen05.cu) and why
+// (profiles/r01_fused_step_b64.summary.txt: a GEMM phase was paced by 96 small MMAs per CTA over the WHOLE activation matrix,
+// by float atomics behind a release fence, and by a separate RMSNorm sub-phase):
+//   * swap-AB: the weights are the UMMA M operand (64 or 128 rows), the sequence rows the N operand (64): D[feature][row].
+//   * split-K inside the CTA pair: each CTA multiplies one K half, so it ingests HALF of the activation columns and issues
+//     at most 48 MMAs per phase; the two partial accumulators are exchanged through distributed shared memory (st.async:
+//     data + transaction-count completion, no fence) and each CTA finalises half of the features - complete sums, plain
+//     stores, no atomics on the residual stream.  Only w2 (K = 4096) is also split over three pairs per 64-feature block;
+//     their partials meet in an L2 scratch buffer and the pair that arrives last adds them in a fixed order (deterministic).
+//   * RMSNorm folded into its neighbours (llama.py:147-158): whoever finalises the residual stream also stores
+//     bf16(h * g_next) - the next GEMM's operand - and the partial sums of squares of its features; the consumer multiplies
+//     its accumulator columns by rsqrt(mean + eps).  No norm phase, no tile counter.
+//   * weights stream through their own shared-memory ring, fed by a dedicated warp that runs ahead of the device-wide
+//     barriers (the weight schedule of a CTA is static), so a phase starts with its first weight stages resident and only
+//     waits for its activation columns.
+// Phases per layer: q|k|v (+RoPE, K/V append) | attention | wo (+residual) | w1|w3 (+SiLU*mul) | w2 (+residual); one
+// device-wide barrier after each.  Embedding in front, heads + CFG / sampling / write-back behind (llama.py:445-517,
+// vaura_model.py:775-827).
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "sampling.cuh"
+
+namespace vaura {
+namespace f2 {
+
+// ------------------------------------------------------------------------------------------------------------------------
+// PTX wrappers (the elected-lane forms: every lane of a converged warp executes the statement, one lane issues; see
+// gemm_tcgen05.cu, lesson vi)
+// ------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try_wait(bar, parity)) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 2000000000ull) __trap();  // 2 s
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_elect(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_elect(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// descriptors by their low words (14-bit address field); the high word of a 128B-swizzled K-major descriptor is constant
+__device__ __forceinline__ void umma_elect_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "n"(0x40004040)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void hw_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// remote shared-memory store of 16 bytes that completes 16 transaction bytes on the mbarrier `rbar` of the destination CTA
+__device__ __forceinline__ void st_async_f4(uint32_t raddr, float a, float b, float c, float d, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(raddr),
+               "f"(a), "f"(b), "f"(c), "f"(d), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {  // bf16 x bf16 -> fp32, both operands K-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int kThreads = 320;       // warp 0: weight stream; warp 1: barrier poll + activation loads + MMA issue; warps 2-9: the rest
+constexpr int kWork = 256;          // threads of warps 2-9
+constexpr int kNS = 6;              // weight ring stages
+constexpr int kStage = 16384;       // one [128 x 64] bf16 weight tile, or two K blocks of a [64 x 64] one
+constexpr int kXSub = 8192;         // [64 rows x 64 k] bf16 activation sub-tile
+constexpr int kXTiles = 12;         // activation K blocks a CTA may hold (K half of d_model 1536)
+constexpr int kXBox = 4;            // K blocks per activation tensor box
+constexpr int kXRow = 68;           // floats per row of the exchange buffer (64 + 4: conflict-free 16-byte reads)
+constexpr int kXbuf = 64 * kXRow * 4;
+constexpr int kAttnSlots = 4, kRunBytes = 16 * kHeadDim * 2;  // per attention warp: 4 staged runs of 16 positions (3 KB each)
+constexpr int kRing = kNS * kStage;           // 96 KB
+constexpr int kXBytes = kXTiles * kXSub;      // 96 KB (activations; attention staging of the 8 work warps)
+constexpr int kOffX = kRing, kOffXbuf = kOffX + kXBytes, kOffBars = kOffXbuf + kXbuf, kOffMisc = kOffBars + 512;
+constexpr int kSmem = kOffMisc + 1024 + 1024;  // + alignment slack
+static_assert(8 * kAttnSlots * kRunBytes <= kXBytes, "attention staging fits the activation region");
+static_assert(8 * (kHeadDim + kMaxCtx) * 4 <= kXbuf, "attention scratch aliases the exchange buffer");
+static_assert(kSmem <= 227 * 1024, "shared memory");
+
+struct Job {       // what a CTA multiplies in one GEMM phase
+  int on;          // participates
+  int row0;        // first weight row (output feature) of the pair's block
+  int kb0, nkb;    // K blocks [kb0, kb0 + nkb) of this CTA (its K half)
+  int m128;        // UMMA M: 128 (one K block per ring stage) or 64 (two K blocks per stage)
+  int outer;       // layer index inside the weight tensor map
+};
+__device__ __forceinline__ int stages_of(const Job& j) { return j.m128 ? j.nkb : (j.nkb + 1) >> 1; }
+
+}  // namespace f2
+
+using namespace f2;
+
+// ------------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_constant__ CUtensorMap tm_attn,
+                   const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wqkv,
+                   const __grid_constant__ CUtensorMap tm_wo, const __grid_constant__ CUtensorMap tm_w13,
+                   const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_heads,
+                   const __grid_constant__ Fused2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* xreg = smem + kOffX;
+  float* xbuf = reinterpret_cast<float*>(smem + kOffXbuf);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint64_t *wfull = bars, *wempty = bars + kNS, *xfull = bars + 2 * kNS, *tmem_full = xfull + 3, *xbar = tmem_full + 1,
+           *go = xbar + 1, *attn_bars = go + 1;  // attn_bars: 8 warps x kAttnSlots
+  float* rs_s = reinterpret_cast<float*>(smem + kOffMisc);          // [64] rsqrt(mean square + eps) of every sequence row
+  float* ssq_s = rs_s + 64;                                         // [2][64] partial sums of squares of the two finalising quadrants
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ssq_s + 128);
+  int* flag_s = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x, G = gridDim.x;
+  const int P = cta >> 1;                    // pair = cluster
+  const int rk = (int)cluster_rank();        // rank inside the pair (== cta & 1)
+  const int R = a.R, D = a.D, F = a.F, L = a.L;
+  const unsigned epoch = a.state->epoch;
+  const int offset = a.state->offset;
+  const int p = offset - 1;                  // position fed by this step
+  if (cta == 0 && tid == 0 && a.step_times) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.step_times[offset] = t;
+  }
+  const unsigned nbar = (unsigned)(5 * L + 2);
+
+  if (tid == 0) {
+    const CUtensorMap* maps[8] = {&tm_hb, &tm_attn, &tm_act, &tm_wqkv, &tm_wo, &tm_w13, &tm_w2, &tm_heads};
+    for (int i = 0; i < 8; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(maps[i]) : "memory");
+    for (int s = 0; s < kNS; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+    for (int i = 0; i < 3; ++i) mbar_init(&xfull[i], 1);
+    mbar_init(tmem_full, 1);
+    mbar_init(xbar, 1);
+    mbar_init(go, 1);
+    for (int i = 0; i < 8 * kAttnSlots; ++i) mbar_init(&attn_bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  hw_cluster_sync();  // the peer's barriers are initialised before any remote store / completion reaches them
+
+  // ---- the static GEMM schedule of this CTA -------------------------------------------------------------------------
+  const int kbD = D / 128;  // K blocks of a K half over d_model
+  auto job_qkv = [&](int l) { Job j; j.on = P < 3 * D / 64; j.row0 = 64 * P; j.kb0 = rk * kbD; j.nkb = kbD; j.m128 = 0; j.outer = l; return j; };
+  auto job_wo = [&](int l) { Job j; j.on = P < D / 64; j.row0 = 64 * P; j.kb0 = rk * kbD; j.nkb = kbD; j.m128 = 0; j.outer = l; return j; };
+  auto job_w13 = [&](int l) { Job j; j.on = P < 2 * F / 128; j.row0 = 128 * P; j.kb0 = rk * kbD; j.nkb = kbD; j.m128 = 1; j.outer = l; return j; };
+  auto job_w2 = [&](int l) {  // 64-feature block = P / 3, K third = P % 3, K half by rank
+    Job j;
+    const int blk = P / 3, t = P % 3, KB = F / 64;
+    const int t0 = t * KB / 3, t1 = (t + 1) * KB / 3, len = t1 - t0, h0 = (len + 1) >> 1;
+    j.on = P < 3 * (D / 64); j.row0 = 64 * blk; j.kb0 = rk ? t0 + h0 : t0; j.nkb = rk ? len - h0 : h0; j.m128 = 0; j.outer = l;
+    return j;
+  };
+  auto job_heads = [&]() { Job j; j.on = P < a.NH / 128; j.row0 = 128 * P; j.kb0 = rk * kbD; j.nkb = kbD; j.m128 = 1; j.outer = 0; return j; };
+
+  // =====================================================================================================================
+  // warp 0: weight stream.  Walks the CTA's jobs of the whole step in order; only the ring's empty barriers hold it back.
+  // =====================================================================================================================
+  if (warp == 0) {
+    int wi = 0;  // stages pushed so far
+    auto push_job = [&](const Job& j, const CUtensorMap* map) {
+      if (!j.on) return;
+      const int ns = stages_of(j);
+      for (int s = 0; s < ns; ++s, ++wi) {
+        const int slot = wi % kNS;
+        mbar_wait(&wempty[slot], ((wi / kNS) & 1) ^ 1);
+        mbar_expect_tx_elect(&wfull[slot], kStage);
+        // box = [64 k][128 rows][1 K block] or [64 k][64 rows][2 K blocks]: 16 KB either way (a box that runs past the
+        // tensor still delivers its full byte count, zero-filled)
+        tma_load_4d_elect(ring + slot * kStage, map, &wfull[slot], 0, j.row0, j.kb0 + (j.m128 ? s : 2 * s), j.outer);
+      }
+    };
+    for (int l = 0; l < L; ++l) {
+      push_job(job_qkv(l), &tm_wqkv);
+      push_job(job_wo(l), &tm_wo);
+      push_job(job_w13(l), &tm_w13);
+      push_job(job_w2(l), &tm_w2);
+    }
+    push_job(job_heads(), &tm_heads);
+    __syncwarp();
+  }
+  // =====================================================================================================================
+  // warp 1: device-wide barrier waits, activation loads, MMA issue
+  // =====================================================================================================================
+  else if (warp == 1) {
+    unsigned bi = 0;   // barriers waited for so far
+    int ci = 0;        // ring stages consumed so far
+    uint32_t xpar = 0; // bit b = parity the next wait on xfull[b] uses
+    auto wait_grid = [&]() {
+      ++bi;
+      if (lane == 0) {
+        if (a.timing && cta == a.timing_cta) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.timing[2 * bi] = t; }
+        const unsigned target = (epoch * nbar + bi) * (unsigned)G;
+        if ((int)(ld_acquire_u32(&a.state->barrier) - target) < 0) {
+          const long long t0 = clock64();
+          while ((int)(ld_acquire_u32(&a.state->barrier) - target) < 0)
+            if (clock64() - t0 > 4000000000ll) __trap();
+        }
+        if (a.timing && cta == a.timing_cta) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.timing[2 * bi + 1] = t; }
+        // generic-proxy stores of the other CTAs (acquired above) -> this CTA's tensor copies (async proxy)
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_arrive(go);  // release.cta: the work warps read what the barrier published
+      }
+      __syncwarp();
+    };
+    auto gemm = [&](const Job& j, const CUtensorMap* xmap) {
+      if (!j.on) return;
+      // activation columns of this CTA's K half: boxes of kXBox K blocks, each with its own barrier
+      const int nbox = (j.nkb + kXBox - 1) / kXBox;
+      for (int b = 0; b < nbox; ++b) {
+        mbar_expect_tx_elect(&xfull[b], kXBox * kXSub);
+        tma_load_4d_elect(xreg + b * kXBox * kXSub, xmap, &xfull[b], 0, 0, j.kb0 + b * kXBox, 0);
+      }
+      const uint32_t idesc = j.m128 ? make_idesc(128, 64) : make_idesc(64, 64);
+      const int ns = stages_of(j);
+      const uint32_t x_lo = (smem_u32(xreg) & 0x3FFFF) >> 4;
+      int box_ready = -1;
+      for (int s = 0; s < ns; ++s, ++ci) {
+        const int slot = ci % kNS;
+        mbar_wait(&wfull[slot], (ci / kNS) & 1);
+        const uint32_t w_lo = (smem_u32(ring + slot * kStage) & 0x3FFFF) >> 4;
+        const int nk = j.m128 ? 1 : min(2, j.nkb - 2 * s);
+        for (int u = 0; u < nk; ++u) {
+          const int kbl = j.m128 ? s : 2 * s + u;  // K block inside the CTA's range
+          if (kbl / kXBox > box_ready) {
+            box_ready = kbl / kXBox;
+            mbar_wait(&xfull[box_ready], (xpar >> box_ready) & 1u);
+            xpar ^= 1u << box_ready;
+          }
+          tcgen05_fence_after();
+          const uint32_t a_lo = w_lo + u * (kXSub >> 4), b_lo = x_lo + kbl * (kXSub >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_elect_lo(tmem_base, a_lo + 2 * k, b_lo + 2 * k, idesc, (kbl | k) != 0);
+        }
+        umma_commit_elect(&wempty[slot]);
+      }
+      umma_commit_elect(tmem_full);
+    };
+    wait_grid();  // embedding done
+    for (int l = 0; l < L; ++l) {
+      gemm(job_qkv(l), &tm_hb);
+      wait_grid();
+      wait_grid();  // attention
+      gemm(job_wo(l), &tm_attn);
+      wait_grid();
+      gemm(job_w13(l), &tm_hb);
+      wait_grid();
+      gemm(job_w2(l), &tm_act);
+      wait_grid();
+    }
+    gemm(job_heads(), &tm_hb);
+    wait_grid();
+    __syncwarp();
+  }
+  // =====================================================================================================================
+  // warps 2-9: embedding, epilogues (pair exchange + finalise), attention, sampling
+  // =====================================================================================================================
+  else {
+    const int wt = tid - 64, aw = warp - 2;       // index among the work threads / warps
+    const int q = warp & 3;                       // TMEM lane quadrant of this warp
+    const int hn = aw >> 2;                       // which half of the 64 accumulator columns (sequence rows) it handles
+    const bool fin = (q >> 1) == rk;              // this warp finalises (its quadrant belongs to this CTA's feature half)
+    uint32_t gp = 0, tp = 0, xp = 0;              // parities: go, tmem_full, xbar
+    const uint32_t peer = (uint32_t)(rk ^ 1);
+    const uint32_t r_xbuf = mapa_u32(smem_u32(xbuf), peer), r_xbar = mapa_u32(smem_u32(xbar), peer);
+
+    auto arrive_grid = [&]() {  // after a barrier over the work warps: everything they stored is ordered before the count
+      named_bar(1, kWork);
+      if (wt == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&a.state->barrier) : "memory");
+    };
+    auto wait_go = [&]() { mbar_wait(go, gp); gp ^= 1; };
+
+    // rs_s[n] = rsqrt(mean_f h[n][f]^2 + eps) from the partial sums of squares the previous finaliser CTAs left
+    auto compute_rs = [&](int nslots) {
+      for (int i = 0; i < 8; ++i) {
+        const int n = aw * 8 + i;
+        float s = 0.f;
+        for (int sl = lane; sl < nslots; sl += 32) s += __ldcg(a.ssq_part + sl * 64 + n);
+        s = warp_sum(s);
+        if (lane == 0) rs_s[n] = rsqrtf(s / (float)D + a.eps);
+      }
+      named_bar(1, kWork);
+    };
+
+    // ---- pair exchange: this warp either sends its quadrant's accumulator rows to the peer or adds the peer's to its own.
+    //      v[c][i] = complete sum of feature `fl` (local to the finalising half) for sequence rows 32 hn + 16 c + i. ----
+    auto exchange = [&](bool m128, float (&v)[2][16], int& fl) {
+      const int nrow = m128 ? 32 : 16;            // valid lanes of a quadrant
+      fl = nrow * (q & 1) + lane;
+      mbar_wait(tmem_full, tp); tp ^= 1;
+      tcgen05_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + 32 * hn + 16 * c, v[c]);
+      if (!fin) {
+        if (lane < nrow) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              st_async_f4(r_xbuf + (uint32_t)(fl * kXRow + 32 * hn + 16 * c + i) * 4, v[c][i], v[c][i + 1], v[c][i + 2], v[c][i + 3], r_xbar);
+        }
+      } else {
+        mbar_wait(xbar, xp);
+        if (lane < nrow) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const uint4 o = lds_u4(xbuf + fl * kXRow + 32 * hn + 16 * c + i);
+              v[c][i] += __uint_as_float(o.x); v[c][i + 1] += __uint_as_float(o.y);
+              v[c][i + 2] += __uint_as_float(o.z); v[c][i + 3] += __uint_as_float(o.w);
+            }
+        }
+      }
+      xp ^= 1;
+      tcgen05_fence_before();
+    };
+    // the receiving side arms its exchange barrier once per GEMM phase (any time before it waits on it)
+    auto arm_xbar = [&](bool m128) { if (wt == 0) mbar_expect_tx(xbar, (m128 ? 64 : 32) * 64 * 4); };
+
+    // ---- residual finaliser (wo, w2): h += v, hb = bf16(h * g_next), partial sums of squares ----
+    auto finalize_resid = [&](float (&v)[2][16], int f, bool valid, const float* g_next, int slot) {
+      float ss[2][16];
+      if (valid) {
+        float* hrow = a.h_t + (size_t)f * 64 + 32 * hn;
+        const float gw = __ldg(g_next + f);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 o = __ldcg(reinterpret_cast<const float4*>(hrow + 16 * c + i));
+            v[c][i] += o.x; v[c][i + 1] += o.y; v[c][i + 2] += o.z; v[c][i + 3] += o.w;
+            *reinterpret_cast<float4*>(hrow + 16 * c + i) = make_float4(v[c][i], v[c][i + 1], v[c][i + 2], v[c][i + 3]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = 32 * hn + 16 * c + i;
+            if (n < R) a.hb[(size_t)n * D + f] = __float2bfloat16_rn(v[c][i] * gw);
+            ss[c][i] = v[c][i] * v[c][i];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ss[c][i] = 0.f;
+      }
+      // sum over the features (lanes) of this warp, then over the two finalising quadrants through shared memory
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float s = warp_sum(ss[c][i]);
+          if (lane == 0) ssq_s[(q & 1) * 64 + 32 * hn + 16 * c + i] = s;
+        }
+      named_bar(2, 128);  // the four finalising warps
+      if ((q & 1) == 0) a.ssq_part[slot * 64 + 32 * hn + lane] = ssq_s[32 * hn + lane] + ssq_s[64 + 32 * hn + lane];
+    };
+
+    // =================================================================================================================
+    // embedding (llama.py:455-472): CTA n < R builds row n
+    // =================================================================================================================
+    if (cta < R) {
+      const int n = cta, C = a.cond_dim, TD = D - C;
+      float ss = 0.f;
+      for (int c = wt; c < (D >> 2); c += kWork) {
+        const int f = 4 * c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f < C) {
+          int vrow = p / a.atpvf;
+          if (vrow > a.cond_tokens) vrow = a.cond_tokens;  // >= Tv -> empty_video_emb row (llama.py:569-572)
+          v = __ldg(reinterpret_cast<const float4*>(a.cond_rows + ((size_t)n * (a.cond_tokens + 1) + vrow) * C + f));
+        } else {
+          const int bt = n % a.batch;  // CFG halves share the token sequence (vaura_model.py:795)
+          for (int k = 0; k < a.Kc; ++k) {  // python sum() adds the codebooks in order (llama.py:455-460)
+            const int tok = a.seq[((size_t)bt * a.Kc + k) * a.S + p];
+            const float4 tv = __ldg(reinterpret_cast<const float4*>(a.tables + ((size_t)k * (a.vocab + 1) + tok) * TD + (f - C)));
+            v.x += tv.x; v.y += tv.y; v.z += tv.z; v.w += tv.w;
+          }
+        }
+        const float4 g = __ldg(reinterpret_cast<const float4*>(a.attn_norm + f));
+        a.h_t[(size_t)f * 64 + n] = v.x; a.h_t[(size_t)(f + 1) * 64 + n] = v.y;
+        a.h_t[(size_t)(f + 2) * 64 + n] = v.z; a.h_t[(size_t)(f + 3) * 64 + n] = v.w;
+        uint2 o;
+        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v.x * g.x, v.y * g.y);
+        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v.z * g.z, v.w * g.w);
+        *reinterpret_cast<uint2*>(a.hb + (size_t)n * D + f) = o;
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) ssq_s[aw] = ss;
+      named_bar(1, kWork);
+      if (wt == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += ssq_s[i];
+        a.ssq_part[n] = t;  // slot 0
+      }
+    }
+    arrive_grid();
+
+    // attention items of this warp and their page tables (constant during the launch): lane i holds page i
+    const int att_stride = G * 8, att_item0 = aw * G + cta;
+    const int att_nitems = att_item0 < R * a.H ? (R * a.H - att_item0 + att_stride - 1) / att_stride : 0;  // <= 2
+    int att_pg[2] = {0, 0}, att_row[2] = {0, 0}, att_hd[2] = {0, 0};
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (i < att_nitems) {
+        const int item = att_item0 + i * att_stride;
+        att_row[i] = item / a.H;
+        att_hd[i] = item % a.H;
+        if (lane < a.kv.max_pages_per_seq) att_pg[i] = a.kv.page_table[att_row[i] * a.kv.max_pages_per_seq + lane];
+      }
+    int att_slot = 0, att_rslot = 0;
+    unsigned att_rphase = 0;
+
+    for (int l = 0; l < L; ++l) {
+      // ===============================================================================================================
+      // q|k|v: scale by rs, RoPE (llama.py:633-650), q -> q_t [feature][row] bf16, k / v -> paged cache
+      // ===============================================================================================================
+      {
+        const Job j = job_qkv(l);
+        wait_go();
+        if (j.on) {
+          arm_xbar(false);
+          compute_rs(l == 0 ? 1 : 2 * (D / 64));
+          float v[2][16];
+          int fl;
+          exchange(false, v, fl);
+          const int f = j.row0 + 32 * rk + fl;          // output feature of wqkv
+          const int sec = f / D, within = f % D, hd = within / kHeadDim, e = within % kHeadDim;
+          const bool valid = fin && lane < 16;
+          float2 cs = make_float2(1.f, 0.f);
+          if (valid && sec != 2) cs = __ldg(reinterpret_cast<const float2*>(a.rope + ((size_t)p * (kHeadDim / 2) + (e >> 1)) * 2));
+          const float sgn = (lane & 1) ? cs.y : -cs.y;   // even feature: x cos - partner sin; odd: x cos + partner sin
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float x = v[c][i] * rs_s[32 * hn + 16 * c + i];
+              const float pr = __shfl_xor_sync(0xffffffffu, x, 1);
+              v[c][i] = x * cs.x + pr * sgn;
+            }
+            if (valid) {
+              if (sec == 0) {
+                uint4 o[2];
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) h2[i] = __floats2bfloat162_rn(v[c][2 * i], v[c][2 * i + 1]);
+                uint4* dst = reinterpret_cast<uint4*>(a.q_t + (size_t)within * 64 + 32 * hn + 16 * c);
+                dst[0] = o[0];
+                dst[1] = o[1];
+              } else {
+                __nv_bfloat16* kvp = reinterpret_cast<__nv_bfloat16*>(a.kv.pages);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int n = 32 * hn + 16 * c + i;
+                  if (n < R) kvp[a.kv.row(l, sec - 1, n, p, hd) + e] = __float2bfloat16_rn(v[c][i]);
+                }
+              }
+            }
+          }
+        }
+        arrive_grid();
+      }
+      // ===============================================================================================================
+      // attention (llama.py:246-255): one warp per (row, head) over the paged bf16 cache, fp32 softmax; K/V runs of 16
+      // positions staged by per-warp bulk copies into the activation region (profiles/r01_fused_step_b64.summary.txt)
+      // ===============================================================================================================
+      {
+        wait_go();
+        float* qs = xbuf + aw * (kHeadDim + kMaxCtx);
+        float* sc = qs + kHeadDim;
+        const __nv_bfloat16* kvp = reinterpret_cast<const __nv_bfloat16*>(a.kv.pages);
+        const int nctx = p + 1, psz = a.kv.page_size, psh = 31 - __clz(psz);
+        const size_t page_stride = (size_t)a.kv.nhead * psz * kHeadDim;
+        const int nitems = att_nitems;
+        const int nr = (nctx + 15) >> 4, total = nitems * 2 * nr;
+        uint8_t* stage = xreg + aw * (kAttnSlots * kRunBytes);
+        uint64_t* abar = attn_bars + aw * kAttnSlots;
+        unsigned short qraw[3] = {0, 0, 0};
+        if (nitems)
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            qraw[i] = __ldcg(reinterpret_cast<const unsigned short*>(a.q_t) + (size_t)(att_hd[0] * kHeadDim + lane + 32 * i) * 64 + att_row[0]);
+        int issued = 0, consumed = 0;
+        int c_it = 0, c_kv = 0, c_run = 0;
+        auto issue_one = [&]() {
+          const int jj = c_run * 16;
+          const int page = __shfl_sync(0xffffffffu, c_it ? att_pg[1] : att_pg[0], jj >> psh);
+          const int hd = c_it ? att_hd[1] : att_hd[0];
+          const __nv_bfloat16* src = kvp + ((size_t)(l * 2 + c_kv) * a.kv.num_pages + page) * page_stride +
+                                     ((size_t)hd * psz + (jj & (psz - 1))) * kHeadDim;
+          mbar_expect_tx_elect(&abar[att_slot], kRunBytes);
+          bulk_load_1d_elect(stage + att_slot * kRunBytes, src, kRunBytes, &abar[att_slot]);
+          att_slot = att_slot + 1 == kAttnSlots ? 0 : att_slot + 1;
+          ++issued;
+          if (++c_run == nr) { c_run = 0; if (++c_kv == 2) { c_kv = 0; ++c_it; } }
+        };
+        auto refill = [&]() {
+          __syncwarp();
+          while (issued < total && issued - consumed < kAttnSlots) issue_one();
+        };
+        auto staged = [&]() -> const uint8_t* {
+          const int sl = att_rslot;
+          mbar_wait(&abar[sl], (att_rphase >> sl) & 1u);
+          att_rphase ^= 1u << sl;
+          att_rslot = sl + 1 == kAttnSlots ? 0 : sl + 1;
+          return stage + sl * kRunBytes;
+        };
+        refill();
+        for (int it = 0; it < nitems; ++it) {
+          const int row = it ? att_row[1] : att_row[0], hd = it ? att_hd[1] : att_hd[0];
+          __syncwarp();
+          if (it)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              qraw[i] = __ldcg(reinterpret_cast<const unsigned short*>(a.q_t) + (size_t)(hd * kHeadDim + lane + 32 * i) * 64 + row);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) qs[lane + 32 * i] = __bfloat162float(__ushort_as_bfloat16(qraw[i]));
+          __syncwarp();
+          const int g = lane >> 2, t = lane & 3;
+          float q24[24];
+#pragma unroll
+          for (int i = 0; i < 24; ++i) q24[i] = qs[(4 * (i >> 3) + t) * 8 + (i & 7)];
+          float mx = -INFINITY;
+          for (int j0 = 0; j0 < nctx; j0 += 32) {
+            const bool two = j0 + 16 < nctx;
+            const uint8_t* runA = staged();
+            const uint8_t* runB = two ? staged() : runA;
+            float sd[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              if (h2 == 1 && !two) break;
+              const uint8_t* kr = (h2 ? runB : runA) + (g * 12 + t) * 16;
+              uint4 kk[2][3];
+#pragma unroll
+              for (int u2 = 0; u2 < 2; ++u2)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) kk[u2][c] = lds_u4(kr + u2 * (8 * 12 * 16) + 64 * c);
+              float ps[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int u2 = 0; u2 < 2; ++u2)
+#pragma unroll
+                  for (int c = 0; c < 3; ++c) {
+                    const uint32_t w = e == 0 ? kk[u2][c].x : e == 1 ? kk[u2][c].y : e == 2 ? kk[u2][c].z : kk[u2][c].w;
+                    ps[u2][c] = fmaf(q24[c * 8 + 2 * e], bf16_lo(w), ps[u2][c]);
+                    ps[u2][c] = fmaf(q24[c * 8 + 2 * e + 1], bf16_hi(w), ps[u2][c]);
+                  }
+              sd[2 * h2] = (ps[0][0] + ps[0][1]) + ps[0][2];
+              sd[2 * h2 + 1] = (ps[1][0] + ps[1][1]) + ps[1][2];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) sd[u] += __shfl_xor_sync(0xffffffffu, sd[u], 2);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) sd[u] += __shfl_xor_sync(0xffffffffu, sd[u], 1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int jj = j0 + 8 * u + g;
+              if (jj < nctx) {
+                const float sv = sd[u] * a.scale;
+                if (t == 0) sc[jj] = sv;
+                mx = fmaxf(mx, sv);
+              }
+            }
+            consumed += two ? 2 : 1;
+            refill();
+          }
+          mx = warp_max(mx);
+          __syncwarp();
+          float sum = 0.f;
+          for (int jj = lane; jj < ((nctx + 31) & ~31); jj += 32) {
+            const float e = jj < nctx ? expf(sc[jj] - mx) : 0.f;
+            __syncwarp();
+            sc[(jj & ~31) + (lane & 1) * 16 + (lane >> 1)] = e;  // even positions first, then odd ones
+            sum += e;
+          }
+          sum = warp_sum(sum);
+          __syncwarp();
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = 0.f;
+          const int half = lane >= 12 ? 1 : 0, dl = lane < 24 ? lane - 12 * half : 0;
+          for (int j0 = 0; j0 < nctx; j0 += 32) {
+            const bool two = j0 + 16 < nctx;
+            const uint8_t* runA = staged() + (half * 12 + dl) * 16;
+            const uint8_t* runB = two ? staged() + (half * 12 + dl) * 16 : runA;
+            float pj[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 pv = lds_u4(sc + j0 + half * 16 + 4 * i);
+              pj[4 * i] = __uint_as_float(pv.x); pj[4 * i + 1] = __uint_as_float(pv.y);
+              pj[4 * i + 2] = __uint_as_float(pv.z); pj[4 * i + 3] = __uint_as_float(pv.w);
+            }
+#pragma unroll
+            for (int b8 = 0; b8 < 2; ++b8) {
+              if (b8 == 1 && !two) break;
+              const uint8_t* rb = b8 ? runB : runA;
+              uint4 vv[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                vv[i] = j0 + 16 * b8 + 2 * i + half < nctx ? lds_u4(rb + i * 24 * 16) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float pw = pj[8 * b8 + i];
+                o[0] = fmaf(pw, bf16_lo(vv[i].x), o[0]); o[1] = fmaf(pw, bf16_hi(vv[i].x), o[1]);
+                o[2] = fmaf(pw, bf16_lo(vv[i].y), o[2]); o[3] = fmaf(pw, bf16_hi(vv[i].y), o[3]);
+                o[4] = fmaf(pw, bf16_lo(vv[i].z), o[4]); o[5] = fmaf(pw, bf16_hi(vv[i].z), o[5]);
+                o[6] = fmaf(pw, bf16_lo(vv[i].w), o[6]); o[7] = fmaf(pw, bf16_hi(vv[i].w), o[7]);
+              }
+            }
+            consumed += two ? 2 : 1;
+            refill();
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += __shfl_down_sync(0xffffffffu, o[i], 12);
+          if (lane < 12) {
+            const float inv = 1.f / sum;
+            uint4 ov;
+            *reinterpret_cast<__nv_bfloat162*>(&ov.x) = __floats2bfloat162_rn(o[0] * inv, o[1] * inv);
+            *reinterpret_cast<__nv_bfloat162*>(&ov.y) = __floats2bfloat162_rn(o[2] * inv, o[3] * inv);
+            *reinterpret_cast<__nv_bfloat162*>(&ov.z) = __floats2bfloat162_rn(o[4] * inv, o[5] * inv);
+            *reinterpret_cast<__nv_bfloat162*>(&ov.w) = __floats2bfloat162_rn(o[6] * inv, o[7] * inv);
+            *reinterpret_cast<uint4*>(a.attn + (size_t)row * D + hd * kHeadDim + 8 * lane) = ov;
+          }
+        }
+        arrive_grid();
+      }
+      // ===============================================================================================================
+      // wo + residual (llama.py:259, :279): complete sums, h += , bf16(h * ffn_norm weight), sums of squares
+      // ===============================================================================================================
+      {
+        const Job j = job_wo(l);
+        wait_go();
+        if (j.on) {
+          arm_xbar(false);
+          float v[2][16];
+          int fl;
+          exchange(false, v, fl);
+          if (fin) finalize_resid(v, j.row0 + 32 * rk + fl, lane < 16, a.ffn_norm + (size_t)l * D, 2 * P + rk);
+        }
+        arrive_grid();
+      }
+      // ===============================================================================================================
+      // w1|w3 (rows interleaved) + SiLU * mul (llama.py:176-177) -> act [row][hidden unit] bf16
+      // ===============================================================================================================
+      {
+        const Job j = job_w13(l);
+        wait_go();
+        if (j.on) {
+          arm_xbar(true);
+          compute_rs(2 * (D / 64));
+          float v[2][16];
+          int fl;
+          exchange(true, v, fl);
+          const int f = j.row0 + 64 * rk + fl;  // even: w1 row f/2, odd: w3 row f/2
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = 32 * hn + 16 * c + i;
+              const float x = v[c][i] * rs_s[n];
+              const float pr = __shfl_xor_sync(0xffffffffu, x, 1);
+              if (fin && !(lane & 1) && n < R)
+                a.act[(size_t)n * F + (f >> 1)] = __float2bfloat16_rn(__fdividef(x, 1.f + __expf(-x)) * pr);
+            }
+        }
+        arrive_grid();
+      }
+      // ===============================================================================================================
+      // w2 + residual (llama.py:177, :282): K split over three pairs per 64-feature block; the pair halves that arrive last
+      // add the three partials in a fixed order and finalise like wo (next layer's attention norm, or the final norm)
+      // ===============================================================================================================
+      {
+        const Job j = job_w2(l);
+        wait_go();
+        if (j.on) {
+          arm_xbar(false);
+          float v[2][16];
+          int fl;
+          exchange(false, v, fl);
+          if (fin) {
+            const int blk = P / 3, third = P % 3;
+            const bool valid = lane < 16;
+            // partial of (block, third, rank): [32 features][64 rows] fp32
+            float* mine = a.w2_part + ((size_t)(blk * 3 + third) * 2 + rk) * (32 * 64);
+            if (valid) {
+#pragma unroll
+              for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                  *reinterpret_cast<float4*>(mine + fl * 64 + 32 * hn + 16 * c + i) = make_float4(v[c][i], v[c][i + 1], v[c][i + 2], v[c][i + 3]);
+            }
+            named_bar(2, 128);
+            if ((q & 1) == 0 && hn == 0 && lane == 0) {  // one thread of the four finalising warps
+              __threadfence();
+              const unsigned old = atomicAdd(a.w2_cnt + blk * 2 + rk, 1u);
+              __threadfence();
+              *flag_s = (old % 3u) == 2u;
+            }
+            named_bar(2, 128);
+            if (*flag_s) {
+              if (valid) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                  for (int i = 0; i < 16; i += 4) {
+                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int t3 = 0; t3 < 3; ++t3) {  // fixed order: the result does not depend on which pair came last
+                      const float4 o = __ldcg(reinterpret_cast<const float4*>(
+                          a.w2_part + ((size_t)(blk * 3 + t3) * 2 + rk) * (32 * 64) + fl * 64 + 32 * hn + 16 * c + i));
+                      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+                    }
+                    v[c][i] = s.x; v[c][i + 1] = s.y; v[c][i + 2] = s.z; v[c][i + 3] = s.w;
+                  }
+              }
+              const float* g_next = l + 1 < L ? a.attn_norm + (size_t)(l + 1) * D : a.final_norm;
+              finalize_resid(v, j.row0 + 32 * rk + fl, valid, g_next, 2 * blk + rk);
+            }
+          }
+        }
+        arrive_grid();
+      }
+    }
+    // =================================================================================================================
+    // final norm + heads (llama.py:503-504): logits [row][K * V] fp32
+    // =================================================================================================================
+    {
+      const Job j = job_heads();
+      wait_go();
+      if (j.on) {
+        arm_xbar(true);
+        compute_rs(2 * (D / 64));
+        float v[2][16];
+        int fl;
+        exchange(true, v, fl);
+        const int f = j.row0 + 64 * rk + fl;
+        if (fin) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = 32 * hn + 16 * c + i;
+              if (n < R) a.logits[(size_t)n * a.NH + f] = v[c][i] * rs_s[n];
+            }
+        }
+      }
+      arrive_grid();
+    }
+    // CFG / sampling / mask-fix / write-back (vaura_model.py:775-827): one warp per (clip, codebook)
+    wait_go();
+    const int nrows = a.sample.B * a.sample.K;
+    for (int u = aw * G + cta; u < nrows; u += G * 8) sample_row(a.sample, u / a.sample.K, u % a.sample.K, lane, offset);
+  }
+
+  if (cta == 0 && tid == 64) {  // every CTA read offset / epoch before its first barrier arrival
+    a.state->epoch = epoch + 1;
+    a.state->offset = offset + 1;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  hw_cluster_sync();  // no CTA leaves while its peer may still address its shared memory
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64));
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------------
+bool fused2_supported(int R, int L, int D, int F, int H, int NH, int sms, int page_size, int max_pages) {
+  const int pairs = sms / 2;
+  return R >= 1 && R <= 64 && L >= 1 && D % 128 == 0 && D / 128 <= kXTiles && F % 64 == 0 && NH % 128 == 0 && D / H == kHeadDim &&
+         3 * D / 64 <= pairs && 3 * (D / 64) <= pairs && 2 * F / 128 <= pairs && NH / 128 <= pairs && (F / 64 + 5) / 6 <= kXTiles &&
+         R * H <= 2 * sms * 8 && R <= sms && max_pages <= 32 && page_size >= 16 && !(page_size & (page_size - 1)) && (sms % 2) == 0 &&
+         2 * (D / 64) <= 64;
+}
+
+size_t fused2_workspace_bytes(int D) {
+  // h_t [D][64] f32 | q_t [D][64] bf16 | ssq_part [64][64] f32 | w2_part [D/64][3][2][32][64] f32 | w2_cnt [2 D / 64] u32
+  return (size_t)D * 64 * 4 + (size_t)D * 64 * 2 + 64 * 64 * 4 + (size_t)(D / 64) * 3 * 2 * 32 * 64 * 4 + 1024;
+}
+
+cudaError_t launch_decode_fused2(const Fused2Args& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
+                                 const void* w_heads, cudaStream_t st) {
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  static int ready[64] = {0};  // per device: shared-memory opt-in done, co-residency of the 74 clusters checked
+  static int dev_sms[64] = {0};
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!ready[dev]) {
+    e = cudaFuncSetAttribute(decode_step_fused2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(sms & ~1);
+    qc.blockDim = dim3(kThreads);
+    qc.dynamicSmemBytes = kSmem;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa;
+    qc.numAttrs = 1;
+    int nclusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&nclusters, decode_step_fused2, &qc);
+    if (e != cudaSuccess) return e;
+    if (nclusters < (sms & ~1) / 2) return cudaErrorCooperativeLaunchTooLarge;
+    dev_sms[dev] = sms & ~1;
+    ready[dev] = 1;
+  }
+  sms = dev_sms[dev];
+  if (!fused2_supported(a.R, a.L, a.D, a.F, a.H, a.NH, sms, a.kv.page_size, a.kv.max_pages_per_seq)) return cudaErrorInvalidValue;
+  const uint64_t D = a.D, F = a.F, L = a.L;
+  CUtensorMap m_hb, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads;
+  bool ok = tc_make_map_kblocks(&m_hb, a.hb, D, a.R, 1, D, (uint64_t)a.R * D, 64, kXBox) &&
+            tc_make_map_kblocks(&m_attn, a.attn, D, a.R, 1, D, (uint64_t)a.R * D, 64, kXBox) &&
+            tc_make_map_kblocks(&m_act, a.act, F, a.R, 1, F, (uint64_t)a.R * F, 64, kXBox) &&
+            tc_make_map_kblocks(&m_wqkv, wqkv, D, 3 * D, L, D, 3 * D * D, 64, 2) &&
+            tc_make_map_kblocks(&m_wo, wo, D, D, L, D, D * D, 64, 2) &&
+            tc_make_map_kblocks(&m_w13, w13, D, 2 * F, L, D, 2 * F * D, 128, 1) &&
+            tc_make_map_kblocks(&m_w2, w2, F, D, L, F, D * F, 64, 2) &&
+            tc_make_map_kblocks(&m_heads, w_heads, D, a.NH, 1, D, (uint64_t)a.NH * D, 128, 1);
+  if (!ok) return cudaErrorUnknown;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(sms);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at;
+  static int coop = -1;  // VAURA_FUSED2_NOCOOP=1: cluster attribute only (Nsight Compute's replay rejects cooperative cluster launches)
+  if (coop < 0) { const char* ev = getenv("VAURA_FUSED2_NOCOOP"); coop = !(ev && ev[0] == '1'); }
+  cfg.numAttrs = coop ? 2 : 1;
+  e = cudaLaunchKernelEx(&cfg, decode_step_fused2, m_hb, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads, a);
+  if (e != cudaSuccess && coop) {
+    // cooperative + cluster launch rejected: co-residency is still established by the occupancy query above (one CTA per SM
+    // on an otherwise idle device), so launch with the cluster attribute alone
+    (void)cudaGetLastError();
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, decode_step_fused2, m_hb, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads, a);
+  }
+  return e;
+}
+
+}  // namespace vaura

@@ -434,17 +434,22 @@ struct EpiLinear {
 // KSUB: 64-wide K blocks per pipeline stage.  The single-thread producer / MMA loops pay ~0.25 us of serialized
 // mbarrier-wait + fence + commit latency per stage; with thin tiles (decode: 64 rows x 32-64 weight rows) that
 // latency, not bandwidth, bounded the mainloop, so linear layers put 4 K blocks (16 UMMAs) behind each barrier.
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128, int KSUB = 1>
+// TERMS > 1 (fp32-equivalent GEMMs of the fp32-activation prefill): operand A holds TERMS bf16 terms of a split fp32
+// matrix side by side ([R][TERMS * Kw], term t of K block kb at column (t * g.bwrap + kb) * 64); a stage carries the TERMS A
+// tiles of one K block and ONE B tile, multiplied TERMS times - the weight tile is fetched once per K block, not per term.
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128, int KSUB = 1, int TERMS = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape g,
                const typename Epi::Params ep) {
   constexpr int SW = BLOCK_K * 2;
   static_assert(TILE_M == 64 || TILE_M == 128, "UMMA M for cta_group::1");
-  constexpr int A_BYTES = TILE_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, SUB_BYTES = A_BYTES + B_BYTES;
+  constexpr int A_BYTES = TILE_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, SUB_BYTES = TERMS * A_BYTES + B_BYTES;
+  constexpr int AT_BYTES = TERMS * A_BYTES;  // offset of the B tile inside a sub-stage
   constexpr int STAGE_BYTES = KSUB * SUB_BYTES;
   constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "stage buffers must stay 1024B aligned for the swizzle");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
+  static_assert(TERMS == 1 || KSUB == 1, "split operands use one K block per stage");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -495,8 +500,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_expect_tx_elect(&full[it], nsub * SUB_BYTES);
       for (int sub = 0; sub < nsub; ++sub) {
         const int gi = u0 + sub, tap = gi / g.kblocks, kb = gi % g.kblocks;
-        const int kbB = g.bwrap ? kb % g.bwrap : kb;
-        tma_load_3d_elect(smem + it * STAGE_BYTES + sub * SUB_BYTES + A_BYTES, &tmB, &full[it], kbB * BLOCK_K, n0, phase * g.ntaps + tap);
+        const int kbB = (TERMS == 1 && g.bwrap) ? kb % g.bwrap : kb;
+        tma_load_3d_elect(smem + it * STAGE_BYTES + sub * SUB_BYTES + AT_BYTES, &tmB, &full[it], kbB * BLOCK_K, n0, phase * g.ntaps + tap);
       }
     }
     if (g.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -511,10 +516,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int sub = 0; sub < nsub; ++sub) {
         const int gi = u0 + sub, tap = gi / g.kblocks, kb = gi % g.kblocks;
-        const int kbB = g.bwrap ? kb % g.bwrap : kb;
+        const int kbB = (TERMS == 1 && g.bwrap) ? kb % g.bwrap : kb;
         uint8_t* sa = ss + sub * SUB_BYTES;
-        if (it >= pre) tma_load_3d_elect(sa + A_BYTES, &tmB, &full[s], kbB * BLOCK_K, n0, phase * g.ntaps + tap);
-        tma_load_3d_elect(sa, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
+        if (it >= pre) tma_load_3d_elect(sa + AT_BYTES, &tmB, &full[s], kbB * BLOCK_K, n0, phase * g.ntaps + tap);
+#pragma unroll
+        for (int t = 0; t < TERMS; ++t)
+          tma_load_3d_elect(sa + t * A_BYTES, &tmA, &full[s], (t * g.bwrap + kb) * BLOCK_K, m0 + g.tap_off[phase * g.ntaps + tap], b);
       }
     }
     __syncwarp();
@@ -528,10 +535,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int nsub = min(KSUB, u_end - (u_begin + it * KSUB));
       for (int sub = 0; sub < nsub; ++sub) {
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES + sub * SUB_BYTES);
-        const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
+        const uint64_t bdesc = make_smem_desc<SW>(a_addr + AT_BYTES);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k)  // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
-          umma_bf16_f16_elect(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | sub | k) != 0);
+        for (int t = 0; t < TERMS; ++t) {
+          const uint64_t adesc = make_smem_desc<SW>(a_addr + t * A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)  // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
+            umma_bf16_f16_elect(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | sub | t | k) != 0);
+        }
       }
       umma_commit_elect(&empty[s]);  // frees the smem slot once these MMAs have read it
     }
@@ -1409,13 +1420,18 @@ static bool make_map_kblocks(CUtensorMap* m, const void* base, uint64_t K, uint6
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128, int KSUB = 1>
+bool tc_make_map_kblocks(void* map, const void* base, uint64_t K, uint64_t rows, uint64_t outer, uint64_t row_stride_el,
+                         uint64_t outer_stride_el, int box_rows, int nblk) {
+  return make_map_kblocks(static_cast<CUtensorMap*>(map), base, K, rows, outer, row_stride_el, outer_stride_el, box_rows, nblk);
+}
+
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128, int KSUB = 1, int TERMS = 1>
 static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcShape& g, const typename Epi::Params& ep,
                              int m_tiles, int n_tiles, cudaStream_t st) {
-  constexpr int smem = STAGES * KSUB * (TILE_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+  constexpr int smem = STAGES * KSUB * (TERMS * TILE_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
   static_assert(smem <= 227 * 1024, "stage ring exceeds shared memory");
   if (KSUB > 1 && g.ntaps != 1) return cudaErrorInvalidValue;
-  auto kern = gemm_tc_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, TILE_M, KSUB>;
+  auto kern = gemm_tc_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, TILE_M, KSUB, TERMS>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1587,13 +1603,14 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st) {
   if (a.K % 64 != 0 || a.N % a.block_n != 0) return cudaErrorInvalidValue;
   const int wk = a.w_k > 0 ? a.w_k : a.K;  // K extent of W (A may hold several bf16 terms side by side)
   if (wk % 64 != 0 || a.K % wk != 0) return cudaErrorInvalidValue;
+  const bool split3 = a.K == 3 * wk;       // three terms: one weight tile per K block multiplied with the three A tiles
   // up to 64 rows: UMMA M=64 halves the activation tile, so twice as many weight bytes fit in flight per SM
-  const int tile_m = a.R <= 64 ? 64 : kTileM;
+  const int tile_m = (a.R <= 64 && !split3) ? 64 : kTileM;
   CUtensorMap ta, tb;
   if (!make_map(&ta, a.A, a.K, a.R, 1, a.lda, (uint64_t)a.R * a.lda, 64, tile_m, false)) return cudaErrorUnknown;
   if (!make_map(&tb, a.W, wk, a.N, 1, wk, (uint64_t)a.N * wk, 64, a.block_n, false)) return cudaErrorUnknown;
   TcShape g{};
-  g.ntaps = 1; g.nphase = 1; g.kblocks = a.K / 64; g.batch = 1;
+  g.ntaps = 1; g.nphase = 1; g.kblocks = split3 ? wk / 64 : a.K / 64; g.batch = 1;
   g.bwrap = wk != a.K ? wk / 64 : 0;
   g.ksplit = (a.epi == EPI_RESID && a.ksplit > 1) ? a.ksplit : 1;
   if (g.ksplit > g.kblocks) g.ksplit = g.kblocks;
@@ -1604,6 +1621,16 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st) {
   ep.pos0 = a.pos0; ep.npos = a.npos; ep.layer = a.layer; ep.d_model = a.d_model; ep.atomic = g.ksplit > 1;
   ep.aux = a.aux;
   const int mt = (a.R + tile_m - 1) / tile_m, nt = a.N / a.block_n;
+  if (split3) {
+    if (g.ksplit != 1) return cudaErrorInvalidValue;
+    switch (a.block_n) {  // stage = 3 x 16 KB of A + the weight tile
+      case 32: return launch_tc<32, 64, 4, 1, EpiLinear, 128, 1, 3>(ta, tb, g, ep, mt, nt, st);
+      case 64: return launch_tc<64, 64, 3, 1, EpiLinear, 128, 1, 3>(ta, tb, g, ep, mt, nt, st);
+      case 128: return launch_tc<128, 64, 3, 1, EpiLinear, 128, 1, 3>(ta, tb, g, ep, mt, nt, st);
+      case 256: return launch_tc<256, 64, 2, 1, EpiLinear, 128, 1, 3>(ta, tb, g, ep, mt, nt, st);
+    }
+    return cudaErrorInvalidValue;
+  }
   if (tile_m == 64) {
     switch (a.block_n) {
       case 16: return launch_tc<16, 64, 4, 1, EpiLinear, 64, 4>(ta, tb, g, ep, mt, nt, st);

@@ -145,6 +145,39 @@ bool fused_step_supported(int R, int D, int F, int NH);
 cudaError_t launch_decode_fused_bf16(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
                                      const void* w_heads, cudaStream_t st);
 
+// fused decode step, second design (decode_fused2.cu: decode_step_fused2): rows <= 64, clusters of two CTAs
+struct Fused2Args {
+  const float *attn_norm, *ffn_norm, *final_norm, *rope;
+  float* h_t;                // [D][64] residual stream, transposed (feature-major), fp32
+  __nv_bfloat16* hb;         // [R][D] bf16(h * next norm weight): the B operand of the next GEMM
+  __nv_bfloat16* q_t;        // [D][64] RoPE'd q, feature-major
+  __nv_bfloat16 *attn, *act; // [R][D], [R][F]
+  float* ssq_part;           // [<= 64 slots][64] partial sums of squares of the residual rows
+  float* w2_part;            // [D/64][3][2][32][64] partial w2 sums of the three K thirds
+  unsigned* w2_cnt;          // [D/64][2] arrival counters of the K thirds (monotonic, start at a multiple of 3)
+  float* logits;             // [R][NH]
+  KvView kv;                 // bf16 pages
+  StepState* state;
+  int R, L, D, F, H, NH;
+  float eps, scale;
+  unsigned long long* timing;      // optional: %globaltimer before / after every device-wide barrier wait of CTA `timing_cta`
+  unsigned long long* step_times;  // [kMaxCtx + 16]: %globaltimer at the start of the launch that samples column `offset`
+  int timing_cta;
+  const int32_t* seq;       // [B][K][S]
+  const float* cond_rows;   // [rows][cond_tokens+1][cond_dim]
+  const float* tables;      // [K][V+1][d - cond_dim]
+  int batch, Kc, S, vocab, cond_dim, cond_tokens, atpvf;
+  SampleArgs sample;        // state = nullptr: the column comes from this kernel's own state read
+};
+bool fused2_supported(int R, int L, int D, int F, int H, int NH, int sms, int page_size, int max_pages);
+size_t fused2_workspace_bytes(int D);
+cudaError_t launch_decode_fused2(const Fused2Args& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
+                                 const void* w_heads, cudaStream_t st);
+// [outer][rows][K] 16-bit tensor seen as (64, rows, K / 64, outer); one box = nblk K blocks of box_rows rows, landing in shared
+// memory as nblk consecutive 128B-swizzled [box_rows x 64] sub-tiles (gemm_tcgen05.cu).  `map` is a CUtensorMap.
+bool tc_make_map_kblocks(void* map, const void* base, uint64_t K, uint64_t rows, uint64_t outer, uint64_t row_stride_el,
+                         uint64_t outer_stride_el, int box_rows, int nblk);
+
 bool conv_tc_supported(int Cin, int Cout, int ntaps, int nphase);
 cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cudaStream_t st);
 cudaError_t init_decode_kernels();
