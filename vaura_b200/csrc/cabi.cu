@@ -357,9 +357,11 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
     if (fuse_io_on < 0) { const char* ev = getenv("VAURA_FUSED_IO"); fuse_io_on = !(ev && ev[0] == '0'); }
     if (fused_on && npos == 1 && !logits_all && state && fused_step_supported(R, d.d_model, d.ffn_dim, d.num_codebooks * d.vocab)) {
       const bool io = fuse_io_on && fuse_sample && sampled && d.cond_dim % 4 == 0 && (d.d_model - d.cond_dim) % 4 == 0;
-      // second design (decode_fused2.cu): swap-AB tiles, K split inside CTA pairs, norms folded into their neighbours
+      // second design (decode_fused2.cu): swap-AB tiles, K split inside CTA pairs, norms folded into their neighbours.
+      // Parity-green but measured slower than decode_step_fused_bf16 (profiles/r02_fused2_timeline.summary.txt: 70 vs 40 us
+      // per layer at position 127), so it is opt-in: VAURA_FUSED2=1.
       static int fused2_on = -1;
-      if (fused2_on < 0) { const char* ev = getenv("VAURA_FUSED2"); fused2_on = !(ev && ev[0] == '0'); }
+      if (fused2_on < 0) { const char* ev = getenv("VAURA_FUSED2"); fused2_on = (ev && ev[0] == '1'); }
       int sms2 = 0, dev2 = 0;
       cudaGetDevice(&dev2);
       cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, dev2);
@@ -382,6 +384,7 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
         { const char* tm = getenv("VAURA_PERSIST_TIMING"); fa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
         fa.step_times = ws.timing + 1024;
         { const char* tc = getenv("VAURA_TIMING_CTA"); fa.timing_cta = tc ? atoi(tc) : 0; }
+        { const char* fl = getenv("VAURA_FUSED2_FLAGS"); fa.flags = fl ? atoi(fl) : 0; }
         fa.seq = seq; fa.cond_rows = cond_rows; fa.tables = w.tok_tables; fa.batch = batch; fa.Kc = d.num_codebooks; fa.S = S;
         fa.vocab = d.vocab; fa.cond_dim = d.cond_dim; fa.cond_tokens = d.cond_tokens; fa.atpvf = d.audio_tokens_per_video_frame;
         fa.sample = *fuse_sample;

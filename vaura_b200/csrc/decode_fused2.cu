@@ -172,7 +172,7 @@ constexpr int kAttnSlots = 4, kRunBytes = 16 * kHeadDim * 2;  // per attention w
 constexpr int kRing = kNS * kStage;           // 96 KB
 constexpr int kXBytes = kXTiles * kXSub;      // 96 KB (activations; attention staging of the 8 work warps)
 constexpr int kOffX = kRing, kOffXbuf = kOffX + kXBytes, kOffBars = kOffXbuf + kXbuf, kOffMisc = kOffBars + 512;
-constexpr int kSmem = kOffMisc + 1024 + 1024;  // + alignment slack
+constexpr int kSmem = kOffMisc + 2048 + 1024;  // + alignment slack
 static_assert(8 * kAttnSlots * kRunBytes <= kXBytes, "attention staging fits the activation region");
 static_assert(8 * (kHeadDim + kMaxCtx) * 4 <= kXbuf, "attention scratch aliases the exchange buffer");
 static_assert(kSmem <= 227 * 1024, "shared memory");
@@ -209,7 +209,8 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
            *go = xbar + 1, *attn_bars = go + 1;  // attn_bars: 8 warps x kAttnSlots
   float* rs_s = reinterpret_cast<float*>(smem + kOffMisc);          // [64] rsqrt(mean square + eps) of every sequence row
   float* ssq_s = rs_s + 64;                                         // [2][64] partial sums of squares of the two finalising quadrants
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ssq_s + 128);
+  uint32_t* kvoff_s = reinterpret_cast<uint32_t*>(ssq_s + 128);     // [64] element offset of (row n, position p, head 0) in a K or V plane
+  uint32_t* tmem_slot = kvoff_s + 64;
   int* flag_s = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -226,6 +227,15 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
     a.step_times[offset] = t;
   }
   const unsigned nbar = (unsigned)(5 * L + 2);
+  if (tid >= 64 && tid < 128) {  // the page of position p is the same in every layer: one look-up per row and launch
+    const int n = tid - 64;
+    uint32_t off = 0;
+    if (n < a.R) {
+      const int page = a.kv.page_table[n * a.kv.max_pages_per_seq + p / a.kv.page_size];
+      off = (uint32_t)((page * a.kv.nhead) * a.kv.page_size + (p % a.kv.page_size)) * kHeadDim;
+    }
+    kvoff_s[n] = off;
+  }
 
   if (tid == 0) {
     const CUtensorMap* maps[8] = {&tm_hb, &tm_attn, &tm_act, &tm_wqkv, &tm_wo, &tm_w13, &tm_w2, &tm_heads};
@@ -267,7 +277,11 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
   // =====================================================================================================================
   if (warp == 0) {
     int wi = 0;  // stages pushed so far
-    auto push_job = [&](const Job& j, const CUtensorMap* map) {
+    uint32_t gpw = 0;
+    // flags bit 0: no run-ahead - a job's weights are requested after the device-wide barrier that starts its phase (`nb`
+    // barriers since the previous job)
+    auto push_job = [&](const Job& j, const CUtensorMap* map, int nb) {
+      if (a.flags & 1) for (int i = 0; i < nb; ++i) { mbar_wait(go, gpw); gpw ^= 1; }
       if (!j.on) return;
       const int ns = stages_of(j);
       for (int s = 0; s < ns; ++s, ++wi) {
@@ -280,12 +294,12 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
       }
     };
     for (int l = 0; l < L; ++l) {
-      push_job(job_qkv(l), &tm_wqkv);
-      push_job(job_wo(l), &tm_wo);
-      push_job(job_w13(l), &tm_w13);
-      push_job(job_w2(l), &tm_w2);
+      push_job(job_qkv(l), &tm_wqkv, 1);
+      push_job(job_wo(l), &tm_wo, 2);
+      push_job(job_w13(l), &tm_w13, 1);
+      push_job(job_w2(l), &tm_w2, 1);
     }
-    push_job(job_heads(), &tm_heads);
+    push_job(job_heads(), &tm_heads, 1);
     __syncwarp();
   }
   // =====================================================================================================================
@@ -312,14 +326,24 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
       }
       __syncwarp();
     };
+    int mst = -1;  // stamps of the last layer: timing[400 + 16 phase + k]: 0 go, 1 loads issued, 2 first weights there, 3.. boxes there, 8 MMAs issued
+    auto mstamp = [&](int k) {
+      if (a.timing && cta == a.timing_cta && lane == 0 && mst >= 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.timing[400 + 16 * mst + k] = t;
+      }
+    };
     auto gemm = [&](const Job& j, const CUtensorMap* xmap) {
       if (!j.on) return;
+      mstamp(0);
       // activation columns of this CTA's K half: boxes of kXBox K blocks, each with its own barrier
       const int nbox = (j.nkb + kXBox - 1) / kXBox;
       for (int b = 0; b < nbox; ++b) {
         mbar_expect_tx_elect(&xfull[b], kXBox * kXSub);
         tma_load_4d_elect(xreg + b * kXBox * kXSub, xmap, &xfull[b], 0, 0, j.kb0 + b * kXBox, 0);
       }
+      mstamp(1);
       const uint32_t idesc = j.m128 ? make_idesc(128, 64) : make_idesc(64, 64);
       const int ns = stages_of(j);
       const uint32_t x_lo = (smem_u32(xreg) & 0x3FFFF) >> 4;
@@ -327,6 +351,7 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
       for (int s = 0; s < ns; ++s, ++ci) {
         const int slot = ci % kNS;
         mbar_wait(&wfull[slot], (ci / kNS) & 1);
+        if (s == 0) mstamp(2);
         const uint32_t w_lo = (smem_u32(ring + slot * kStage) & 0x3FFFF) >> 4;
         const int nk = j.m128 ? 1 : min(2, j.nkb - 2 * s);
         for (int u = 0; u < nk; ++u) {
@@ -335,6 +360,7 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
             box_ready = kbl / kXBox;
             mbar_wait(&xfull[box_ready], (xpar >> box_ready) & 1u);
             xpar ^= 1u << box_ready;
+            mstamp(3 + box_ready);
           }
           tcgen05_fence_after();
           const uint32_t a_lo = w_lo + u * (kXSub >> 4), b_lo = x_lo + kbl * (kXSub >> 4);
@@ -344,19 +370,26 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
         umma_commit_elect(&wempty[slot]);
       }
       umma_commit_elect(tmem_full);
+      mstamp(8);
     };
     wait_grid();  // embedding done
     for (int l = 0; l < L; ++l) {
+      const bool lastl = l == L - 1;
+      mst = lastl ? 0 : -1;
       gemm(job_qkv(l), &tm_hb);
       wait_grid();
       wait_grid();  // attention
+      mst = lastl ? 2 : -1;
       gemm(job_wo(l), &tm_attn);
       wait_grid();
+      mst = lastl ? 3 : -1;
       gemm(job_w13(l), &tm_hb);
       wait_grid();
+      mst = lastl ? 4 : -1;
       gemm(job_w2(l), &tm_act);
       wait_grid();
     }
+    mst = -1;
     gemm(job_heads(), &tm_hb);
     wait_grid();
     __syncwarp();
@@ -373,21 +406,40 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
     const uint32_t peer = (uint32_t)(rk ^ 1);
     const uint32_t r_xbuf = mapa_u32(smem_u32(xbuf), peer), r_xbar = mapa_u32(smem_u32(xbar), peer);
 
+    // optional stamps of warps 2 and 4 (lane 0) in the last layer: timing[600 + 200 (aw / 2) + 8 phase + k]
+    int st_phase = -1;
+    auto wstamp = [&](int k) {
+      if (a.timing && cta == a.timing_cta && lane == 0 && (aw == 0 || aw == 2) && st_phase >= 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.timing[600 + 200 * (aw >> 1) + 8 * st_phase + k] = t;
+      }
+    };
     auto arrive_grid = [&]() {  // after a barrier over the work warps: everything they stored is ordered before the count
+      wstamp(6);
       named_bar(1, kWork);
       if (wt == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&a.state->barrier) : "memory");
+      wstamp(7);
     };
-    auto wait_go = [&]() { mbar_wait(go, gp); gp ^= 1; };
+    auto wait_go = [&]() { mbar_wait(go, gp); gp ^= 1; wstamp(0); };
 
     // rs_s[n] = rsqrt(mean_f h[n][f]^2 + eps) from the partial sums of squares the previous finaliser CTAs left
     auto compute_rs = [&](int nslots) {
-      for (int i = 0; i < 8; ++i) {
-        const int n = aw * 8 + i;
-        float s = 0.f;
-        for (int sl = lane; sl < nslots; sl += 32) s += __ldcg(a.ssq_part + sl * 64 + n);
-        s = warp_sum(s);
-        if (lane == 0) rs_s[n] = rsqrtf(s / (float)D + a.eps);
+      // warp aw owns rows 8 aw .. 8 aw + 7: lane = (slot group sg = lane / 8, row i = lane % 8); every lane's loads (<= 16
+      // slots) are issued before any is used
+      const int i = lane & 7, sg = lane >> 3, n = aw * 8 + i;
+      float part[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int sl = sg + 4 * k;
+        part[k] = sl < nslots ? __ldcg(a.ssq_part + sl * 64 + n) : 0.f;
       }
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s += part[k];
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      if (lane < 8) rs_s[n] = rsqrtf(s / (float)D + a.eps);
       named_bar(1, kWork);
     };
 
@@ -395,9 +447,11 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
     //      v[c][i] = complete sum of feature `fl` (local to the finalising half) for sequence rows 32 hn + 16 c + i. ----
     auto exchange = [&](bool m128, float (&v)[2][16], int& fl) {
       const int nrow = m128 ? 32 : 16;            // valid lanes of a quadrant
-      fl = nrow * (q & 1) + lane;
+      fl = nrow * (q & 1) + lane;                 // feature index inside the finalising half
+      wstamp(1);
       mbar_wait(tmem_full, tp); tp ^= 1;
       tcgen05_fence_after();
+      wstamp(2);
 #pragma unroll
       for (int c = 0; c < 2; ++c) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + 32 * hn + 16 * c, v[c]);
       if (!fin) {
@@ -423,22 +477,36 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
       }
       xp ^= 1;
       tcgen05_fence_before();
+      wstamp(3);
     };
     // the receiving side arms its exchange barrier once per GEMM phase (any time before it waits on it)
     auto arm_xbar = [&](bool m128) { if (wt == 0) mbar_expect_tx(xbar, (m128 ? 64 : 32) * 64 * 4); };
 
-    // ---- residual finaliser (wo, w2): h += v, hb = bf16(h * g_next), partial sums of squares ----
-    auto finalize_resid = [&](float (&v)[2][16], int f, bool valid, const float* g_next, int slot) {
+    // ---- residual finaliser (wo, w2): h += v, hb = bf16(h * g_next), partial sums of squares.  The old residual values and
+    //      the norm weight are requested by prefetch_resid BEFORE the accumulator wait (their L2 latency overlaps the MMAs). ----
+    auto prefetch_resid = [&](int f, bool valid, const float* g_next, float (&hold)[2][16], float& gw) {
+      gw = 0.f;
+      if (valid) {
+        gw = __ldg(g_next + f);
+        const float* hrow = a.h_t + (size_t)f * 64 + 32 * hn;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 o = __ldcg(reinterpret_cast<const float4*>(hrow + 16 * c + i));
+            hold[c][i] = o.x; hold[c][i + 1] = o.y; hold[c][i + 2] = o.z; hold[c][i + 3] = o.w;
+          }
+      }
+    };
+    auto finalize_resid = [&](float (&v)[2][16], const float (&hold)[2][16], float gw, int f, bool valid, int slot) {
       float ss[2][16];
       if (valid) {
         float* hrow = a.h_t + (size_t)f * 64 + 32 * hn;
-        const float gw = __ldg(g_next + f);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
-            const float4 o = __ldcg(reinterpret_cast<const float4*>(hrow + 16 * c + i));
-            v[c][i] += o.x; v[c][i + 1] += o.y; v[c][i + 2] += o.z; v[c][i + 3] += o.w;
+            v[c][i] += hold[c][i]; v[c][i + 1] += hold[c][i + 1]; v[c][i + 2] += hold[c][i + 2]; v[c][i + 3] += hold[c][i + 3];
             *reinterpret_cast<float4*>(hrow + 16 * c + i) = make_float4(v[c][i], v[c][i + 1], v[c][i + 2], v[c][i + 3]);
           }
 #pragma unroll
@@ -454,13 +522,17 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) ss[c][i] = 0.f;
       }
-      // sum over the features (lanes) of this warp, then over the two finalising quadrants through shared memory
+      // sum over the 16 features (lanes 0-15) of this warp: after four butterfly steps lane 0 holds every column's sum
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float s = warp_sum(ss[c][i]);
-          if (lane == 0) ssq_s[(q & 1) * 64 + 32 * hn + 16 * c + i] = s;
+          float s2 = ss[c][i];
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+          if (lane == 0) ssq_s[(q & 1) * 64 + 32 * hn + 16 * c + i] = s2;
         }
       named_bar(2, 128);  // the four finalising warps
       if ((q & 1) == 0) a.ssq_part[slot * 64 + 32 * hn + lane] = ssq_s[32 * hn + lane] + ssq_s[64 + 32 * hn + lane];
@@ -528,42 +600,59 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
       // ===============================================================================================================
       {
         const Job j = job_qkv(l);
+        st_phase = l == L - 1 ? 0 : -1;
         wait_go();
         if (j.on) {
           arm_xbar(false);
           compute_rs(l == 0 ? 1 : 2 * (D / 64));
           float v[2][16];
-          int fl;
-          exchange(false, v, fl);
+          int fl = 16 * (q & 1) + lane;
           const int f = j.row0 + 32 * rk + fl;          // output feature of wqkv
           const int sec = f / D, within = f % D, hd = within / kHeadDim, e = within % kHeadDim;
           const bool valid = fin && lane < 16;
+          // requested before the accumulator wait: RoPE pair of this feature
           float2 cs = make_float2(1.f, 0.f);
           if (valid && sec != 2) cs = __ldg(reinterpret_cast<const float2*>(a.rope + ((size_t)p * (kHeadDim / 2) + (e >> 1)) * 2));
-          const float sgn = (lane & 1) ? cs.y : -cs.y;   // even feature: x cos - partner sin; odd: x cos + partner sin
+          exchange(false, v, fl);
+          if (fin) {  // (the partner of a RoPE pair sits in the neighbouring lane of the same warp)
+            const float sgn = (lane & 1) ? cs.y : -cs.y;   // even feature: x cos - partner sin; odd: x cos + partner sin
+            // element offset of (layer, K or V, row n, position p, head hd, e) = plane + kvoff_s[n] + hd * page_size * 96 + e
+            const size_t plane = (size_t)(l * 2 + (sec == 2 ? 1 : 0)) * a.kv.num_pages * a.kv.nhead * a.kv.page_size * kHeadDim +
+                                 (size_t)hd * a.kv.page_size * kHeadDim + e;
+            __nv_bfloat16* kvp = reinterpret_cast<__nv_bfloat16*>(a.kv.pages) + plane;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < 2; ++c) {
+              float rsv[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float x = v[c][i] * rs_s[32 * hn + 16 * c + i];
-              const float pr = __shfl_xor_sync(0xffffffffu, x, 1);
-              v[c][i] = x * cs.x + pr * sgn;
-            }
-            if (valid) {
-              if (sec == 0) {
-                uint4 o[2];
-                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(o);
+              for (int i = 0; i < 16; i += 4) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rs_s + 32 * hn + 16 * c + i);
+                rsv[i] = r4.x; rsv[i + 1] = r4.y; rsv[i + 2] = r4.z; rsv[i + 3] = r4.w;
+              }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) h2[i] = __floats2bfloat162_rn(v[c][2 * i], v[c][2 * i + 1]);
-                uint4* dst = reinterpret_cast<uint4*>(a.q_t + (size_t)within * 64 + 32 * hn + 16 * c);
-                dst[0] = o[0];
-                dst[1] = o[1];
-              } else {
-                __nv_bfloat16* kvp = reinterpret_cast<__nv_bfloat16*>(a.kv.pages);
+              for (int i = 0; i < 16; ++i) {
+                const float x = v[c][i] * rsv[i];
+                const float pr = __shfl_xor_sync(0xffffffffu, x, 1);
+                v[c][i] = x * cs.x + pr * sgn;
+              }
+              if (valid) {
+                if (sec == 0) {
+                  uint4 o[2];
+                  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const int n = 32 * hn + 16 * c + i;
-                  if (n < R) kvp[a.kv.row(l, sec - 1, n, p, hd) + e] = __float2bfloat16_rn(v[c][i]);
+                  for (int i = 0; i < 8; ++i) h2[i] = __floats2bfloat162_rn(v[c][2 * i], v[c][2 * i + 1]);
+                  uint4* dst = reinterpret_cast<uint4*>(a.q_t + (size_t)within * 64 + 32 * hn + 16 * c);
+                  dst[0] = o[0];
+                  dst[1] = o[1];
+                } else {
+                  uint32_t off[16];
+#pragma unroll
+                  for (int i = 0; i < 16; i += 4) {
+                    const uint4 o4 = *reinterpret_cast<const uint4*>(kvoff_s + 32 * hn + 16 * c + i);
+                    off[i] = o4.x; off[i + 1] = o4.y; off[i + 2] = o4.z; off[i + 3] = o4.w;
+                  }
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (32 * hn + 16 * c + i < R) kvp[off[i]] = __float2bfloat16_rn(v[c][i]);
                 }
               }
             }
@@ -576,6 +665,7 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
       // positions staged by per-warp bulk copies into the activation region (profiles/r01_fused_step_b64.summary.txt)
       // ===============================================================================================================
       {
+        st_phase = l == L - 1 ? 1 : -1;
         wait_go();
         float* qs = xbuf + aw * (kHeadDim + kMaxCtx);
         float* sc = qs + kHeadDim;
@@ -741,13 +831,16 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
       // ===============================================================================================================
       {
         const Job j = job_wo(l);
+        st_phase = l == L - 1 ? 2 : -1;
         wait_go();
         if (j.on) {
           arm_xbar(false);
-          float v[2][16];
-          int fl;
+          float v[2][16], hold[2][16], gw;
+          int fl = 16 * (q & 1) + lane;
+          const int f = j.row0 + 32 * rk + fl;
+          prefetch_resid(f, fin && lane < 16, a.ffn_norm + (size_t)l * D, hold, gw);
           exchange(false, v, fl);
-          if (fin) finalize_resid(v, j.row0 + 32 * rk + fl, lane < 16, a.ffn_norm + (size_t)l * D, 2 * P + rk);
+          if (fin) finalize_resid(v, hold, gw, f, lane < 16, 2 * P + rk);
         }
         arrive_grid();
       }
@@ -756,6 +849,7 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
       // ===============================================================================================================
       {
         const Job j = job_w13(l);
+        st_phase = l == L - 1 ? 3 : -1;
         wait_go();
         if (j.on) {
           arm_xbar(true);
@@ -764,16 +858,31 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
           int fl;
           exchange(true, v, fl);
           const int f = j.row0 + 64 * rk + fl;  // even: w1 row f/2, odd: w3 row f/2
+          if (fin) {
+            __nv_bfloat16* arow = a.act + (f >> 1);
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
+            for (int c = 0; c < 2; ++c) {
+              float rsv[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int n = 32 * hn + 16 * c + i;
-              const float x = v[c][i] * rs_s[n];
-              const float pr = __shfl_xor_sync(0xffffffffu, x, 1);
-              if (fin && !(lane & 1) && n < R)
-                a.act[(size_t)n * F + (f >> 1)] = __float2bfloat16_rn(__fdividef(x, 1.f + __expf(-x)) * pr);
+              for (int i = 0; i < 16; i += 4) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rs_s + 32 * hn + 16 * c + i);
+                rsv[i] = r4.x; rsv[i + 1] = r4.y; rsv[i + 2] = r4.z; rsv[i + 3] = r4.w;
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float x = v[c][i] * rsv[i];
+                const float pr = __shfl_xor_sync(0xffffffffu, x, 1);
+                v[c][i] = __fdividef(x, 1.f + __expf(-x)) * pr;  // SiLU(w1 x) * (w3 x) on the even lanes
+              }
+              if (!(lane & 1)) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int n = 32 * hn + 16 * c + i;
+                  if (n < R) arow[(size_t)n * F] = __float2bfloat16_rn(v[c][i]);
+                }
+              }
             }
+          }
         }
         arrive_grid();
       }
@@ -783,11 +892,14 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
       // ===============================================================================================================
       {
         const Job j = job_w2(l);
+        st_phase = l == L - 1 ? 4 : -1;
         wait_go();
         if (j.on) {
           arm_xbar(false);
-          float v[2][16];
-          int fl;
+          float v[2][16], hold[2][16], gw;
+          int fl = 16 * (q & 1) + lane;
+          const int f = j.row0 + 32 * rk + fl;
+          prefetch_resid(f, fin && lane < 16, l + 1 < L ? a.attn_norm + (size_t)(l + 1) * D : a.final_norm, hold, gw);
           exchange(false, v, fl);
           if (fin) {
             const int blk = P / 3, third = P % 3;
@@ -825,8 +937,7 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
                     v[c][i] = s.x; v[c][i + 1] = s.y; v[c][i + 2] = s.z; v[c][i + 3] = s.w;
                   }
               }
-              const float* g_next = l + 1 < L ? a.attn_norm + (size_t)(l + 1) * D : a.final_norm;
-              finalize_resid(v, j.row0 + 32 * rk + fl, valid, g_next, 2 * blk + rk);
+              finalize_resid(v, hold, gw, f, valid, 2 * blk + rk);
             }
           }
         }
@@ -838,6 +949,7 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
     // =================================================================================================================
     {
       const Job j = job_heads();
+      st_phase = -1;
       wait_go();
       if (j.on) {
         arm_xbar(true);
@@ -847,13 +959,21 @@ decode_step_fused2(const __grid_constant__ CUtensorMap tm_hb, const __grid_const
         exchange(true, v, fl);
         const int f = j.row0 + 64 * rk + fl;
         if (fin) {
+          float* lrow = a.logits + f;
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
+          for (int c = 0; c < 2; ++c) {
+            float rsv[16];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rs_s + 32 * hn + 16 * c + i);
+              rsv[i] = r4.x; rsv[i + 1] = r4.y; rsv[i + 2] = r4.z; rsv[i + 3] = r4.w;
+            }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int n = 32 * hn + 16 * c + i;
-              if (n < R) a.logits[(size_t)n * a.NH + f] = v[c][i] * rs_s[n];
+              if (n < R) lrow[(size_t)n * a.NH] = v[c][i] * rsv[i];
             }
+          }
         }
       }
       arrive_grid();

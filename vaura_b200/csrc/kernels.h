@@ -163,6 +163,7 @@ struct Fused2Args {
   unsigned long long* timing;      // optional: %globaltimer before / after every device-wide barrier wait of CTA `timing_cta`
   unsigned long long* step_times;  // [kMaxCtx + 16]: %globaltimer at the start of the launch that samples column `offset`
   int timing_cta;
+  int flags;                // bit 0: the weight ring does not run ahead of the device-wide barriers (experiment)
   const int32_t* seq;       // [B][K][S]
   const float* cond_rows;   // [rows][cond_tokens+1][cond_dim]
   const float* tables;      // [K][V+1][d - cond_dim]
