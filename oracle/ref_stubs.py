@@ -196,3 +196,103 @@ def build_reference_model(sdims, cdims, seed=0, codec_half=False):
     model.eval()
     model.sampler.audio_tokens_per_video_frame = 7  # scripts/generate.py:216
     return model
+
+
+# ------------------------------------------------------------------------------------------------
+# Segment-AVCLIP / MotionFormer: stubs for timm + omegaconf so the reference's own
+# models/modules/feature_extractors/avclip/motionformer.py imports and runs unmodified
+# ------------------------------------------------------------------------------------------------
+class _AttrDict(dict):
+    """What the reference needs from an OmegaConf node: attribute read / write and .get()."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _to_attr(o):
+    if isinstance(o, dict):
+        return _AttrDict({k: _to_attr(v) for k, v in o.items()})
+    if isinstance(o, list):
+        return [_to_attr(v) for v in o]
+    return o
+
+
+def install_motionformer_stubs():
+    import yaml
+
+    avclip = os.path.join(REFERENCE_ROOT, "models", "modules", "feature_extractors", "avclip")
+    for p in (REFERENCE_ROOT, avclip):  # motionformer.py imports `motionformer_src.*` as a top-level package
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+    oc = types.ModuleType("omegaconf")
+
+    class OmegaConf:
+        @staticmethod
+        def load(path):
+            with open(path) as f:
+                return _to_attr(yaml.safe_load(f))
+
+    oc.OmegaConf = OmegaConf
+    sys.modules["omegaconf"] = oc
+
+    class DropPath(nn.Module):  # timm.models.layers.DropPath: stochastic depth, identity in eval mode
+        def __init__(self, drop_prob=0.0):
+            super().__init__()
+            self.drop_prob = drop_prob
+
+        def forward(self, x):
+            assert not self.training, "stub DropPath is eval-only"
+            return x
+
+    def trunc_normal_(tensor, mean=0.0, std=1.0, a=-2.0, b=2.0):
+        return nn.init.trunc_normal_(tensor, mean=mean, std=std, a=a, b=b)
+
+    timm = types.ModuleType("timm")
+    t_models = types.ModuleType("timm.models")
+    t_layers = types.ModuleType("timm.models.layers")
+    t_layers.trunc_normal_ = trunc_normal_
+    t_layers.DropPath = DropPath
+    t_layers.to_2tuple = lambda x: x if isinstance(x, tuple) else (x, x)
+    t_data = types.ModuleType("timm.data")
+    t_data.IMAGENET_DEFAULT_MEAN = (0.485, 0.456, 0.406)
+    t_data.IMAGENET_DEFAULT_STD = (0.229, 0.224, 0.225)
+    t_resnet = types.ModuleType("timm.models.resnet")
+    t_resnet.resnet26d = t_resnet.resnet50d = None
+    t_registry = types.ModuleType("timm.models.registry")
+    t_registry.register_model = lambda f: f
+    timm.models, timm.data = t_models, t_data
+    t_models.layers, t_models.resnet, t_models.registry = t_layers, t_resnet, t_registry
+    sys.modules.update({"timm": timm, "timm.models": t_models, "timm.models.layers": t_layers, "timm.data": t_data,
+                        "timm.models.resnet": t_resnet, "timm.models.registry": t_registry})
+
+
+def build_reference_motionformer(seed=7):
+    """The reference's own MotionFormer in the shipped configuration
+    (configs/modules/feature_extractors/avclip_vggsound.yaml: extract_features, factorize_space_time,
+    agg_space_module TransformerEncoderLayer, agg_time_module Identity, no global representation) with the synthetic
+    weights of vaura_b200.synthetic.make_motionformer_state_dict."""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from vaura_b200.synthetic import make_motionformer_state_dict
+
+    install_motionformer_stubs()
+    from models.modules.feature_extractors.avclip.motionformer import MotionFormer  # reference code
+
+    m = MotionFormer(extract_features=True, ckpt_path=None, factorize_space_time=True,
+                     agg_space_module="TransformerEncoderLayer", agg_time_module="torch.nn.Identity",
+                     add_global_repr=False)
+    sd = make_motionformer_state_dict(seed)
+    own = m.state_dict()
+    missing = [k for k in own if k not in sd]
+    unexpected = [k for k in sd if k not in own]
+    assert not unexpected, unexpected
+    # keys the path never reads (2-D patch_embed, classification head leftovers) may stay at their init
+    assert all(k.startswith(("patch_embed.", "pre_logits", "head")) for k in missing), missing
+    m.load_state_dict(sd, strict=False)
+    return m.eval()

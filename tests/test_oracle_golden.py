@@ -121,3 +121,19 @@ def test_full_size_greedy_matches_reference():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     oracle = vo.SamplerOracle(make_sampler_state_dict(FULL_SAMPLER, 0), FULL_SAMPLER)
     _check_greedy(g, oracle, FULL_CODEC, 2e-5)
+
+
+def test_motionformer_oracle_matches_reference_golden():
+    """the restated Segment-AVCLIP tower against features the reference's own MotionFormer produced
+    (oracle/make_golden_motionformer.py) on the same seeded weights and video segments."""
+    from oracle import motionformer_oracle as mo
+    from vaura_b200.synthetic import FULL_AVCLIP, make_motionformer_state_dict, make_video_segments
+
+    g = np.load(os.path.join(GOLD, "motionformer_full.npz"))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    frames = make_video_segments(int(g["batch"]), int(g["frame_seed"]), int(g["segments"]))
+    mine = mo.motionformer_features(frames, make_motionformer_state_dict(int(g["weight_seed"])), FULL_AVCLIP)
+    ref = torch.from_numpy(g["features"])
+    assert mine.shape == ref.shape == (1, 2, 8, 768)
+    err = float((mine - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, err

@@ -205,6 +205,104 @@ def make_checkpoint_state_dict(sdims: SamplerDims = FULL_SAMPLER, cdims: CodecDi
     return sd
 
 
+@dataclass(frozen=True)
+class AvclipDims:
+    """Segment-AVCLIP visual tower = MotionFormer `divided_224_16x4` (motionformer_src/divided_224_16x4.yaml: ViT-B/16,
+    2-frame tubelets, divided space-time attention) + one spatial aggregation layer (motionformer.py:166-185)."""
+    embed_dim: int = 768
+    depth: int = 12
+    num_heads: int = 12
+    mlp_ratio: int = 4
+    img_size: int = 224
+    patch_size: int = 16
+    in_chans: int = 3
+    frames: int = 16          # frames per segment
+    tubelet: int = 2          # PATCH_SIZE_TEMP
+
+    @property
+    def grid(self) -> int:
+        return self.img_size // self.patch_size
+
+    @property
+    def temporal(self) -> int:  # TEMPORAL_RESOLUTION
+        return self.frames // self.tubelet
+
+    @property
+    def patches_per_frame(self) -> int:
+        return self.grid * self.grid
+
+    @property
+    def tokens(self) -> int:  # CLS + t * h * w
+        return 1 + self.temporal * self.patches_per_frame
+
+    @property
+    def patch_k(self) -> int:
+        return self.in_chans * self.tubelet * self.patch_size * self.patch_size
+
+
+FULL_AVCLIP = AvclipDims()
+TINY_AVCLIP = AvclipDims(embed_dim=128, depth=2, num_heads=2, img_size=64, frames=8)
+
+
+def make_motionformer_state_dict(seed: int = 7, dims: AvclipDims = FULL_AVCLIP) -> Dict[str, torch.Tensor]:
+    """State dict with the reference's parameter names (video_model_builder.py:44-123, vit_helper.py:80-171, :392-472,
+    motionformer.py:166-185).  Matrices are bf16-representable (the GPU path stores them as bf16); the scales keep every
+    sub-layer's output at O(1) so that attention is neither uniform nor one-hot."""
+    sd: Dict[str, torch.Tensor] = {}
+    D, H = dims.embed_dim, dims.mlp_ratio * dims.embed_dim
+
+    def mat(key, shape, fan_in, gain=1.0):
+        sd[key] = _bf16r(_randn(seed, key, shape, gain / fan_in ** 0.5))
+
+    def vec(key, n, std=0.05, mean=0.0):
+        sd[key] = mean + _randn(seed, key, (n,), std)
+
+    sd["cls_token"] = _randn(seed, "cls_token", (1, 1, D), 0.5)
+    sd["pos_embed"] = _randn(seed, "pos_embed", (1, dims.patches_per_frame + 1, D), 0.2)
+    sd["temp_embed"] = _randn(seed, "temp_embed", (1, dims.temporal, D), 0.2)
+    mat("patch_embed_3d.proj.weight", (D, dims.in_chans, dims.tubelet, dims.patch_size, dims.patch_size), dims.patch_k)
+    vec("patch_embed_3d.proj.bias", D)
+    for i in range(dims.depth):
+        p = f"blocks.{i}"
+        for n in ("norm1", "norm2", "norm3"):
+            vec(f"{p}.{n}.weight", D, 0.1, 1.0)
+            vec(f"{p}.{n}.bias", D)
+        for a in ("attn", "timeattn"):
+            mat(f"{p}.{a}.qkv.weight", (3 * D, D), D)
+            vec(f"{p}.{a}.qkv.bias", 3 * D)
+            mat(f"{p}.{a}.proj.weight", (D, D), D, 0.5)
+            vec(f"{p}.{a}.proj.bias", D)
+        mat(f"{p}.mlp.fc1.weight", (H, D), D)
+        vec(f"{p}.mlp.fc1.bias", H)
+        mat(f"{p}.mlp.fc2.weight", (D, H), H, 0.5)
+        vec(f"{p}.mlp.fc2.bias", D)
+    vec("norm.weight", D, 0.1, 1.0)
+    vec("norm.bias", D)
+    p = "spatial_attn_agg"
+    sd[f"{p}.cls_token"] = _randn(seed, f"{p}.cls_token", (1, 1, D), 0.5)
+    mat(f"{p}.self_attn.in_proj_weight", (3 * D, D), D)
+    vec(f"{p}.self_attn.in_proj_bias", 3 * D)
+    mat(f"{p}.self_attn.out_proj.weight", (D, D), D, 0.5)
+    vec(f"{p}.self_attn.out_proj.bias", D)
+    mat(f"{p}.linear1.weight", (H, D), D)
+    vec(f"{p}.linear1.bias", H)
+    mat(f"{p}.linear2.weight", (D, H), H, 0.5)
+    vec(f"{p}.linear2.bias", D)
+    for n in ("norm1", "norm2"):
+        vec(f"{p}.{n}.weight", D, 0.1, 1.0)
+        vec(f"{p}.{n}.bias", D)
+    return sd
+
+
+def make_video_segments(batch: int, seed: int, segments: int = 4, dims: AvclipDims = FULL_AVCLIP) -> torch.Tensor:
+    """Synthetic normalised RGB segments ``(B, S, C, T, H, W)`` (the extractor's input, motionformer.py:252-264);
+    clip ``b`` only depends on ``(seed, b)``."""
+    return torch.stack([
+        _randn(seed, f"frames.{b}", (segments, dims.in_chans, dims.frames, dims.img_size, dims.img_size))
+        for b in range(batch)
+    ])
+
+
 def make_avclip_features(batch: int, seed: int, segments: int = 4, tokens_per_segment: int = 8,
                          width: int = 768) -> torch.Tensor:
     """Synthetic Segment-AVCLIP output ``(B, S, t, D)`` as MotionFormer returns it
