@@ -210,6 +210,43 @@ size_t vaura_codec_workspace_bytes(const vaura_codec* c, int32_t batch, int32_t 
 int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t batch, int32_t frames, uint16_t* wav_out,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Segment-AVCLIP visual features, replaces MotionFormer.forward in the shipped configuration
+ *      (models/modules/feature_extractors/avclip/motionformer.py:252-342; extract_features, factorize_space_time,
+ *      agg_space_module = TransformerEncoderLayer, agg_time_module = Identity, add_global_repr = False;
+ *      motionformer_src/divided_224_16x4.yaml) ---------------------------------------------------------------- */
+typedef struct vaura_avclip vaura_avclip;     /* opaque: video segments -> per-frame features */
+typedef struct {
+  int32_t embed_dim;   /* 768 */
+  int32_t depth;       /* 12 */
+  int32_t num_heads;   /* 12 (head width must be 64) */
+  int32_t mlp_ratio;   /* 4 */
+  int32_t img_size;    /* 224 */
+  int32_t patch_size;  /* 16 */
+  int32_t in_chans;    /* 3 */
+  int32_t frames;      /* 16 frames per segment */
+  int32_t tubelet;     /* 2 (VIT.PATCH_SIZE_TEMP) */
+} vaura_avclip_dims;
+
+/* bf16 matrices [out][in], fp32 vectors; `blob` is one device allocation indexed by the host offsets table.  Slot order
+ * (vaura_b200/weights.py:pack_avclip): 0 tubelet W [D][C*2*16*16]  1 tubelet bias  2 position table f32 [t*n][D]
+ * (pos_embed[1 + patch] + temp_embed[frame])  3 CLS row f32 [D] (cls_token + pos_embed[0]);
+ * per block i (base 4 + 18 i): norm3 w,b | timeattn qkv W,b | timeattn proj W,b | norm1 w,b | attn qkv W,b | attn proj W,b |
+ * norm2 w,b | fc1 W,b | fc2 W,b;  tail (base 4 + 18 depth): norm w,b | agg cls_token | agg norm1 w,b | in_proj W,b |
+ * out_proj W,b | agg norm2 w,b | linear1 W,b | linear2 W,b.                                                         */
+typedef struct {
+  const void* blob;
+  const int64_t* offsets;
+  int32_t n_offsets;
+} vaura_avclip_weights;
+
+int vaura_avclip_create(const vaura_avclip_dims* dims, const vaura_avclip_weights* w, vaura_avclip** out);
+void vaura_avclip_destroy(vaura_avclip* a);
+/* workspace for processing `segments` segments at a time (forward walks its input in chunks that fit) */
+size_t vaura_avclip_workspace_bytes(const vaura_avclip* a, int32_t segments);
+/* frames [segments][C][T][H][W] f32 (normalised RGB) -> features [segments][T / tubelet][D] f32 */
+int vaura_avclip_forward(vaura_avclip* a, const float* frames, int32_t segments, float* features_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ EXPORTS = [
     "vaura_sampler_create", "vaura_sampler_destroy", "vaura_sampler_cond_project",
     "vaura_sampler_workspace_bytes", "vaura_sampler_generate", "vaura_sampler_forward", "vaura_sample_logits",
     "vaura_codec_create", "vaura_codec_destroy", "vaura_codec_workspace_bytes", "vaura_codec_decode",
+    "vaura_avclip_create", "vaura_avclip_destroy", "vaura_avclip_workspace_bytes", "vaura_avclip_forward",
 ]
 
 PRECISION_AUTO, PRECISION_FP32ACT, PRECISION_BF16 = 0, 1, 2
@@ -54,6 +55,13 @@ class CodecWeightsC(C.Structure):
     _fields_ = [("blob", C.c_void_p), ("offsets", C.POINTER(C.c_int64)), ("n_offsets", C.c_int32)]
 
 
+class AvclipDimsC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("embed_dim", "depth", "num_heads", "mlp_ratio", "img_size", "patch_size",
+                                         "in_chans", "frames", "tubelet")]
+
+
+AvclipWeightsC = CodecWeightsC  # same layout: blob + host offsets table
+
 _lib = None
 
 
@@ -94,6 +102,12 @@ def load():
     lib.vaura_codec_workspace_bytes.restype = C.c_size_t
     lib.vaura_codec_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_size_t, C.c_void_p]
+    lib.vaura_avclip_create.argtypes = [C.POINTER(AvclipDimsC), C.POINTER(AvclipWeightsC), C.POINTER(C.c_void_p)]
+    lib.vaura_avclip_destroy.argtypes = [C.c_void_p]
+    lib.vaura_avclip_destroy.restype = None
+    lib.vaura_avclip_workspace_bytes.argtypes = [C.c_void_p, C.c_int32]
+    lib.vaura_avclip_workspace_bytes.restype = C.c_size_t
+    lib.vaura_avclip_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here = the .so is stale w.r.t. the header
     _lib = lib

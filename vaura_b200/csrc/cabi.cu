@@ -833,3 +833,147 @@ extern "C" int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t 
   CUL(launch_conv_out_tanh(act_in, F(tail + 1), F(tail + 2), (__half*)wav_out, B, t, d.decoder_dim >> d.n_blocks, st));
   return VAURA_OK;
 }
+
+// ---- Segment-AVCLIP visual tower (avclip.cu) ------------------------------------------------------------
+struct vaura_avclip {
+  vaura_avclip_dims d;
+  const char* blob;
+  std::vector<int64_t> off;
+};
+
+struct AvclipWs {
+  float* x;
+  __nv_bfloat16 *xn, *qkv, *att, *hid, *acls, *xn2, *hid2;
+  size_t bytes;
+};
+
+static AvclipWs avclip_carve(const vaura_avclip_dims& d, int S, void* base) {
+  AvclipWs w;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(n);
+    return r;
+  };
+  const size_t D = d.embed_dim, t = d.frames / d.tubelet, g = d.img_size / d.patch_size, n = g * g, T = 1 + t * n;
+  const size_t rows = (size_t)S * t * (n + 1);  // >= S * T: the aggregation sequences have one CLS row per frame
+  const size_t Kp = (size_t)d.in_chans * d.tubelet * d.patch_size * d.patch_size;
+  size_t hid = (size_t)S * T * d.mlp_ratio * D;
+  if ((size_t)S * t * n * Kp > hid) hid = (size_t)S * t * n * Kp;
+  w.x = (float*)take((size_t)S * T * D * 4);
+  w.xn = (__nv_bfloat16*)take(rows * D * 2);
+  w.qkv = (__nv_bfloat16*)take(rows * 3 * D * 2);
+  w.att = (__nv_bfloat16*)take((size_t)S * T * D * 2);
+  w.hid = (__nv_bfloat16*)take(hid * 2);
+  w.acls = (__nv_bfloat16*)take((size_t)S * t * D * 2);
+  w.xn2 = (__nv_bfloat16*)take((size_t)S * t * D * 2);
+  w.hid2 = (__nv_bfloat16*)take((size_t)S * t * d.mlp_ratio * D * 2);
+  w.bytes = off;
+  return w;
+}
+
+extern "C" int vaura_avclip_create(const vaura_avclip_dims* dims, const vaura_avclip_weights* w, vaura_avclip** out) {
+  if (!dims || !w || !out || !w->blob || !w->offsets) return fail(VAURA_ERR_INVALID, "null argument");
+  const vaura_avclip_dims& d = *dims;
+  if (d.depth < 1 || d.num_heads < 1 || d.embed_dim != d.num_heads * 64)
+    return fail(VAURA_ERR_UNSUPPORTED, "head width %d unsupported (kernels are built for 64)", d.num_heads ? d.embed_dim / d.num_heads : 0);
+  if (d.embed_dim % 128 || d.embed_dim > 1024 || (d.embed_dim != 256 && d.embed_dim != 512 && d.embed_dim != 768 && d.embed_dim != 1024))
+    return fail(VAURA_ERR_UNSUPPORTED, "embed_dim %d unsupported (256, 512, 768, 1024)", d.embed_dim);
+  if (d.tubelet < 1 || d.frames % d.tubelet || d.frames / d.tubelet != 8)
+    return fail(VAURA_ERR_UNSUPPORTED, "frames / tubelet must be 8 (TEMPORAL_RESOLUTION of divided_224_16x4)");
+  if (d.patch_size % 8 || d.img_size % d.patch_size || (d.in_chans * d.tubelet * d.patch_size * d.patch_size) % 64)
+    return fail(VAURA_ERR_UNSUPPORTED, "patch geometry unsupported");
+  const int g = d.img_size / d.patch_size;
+  if (g * g + 1 > 1024) return fail(VAURA_ERR_UNSUPPORTED, "more than 1023 patches per frame");
+  if (d.mlp_ratio < 1) return fail(VAURA_ERR_INVALID, "mlp_ratio");
+  const int want = 4 + 18 * d.depth + 15;
+  if (w->n_offsets != want) return fail(VAURA_ERR_INVALID, "avclip blob has %d slots, expected %d", w->n_offsets, want);
+  vaura_avclip* a = new (std::nothrow) vaura_avclip();
+  if (!a) return fail(VAURA_ERR_INVALID, "out of host memory");
+  a->d = d;
+  a->blob = (const char*)w->blob;
+  a->off.assign(w->offsets, w->offsets + w->n_offsets);
+  *out = a;
+  return VAURA_OK;
+}
+
+extern "C" void vaura_avclip_destroy(vaura_avclip* a) { delete a; }
+
+extern "C" size_t vaura_avclip_workspace_bytes(const vaura_avclip* a, int32_t segments) {
+  if (!a || segments <= 0) return 0;
+  return avclip_carve(a->d, segments, nullptr).bytes;
+}
+
+static int avclip_chunk(const vaura_avclip* a, const float* frames, int S, float* feats, const AvclipWs& ws, cudaStream_t st) {
+  const vaura_avclip_dims& d = a->d;
+  const int D = d.embed_dim, H = d.num_heads, t = d.frames / d.tubelet, g = d.img_size / d.patch_size, n = g * g, T = 1 + t * n;
+  const int Kp = d.in_chans * d.tubelet * d.patch_size * d.patch_size, F = d.mlp_ratio * D;
+  const float eps = 1e-6f;  // partial(nn.LayerNorm, eps=1e-6) (video_model_builder.py:41), layer_norm_eps=1e-6 (motionformer.py:176)
+  auto W = [&](int slot) { return (const void*)(a->blob + a->off[slot]); };
+  auto V = [&](int slot) { return (const float*)(a->blob + a->off[slot]); };
+  auto linear = [&](const void* A, int lda, int M, int K, int wslot, int N, int mode, int gelu, void* out_bf16, float* out_f32,
+                    int ldo) -> int {
+    VitLinearArgs l{};
+    l.A = A; l.lda = lda; l.M = M; l.K = K; l.W = W(wslot); l.bias = V(wslot + 1); l.N = N; l.mode = mode; l.gelu = gelu;
+    l.out_bf16 = out_bf16; l.out_f32 = out_f32; l.ldo = ldo;
+    CUL(launch_vit_linear(l, st));
+    return VAURA_OK;
+  };
+  int rc;
+  // tubelet embedding + position embeddings (video_model_builder.py:185, :213-245)
+  CUL(launch_vit_patchify(frames, ws.hid, S, d.in_chans, d.frames, d.img_size, d.img_size, d.tubelet, d.patch_size, st));
+  {
+    VitLinearArgs l{};
+    l.A = ws.hid; l.lda = Kp; l.M = S * t * n; l.K = Kp; l.W = W(0); l.bias = V(1); l.N = D; l.mode = VIT_PATCH;
+    l.out_f32 = ws.x; l.ldo = D; l.pos = V(2); l.rows_in = t * n; l.rows_out = T; l.row_off = 1;
+    CUL(launch_vit_linear(l, st));
+  }
+  CUL(launch_vit_broadcast_row(ws.x, V(3), D, S, (size_t)T, st));
+  for (int i = 0; i < d.depth; ++i) {  // DividedSpaceTimeBlock.forward (vit_helper.py:443-472)
+    const int b = 4 + 18 * i;
+    CUL(launch_vit_layernorm(ws.x, V(b), V(b + 1), ws.xn, S * T, D, eps, st));
+    if ((rc = linear(ws.xn, D, S * T, D, b + 2, 3 * D, VIT_STORE_BF16, 0, ws.qkv, nullptr, 3 * D))) return rc;
+    CUL(launch_vit_time_attn(ws.qkv, ws.att, S, t, n, H, st));
+    CUL(launch_vit_cls_attn(ws.qkv, ws.att, S, T, H, T, st));
+    if ((rc = linear(ws.att, D, S * T, D, b + 4, D, VIT_RESID_F32, 0, nullptr, ws.x, D))) return rc;
+    CUL(launch_vit_layernorm(ws.x, V(b + 6), V(b + 7), ws.xn, S * T, D, eps, st));
+    if ((rc = linear(ws.xn, D, S * T, D, b + 8, 3 * D, VIT_STORE_BF16, 0, ws.qkv, nullptr, 3 * D))) return rc;
+    CUL(launch_vit_space_attn(ws.qkv, ws.att, S, t, n, H, st));
+    CUL(launch_vit_cls_attn(ws.qkv, ws.att, S, T, H, T, st));
+    if ((rc = linear(ws.att, D, S * T, D, b + 10, D, VIT_RESID_F32, 0, nullptr, ws.x, D))) return rc;
+    CUL(launch_vit_layernorm(ws.x, V(b + 12), V(b + 13), ws.xn, S * T, D, eps, st));
+    if ((rc = linear(ws.xn, D, S * T, D, b + 14, F, VIT_STORE_BF16, 1, ws.hid, nullptr, F))) return rc;
+    if ((rc = linear(ws.hid, F, S * T, F, b + 16, D, VIT_RESID_F32, 0, nullptr, ws.x, D))) return rc;
+  }
+  // feature head (motionformer.py:309-342): final norm on the patch tokens, one aggregation sequence per frame
+  const int tb = 4 + 18 * d.depth;
+  CUL(launch_vit_final_norm_agg(ws.x, V(tb + 2), V(tb), V(tb + 1), V(tb + 3), V(tb + 4), ws.xn, S, t, n, D, eps, st));
+  if ((rc = linear(ws.xn, D, S * t * (n + 1), D, tb + 5, 3 * D, VIT_STORE_BF16, 0, ws.qkv, nullptr, 3 * D))) return rc;
+  CUL(launch_vit_cls_attn(ws.qkv, ws.acls, S * t, n + 1, H, 1, st));
+  CUL(launch_vit_broadcast_row(feats, V(tb + 2), D, S * t, 1, st));  // residual of the CLS row = the CLS token itself
+  if ((rc = linear(ws.acls, D, S * t, D, tb + 7, D, VIT_RESID_F32, 0, nullptr, feats, D))) return rc;
+  CUL(launch_vit_layernorm(feats, V(tb + 9), V(tb + 10), ws.xn2, S * t, D, eps, st));
+  if ((rc = linear(ws.xn2, D, S * t, D, tb + 11, F, VIT_STORE_BF16, 1, ws.hid2, nullptr, F))) return rc;
+  if ((rc = linear(ws.hid2, F, S * t, F, tb + 13, D, VIT_RESID_F32, 0, nullptr, feats, D))) return rc;
+  return VAURA_OK;
+}
+
+extern "C" int vaura_avclip_forward(vaura_avclip* a, const float* frames, int32_t segments, float* features_out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  if (!a || !frames || !features_out || !workspace || segments <= 0) return fail(VAURA_ERR_INVALID, "bad argument");
+  const vaura_avclip_dims& d = a->d;
+  int chunk = segments;
+  while (chunk > 1 && avclip_carve(d, chunk, nullptr).bytes > workspace_bytes) chunk = (chunk + 1) / 2;
+  if (avclip_carve(d, chunk, nullptr).bytes > workspace_bytes)
+    return fail(VAURA_ERR_WORKSPACE, "workspace %zu < %zu bytes (one segment)", workspace_bytes, avclip_carve(d, 1, nullptr).bytes);
+  const AvclipWs ws = avclip_carve(d, chunk, workspace);
+  const size_t seg_in = (size_t)d.in_chans * d.frames * d.img_size * d.img_size;
+  const size_t seg_out = (size_t)(d.frames / d.tubelet) * d.embed_dim;
+  for (int s0 = 0; s0 < segments; s0 += chunk) {
+    const int ns = segments - s0 < chunk ? segments - s0 : chunk;
+    int rc = avclip_chunk(a, frames + (size_t)s0 * seg_in, ns, features_out + (size_t)s0 * seg_out, ws, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return VAURA_OK;
+}

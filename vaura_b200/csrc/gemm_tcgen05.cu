@@ -428,6 +428,62 @@ struct EpiLinear {
   }
 };
 
+// ---- linear-layer epilogues of the Segment-AVCLIP visual tower (avclip.cu; motionformer_src/vit_helper.py) -------------
+struct EpiVit {
+  struct Params {
+    int mode;                  // VIT_STORE_BF16 / VIT_RESID_F32 / VIT_PATCH (kernels.h)
+    int gelu;                  // VIT_STORE_BF16: exact (erf) GELU after the bias (nn.GELU(), vit_helper.py:486)
+    int M, N, ldo;
+    const float* bias;         // [N]
+    __nv_bfloat16* out_bf16;   // VIT_STORE_BF16: [M][ldo]
+    float* out_f32;            // VIT_RESID_F32: residual stream, updated in place [M][ldo]; VIT_PATCH: token rows
+    const float* pos;          // VIT_PATCH: [rows_in][N] position table added to the embedded tubelets
+    int rows_in, rows_out, row_off;  // VIT_PATCH: GEMM row m -> token row (m / rows_in) * rows_out + row_off + m % rows_in
+  };
+  __device__ static void load_residual(const Params&, int, int, int, int, uint4&, uint4&) {}
+  __device__ static void apply(const Params& p, int b, int phase, int m, int n0, float (&v)[16], const uint4&, const uint4&) {
+    apply(p, b, phase, m, n0, v);
+  }
+  __device__ static void apply(const Params& p, int /*b*/, int /*phase*/, int m, int n0, float (&v)[16]) {
+    if (m >= p.M || n0 >= p.N) return;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + i);
+      v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+    }
+    if (p.mode == VIT_STORE_BF16) {
+      if (p.gelu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+      }
+      uint4 o[2];
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      __nv_bfloat16* dst = p.out_bf16 + (size_t)m * p.ldo + n0;
+      *reinterpret_cast<uint4*>(dst) = o[0];
+      *reinterpret_cast<uint4*>(dst + 8) = o[1];
+    } else if (p.mode == VIT_RESID_F32) {
+      float* o = p.out_f32 + (size_t)m * p.ldo + n0;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        float4 h = *reinterpret_cast<float4*>(o + i);
+        h.x += v[i]; h.y += v[i + 1]; h.z += v[i + 2]; h.w += v[i + 3];
+        *reinterpret_cast<float4*>(o + i) = h;
+      }
+    } else {  // VIT_PATCH
+      const int seg = m / p.rows_in, tok = m % p.rows_in;
+      const float* ps = p.pos + (size_t)tok * p.N + n0;
+      float* o = p.out_f32 + ((size_t)seg * p.rows_out + p.row_off + tok) * p.ldo + n0;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(ps + i);
+        *reinterpret_cast<float4*>(o + i) = make_float4(v[i] + q.x, v[i + 1] + q.y, v[i + 2] + q.z, v[i + 3] + q.w);
+      }
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -1647,6 +1703,27 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st) {
     case 128: return launch_tc<128, 64, 6, 1, EpiLinear>(ta, tb, g, ep, mt, nt, st);
   }
   return cudaErrorInvalidValue;
+}
+
+// Linear layer of the Segment-AVCLIP tower: out = A[M][K] (bf16) x W[N][K]^T (bf16) + bias, epilogue per VitLinearArgs::mode.
+// Persistent tile loop with a double-buffered TMEM accumulator (gemm_tc_persistent_kernel): M is 10^4..10^6 token rows, so
+// the epilogue of one 128 x BLOCK_N tile overlaps the mainloop of the next.
+cudaError_t launch_vit_linear(const VitLinearArgs& a, cudaStream_t st) {
+  if (a.K % 64 != 0 || a.M <= 0) return cudaErrorInvalidValue;
+  const int bn = a.N % 256 == 0 ? 256 : (a.N % 128 == 0 ? 128 : 0);
+  if (!bn) return cudaErrorInvalidValue;
+  CUtensorMap ta, tb;
+  if (!make_map(&ta, a.A, a.K, a.M, 1, a.lda, (uint64_t)a.M * a.lda, 64, kTileM, false)) return cudaErrorUnknown;
+  if (!make_map(&tb, a.W, a.K, a.N, 1, a.K, (uint64_t)a.N * a.K, 64, bn, false)) return cudaErrorUnknown;
+  TcShape g{};
+  g.ntaps = 1; g.nphase = 1; g.kblocks = a.K / 64; g.batch = 1; g.ksplit = 1; g.pdl = 0;
+  EpiVit::Params ep{};
+  ep.mode = a.mode; ep.gelu = a.gelu; ep.M = a.M; ep.N = a.N; ep.ldo = a.ldo; ep.bias = a.bias;
+  ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16); ep.out_f32 = a.out_f32; ep.pos = a.pos;
+  ep.rows_in = a.rows_in; ep.rows_out = a.rows_out; ep.row_off = a.row_off;
+  const int mt = (a.M + kTileM - 1) / kTileM, nt = a.N / bn;
+  if (bn == 256) return launch_tc_persistent<256, 64, 4, 1, EpiVit>(ta, tb, g, ep, mt, nt, st);
+  return launch_tc_persistent<128, 64, 6, 1, EpiVit>(ta, tb, g, ep, mt, nt, st);
 }
 
 }  // namespace vaura

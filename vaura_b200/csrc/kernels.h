@@ -179,6 +179,29 @@ cudaError_t launch_decode_fused2(const Fused2Args& a, const void* wqkv, const vo
 bool tc_make_map_kblocks(void* map, const void* base, uint64_t K, uint64_t rows, uint64_t outer, uint64_t row_stride_el,
                          uint64_t outer_stride_el, int box_rows, int nblk);
 
+// ---- Segment-AVCLIP visual tower (avclip.cu) ----------------------------------------------------------------------------
+enum { VIT_STORE_BF16 = 0, VIT_RESID_F32 = 1, VIT_PATCH = 2 };
+struct VitLinearArgs {
+  const void* A;       // bf16 [M][lda]
+  const void* W;       // bf16 [N][K]
+  const float* bias;   // [N]
+  void* out_bf16;      // VIT_STORE_BF16
+  float* out_f32;      // VIT_RESID_F32 (in place) / VIT_PATCH
+  const float* pos;    // VIT_PATCH
+  int M, N, K, lda, ldo, mode, gelu;
+  int rows_in, rows_out, row_off;
+};
+cudaError_t launch_vit_linear(const VitLinearArgs& a, cudaStream_t st);
+cudaError_t launch_vit_patchify(const float* frames, void* A, int S, int C, int T, int H, int W, int tub, int ps, cudaStream_t st);
+cudaError_t launch_vit_broadcast_row(float* dst, const float* src, int D, int count, size_t row_stride, cudaStream_t st);
+cudaError_t launch_vit_layernorm(const float* x, const float* g, const float* b, void* out_bf16, int rows, int D, float eps,
+                                 cudaStream_t st);
+cudaError_t launch_vit_final_norm_agg(const float* x, const float* agg_cls, const float* gf, const float* bf, const float* g1,
+                                      const float* b1, void* out_bf16, int S, int t, int n, int D, float eps, cudaStream_t st);
+cudaError_t launch_vit_time_attn(const void* qkv, void* out, int S, int t, int n, int heads, cudaStream_t st);
+cudaError_t launch_vit_cls_attn(const void* qkv, void* out, int seqs, int len, int heads, int out_rows_per_seq, cudaStream_t st);
+cudaError_t launch_vit_space_attn(const void* qkv, void* out, int S, int t, int n, int heads, cudaStream_t st);
+
 bool conv_tc_supported(int Cin, int Cout, int ntaps, int nphase);
 cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cudaStream_t st);
 cudaError_t init_decode_kernels();

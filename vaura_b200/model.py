@@ -85,7 +85,14 @@ class VAURAModel(torch.nn.Module):
             raise KeyError("state dict lacks `sampler.*` or `audio_encoder.model.*` entries")
         self.sampler.load_state_dict(parts["sampler"], device=device)
         self.audio_encoder.load_state_dict(parts["codec"], device=device)
+        self._load_feature_extractor(parts["feature_extractor"], device)
         return self
+
+    def _load_feature_extractor(self, sd, device):
+        """`visual_feature_extractor.*` entries of the checkpoint (the Segment-AVCLIP tower, vaura_model.py:64-75).  A
+        checkpoint without them leaves the extractor in pass-through mode (precomputed features only)."""
+        if sd and self.using_avclip and any(k.startswith("blocks.") for k in sd):
+            self.visual_feature_extractor.load_state_dict(sd, device=device)
 
     @classmethod
     def load_from_checkpoint(cls, checkpoint_path, hparams_file=None, map_location=None, **overrides):
@@ -104,6 +111,7 @@ class VAURAModel(torch.nn.Module):
             device = torch.device(map_location)
         model.sampler.load_state_dict(parts["sampler"], device=device)
         model.audio_encoder.load_state_dict(parts["codec"], device=device)
+        model._load_feature_extractor(parts["feature_extractor"], device)
         return model
 
     # ---- generation --------------------------------------------------------------------------------

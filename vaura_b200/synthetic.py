@@ -321,7 +321,10 @@ def build_model(sdims: SamplerDims = FULL_SAMPLER, cdims: CodecDims = FULL_CODEC
     cfg = dict(
         use_visual_conditioning=True,
         feature_extractor_config={"target": "models.modules.feature_extractors.avclip.motionformer.MotionFormer",
-                                  "params": {}},
+                                  # configs/modules/feature_extractors/avclip_vggsound.yaml (ckpt comes with the model)
+                                  "params": dict(extract_features=True, factorize_space_time=True,
+                                                 agg_space_module="TransformerEncoderLayer",
+                                                 agg_time_module="torch.nn.Identity", add_global_repr=False)},
         audio_encoder_config={"target": "models.modules.dac.model.DacModelWrapper",
                               "params": {"model_sr": 44100, "dims": cdims}},
         sampler_config={"target": "models.modules.sampler.llama.Transformer",

@@ -290,6 +290,65 @@ def pack_codec(sd: Dict[str, torch.Tensor], dims: CodecDims, device):
     return blob.to(device), offsets
 
 
+def pack_avclip(sd: Dict[str, torch.Tensor], dims, device):
+    """MotionFormer state dict (reference names: video_model_builder.py:44-123, motionformer.py:166-185) ->
+    (blob uint8 device tensor, offsets).  Slot order: include/vaura_b200.h (vaura_avclip_weights).  Matrices are stored as
+    bf16 [out][in]; the tubelet Conv3d weight (D, C, 2, 16, 16) is already the [D][C*2*16*16] GEMM operand."""
+    parts: List[torch.Tensor] = []
+
+    def m(key):
+        parts.append(sd[key].reshape(sd[key].shape[0], -1).to(torch.bfloat16).contiguous())
+
+    def f(t):
+        parts.append(t.reshape(-1).to(torch.float32).contiguous())
+
+    def lin(prefix, wname="weight", bname="bias"):
+        m(f"{prefix}.{wname}" if wname == "weight" else f"{prefix}{wname}")
+        f(sd[f"{prefix}.{bname}" if bname == "bias" else f"{prefix}{bname}"])
+
+    def norm(prefix):
+        f(sd[prefix + ".weight"])
+        f(sd[prefix + ".bias"])
+
+    t, n = dims.temporal, dims.patches_per_frame
+    lin("patch_embed_3d.proj")
+    pos = sd["pos_embed"].float()[0]  # (1 + n, D)
+    # total_pos_embed of video_model_builder.py:238-245 ("separate"): patch position tiled over frames + frame embedding
+    f(pos[1:].repeat(t, 1) + sd["temp_embed"].float()[0].repeat_interleave(n, 0))
+    f(sd["cls_token"].float().reshape(-1) + pos[0])
+    for i in range(dims.depth):
+        p = f"blocks.{i}"
+        norm(f"{p}.norm3"); lin(f"{p}.timeattn.qkv"); lin(f"{p}.timeattn.proj")
+        norm(f"{p}.norm1"); lin(f"{p}.attn.qkv"); lin(f"{p}.attn.proj")
+        norm(f"{p}.norm2"); lin(f"{p}.mlp.fc1"); lin(f"{p}.mlp.fc2")
+    norm("norm")
+    a = "spatial_attn_agg"
+    f(sd[f"{a}.cls_token"])
+    norm(f"{a}.norm1")
+    lin(f"{a}.self_attn.in_proj", "_weight", "_bias")
+    lin(f"{a}.self_attn.out_proj")
+    norm(f"{a}.norm2")
+    lin(f"{a}.linear1")
+    lin(f"{a}.linear2")
+    offsets, cur = [], 0
+    for tns in parts:
+        offsets.append(cur)
+        cur += (tns.numel() * tns.element_size() + 255) // 256 * 256
+    blob = torch.zeros(cur, dtype=torch.uint8)
+    for o, tns in zip(offsets, parts):
+        blob[o:o + tns.numel() * tns.element_size()] = tns.view(-1).view(torch.uint8)
+    return blob.to(device), offsets
+
+
+def avclip_flops(dims, segments: int = 1) -> float:
+    """Dense-contraction FLOPs of the tower for `segments` segments (2 * M * N * K per linear layer, attention included)."""
+    D, T, t, n, F = dims.embed_dim, dims.tokens, dims.temporal, dims.patches_per_frame, dims.mlp_ratio * dims.embed_dim
+    per_block = 2 * T * D * (3 * D) * 2 + 2 * T * D * D * 2 + 2 * T * D * F * 2
+    attn = 2 * 2 * D * (t * n * (t + 1) + t * n * (n + 1) + 2 * T)
+    agg = 2 * t * (n + 1) * D * 3 * D + 2 * 2 * D * t * (n + 1) + 2 * t * (D * D + 2 * D * F)
+    return float(segments) * (2 * t * n * dims.patch_k * D + dims.depth * (per_block + attn) + agg)
+
+
 def codec_flops(dims: CodecDims, frames: int) -> float:
     """2*Cin*Cout*k*Lout per conv (ConvT counted over its input length), SURVEY Appendix A."""
     fl = 2.0 * dims.latent_dim * dims.decoder_dim * 7 * frames
