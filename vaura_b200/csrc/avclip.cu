@@ -11,6 +11,8 @@
 //   qkv  bf16 [S*t*(n+1)][3D]                          att bf16 [S*T][D]        attention output ("b n (h d)")
 //   hid  bf16 [S*T][4D]     GELU(fc1) / tubelet matrix [S*t*n][C*2*16*16]
 // Token order inside a segment: CLS, then (frame, row, column) - PatchEmbed3D flattens (t, h, w) (vit_helper.py:547-552).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -389,6 +391,141 @@ vit_space_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
+// space attention on the tensor cores (mma.sync m16n8k16, bf16 in / fp32 accumulate): same CTA = (head, frame, segment) and the
+// same result as vit_space_attn_kernel up to the bf16 rounding of the probabilities.  K [key][dim] and V^T [dim][key] of the
+// n + 1 keys sit in shared memory (row strides chosen so that the B-fragment reads of a warp hit 32 different banks); a warp
+// owns 16 queries at a time: S = Q K^T for all keys in registers (NKT x 2 accumulator tiles), softmax on the fragments, the
+// probabilities re-used as the A operand of P V (the accumulator layout of two n8 tiles is the A layout of one k16 step).
+// The FLOPs of this phase are 3 % of the tower's; it only has to stay off the critical path (SIMT: 53 % of the tower's time,
+// profiles/r02_avclip_launches.summary.txt).
+// ------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int kSpTcThreads = 128;
+template <int NKT>  // key tiles of 16: (n + 1) <= 16 * NKT
+struct SpTc {
+  static constexpr int NKP = 16 * NKT;           // padded keys
+  static constexpr int KST = 72;                 // K row stride (bf16): 36 words -> bank 4 g + t
+  static constexpr int VST = NKP + 8;            // V^T row stride (bf16): (NKP + 8) / 2 words; 108 for NKT = 13 -> bank 12 g + t
+  static constexpr size_t smem = (size_t)NKP * KST * 2 + (size_t)kVitDh * VST * 2;
+};
+
+template <int NKT>
+__global__ void __launch_bounds__(kSpTcThreads)
+vit_space_attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int t, int n, int heads,
+                         float scale) {
+  using G = SpTc<NKT>;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smraw);       // [NKP][KST]
+  __nv_bfloat16* Vt = Ks + (size_t)G::NKP * G::KST;                  // [64][VST]
+  const int nk = n + 1;
+  const int h = blockIdx.x, f = blockIdx.y, s = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = heads * kVitDh, T = 1 + t * n;
+  const size_t ld = 3 * (size_t)D;
+  const __nv_bfloat16* seg = qkv + (size_t)s * T * ld + h * kVitDh;
+  for (int i = tid; i < G::NKP * 8; i += kSpTcThreads) {
+    const int j = i >> 3, c = i & 7;
+    uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = kk;
+    if (j < nk) {
+      const __nv_bfloat16* src = seg + (size_t)(j == 0 ? 0 : 1 + f * n + (j - 1)) * ld;
+      kk = *reinterpret_cast<const uint4*>(src + D + 8 * c);
+      vv = *reinterpret_cast<const uint4*>(src + 2 * D + 8 * c);
+    }
+    *reinterpret_cast<uint4*>(Ks + (size_t)j * G::KST + 8 * c) = kk;
+    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Vt[(size_t)(8 * c + e) * G::VST + j] = ve[e];
+  }
+  __syncthreads();
+  const int g = lane >> 2, tq = lane & 3;
+  const uint32_t* Kw = reinterpret_cast<const uint32_t*>(Ks);
+  const uint32_t* Vw = reinterpret_cast<const uint32_t*>(Vt);
+  const float sl2 = scale * 1.4426950408889634f;  // exp(x * scale) = exp2(x * scale * log2 e)
+  for (int q0 = 16 * warp; q0 < n; q0 += 16 * (kSpTcThreads / 32)) {
+    // Q fragments of the 16 queries q0 .. q0 + 15 (rows beyond n are clamped: computed, never stored)
+    const int r0 = min(q0 + g, n - 1), r1 = min(q0 + g + 8, n - 1);
+    const uint32_t* qa = reinterpret_cast<const uint32_t*>(seg + (size_t)(1 + f * n + r0) * ld);
+    const uint32_t* qb = reinterpret_cast<const uint32_t*>(seg + (size_t)(1 + f * n + r1) * ld);
+    uint32_t aq[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      aq[ks][0] = __ldg(qa + 8 * ks + tq);
+      aq[ks][1] = __ldg(qb + 8 * ks + tq);
+      aq[ks][2] = __ldg(qa + 8 * ks + 4 + tq);
+      aq[ks][3] = __ldg(qb + 8 * ks + 4 + tq);
+    }
+    float sacc[2 * NKT][4];
+#pragma unroll
+    for (int nt = 0; nt < 2 * NKT; ++nt) {
+      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+      const uint32_t* kr = Kw + (size_t)(8 * nt + g) * (G::KST / 2) + tq;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) mma_bf16_16816(sacc[nt], aq[ks], kr[8 * ks], kr[8 * ks + 4]);
+    }
+    // softmax over the keys of rows g (values 0, 1 of a tile) and g + 8 (values 2, 3); keys >= nk are masked
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NKT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = 8 * nt + 2 * tq + e < nk;
+        if (!ok) { sacc[nt][e] = -INFINITY; sacc[nt][2 + e] = -INFINITY; }
+        m0 = fmaxf(m0, sacc[nt][e]);
+        m1 = fmaxf(m1, sacc[nt][2 + e]);
+      }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+    const float b0 = m0 * sl2, b1 = m1 * sl2;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NKT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sacc[nt][e] = exp2f(fmaf(sacc[nt][e], sl2, -b0));
+        sacc[nt][2 + e] = exp2f(fmaf(sacc[nt][2 + e], sl2, -b1));
+        s0 += sacc[nt][e];
+        s1 += sacc[nt][2 + e];
+      }
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    float oacc[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < NKT; ++kt) {
+      uint32_t ap[4];
+      ap[0] = pack_bf16(sacc[2 * kt][0], sacc[2 * kt][1]);
+      ap[1] = pack_bf16(sacc[2 * kt][2], sacc[2 * kt][3]);
+      ap[2] = pack_bf16(sacc[2 * kt + 1][0], sacc[2 * kt + 1][1]);
+      ap[3] = pack_bf16(sacc[2 * kt + 1][2], sacc[2 * kt + 1][3]);
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        const uint32_t* vr = Vw + (size_t)(8 * dt + g) * (G::VST / 2) + 8 * kt + tq;
+        mma_bf16_16816(oacc[dt], ap, vr[0], vr[4]);
+      }
+    }
+    const float i0 = 1.f / s0, i1 = 1.f / s1;
+    __nv_bfloat16* o0 = out + ((size_t)s * T + 1 + f * n + q0 + g) * D + h * kVitDh + 2 * tq;
+    __nv_bfloat16* o1 = o0 + (size_t)8 * D;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      if (q0 + g < n) *reinterpret_cast<__nv_bfloat162*>(o0 + 8 * dt) = __floats2bfloat162_rn(oacc[dt][0] * i0, oacc[dt][1] * i0);
+      if (q0 + g + 8 < n) *reinterpret_cast<__nv_bfloat162*>(o1 + 8 * dt) = __floats2bfloat162_rn(oacc[dt][2] * i1, oacc[dt][3] * i1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------------------
 cudaError_t launch_vit_patchify(const float* frames, void* A, int S, int C, int T, int H, int W, int tub, int ps, cudaStream_t st) {
@@ -446,6 +583,20 @@ cudaError_t launch_vit_cls_attn(const void* qkv, void* out, int seqs, int len, i
   return cudaGetLastError();
 }
 cudaError_t launch_vit_space_attn(const void* qkv, void* out, int S, int t, int n, int heads, cudaStream_t st) {
+  static int simt = -1;  // VAURA_AVCLIP_SIMT_ATTN=1: the SIMT kernel for every shape
+  if (simt < 0) { const char* e = getenv("VAURA_AVCLIP_SIMT_ATTN"); simt = e && e[0] == '1'; }
+  if (!simt && n + 1 <= 16 * 13 && n + 1 > 16 * 12) {  // 14 x 14 patches + CLS = 197 keys
+    using G = SpTc<13>;
+    static bool attr_tc = false;
+    if (!attr_tc) {
+      cudaError_t e = cudaFuncSetAttribute(vit_space_attn_tc_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
+      if (e != cudaSuccess) return e;
+      attr_tc = true;
+    }
+    vit_space_attn_tc_kernel<13><<<dim3(heads, t, S), kSpTcThreads, G::smem, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), t, n, heads, 0.125f);
+    return cudaGetLastError();
+  }
   const size_t smem = space_attn_smem(n);
   static bool attr = false;
   if (!attr) {
