@@ -15,7 +15,9 @@ e2e = the same through the public API with pinned host inputs and the waveform r
 roofline = the dominant kernel (one launch = one decode step) timed with CUDA events against MEASURED_PEAKS.json;
 cpu_baseline = the oracle port of the reference's algorithm (no KV cache, fp32) run for one whole clip on this box's
 host cores.  At N = 1 the default workload also carries sub-records for the other halves of BASELINE's metric:
-`b1` (one clip, batch 1), `b64_cfg` (128 sequence rows) and `long_b1` (10.24 s clip by overlapping windows, config 3).
+`b1` (one clip, batch 1), `b64_cfg` (128 sequence rows), `long_b1` (10.24 s clip by overlapping windows, config 3) and
+`frames_b64` (config 5 on one GPU: raw video frames -> Segment-AVCLIP tower -> decode -> codec, frames copied from pinned host
+memory inside the timed region, with the tower's own tensor-roofline record).
 
 `--workload dataset` is BASELINE config 4 in miniature: `driver.generate_dataset` over --clips-per-gpu x N clips
 sharded by clip index, ending in the waveform all-gather, all inside the timed region.
@@ -222,7 +224,7 @@ def main():
     ap.add_argument("--workload", default="b64", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-sub", action="store_true", help="skip the b1 / b64_cfg / long_b1 sub-records")
+    ap.add_argument("--no-sub", action="store_true", help="skip the b1 / b64_cfg / long_b1 / frames_b64 sub-records")
     ap.add_argument("--clips-per-gpu", type=int, default=128, help="dataset workload: clips per rank and step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -430,6 +432,48 @@ def main():
                 "prefill_note": "generate() with the window's prompt, stopped after the first sampled column: host glue + "
                                 "the first pass over the prompt columns + one sampling launch"}
 
+    # ---- BASELINE config 5 on one GPU: video frames -> Segment-AVCLIP features -> AR decode -> codec ------------------------
+    def frames_record(steps):
+        from vaura_b200.synthetic import FULL_AVCLIP, make_motionformer_state_dict
+        from vaura_b200.weights import avclip_flops
+        w = WORKLOADS["b64"]
+        nb, segs = w["batch"], 4
+        fx = model.visual_feature_extractor
+        if not fx.has_weights:
+            fx.load_state_dict(make_motionformer_state_dict(7), device=str(dev))
+        gsrc = torch.Generator().manual_seed(5)
+        fr_host = torch.empty(nb, segs, 3, FULL_AVCLIP.frames, FULL_AVCLIP.img_size, FULL_AVCLIP.img_size).pin_memory()
+        fr_host.normal_(generator=gsrc)
+        ids = torch.arange(nb, dtype=torch.int32)
+        wh = torch.empty(nb, 1, w["T"] * 512, dtype=torch.float16).pin_memory()
+        kws = gen_kw(w)
+
+        def e2e_step():
+            f = fr_host.to(dev, non_blocking=True)
+            wv = model.generate(frames=f, clip_indices=ids, **kws)["generated_audio"]
+            wh.copy_(wv, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        e2e_step()
+        ms_s = timed(e2e_step, steps, collective=False) / steps
+        fr_dev = fr_host.to(dev)
+        fx(fr_dev)
+        ms_fx = timed(lambda: fx(fr_dev), steps, collective=False) / steps
+        tf = avclip_flops(FULL_AVCLIP, nb * segs) / 1e12
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1434.4) \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1434.4
+        del fr_dev
+        return {"workload": "64 x 2.56 s clips from raw frames (64 x 4 segments of 16 x 3 x 224 x 224 fp32): Segment-AVCLIP tower "
+                            "-> AR decode (top-k 128) -> codec",
+                "e2e": nb * w["T"] * AUDIO_SEC_PER_TOKEN / (ms_s / 1e3), "unit": "audio-s/s", "ms_per_step": ms_s,
+                "h2d_bytes_per_step": fr_host.numel() * 4, "d2h_bytes_per_step": wh.numel() * 2,
+                "avclip": {"ms_per_256_segments": ms_fx, "segments_per_s": nb * segs / (ms_fx / 1e3),
+                           "roofline": {"kernel": "gemm_tc_persistent_kernel<256,64,4,bf16,EpiVit> (70 % of the tower's time) + "
+                                                  "attention / LayerNorm kernels: whole tower", "bound": "tensor",
+                                        "achieved": tf / (ms_fx / 1e3), "peak": pk, "unit": "TFLOP/s",
+                                        "frac": tf / (ms_fx / 1e3) / pk, "traffic": None,
+                                        "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)",
+                                        "algorithmic_flops": tf * 1e12}}}
+
     if args.workload == "long_b1":
         for _ in range(max(args.warmup, 1)):
             pass
@@ -533,6 +577,7 @@ def main():
             line[name] = {"workload": w["name"], "e2e": w["batch"] * w["T"] * AUDIO_SEC_PER_TOKEN / (ms_s / 1e3),
                           "unit": "audio-s/s", "ms_per_step": ms_s, "roofline": r, "decode_step": s}
         line["long_b1"] = long_clip_record(2)
+        line["frames_b64"] = frames_record(2)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -141,3 +141,18 @@ def generate_dataset(generate_batch: Callable[[torch.Tensor], torch.Tensor], n_i
 
 def _default_device():
     return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+
+
+def save_waveforms(waveforms: torch.Tensor, names, output_dir, audio_norm_strategy: str = "clip", sample_rate: int = 44100,
+                   frames=None, v_fps: float = 25.0) -> list:
+    """The output loop of scripts/generate.py:372-384 for a batch (or the gathered set) of generated clips: normalise on
+    the device the waveforms live on, then one `<name>.wav` (+ mp4 when frames and PyAV are there) per clip.
+    Returns the per-clip dicts of paths written (postprocess.save_results)."""
+    from . import postprocess as pp
+
+    norm = pp.normalize_batch(waveforms, audio_norm_strategy, sample_rate).cpu()
+    out = []
+    for i, name in enumerate(names):
+        out.append(pp.save_results(norm[i], None if frames is None else frames[i], output_dir, str(name), v_fps, sample_rate,
+                                   audio_norm_strategy=audio_norm_strategy, pre_normalized=True))
+    return out
