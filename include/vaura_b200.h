@@ -210,6 +210,23 @@ size_t vaura_codec_workspace_bytes(const vaura_codec* c, int32_t batch, int32_t 
 int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t batch, int32_t frames, uint16_t* wav_out,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- codec encode, replaces DacModelWrapper.encode (models/modules/dac/model.py:30-39: preprocess + dac `encode`,
+ *      codes only).  Same vaura_codec_dims (+ encoder_dim); its own weight blob (vaura_b200/weights.py:pack_codec_encoder):
+ *      0 conv_in W f32 [C0][7]  1 conv_in bias;  per block i (base 2 + 21 i): three residual units (+6 j: alpha1 | conv7 W f16
+ *      [7][C][C] | bias | alpha2 | conv1 W f16 [1][C][C] | bias), +18 block snake alpha, +19 strided conv as three taps over
+ *      frames of `stride` samples W f16 [3][2C][stride*C], +20 bias;  tail (base 2 + 21 n): final snake alpha | conv k3 W f16
+ *      [3][latent][Cn] | bias | in_proj W f32 [Kc][Dc][latent] | in_proj bias [Kc][Dc] | l2-normalised codebooks f32
+ *      [Kc][V][Dc] | out_proj(codebook) tables f32 [Kc][V][latent] | tap-offset tables int32.                          */
+typedef struct vaura_codec_encoder vaura_codec_encoder;
+int vaura_codec_encoder_create(const vaura_codec_dims* dims, int32_t encoder_dim, int32_t codebook_dim,
+                               const vaura_codec_weights* w, vaura_codec_encoder** out);
+void vaura_codec_encoder_destroy(vaura_codec_encoder* c);
+size_t vaura_codec_encoder_workspace_bytes(const vaura_codec_encoder* c, int32_t batch, int32_t samples);
+/* wav [B][samples] f32 (samples a multiple of the hop length: the caller pads, DAC.preprocess) -> codes [B][Kc][samples/hop]
+ * int32; latent_out (optional) [B][samples/hop][latent] f16 = the encoder output before quantisation */
+int vaura_codec_encode(vaura_codec_encoder* c, const float* wav, int32_t batch, int32_t samples, int32_t* codes_out,
+                       uint16_t* latent_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Segment-AVCLIP visual features, replaces MotionFormer.forward in the shipped configuration
  *      (models/modules/feature_extractors/avclip/motionformer.py:252-342; extract_features, factorize_space_time,
  *      agg_space_module = TransformerEncoderLayer, agg_time_module = Identity, add_global_repr = False;

@@ -71,3 +71,78 @@ class DacDecodeOracle:
     def decode(self, codes: torch.Tensor) -> torch.Tensor:
         """codes (B,Kc,T) -> waveform (B,1,hop*T)  (models/modules/dac/model.py:41-48)."""
         return self.decode_latent(self.from_codes(codes).to(self.dtype))
+
+
+class DacEncodeOracle:
+    """CPU restatement of the wav -> codes direction the reference reaches through ``DacModelWrapper.encode``
+    (models/modules/dac/model.py:30-39: ``model.preprocess(wav, sr)``; ``_, codes, _, _, _ = model.encode(wav)``), i.e. of
+    dac 1.0.0's ``DAC.preprocess`` (right-pad to a multiple of the hop length), ``Encoder`` / ``EncoderBlock`` /
+    ``ResidualUnit`` (dac/model/dac.py) and ``ResidualVectorQuantize.forward`` / ``VectorQuantize.decode_latents``
+    (dac/nn/quantize.py: factorised, l2-normalised nearest-neighbour look-up; the residual passed on is
+    ``residual - out_proj(codebook[idx])``).  Cross-checked against ``transformers.DacModel.encode`` (modeling_dac.py:102-171,
+    :210-232, :265-343, :442-473) in tests/test_oracle_golden.py; parity with dac 1.0.0 proper is UNPINNED (see the header)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], cdims, dtype=torch.float32):
+        self.c = cdims
+        self.dtype = dtype
+        self.sd = {k: v.to(dtype) for k, v in sd.items()}
+
+    def _w(self, key):
+        return fold_weight_norm(self.sd[key + ".weight_g"].float(), self.sd[key + ".weight_v"].float()).to(self.dtype)
+
+    def preprocess(self, wav: torch.Tensor) -> torch.Tensor:
+        hop = self.c.hop_length
+        length = wav.shape[-1]
+        right = math.ceil(length / hop) * hop - length
+        return F.pad(wav, (0, right))
+
+    def encode_latent(self, wav: torch.Tensor) -> torch.Tensor:
+        """wav (B,1,L) -> z (B,latent,L/hop)."""
+        sd, c = self.sd, self.c
+        x = F.conv1d(wav, self._w("encoder.block.0"), sd["encoder.block.0.bias"], padding=3)
+        for i, s in enumerate(c.encoder_rates):
+            p = f"encoder.block.{i + 1}.block"
+            for j, dil in enumerate((1, 3, 9)):
+                q = f"{p}.{j}.block"
+                y = snake(x, sd[f"{q}.0.alpha"])
+                y = F.conv1d(y, self._w(f"{q}.1"), sd[f"{q}.1.bias"], dilation=dil, padding=((7 - 1) * dil) // 2)
+                y = snake(y, sd[f"{q}.2.alpha"])
+                y = F.conv1d(y, self._w(f"{q}.3"), sd[f"{q}.3.bias"])
+                x = x + y
+            x = snake(x, sd[f"{p}.3.alpha"])
+            x = F.conv1d(x, self._w(f"{p}.4"), sd[f"{p}.4.bias"], stride=s, padding=math.ceil(s / 2))
+        n = len(c.encoder_rates)
+        x = snake(x, sd[f"encoder.block.{n + 1}.alpha"])
+        return F.conv1d(x, self._w(f"encoder.block.{n + 2}"), sd[f"encoder.block.{n + 2}.bias"], padding=1)
+
+    def quantize(self, z: torch.Tensor, return_margins: bool = False):
+        """z (B,latent,T) -> codes (B,Kc,T) int64 (+ per-cell top-2 similarity gaps when asked)."""
+        sd = self.sd
+        residual = z
+        codes, margins = [], []
+        for k in range(self.c.n_codebooks):
+            p = f"quantizer.quantizers.{k}"
+            e = F.conv1d(residual, self._w(f"{p}.in_proj"), sd[f"{p}.in_proj.bias"])          # (B, 8, T)
+            B, Dc, T = e.shape
+            enc = F.normalize(e.permute(0, 2, 1).reshape(B * T, Dc))
+            cb = F.normalize(sd[f"{p}.codebook.weight"])
+            dist = enc.pow(2).sum(1, keepdim=True) - 2 * enc @ cb.t() + cb.pow(2).sum(1, keepdim=True).t()
+            idx = (-dist).max(1)[1].reshape(B, T)
+            if return_margins:
+                top2 = torch.topk(-dist, 2, dim=1).values
+                margins.append((top2[:, 0] - top2[:, 1]).reshape(B, T))
+            zq = F.embedding(idx, sd[f"{p}.codebook.weight"]).transpose(1, 2)
+            zq = F.conv1d(zq, self._w(f"{p}.out_proj"), sd[f"{p}.out_proj.bias"])
+            residual = residual - zq
+            codes.append(idx)
+        codes = torch.stack(codes, dim=1)
+        return (codes, torch.stack(margins, dim=1)) if return_margins else codes
+
+    @torch.no_grad()
+    def encode(self, wav: torch.Tensor) -> torch.Tensor:
+        """wav (L,) | (C,L) | (B,1,L) -> codes (B,Kc,ceil(L/hop))  (models/modules/dac/model.py:30-39)."""
+        if wav.ndim < 2:
+            wav = wav.unsqueeze(0)
+        if wav.ndim < 3:
+            wav = wav.unsqueeze(0)
+        return self.quantize(self.encode_latent(self.preprocess(wav.to(self.dtype))))

@@ -27,7 +27,7 @@ def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "vaura_model.py"))
 
 
-def _hf_dac(cdims):
+def _hf_dac(cdims, with_encoder=False):
     from transformers import DacConfig, DacModel
 
     cfg = DacConfig(
@@ -39,7 +39,7 @@ def _hf_dac(cdims):
         n_codebooks=cdims.n_codebooks,
         codebook_size=cdims.codebook_size,
         codebook_dim=cdims.codebook_dim,
-        encoder_hidden_size=8,  # encoder is not on the path; keep it tiny
+        encoder_hidden_size=cdims.encoder_dim if with_encoder else 8,
     )
     return DacModel(cfg).eval()
 
@@ -82,6 +82,39 @@ def load_dac_names_into_hf(hf_model, codec_sd):
         dec.snake1.alpha.copy_(codec_sd[f"decoder.model.{n + 1}.alpha"])
         dec.conv2.weight.copy_(w(f"decoder.model.{n + 2}"))
         dec.conv2.bias.copy_(codec_sd[f"decoder.model.{n + 2}.bias"])
+    return hf_model
+
+
+def load_dac_encoder_names_into_hf(hf_model, codec_sd):
+    """dac-1.0.0 encoder / in_proj key names (weight-normed) -> transformers.DacModel (plain convs)."""
+    def w(key):
+        return fold_weight_norm(codec_sd[key + ".weight_g"], codec_sd[key + ".weight_v"])
+
+    with torch.no_grad():
+        for k, q in enumerate(hf_model.quantizer.quantizers):
+            p = f"quantizer.quantizers.{k}.in_proj"
+            q.in_proj.weight.copy_(w(p))
+            q.in_proj.bias.copy_(codec_sd[p + ".bias"])
+        enc = hf_model.encoder
+        enc.conv1.weight.copy_(w("encoder.block.0"))
+        enc.conv1.bias.copy_(codec_sd["encoder.block.0.bias"])
+        for i, blk in enumerate(enc.block):
+            p = f"encoder.block.{i + 1}.block"
+            for j, ru in enumerate((blk.res_unit1, blk.res_unit2, blk.res_unit3)):
+                q = f"{p}.{j}.block"
+                ru.snake1.alpha.copy_(codec_sd[f"{q}.0.alpha"])
+                ru.conv1.weight.copy_(w(f"{q}.1"))
+                ru.conv1.bias.copy_(codec_sd[f"{q}.1.bias"])
+                ru.snake2.alpha.copy_(codec_sd[f"{q}.2.alpha"])
+                ru.conv2.weight.copy_(w(f"{q}.3"))
+                ru.conv2.bias.copy_(codec_sd[f"{q}.3.bias"])
+            blk.snake1.alpha.copy_(codec_sd[f"{p}.3.alpha"])
+            blk.conv1.weight.copy_(w(f"{p}.4"))
+            blk.conv1.bias.copy_(codec_sd[f"{p}.4.bias"])
+        n = len(enc.block)
+        enc.snake1.alpha.copy_(codec_sd[f"encoder.block.{n + 1}.alpha"])
+        enc.conv2.weight.copy_(w(f"encoder.block.{n + 2}"))
+        enc.conv2.bias.copy_(codec_sd[f"encoder.block.{n + 2}.bias"])
     return hf_model
 
 

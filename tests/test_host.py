@@ -315,3 +315,21 @@ def test_generate_dataset_isolates_failures():
     out = generate_dataset(gen, 9, 4, 0, 1, failed=failed)
     assert failed == [5] and out.shape == (9, 1, 4)
     assert out[:, 0, 0].tolist() == [0, 1, 2, 3, 4, 0, 6, 7, 8]
+
+
+def test_strided_conv_as_three_frame_taps():
+    """weights.strided_conv_frames: WNConv1d(k = 2 s, stride s, pad ceil(s / 2)) == a 3-tap conv over frames of s samples."""
+    import torch.nn.functional as F
+
+    from vaura_b200.weights import strided_conv_frames
+
+    torch.manual_seed(0)
+    for s in (2, 4, 8):
+        cin, cout, T = 5, 7, 16 * s
+        w, x = torch.randn(cout, cin, 2 * s), torch.randn(1, cin, T)
+        ref = F.conv1d(x, w, stride=s, padding=(s + 1) // 2)
+        wf = strided_conv_frames(w, s)                                  # [3][cout][s * cin]
+        frames = x[0].t().reshape(T // s, s * cin)                      # channels-last [T][cin] -> [T / s][s * cin]
+        fp = F.pad(frames, (0, 0, 1, 1))
+        mine = sum(fp[f:f + T // s] @ wf[f].t() for f in range(3)).t()[None]
+        assert torch.allclose(mine, ref, atol=1e-5), s

@@ -137,3 +137,26 @@ def test_motionformer_oracle_matches_reference_golden():
     assert mine.shape == ref.shape == (1, 2, 8, 768)
     err = float((mine - ref).abs().max() / ref.abs().max())
     assert err < 1e-5, err
+
+
+def test_dac_encode_oracle_matches_transformers():
+    """the restated dac encoder + residual VQ against transformers.DacModel.encode (the independent statement of
+    the same architecture; dac 1.0.0 itself is absent -> parity with it stays unpinned)."""
+    from oracle import ref_stubs
+    from oracle.dac_oracle import DacEncodeOracle
+    from vaura_b200.synthetic import TINY_CODEC, make_codec_state_dict
+
+    sd = make_codec_state_dict(TINY_CODEC, 100, with_encoder=True)
+    hf = ref_stubs._hf_dac(TINY_CODEC, with_encoder=True)
+    ref_stubs.load_dac_names_into_hf(hf, sd)
+    ref_stubs.load_dac_encoder_names_into_hf(hf, sd)
+    g = torch.Generator().manual_seed(3)
+    wav = 0.3 * torch.randn(2, 1, 5000, generator=g)
+    o = DacEncodeOracle(sd, TINY_CODEC)
+    padded = o.preprocess(wav)
+    assert padded.shape[-1] == 5120 and torch.equal(padded[..., :5000], wav) and float(padded[..., 5000:].abs().max()) == 0.0
+    with torch.no_grad():
+        out = hf.encode(padded)
+        z_hf = hf.encoder(padded)
+    assert torch.allclose(o.encode_latent(padded), z_hf, atol=1e-5)
+    assert torch.equal(o.encode(wav), out.audio_codes)

@@ -13,6 +13,7 @@ EXPORTS = [
     "vaura_sampler_create", "vaura_sampler_destroy", "vaura_sampler_cond_project",
     "vaura_sampler_workspace_bytes", "vaura_sampler_generate", "vaura_sampler_forward", "vaura_sample_logits",
     "vaura_codec_create", "vaura_codec_destroy", "vaura_codec_workspace_bytes", "vaura_codec_decode",
+    "vaura_codec_encoder_create", "vaura_codec_encoder_destroy", "vaura_codec_encoder_workspace_bytes", "vaura_codec_encode",
     "vaura_avclip_create", "vaura_avclip_destroy", "vaura_avclip_workspace_bytes", "vaura_avclip_forward",
 ]
 
@@ -101,6 +102,14 @@ def load():
     lib.vaura_codec_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.vaura_codec_workspace_bytes.restype = C.c_size_t
     lib.vaura_codec_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.c_void_p]
+    lib.vaura_codec_encoder_create.argtypes = [C.POINTER(CodecDimsC), C.c_int32, C.c_int32, C.POINTER(CodecWeightsC),
+                                               C.POINTER(C.c_void_p)]
+    lib.vaura_codec_encoder_destroy.argtypes = [C.c_void_p]
+    lib.vaura_codec_encoder_destroy.restype = None
+    lib.vaura_codec_encoder_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.vaura_codec_encoder_workspace_bytes.restype = C.c_size_t
+    lib.vaura_codec_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_size_t, C.c_void_p]
     lib.vaura_avclip_create.argtypes = [C.POINTER(AvclipDimsC), C.POINTER(AvclipWeightsC), C.POINTER(C.c_void_p)]
     lib.vaura_avclip_destroy.argtypes = [C.c_void_p]

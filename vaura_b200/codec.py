@@ -4,7 +4,8 @@ The class keeps the reference's name (checked at models/vaura_model.py:87) and c
 ``decode(codes | [(codes, None)]) -> (B, 1, hop*T) float16`` (fp16 because the reference halves the
 codec, vaura_model.py:92).  Weights come from the Lightning checkpoint's ``audio_encoder.model.*``
 entries (dac 1.0.0 names); the reference's ``dac.utils.download`` needs the network and is not mirrored.
-``encode`` (wav -> codes) is a "next" row and raises.
+``encode`` (wav -> codes, SURVEY §8f row 3: raw-audio prompts and ``compress_original_audio``, scripts/generate.py:286-301)
+runs the DAC encoder + residual vector quantisation when the checkpoint carries the encode half.
 """
 from __future__ import annotations
 
@@ -15,7 +16,7 @@ import torch
 
 from . import _cabi
 from .synthetic import CodecDims
-from .weights import pack_codec
+from .weights import pack_codec, pack_codec_encoder
 
 MODEL_SR = [16000, 24000, 44000, 44100]
 
@@ -33,6 +34,10 @@ class DacModelWrapper(torch.nn.Module):
         self._offsets = None
         self._handle = None
         self._ws = None
+        self._enc_blob = None
+        self._enc_offsets = None
+        self._enc_handle = None
+        self._enc_ws = None
         if ckpt_path is not None:
             sd = torch.load(ckpt_path, map_location="cpu", weights_only=False)
             self.load_state_dict(sd.get("state_dict", sd))
@@ -72,6 +77,11 @@ class DacModelWrapper(torch.nn.Module):
         if not self._dims_given:
             self.dims = self.dims_from_state_dict(state_dict, self.model_sr)
         self._blob, self._offsets = pack_codec(state_dict, self.dims, device)
+        if "encoder.block.0.weight_v" in state_dict or "encoder.block.0.weight" in state_dict:
+            if not self._dims_given:  # encoder width is read off the first convolution (dac `encoder_dim`)
+                key = "encoder.block.0.weight_v" if "encoder.block.0.weight_v" in state_dict else "encoder.block.0.weight"
+                self.dims = CodecDims(**{**self.dims.__dict__, "encoder_dim": int(state_dict[key].shape[0])})
+            self._enc_blob, self._enc_offsets = pack_codec_encoder(state_dict, self.dims, device)
         self._destroy()
         return torch.nn.modules.module._IncompatibleKeys([], [])
 
@@ -79,6 +89,9 @@ class DacModelWrapper(torch.nn.Module):
         if self._handle is not None:
             _cabi.load().vaura_codec_destroy(self._handle)
             self._handle = None
+        if self._enc_handle is not None:
+            _cabi.load().vaura_codec_encoder_destroy(self._enc_handle)
+            self._enc_handle = None
 
     def __del__(self):
         try:
@@ -104,8 +117,60 @@ class DacModelWrapper(torch.nn.Module):
     def forward(self, wav: torch.Tensor):
         return self.encode(wav)
 
-    def encode(self, wav: torch.Tensor):
-        raise NotImplementedError("DAC encode (wav -> codes) is outside the built hot path (SURVEY §8f row 3)")
+    def preprocess(self, wav: torch.Tensor, sample_rate: tp.Optional[int] = None) -> torch.Tensor:
+        """dac 1.0.0 ``DAC.preprocess``: zero-pad on the right to a multiple of the hop length."""
+        assert sample_rate is None or sample_rate == self.dims.sample_rate or sample_rate == self.model_sr
+        hop = self.dims.hop_length
+        right = -wav.shape[-1] % hop
+        return torch.nn.functional.pad(wav, (0, right)) if right else wav
+
+    def encoder_handle(self):
+        if self._enc_blob is None:
+            raise RuntimeError("the checkpoint held no `encoder.*` / `quantizer.*.in_proj` entries: encode() needs the "
+                               "encode half of the DAC weights")
+        if self._enc_handle is None:
+            lib = _cabi.load()
+            d = self.dims
+            rates = (C.c_int32 * 8)(*d.decoder_rates)
+            dc = _cabi.CodecDimsC(d.latent_dim, d.decoder_dim, len(d.decoder_rates), rates, d.n_codebooks, d.codebook_size)
+            offs = (C.c_int64 * len(self._enc_offsets))(*self._enc_offsets)
+            wc = _cabi.CodecWeightsC(self._enc_blob.data_ptr(), offs, len(self._enc_offsets))
+            h = C.c_void_p()
+            _cabi.check(lib.vaura_codec_encoder_create(C.byref(dc), d.encoder_dim, d.codebook_dim, C.byref(wc), C.byref(h)),
+                        "vaura_codec_encoder_create")
+            self._enc_handle = h
+        return self._enc_handle
+
+    @torch.no_grad()
+    def encode(self, wav: torch.Tensor, max_batch: int = 8, _return_latent: bool = False):
+        """wav (L,) | (C, L) | (B, 1, L) -> codes (B, n_codebooks, ceil(L / hop)) int64
+        (models/modules/dac/model.py:30-39: unsqueeze to 3 dims, ``model.preprocess``, codes of ``model.encode``)."""
+        if wav.ndim < 2:
+            wav = wav.unsqueeze(0)
+        if wav.ndim < 3:
+            wav = wav.unsqueeze(0)
+        if wav.shape[1] != 1:
+            raise ValueError(f"expected mono audio (B, 1, L), got {tuple(wav.shape)}")
+        h = self.encoder_handle()
+        lib = _cabi.load()
+        dev = self._enc_blob.device
+        x = self.preprocess(wav.to(device=dev, dtype=torch.float32), self.model_sr)[:, 0].contiguous()
+        B, L = x.shape
+        T = L // self.dims.hop_length
+        codes = torch.empty(B, self.dims.n_codebooks, T, dtype=torch.int32, device=dev)
+        latent = torch.empty(B, T, self.dims.latent_dim, dtype=torch.float16, device=dev) if _return_latent else None
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            for b0 in range(0, B, max_batch):
+                nb = min(max_batch, B - b0)
+                nbytes = lib.vaura_codec_encoder_workspace_bytes(h, nb, L)
+                if self._enc_ws is None or self._enc_ws.numel() < nbytes:
+                    self._enc_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                _cabi.check(lib.vaura_codec_encode(h, x[b0:b0 + nb].data_ptr(), nb, L, codes[b0:b0 + nb].data_ptr(),
+                                                   latent[b0:b0 + nb].data_ptr() if latent is not None else None,
+                                                   self._enc_ws.data_ptr(), self._enc_ws.numel(), st), "vaura_codec_encode")
+        codes = codes.to(torch.int64)
+        return (codes, latent) if _return_latent else codes
 
     @torch.no_grad()
     def decode(self, codes: tp.Union[torch.Tensor, tp.List[tp.Tuple[torch.Tensor, tp.Any]]], max_batch: int = 16,

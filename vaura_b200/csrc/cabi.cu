@@ -834,6 +834,142 @@ extern "C" int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t 
   return VAURA_OK;
 }
 
+// ---- codec encode --------------------------------------------------------------------------------------
+struct vaura_codec_encoder {
+  vaura_codec_dims d;
+  int enc_dim, cb_dim;
+  const char* blob;
+  std::vector<int64_t> off;
+  std::vector<int> taps;  // host copy: [k7 d1][k7 d3][k7 d9][k1][k3]
+  bool use_tc = true;
+};
+
+extern "C" int vaura_codec_encoder_create(const vaura_codec_dims* dims, int32_t encoder_dim, int32_t codebook_dim,
+                                          const vaura_codec_weights* w, vaura_codec_encoder** out) {
+  if (!dims || !w || !out || !w->blob || !w->offsets) return fail(VAURA_ERR_INVALID, "null argument");
+  if (dims->n_blocks < 1 || dims->n_blocks > 8) return fail(VAURA_ERR_INVALID, "n_blocks must be 1..8");
+  const int want = 2 + 21 * dims->n_blocks + 8;
+  if (w->n_offsets != want) return fail(VAURA_ERR_INVALID, "codec encoder blob has %d slots, expected %d", w->n_offsets, want);
+  if (encoder_dim % 16 || encoder_dim < 16) return fail(VAURA_ERR_UNSUPPORTED, "encoder_dim must be a multiple of 16");
+  if (codebook_dim < 1 || codebook_dim > 32) return fail(VAURA_ERR_UNSUPPORTED, "codebook_dim must be 1..32");
+  if (dims->latent_dim > 8192 || dims->n_codebooks > 32) return fail(VAURA_ERR_UNSUPPORTED, "latent_dim / n_codebooks too large");
+  vaura_codec_encoder* c = new (std::nothrow) vaura_codec_encoder();
+  if (!c) return fail(VAURA_ERR_INVALID, "out of host memory");
+  c->d = *dims; c->enc_dim = encoder_dim; c->cb_dim = codebook_dim;
+  c->blob = (const char*)w->blob;
+  c->off.assign(w->offsets, w->offsets + w->n_offsets);
+  for (int dil : {1, 3, 9})
+    for (int j = 0; j < 7; ++j) c->taps.push_back(j * dil - 3 * dil);
+  c->taps.push_back(0);
+  for (int j = 0; j < 3; ++j) c->taps.push_back(j - 1);
+  const char* env = getenv("VAURA_CODEC_SIMT");
+  c->use_tc = !(env && env[0] == '1');
+  *out = c;
+  return VAURA_OK;
+}
+
+extern "C" void vaura_codec_encoder_destroy(vaura_codec_encoder* c) { delete c; }
+
+struct EncWs {
+  float* wav_unused;
+  __half *x, *x2, *a0, *a1, *h, *z;
+  size_t bytes;
+};
+
+static EncWs enc_carve(const vaura_codec_encoder* c, int B, int L, void* base) {
+  EncWs w{};
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(n);
+    return (__half*)r;
+  };
+  // activation size per clip: L * C0 in the first block; a block with stride s turns (T, C) into (T / s, 2 C), never larger
+  size_t maxel = (size_t)L * c->enc_dim, t = L, ch = c->enc_dim;
+  for (int i = 0; i < c->d.n_blocks; ++i) {
+    const int s = c->d.rates[c->d.n_blocks - 1 - i];
+    t /= s; ch *= 2;
+    if (t * ch > maxel) maxel = t * ch;
+  }
+  w.x = take(B * maxel * 2); w.x2 = take(B * maxel * 2); w.a0 = take(B * maxel * 2); w.a1 = take(B * maxel * 2);
+  w.h = take(B * maxel * 2);
+  w.z = take((size_t)B * t * c->d.latent_dim * 2);
+  w.bytes = off;
+  return w;
+}
+
+extern "C" size_t vaura_codec_encoder_workspace_bytes(const vaura_codec_encoder* c, int32_t batch, int32_t samples) {
+  if (!c || batch <= 0 || samples <= 0) return 0;
+  return enc_carve(c, batch, samples, nullptr).bytes;
+}
+
+extern "C" int vaura_codec_encode(vaura_codec_encoder* c, const float* wav, int32_t B, int32_t L, int32_t* codes_out,
+                                  uint16_t* latent_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!c || !wav || !codes_out || !workspace || B <= 0 || L <= 0) return fail(VAURA_ERR_INVALID, "bad argument");
+  const vaura_codec_dims& d = c->d;
+  int hop = 1;
+  for (int i = 0; i < d.n_blocks; ++i) hop *= d.rates[i];
+  if (L % hop) return fail(VAURA_ERR_INVALID, "samples %d is not a multiple of the hop length %d (pad first: DAC.preprocess)", L, hop);
+  EncWs ws = enc_carve(c, B, L, workspace);
+  if (ws.bytes > workspace_bytes) return fail(VAURA_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  auto H = [&](int slot) { return (const __half*)(c->blob + c->off[slot]); };
+  auto F = [&](int slot) { return (const float*)(c->blob + c->off[slot]); };
+  const int tail = 2 + 21 * d.n_blocks;
+  const int* taps = (const int*)(c->blob + c->off[tail + 7]);
+  const int* taps_k7[3] = {taps, taps + 7, taps + 14};
+  const int* taps_k1 = taps + 21;
+  const int* taps_k3 = taps + 22;
+  auto conv = [&](const ConvArgs& a, int tap_index) -> int {
+    if (c->use_tc && conv_tc_supported(a.Cin, a.Cout, a.ntaps, a.nphase)) {
+      CUL(launch_conv_tc(a, c->taps.data() + tap_index, B, st));
+    } else {
+      CUL(launch_conv_gemm(a, B, st));
+    }
+    return VAURA_OK;
+  };
+  int rc;
+  int t = L, ch = c->enc_dim;
+  __half *x = ws.x, *x2 = ws.x2, *act = ws.a0, *act2 = ws.a1;
+  CUL(launch_enc_conv_in(wav, F(0), F(1), F(2), x, act, B, L, ch, st));
+  for (int i = 0; i < d.n_blocks; ++i) {
+    const int base = 2 + 21 * i, s = d.rates[d.n_blocks - 1 - i];  // encoder strides = reversed decoder rates
+    for (int j = 0; j < 3; ++j) {
+      const int rb = base + 6 * j;
+      ConvArgs c7{};
+      c7.in = act; c7.W = H(rb + 1); c7.tap_off = taps_k7[j]; c7.bias = F(rb + 2); c7.alpha = F(rb + 3); c7.out_act = ws.h;
+      c7.Tin = t; c7.Tq = t; c7.Tout = t; c7.Cin = ch; c7.Cout = ch; c7.ntaps = 7; c7.nphase = 1; c7.ostride = 1;
+      if ((rc = conv(c7, 7 * j))) return rc;
+      ConvArgs c1{};
+      c1.in = ws.h; c1.W = H(rb + 4); c1.tap_off = taps_k1; c1.bias = F(rb + 5);
+      c1.alpha = j < 2 ? F(rb + 6) : F(base + 18);  // next residual unit's first Snake, or the block's Snake before the stride
+      c1.residual = x; c1.out_raw = j < 2 ? x : nullptr; c1.out_act = act;
+      c1.Tin = t; c1.Tq = t; c1.Tout = t; c1.Cin = ch; c1.Cout = ch; c1.ntaps = 1; c1.nphase = 1; c1.ostride = 1;
+      if ((rc = conv(c1, 21))) return rc;
+    }
+    // WNConv1d(C -> 2C, k = 2 s, stride s, pad ceil(s / 2)) as a three-tap convolution over frames of s samples
+    if (t % s) return fail(VAURA_ERR_INVALID, "length %d is not a multiple of stride %d", t, s);
+    ConvArgs cs{};
+    cs.in = act; cs.W = H(base + 19); cs.tap_off = taps_k3; cs.bias = F(base + 20);
+    cs.alpha = i + 1 < d.n_blocks ? F(2 + 21 * (i + 1)) : F(tail);  // next block's first Snake, or the final Snake
+    cs.out_raw = i + 1 < d.n_blocks ? x2 : nullptr; cs.out_act = act2;
+    cs.Tin = t / s; cs.Tq = t / s; cs.Tout = t / s; cs.Cin = s * ch; cs.Cout = 2 * ch; cs.ntaps = 3; cs.nphase = 1; cs.ostride = 1;
+    if ((rc = conv(cs, 22))) return rc;
+    t /= s; ch *= 2;
+    __half* tmp = x; x = x2; x2 = tmp;
+    tmp = act; act = act2; act2 = tmp;
+  }
+  __half* zdst = latent_out ? (__half*)latent_out : ws.z;
+  ConvArgs cz{};
+  cz.in = act; cz.W = H(tail + 1); cz.tap_off = taps_k3; cz.bias = F(tail + 2); cz.alpha = nullptr; cz.out_raw = zdst;
+  cz.Tin = t; cz.Tq = t; cz.Tout = t; cz.Cin = ch; cz.Cout = d.latent_dim; cz.ntaps = 3; cz.nphase = 1; cz.ostride = 1;
+  if ((rc = conv(cz, 22))) return rc;
+  CUL(launch_rvq_encode(zdst, F(tail + 3), F(tail + 4), F(tail + 5), F(tail + 6), codes_out, B, d.n_codebooks, t,
+                        d.codebook_size, d.latent_dim, c->cb_dim, st));
+  return VAURA_OK;
+}
+
 // ---- Segment-AVCLIP visual tower (avclip.cu) ------------------------------------------------------------
 struct vaura_avclip {
   vaura_avclip_dims d;

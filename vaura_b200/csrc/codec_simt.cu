@@ -189,4 +189,125 @@ cudaError_t launch_conv_out_tanh(const __half* in, const float* W, const float* 
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// encode direction (dac 1.0.0 Encoder / ResidualVectorQuantize.forward, reached through
+// DacModelWrapper.encode, models/modules/dac/model.py:30-39).  The encoder's ResidualUnits, strided convolutions (run as
+// three-tap convolutions over frames of `stride` samples) and the final k3 convolution go through the same implicit-GEMM
+// kernels as the decoder; only the two ends are new.
+// ------------------------------------------------------------------------------------------------------------------------
+// first layer: WNConv1d(1 -> C, k 7, pad 3) on the waveform, raw output + Snake with the first residual unit's alpha
+__global__ void __launch_bounds__(256) enc_conv_in_kernel(const float* __restrict__ wav, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, const float* __restrict__ alpha,
+                                                          __half* __restrict__ out_raw, __half* __restrict__ out_act, int L, int C) {
+  // thread = (time step, 8 channels)
+  const int c8 = C / 8;
+  const size_t total = (size_t)L * c8;
+  const int b = blockIdx.y;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % c8) * 8, t = (int)(i / c8);
+    float x[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int r = t + j - 3;
+      x[j] = (r >= 0 && r < L) ? __ldg(wav + (size_t)b * L + r) : 0.f;
+    }
+    uint4 raw, act;
+    __half2* hr = reinterpret_cast<__half2*>(&raw);
+    __half2* ha = reinterpret_cast<__half2*>(&act);
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      float v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = c0 + e + u;
+        float acc = __ldg(bias + c);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc = fmaf(__ldg(W + c * 7 + j), x[j], acc);
+        v[u] = acc;
+      }
+      hr[e / 2] = __floats2half2_rn(v[0], v[1]);
+      ha[e / 2] = __floats2half2_rn(snake_f(v[0], __ldg(alpha + c0 + e), __ldg(alpha + C + c0 + e)),
+                                    snake_f(v[1], __ldg(alpha + c0 + e + 1), __ldg(alpha + C + c0 + e + 1)));
+    }
+    const size_t o = ((size_t)b * L + t) * C + c0;
+    *reinterpret_cast<uint4*>(out_raw + o) = raw;
+    *reinterpret_cast<uint4*>(out_act + o) = act;
+  }
+}
+
+cudaError_t launch_enc_conv_in(const float* wav, const float* W, const float* bias, const float* alpha, __half* out_raw,
+                               __half* out_act, int B, int L, int C, cudaStream_t st) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const size_t total = (size_t)L * (C / 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  enc_conv_in_kernel<<<dim3(blocks, B), 256, 0, st>>>(wav, W, bias, alpha, out_raw, out_act, L, C);
+  return cudaGetLastError();
+}
+
+// residual vector quantisation of one latent frame per CTA (dac/nn/quantize.py VectorQuantize.decode_latents +
+// ResidualVectorQuantize.forward): for every codebook k: e = in_proj_k(residual), cosine nearest neighbour among the
+// l2-normalised code vectors (first index on ties, like torch.max), residual -= out_proj_k(codebook_k[idx]) (fp32 table).
+constexpr int kRvqThreads = 256;
+__global__ void __launch_bounds__(kRvqThreads)
+rvq_encode_kernel(const __half* __restrict__ z, const float* __restrict__ w_in, const float* __restrict__ b_in,
+                  const float* __restrict__ cb_norm, const float* __restrict__ tables, int32_t* __restrict__ codes, int Kc, int T,
+                  int Vc, int latent, int Dc) {
+  extern __shared__ float rsm[];
+  float* res = rsm;                 // [latent]
+  float* e = rsm + latent;          // [Dc] (<= 32)
+  float* bestv = e + 32;            // [warps]
+  int* besti = reinterpret_cast<int*>(bestv + kRvqThreads / 32);
+  const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int c = tid; c < latent; c += kRvqThreads) res[c] = __half2float(z[((size_t)b * T + t) * latent + c]);
+  __syncthreads();
+  for (int k = 0; k < Kc; ++k) {
+    // in_proj: Dc dot products of length `latent`, one warp each (round robin)
+    for (int d = warp; d < Dc; d += kRvqThreads / 32) {
+      const float* w = w_in + ((size_t)k * Dc + d) * latent;
+      float acc = 0.f;
+      for (int c = lane; c < latent; c += 32) acc = fmaf(__ldg(w + c), res[c], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) e[d] = acc + __ldg(b_in + k * Dc + d);
+    }
+    __syncthreads();
+    float ev[32], nrm = 0.f;
+    for (int d = 0; d < Dc; ++d) { ev[d] = e[d]; nrm += ev[d] * ev[d]; }
+    const float inv = 1.f / fmaxf(sqrtf(nrm), 1e-12f);  // F.normalize: x / max(||x||, eps)
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = tid; j < Vc; j += kRvqThreads) {
+      const float* cv = cb_norm + ((size_t)k * Vc + j) * Dc;
+      float dot = 0.f, cn = 0.f;
+      for (int d = 0; d < Dc; ++d) { const float c = __ldg(cv + d); dot = fmaf(ev[d] * inv, c, dot); cn = fmaf(c, c, cn); }
+      // -dist = -(|e|^2 - 2 e.c + |c|^2) with |e| = 1 after normalisation; the common -1 is dropped
+      const float sc = 2.f * dot - cn;
+      if (sc > bv) { bv = sc; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { bestv[warp] = bv; besti[warp] = bi; }
+    __syncthreads();
+    bv = bestv[0]; bi = besti[0];
+    for (int w2 = 1; w2 < kRvqThreads / 32; ++w2)
+      if (bestv[w2] > bv || (bestv[w2] == bv && besti[w2] < bi)) { bv = bestv[w2]; bi = besti[w2]; }
+    if (tid == 0) codes[((size_t)b * Kc + k) * T + t] = bi;
+    const float* tb = tables + ((size_t)k * Vc + bi) * latent;
+    for (int c = tid; c < latent; c += kRvqThreads) res[c] -= __ldg(tb + c);
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_rvq_encode(const __half* z, const float* w_in, const float* b_in, const float* cb_norm, const float* tables,
+                              int32_t* codes, int B, int Kc, int T, int Vc, int latent, int Dc, cudaStream_t st) {
+  if (Dc > 32 || Dc < 1) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)latent + 32 + 2 * (kRvqThreads / 32)) * 4;
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  rvq_encode_kernel<<<dim3(T, B), kRvqThreads, smem, st>>>(z, w_in, b_in, cb_norm, tables, codes, Kc, T, Vc, latent, Dc);
+  return cudaGetLastError();
+}
+
 }  // namespace vaura

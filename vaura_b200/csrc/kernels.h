@@ -82,6 +82,10 @@ cudaError_t launch_from_codes(const int32_t* codes, const __half* tables, __half
 cudaError_t launch_conv_gemm(const ConvArgs& a, int B, cudaStream_t st);
 cudaError_t launch_conv_out_tanh(const __half* in, const float* W, const float* bias, __half* wav, int B, int T, int C,
                                  cudaStream_t st);
+cudaError_t launch_enc_conv_in(const float* wav, const float* W, const float* bias, const float* alpha, __half* out_raw,
+                               __half* out_act, int B, int L, int C, cudaStream_t st);
+cudaError_t launch_rvq_encode(const __half* z, const float* w_in, const float* b_in, const float* cb_norm, const float* tables,
+                              int32_t* codes, int B, int Kc, int T, int Vc, int latent, int Dc, cudaStream_t st);
 struct LinearTcArgs {
   const void* A;        // bf16 [R][lda]
   const void* W;        // bf16 [N][K]

@@ -149,7 +149,9 @@ class VAURAModel(torch.nn.Module):
         if audio is None:
             audio = torch.zeros((num_samples, K, 0), dtype=torch.long, device=dev)
         elif not prompt_is_encoded:
-            audio = self.audio_encoder.encode(audio)  # raises: SURVEY §8f row 3
+            # raw-audio prompt -> codes (B, K, Tp).  The reference's EnCodec-era unpacking of the encoder output
+            # (vaura_model.py:464-469) does not type-check against DacModelWrapper.encode's tensor; the codes are used as they are
+            audio = self.audio_encoder.encode(audio)
         B, K, T = audio.shape
         vis_feats = self._handle_visual_conditioning(frames.to(dev), clip_indices, B)
         start_offset = T

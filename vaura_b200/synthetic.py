@@ -80,17 +80,22 @@ class CodecDims:
     codebook_size: int = 1024
     codebook_dim: int = 8
     sample_rate: int = 44100
+    encoder_dim: int = 64  # dac 1.0.0 `encoder_dim`; channels double per EncoderBlock, strides = reversed decoder rates
 
     @property
     def hop_length(self) -> int:
         return int(math.prod(self.decoder_rates))
+
+    @property
+    def encoder_rates(self) -> Tuple[int, ...]:
+        return tuple(reversed(self.decoder_rates))
 
 
 FULL_SAMPLER = SamplerDims()
 FULL_CODEC = CodecDims()
 # Small shapes for fast parity cases: same head_dim (96), same vocabulary.
 TINY_SAMPLER = SamplerDims(num_layers=2, d_model=384, nhead=4)
-TINY_CODEC = CodecDims(latent_dim=256, decoder_dim=512)
+TINY_CODEC = CodecDims(latent_dim=256, decoder_dim=512, encoder_dim=32)
 
 
 def _gen(seed: int, key: str) -> torch.Generator:
@@ -158,14 +163,14 @@ def _wn(sd, seed, key, shape, fan_in, norm_dims):
     sd[key + ".bias"] = _randn(seed, key + ".bias", (shape[0],), 0.05)
 
 
-def make_codec_state_dict(dims: CodecDims = FULL_CODEC, seed: int = 100) -> Dict[str, torch.Tensor]:
+def make_codec_state_dict(dims: CodecDims = FULL_CODEC, seed: int = 100, with_encoder: bool = False) -> Dict[str, torch.Tensor]:
     """State dict for the decode half of ``dac.DAC`` (dac 1.0.0 names, no prefix).
 
     ``quantizer.quantizers.{k}.codebook.weight``, ``...out_proj.{weight_g,weight_v,bias}``,
     ``decoder.model.0`` (conv k7), ``decoder.model.{1+i}.block.{0: Snake alpha, 1: ConvTranspose1d,
     2..4: ResidualUnit.block.{0: alpha, 1: conv k7 dilated, 2: alpha, 3: conv k1}}``,
-    ``decoder.model.{n+1}.alpha``, ``decoder.model.{n+2}`` (conv k7 -> 1).  Encoder / in_proj are
-    not on the path and are not generated.
+    ``decoder.model.{n+1}.alpha``, ``decoder.model.{n+2}`` (conv k7 -> 1).  ``with_encoder`` adds the encode half
+    (make_codec_encoder_state_dict).
     """
     sd: Dict[str, torch.Tensor] = {}
     for k in range(dims.n_codebooks):
@@ -194,6 +199,34 @@ def make_codec_state_dict(dims: CodecDims = FULL_CODEC, seed: int = 100) -> Dict
     cl = ch // 2 ** n
     sd[f"decoder.model.{n + 1}.alpha"] = _rand(seed, "final.alpha", (1, cl, 1), 0.5, 2.0)
     _wn(sd, seed, f"decoder.model.{n + 2}", (1, cl, 7), cl * 7 * 4, (1, 2))
+    if with_encoder:
+        sd.update(make_codec_encoder_state_dict(dims, seed))
+    return sd
+
+
+def make_codec_encoder_state_dict(dims: CodecDims = FULL_CODEC, seed: int = 100) -> Dict[str, torch.Tensor]:
+    """The encode half (dac 1.0.0 names): ``encoder.block.0`` (conv k7, 1 -> encoder_dim), ``encoder.block.{1+i}.block.{0..2:
+    ResidualUnit.block.{0: alpha, 1: conv k7 dilated, 2: alpha, 3: conv k1}, 3: Snake alpha, 4: conv k = 2 s, stride s}``,
+    ``encoder.block.{n+1}.alpha``, ``encoder.block.{n+2}`` (conv k3 -> latent) and ``quantizer.quantizers.{k}.in_proj``."""
+    sd: Dict[str, torch.Tensor] = {}
+    c = dims.encoder_dim
+    _wn(sd, seed, "encoder.block.0", (c, 1, 7), 7 * 0.25, (1, 2))
+    for i, s in enumerate(dims.encoder_rates):
+        p = f"encoder.block.{i + 1}.block"
+        for j in range(3):
+            q = f"{p}.{j}.block"
+            sd[f"{q}.0.alpha"] = _rand(seed, f"{q}.0.alpha", (1, c, 1), 0.5, 2.0)
+            _wn(sd, seed, f"{q}.1", (c, c, 7), c * 7 * 2, (1, 2))
+            sd[f"{q}.2.alpha"] = _rand(seed, f"{q}.2.alpha", (1, c, 1), 0.5, 2.0)
+            _wn(sd, seed, f"{q}.3", (c, c, 1), c * 8, (1, 2))
+        sd[f"{p}.3.alpha"] = _rand(seed, f"{p}.3.alpha", (1, c, 1), 0.5, 2.0)
+        _wn(sd, seed, f"{p}.4", (2 * c, c, 2 * s), c * 2 * s * 0.5, (1, 2))
+        c *= 2
+    n = len(dims.encoder_rates)
+    sd[f"encoder.block.{n + 1}.alpha"] = _rand(seed, f"encoder.block.{n + 1}.alpha", (1, c, 1), 0.5, 2.0)
+    _wn(sd, seed, f"encoder.block.{n + 2}", (dims.latent_dim, c, 3), c * 3 * 0.5, (1, 2))
+    for k in range(dims.n_codebooks):
+        _wn(sd, seed, f"quantizer.quantizers.{k}.in_proj", (dims.codebook_dim, dims.latent_dim, 1), dims.latent_dim * 0.05, (1, 2))
     return sd
 
 

@@ -290,6 +290,93 @@ def pack_codec(sd: Dict[str, torch.Tensor], dims: CodecDims, device):
     return blob.to(device), offsets
 
 
+def strided_conv_frames(w: torch.Tensor, stride: int) -> torch.Tensor:
+    """WNConv1d(Cin -> Cout, k = 2 s, stride s, padding ceil(s / 2)) weight (Cout, Cin, 2 s) -> [3][Cout][s * Cin]: the same
+    convolution as three taps (frame offsets -1, 0, +1) over the channels-last input seen as frames of s samples
+    ([T][Cin] -> [T / s][s * Cin], a free reshape): out[q] = sum_f W_f . frame[q + f].  Sample u = j - pad of tap j lies in
+    frame floor(u / s) at row u mod s; positions no tap reaches stay zero."""
+    cout, cin, k = w.shape
+    assert k == 2 * stride
+    pad = (stride + 1) // 2
+    out = torch.zeros(3, cout, stride * cin, dtype=w.dtype)
+    for j in range(k):
+        u = j - pad
+        f, r = u // stride, u % stride
+        out[f + 1, :, r * cin:(r + 1) * cin] = w[:, :, j]
+    return out
+
+
+def pack_codec_encoder(sd: Dict[str, torch.Tensor], dims: CodecDims, device):
+    """Encode half of a dac state dict -> (blob, offsets).  Slot order: include/vaura_b200.h (vaura_codec_encoder_create)."""
+    parts: List[torch.Tensor] = []
+
+    def h(t):
+        parts.append(t.to(torch.float16).contiguous())
+
+    def f(t):
+        parts.append(t.to(torch.float32).contiguous())
+
+    def snake(alpha):
+        al = alpha.reshape(-1).to(torch.float32)
+        parts.append(torch.cat([al, (al + 1e-9).reciprocal()]).contiguous())
+
+    rates = dims.encoder_rates
+    n = len(rates)
+    f(_conv_w(sd, "encoder.block.0")[:, 0, :])  # (C0, 1, 7) -> [C0][7]
+    f(sd["encoder.block.0.bias"])
+    for i, s in enumerate(rates):
+        p = f"encoder.block.{i + 1}.block"
+        for j in range(3):
+            q = f"{p}.{j}.block"
+            snake(sd[f"{q}.0.alpha"])
+            h(_conv_w(sd, f"{q}.1").permute(2, 0, 1))
+            f(sd[f"{q}.1.bias"])
+            snake(sd[f"{q}.2.alpha"])
+            h(_conv_w(sd, f"{q}.3").permute(2, 0, 1))
+            f(sd[f"{q}.3.bias"])
+        snake(sd[f"{p}.3.alpha"])
+        h(strided_conv_frames(_conv_w(sd, f"{p}.4").float(), s))
+        f(sd[f"{p}.4.bias"])
+    snake(sd[f"encoder.block.{n + 1}.alpha"])
+    h(_conv_w(sd, f"encoder.block.{n + 2}").permute(2, 0, 1))
+    f(sd[f"encoder.block.{n + 2}.bias"])
+    w_in, b_in, cbn, tables = [], [], [], []
+    for k in range(dims.n_codebooks):
+        p = f"quantizer.quantizers.{k}"
+        w_in.append(_conv_w(sd, f"{p}.in_proj")[:, :, 0].float())          # (Dc, latent)
+        b_in.append(sd[f"{p}.in_proj.bias"].float())
+        cb = sd[f"{p}.codebook.weight"].float()
+        cbn.append(torch.nn.functional.normalize(cb))
+        W = _conv_w(sd, f"{p}.out_proj")[:, :, 0].float()                   # (latent, Dc)
+        tables.append(cb @ W.t() + sd[f"{p}.out_proj.bias"].float())
+    f(torch.stack(w_in)); f(torch.stack(b_in)); f(torch.stack(cbn)); f(torch.stack(tables))
+    taps: List[int] = []
+    for dil in (1, 3, 9):
+        taps += [j * dil - 3 * dil for j in range(7)]
+    taps += [0]
+    taps += [-1, 0, 1]
+    parts.append(torch.tensor(taps, dtype=torch.int32))
+    offsets, cur = [], 0
+    for t in parts:
+        offsets.append(cur)
+        cur += (t.numel() * t.element_size() + 255) // 256 * 256
+    blob = torch.zeros(cur, dtype=torch.uint8)
+    for o, t in zip(offsets, parts):
+        blob[o:o + t.numel() * t.element_size()] = t.view(-1).view(torch.uint8)
+    return blob.to(device), offsets
+
+
+def codec_encoder_flops(dims: CodecDims, samples: int) -> float:
+    """2 * Cin * Cout * k * Lout per convolution of the encoder (the strided ones counted at their real 2 s taps)."""
+    c, t, fl = dims.encoder_dim, samples, 2.0 * dims.encoder_dim * 7 * samples
+    for s in dims.encoder_rates:
+        fl += 3 * (2.0 * c * c * 7 * t + 2.0 * c * c * t)
+        t //= s
+        fl += 2.0 * c * (2 * c) * (2 * s) * t
+        c *= 2
+    return fl + 2.0 * c * dims.latent_dim * 3 * t
+
+
 def pack_avclip(sd: Dict[str, torch.Tensor], dims, device):
     """MotionFormer state dict (reference names: video_model_builder.py:44-123, motionformer.py:166-185) ->
     (blob uint8 device tensor, offsets).  Slot order: include/vaura_b200.h (vaura_avclip_weights).  Matrices are stored as
