@@ -211,7 +211,7 @@ int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t batch, int3
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- codec encode, replaces DacModelWrapper.encode (models/modules/dac/model.py:30-39: preprocess + dac `encode`,
- *      codes only).  Same vaura_codec_dims (+ encoder_dim); its own weight blob (vaura_b200/weights.py:pack_codec_encoder):
+ *      codes only).  Same dims struct as the decoder plus encoder_dim; its own weight blob (vaura_b200/weights.py:pack_codec_encoder):
  *      0 conv_in W f32 [C0][7]  1 conv_in bias;  per block i (base 2 + 21 i): three residual units (+6 j: alpha1 | conv7 W f16
  *      [7][C][C] | bias | alpha2 | conv1 W f16 [1][C][C] | bias), +18 block snake alpha, +19 strided conv as three taps over
  *      frames of `stride` samples W f16 [3][2C][stride*C], +20 bias;  tail (base 2 + 21 n): final snake alpha | conv k3 W f16
