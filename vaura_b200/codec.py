@@ -69,8 +69,11 @@ class DacModelWrapper(torch.nn.Module):
         while f"quantizer.quantizers.{n_q}.codebook.weight" in sd:
             n_q += 1
         size, cdim = sd["quantizer.quantizers.0.codebook.weight"].shape
+        extra = {}
+        if any(k.startswith("encoder.block.0.") for k in sd):  # encode half present: its width is dac's `encoder_dim`
+            extra["encoder_dim"] = int(shape("encoder.block.0")[0])
         return CodecDims(latent_dim=latent, decoder_dim=decoder_dim, decoder_rates=tuple(rates), n_codebooks=n_q,
-                         codebook_size=size, codebook_dim=cdim, sample_rate=sample_rate)
+                         codebook_size=size, codebook_dim=cdim, sample_rate=sample_rate, **extra)
 
     def load_state_dict(self, state_dict, strict: bool = True, device=None):
         device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -78,9 +81,6 @@ class DacModelWrapper(torch.nn.Module):
             self.dims = self.dims_from_state_dict(state_dict, self.model_sr)
         self._blob, self._offsets = pack_codec(state_dict, self.dims, device)
         if "encoder.block.0.weight_v" in state_dict or "encoder.block.0.weight" in state_dict:
-            if not self._dims_given:  # encoder width is read off the first convolution (dac `encoder_dim`)
-                key = "encoder.block.0.weight_v" if "encoder.block.0.weight_v" in state_dict else "encoder.block.0.weight"
-                self.dims = CodecDims(**{**self.dims.__dict__, "encoder_dim": int(state_dict[key].shape[0])})
             self._enc_blob, self._enc_offsets = pack_codec_encoder(state_dict, self.dims, device)
         self._destroy()
         return torch.nn.modules.module._IncompatibleKeys([], [])

@@ -150,7 +150,9 @@ def write_video(filename: str, video_array, fps: float, audio_array: tp.Optional
                 video_codec: str = "h264", audio_codec: str = "aac", options: tp.Optional[dict] = None) -> bool:
     """The mux of utils/utils.py `write_video` (PyAV).  Returns False (after a warning) when PyAV is not installed."""
     try:
-        import av  # noqa: F401
+        import av
+        if not hasattr(av, "open"):
+            raise ImportError("av without av.open")
     except Exception:
         logger.warning("PyAV is not installed: %s not written (the wav next to it is)", filename)
         return False

@@ -234,7 +234,8 @@ def make_checkpoint_state_dict(sdims: SamplerDims = FULL_SAMPLER, cdims: CodecDi
                                seed: int = 0) -> Dict[str, torch.Tensor]:
     """Lightning-style flat state dict: ``sampler.*`` + ``audio_encoder.model.*``."""
     sd = {"sampler." + k: v for k, v in make_sampler_state_dict(sdims, seed).items()}
-    sd.update({"audio_encoder.model." + k: v for k, v in make_codec_state_dict(cdims, seed + 100).items()})
+    # a real checkpoint carries both halves of the codec (dac.DAC: encoder + quantizer + decoder)
+    sd.update({"audio_encoder.model." + k: v for k, v in make_codec_state_dict(cdims, seed + 100, with_encoder=True).items()})
     return sd
 
 
