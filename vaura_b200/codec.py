@@ -81,6 +81,10 @@ class DacModelWrapper(torch.nn.Module):
             self.dims = self.dims_from_state_dict(state_dict, self.model_sr)
         self._blob, self._offsets = pack_codec(state_dict, self.dims, device)
         if "encoder.block.0.weight_v" in state_dict or "encoder.block.0.weight" in state_dict:
+            # the encoder width is read off its first convolution whatever the YAML said (dac `encoder_dim`)
+            enc_dim = self.dims_from_state_dict(state_dict, self.model_sr).encoder_dim
+            if enc_dim != self.dims.encoder_dim:
+                self.dims = CodecDims(**{**self.dims.__dict__, "encoder_dim": enc_dim})
             self._enc_blob, self._enc_offsets = pack_codec_encoder(state_dict, self.dims, device)
         self._destroy()
         return torch.nn.modules.module._IncompatibleKeys([], [])

@@ -274,8 +274,9 @@ static int transformer_pass(const vaura_sampler* s, const Workspace& ws, const i
 // (LinearTcArgs::w_k re-reads their K blocks) and tcgen05 accumulates in fp32 - the products are the fp32 products, only
 // the summation order differs from gemv_kernel.  The weights are read once per pass instead of once per 8 rows
 // (launch_gemv_nb: ceil(166 / 8) = 21 passes for a 166-position prompt).  KV cache, q, attention and the residual stream
-// stay fp32, so the decode steps that follow continue bit-compatibly.  No split-K: every output element has one owner
-// and the result is deterministic.
+// stay fp32, so the decode steps that follow continue bit-compatibly.  Every output element has one owner: with one or two row
+// tiles (a prompt window) K is split over a cluster of 2 or 4 CTAs whose partial sums meet in the owner's shared memory and are
+// added in rank order (gemm_tc_kernel, CK > 1) - deterministic, no float atomics.
 static int transformer_pass_tc3(const vaura_sampler* s, const Workspace& ws, const int32_t* seq, int batch, int S,
                                 const float* cond_rows, int rows, int npos, int pos0, const StepState* state,
                                 const KvView& kv, float* logits_dst, bool logits_all, cudaStream_t st) {
@@ -299,7 +300,7 @@ static int transformer_pass_tc3(const vaura_sampler* s, const Workspace& ws, con
   for (int l = 0; l < d.num_layers; ++l) {
     LinearTcArgs g{};
     g.state = state; g.pos0 = pos0; g.npos = npos; g.R = R; g.layer = l; g.d_model = d.d_model; g.kv = kv; g.rope = w.rope;
-    g.ksplit = 1; g.pdl = 0;
+    g.ksplit = 0; g.pdl = 0;  // 0 = auto: K split inside clusters when the tiles cover less than half of the SMs (prompt prefill)
     CUL(launch_rmsnorm_split3(ws.h, w.attn_norm + l * D, ws.x3, R, (int)D, D, d.norm_eps, st));
     g.A = ws.x3; g.lda = 3 * D; g.K = 3 * D; g.w_k = D; g.W = w.wqkv + (size_t)l * 3 * D * D; g.N = 3 * D; g.epi = EPI_QKV_F32;
     g.out_f32 = ws.q; g.ldo = D; g.block_n = pick_bn(3 * D);

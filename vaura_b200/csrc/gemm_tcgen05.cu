@@ -173,6 +173,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// thread-block cluster helpers (split-K inside a cluster, partial sums exchanged through distributed shared memory)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 16-byte store into a peer CTA's shared memory that completes 16 transaction bytes on the peer's mbarrier `rbar`
+__device__ __forceinline__ void st_async_f4(uint32_t raddr, float a, float b, float c, float d, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(raddr),
+               "f"(a), "f"(b), "f"(c), "f"(d), "r"(rbar)
+               : "memory");
+}
+
 // UMMA shared-memory matrix descriptor for a K-major tile whose rows are one swizzle atom wide
 // (BLOCK_K * 2 bytes == swizzle bytes): SBO = 8 rows * swizzle bytes, LBO unused, version 1 (sm_100).
 template <int SWIZZLE_BYTES>
@@ -493,7 +514,11 @@ struct EpiVit {
 // TERMS > 1 (fp32-equivalent GEMMs of the fp32-activation prefill): operand A holds TERMS bf16 terms of a split fp32
 // matrix side by side ([R][TERMS * Kw], term t of K block kb at column (t * g.bwrap + kb) * 64); a stage carries the TERMS A
 // tiles of one K block and ONE B tile, multiplied TERMS times - the weight tile is fetched once per K block, not per term.
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128, int KSUB = 1, int TERMS = 1>
+// CK > 1: the CK CTAs of a cluster (1, 1, CK) share one output tile and split its K range (g.ksplit == CK); after the mainloop
+// CTA r finalises columns [r, r + 1) * BLOCK_N / CK: the others send it their partial accumulators with st.async (data +
+// transaction-count completion on the owner's mbarrier) into the idle stage ring, the owner adds the CK partials in rank order
+// (deterministic) and runs the epilogue on complete sums - every element keeps one owner and there are no float atomics.
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128, int KSUB = 1, int TERMS = 1, int CK = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape g,
                const typename Epi::Params ep) {
@@ -512,7 +537,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* xbar = tmem_full + 1;  // CK > 1: completes when the peers' partial sums of this CTA's columns have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 1);
+  static_assert(CK == 1 || (TILE_M == 128 && (BLOCK_N / CK) % 16 == 0 && BLOCK_N % CK == 0), "cluster split-K tile shape");
+  static_assert(CK == 1 || (size_t)(CK - 1) * 128 * (BLOCK_N / CK + 4) * 4 <= (size_t)STAGES * STAGE_BYTES,
+                "the receive buffer aliases the stage ring");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TILE_M, n0 = blockIdx.y * BLOCK_N;
@@ -531,6 +560,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&empty[s], 1);
     }
     mbar_init(tmem_full, 1);
+    if (CK > 1) {
+      mbar_init(xbar, 1);
+      mbar_expect_tx(xbar, (uint32_t)((CK - 1) * 128 * (BLOCK_N / CK) * 4));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -541,6 +574,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (CK > 1) cluster_sync_all();  // every peer's exchange barrier is initialised and armed before anything can reach it
 
   // NOTE: triggering the dependent grid BEFORE this grid's own griddepcontrol.wait was measured to break the chain
   // (the dependent's wait then no longer covers our prerequisite); the trigger is issued after the wait, below.
@@ -610,6 +644,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (g.pdl & 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     mbar_wait(tmem_full, 0);
     tcgen05_fence_after();
+  }
+  if constexpr (CK > 1) {
+    // all MMAs of all CTAs of the cluster have completed (the epilogue warps arrive after their accumulator wait): the stage
+    // rings are idle and may receive partial sums
+    cluster_sync_all();
+    if (warp >= 2) {
+      constexpr int OWN = BLOCK_N / CK, RST = OWN + 4;  // columns finalised per CTA; receive row stride (floats, conflict-free)
+      float* recv = reinterpret_cast<float*>(smem);     // [CK - 1 senders in rank order][128 rows][RST]
+      const uint32_t my = cluster_ctarank();
+      const int q = warp & 3, row = q * 32 + lane, m = m0 + row;
+      constexpr int kChunks = BLOCK_N / 16, kHalf = (kChunks + 1) / 2;
+      const int c_begin = (warp - 2) < 4 ? 0 : kHalf * 16, c_end = (warp - 2) < 4 ? kHalf * 16 : BLOCK_N;
+      const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; c += 16) {
+        const uint32_t owner = (uint32_t)(c / OWN);
+        if (owner == my) continue;
+        float v[16];
+        tmem_ld16(tq + c, v);
+        const uint32_t slot = my < owner ? my : my - 1;
+        const uint32_t ra = mapa_u32(smem_u32(recv + ((size_t)slot * 128 + row) * RST + (c % OWN)), owner);
+        const uint32_t rb = mapa_u32(smem_u32(xbar), owner);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) st_async_f4(ra + 4 * i, v[i], v[i + 1], v[i + 2], v[i + 3], rb);
+      }
+      mbar_wait(xbar, 0);
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; c += 16) {
+        if ((uint32_t)(c / OWN) != my) continue;
+        float own[16], v[16];
+        tmem_ld16(tq + c, own);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+#pragma unroll
+        for (uint32_t r = 0; r < (uint32_t)CK; ++r) {  // rank order: the sum does not depend on arrival order
+          if (r == my) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += own[i];
+          } else {
+            const float* src = recv + ((size_t)(r < my ? r : r - 1) * 128 + row) * RST + (c % OWN);
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const uint4 o = lds_u4(src + i);
+              v[i] += __uint_as_float(o.x); v[i + 1] += __uint_as_float(o.y);
+              v[i + 2] += __uint_as_float(o.z); v[i + 3] += __uint_as_float(o.w);
+            }
+          }
+        }
+        Epi::apply(ep, b, phase, m, n0 + c, v);
+      }
+    }
+  } else if (warp >= 2) {
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
     // M=128: accumulator row i sits in lane i.  M=64: rows 16q..16q+15 sit in lanes 32q..32q+15 (half-filled quadrants)
     const int m = TILE_M == 128 ? m0 + q * 32 + lane : m0 + q * 16 + lane;
@@ -1481,13 +1567,14 @@ bool tc_make_map_kblocks(void* map, const void* base, uint64_t K, uint64_t rows,
   return make_map_kblocks(static_cast<CUtensorMap*>(map), base, K, rows, outer, row_stride_el, outer_stride_el, box_rows, nblk);
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128, int KSUB = 1, int TERMS = 1>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int TILE_M = 128, int KSUB = 1, int TERMS = 1, int CK = 1>
 static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcShape& g, const typename Epi::Params& ep,
                              int m_tiles, int n_tiles, cudaStream_t st) {
   constexpr int smem = STAGES * KSUB * (TERMS * TILE_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
   static_assert(smem <= 227 * 1024, "stage ring exceeds shared memory");
   if (KSUB > 1 && g.ntaps != 1) return cudaErrorInvalidValue;
-  auto kern = gemm_tc_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, TILE_M, KSUB, TERMS>;
+  if (CK > 1 && g.ksplit != CK) return cudaErrorInvalidValue;
+  auto kern = gemm_tc_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, TILE_M, KSUB, TERMS, CK>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1499,11 +1586,20 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr1[1];
-  attr1[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr1[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr1[2];
+  int na = 0;
+  if (g.pdl) {
+    attr1[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr1[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (CK > 1) {
+    attr1[na].id = cudaLaunchAttributeClusterDimension;
+    attr1[na].val.clusterDim.x = 1; attr1[na].val.clusterDim.y = 1; attr1[na].val.clusterDim.z = CK;
+    ++na;
+  }
   cfg.attrs = attr1;
-  cfg.numAttrs = g.pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, g, ep);
 }
 template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int KSUB = 1>
@@ -1654,6 +1750,8 @@ cudaError_t launch_decode_fused_bf16(const FusedStepArgs& a, const void* wqkv, c
                                             : launch_decode_fused_t<128>(a, wqkv, wo, w13, w2, w_heads, st);
 }
 
+static int mt_for(int R) { return (R + kTileM - 1) / kTileM; }
+
 // Linear layer of the bf16 sampler path: out = A[R][K] (bf16) x W[N][K]^T (bf16) with a fused epilogue.
 cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st) {
   if (a.K % 64 != 0 || a.N % a.block_n != 0) return cudaErrorInvalidValue;
@@ -1677,6 +1775,31 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st) {
   ep.pos0 = a.pos0; ep.npos = a.npos; ep.layer = a.layer; ep.d_model = a.d_model; ep.atomic = g.ksplit > 1;
   ep.aux = a.aux;
   const int mt = (a.R + tile_m - 1) / tile_m, nt = a.N / a.block_n;
+  if (split3 && a.ksplit == 0 && (a.epi != EPI_STORE || a.perm_S == 0)) {
+    // auto: when the tiles of this GEMM cover less than half of the SMs (prompt prefill: one or two row tiles), split K over
+    // clusters of 4 or 2 CTAs (partial sums through DSMEM, rank-ordered: deterministic) and widen the 1536-wide tiles
+    static int ck_on = -1;
+    if (ck_on < 0) { const char* e = getenv("VAURA_PREFILL_CK"); ck_on = !(e && e[0] == '0'); }
+    const int bn = a.N % 256 == 0 && a.N >= 4096 ? 256 : (a.N % 128 == 0 ? 128 : 0);
+    const int kb = wk / 64;
+    if (ck_on && bn) {
+      const int tiles = mt_for(a.R) * (a.N / bn);
+      // a B200 co-schedules 33 clusters of 4 CTAs that need a whole SM each (profiles/probes/cluster_occ.cu): more would run
+      // as a second wave
+      const int ck = (tiles <= 32 && kb >= 8) ? 4 : ((tiles * 2 <= 148 && kb >= 4) ? 2 : 1);
+      if (ck > 1) {
+        CUtensorMap tb2;
+        if (!make_map(&tb2, a.W, wk, a.N, 1, wk, (uint64_t)a.N * wk, 64, bn, false)) return cudaErrorUnknown;
+        g.ksplit = ck;
+        ep.atomic = 0;
+        const int nt2 = a.N / bn;
+        if (bn == 256 && ck == 4) return launch_tc<256, 64, 2, 1, EpiLinear, 128, 1, 3, 4>(ta, tb2, g, ep, mt, nt2, st);
+        if (bn == 256 && ck == 2) return launch_tc<256, 64, 2, 1, EpiLinear, 128, 1, 3, 2>(ta, tb2, g, ep, mt, nt2, st);
+        if (bn == 128 && ck == 4) return launch_tc<128, 64, 3, 1, EpiLinear, 128, 1, 3, 4>(ta, tb2, g, ep, mt, nt2, st);
+        return launch_tc<128, 64, 3, 1, EpiLinear, 128, 1, 3, 2>(ta, tb2, g, ep, mt, nt2, st);
+      }
+    }
+  }
   if (split3) {
     if (g.ksplit != 1) return cudaErrorInvalidValue;
     switch (a.block_n) {  // stage = 3 x 16 KB of A + the weight tile
