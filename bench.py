@@ -316,7 +316,11 @@ def main():
         tokens_only()
         ms_tok = timed(tokens_only, 3, collective=False) / 3
         nsteps = w["T"] + 8
-        k_ms = ms_tok / nsteps
+        # the step kernel's average launch duration: CUDA events recorded inside vaura_sampler_generate right around the step
+        # launches of the last call (the whole-call time ms_tok / nsteps also carries the first pass and the host glue of
+        # generate(): ~1 ms per call; it is reported next to it as us_per_step_whole_call)
+        loop_ms, loop_steps = model.sampler.last_loop_ms()
+        k_ms = loop_ms / loop_steps if loop_steps > 0 else ms_tok / nsteps
         bf16 = rows >= 16 or (rows >= 3 and sampling)
         kv_el = 2 if bf16 else 4
         kv_bytes = d.num_layers * 2 * d.d_model * kv_el * rows * nsteps / 2  # K/V read at the mean context (S/2 positions)
@@ -336,6 +340,8 @@ def main():
         ach = alg / (k_ms * 1e-3) / 1e9
         roof = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic_tab.get(key), "peak_source": peak_src, "us_per_launch": k_ms * 1e3,
+                "launches_timed": loop_steps, "us_per_step_whole_call": ms_tok / nsteps * 1e3,
+                "frac_whole_call": alg / (ms_tok / nsteps * 1e-3) / 1e9 / peak,
                 "algorithmic_bytes_per_launch": alg,
                 "algorithmic_bytes": f"weights {step_bytes} + K/V read {int(kv_bytes)} (24 layers x 2 x 1536 x {kv_el} B x "
                                      f"{rows} rows x mean context {nsteps // 2})"}

@@ -183,6 +183,11 @@ int vaura_sample_logits(const float* logits, int32_t rows, int32_t K, int32_t V,
                         uint64_t seed, const int32_t* clip_ids, int32_t offset, int32_t* tokens_out,
                         float* probs_out, void* stream);
 
+/* Device time of the decode-step launches of the last vaura_sampler_generate call on this handle: CUDA events recorded on
+ * the caller's stream right before the first and right after the last step launch (first pass, memsets and host glue are
+ * outside).  Synchronises on the second event.  Used by bench.py for the step kernel's average launch duration. */
+int vaura_sampler_last_loop_ms(vaura_sampler* s, float* ms_out, int32_t* steps_out);
+
 /* ---- codec decode, replaces DacModelWrapper.decode (models/modules/dac/model.py:41-48) ------------ */
 typedef struct {
   int32_t latent_dim;    /* 1024 */

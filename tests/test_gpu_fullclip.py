@@ -186,3 +186,46 @@ def test_philox_stream_id_separates_calls():
     toks, probs = sample_logits(logits.cuda(), temp=1.0, top_k=32, seed=7, offset=3, return_probs=True)
     u = vo.philox_uniform(7, 0, 3, 0, stream_id=0)
     assert vo.inverse_cdf_draw(probs[0, 0].cpu().numpy(), u) == int(toks[0, 0])
+
+
+def test_opt_in_fused2_step_kernel_matches_default_step_kernel(tmp_path):
+    """decode_step_fused2 (VAURA_FUSED2=1; parity-green but slower, profiles/r02_fused2_timeline.summary.txt) is selected once
+    per process, so it runs in a child process: greedy tokens of a 40-token, 16-clip generate against the default kernel's in
+    this process, and its logits against the default kernel's within the bf16 tolerance."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "fused2_child.py"
+    out = tmp_path / "fused2.pt"
+    script.write_text(
+        "import sys, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from vaura_b200.synthetic import FULL_CODEC, FULL_SAMPLER, build_model, make_avclip_features\n"
+        "m = build_model(FULL_SAMPLER, FULL_CODEC)\n"
+        "o = m.generate(frames=make_avclip_features(16, 77).cuda(), max_new_tokens=40, use_sampling=False, prompt_is_encoded=True,\n"
+        "               return_sampled_indices=True, _return_logits=True, _decode_audio=False)\n"
+        f"torch.save({{'codes': o['sampled_indices'].cpu(), 'logits': o['_logits'].cpu()}}, {str(out)!r})\n")
+    res = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, VAURA_FUSED2=flag)
+        r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[flag] = torch.load(out)
+    a, b = res["0"], res["1"]
+    la, lb = a["logits"][1:], b["logits"][1:]                      # (S-1, B, K, V): logits of the step that samples column s
+    # greedy histories may part at a near-tie; logits are comparable up to and including the first step whose tokens differ
+    seq_a, _ = vo.build_pattern_sequence(a["codes"], 1024)
+    seq_b, _ = vo.build_pattern_sequence(b["codes"], 1024)
+    same = (seq_a == seq_b).all(dim=1)[:, 1:]                      # (B, S-1) column s equal in both runs
+    worst, full = 0.0, 0
+    for clip in range(same.shape[0]):
+        diff = (~same[clip]).nonzero()
+        upto = int(diff[0]) + 1 if len(diff) else same.shape[1]
+        full += int(len(diff) == 0)
+        e = (la[:upto, clip] - lb[:upto, clip]).abs().amax(dim=(1, 2)) / la[:upto, clip].abs().amax(dim=(1, 2))
+        worst = max(worst, float(e.max()))
+    print(f"[fused2 vs fused] max per-step logit difference {worst:.3e} of max |logit| on common histories; "
+          f"{full} of {same.shape[0]} clips identical over 40 tokens")
+    assert worst < 2 * BF16_LOGIT_TOL, worst
+    assert full >= same.shape[0] // 2

@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(HERE, "_lib", "libvaura_b200.so")
 EXPORTS = [
     "vaura_version", "vaura_arch", "vaura_last_error", "vaura_launch_count", "vaura_gemv_bf16w", "vaura_linear_bf16",
     "vaura_sampler_create", "vaura_sampler_destroy", "vaura_sampler_cond_project",
-    "vaura_sampler_workspace_bytes", "vaura_sampler_generate", "vaura_sampler_forward", "vaura_sample_logits",
+    "vaura_sampler_workspace_bytes", "vaura_sampler_generate", "vaura_sampler_last_loop_ms", "vaura_sampler_forward",
+    "vaura_sample_logits",
     "vaura_codec_create", "vaura_codec_destroy", "vaura_codec_workspace_bytes", "vaura_codec_decode",
     "vaura_codec_encoder_create", "vaura_codec_encoder_destroy", "vaura_codec_encoder_workspace_bytes", "vaura_codec_encode",
     "vaura_avclip_create", "vaura_avclip_destroy", "vaura_avclip_workspace_bytes", "vaura_avclip_forward",
@@ -91,6 +92,7 @@ def load():
     lib.vaura_sampler_workspace_bytes.restype = C.c_size_t
     lib.vaura_sampler_generate.argtypes = [C.c_void_p, C.POINTER(GenerateParamsC), C.POINTER(KvCacheC), C.c_void_p,
                                            C.c_size_t, C.c_void_p]
+    lib.vaura_sampler_last_loop_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.vaura_sampler_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                           C.POINTER(KvCacheC), C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.vaura_sample_logits.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32,

@@ -528,6 +528,11 @@ vit_space_attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* _
 // ------------------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------------------
+static int device_slot() {  // shared-memory opt-in is a per-device function attribute
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
+}
 cudaError_t launch_vit_patchify(const float* frames, void* A, int S, int C, int T, int H, int W, int tub, int ps, cudaStream_t st) {
   if (ps % 8 || W % 8 || H % ps || W % ps || T % tub) return cudaErrorInvalidValue;
   const size_t total = (size_t)S * (T / tub) * (H / ps) * (W / ps) * (C * tub * ps * ps / 8);
@@ -570,11 +575,12 @@ cudaError_t launch_vit_time_attn(const void* qkv, void* out, int S, int t, int n
 }
 cudaError_t launch_vit_cls_attn(const void* qkv, void* out, int seqs, int len, int heads, int out_rows_per_seq, cudaStream_t st) {
   const size_t smem = (96 + 2048 + (size_t)len) * 4;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {false};
+  const int slot = device_slot();
+  if (!attr[slot]) {
     cudaError_t e = cudaFuncSetAttribute(vit_cls_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr[slot] = true;
   }
   if (smem > 96 * 1024) return cudaErrorInvalidValue;
   vit_cls_attn_kernel<<<dim3(heads, seqs), kClsThreads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
@@ -587,22 +593,24 @@ cudaError_t launch_vit_space_attn(const void* qkv, void* out, int S, int t, int 
   if (simt < 0) { const char* e = getenv("VAURA_AVCLIP_SIMT_ATTN"); simt = e && e[0] == '1'; }
   if (!simt && n + 1 <= 16 * 13 && n + 1 > 16 * 12) {  // 14 x 14 patches + CLS = 197 keys
     using G = SpTc<13>;
-    static bool attr_tc = false;
-    if (!attr_tc) {
+    static bool attr_tc[64] = {false};
+    const int slot = device_slot();
+    if (!attr_tc[slot]) {
       cudaError_t e = cudaFuncSetAttribute(vit_space_attn_tc_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
       if (e != cudaSuccess) return e;
-      attr_tc = true;
+      attr_tc[slot] = true;
     }
     vit_space_attn_tc_kernel<13><<<dim3(heads, t, S), kSpTcThreads, G::smem, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), t, n, heads, 0.125f);
     return cudaGetLastError();
   }
   const size_t smem = space_attn_smem(n);
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {false};
+  const int slot = device_slot();
+  if (!attr[slot]) {
     cudaError_t e = cudaFuncSetAttribute(vit_space_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr[slot] = true;
   }
   if (smem > 100 * 1024) return cudaErrorInvalidValue;
   vit_space_attn_kernel<<<dim3(heads, t, S), kSpThreads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),

@@ -55,6 +55,8 @@ struct vaura_sampler {
   unsigned long long graph_nodes = 0;    // kernel nodes of graph_exec
   cudaStream_t capture_stream = nullptr; // capture origin only (the legacy default stream cannot be captured);
                                          // nothing ever executes on it, graphs are launched on the caller's stream
+  cudaEvent_t loop_ev[2] = {nullptr, nullptr};  // recorded on the caller's stream around the decode-step launches of the
+  int loop_steps = 0;                           // last generate() call (vaura_sampler_last_loop_ms)
 };
 
 extern "C" int vaura_version(void) { return 1; }
@@ -118,6 +120,7 @@ extern "C" void vaura_sampler_destroy(vaura_sampler* s) {
   if (!s) return;
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
+  for (cudaEvent_t e : s->loop_ev) if (e) cudaEventDestroy(e);
   delete s;
 }
 
@@ -524,6 +527,13 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   if (ws.bytes > workspace_bytes) return fail(VAURA_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
   cudaStream_t st = (cudaStream_t)stream;
   const KvView kvv = kv_view(kv, d.nhead);
+  // CUDA events on the caller's stream around the decode-step launches alone (first pass, memsets and host glue outside):
+  // what bench.py divides by the step count for the step kernel's average launch duration
+  auto loop_mark = [&](int which, int nsteps_) {
+    if (!s->loop_ev[which] && cudaEventCreate(&s->loop_ev[which]) != cudaSuccess) { s->loop_ev[which] = nullptr; return; }
+    cudaEventRecord(s->loop_ev[which], st);
+    s->loop_steps = nsteps_;
+  };
 
   SampleArgs sa{};
   sa.logits = ws.logits; sa.sequence = p->sequence; sa.logits_out = p->logits_out; sa.clip_ids = p->clip_ids;
@@ -593,11 +603,13 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
       { const char* tu = getenv("VAURA_CLUSTER_TAIL_UNITS"); pa.tail_units = tu ? atoi(tu) : 0; }
       CU(cudaMemsetAsync(ws.xfix, 0, cluster_xfix_bytes(rows, d.num_layers), st));
     }
+    loop_mark(0, nsteps);
     for (int i = 0; i < nsteps; ++i) {
       if (use_cluster) CUL(launch_decode_cluster(pa, rows, st));
       else if (use_tc) CUL(launch_decode_persistent_tc(pa, rows, st));
       else CUL(launch_decode_persistent(pa, rows, st));
     }
+    loop_mark(1, nsteps);
     return VAURA_OK;
   }
   if (precision == VAURA_PRECISION_BF16 && ws.f2)  // decode_step_fused2: arrival counters of the w2 K thirds start at 0
@@ -609,10 +621,12 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   key.p = *p; key.kv = *kv; key.workspace = workspace; key.precision = precision;
   cudaGetDevice(&key.device);
   if (s->graph_exec && s->graph_key == key) {
+    loop_mark(0, nsteps);
     for (int i = 0; i < nsteps; ++i) {
       CU(cudaGraphLaunch(s->graph_exec, st));
       g_launches += s->graph_nodes;
     }
+    loop_mark(1, nsteps);
     return VAURA_OK;
   }
   cudaGraph_t graph = nullptr;
@@ -639,10 +653,21 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   if (ce != cudaSuccess) return fail(VAURA_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
   s->graph_key = key;
   s->graph_nodes = g_capture_nodes;
+  loop_mark(0, nsteps);
   for (int i = 0; i < nsteps; ++i) {
     CU(cudaGraphLaunch(s->graph_exec, st));
     g_launches += s->graph_nodes;
   }
+  loop_mark(1, nsteps);
+  return VAURA_OK;
+}
+
+extern "C" int vaura_sampler_last_loop_ms(vaura_sampler* s, float* ms_out, int32_t* steps_out) {
+  if (!s || !ms_out || !steps_out) return fail(VAURA_ERR_INVALID, "null argument");
+  if (!s->loop_ev[0] || !s->loop_ev[1] || s->loop_steps <= 0) return fail(VAURA_ERR_INVALID, "no generate() call has run its step loop yet");
+  CU(cudaEventSynchronize(s->loop_ev[1]));
+  CU(cudaEventElapsedTime(ms_out, s->loop_ev[0], s->loop_ev[1]));
+  *steps_out = s->loop_steps;
   return VAURA_OK;
 }
 

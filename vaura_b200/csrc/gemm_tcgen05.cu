@@ -218,6 +218,8 @@ struct TcShape {
                                // prerequisite grid has finished, everything else waits on griddepcontrol
   int bwrap;                   // > 0: operand B has only this many K blocks; block kb of the K loop reads block kb % bwrap
                                // (A = several bf16 terms of a split fp32 operand side by side, see LinearTcArgs::w_k)
+  int n_fastest;               // persistent kernel: consecutive tiles walk N first (CTAs that run at the same time share the
+                               // activation rows in L2: the operand that does not fit when M is 10^4..10^6 rows)
   int tap_off[32];             // [nphase][ntaps] row shift of the A box
 };
 
@@ -775,10 +777,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 
   // tile -> (m0, n0, batch, phase); m fastest so that neighbouring CTAs share the weight tile in L2
   auto tile_coords = [&](int t, int& m0, int& n0, int& b, int& phase) {
-    m0 = (t % m_tiles) * TILE_M;
-    const int r = t / m_tiles;
-    n0 = (r % n_tiles) * BLOCK_N;
-    const int zz = r / n_tiles;
+    int zz;
+    if (g.n_fastest) {
+      n0 = (t % n_tiles) * BLOCK_N;
+      const int r = t / n_tiles;
+      m0 = (r % m_tiles) * TILE_M;
+      zz = r / m_tiles;
+    } else {
+      m0 = (t % m_tiles) * TILE_M;
+      const int r = t / m_tiles;
+      n0 = (r % n_tiles) * BLOCK_N;
+      zz = r / n_tiles;
+    }
     b = zz / g.nphase;
     phase = zz % g.nphase;
   };
@@ -1513,6 +1523,14 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pp.tmem_base), "r"(kAccCols));
 }
 
+// One-time per-device set-up of a kernel (dynamic shared-memory opt-in is a per-device function attribute): a process that
+// drives several GPUs must repeat it on each of them.  Returns the device ordinal clamped into the table.
+static int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
@@ -1575,11 +1593,12 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const
   if (KSUB > 1 && g.ntaps != 1) return cudaErrorInvalidValue;
   if (CK > 1 && g.ksplit != CK) return cudaErrorInvalidValue;
   auto kern = gemm_tc_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, TILE_M, KSUB, TERMS, CK>;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {false};
+  const int slot = current_device_slot();
+  if (!attr[slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr[slot] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(m_tiles, n_tiles, g.batch * g.nphase * g.ksplit);
@@ -1609,14 +1628,16 @@ static cudaError_t launch_tc_persistent(const CUtensorMap& ta, const CUtensorMap
   static_assert(smem <= 227 * 1024, "stage ring exceeds shared memory");
   if (g.kblocks % KSUB) return cudaErrorInvalidValue;
   auto kern = gemm_tc_persistent_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, KSUB>;
-  static int sms = 0;
-  if (!sms) {
+  static int sms_tab[64] = {0};
+  const int slot = current_device_slot();
+  if (!sms_tab[slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&sms_tab[slot], cudaDevAttrMultiProcessorCount, dev);
   }
+  const int sms = sms_tab[slot];
   const int ntiles = m_tiles * n_tiles * g.batch * g.nphase;
   kern<<<dim3(ntiles < sms ? ntiles : sms), dim3(kGemmThreads), smem, st>>>(ta, tb, g, ep, m_tiles, n_tiles);
   return cudaGetLastError();
@@ -1689,17 +1710,20 @@ bool fused_step_supported(int R, int D, int F, int NH) {
 template <int TM>
 static cudaError_t launch_decode_fused_t(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
                                          const void* w_heads, cudaStream_t st) {
-  static int sms = 0;
-  if (!sms) {
+  static int sms_tab[64] = {0};
+  const int slot = current_device_slot();
+  if (!sms_tab[slot]) {
     cudaError_t e = cudaFuncSetAttribute(decode_step_fused_bf16<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::kSmem);
     if (e != cudaSuccess) return e;
-    int dev = 0, occ = 0;
+    int dev = 0, occ = 0, n = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_step_fused_bf16<TM>, kGemmThreads, fused::kSmem);
     if (e != cudaSuccess) return e;
-    if (occ < 1) { sms = 0; return cudaErrorLaunchOutOfResources; }
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    sms_tab[slot] = n;
   }
+  const int sms = sms_tab[slot];
   const int need = a.D / 64 * (a.wo_ksplit > a.w2_ksplit ? a.wo_ksplit : a.w2_ksplit);
   // one tile per CTA per phase, one residual row per CTA in the norm phases
   if (3 * a.D / 32 > sms || 2 * a.F / 64 > sms || need > sms || a.R > sms) return cudaErrorInvalidValue;
@@ -1840,6 +1864,11 @@ cudaError_t launch_vit_linear(const VitLinearArgs& a, cudaStream_t st) {
   if (!make_map(&tb, a.W, a.K, a.N, 1, a.K, (uint64_t)a.N * a.K, 64, bn, false)) return cudaErrorUnknown;
   TcShape g{};
   g.ntaps = 1; g.nphase = 1; g.kblocks = a.K / 64; g.batch = 1; g.ksplit = 1; g.pdl = 0;
+  {
+    static int nf = -1;  // VAURA_AVCLIP_M_FASTEST=1: the codec's tile order (A/B measurement)
+    if (nf < 0) { const char* e = getenv("VAURA_AVCLIP_M_FASTEST"); nf = !(e && e[0] == '1'); }
+    g.n_fastest = nf;
+  }
   EpiVit::Params ep{};
   ep.mode = a.mode; ep.gelu = a.gelu; ep.M = a.M; ep.N = a.N; ep.ldo = a.ldo; ep.bias = a.bias;
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16); ep.out_f32 = a.out_f32; ep.pos = a.pos;

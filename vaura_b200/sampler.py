@@ -118,6 +118,13 @@ class Transformer(torch.nn.Module):
         except Exception:
             pass
 
+    def last_loop_ms(self):
+        """(ms, steps) of the decode-step launches of the last generate call: CUDA events recorded inside
+        ``vaura_sampler_generate`` around the step launches alone (include/vaura_b200.h: vaura_sampler_last_loop_ms)."""
+        ms, steps = C.c_float(), C.c_int32()
+        _cabi.check(_cabi.load().vaura_sampler_last_loop_ms(self.handle(), C.byref(ms), C.byref(steps)), "vaura_sampler_last_loop_ms")
+        return float(ms.value), int(steps.value)
+
     def handle(self):
         if self.weights is None:
             raise RuntimeError("sampler weights are not loaded (load_state_dict / load_from_checkpoint first)")
