@@ -228,4 +228,10 @@ def test_opt_in_fused2_step_kernel_matches_default_step_kernel(tmp_path):
     print(f"[fused2 vs fused] max per-step logit difference {worst:.3e} of max |logit| on common histories; "
           f"{full} of {same.shape[0]} clips identical over 40 tokens")
     assert worst < 2 * BF16_LOGIT_TOL, worst
-    assert full >= same.shape[0] // 2
+    # tokens on common histories: with flat random-init logits a near-tie flips now and then (0.6 % of the cells against the
+    # fp32 oracle, test_fused_bf16_step_full_clip_64_rows), after which the two greedy runs are different sequences
+    agree = (la.argmax(-1) == lb.argmax(-1))                        # (S-1, B, K)
+    prefix = torch.stack([torch.cat([torch.ones(1, dtype=torch.bool), same[c].cumprod(0).bool()[:-1]]) for c in range(same.shape[0])], 1)
+    rate = float(agree[prefix[:, :, None].expand_as(agree)].float().mean())
+    print(f"[fused2 vs fused] argmax agreement on common histories {rate:.4f}")
+    assert rate >= 0.97, rate

@@ -728,8 +728,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // KSUB > 1: a stage holds KSUB K blocks of each operand (KSUB activation sub-tiles, then KSUB weight sub-tiles), loaded by
 // ONE 4-D tensor box per operand (maps from make_map_kblocks) - for channel counts that force a narrow K block (Cin = 96:
 // 32-wide blocks) the copies and barrier round trips per tap drop from 3 to 1.
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int KSUB = 1>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// OCC = 2: two CTAs per SM (half the ring each, 2 x 2 accumulator buffers of <= 128 TMEM columns): for the narrow layers whose
+// tiles are paced by the serial work of one producer / MMA / epilogue chain rather than by bytes in flight.
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int KSUB = 1, int OCC = 1>
+__global__ void __launch_bounds__(kGemmThreads, OCC)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape g,
                           const typename Epi::Params ep, const int m_tiles, const int n_tiles) {
   constexpr int SW = BLOCK_K * 2;
@@ -737,6 +739,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   constexpr int A_BYTES = TILE_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, STAGE_BYTES = KSUB * (A_BYTES + B_BYTES);
   constexpr int ACC_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;  // per accumulator buffer
   constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static_assert(OCC * TMEM_COLS <= 512, "the co-resident CTAs share the SM's 512 TMEM columns");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "stage buffers must stay 1024B aligned for the swizzle");
 
   extern __shared__ uint8_t smem_raw[];
@@ -1621,13 +1624,13 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const
   cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, g, ep);
 }
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int KSUB = 1>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int KSUB = 1, int OCC = 1>
 static cudaError_t launch_tc_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const TcShape& g,
                                         const typename Epi::Params& ep, int m_tiles, int n_tiles, cudaStream_t st) {
   constexpr int smem = STAGES * KSUB * (kTileM * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
-  static_assert(smem <= 227 * 1024, "stage ring exceeds shared memory");
+  static_assert(OCC * (smem + 1024) <= 227 * 1024, "stage ring exceeds shared memory");
   if (g.kblocks % KSUB) return cudaErrorInvalidValue;
-  auto kern = gemm_tc_persistent_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, KSUB>;
+  auto kern = gemm_tc_persistent_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, KSUB, OCC>;
   static int sms_tab[64] = {0};
   const int slot = current_device_slot();
   if (!sms_tab[slot]) {
@@ -1639,7 +1642,7 @@ static cudaError_t launch_tc_persistent(const CUtensorMap& ta, const CUtensorMap
   }
   const int sms = sms_tab[slot];
   const int ntiles = m_tiles * n_tiles * g.batch * g.nphase;
-  kern<<<dim3(ntiles < sms ? ntiles : sms), dim3(kGemmThreads), smem, st>>>(ta, tb, g, ep, m_tiles, n_tiles);
+  kern<<<dim3(ntiles < OCC * sms ? ntiles : OCC * sms), dim3(kGemmThreads), smem, st>>>(ta, tb, g, ep, m_tiles, n_tiles);
   return cudaGetLastError();
 }
 
@@ -1681,6 +1684,10 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cu
     if (!make_map_kblocks(&ta4, a.in, a.Cin, a.Tin, B, a.Cin, (uint64_t)a.Tin * a.Cin, kTileM, 3, 32, true) ||
         !make_map_kblocks(&tb4, a.W, a.Cin, a.Cout, (uint64_t)a.ntaps * a.nphase, a.Cin, (uint64_t)a.Cout * a.Cin, bn, 3, 32, true))
       return cudaErrorUnknown;
+    static int occ2 = -1;  // VAURA_CONV_OCC2=1: two CTAs per SM for the 96-channel layers (measured neutral: 9.58 vs 9.54 ms per
+                           // 16 clips - these layers are bound by bytes in flight per SM, not by the per-CTA serial chain)
+    if (occ2 < 0) { const char* e = getenv("VAURA_CONV_OCC2"); occ2 = (e && e[0] == '1'); }
+    if (bn == 96 && occ2) return launch_tc_persistent<96, 32, 2, 0, EpiConv, 3, 2>(ta4, tb4, g, ep, mt, nt, st);
     if (bn == 96) return launch_tc_persistent<96, 32, 4, 0, EpiConv, 3>(ta4, tb4, g, ep, mt, nt, st);
     if (bn == 32) return launch_tc_persistent<32, 32, 4, 0, EpiConv, 3>(ta4, tb4, g, ep, mt, nt, st);
     return launch_tc_persistent<16, 32, 4, 0, EpiConv, 3>(ta4, tb4, g, ep, mt, nt, st);
@@ -1689,6 +1696,11 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cu
   if (bn == BN && bk == BK)                                                                                    \
     return persistent ? launch_tc_persistent<BN, BK, ST, 0, EpiConv>(ta, tb, g, ep, mt, nt, st)                \
                       : launch_tc<BN, BK, ST, 0, EpiConv>(ta, tb, g, ep, mt, nt, st);
+  {
+    static int occ2b = -1;
+    if (occ2b < 0) { const char* e = getenv("VAURA_CONV_OCC2"); occ2b = (e && e[0] == '1'); }
+    if (persistent && occ2b && bn == 96 && bk == 64) return launch_tc_persistent<96, 64, 3, 0, EpiConv, 1, 2>(ta, tb, g, ep, mt, nt, st);
+  }
   TC_CASE(256, 64, 4)
   TC_CASE(192, 64, 4)
   TC_CASE(128, 64, 6)
