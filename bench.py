@@ -480,6 +480,39 @@ def main():
                                         "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)",
                                         "algorithmic_flops": tf * 1e12}}}
 
+    # ---- DAC encode: 64 x 2.56 s of audio -> codes, waveforms from pinned host memory ----------------------------
+    def encode_record(steps):
+        from vaura_b200.synthetic import make_codec_state_dict
+        from vaura_b200.weights import codec_encoder_flops
+        enc = model.audio_encoder
+        if enc._enc_blob is None:
+            enc.load_state_dict(make_codec_state_dict(FULL_CODEC, 100, with_encoder=True), device=str(dev))
+        nb, L = 64, 220 * FULL_CODEC.hop_length
+        wav_h = (0.3 * torch.randn(nb, 1, L, generator=torch.Generator().manual_seed(6))).pin_memory()
+        codes_h = torch.empty(nb, FULL_CODEC.n_codebooks, 220, dtype=torch.int64).pin_memory()
+
+        def e2e_step():
+            c = enc.encode(wav_h.to(dev, non_blocking=True))
+            codes_h.copy_(c, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        e2e_step()
+        ms_s = timed(e2e_step, steps, collective=False) / steps
+        wav_d = wav_h.to(dev)
+        ms_k = timed(lambda: enc.encode(wav_d), steps, collective=False) / steps
+        tf = codec_encoder_flops(FULL_CODEC, L) * nb / 1e12
+        pk = 1434.4
+        pf = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pf):
+            pk = json.load(open(pf)).get("bf16_tflops_sustained", pk)
+        return {"workload": "64 x 2.56 s of 44.1 kHz audio -> 9 x 220 codes (DAC encoder + residual VQ)",
+                "e2e_ms_per_batch": ms_s, "audio_s_per_s": nb * 220 * AUDIO_SEC_PER_TOKEN / (ms_s / 1e3),
+                "h2d_bytes_per_step": wav_h.numel() * 4, "d2h_bytes_per_step": codes_h.numel() * 8,
+                "roofline": {"kernel": "gemm_tc_persistent_kernel<.., EpiConv> implicit-GEMM convolutions of the encoder + "
+                                       "enc_conv_in_kernel + rvq_encode_kernel: whole encode", "bound": "tensor",
+                             "achieved": tf / (ms_k / 1e3), "peak": pk, "unit": "TFLOP/s", "frac": tf / (ms_k / 1e3) / pk,
+                             "traffic": None, "ms_resident": ms_k, "algorithmic_flops": tf * 1e12,
+                             "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"}}
+
     if args.workload == "long_b1":
         for _ in range(max(args.warmup, 1)):
             pass
@@ -584,6 +617,7 @@ def main():
                           "unit": "audio-s/s", "ms_per_step": ms_s, "roofline": r, "decode_step": s}
         line["long_b1"] = long_clip_record(2)
         line["frames_b64"] = frames_record(2)
+        line["codec_encode_b64"] = encode_record(3)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

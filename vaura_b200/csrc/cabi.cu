@@ -826,6 +826,9 @@ extern "C" int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t 
   int ct_index = 29;
   __half* act_in = ws.a0;
   __half* act_out = ws.a1;
+  __half* act_spare = ws.h;  // fused residual units write their activated output next to the one they read (halo rows)
+  static int fused_ru = -1;  // VAURA_CODEC_FUSED_RU=0: conv k7 and conv k1 of a residual unit as two launches
+  if (fused_ru < 0) { const char* e = getenv("VAURA_CODEC_FUSED_RU"); fused_ru = !(e && e[0] == '0'); }
   int t = T;
   for (int i = 0; i < d.n_blocks; ++i) {
     const int base = 3 + 21 * i, s = d.rates[i];
@@ -839,17 +842,27 @@ extern "C" int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t 
     taps_ct += 2 * s;
     ct_index += 2 * s;
     t *= s;
+    const bool fuse = fused_ru && c->use_tc && ru_fused_supported(cout);
     for (int j = 0; j < 3; ++j) {
       const int rb = base + 3 + 6 * j;
-      ConvArgs c7{};
-      c7.in = act_out; c7.W = H(rb + 1); c7.tap_off = taps_k7[j]; c7.bias = F(rb + 2); c7.alpha = F(rb + 3);
-      c7.out_act = ws.h; c7.Tin = t; c7.Tq = t; c7.Tout = t; c7.Cin = cout; c7.Cout = cout; c7.ntaps = 7; c7.nphase = 1;
-      c7.ostride = 1;
-      if ((rc = conv_dispatch(c, c7, 7 * j, B, st))) return rc;
       // alpha of whatever consumes the block output next: next res unit, next block's snake, or the final snake
       const float* next_alpha = j < 2 ? F(rb + 6) : (i + 1 < d.n_blocks ? F(3 + 21 * (i + 1)) : F(tail));
+      if (fuse) {  // one launch per unit, the k7 output stays in shared memory (gemm_ru_fused_kernel)
+        RuArgs r{};
+        r.act = act_out; r.x = ws.x; r.W7 = H(rb + 1); r.W1 = H(rb + 4); r.bias7 = F(rb + 2); r.alpha2 = F(rb + 3);
+        r.bias1 = F(rb + 5); r.alpha_next = next_alpha; r.out_raw = j < 2 ? ws.x : nullptr; r.out_act = act_spare;
+        r.T = t; r.C = cout;
+        CUL(launch_ru_fused(r, c->taps.data() + 7 * j, B, st));
+        __half* tmp2 = act_out; act_out = act_spare; act_spare = tmp2;
+        continue;
+      }
+      ConvArgs c7{};
+      c7.in = act_out; c7.W = H(rb + 1); c7.tap_off = taps_k7[j]; c7.bias = F(rb + 2); c7.alpha = F(rb + 3);
+      c7.out_act = act_spare; c7.Tin = t; c7.Tq = t; c7.Tout = t; c7.Cin = cout; c7.Cout = cout; c7.ntaps = 7; c7.nphase = 1;
+      c7.ostride = 1;
+      if ((rc = conv_dispatch(c, c7, 7 * j, B, st))) return rc;
       ConvArgs c1{};
-      c1.in = ws.h; c1.W = H(rb + 4); c1.tap_off = taps_k1; c1.bias = F(rb + 5); c1.alpha = next_alpha; c1.residual = ws.x;
+      c1.in = act_spare; c1.W = H(rb + 4); c1.tap_off = taps_k1; c1.bias = F(rb + 5); c1.alpha = next_alpha; c1.residual = ws.x;
       c1.out_raw = j < 2 ? ws.x : nullptr; c1.out_act = act_out; c1.Tin = t; c1.Tq = t; c1.Tout = t; c1.Cin = cout;
       c1.Cout = cout; c1.ntaps = 1; c1.nphase = 1; c1.ostride = 1;
       if ((rc = conv_dispatch(c, c1, 21, B, st))) return rc;
@@ -957,18 +970,29 @@ extern "C" int vaura_codec_encode(vaura_codec_encoder* c, const float* wav, int3
   };
   int rc;
   int t = L, ch = c->enc_dim;
-  __half *x = ws.x, *x2 = ws.x2, *act = ws.a0, *act2 = ws.a1;
+  __half *x = ws.x, *x2 = ws.x2, *act = ws.a0, *act2 = ws.a1, *spare = ws.h;
+  static int fused_ru = -1;  // VAURA_CODEC_FUSED_RU=0: conv k7 and conv k1 of a residual unit as two launches
+  if (fused_ru < 0) { const char* e = getenv("VAURA_CODEC_FUSED_RU"); fused_ru = !(e && e[0] == '0'); }
   CUL(launch_enc_conv_in(wav, F(0), F(1), F(2), x, act, B, L, ch, st));
   for (int i = 0; i < d.n_blocks; ++i) {
     const int base = 2 + 21 * i, s = d.rates[d.n_blocks - 1 - i];  // encoder strides = reversed decoder rates
+    const bool fuse = fused_ru && c->use_tc && ru_fused_supported(ch);
     for (int j = 0; j < 3; ++j) {
       const int rb = base + 6 * j;
+      if (fuse) {  // one launch per unit (gemm_ru_fused_kernel); the activated output goes to the spare buffer (halo rows)
+        RuArgs r{};
+        r.act = act; r.x = x; r.W7 = H(rb + 1); r.W1 = H(rb + 4); r.bias7 = F(rb + 2); r.alpha2 = F(rb + 3); r.bias1 = F(rb + 5);
+        r.alpha_next = j < 2 ? F(rb + 6) : F(base + 18); r.out_raw = j < 2 ? x : nullptr; r.out_act = spare; r.T = t; r.C = ch;
+        CUL(launch_ru_fused(r, c->taps.data() + 7 * j, B, st));
+        __half* tmp2 = act; act = spare; spare = tmp2;
+        continue;
+      }
       ConvArgs c7{};
-      c7.in = act; c7.W = H(rb + 1); c7.tap_off = taps_k7[j]; c7.bias = F(rb + 2); c7.alpha = F(rb + 3); c7.out_act = ws.h;
+      c7.in = act; c7.W = H(rb + 1); c7.tap_off = taps_k7[j]; c7.bias = F(rb + 2); c7.alpha = F(rb + 3); c7.out_act = spare;
       c7.Tin = t; c7.Tq = t; c7.Tout = t; c7.Cin = ch; c7.Cout = ch; c7.ntaps = 7; c7.nphase = 1; c7.ostride = 1;
       if ((rc = conv(c7, 7 * j))) return rc;
       ConvArgs c1{};
-      c1.in = ws.h; c1.W = H(rb + 4); c1.tap_off = taps_k1; c1.bias = F(rb + 5);
+      c1.in = spare; c1.W = H(rb + 4); c1.tap_off = taps_k1; c1.bias = F(rb + 5);
       c1.alpha = j < 2 ? F(rb + 6) : F(base + 18);  // next residual unit's first Snake, or the block's Snake before the stride
       c1.residual = x; c1.out_raw = j < 2 ? x : nullptr; c1.out_act = act;
       c1.Tin = t; c1.Tq = t; c1.Tout = t; c1.Cin = ch; c1.Cout = ch; c1.ntaps = 1; c1.nphase = 1; c1.ostride = 1;

@@ -891,6 +891,211 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused ResidualUnit of the DAC decoder / encoder (dac 1.0.0 ResidualUnit: Snake -> conv k7 dilated -> Snake -> conv k1, + x)
+// for C <= 256 channels, where the stand-alone k1 convolution is pure memory traffic (reads h and x, writes x and
+// Snake(x): 49 % of the HBM peak at 192 channels, r02_codec_launches_b16.csv) and the k7 convolution writes h only to have
+// it read back.  Per 128-row tile:  acc1 = conv7(act) (7 taps x C / BK K blocks from the ring)  ->  the epilogue warps turn
+// acc1 into h = Snake(acc1 + b7) in fp16 and store it into shared memory in the UMMA K-major swizzled layout  ->
+// acc2 = h x W1^T (W1 K blocks streamed through the same ring)  ->  epilogue: + b1 + x, raw and Snake'd outputs.
+// h never leaves the SM: the unit moves 4 activation passes instead of 6 and one launch instead of two.
+// TMEM: acc1 at column 0, acc2 at column ACC (two accumulators of C <= 256 columns).  The k7 mainloop of tile i + 1 overlaps
+// the second epilogue of tile i; the first epilogue (acc1 -> h) is on the MMA warp's critical path, so it hands h over K block
+// by K block (the k1 GEMM starts on block 0 while the others are produced) and reads its bias / Snake parameters from shared
+// memory.  A variant skewed by one tile (k1 of tile i - 1 issued behind the k7 mainloop of tile i, acc2 written over acc1)
+// measured slower (9.23 vs 8.45 ms per 16 clips): with two 256-column buffers the second epilogue then sits between two k7
+// mainloops instead of under one.
+// ------------------------------------------------------------------------------------------------
+struct RuParams {
+  const float *bias7, *alpha2;   // conv k7 bias; Snake after it ([C] alpha | [C] 1 / (alpha + 1e-9))
+  EpiConv::Params k1;            // conv k1 epilogue: bias, Snake of the consumer, residual x, raw / activated outputs
+};
+
+template <int C, int BLOCK_K, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW7,
+                     const __grid_constant__ CUtensorMap tmW1, const TcShape g, const RuParams rp, const int m_tiles) {
+  constexpr int SW = BLOCK_K * 2, KB = C / BLOCK_K;
+  constexpr int A_BYTES = kTileM * BLOCK_K * 2, B_BYTES = C * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int H_BYTES = KB * A_BYTES;
+  constexpr int ACC = C <= 32 ? 32 : C <= 64 ? 64 : C <= 128 ? 128 : 256, TMEM_COLS = 2 * ACC;
+  static_assert(C % BLOCK_K == 0 && C % 16 == 0 && C <= 256, "channel count");
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "stage buffers must stay 1024B aligned for the swizzle");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* hs = smem + STAGES * STAGE_BYTES;  // h tile: KB sub-tiles [128 rows][BLOCK_K] fp16, swizzled like a TMA-written A tile
+  float* par = reinterpret_cast<float*>(hs + H_BYTES);  // [3][C]: conv k7 bias | Snake alpha | 1 / (alpha + 1e-9)
+  uint64_t* full = reinterpret_cast<uint64_t*>(par + 3 * C);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc1_full = empty + STAGES;
+  uint64_t* h_ready = acc1_full + 1;   // [KB] 8 arrivals each: every epilogue warp has stored its part of K block kb of h
+  uint64_t* acc2_full = h_ready + KB;
+  uint64_t* acc2_free = acc2_full + 1; // 8 arrivals: acc2 drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int units7 = g.ntaps * KB;  // ring stages of the k7 mainloop per tile; KB more carry the W1 K blocks
+  const int ntiles = m_tiles * g.batch;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW7) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc1_full, 1);
+    for (int kb = 0; kb < KB; ++kb) mbar_init(&h_ready[kb], 8);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_free, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  for (int i = threadIdx.x; i < C; i += kGemmThreads) {
+    par[i] = rp.bias7[i];
+    par[C + i] = rp.alpha2[i];
+    par[2 * C + i] = rp.alpha2[C + i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    int git = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int m0 = (t % m_tiles) * kTileM, b = t / m_tiles;
+      for (int it = 0; it < units7 + KB; ++it, ++git) {
+        const int s = git % STAGES;
+        const uint32_t ph = (git / STAGES) & 1;
+        uint8_t* ss = smem + s * STAGE_BYTES;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (it < units7) {
+          const int tap = it / KB, kb = it % KB;
+          mbar_expect_tx_elect(&full[s], STAGE_BYTES);
+          tma_load_3d_elect(ss + A_BYTES, &tmW7, &full[s], kb * BLOCK_K, 0, tap);
+          tma_load_3d_elect(ss, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[tap], b);
+        } else {
+          mbar_expect_tx_elect(&full[s], B_BYTES);
+          tma_load_3d_elect(ss + A_BYTES, &tmW1, &full[s], (it - units7) * BLOCK_K, 0, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(kTileM, C, 0);
+    int git = 0, tc = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
+      const uint32_t tph = tc & 1;
+      for (int it = 0; it < units7; ++it, ++git) {
+        const int s = git % STAGES;
+        mbar_wait(&full[s], (git / STAGES) & 1);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) umma_bf16_f16_elect(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        umma_commit_elect(&empty[s]);
+      }
+      umma_commit_elect(acc1_full);
+      mbar_wait(acc2_free, tph ^ 1);       // the previous tile's second epilogue has drained acc2 (first use passes)
+      for (int kb = 0; kb < KB; ++kb, ++git) {
+        const int s = git % STAGES;
+        mbar_wait(&h_ready[kb], tph);      // K block kb of this tile's h is in shared memory
+        mbar_wait(&full[s], (git / STAGES) & 1);
+        tcgen05_fence_after();
+        const uint64_t adesc = make_smem_desc<SW>(smem_u32(hs + kb * A_BYTES));
+        const uint64_t bdesc = make_smem_desc<SW>(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) umma_bf16_f16_elect(tmem_base + ACC, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit_elect(&empty[s]);
+      }
+      umma_commit_elect(acc2_full);
+    }
+    __syncwarp();
+  } else {
+    // first epilogue: the eight warps split the columns K block by K block (two warps per TMEM lane quadrant take the two
+    // halves of every K block), so that the MMA warp can start the k1 GEMM on K block 0 while the others are produced
+    const int q = warp & 3, row = q * 32 + lane, half = (warp - 2) >> 2;
+    constexpr int kChunks = C / 16, kHalf = (kChunks + 1) / 2;
+    constexpr int CPB = BLOCK_K / 16, CPH = (CPB + 1) / 2;  // 16-column chunks per K block / per warp and K block
+    const int c_begin = half == 0 ? 0 : kHalf * 16, c_end = half == 0 ? kHalf * 16 : C;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    int tc = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
+      const int m0 = (t % m_tiles) * kTileM, b = t / m_tiles, m = m0 + row;
+      const uint32_t tph = tc & 1;
+      // residual rows of the second epilogue: in flight while the tile's MMAs run
+      uint4 res[kHalf][2];
+#pragma unroll
+      for (int i = 0; i < kHalf; ++i) {
+        const int c = c_begin + 16 * i;
+        if (c < c_end) EpiConv::load_residual(rp.k1, b, 0, m, c, res[i][0], res[i][1]);
+      }
+      // ---- first epilogue: h = Snake(acc1 + b7) -> shared memory, K-major, 128B / 64B swizzle (what a tensor copy would write)
+      mbar_wait(acc1_full, tph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+        for (int i = 0; i < CPH; ++i) {
+          const int cc = half * CPH + i;  // chunk inside the K block
+          if (cc < CPB) {
+            const int c = kb * BLOCK_K + 16 * cc;
+            float v[16];
+            tmem_ld16(tq + c, v);
+            uint4 o[2];
+            __half2* h2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(par + c + e);
+              const float4 al = *reinterpret_cast<const float4*>(par + C + c + e);
+              const float4 ia = *reinterpret_cast<const float4*>(par + 2 * C + c + e);
+              h2[e / 2] = __floats2half2_rn(snake_eval(v[e] + bb.x, al.x, ia.x), snake_eval(v[e + 1] + bb.y, al.y, ia.y));
+              h2[e / 2 + 1] = __floats2half2_rn(snake_eval(v[e + 2] + bb.z, al.z, ia.z), snake_eval(v[e + 3] + bb.w, al.w, ia.w));
+            }
+            const int j = 2 * cc;  // first 16-byte chunk inside the row of this K block
+            uint8_t* rowp = hs + kb * A_BYTES + row * SW;
+            const int sw = SW == 128 ? (row & 7) : ((row >> 1) & 3);
+            *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = o[0];
+            *reinterpret_cast<uint4*>(rowp + (((j + 1) ^ sw) << 4)) = o[1];
+          }
+        }
+        // generic-proxy stores -> visible to the tensor core's (async-proxy) operand reads, then tell the MMA warp
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&h_ready[kb])) : "memory");
+      }
+      // ---- second epilogue: acc2 + b1 + x -> raw x' and Snake(x') for the consumer
+      mbar_wait(acc2_full, tph);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int i = 0; i < kHalf; ++i) {
+        const int c = c_begin + 16 * i;
+        if (c < c_end) {
+          float v[16];
+          tmem_ld16(tq + ACC + c, v);
+          EpiConv::apply(rp.k1, b, 0, m, c, v, res[i][0], res[i][1]);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc2_free)) : "memory");
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused decode step of the bf16 path for up to 64 sequence rows (one new position per row): ONE cooperative kernel runs
 // the 24 layers + final norm + heads that transformer_pass_bf16 issues as 170 launches.  Each phase is the same tile
 // arithmetic as the stand-alone kernels (rmsnorm_bf16_kernel, gemm_tc_kernel with UMMA M = 64 and 4 K blocks per stage,
@@ -1644,6 +1849,50 @@ static cudaError_t launch_tc_persistent(const CUtensorMap& ta, const CUtensorMap
   const int ntiles = m_tiles * n_tiles * g.batch * g.nphase;
   kern<<<dim3(ntiles < OCC * sms ? ntiles : OCC * sms), dim3(kGemmThreads), smem, st>>>(ta, tb, g, ep, m_tiles, n_tiles);
   return cudaGetLastError();
+}
+
+template <int C, int BLOCK_K, int STAGES>
+static cudaError_t launch_ru_fused_t(const RuArgs& a, const int* taps7_host, int B, cudaStream_t st) {
+  constexpr int smem = STAGES * (kTileM * BLOCK_K * 2 + C * BLOCK_K * 2) + (C / BLOCK_K) * kTileM * BLOCK_K * 2 + 3 * C * 4 + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "ring + h tile exceed shared memory");
+  CUtensorMap ta, t7, t1;
+  if (!make_map(&ta, a.act, C, a.T, B, C, (uint64_t)a.T * C, BLOCK_K, kTileM, true) ||
+      !make_map(&t7, a.W7, C, C, 7, C, (uint64_t)C * C, BLOCK_K, C, true) ||
+      !make_map(&t1, a.W1, C, C, 1, C, (uint64_t)C * C, BLOCK_K, C, true))
+    return cudaErrorUnknown;
+  auto kern = gemm_ru_fused_kernel<C, BLOCK_K, STAGES>;
+  static int sms_tab[64] = {0};
+  const int slot = current_device_slot();
+  if (!sms_tab[slot]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms_tab[slot], cudaDevAttrMultiProcessorCount, dev);
+  }
+  TcShape g{};
+  g.ntaps = 7; g.nphase = 1; g.kblocks = C / BLOCK_K; g.batch = B; g.ksplit = 1;
+  for (int i = 0; i < 7; ++i) g.tap_off[i] = taps7_host[i];
+  RuParams rp{};
+  rp.bias7 = a.bias7; rp.alpha2 = a.alpha2;
+  rp.k1 = EpiConv::Params{a.bias1, a.alpha_next, a.x, a.out_raw, a.out_act, a.T, a.T, C, 1};
+  const int mt = (a.T + kTileM - 1) / kTileM, ntiles = mt * B, sms = sms_tab[slot];
+  kern<<<dim3(ntiles < sms ? ntiles : sms), dim3(kGemmThreads), smem, st>>>(ta, t7, t1, g, rp, mt);
+  return cudaGetLastError();
+}
+
+bool ru_fused_supported(int C) { return C == 192 || C == 96 || C == 128 || C == 64 || C == 256; }
+
+// One launch per ResidualUnit (see gemm_ru_fused_kernel)
+cudaError_t launch_ru_fused(const RuArgs& a, const int* taps7_host, int B, cudaStream_t st) {
+  switch (a.C) {
+    case 256: return launch_ru_fused_t<256, 64, 3>(a, taps7_host, B, st);
+    case 192: return launch_ru_fused_t<192, 64, 4>(a, taps7_host, B, st);
+    case 128: return launch_ru_fused_t<128, 64, 5>(a, taps7_host, B, st);
+    case 96: return launch_ru_fused_t<96, 32, 10>(a, taps7_host, B, st);
+    case 64: return launch_ru_fused_t<64, 64, 8>(a, taps7_host, B, st);
+  }
+  return cudaErrorInvalidValue;
 }
 
 bool conv_tc_supported(int Cin, int Cout, int ntaps, int nphase) {

@@ -206,6 +206,18 @@ cudaError_t launch_vit_time_attn(const void* qkv, void* out, int S, int t, int n
 cudaError_t launch_vit_cls_attn(const void* qkv, void* out, int seqs, int len, int heads, int out_rows_per_seq, cudaStream_t st);
 cudaError_t launch_vit_space_attn(const void* qkv, void* out, int S, int t, int n, int heads, cudaStream_t st);
 
+// fused ResidualUnit (conv k7 -> Snake -> conv k1 -> + x) of the codec for narrow layers (gemm_tcgen05.cu: gemm_ru_fused_kernel)
+struct RuArgs {
+  const __half* act;       // [B][T][C] Snake(x, alpha1): the unit's activated input
+  const __half* x;         // [B][T][C] the unit's raw input (residual)
+  const __half *W7, *W1;   // [7][C][C], [1][C][C]
+  const float *bias7, *alpha2, *bias1, *alpha_next;
+  __half* out_raw;         // [B][T][C] x + unit(x) or nullptr (may alias x: every element is read and written by one thread)
+  __half* out_act;         // [B][T][C] Snake(out, alpha_next)
+  int T, C;
+};
+bool ru_fused_supported(int C);
+cudaError_t launch_ru_fused(const RuArgs& a, const int* taps7_host, int B, cudaStream_t st);
 bool conv_tc_supported(int Cin, int Cout, int ntaps, int nphase);
 cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cudaStream_t st);
 cudaError_t init_decode_kernels();
