@@ -455,8 +455,8 @@ def main():
         kws = gen_kw(w)
 
         def e2e_step():
-            f = fr_host.to(dev, non_blocking=True)
-            wv = model.generate(frames=f, clip_indices=ids, **kws)["generated_audio"]
+            # the pinned host tensor goes straight into generate(): the extractor copies it chunk by chunk under its own compute
+            wv = model.generate(frames=fr_host, clip_indices=ids, **kws)["generated_audio"]
             wh.copy_(wv, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         e2e_step()

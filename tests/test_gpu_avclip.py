@@ -87,3 +87,16 @@ def test_generate_from_raw_frames_matches_generate_from_features(tower):
     b = model.generate(frames=feats, **kw)
     assert torch.equal(a["sampled_indices"], b["sampled_indices"])
     assert torch.equal(a["generated_audio"], b["generated_audio"])
+
+
+def test_pinned_host_frames_are_copied_chunk_by_chunk_with_the_same_result(tower):
+    """Frames handed over in pinned host memory take the overlapped copy path (two staging buffers, ragged last chunk)."""
+    frames = make_video_segments(1, 57, 5)
+    ref, _ = tower(frames.cuda())
+    tower.max_chunk_segments, tower._ws = 2, None
+    try:
+        got, _ = tower(frames.pin_memory())
+        again, _ = tower(frames.pin_memory())  # staging buffers re-used by a second call
+    finally:
+        tower.max_chunk_segments, tower._ws = 32, None
+    assert got.device.type == "cuda" and torch.equal(got, ref) and torch.equal(again, ref)

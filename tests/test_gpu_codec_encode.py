@@ -58,3 +58,18 @@ def test_encode_decode_round_trip_and_shapes(codec):
     assert audio.shape == (1, 1, 512 * 20)
     with pytest.raises(ValueError):
         codec.encode(torch.zeros(1, 2, 1024).cuda())
+
+
+def test_encode_of_less_than_one_hop_and_batches_beyond_the_chunk(codec):
+    """Edge sizes: 100 samples (padded to one 512-sample frame) and a batch larger than the 8-clip workspace chunk."""
+    sd = make_codec_state_dict(FULL_CODEC, 100, with_encoder=True)
+    oracle = DacEncodeOracle(sd, FULL_CODEC)
+    g = torch.Generator().manual_seed(4)
+    short = 0.3 * torch.randn(1, 1, 100, generator=g)
+    c = codec.encode(short.cuda())
+    assert c.shape == (1, 9, 1)
+    assert int(c[0, 0, 0]) == int(oracle.encode(short)[0, 0, 0])
+    wav = 0.3 * torch.randn(11, 1, 512 * 6, generator=g)
+    many = codec.encode(wav.cuda())
+    one = torch.cat([codec.encode(wav[i:i + 1].cuda()) for i in range(11)])
+    assert many.shape == (11, 9, 6) and torch.equal(many, one)

@@ -153,7 +153,9 @@ class VAURAModel(torch.nn.Module):
             # (vaura_model.py:464-469) does not type-check against DacModelWrapper.encode's tensor; the codes are used as they are
             audio = self.audio_encoder.encode(audio)
         B, K, T = audio.shape
-        vis_feats = self._handle_visual_conditioning(frames.to(dev), clip_indices, B)
+        # raw video segments in pinned host memory stay there: the extractor overlaps their copy with its own compute
+        host_frames = self.using_avclip and frames.dim() == 6 and frames.device.type == "cpu" and frames.is_pinned()
+        vis_feats = self._handle_visual_conditioning(frames if host_frames else frames.to(dev), clip_indices, B)
         start_offset = T
         assert start_offset < max_new_tokens, "gt audio prompt can not be longer than max_new_tokens"
         pattern = self.pattern_provider.get_pattern(max_new_tokens)
