@@ -333,3 +333,53 @@ def test_strided_conv_as_three_frame_taps():
         fp = F.pad(frames, (0, 0, 1, 1))
         mine = sum(fp[f:f + T // s] @ wf[f].t() for f in range(3)).t()[None]
         assert torch.allclose(mine, ref, atol=1e-5), s
+
+
+def test_avclip_and_codec_encoder_blobs_have_the_slot_counts_the_header_states():
+    """include/vaura_b200.h: avclip blob = 4 + 18 * depth + 15 slots, codec encoder blob = 2 + 21 * n_blocks + 8 slots; the
+    position table is pos_embed[1 + patch] + temp_embed[frame] (video_model_builder.py:238-245)."""
+    from vaura_b200.synthetic import (TINY_AVCLIP, TINY_CODEC, make_codec_state_dict, make_motionformer_state_dict)
+    from vaura_b200.weights import avclip_flops, codec_encoder_flops, pack_avclip, pack_codec_encoder
+
+    sd = make_motionformer_state_dict(3, TINY_AVCLIP)
+    blob, offs = pack_avclip(sd, TINY_AVCLIP, "cpu")
+    assert len(offs) == 4 + 18 * TINY_AVCLIP.depth + 15 and all(o % 256 == 0 for o in offs) and offs == sorted(offs)
+    t, n, D = TINY_AVCLIP.temporal, TINY_AVCLIP.patches_per_frame, TINY_AVCLIP.embed_dim
+    pos = blob[offs[2]:offs[2] + t * n * D * 4].view(torch.float32).reshape(t, n, D)
+    want = sd["pos_embed"][0, 1:][None] + sd["temp_embed"][0][:, None]
+    assert torch.allclose(pos, want)
+    cls = blob[offs[3]:offs[3] + D * 4].view(torch.float32)
+    assert torch.allclose(cls, sd["cls_token"].reshape(-1) + sd["pos_embed"][0, 0])
+    assert avclip_flops(TINY_AVCLIP, 2) == 2 * avclip_flops(TINY_AVCLIP, 1) > 0
+
+    csd = make_codec_state_dict(TINY_CODEC, 100, with_encoder=True)
+    blob, offs = pack_codec_encoder(csd, TINY_CODEC, "cpu")
+    assert len(offs) == 2 + 21 * len(TINY_CODEC.decoder_rates) + 8 and all(o % 256 == 0 for o in offs)
+    assert codec_encoder_flops(TINY_CODEC, 512 * 4) > 0
+
+
+def test_motionformer_host_class_contract_without_a_gpu():
+    """Class name / constructor keywords / pass-through / unsupported configurations (motionformer.py:47-75, :252-307)."""
+    from vaura_b200.codec import DacModelWrapper
+    from vaura_b200.features import MotionFormer
+
+    m = MotionFormer(extract_features=True, ckpt_path="/path/to/vggsound/epoch_best.pt", factorize_space_time=True,
+                     agg_space_module="TransformerEncoderLayer", agg_time_module="torch.nn.Identity", add_global_repr=False)
+    assert m.__class__.__name__ == "MotionFormer" and m.embed_dim == 768 and not m.has_weights
+    feats = torch.zeros(2, 4, 8, 768)
+    out, glob = m(feats)
+    assert out is feats and glob is None
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 3, 16, 224, 224))          # raw frames need the tower's weights
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 16, 224, 224))
+    for bad in (dict(extract_features=False), dict(extract_features=True, factorize_space_time=False),
+                dict(extract_features=True, agg_space_module="AveragePooling"),
+                dict(extract_features=True, agg_time_module="TransformerEncoderLayer"),
+                dict(extract_features=True, add_global_repr=True)):
+        with pytest.raises(NotImplementedError):
+            MotionFormer(**bad)._check_supported()
+    c = DacModelWrapper(model_sr=44100)
+    assert c.preprocess(torch.zeros(1, 1, 1000)).shape[-1] == 1024 and c.preprocess(torch.zeros(1, 1, 1024)).shape[-1] == 1024
+    with pytest.raises(RuntimeError):
+        c.encoder_handle()
