@@ -119,6 +119,28 @@ def test_codec_decode_matches_oracle(tiny_model):
         tiny_model.audio_encoder.decode(torch.full((1, 9, 4), 1024).cuda())  # special id is not a codec code
 
 
+def test_codec_decode_full_size_both_snr_bounds():
+    """two bounds for the full-size codec - against the fp32 oracle, and against the oracle with the weights the
+    reference's `.half()` leaves (vaura_model.py:92: weight_g / weight_v rounded to fp16 before the weight-norm fold;
+    activations kept in fp32 here, CPU fp16 convolutions being neither fast nor what a GPU accumulates).  The GPU path folds in
+    fp32 and rounds the folded weight once, so the two differ by two independent roundings: the second bound is its own number,
+    not a tighter one."""
+    from vaura_b200.codec import DacModelWrapper
+    from vaura_b200.synthetic import FULL_CODEC
+
+    sd = make_codec_state_dict(FULL_CODEC, 100)
+    m = DacModelWrapper(44100, dims=FULL_CODEC)
+    m.load_state_dict(sd, device="cuda:0")
+    codes = torch.randint(0, 1024, (1, 9, 40), generator=torch.Generator().manual_seed(2))
+    wav = m.decode(codes.cuda()).float().cpu()
+    ref32 = DacDecodeOracle(sd, FULL_CODEC).decode(codes)
+    sd16 = {k: (v.half().float() if v.is_floating_point() else v) for k, v in sd.items()}
+    ref16 = DacDecodeOracle(sd16, FULL_CODEC).decode(codes)
+    s32, s16 = snr_db(ref32, wav), snr_db(ref16, wav)
+    print(f"[codec full size] SNR vs fp32 oracle {s32:.1f} dB, vs fp16-weight oracle {s16:.1f} dB")
+    assert s32 > 45.0 and s16 > 40.0
+
+
 def test_full_size_greedy_matches_reference_golden():
     """BASELINE.json config 1 on the B200: 24 layers, B=1, 2.56 s clip, greedy; the tokens are the ones the
     unmodified reference produced (tests/golden/full_greedy.npz)."""
