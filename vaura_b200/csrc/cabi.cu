@@ -555,7 +555,11 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
                            cluster_supported(rows, d.num_layers, d.d_model, d.ffn_dim, d.nhead, K * d.vocab, kv->page_size,
                                              d.cond_dim, S) &&
                            cluster_launchable(rows, phase_timing);
-  const bool cluster_first = use_cluster && npre == 1;
+  // Without a prompt the first pass is the decode step of position 0 with an empty K/V cache: the step kernels run it as
+  // their first launch (cluster kernel; graph-replayed bf16 step, fused or not) instead of ~170 separate first-pass kernels
+  static int bf16_first = -1;  // VAURA_BF16_STEP_FIRST=0: keep the separate first pass on the bf16 path
+  if (bf16_first < 0) { const char* e = getenv("VAURA_BF16_STEP_FIRST"); bf16_first = !(e && e[0] == '0'); }
+  const bool cluster_first = npre == 1 && (use_cluster || (bf16_first && !persist && precision == VAURA_PRECISION_BF16));
   int nsteps = p->end_offset - (p->start_offset + 1);
   if (!cluster_first) {
     // first pass: positions [0, start) -> sample column start
