@@ -476,8 +476,17 @@ struct EpiVit {
     }
     if (p.mode == VIT_STORE_BF16) {
       if (p.gelu) {
+        // exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the
+        // bf16 rounding of the stored value): one reciprocal, one exponential and five FMAs instead of erff's ~25 instructions -
+        // the fc1 epilogue (128 values per thread and tile) was longer than the tile's MMAs (fc1 681 TFLOP/s vs 935 for q|k|v)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+        for (int i = 0; i < 16; ++i) {
+          const float x = v[i], z = fabsf(x) * 0.70710678118654752f;
+          const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+          const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+          const float e = 1.f - poly * __expf(-z * z);       // erf(|x| / sqrt 2)
+          v[i] = 0.5f * x * (1.f + copysignf(e, x));
+        }
       }
       uint4 o[2];
       __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
@@ -730,8 +739,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // 32-wide blocks) the copies and barrier round trips per tap drop from 3 to 1.
 // OCC = 2: two CTAs per SM (half the ring each, 2 x 2 accumulator buffers of <= 128 TMEM columns): for the narrow layers whose
 // tiles are paced by the serial work of one producer / MMA / epilogue chain rather than by bytes in flight.
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int KSUB = 1, int OCC = 1>
-__global__ void __launch_bounds__(kGemmThreads, OCC)
+// EW: epilogue warps (8 or 16 = two or four per TMEM lane quadrant, splitting the accumulator columns).  With a short K (the
+// tower's K = 768: 3.2 us of MMAs per 128 x 256 tile) the tile rate is set by the epilogue, whose cost per warp is instruction
+// and store-transaction bound; sixteen warps halve it (tower: 186.8 -> 179.7 ms per 256 segments; the codec's convolutions
+// measured the same with 8 and 16).  What then bounds these GEMMs is the operand ingest: 590 KB per tile at the ~75 GB/s per SM
+// that four 48 KB stages in flight sustain = 7.8 us per tile = ~950 TFLOP/s; only tiles that share an operand between two SMs
+// (cta_group::2) would lower the bytes per FLOP.
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int KSUB = 1, int OCC = 1, int EW = 8>
+__global__ void __launch_bounds__(64 + 32 * EW, OCC)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape g,
                           const typename Epi::Params ep, const int m_tiles, const int n_tiles) {
   constexpr int SW = BLOCK_K * 2;
@@ -765,7 +780,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
+      mbar_init(&tempty[i], EW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -849,8 +864,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     __syncwarp();
   } else {
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    constexpr int kChunks = BLOCK_N / 16, kHalf = (kChunks + 1) / 2;
-    const int c_begin = (warp - 2) < 4 ? 0 : kHalf * 16, c_end = (warp - 2) < 4 ? kHalf * 16 : BLOCK_N;
+    // the EW / 4 warps of a quadrant split the accumulator columns into equal runs of 16-column chunks
+    constexpr int kParts = EW / 4, kChunks = BLOCK_N / 16, kHalf = (kChunks + kParts - 1) / kParts;
+    static_assert(EW == 8 || EW == 16, "epilogue warps");
+    const int part = (warp - 2) >> 2;
+    const int c_begin = part * kHalf * 16, c_end = (part + 1) * kHalf * 16 < BLOCK_N ? (part + 1) * kHalf * 16 : BLOCK_N;
     int tc = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
       int m0, n0, b, phase;
@@ -1829,13 +1847,13 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const
   cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, g, ep);
 }
-template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int KSUB = 1, int OCC = 1>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int FMT, class Epi, int KSUB = 1, int OCC = 1, int EW = 8>
 static cudaError_t launch_tc_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const TcShape& g,
                                         const typename Epi::Params& ep, int m_tiles, int n_tiles, cudaStream_t st) {
   constexpr int smem = STAGES * KSUB * (kTileM * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
   static_assert(OCC * (smem + 1024) <= 227 * 1024, "stage ring exceeds shared memory");
   if (g.kblocks % KSUB) return cudaErrorInvalidValue;
-  auto kern = gemm_tc_persistent_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, KSUB, OCC>;
+  auto kern = gemm_tc_persistent_kernel<BLOCK_N, BLOCK_K, STAGES, FMT, Epi, KSUB, OCC, EW>;
   static int sms_tab[64] = {0};
   const int slot = current_device_slot();
   if (!sms_tab[slot]) {
@@ -1847,7 +1865,7 @@ static cudaError_t launch_tc_persistent(const CUtensorMap& ta, const CUtensorMap
   }
   const int sms = sms_tab[slot];
   const int ntiles = m_tiles * n_tiles * g.batch * g.nphase;
-  kern<<<dim3(ntiles < OCC * sms ? ntiles : OCC * sms), dim3(kGemmThreads), smem, st>>>(ta, tb, g, ep, m_tiles, n_tiles);
+  kern<<<dim3(ntiles < OCC * sms ? ntiles : OCC * sms), dim3(64 + 32 * EW), smem, st>>>(ta, tb, g, ep, m_tiles, n_tiles);
   return cudaGetLastError();
 }
 
@@ -2135,7 +2153,10 @@ cudaError_t launch_vit_linear(const VitLinearArgs& a, cudaStream_t st) {
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16); ep.out_f32 = a.out_f32; ep.pos = a.pos;
   ep.rows_in = a.rows_in; ep.rows_out = a.rows_out; ep.row_off = a.row_off;
   const int mt = (a.M + kTileM - 1) / kTileM, nt = a.N / bn;
-  if (bn == 256) return launch_tc_persistent<256, 64, 4, 1, EpiVit>(ta, tb, g, ep, mt, nt, st);
+  static int ew16 = -1;  // VAURA_AVCLIP_EW8=1: eight epilogue warps (A/B measurement)
+  if (ew16 < 0) { const char* e = getenv("VAURA_AVCLIP_EW8"); ew16 = !(e && e[0] == '1'); }
+  if (bn == 256) return ew16 ? launch_tc_persistent<256, 64, 4, 1, EpiVit, 1, 1, 16>(ta, tb, g, ep, mt, nt, st)
+                             : launch_tc_persistent<256, 64, 4, 1, EpiVit>(ta, tb, g, ep, mt, nt, st);
   return launch_tc_persistent<128, 64, 6, 1, EpiVit>(ta, tb, g, ep, mt, nt, st);
 }
 
