@@ -909,6 +909,171 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant of the persistent GEMM (cta_group::2): the two CTAs of a cluster (2, 1, 1) compute one 256 x BLOCK_N tile with
+// UMMA M = 256 - CTA r holds rows [128 r, 128 r + 128) of A, rows [BLOCK_N / 2 * r, ...) of W and its own 128 x BLOCK_N
+// accumulator in TMEM; the leader CTA's MMA warp issues tcgen05.mma.cta_group::2, which reads both CTAs' shared memory.
+// Per 128 x 256 outputs a CTA ingests (128 + 128) x 64 x 2 B = 32 KB per K block instead of 48 KB: the single-CTA kernel is
+// bound by operand ingest (~75 GB/s per SM = bytes in flight / latency), so the tile rate rises by up to 1.5 x.
+// Protocol (CUTLASS sm100 2-SM pipeline): both producers load their halves with cp.async.bulk.tensor...cta_group::2 signalling
+// the LEADER's full barrier (peer bit of the barrier address cleared); the leader's producer arms it with the bytes of both;
+// tcgen05.commit.cta_group::2 ... multicast::cluster frees the stage in both CTAs and publishes the accumulator to both
+// epilogues; the epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier (remote mbarrier.arrive).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d_2sm_elect(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc_elect(uint64_t* bar) {  // arrives on `bar` of both CTAs of the pair
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t.reg .b16 m;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int BLOCK_N, int STAGES, int FMT, class Epi, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
+gemm_tc2_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape g,
+                           const typename Epi::Params ep, const int m_tiles, const int n_tiles) {
+  constexpr int BLOCK_K = 64, SW = 128, HALF_N = BLOCK_N / 2;
+  constexpr int A_BYTES = kTileM * BLOCK_K * 2, B_BYTES = HALF_N * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int ACC_COLS = BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256, TMEM_COLS = 2 * ACC_COLS;
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256 && B_BYTES % 1024 == 0, "tile shape");
+  static_assert(EW == 8 || EW == 16, "epilogue warps");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // used in the leader CTA only
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;   // [2] accumulator buffer complete (both CTAs)
+  uint64_t* tempty = tfull + 2;       // [2] leader only: drained by the 2 x EW epilogue warps of the pair
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int iters = g.kblocks;
+  const int ntiles = m_tiles * n_tiles;  // tiles of 256 rows x BLOCK_N columns
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 2 * EW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();  // both CTAs' barriers exist before anything can signal them; both are resident before the paired alloc
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int t, int& m0, int& n0) {  // N first: the pairs that run together share activation rows in L2
+    n0 = (t % n_tiles) * BLOCK_N;
+    m0 = (t / n_tiles) * (2 * kTileM);
+  };
+
+  if (warp == 0) {
+    int git = 0;
+    for (int t = pair; t < ntiles; t += npairs) {
+      int m0, n0;
+      tile_coords(t, m0, n0);
+      for (int it = 0; it < iters; ++it, ++git) {
+        const int s = git % STAGES;
+        uint8_t* ss = smem + s * STAGE_BYTES;
+        mbar_wait(&empty[s], ((git / STAGES) & 1) ^ 1);
+        if (rank == 0) mbar_expect_tx_elect(&full[s], 2 * STAGE_BYTES);
+        tma_load_3d_2sm_elect(ss + A_BYTES, &tmB, &full[s], it * BLOCK_K, n0 + (int)rank * HALF_N, 0);
+        tma_load_3d_2sm_elect(ss, &tmA, &full[s], it * BLOCK_K, m0 + (int)rank * kTileM, 0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * kTileM, BLOCK_N, FMT);
+      int git = 0, tc = 0;
+      for (int t = pair; t < ntiles; t += npairs, ++tc) {
+        const int ab = tc & 1;
+        mbar_wait(&tempty[ab], ((tc >> 1) & 1) ^ 1);  // both epilogues have drained this buffer (first use passes)
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + ab * ACC_COLS;
+        for (int it = 0; it < iters; ++it, ++git) {
+          const int s = git % STAGES;
+          mbar_wait(&full[s], (git / STAGES) & 1);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) umma2_f16_elect(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          umma2_commit_mc_elect(&empty[s]);
+        }
+        umma2_commit_mc_elect(&tfull[ab]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    constexpr int kParts = EW / 4, kChunks = BLOCK_N / 16, kHalf = (kChunks + kParts - 1) / kParts;
+    const int part = (warp - 2) >> 2;
+    const int c_begin = part * kHalf * 16, c_end = (part + 1) * kHalf * 16 < BLOCK_N ? (part + 1) * kHalf * 16 : BLOCK_N;
+    const uint32_t rempty = mapa_u32(smem_u32(&tempty[0]), 0);  // the leader's accumulator-empty barriers
+    int tc = 0;
+    for (int t = pair; t < ntiles; t += npairs, ++tc) {
+      int m0, n0;
+      tile_coords(t, m0, n0);
+      const int ab = tc & 1;
+      const int m = m0 + (int)rank * kTileM + q * 32 + lane;
+      mbar_wait(&tfull[ab], (tc >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int i = 0; i < kHalf; ++i) {
+        const int c = c_begin + 16 * i;
+        if (c < c_end) {
+          float v[16];
+          tmem_ld16(tacc + c, v);
+          Epi::apply(ep, 0, 0, m, n0 + c, v);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(rempty + 8u * (uint32_t)ab) : "memory");
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA frees its half of the paired allocation while the other may still use its own
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused ResidualUnit of the DAC decoder / encoder (dac 1.0.0 ResidualUnit: Snake -> conv k7 dilated -> Snake -> conv k1, + x)
 // for C <= 256 channels, where the stand-alone k1 convolution is pure memory traffic (reads h and x, writes x and
 // Snake(x): 49 % of the HBM peak at 192 channels, r02_codec_launches_b16.csv) and the k7 convolution writes h only to have
@@ -2153,6 +2318,31 @@ cudaError_t launch_vit_linear(const VitLinearArgs& a, cudaStream_t st) {
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16); ep.out_f32 = a.out_f32; ep.pos = a.pos;
   ep.rows_in = a.rows_in; ep.rows_out = a.rows_out; ep.row_off = a.row_off;
   const int mt = (a.M + kTileM - 1) / kTileM, nt = a.N / bn;
+  // CTA-pair tiles (gemm_tc2_persistent_kernel) by default: q|k|v 187 -> 171 us, fc1 358 -> 245 us, fc2 212 -> 192 us per 32
+  // segments (12.96 vs 15.19 ms of GEMMs per forward).  VAURA_AVCLIP_2CTA=0: one CTA per tile (A/B measurement)
+  static int two_cta = -1;
+  if (two_cta < 0) { const char* e = getenv("VAURA_AVCLIP_2CTA"); two_cta = !(e && e[0] == '0'); }
+  if (two_cta && bn == 256) {
+    constexpr int ST = 6, EWP = 16;
+    constexpr int smem2 = ST * (kTileM * 64 * 2 + 128 * 64 * 2) + 1024 + 256;
+    CUtensorMap tb2;
+    if (!make_map(&tb2, a.W, a.K, a.N, 1, a.K, (uint64_t)a.N * a.K, 64, 128, false)) return cudaErrorUnknown;
+    auto kern = gemm_tc2_persistent_kernel<256, ST, 1, EpiVit, EWP>;
+    static int sms_tab[64] = {0};
+    const int slot = current_device_slot();
+    if (!sms_tab[slot]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+      if (e != cudaSuccess) return e;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms_tab[slot], cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int mt2 = (a.M + 2 * kTileM - 1) / (2 * kTileM);
+    int grid = sms_tab[slot] & ~1;
+    if (2 * mt2 * nt < grid) grid = 2 * mt2 * nt;
+    kern<<<dim3(grid), dim3(64 + 32 * EWP), smem2, st>>>(ta, tb2, g, ep, mt2, nt);
+    return cudaGetLastError();
+  }
   static int ew16 = -1;  // VAURA_AVCLIP_EW8=1: eight epilogue warps (A/B measurement)
   if (ew16 < 0) { const char* e = getenv("VAURA_AVCLIP_EW8"); ew16 = !(e && e[0] == '1'); }
   if (bn == 256) return ew16 ? launch_tc_persistent<256, 64, 4, 1, EpiVit, 1, 1, 16>(ta, tb, g, ep, mt, nt, st)
