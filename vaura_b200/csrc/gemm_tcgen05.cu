@@ -2248,7 +2248,11 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st) {
     // clusters of 4 or 2 CTAs (partial sums through DSMEM, rank-ordered: deterministic) and widen the 1536-wide tiles
     static int ck_on = -1;
     if (ck_on < 0) { const char* e = getenv("VAURA_PREFILL_CK"); ck_on = !(e && e[0] == '0'); }
-    const int bn = a.N % 256 == 0 && a.N >= 4096 ? 256 : (a.N % 128 == 0 ? 128 : 0);
+    // 256-wide tiles from N = 8192 (w1|w3); q|k|v (N = 4608) runs 128-wide tiles in pairs = 144 CTAs instead of 72: prefill of a
+    // 167-position window 3.59 -> 3.33 ms (128-wide for w1|w3 as well: 3.51).  VAURA_PREFILL_BN256_FROM overrides.
+    static int bn_thr = -1;
+    if (bn_thr < 0) { const char* e = getenv("VAURA_PREFILL_BN256_FROM"); bn_thr = e ? atoi(e) : 8192; }
+    const int bn = a.N % 256 == 0 && a.N >= bn_thr ? 256 : (a.N % 128 == 0 ? 128 : 0);
     const int kb = wk / 64;
     if (ck_on && bn) {
       const int tiles = mt_for(a.R) * (a.N / bn);
