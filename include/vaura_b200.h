@@ -199,12 +199,12 @@ typedef struct {
 } vaura_codec_dims;
 
 /* Folded (weight-norm removed) fp16 weights, channels-last GEMM layouts (vaura_b200/weights.py):
- *   code_tables [Kc][codebook_size][latent] f16 = codebook_k @ out_proj_k^T (+ bias_k folded into k=0)
+ *   code_tables [Kc][codebook_size][latent] f16 = codebook_k @ out_proj_k^T + bias_k (every table carries its own bias)
  *   conv weights  [taps][Cout][Cin] f16;  conv-transpose [stride][2][Cout][Cin] f16 (polyphase)
  *   biases / snake alphas f32.  `blob` is one device allocation; the offsets table indexes it.     */
 typedef struct {
   const void* blob;
-  const int64_t* offsets; /* host array, see vaura_b200/weights.py:CODEC_SLOTS for the slot order */
+  const int64_t* offsets; /* host array, slot order: vaura_b200/weights.py:pack_codec, listed in csrc/cabi.cu above struct vaura_codec */
   int32_t n_offsets;
 } vaura_codec_weights;
 

@@ -39,11 +39,18 @@ static thread_local bool g_capturing = false;
 
 // Everything a captured decode-step graph bakes in: pointers, shapes and sampling parameters.  A generate() call whose key
 // equals the cached one replays the instantiated graph instead of capturing, instantiating and re-encoding tensor maps.
+// VAURA_DETERMINISTIC=1 (read at every call): the bf16 step kernel adds its split-K partial sums in a fixed order instead of
+// with float atomics, so a repeated call returns the same bits (reproducibility)
+static int deterministic_mode() {
+  const char* ev = getenv("VAURA_DETERMINISTIC");
+  return ev && ev[0] == '1';
+}
+
 struct GraphKey {
   vaura_generate_params p;
   vaura_kv_cache kv;
   void* workspace;
-  int precision, device;
+  int precision, device, deterministic;
   bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 
@@ -141,6 +148,7 @@ struct Workspace {
   __nv_bfloat16 *xn_b, *q_b, *attn_b, *act_b;            // bf16 path (h and logits stay fp32)
   __nv_bfloat16 *x3, *act3;                              // fp32act path, tensor-core prefill: operands as three bf16 terms
   char* f2;                                              // bf16 path, decode_step_fused2: h_t | q_t | ssq_part | w2_part | w2_cnt
+  float* part;                                           // bf16 path, decode_step_fused_bf16: split-K partial sums of wo / w2
   size_t bytes;
 };
 
@@ -166,6 +174,7 @@ static Workspace carve(const vaura_sampler_dims& d, int rows, int max_pos, int p
     w.attn_b = (__nv_bfloat16*)take(R * d.d_model * 2);
     w.act_b = (__nv_bfloat16*)take(R * d.ffn_dim * 2);
     w.f2 = (char*)take(fused2_workspace_bytes(d.d_model));
+    w.part = (float*)take(fused_part_bytes(rows <= 128 ? rows : 1, d.d_model));
   } else {
     w.q = (float*)take(R * d.d_model * 4);
     w.attn = (float*)take(R * d.d_model * 4);
@@ -403,7 +412,10 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
       fa.h = ws.h; fa.xn = ws.xn_b; fa.q = ws.q_b; fa.attn = ws.attn_b; fa.act = ws.act_b; fa.logits = logits_dst;
       fa.kv = kv; fa.state = const_cast<StepState*>(state);
       fa.R = R; fa.L = d.num_layers; fa.D = d.d_model; fa.F = d.ffn_dim; fa.H = d.nhead; fa.NH = d.num_codebooks * d.vocab;
-      fa.wo_ksplit = 6; fa.w2_ksplit = 6;
+      fa.wo_ksplit = kFusedKsplit; fa.w2_ksplit = kFusedKsplit;
+      // split-K sums of wo / w2: float reductions into h (default), or - reproducible mode - one partial slice per K split,
+      // added in order by the CTA that normalises the row (measured 7 % slower per step: 1102 vs 1029 us at 64 rows)
+      fa.part = deterministic_mode() ? ws.part : nullptr;
       fa.eps = d.norm_eps; fa.scale = 1.0f / sqrtf((float)kHeadDim);
       { const char* tm = getenv("VAURA_PERSIST_TIMING"); fa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
       fa.step_times = ws.timing + 1024;
@@ -622,7 +634,7 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   // shapes and sampling parameters as the last one replays the graph instantiated then
   GraphKey key;
   memset(&key, 0, sizeof(key));
-  key.p = *p; key.kv = *kv; key.workspace = workspace; key.precision = precision;
+  key.p = *p; key.kv = *kv; key.workspace = workspace; key.precision = precision; key.deterministic = deterministic_mode();
   cudaGetDevice(&key.device);
   if (s->graph_exec && s->graph_key == key) {
     loop_mark(0, nsteps);
@@ -711,7 +723,7 @@ extern "C" int vaura_sample_logits(const float* logits, int32_t rows, int32_t K,
 }
 
 // ---- codec ------------------------------------------------------------------------------------------
-// slot order of the weight blob (must match vaura_b200/weights.py: CODEC_SLOTS)
+// slot order of the weight blob (written by vaura_b200/weights.py: pack_codec)
 //   0 code_tables f16 [Kc][Vc][latent]     1 conv_in W f16 [7][C0][latent]     2 conv_in bias f32
 //   per block i (base 3 + 21 i): +0 snake alpha f32 [Cin]  +1 convT W f16 [s][2][Cout][Cin]  +2 convT bias
 //       per residual unit j (base +3 + 6 j): +0 alpha1  +1 conv7 W f16 [7][C][C]  +2 bias  +3 alpha2

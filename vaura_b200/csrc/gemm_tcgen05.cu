@@ -1292,6 +1292,7 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 namespace fused {
 constexpr int kKsub = 4, kBlockK = 64;
 constexpr int kAccCols = 64;  // TMEM columns of the accumulator (BN <= 64)
+constexpr int kMaxParts = kFusedKsplit;  // K slices of a residual GEMM (wo, w2) = partial-sum slices a row CTA adds up
 constexpr int kBMax = 64 * kBlockK * 2;                   // 8 KB weight sub-tile (BN = 64; BN = 32 uses half of it)
 // TM = UMMA M = rows of the activation tile: 64 (up to 64 sequence rows) or 128 (up to 128, e.g. 64 clips with CFG)
 template <int TM>
@@ -1519,7 +1520,10 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   // ---- RMSNorm of the residual row `cta` (llama.py:147-158): fp32 math, bf16 output = the next GEMM's A operand.
   //      embed = true (first phase of a step with fuse_io): the row is built here from the conditioning row and the 9
   //      folded token tables (llama.py:455-472, what embed_kernel does) and stored to h on the way ----
-  auto rmsnorm_phase = [&](const float* w, bool embed) {
+  //      nparts > 0 (after a split-K residual GEMM with a.part): the row is first completed, h[row] += part[0][row] + ... +
+  //      part[nparts-1][row] in that fixed order (every output element has one owner: no float atomics, results are
+  //      reproducible from run to run), and stored back ----
+  auto rmsnorm_phase = [&](const float* w, bool embed, int nparts = 0) {
     if (cta < R) {
       float* red = scratch;
       float* hrow = a.h + (size_t)cta * D;
@@ -1539,6 +1543,16 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
         if (c < n4) {
           if (!embed) {
             v[i] = __ldcg(reinterpret_cast<const float4*>(hrow) + c);
+            if (nparts > 0) {
+              float4 pv[fused::kMaxParts];
+#pragma unroll
+              for (int sp = 0; sp < fused::kMaxParts; ++sp)
+                if (sp < nparts) pv[sp] = __ldcg(reinterpret_cast<const float4*>(a.part + ((size_t)sp * R + cta) * D) + c);
+#pragma unroll
+              for (int sp = 0; sp < fused::kMaxParts; ++sp)
+                if (sp < nparts) { v[i].x += pv[sp].x; v[i].y += pv[sp].y; v[i].z += pv[sp].z; v[i].w += pv[sp].w; }
+              reinterpret_cast<float4*>(hrow)[c] = v[i];
+            }
           } else {
             const int C = a.cond_dim, TD = D - C, f = 4 * c;
             if (f < C) {
@@ -1836,6 +1850,15 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     for (int t = cta; t < a.NH / 64; t += G) prefetch_rows(a.w_heads, (size_t)t * 64, 64, D, 0, D);
   };
 
+  // where a wo / w2 tile of K slice `split` puts its 64 x 64 sums: its own slice of a.part with plain stores (the row CTAs
+  // add the slices in order, rmsnorm_phase), or - a.part == nullptr, the round-1 scheme kept for A/B runs - straight into h
+  // with vector float reductions, whose order is not fixed
+  auto resid_target = [&](int split) {
+    ep.N = D; ep.ldo = D; ep.perm_S = 0;
+    if (a.part) { ep.mode = EPI_STORE; ep.out_f32 = a.part + (size_t)split * R * D; ep.atomic = 0; }
+    else { ep.mode = EPI_RESID; ep.out_f32 = a.h; ep.atomic = 1; }
+  };
+
   prefetch_wqkv(0);
   rmsnorm_phase(a.attn_norm, a.fuse_io);
   sync_all();
@@ -1856,14 +1879,14 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       prefetch_w13(l);
       if (cta < (int)tiles_wo) {
         const int split = cta / nt, kb = D / kBlockK;
-        ep.mode = EPI_RESID; ep.N = D; ep.out_f32 = a.h; ep.ldo = D; ep.atomic = 1;
+        resid_target(split);
         fused_gemm_tile<64, TM>(pp, &tm_attn, &tm_wo, l, (cta % nt) * 64, kb * split / a.wo_ksplit, kb * (split + 1) / a.wo_ksplit, ep);
         tiles_arrive();
       }
       tiles_seen += tiles_wo;
       if (cta < R) {
         tiles_wait();
-        rmsnorm_phase(a.ffn_norm + (size_t)l * D, false);
+        rmsnorm_phase(a.ffn_norm + (size_t)l * D, false, a.part ? a.wo_ksplit : 0);
       }
     }
     sync_all();
@@ -1881,14 +1904,14 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       if (l + 1 < a.L) prefetch_wqkv(l + 1); else prefetch_heads();
       if (cta < (int)tiles_w2) {
         const int split = cta / nt, kb = F / kBlockK;
-        ep.mode = EPI_RESID; ep.N = D; ep.out_f32 = a.h; ep.ldo = D; ep.atomic = 1;
+        resid_target(split);
         fused_gemm_tile<64, TM>(pp, &tm_act, &tm_w2, l, (cta % nt) * 64, kb * split / a.w2_ksplit, kb * (split + 1) / a.w2_ksplit, ep);
         tiles_arrive();
       }
       tiles_seen += tiles_w2;
       if (cta < R) {
         tiles_wait();
-        rmsnorm_phase(l + 1 < a.L ? a.attn_norm + (size_t)(l + 1) * D : a.final_norm, false);
+        rmsnorm_phase(l + 1 < a.L ? a.attn_norm + (size_t)(l + 1) * D : a.final_norm, false, a.part ? a.w2_ksplit : 0);
       }
     }
     sync_all();
@@ -2151,6 +2174,8 @@ bool fused_step_supported(int R, int D, int F, int NH) {
   return R >= 1 && R <= 128 && D % 64 == 0 && F % 64 == 0 && NH % 64 == 0 && (3 * D) % 32 == 0 && D / 4 <= 2 * kGemmThreads;
 }
 
+size_t fused_part_bytes(int R, int D) { return (size_t)kFusedKsplit * R * D * sizeof(float); }
+
 template <int TM>
 static cudaError_t launch_decode_fused_t(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
                                          const void* w_heads, cudaStream_t st) {
@@ -2169,6 +2194,8 @@ static cudaError_t launch_decode_fused_t(const FusedStepArgs& a, const void* wqk
   }
   const int sms = sms_tab[slot];
   const int need = a.D / 64 * (a.wo_ksplit > a.w2_ksplit ? a.wo_ksplit : a.w2_ksplit);
+  if (a.wo_ksplit < 1 || a.w2_ksplit < 1 || (a.part && (a.wo_ksplit > kFusedKsplit || a.w2_ksplit > kFusedKsplit)))
+    return cudaErrorInvalidValue;
   // one tile per CTA per phase, one residual row per CTA in the norm phases
   if (3 * a.D / 32 > sms || 2 * a.F / 64 > sms || need > sms || a.R > sms) return cudaErrorInvalidValue;
   // attention phase: at most two (row, head) items per warp, lane i holds page i, 16-position runs inside a page

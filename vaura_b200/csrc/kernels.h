@@ -125,6 +125,7 @@ struct FusedStepArgs {
   float* h;                  // [R][D] residual stream (written by embed_kernel before this kernel)
   __nv_bfloat16 *xn, *q, *attn, *act;  // [R][D], [R][D], [R][D], [R][F]
   float* logits;             // [R][NH]
+  float* part;               // [max(wo_ksplit, w2_ksplit)][R][D] split-K partial sums of the two residual GEMMs (fp32)
   KvView kv;                 // bf16 pages
   StepState* state;
   int R, L, D, F, H, NH;     // rows, layers, d_model, ffn, heads, K*V logits per row
@@ -146,6 +147,8 @@ struct FusedStepArgs {
 };
 
 bool fused_step_supported(int R, int D, int F, int NH);
+constexpr int kFusedKsplit = 6;  // K slices of the wo / w2 tiles of decode_step_fused_bf16 (24 x 6 = 144 tiles: one per CTA)
+size_t fused_part_bytes(int R, int D);
 cudaError_t launch_decode_fused_bf16(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
                                      const void* w_heads, cudaStream_t st);
 
