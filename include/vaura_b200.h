@@ -97,15 +97,7 @@ typedef struct {
   const float* fc1;         /* [cond_dim][cond_in]  cls_embeddings.projection.fc1.weight           */
   const float* fc2;         /* [cond_dim][cond_dim] cls_embeddings.projection.fc2.weight           */
   const float* empty_video_emb; /* [cond_dim] (llama.py:336-338) */
-  /* Optional second copy of the five matrices in K-block-major order for the tensor-core persistent decode kernel
-   * (rows <= 2): X_t[l][kb][n][64] = X[l][n][64*kb .. 64*kb+63], so the [rows x 64] tile a CTA fetches per K block is
-   * one contiguous chunk.  NULL disables that kernel (the SIMT persistent kernel is used instead). */
-  const uint16_t* wqkv_t;
-  const uint16_t* wo_t;
-  const uint16_t* w13_t;
-  const uint16_t* w2_t;
-  const uint16_t* w_heads_t;
-  /* Optional third copy for the cluster-persistent decode kernel (rows <= 2; csrc/decode_cluster.cu), as 12288-byte
+  /* Optional second copy for the cluster-persistent decode kernel (rows <= 2; csrc/decode_cluster.cu), as 12288-byte
    * slots of 16x16 bf16 tiles in mma.m16n8k16 A-fragment register order, in consumption order:
    *   [16 heads][4 ranks][L][18 q|k|v + 6 wo slots]   shared by the two clusters that serve a head
    *   [128 CTAs][L x (16 w13 + 8 w2) + 18 heads slots]

@@ -31,7 +31,7 @@ class SamplerDimsC(C.Structure):
 class SamplerWeightsC(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "wqkv", "wo", "w13", "w2", "w_heads", "attn_norm", "ffn_norm", "final_norm", "tok_tables", "rope",
-        "fc1", "fc2", "empty_video_emb", "wqkv_t", "wo_t", "w13_t", "w2_t", "w_heads_t", "wstream")]
+        "fc1", "fc2", "empty_video_emb", "wstream")]
 
 
 class KvCacheC(C.Structure):

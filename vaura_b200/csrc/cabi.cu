@@ -560,10 +560,9 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   // rows <= 2: cluster variant (decode_cluster.cu) when the weight streams were packed.  Without a prompt it also runs
   // the first position (a decode step with an empty KV cache), so the whole clip is one kernel per column.
   const char* nocl = getenv("VAURA_NO_CLUSTER");
-  const char* ptc = getenv("VAURA_PERSIST_TC");
   const char* ptm = getenv("VAURA_PERSIST_TIMING");
   const bool phase_timing = ptm && ptm[0] == '1';
-  const bool use_cluster = persist && s->w.wstream && !(nocl && nocl[0] == '1') && !(ptc && ptc[0] == '1') &&
+  const bool use_cluster = persist && s->w.wstream && !(nocl && nocl[0] == '1') &&
                            cluster_supported(rows, d.num_layers, d.d_model, d.ffn_dim, d.nhead, K * d.vocab, kv->page_size,
                                              d.cond_dim, S) &&
                            cluster_launchable(rows, phase_timing);
@@ -592,7 +591,6 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     PersistArgs pa{};
     const vaura_sampler_weights& w = s->w;
     pa.wqkv = w.wqkv; pa.wo = w.wo; pa.w13 = w.w13; pa.w2 = w.w2; pa.w_heads = w.w_heads; pa.attn_norm = w.attn_norm;
-    pa.wqkv_t = w.wqkv_t; pa.wo_t = w.wo_t; pa.w13_t = w.w13_t; pa.w2_t = w.w2_t; pa.w_heads_t = w.w_heads_t;
     pa.ffn_norm = w.ffn_norm; pa.final_norm = w.final_norm; pa.tok_tables = w.tok_tables; pa.rope = w.rope;
     pa.seq = p->sequence; pa.cond_rows = p->cond_rows; pa.h = ws.h; pa.q = ws.q; pa.act = ws.act; pa.logits = ws.logits;
     pa.attn_part = ws.attn_part; pa.kv = kvv; pa.state = ws.state; pa.sample = sa; pa.sample.state = nullptr;
@@ -602,15 +600,6 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     { const char* tm = getenv("VAURA_PERSIST_TIMING"); pa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
     pa.step_times = ws.timing + 1024;  // workspace bytes [256 + 8192, ...): one timestamp per generated column
     { const char* tc = getenv("VAURA_TIMING_CTA"); pa.timing_cta = tc ? atoi(tc) : 0; }
-    int sms = 0, dev = 0;
-    CU(cudaGetDevice(&dev));
-    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    // The tensor-core variant (decode_persistent_tc.cu) is parity-green but measured slower than the SIMT variant on
-    // B200 (1.07 vs 0.80 ms per step at one row: its phases are bound by the number of tiny tcgen05.mma / TMA
-    // operations per K block); it is opt-in until the work partition is changed.
-    const char* tc = getenv("VAURA_PERSIST_TC");
-    const bool use_tc = (tc && tc[0] == '1') && w.wqkv_t && w.wo_t && w.w13_t && w.w2_t && w.w_heads_t &&
-                        persistent_tc_supported(rows, d.d_model, d.ffn_dim, kv->page_size, K * d.vocab / 2, d.ffn_dim, sms);
     if (use_cluster) {
       pa.wstream = w.wstream;
       pa.xfix = ws.xfix;
@@ -622,7 +611,6 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     loop_mark(0, nsteps);
     for (int i = 0; i < nsteps; ++i) {
       if (use_cluster) CUL(launch_decode_cluster(pa, rows, st));
-      else if (use_tc) CUL(launch_decode_persistent_tc(pa, rows, st));
       else CUL(launch_decode_persistent(pa, rows, st));
     }
     loop_mark(1, nsteps);

@@ -228,7 +228,6 @@ cudaError_t init_decode_kernels();
 // persistent decode-step kernel (decode_persistent.cu)
 struct PersistArgs {
   const uint16_t *wqkv, *wo, *w13, *w2, *w_heads;
-  const uint16_t *wqkv_t, *wo_t, *w13_t, *w2_t, *w_heads_t;  // K-block-major copies (tensor-core variant)
   const uint8_t* wstream;       // fragment-ordered weight streams (cluster variant, decode_cluster.cu)
   long long* xfix;              // cluster variant: residual buffers [2L+1][rows][D] (word = fixed-point sum << 6 | count)
   const float *attn_norm, *ffn_norm, *final_norm, *tok_tables, *rope;
@@ -250,9 +249,6 @@ struct PersistArgs {
 bool persistent_supported(int rows, int D, int F, int page_size);
 size_t persistent_attn_part_bytes(int rows, int H);
 cudaError_t launch_decode_persistent(PersistArgs& a, int rows, cudaStream_t st);
-// tensor-core variant (decode_persistent_tc.cu)
-bool persistent_tc_supported(int rows, int D, int F, int page_size, int head_pairs, int f_pairs, int sms);
-cudaError_t launch_decode_persistent_tc(PersistArgs& a, int rows, cudaStream_t st);
 
 // cluster variant (decode_cluster.cu): 32 clusters x 4 CTAs, mma.sync from fragment-ordered weight streams
 bool cluster_supported(int rows, int L, int D, int F, int H, int head_rows, int page_size, int cond_dim, int max_ctx);

@@ -142,7 +142,7 @@ class Transformer(torch.nn.Module):
         w = self.weights
         wc = _cabi.SamplerWeightsC(*[w[n].data_ptr() if n in w else None for n in (
             "wqkv", "wo", "w13", "w2", "w_heads", "attn_norm", "ffn_norm", "final_norm", "tok_tables", "rope", "fc1",
-            "fc2", "empty_video_emb", "wqkv_t", "wo_t", "w13_t", "w2_t", "w_heads_t", "wstream")])
+            "fc2", "empty_video_emb", "wstream")])
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             _cabi.check(lib.vaura_sampler_create(C.byref(dc), C.byref(wc), C.byref(h)), "vaura_sampler_create")

@@ -75,15 +75,6 @@ def pack_sampler(sd: Dict[str, torch.Tensor], dims: SamplerDims, device) -> Dict
     out["w2"] = bf16_stack([f"layers.{i}.feed_forward.w2.weight" for i in range(L)])
     out["w_heads"] = torch.cat([sd[f"lm_heads.{k}.weight"].detach().to(device=device, dtype=torch.bfloat16)
                                 for k in range(K)]).contiguous()
-    # K-block-major copies for the tensor-core persistent decode kernel: [L][K/64][N][64]
-    def kblock_major(w):  # (..., N, K) -> (..., K/64, N, 64)
-        *lead, N, K = w.shape
-        return w.reshape(*lead, N, K // 64, 64).transpose(-3, -2).contiguous()
-
-    import os
-    if os.environ.get("VAURA_PERSIST_TC") == "1" and d % 64 == 0 and F % 64 == 0:
-        for name in ("wqkv", "wo", "w13", "w2", "w_heads"):
-            out[name + "_t"] = kblock_major(out[name])
     if cluster_stream_supported(dims):
         out["wstream"] = pack_cluster_stream(out, dims)
     out["attn_norm"] = torch.stack([f32(f"layers.{i}.attention_norm.weight") for i in range(L)]).to(device).contiguous()
