@@ -589,8 +589,7 @@ cudaError_t launch_vit_cls_attn(const void* qkv, void* out, int seqs, int len, i
   return cudaGetLastError();
 }
 cudaError_t launch_vit_space_attn(const void* qkv, void* out, int S, int t, int n, int heads, cudaStream_t st) {
-  static int simt = -1;  // VAURA_AVCLIP_SIMT_ATTN=1: the SIMT kernel for every shape
-  if (simt < 0) { const char* e = getenv("VAURA_AVCLIP_SIMT_ATTN"); simt = e && e[0] == '1'; }
+  const bool simt = knobs().avclip_simt_attn;  // the SIMT kernel for every shape
   if (!simt && n + 1 <= 16 * 13 && n + 1 > 16 * 12) {  // 14 x 14 patches + CLS = 197 keys
     using G = SpTc<13>;
     static bool attr_tc[64] = {false};

@@ -39,18 +39,16 @@ static thread_local bool g_capturing = false;
 
 // Everything a captured decode-step graph bakes in: pointers, shapes and sampling parameters.  A generate() call whose key
 // equals the cached one replays the instantiated graph instead of capturing, instantiating and re-encoding tensor maps.
-// VAURA_DETERMINISTIC=1 (read at every call): the bf16 step kernel adds its split-K partial sums in a fixed order instead of
-// with float atomics, so a repeated call returns the same bits (reproducibility)
-static int deterministic_mode() {
-  const char* ev = getenv("VAURA_DETERMINISTIC");
-  return ev && ev[0] == '1';
-}
+// VAURA_DETERMINISTIC=1: the bf16 step kernel adds its split-K partial sums in a fixed order instead of with float atomics,
+// so a repeated call returns the same bits (reproducibility)
+static int deterministic_mode() { return knobs().deterministic; }
 
 struct GraphKey {
   vaura_generate_params p;
   vaura_kv_cache kv;
   void* workspace;
-  int precision, device, deterministic;
+  int precision, device;
+  Knobs knobs;  // a step captured under other knob settings is not replayed
   bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 
@@ -73,6 +71,7 @@ extern "C" unsigned long long vaura_launch_count(void) { return g_launches; }
 
 extern "C" int vaura_linear_bf16(const uint16_t* A, const uint16_t* W, float* y, int32_t R, int32_t N, int32_t K,
                                  int32_t block_n, void* stream) {
+  refresh_knobs();
   if (!A || !W || !y || R <= 0 || N <= 0 || K <= 0 || (K % 64) || block_n <= 0 || (N % block_n))
     return fail(VAURA_ERR_INVALID, "bad argument");
   LinearTcArgs g{};
@@ -83,6 +82,7 @@ extern "C" int vaura_linear_bf16(const uint16_t* A, const uint16_t* W, float* y,
 }
 
 extern "C" int vaura_gemv_bf16w(const uint16_t* W, const float* x, float* y, int32_t N, int32_t K, int32_t R, void* stream) {
+  refresh_knobs();
   if (!W || !x || !y || N <= 0 || K <= 0 || R <= 0 || (N & 1) || (K & 7)) return fail(VAURA_ERR_INVALID, "bad argument");
   CU(init_decode_kernels());
   GemvArgs g{};
@@ -93,6 +93,7 @@ extern "C" int vaura_gemv_bf16w(const uint16_t* W, const float* x, float* y, int
 
 extern "C" int vaura_sampler_create(const vaura_sampler_dims* dims, const vaura_sampler_weights* weights,
                                     vaura_sampler** out) {
+  refresh_knobs();
   if (!dims || !weights || !out) return fail(VAURA_ERR_INVALID, "null argument");
   const vaura_sampler_dims& d = *dims;
   if (d.nhead <= 0 || d.d_model % d.nhead != 0 || d.d_model / d.nhead != kHeadDim)
@@ -133,6 +134,7 @@ extern "C" void vaura_sampler_destroy(vaura_sampler* s) {
 
 extern "C" int vaura_sampler_cond_project(vaura_sampler* s, const float* feats, int32_t rows, int32_t tv,
                                           float* rows_out, void* stream) {
+  refresh_knobs();
   if (!s || !feats || !rows_out || rows <= 0 || tv <= 0) return fail(VAURA_ERR_INVALID, "bad argument");
   CUL(launch_cond_project(feats, s->w.fc1, s->w.fc2, s->w.empty_video_emb, rows_out, rows, tv, s->d.cond_in,
                          s->d.cond_dim, (cudaStream_t)stream));
@@ -237,9 +239,7 @@ static int transformer_pass(const vaura_sampler* s, const Workspace& ws, const i
   const vaura_sampler_weights& w = s->w;
   const int R = rows * npos;
   {
-    static int tc3 = -1;  // VAURA_PREFILL_TC=0: keep multi-position passes on the GEMV kernels
-    if (tc3 < 0) { const char* ev = getenv("VAURA_PREFILL_TC"); tc3 = !(ev && ev[0] == '0'); }
-    if (tc3 && npos > 1 && R >= 16 && ws.x3 && d.d_model % 64 == 0 && d.ffn_dim % 64 == 0)
+    if (knobs().prefill_tc && npos > 1 && R >= 16 && ws.x3 && d.d_model % 64 == 0 && d.ffn_dim % 64 == 0)
       return transformer_pass_tc3(s, ws, seq, batch, S, cond_rows, rows, npos, pos0, state, kv, logits_dst, logits_all, st);
   }
   EmbedArgs e{};
@@ -365,16 +365,13 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
   // rows <= 64, one new position per row (graph-replayed decode step): one cooperative kernel for all layers + heads
   // and, when the caller hands in the sampling arguments, for the embedding and the sampling stage as well
   {
-    static int fused_on = -1, fuse_io_on = -1;
-    if (fused_on < 0) { const char* ev = getenv("VAURA_FUSED_STEP"); fused_on = !(ev && ev[0] == '0'); }
-    if (fuse_io_on < 0) { const char* ev = getenv("VAURA_FUSED_IO"); fuse_io_on = !(ev && ev[0] == '0'); }
+    const bool fused_on = knobs().fused_step, fuse_io_on = knobs().fused_io;
     if (fused_on && npos == 1 && !logits_all && state && fused_step_supported(R, d.d_model, d.ffn_dim, d.num_codebooks * d.vocab)) {
       const bool io = fuse_io_on && fuse_sample && sampled && d.cond_dim % 4 == 0 && (d.d_model - d.cond_dim) % 4 == 0;
       // second design (decode_fused2.cu): swap-AB tiles, K split inside CTA pairs, norms folded into their neighbours.
       // Parity-green but measured slower than decode_step_fused_bf16 (profiles/r02_fused2_timeline.summary.txt: 70 vs 40 us
       // per layer at position 127), so it is opt-in: VAURA_FUSED2=1.
-      static int fused2_on = -1;
-      if (fused2_on < 0) { const char* ev = getenv("VAURA_FUSED2"); fused2_on = (ev && ev[0] == '1'); }
+      const bool fused2_on = knobs().fused2;
       int sms2 = 0, dev2 = 0;
       cudaGetDevice(&dev2);
       cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, dev2);
@@ -394,10 +391,10 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
         fa.kv = kv; fa.state = const_cast<StepState*>(state);
         fa.R = R; fa.L = d.num_layers; fa.D = d.d_model; fa.F = d.ffn_dim; fa.H = d.nhead; fa.NH = d.num_codebooks * d.vocab;
         fa.eps = d.norm_eps; fa.scale = 1.0f / sqrtf((float)kHeadDim);
-        { const char* tm = getenv("VAURA_PERSIST_TIMING"); fa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
+        fa.timing = knobs().phase_timing ? ws.timing : nullptr;
         fa.step_times = ws.timing + 1024;
-        { const char* tc = getenv("VAURA_TIMING_CTA"); fa.timing_cta = tc ? atoi(tc) : 0; }
-        { const char* fl = getenv("VAURA_FUSED2_FLAGS"); fa.flags = fl ? atoi(fl) : 0; }
+        fa.timing_cta = knobs().timing_cta;
+        fa.flags = knobs().fused2_flags;
         fa.seq = seq; fa.cond_rows = cond_rows; fa.tables = w.tok_tables; fa.batch = batch; fa.Kc = d.num_codebooks; fa.S = S;
         fa.vocab = d.vocab; fa.cond_dim = d.cond_dim; fa.cond_tokens = d.cond_tokens; fa.atpvf = d.audio_tokens_per_video_frame;
         fa.sample = *fuse_sample;
@@ -417,9 +414,9 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
       // added in order by the CTA that normalises the row (measured 7 % slower per step: 1102 vs 1029 us at 64 rows)
       fa.part = deterministic_mode() ? ws.part : nullptr;
       fa.eps = d.norm_eps; fa.scale = 1.0f / sqrtf((float)kHeadDim);
-      { const char* tm = getenv("VAURA_PERSIST_TIMING"); fa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
+      fa.timing = knobs().phase_timing ? ws.timing : nullptr;
       fa.step_times = ws.timing + 1024;
-      { const char* tc = getenv("VAURA_TIMING_CTA"); fa.timing_cta = tc ? atoi(tc) : 0; }
+      fa.timing_cta = knobs().timing_cta;
       fa.fuse_io = io ? 1 : 0;
       if (io) {
         fa.seq = seq; fa.cond_rows = cond_rows; fa.tables = w.tok_tables; fa.batch = batch; fa.Kc = d.num_codebooks; fa.S = S;
@@ -436,23 +433,14 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
   const size_t D = d.d_model, F = d.ffn_dim;
   // narrow N tiles when there is a single M tile so the weight stream is spread over all SMs
   const bool small = R <= 128;
-  const char* nopdl = getenv("VAURA_NO_PDL");
   // Programmatic dependent launch is OFF by default: measured on B200 it gave no step-time gain, and an explicit
   // griddepcontrol.launch_dependents inside the GEMM made dependents observe stale activations.
   // VAURA_PDL_MODE bits: 1 attribute+wait, 2 GEMM trigger after its wait, 4 weight prefetch before the wait,
   // 8 trigger in the small kernels.
-  int pdl = 0;
-  (void)nopdl;
-  { const char* m = getenv("VAURA_PDL_MODE"); if (m) pdl = atoi(m); }
-  const char* nosplit = getenv("VAURA_NO_SPLITK");
-  const bool splitk = small && !(nosplit && nosplit[0] == '1');
+  const int pdl = knobs().pdl_mode;
+  const bool splitk = small && !knobs().no_splitk;
   // tuning knobs of the two residual GEMMs (N tile, split-K factor)
-  static int wo_bn = 0, wo_ks = 0, w2_bn = 0, w2_ks = 0;
-  if (!wo_bn) {
-    auto envi = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
-    wo_bn = envi("VAURA_WO_BN", 64); wo_ks = envi("VAURA_WO_KSPLIT", 6);
-    w2_bn = envi("VAURA_W2_BN", 64); w2_ks = envi("VAURA_W2_KSPLIT", 6);  // 24 x 6 = 144 CTAs: one wave (8 -> 192 CTAs was 6 % slower)
-  }
+  const int wo_bn = knobs().wo_bn, wo_ks = knobs().wo_ksplit, w2_bn = knobs().w2_bn, w2_ks = knobs().w2_ksplit;
   for (int l = 0; l < d.num_layers; ++l) {
     LinearTcArgs g{};
     g.state = state; g.pos0 = pos0; g.npos = npos; g.R = R; g.layer = l; g.d_model = d.d_model; g.kv = kv; g.rope = w.rope;
@@ -506,9 +494,9 @@ static int run_pass(int precision, const vaura_sampler* s, const Workspace& ws, 
 static int check_kv(const vaura_sampler* s, const vaura_kv_cache* kv, int want_dtype) {
   if (!kv || !kv->pages || !kv->page_table) return fail(VAURA_ERR_INVALID, "kv cache missing");
   {
-    const char* ap = getenv("VAURA_ANY_PAGE");  // experiment: any power-of-two page >= 16 on the bf16 path
+    // VAURA_ANY_PAGE=1 (experiment): any power-of-two page >= 16 on the bf16 path
     const bool pow2 = kv->page_size >= 16 && !(kv->page_size & (kv->page_size - 1));
-    if (kv->page_size != 16 && kv->page_size != 32 && !(ap && ap[0] == '1' && pow2))
+    if (kv->page_size != 16 && kv->page_size != 32 && !(knobs().any_page && pow2))
       return fail(VAURA_ERR_INVALID, "page_size must be 16 or 32");
   }
   if (kv->max_pages_per_seq * kv->page_size < s->d.block_size)
@@ -520,6 +508,7 @@ static int check_kv(const vaura_sampler* s, const vaura_kv_cache* kv, int want_d
 
 extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_params* p, const vaura_kv_cache* kv,
                                       void* workspace, size_t workspace_bytes, void* stream) {
+  refresh_knobs();
   if (!s || !p || !workspace) return fail(VAURA_ERR_INVALID, "null argument");
   const vaura_sampler_dims& d = s->d;
   const int K = d.num_codebooks, S = p->timesteps + K;
@@ -554,22 +543,18 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   sa.top_p = p->top_p; sa.seed_lo = (uint32_t)p->seed; sa.seed_hi = (uint32_t)(p->seed >> 32);
   sa.stream_id = p->stream_id;
 
-  const char* no_persist = getenv("VAURA_NO_PERSISTENT");
   const bool persist = precision == VAURA_PRECISION_FP32ACT && persistent_supported(rows, d.d_model, d.ffn_dim, kv->page_size) &&
-                       !(no_persist && no_persist[0] == '1');
+                       !knobs().no_persistent;
   // rows <= 2: cluster variant (decode_cluster.cu) when the weight streams were packed.  Without a prompt it also runs
   // the first position (a decode step with an empty KV cache), so the whole clip is one kernel per column.
-  const char* nocl = getenv("VAURA_NO_CLUSTER");
-  const char* ptm = getenv("VAURA_PERSIST_TIMING");
-  const bool phase_timing = ptm && ptm[0] == '1';
-  const bool use_cluster = persist && s->w.wstream && !(nocl && nocl[0] == '1') &&
+  const bool phase_timing = knobs().phase_timing;
+  const bool use_cluster = persist && s->w.wstream && !knobs().no_cluster &&
                            cluster_supported(rows, d.num_layers, d.d_model, d.ffn_dim, d.nhead, K * d.vocab, kv->page_size,
                                              d.cond_dim, S) &&
                            cluster_launchable(rows, phase_timing);
   // Without a prompt the first pass is the decode step of position 0 with an empty K/V cache: the step kernels run it as
   // their first launch (cluster kernel; graph-replayed bf16 step, fused or not) instead of ~170 separate first-pass kernels
-  static int bf16_first = -1;  // VAURA_BF16_STEP_FIRST=0: keep the separate first pass on the bf16 path
-  if (bf16_first < 0) { const char* e = getenv("VAURA_BF16_STEP_FIRST"); bf16_first = !(e && e[0] == '0'); }
+  const bool bf16_first = knobs().bf16_step_first;  // 0: keep the separate first pass on the bf16 path
   const bool cluster_first = npre == 1 && (use_cluster || (bf16_first && !persist && precision == VAURA_PRECISION_BF16));
   int nsteps = p->end_offset - (p->start_offset + 1);
   if (!cluster_first) {
@@ -597,15 +582,15 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
     pa.L = d.num_layers; pa.D = d.d_model; pa.F = d.ffn_dim; pa.H = d.nhead; pa.Kc = K; pa.V = d.vocab; pa.S = S;
     pa.batch = p->batch; pa.cond_dim = d.cond_dim; pa.cond_tokens = d.cond_tokens; pa.atpvf = d.audio_tokens_per_video_frame;
     pa.eps = d.norm_eps; pa.scale = 1.0f / sqrtf((float)kHeadDim);
-    { const char* tm = getenv("VAURA_PERSIST_TIMING"); pa.timing = (tm && tm[0] == '1') ? ws.timing : nullptr; }
+    pa.timing = phase_timing ? ws.timing : nullptr;
     pa.step_times = ws.timing + 1024;  // workspace bytes [256 + 8192, ...): one timestamp per generated column
-    { const char* tc = getenv("VAURA_TIMING_CTA"); pa.timing_cta = tc ? atoi(tc) : 0; }
+    pa.timing_cta = knobs().timing_cta;
     if (use_cluster) {
       pa.wstream = w.wstream;
       pa.xfix = ws.xfix;
-      { const char* rl = getenv("VAURA_CLUSTER_RING"); pa.prefetch_ahead = rl ? atoi(rl) : 0; }
-      { const char* pc = getenv("VAURA_CLUSTER_L2_AHEAD"); pa.pace_cycles = pc ? atoi(pc) : -1; }
-      { const char* tu = getenv("VAURA_CLUSTER_TAIL_UNITS"); pa.tail_units = tu ? atoi(tu) : 0; }
+      pa.prefetch_ahead = knobs().cluster_ring;
+      pa.pace_cycles = knobs().cluster_l2_ahead;
+      pa.tail_units = knobs().cluster_tail_units;
       CU(cudaMemsetAsync(ws.xfix, 0, cluster_xfix_bytes(rows, d.num_layers), st));
     }
     loop_mark(0, nsteps);
@@ -622,7 +607,7 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   // shapes and sampling parameters as the last one replays the graph instantiated then
   GraphKey key;
   memset(&key, 0, sizeof(key));
-  key.p = *p; key.kv = *kv; key.workspace = workspace; key.precision = precision; key.deterministic = deterministic_mode();
+  key.p = *p; key.kv = *kv; key.workspace = workspace; key.precision = precision; key.knobs = knobs();
   cudaGetDevice(&key.device);
   if (s->graph_exec && s->graph_key == key) {
     loop_mark(0, nsteps);
@@ -678,6 +663,7 @@ extern "C" int vaura_sampler_last_loop_ms(vaura_sampler* s, float* ms_out, int32
 extern "C" int vaura_sampler_forward(vaura_sampler* s, const int32_t* sequence, const float* cond_rows, int32_t rows,
                                      int32_t S, float* logits_out, const vaura_kv_cache* kv, int32_t precision,
                                      void* workspace, size_t workspace_bytes, void* stream) {
+  refresh_knobs();
   if (!s || !sequence || !cond_rows || !logits_out || !workspace || rows <= 0 || S <= 0)
     return fail(VAURA_ERR_INVALID, "bad argument");
   const vaura_sampler_dims& d = s->d;
@@ -698,6 +684,7 @@ extern "C" int vaura_sample_logits(const float* logits, int32_t rows, int32_t K,
                                    float cfg_scale, int32_t use_sampling, float temp, int32_t top_k, float top_p,
                                    uint64_t seed, const int32_t* clip_ids, int32_t offset, int32_t* tokens_out,
                                    float* probs_out, void* stream) {
+  refresh_knobs();
   if (!logits || !tokens_out || rows <= 0 || K <= 0) return fail(VAURA_ERR_INVALID, "bad argument");
   if (V != 1024) return fail(VAURA_ERR_UNSUPPORTED, "vocab %d unsupported (sampling kernel is built for 1024)", V);
   SampleArgs sa{};
@@ -737,6 +724,7 @@ static int conv_dispatch(const vaura_codec* c, const ConvArgs& a, int tap_index,
 }
 
 extern "C" int vaura_codec_create(const vaura_codec_dims* dims, const vaura_codec_weights* w, vaura_codec** out) {
+  refresh_knobs();
   if (!dims || !w || !out || !w->blob || !w->offsets) return fail(VAURA_ERR_INVALID, "null argument");
   const int want = 3 + 21 * dims->n_blocks + 3 + 1;
   if (w->n_offsets != want) return fail(VAURA_ERR_INVALID, "codec blob has %d slots, expected %d", w->n_offsets, want);
@@ -761,8 +749,7 @@ extern "C" int vaura_codec_create(const vaura_codec_dims* dims, const vaura_code
       c->taps.push_back(r + pad >= s ? 1 : -1);
     }
   }
-  const char* env = getenv("VAURA_CODEC_SIMT");
-  c->use_tc = !(env && env[0] == '1');
+  c->use_tc = !knobs().codec_simt;
   *out = c;
   return VAURA_OK;
 }
@@ -805,6 +792,7 @@ extern "C" size_t vaura_codec_workspace_bytes(const vaura_codec* c, int32_t batc
 
 extern "C" int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t B, int32_t T, uint16_t* wav_out,
                                   void* workspace, size_t workspace_bytes, void* stream) {
+  refresh_knobs();
   if (!c || !codes || !wav_out || !workspace || B <= 0 || T <= 0) return fail(VAURA_ERR_INVALID, "bad argument");
   const vaura_codec_dims& d = c->d;
   CodecWs ws = codec_carve(d, B, T, workspace);
@@ -831,8 +819,7 @@ extern "C" int vaura_codec_decode(vaura_codec* c, const int32_t* codes, int32_t 
   __half* act_in = ws.a0;
   __half* act_out = ws.a1;
   __half* act_spare = ws.h;  // fused residual units write their activated output next to the one they read (halo rows)
-  static int fused_ru = -1;  // VAURA_CODEC_FUSED_RU=0: conv k7 and conv k1 of a residual unit as two launches
-  if (fused_ru < 0) { const char* e = getenv("VAURA_CODEC_FUSED_RU"); fused_ru = !(e && e[0] == '0'); }
+  const bool fused_ru = knobs().codec_fused_ru;  // 0: conv k7 and conv k1 of a residual unit as two launches
   int t = T;
   for (int i = 0; i < d.n_blocks; ++i) {
     const int base = 3 + 21 * i, s = d.rates[i];
@@ -889,6 +876,7 @@ struct vaura_codec_encoder {
 
 extern "C" int vaura_codec_encoder_create(const vaura_codec_dims* dims, int32_t encoder_dim, int32_t codebook_dim,
                                           const vaura_codec_weights* w, vaura_codec_encoder** out) {
+  refresh_knobs();
   if (!dims || !w || !out || !w->blob || !w->offsets) return fail(VAURA_ERR_INVALID, "null argument");
   if (dims->n_blocks < 1 || dims->n_blocks > 8) return fail(VAURA_ERR_INVALID, "n_blocks must be 1..8");
   const int want = 2 + 21 * dims->n_blocks + 8;
@@ -905,8 +893,7 @@ extern "C" int vaura_codec_encoder_create(const vaura_codec_dims* dims, int32_t 
     for (int j = 0; j < 7; ++j) c->taps.push_back(j * dil - 3 * dil);
   c->taps.push_back(0);
   for (int j = 0; j < 3; ++j) c->taps.push_back(j - 1);
-  const char* env = getenv("VAURA_CODEC_SIMT");
-  c->use_tc = !(env && env[0] == '1');
+  c->use_tc = !knobs().codec_simt;
   *out = c;
   return VAURA_OK;
 }
@@ -949,6 +936,7 @@ extern "C" size_t vaura_codec_encoder_workspace_bytes(const vaura_codec_encoder*
 
 extern "C" int vaura_codec_encode(vaura_codec_encoder* c, const float* wav, int32_t B, int32_t L, int32_t* codes_out,
                                   uint16_t* latent_out, void* workspace, size_t workspace_bytes, void* stream) {
+  refresh_knobs();
   if (!c || !wav || !codes_out || !workspace || B <= 0 || L <= 0) return fail(VAURA_ERR_INVALID, "bad argument");
   const vaura_codec_dims& d = c->d;
   int hop = 1;
@@ -975,8 +963,7 @@ extern "C" int vaura_codec_encode(vaura_codec_encoder* c, const float* wav, int3
   int rc;
   int t = L, ch = c->enc_dim;
   __half *x = ws.x, *x2 = ws.x2, *act = ws.a0, *act2 = ws.a1, *spare = ws.h;
-  static int fused_ru = -1;  // VAURA_CODEC_FUSED_RU=0: conv k7 and conv k1 of a residual unit as two launches
-  if (fused_ru < 0) { const char* e = getenv("VAURA_CODEC_FUSED_RU"); fused_ru = !(e && e[0] == '0'); }
+  const bool fused_ru = knobs().codec_fused_ru;  // 0: conv k7 and conv k1 of a residual unit as two launches
   CUL(launch_enc_conv_in(wav, F(0), F(1), F(2), x, act, B, L, ch, st));
   for (int i = 0; i < d.n_blocks; ++i) {
     const int base = 2 + 21 * i, s = d.rates[d.n_blocks - 1 - i];  // encoder strides = reversed decoder rates
@@ -1064,6 +1051,7 @@ static AvclipWs avclip_carve(const vaura_avclip_dims& d, int S, void* base) {
 }
 
 extern "C" int vaura_avclip_create(const vaura_avclip_dims* dims, const vaura_avclip_weights* w, vaura_avclip** out) {
+  refresh_knobs();
   if (!dims || !w || !out || !w->blob || !w->offsets) return fail(VAURA_ERR_INVALID, "null argument");
   const vaura_avclip_dims& d = *dims;
   if (d.depth < 1 || d.num_heads < 1 || d.embed_dim != d.num_heads * 64)
@@ -1151,6 +1139,7 @@ static int avclip_chunk(const vaura_avclip* a, const float* frames, int S, float
 
 extern "C" int vaura_avclip_forward(vaura_avclip* a, const float* frames, int32_t segments, float* features_out, void* workspace,
                                     size_t workspace_bytes, void* stream) {
+  refresh_knobs();
   if (!a || !frames || !features_out || !workspace || segments <= 0) return fail(VAURA_ERR_INVALID, "bad argument");
   const vaura_avclip_dims& d = a->d;
   int chunk = segments;

@@ -977,9 +977,8 @@ static int cluster_mode(cudaError_t* err) {
   if (nclusters < NCL) { *err = cudaErrorCooperativeLaunchTooLarge; return mode = 0; }
   // VAURA_CLUSTER_NOCOOP=1: skip the cooperative attribute (Nsight Compute's kernel replay rejects cooperative
   // cluster launches); co-residency is already established by the occupancy query above
-  const char* nc = getenv("VAURA_CLUSTER_NOCOOP");
   *err = cudaSuccess;
-  return mode = (nc && nc[0] == '1') ? 2 : 1;
+  return mode = knobs().cluster_nocoop ? 2 : 1;
 }
 
 template <int NB, bool TM>

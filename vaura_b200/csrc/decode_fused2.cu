@@ -1062,8 +1062,7 @@ cudaError_t launch_decode_fused2(const Fused2Args& a, const void* wqkv, const vo
   at[1].id = cudaLaunchAttributeCooperative;
   at[1].val.cooperative = 1;
   cfg.attrs = at;
-  static int coop = -1;  // VAURA_FUSED2_NOCOOP=1: cluster attribute only (Nsight Compute's replay rejects cooperative cluster launches)
-  if (coop < 0) { const char* ev = getenv("VAURA_FUSED2_NOCOOP"); coop = !(ev && ev[0] == '1'); }
+  const bool coop = !knobs().fused2_nocoop;  // cluster attribute only: Nsight Compute's replay rejects cooperative cluster launches
   cfg.numAttrs = coop ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, decode_step_fused2, m_hb, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads, a);
   if (e != cudaSuccess && coop) {

@@ -684,11 +684,7 @@ static cudaError_t launch_persist_t(PersistArgs& a, cudaStream_t st) {
   const size_t smem = persist_smem(NB, a.D, a.F, slot_cap);
   if (slot_cap < 4 * a.D || slot_cap < 4 * a.F) return cudaErrorInvalidValue;  // a slot must hold one row pair
   a.slot_cap = slot_cap;
-  {
-    const char* e = getenv("VAURA_PERSIST_PREFETCH");
-    a.prefetch_ahead = e ? atoi(e) : 0;  // groups of L2 prefetch ahead of the smem fill (measured: no gain, off)
-    if (a.prefetch_ahead < 0) a.prefetch_ahead = 0;
-  }
+  a.prefetch_ahead = knobs().persist_prefetch;  // groups of L2 prefetch ahead of the smem fill (measured: no gain, off)
   static int grid = 0;
   if (!grid) {
     cudaError_t e = cudaFuncSetAttribute(decode_step_persistent<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -2130,18 +2130,16 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cu
   EpiConv::Params ep{a.bias, a.alpha, a.residual, a.out_raw, a.out_act, a.Tq, a.Tout, a.Cout, a.ostride};
   const int mt = (a.Tq + kTileM - 1) / kTileM, nt = a.Cout / bn;
   // persistent tile loop (double-buffered TMEM accumulator) unless VAURA_CONV_PERSISTENT=0
-  static int persistent = -1, ksub3 = -1;
-  if (persistent < 0) { const char* e = getenv("VAURA_CONV_PERSISTENT"); persistent = !(e && e[0] == '0'); }
-  if (ksub3 < 0) { const char* e = getenv("VAURA_CONV_KSUB"); ksub3 = !(e && e[0] == '0'); }
+  const bool persistent = knobs().conv_persistent, ksub3 = knobs().conv_ksub;
   // 96 input channels = three 32-wide K blocks per tap: one stage (one tensor box per operand) per tap
   if (persistent && ksub3 && bk == 32 && a.Cin == 96 && (bn == 96 || bn == 32 || bn == 16)) {
     CUtensorMap ta4, tb4;
     if (!make_map_kblocks(&ta4, a.in, a.Cin, a.Tin, B, a.Cin, (uint64_t)a.Tin * a.Cin, kTileM, 3, 32, true) ||
         !make_map_kblocks(&tb4, a.W, a.Cin, a.Cout, (uint64_t)a.ntaps * a.nphase, a.Cin, (uint64_t)a.Cout * a.Cin, bn, 3, 32, true))
       return cudaErrorUnknown;
-    static int occ2 = -1;  // VAURA_CONV_OCC2=1: two CTAs per SM for the 96-channel layers (measured neutral: 9.58 vs 9.54 ms per
-                           // 16 clips - these layers are bound by bytes in flight per SM, not by the per-CTA serial chain)
-    if (occ2 < 0) { const char* e = getenv("VAURA_CONV_OCC2"); occ2 = (e && e[0] == '1'); }
+    // VAURA_CONV_OCC2=1: two CTAs per SM for the 96-channel layers (measured neutral: 9.58 vs 9.54 ms per 16 clips - these
+    // layers are bound by bytes in flight per SM, not by the per-CTA serial chain)
+    const bool occ2 = knobs().conv_occ2;
     if (bn == 96 && occ2) return launch_tc_persistent<96, 32, 2, 0, EpiConv, 3, 2>(ta4, tb4, g, ep, mt, nt, st);
     if (bn == 96) return launch_tc_persistent<96, 32, 4, 0, EpiConv, 3>(ta4, tb4, g, ep, mt, nt, st);
     if (bn == 32) return launch_tc_persistent<32, 32, 4, 0, EpiConv, 3>(ta4, tb4, g, ep, mt, nt, st);
@@ -2152,9 +2150,7 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const int* tap_off_host, int B, cu
     return persistent ? launch_tc_persistent<BN, BK, ST, 0, EpiConv>(ta, tb, g, ep, mt, nt, st)                \
                       : launch_tc<BN, BK, ST, 0, EpiConv>(ta, tb, g, ep, mt, nt, st);
   {
-    static int occ2b = -1;
-    if (occ2b < 0) { const char* e = getenv("VAURA_CONV_OCC2"); occ2b = (e && e[0] == '1'); }
-    if (persistent && occ2b && bn == 96 && bk == 64) return launch_tc_persistent<96, 64, 3, 0, EpiConv, 1, 2>(ta, tb, g, ep, mt, nt, st);
+    if (persistent && knobs().conv_occ2 && bn == 96 && bk == 64) return launch_tc_persistent<96, 64, 3, 0, EpiConv, 1, 2>(ta, tb, g, ep, mt, nt, st);
   }
   TC_CASE(256, 64, 4)
   TC_CASE(192, 64, 4)
@@ -2230,18 +2226,14 @@ static cudaError_t launch_decode_fused_t(const FusedStepArgs& a, const void* wqk
   b.w_13 = static_cast<const __nv_bfloat16*>(w13);
   b.w_2 = static_cast<const __nv_bfloat16*>(w2);
   b.w_heads = static_cast<const __nv_bfloat16*>(w_heads);
-  {
-    const char* pf = getenv("VAURA_FUSED_L2_PREFETCH");
-    b.l2_prefetch = pf ? atoi(pf) : 1;
-  }
+  b.l2_prefetch = knobs().fused_l2_prefetch;
   return cudaLaunchKernelEx(&cfg, decode_step_fused_bf16<TM>, m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads, b);
 }
 
 cudaError_t launch_decode_fused_bf16(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
                                      const void* w_heads, cudaStream_t st) {
   if (!fused_step_supported(a.R, a.D, a.F, a.NH)) return cudaErrorInvalidValue;
-  const char* tm = getenv("VAURA_FUSED_TM128");  // experiment: UMMA M = 128 also for <= 64 rows
-  return a.R <= 64 && !(tm && tm[0] == '1') ? launch_decode_fused_t<64>(a, wqkv, wo, w13, w2, w_heads, st)
+  return a.R <= 64 && !knobs().fused_tm128 ? launch_decode_fused_t<64>(a, wqkv, wo, w13, w2, w_heads, st)
                                             : launch_decode_fused_t<128>(a, wqkv, wo, w13, w2, w_heads, st);
 }
 
@@ -2273,12 +2265,10 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t st) {
   if (split3 && a.ksplit == 0 && (a.epi != EPI_STORE || a.perm_S == 0)) {
     // auto: when the tiles of this GEMM cover less than half of the SMs (prompt prefill: one or two row tiles), split K over
     // clusters of 4 or 2 CTAs (partial sums through DSMEM, rank-ordered: deterministic) and widen the 1536-wide tiles
-    static int ck_on = -1;
-    if (ck_on < 0) { const char* e = getenv("VAURA_PREFILL_CK"); ck_on = !(e && e[0] == '0'); }
+    const bool ck_on = knobs().prefill_ck;
     // 256-wide tiles from N = 8192 (w1|w3); q|k|v (N = 4608) runs 128-wide tiles in pairs = 144 CTAs instead of 72: prefill of a
     // 167-position window 3.59 -> 3.33 ms (128-wide for w1|w3 as well: 3.51).  VAURA_PREFILL_BN256_FROM overrides.
-    static int bn_thr = -1;
-    if (bn_thr < 0) { const char* e = getenv("VAURA_PREFILL_BN256_FROM"); bn_thr = e ? atoi(e) : 8192; }
+    const int bn_thr = knobs().prefill_bn256_from;
     const int bn = a.N % 256 == 0 && a.N >= bn_thr ? 256 : (a.N % 128 == 0 ? 128 : 0);
     const int kb = wk / 64;
     if (ck_on && bn) {
@@ -2339,11 +2329,7 @@ cudaError_t launch_vit_linear(const VitLinearArgs& a, cudaStream_t st) {
   if (!make_map(&tb, a.W, a.K, a.N, 1, a.K, (uint64_t)a.N * a.K, 64, bn, false)) return cudaErrorUnknown;
   TcShape g{};
   g.ntaps = 1; g.nphase = 1; g.kblocks = a.K / 64; g.batch = 1; g.ksplit = 1; g.pdl = 0;
-  {
-    static int nf = -1;  // VAURA_AVCLIP_M_FASTEST=1: the codec's tile order (A/B measurement)
-    if (nf < 0) { const char* e = getenv("VAURA_AVCLIP_M_FASTEST"); nf = !(e && e[0] == '1'); }
-    g.n_fastest = nf;
-  }
+  g.n_fastest = !knobs().avclip_m_fastest;  // M fastest = the codec's tile order (A/B measurement)
   EpiVit::Params ep{};
   ep.mode = a.mode; ep.gelu = a.gelu; ep.M = a.M; ep.N = a.N; ep.ldo = a.ldo; ep.bias = a.bias;
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16); ep.out_f32 = a.out_f32; ep.pos = a.pos;
@@ -2351,8 +2337,7 @@ cudaError_t launch_vit_linear(const VitLinearArgs& a, cudaStream_t st) {
   const int mt = (a.M + kTileM - 1) / kTileM, nt = a.N / bn;
   // CTA-pair tiles (gemm_tc2_persistent_kernel) by default: q|k|v 187 -> 171 us, fc1 358 -> 245 us, fc2 212 -> 192 us per 32
   // segments (12.96 vs 15.19 ms of GEMMs per forward).  VAURA_AVCLIP_2CTA=0: one CTA per tile (A/B measurement)
-  static int two_cta = -1;
-  if (two_cta < 0) { const char* e = getenv("VAURA_AVCLIP_2CTA"); two_cta = !(e && e[0] == '0'); }
+  const bool two_cta = knobs().avclip_2cta;
   if (two_cta && bn == 256) {
     constexpr int ST = 6, EWP = 16;
     constexpr int smem2 = ST * (kTileM * 64 * 2 + 128 * 64 * 2) + 1024 + 256;
@@ -2374,8 +2359,7 @@ cudaError_t launch_vit_linear(const VitLinearArgs& a, cudaStream_t st) {
     kern<<<dim3(grid), dim3(64 + 32 * EWP), smem2, st>>>(ta, tb2, g, ep, mt2, nt);
     return cudaGetLastError();
   }
-  static int ew16 = -1;  // VAURA_AVCLIP_EW8=1: eight epilogue warps (A/B measurement)
-  if (ew16 < 0) { const char* e = getenv("VAURA_AVCLIP_EW8"); ew16 = !(e && e[0] == '1'); }
+  const bool ew16 = !knobs().avclip_ew8;  // eight epilogue warps: A/B measurement
   if (bn == 256) return ew16 ? launch_tc_persistent<256, 64, 4, 1, EpiVit, 1, 1, 16>(ta, tb, g, ep, mt, nt, st)
                              : launch_tc_persistent<256, 64, 4, 1, EpiVit>(ta, tb, g, ep, mt, nt, st);
   return launch_tc_persistent<128, 64, 6, 1, EpiVit>(ta, tb, g, ep, mt, nt, st);

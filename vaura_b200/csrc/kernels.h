@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "common.cuh"
+#include "knobs.h"
 
 namespace vaura {
 
