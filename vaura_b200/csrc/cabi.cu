@@ -151,6 +151,7 @@ struct Workspace {
   __nv_bfloat16 *x3, *act3;                              // fp32act path, tensor-core prefill: operands as three bf16 terms
   char* f2;                                              // bf16 path, decode_step_fused2: h_t | q_t | ssq_part | w2_part | w2_cnt
   float* part;                                           // bf16 path, decode_step_fused_bf16: split-K partial sums of wo / w2
+  int prefill_terms;                                     // fp32act path, tensor-core prefill: 3 (fp32-equivalent) or 1 (bf16 operands)
   size_t bytes;
 };
 
@@ -226,6 +227,9 @@ static KvView kv_view(const vaura_kv_cache* kv, int nhead) {
 static int transformer_pass_tc3(const vaura_sampler* s, const Workspace& ws, const int32_t* seq, int batch, int S,
                                 const float* cond_rows, int rows, int npos, int pos0, const StepState* state,
                                 const KvView& kv, float* logits_dst, bool logits_all, cudaStream_t st);
+static int transformer_pass_tc1(const vaura_sampler* s, const Workspace& ws, const int32_t* seq, int batch, int S,
+                                const float* cond_rows, int rows, int npos, int pos0, const StepState* state,
+                                const KvView& kv, float* logits_dst, cudaStream_t st);
 
 // One transformer pass over `npos` new positions per sequence row (fp32act path).
 //   state != nullptr: positions come from the device-resident loop state (graph replay);
@@ -239,7 +243,10 @@ static int transformer_pass(const vaura_sampler* s, const Workspace& ws, const i
   const vaura_sampler_weights& w = s->w;
   const int R = rows * npos;
   {
-    if (knobs().prefill_tc && npos > 1 && R >= 16 && ws.x3 && d.d_model % 64 == 0 && d.ffn_dim % 64 == 0)
+    const bool tc = knobs().prefill_tc && npos > 1 && R >= 16 && ws.x3 && d.d_model % 64 == 0 && d.ffn_dim % 64 == 0;
+    if (tc && ws.prefill_terms == 1 && !logits_all)
+      return transformer_pass_tc1(s, ws, seq, batch, S, cond_rows, rows, npos, pos0, state, kv, logits_dst, st);
+    if (tc)
       return transformer_pass_tc3(s, ws, seq, batch, S, cond_rows, rows, npos, pos0, state, kv, logits_dst, logits_all, st);
   }
   EmbedArgs e{};
@@ -347,6 +354,73 @@ static int transformer_pass_tc3(const vaura_sampler* s, const Workspace& ws, con
     g.x = ws.h + (size_t)(npos - 1) * D; g.ldx = (size_t)npos * D; g.R = rows;
     CUL(launch_gemv(EPI_STORE, true, g, st));
   }
+  return VAURA_OK;
+}
+
+// Prompt prefill of a call that samples (no bit-exactness contract): the same pass with the GEMM operands
+// rounded to bf16 once (one term instead of three: a third of the MMA work and of the activation bytes every CTA ingests).
+// Residual stream, q, K/V pages and the attention arithmetic stay fp32, so the fp32-activation decode steps that follow read
+// the cache they expect; the split-K residual GEMMs use float reductions (a sampling call is not reproducible bit for bit
+// across precision modes anyway).  Logits stay within the bf16 tolerance (1e-2 of max |logit|), tests/test_gpu_prefill.py.
+static int transformer_pass_tc1(const vaura_sampler* s, const Workspace& ws, const int32_t* seq, int batch, int S,
+                                const float* cond_rows, int rows, int npos, int pos0, const StepState* state,
+                                const KvView& kv, float* logits_dst, cudaStream_t st) {
+  const vaura_sampler_dims& d = s->d;
+  const vaura_sampler_weights& w = s->w;
+  const int R = rows * npos;
+  EmbedArgs e{};
+  e.seq = seq; e.cond_rows = cond_rows; e.tables = w.tok_tables; e.h = ws.h; e.state = state; e.pos0 = pos0;
+  e.npos = npos; e.batch = batch; e.K = d.num_codebooks; e.S = S; e.vocab = d.vocab; e.d_model = d.d_model;
+  e.cond_dim = d.cond_dim; e.cond_tokens = d.cond_tokens; e.atpvf = d.audio_tokens_per_video_frame;
+  CUL(launch_embed(e, R, st));
+  const size_t D = d.d_model, F = d.ffn_dim;
+  const int mt = (R + (R <= 64 ? 63 : 127)) / (R <= 64 ? 64 : 128);
+  // N tile and K split so that the tiles of a GEMM cover the SMs about once
+  auto tile_n = [&](int N, int want) {
+    int bn = 128;
+    while (bn > 32 && (N % bn != 0 || mt * (N / bn) < want)) bn >>= 1;
+    return N % bn == 0 ? bn : 0;
+  };
+  auto split_k = [&](int N, int bn, int kblocks) {
+    int ks = 148 / (mt * (N / bn));
+    if (ks > 6) ks = 6;
+    if (ks > kblocks / 4) ks = kblocks / 4;
+    return ks < 1 ? 1 : ks;
+  };
+  const int bn_qkv = tile_n(3 * (int)D, 96), bn_13 = tile_n(2 * (int)F, 96), bn_o = tile_n((int)D, 24);
+  if (!bn_qkv || !bn_13 || !bn_o) return fail(VAURA_ERR_UNSUPPORTED, "bf16 prefill: d_model %d / ffn %d do not tile", d.d_model, d.ffn_dim);
+  __nv_bfloat16* xn = ws.x3;     // [R][D] here
+  __nv_bfloat16* act = ws.act3;  // [R][F] here
+  for (int l = 0; l < d.num_layers; ++l) {
+    LinearTcArgs g{};
+    g.state = state; g.pos0 = pos0; g.npos = npos; g.R = R; g.layer = l; g.d_model = d.d_model; g.kv = kv; g.rope = w.rope;
+    g.ksplit = 1; g.pdl = 0;
+    CUL(launch_rmsnorm_bf16(ws.h, w.attn_norm + l * D, xn, R, (int)D, D, d.norm_eps, 0, st));
+    g.A = xn; g.lda = D; g.K = D; g.W = w.wqkv + (size_t)l * 3 * D * D; g.N = 3 * D; g.epi = EPI_QKV_F32;
+    g.out_f32 = ws.q; g.ldo = D; g.block_n = bn_qkv;
+    CUL(launch_linear_tc(g, st));
+    AttnArgs a{};
+    a.q = ws.q; a.out = ws.attn; a.out3 = reinterpret_cast<uint16_t*>(xn); a.out_terms = 1; a.kv = kv; a.state = state;
+    a.pos0 = pos0; a.npos = npos; a.layer = l; a.d_model = d.d_model; a.scale = 1.0f / sqrtf((float)kHeadDim);
+    CUL(launch_attn(a, d.nhead, R, st));
+    g.A = xn; g.lda = D; g.K = D; g.W = w.wo + (size_t)l * D * D; g.N = D; g.epi = EPI_RESID; g.out_f32 = ws.h; g.ldo = D;
+    g.block_n = bn_o; g.ksplit = split_k((int)D, bn_o, (int)D / 64);
+    CUL(launch_linear_tc(g, st));
+    g.ksplit = 1;
+    CUL(launch_rmsnorm_bf16(ws.h, w.ffn_norm + l * D, xn, R, (int)D, D, d.norm_eps, 0, st));
+    g.A = xn; g.lda = D; g.K = D; g.W = w.w13 + (size_t)l * 2 * F * D; g.N = 2 * F; g.epi = EPI_SWIGLU;
+    g.out_bf16 = act; g.ldo = F; g.block_n = bn_13;
+    CUL(launch_linear_tc(g, st));
+    g.A = act; g.lda = F; g.K = F; g.W = w.w2 + (size_t)l * D * F; g.N = D; g.epi = EPI_RESID; g.out_f32 = ws.h; g.ldo = D;
+    g.block_n = bn_o; g.ksplit = split_k((int)D, bn_o, (int)F / 64);
+    CUL(launch_linear_tc(g, st));
+  }
+  // only the last position of every sequence row feeds the heads: a few rows, the weight-streaming GEMV (fp32 activations)
+  GemvArgs g{};
+  g.state = state; g.pos0 = pos0; g.npos = npos; g.layer = 0; g.d_model = d.d_model; g.eps = d.norm_eps;
+  g.W = w.w_heads; g.norm_w = w.final_norm; g.N = d.num_codebooks * d.vocab; g.K = D; g.ldo = g.N; g.out = logits_dst;
+  g.x = ws.h + (size_t)(npos - 1) * D; g.ldx = (size_t)npos * D; g.R = rows;
+  CUL(launch_gemv(EPI_STORE, true, g, st));
   return VAURA_OK;
 }
 
@@ -526,6 +600,8 @@ extern "C" int vaura_sampler_generate(vaura_sampler* s, const vaura_generate_par
   const int npre = p->start_offset;  // columns [0, start) are consumed by the first pass (prefill when > 1)
   Workspace ws = carve(d, rows, npre, precision, workspace);
   if (ws.bytes > workspace_bytes) return fail(VAURA_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+  // a call that samples has no bit-exactness contract: its prompt prefill takes bf16 operands (transformer_pass_tc1)
+  ws.prefill_terms = (p->use_sampling && p->temp > 0.f && knobs().prefill_bf16) ? 1 : 3;
   cudaStream_t st = (cudaStream_t)stream;
   const KvView kvv = kv_view(kv, d.nhead);
   // CUDA events on the caller's stream around the decode-step launches alone (first pass, memsets and host glue outside):

@@ -308,7 +308,9 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnArgs a) {
     for (; jj < nctx; ++jj) a0 = fmaf(sc[jj], kvp[a.kv.row(a.layer, 1, b, jj, h) + tid], a0);
     const float o = ((a0 + a1) + (a2 + a3)) / sum;
     a.out[(size_t)row * a.d_model + h * kHeadDim + tid] = o;
-    if (a.out3) {  // the wo GEMM of the tensor-core prefill reads the row as three bf16 terms
+    if (a.out3 && a.out_terms == 1) {  // bf16-operand prefill: the row rounded once
+      reinterpret_cast<__nv_bfloat16*>(a.out3)[(size_t)row * a.d_model + h * kHeadDim + tid] = __float2bfloat16_rn(o);
+    } else if (a.out3) {  // the wo GEMM of the tensor-core prefill reads the row as three bf16 terms
       __nv_bfloat16 t1, t2, t3;
       split3(o, t1, t2, t3);
       __nv_bfloat16* o3 = reinterpret_cast<__nv_bfloat16*>(a.out3) + (size_t)row * 3 * a.d_model + h * kHeadDim + tid;
@@ -425,7 +427,9 @@ __global__ void __launch_bounds__(kPfThreads) attn_prefill_kernel(AttnArgs a) {
       const float o = acc[u][i] * inv;
       const int col = h * kHeadDim + lane + 32 * i;
       a.out[row * a.d_model + col] = o;
-      if (a.out3) {
+      if (a.out3 && a.out_terms == 1) {
+        reinterpret_cast<__nv_bfloat16*>(a.out3)[row * a.d_model + col] = __float2bfloat16_rn(o);
+      } else if (a.out3) {
         __nv_bfloat16 t1, t2, t3;
         split3(o, t1, t2, t3);
         __nv_bfloat16* o3 = reinterpret_cast<__nv_bfloat16*>(a.out3) + row * 3 * a.d_model + col;

@@ -43,6 +43,7 @@ struct AttnArgs {
   const float* q;   // [rows*npos][d]
   float* out;       // [rows*npos][d]
   uint16_t* out3;   // optional: the same rows as three bf16 terms [rows*npos][3 d] (hi | mid | lo), see split3()
+  int out_terms;    // 0 / 3: three terms; 1: out3 is [rows*npos][d], the rows rounded to bf16 (bf16-activation prefill)
   KvView kv;
   const StepState* state;
   int pos0, npos;

@@ -43,6 +43,7 @@ Knobs read_env() {
   k.w2_ksplit = env_int("VAURA_W2_KSPLIT", 6);  // 24 x 6 = 144 CTAs: one wave (8 -> 192 CTAs was 6 % slower)
   k.fused_l2_prefetch = env_int("VAURA_FUSED_L2_PREFETCH", 1);
   k.fused_tm128 = env_flag("VAURA_FUSED_TM128", 0);
+  k.prefill_bf16 = env_flag("VAURA_PREFILL_BF16", 1);
   k.prefill_ck = env_flag("VAURA_PREFILL_CK", 1);
   k.prefill_bn256_from = env_int("VAURA_PREFILL_BN256_FROM", 8192);
   k.codec_simt = env_flag("VAURA_CODEC_SIMT", 0);

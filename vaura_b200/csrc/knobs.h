@@ -37,6 +37,7 @@ struct Knobs {
   int fused_l2_prefetch;   // VAURA_FUSED_L2_PREFETCH=0  no L2 prefetch of the next phase's weight tile
   int fused_tm128;         // VAURA_FUSED_TM128=1        UMMA M = 128 also for <= 64 rows
   // ---- tensor-core prefill ----
+  int prefill_bf16;        // VAURA_PREFILL_BF16=0       a sampling call keeps the three-term (fp32-equivalent) prompt prefill
   int prefill_ck;          // VAURA_PREFILL_CK=0         no K split inside clusters
   int prefill_bn256_from;  // VAURA_PREFILL_BN256_FROM=n 256-wide tiles from this N (8192)
   // ---- codec ----
