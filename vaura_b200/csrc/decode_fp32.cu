@@ -321,19 +321,26 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnArgs a) {
 
 // ------------------------------------------------------------------------------------------------
 // causal attention of a multi-position pass (prompt prefill, teacher-forced forward) over the paged fp32 KV cache:
-// one CTA per (head, 32 consecutive query positions of one sequence).  Keys / values are staged 32 positions at a time
-// in shared memory and shared by the 32 queries (attn_kernel re-reads the whole context per query: 166 x the K/V
-// traffic for a 166-position prompt); flash-style online softmax in fp32 (llama.py:246-255, scale 1/sqrt(96)).
-// Warp w owns queries 4w..4w+3: scores with lane = key (K rows padded to 97 floats: conflict-free), P.V with lane =
-// output dims lane, lane + 32, lane + 64.
+// one CTA per (head, 8 QW consecutive query positions of one sequence), QW = queries per warp.  Keys / values are staged 32
+// positions at a time in shared memory and shared by the CTA's queries (attn_kernel re-reads the whole context per query:
+// 166 x the K/V traffic for a 166-position prompt); flash-style online softmax in fp32 (llama.py:246-255, scale 1/sqrt(96)).
+// Warp w owns queries QW w .. QW w + QW - 1: scores with lane = key (K rows padded to 97 floats: conflict-free), P.V with
+// lane = output dims lane, lane + 32, lane + 64.
+// The kernel is bound by its own instruction latency (ncu, 167 positions, QW = 4: 96 CTAs = two warps per scheduler on 96 SMs,
+// issue slots 36 % busy, short-scoreboard and wait stalls, 53.6 k cycles = the CTA of the last query block), so a single
+// prompt window takes fewer queries per warp - more CTAs, shorter chains, more warps per scheduler to hide the shared-memory
+// latency - and the query blocks are issued last-first: the blocks that see the most keys start first on SMs of their own
+// (25.8 -> 18.8 us per launch).
 // ------------------------------------------------------------------------------------------------
-constexpr int kPfQ = 32, kPfK = 32, kPfThreads = 256;
+constexpr int kPfK = 32, kPfThreads = 256;
+template <int QW>
 __global__ void __launch_bounds__(kPfThreads) attn_prefill_kernel(AttnArgs a) {
+  constexpr int kPfQ = 8 * QW;
   __shared__ float qs[kPfQ][kHeadDim];
   __shared__ float ks[kPfK][kHeadDim + 1];
   __shared__ float vs[kPfK][kHeadDim];
-  __shared__ float ps[kPfThreads / 32][kPfK][4];
-  const int h = blockIdx.x, j0 = blockIdx.y * kPfQ, b = blockIdx.z;
+  __shared__ float ps[kPfThreads / 32][kPfK][QW];
+  const int h = blockIdx.x, j0 = ((int)gridDim.y - 1 - (int)blockIdx.y) * kPfQ, b = blockIdx.z;
   const int pos0 = a.state ? a.state->offset - a.npos : a.pos0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nq = min(kPfQ, a.npos - j0);
@@ -344,13 +351,12 @@ __global__ void __launch_bounds__(kPfThreads) attn_prefill_kernel(AttnArgs a) {
     if (qi < nq) v = *reinterpret_cast<const float4*>(a.q + (size_t)(b * a.npos + j0 + qi) * a.d_model + h * kHeadDim + 4 * c);
     *reinterpret_cast<float4*>(&qs[qi][4 * c]) = v;
   }
-  float m[4], l[4], acc[4][3];
+  float m[QW], l[QW], acc[QW][3];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) { m[u] = -INFINITY; l[u] = 0.f; acc[u][0] = acc[u][1] = acc[u][2] = 0.f; }
+  for (int u = 0; u < QW; ++u) { m[u] = -INFINITY; l[u] = 0.f; acc[u][0] = acc[u][1] = acc[u][2] = 0.f; }
   const int last_pos = pos0 + j0 + nq - 1;  // last key any query of this block may see
   // key / value rows of a tile travel through registers: 8 threads per position, 3 float4 each; the rows of tile k0 + 32 are
-  // requested before tile k0 is consumed, so their latency overlaps its arithmetic (27.1 -> 25.8 us per launch at 167 positions:
-  // what is left is the serial score / P.V arithmetic of eight warps per (head, 32 queries) on 96 of the SMs)
+  // requested before tile k0 is consumed, so their latency overlaps its arithmetic
   const int sr = tid >> 3, scol = tid & 7;
   float4 kreg[3], vreg[3];
   auto fetch = [&](int k0) {
@@ -375,24 +381,26 @@ __global__ void __launch_bounds__(kPfThreads) attn_prefill_kernel(AttnArgs a) {
     }
     if (k0 + kPfK <= last_pos) fetch(k0 + kPfK);
     __syncthreads();
-    // scores of this warp's 4 queries against key k0 + lane
-    float sc[4] = {0.f, 0.f, 0.f, 0.f};
+    // scores of this warp's queries against key k0 + lane
+    float sc[QW];
+#pragma unroll
+    for (int u = 0; u < QW; ++u) sc[u] = 0.f;
     const int kpos = k0 + lane;
 #pragma unroll 4
     for (int d4 = 0; d4 < kHeadDim / 4; ++d4) {
       const float k0v = ks[lane][4 * d4], k1v = ks[lane][4 * d4 + 1], k2v = ks[lane][4 * d4 + 2], k3v = ks[lane][4 * d4 + 3];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float4 qv = *reinterpret_cast<const float4*>(&qs[4 * warp + u][4 * d4]);
+      for (int u = 0; u < QW; ++u) {
+        const float4 qv = *reinterpret_cast<const float4*>(&qs[QW * warp + u][4 * d4]);
         sc[u] = fmaf(qv.x, k0v, sc[u]); sc[u] = fmaf(qv.y, k1v, sc[u]);
         sc[u] = fmaf(qv.z, k2v, sc[u]); sc[u] = fmaf(qv.w, k3v, sc[u]);
       }
     }
-    float corr[4];
+    float corr[QW];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int qpos = pos0 + j0 + 4 * warp + u;
-      const bool ok = kpos <= qpos && 4 * warp + u < nq;
+    for (int u = 0; u < QW; ++u) {
+      const int qpos = pos0 + j0 + QW * warp + u;
+      const bool ok = kpos <= qpos && QW * warp + u < nq;
       const float sv = ok ? sc[u] * a.scale : -INFINITY;
       const float mn = fmaxf(m[u], warp_max(sv));
       const float pe = ok ? expf(sv - mn) : 0.f;           // mn is finite whenever ok (the key itself is visible)
@@ -404,21 +412,30 @@ __global__ void __launch_bounds__(kPfThreads) attn_prefill_kernel(AttnArgs a) {
     }
     __syncwarp();
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { acc[u][0] *= corr[u]; acc[u][1] *= corr[u]; acc[u][2] *= corr[u]; }
+    for (int u = 0; u < QW; ++u) { acc[u][0] *= corr[u]; acc[u][1] *= corr[u]; acc[u][2] *= corr[u]; }
     const int nk = min(kPfK, last_pos - k0 + 1);
     for (int j = 0; j < nk; ++j) {
-      const float4 pv = *reinterpret_cast<const float4*>(&ps[warp][j][0]);
       const float v0 = vs[j][lane], v1 = vs[j][lane + 32], v2 = vs[j][lane + 64];
-      acc[0][0] = fmaf(pv.x, v0, acc[0][0]); acc[0][1] = fmaf(pv.x, v1, acc[0][1]); acc[0][2] = fmaf(pv.x, v2, acc[0][2]);
-      acc[1][0] = fmaf(pv.y, v0, acc[1][0]); acc[1][1] = fmaf(pv.y, v1, acc[1][1]); acc[1][2] = fmaf(pv.y, v2, acc[1][2]);
-      acc[2][0] = fmaf(pv.z, v0, acc[2][0]); acc[2][1] = fmaf(pv.z, v1, acc[2][1]); acc[2][2] = fmaf(pv.z, v2, acc[2][2]);
-      acc[3][0] = fmaf(pv.w, v0, acc[3][0]); acc[3][1] = fmaf(pv.w, v1, acc[3][1]); acc[3][2] = fmaf(pv.w, v2, acc[3][2]);
+      float pw[QW];
+      if constexpr (QW == 4) {
+        const float4 pv = *reinterpret_cast<const float4*>(&ps[warp][j][0]);
+        pw[0] = pv.x; pw[1] = pv.y; pw[2] = pv.z; pw[3] = pv.w;
+      } else if constexpr (QW == 2) {
+        const float2 pv = *reinterpret_cast<const float2*>(&ps[warp][j][0]);
+        pw[0] = pv.x; pw[1] = pv.y;
+      } else {
+        pw[0] = ps[warp][j][0];
+      }
+#pragma unroll
+      for (int u = 0; u < QW; ++u) {
+        acc[u][0] = fmaf(pw[u], v0, acc[u][0]); acc[u][1] = fmaf(pw[u], v1, acc[u][1]); acc[u][2] = fmaf(pw[u], v2, acc[u][2]);
+      }
     }
     __syncwarp();
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int qi = 4 * warp + u;
+  for (int u = 0; u < QW; ++u) {
+    const int qi = QW * warp + u;
     if (qi >= nq) continue;
     const size_t row = (size_t)b * a.npos + j0 + qi;
     const float inv = 1.f / l[u];
@@ -440,8 +457,18 @@ __global__ void __launch_bounds__(kPfThreads) attn_prefill_kernel(AttnArgs a) {
 }
 
 cudaError_t launch_attn(const AttnArgs& a, int nhead, int rows, cudaStream_t st) {
-  if (a.npos >= 16 && rows % a.npos == 0) {  // multi-position pass: keys / values shared by 32 queries per CTA
-    attn_prefill_kernel<<<dim3(nhead, (a.npos + kPfQ - 1) / kPfQ, rows / a.npos), kPfThreads, 0, st>>>(a);
+  if (a.npos >= 16 && rows % a.npos == 0) {  // multi-position pass: keys / values shared by the 8 QW queries of a CTA
+    const int seqs = rows / a.npos;
+    auto ctas = [&](int qw) { return (long long)nhead * ((a.npos + 8 * qw - 1) / (8 * qw)) * seqs; };
+    // four queries per warp (fewest instructions in total) when that still gives every SM two CTAs; a single prompt window
+    // does not: two per warp.  Measured at 167 positions, one sequence: 23.9 / 18.8 / 19.5 us per launch with 4 / 2 / 1 queries
+    // per warp (25.8 us before the blocks were issued last-first)
+    int qw = ctas(4) >= 296 ? 4 : 2;
+    if (knobs().prefill_attn_qw == 1 || knobs().prefill_attn_qw == 2 || knobs().prefill_attn_qw == 4) qw = knobs().prefill_attn_qw;
+    const dim3 grid(nhead, (a.npos + 8 * qw - 1) / (8 * qw), seqs);
+    if (qw == 4) attn_prefill_kernel<4><<<grid, kPfThreads, 0, st>>>(a);
+    else if (qw == 2) attn_prefill_kernel<2><<<grid, kPfThreads, 0, st>>>(a);
+    else attn_prefill_kernel<1><<<grid, kPfThreads, 0, st>>>(a);
     return cudaGetLastError();
   }
   attn_kernel<<<dim3(nhead, rows), 128, 0, st>>>(a);

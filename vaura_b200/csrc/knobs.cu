@@ -45,6 +45,7 @@ Knobs read_env() {
   k.fused_tm128 = env_flag("VAURA_FUSED_TM128", 0);
   k.prefill_bf16 = env_flag("VAURA_PREFILL_BF16", 1);
   k.prefill_ck = env_flag("VAURA_PREFILL_CK", 1);
+  k.prefill_attn_qw = env_int("VAURA_PREFILL_ATTN_QW", 0);
   k.prefill_bn256_from = env_int("VAURA_PREFILL_BN256_FROM", 8192);
   k.codec_simt = env_flag("VAURA_CODEC_SIMT", 0);
   k.codec_fused_ru = env_flag("VAURA_CODEC_FUSED_RU", 1);

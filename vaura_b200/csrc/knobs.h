@@ -39,6 +39,7 @@ struct Knobs {
   // ---- tensor-core prefill ----
   int prefill_bf16;        // VAURA_PREFILL_BF16=0       a sampling call keeps the three-term (fp32-equivalent) prompt prefill
   int prefill_ck;          // VAURA_PREFILL_CK=0         no K split inside clusters
+  int prefill_attn_qw;     // VAURA_PREFILL_ATTN_QW=1|2|4 queries per warp of the fp32 prefill attention (0 = by grid size)
   int prefill_bn256_from;  // VAURA_PREFILL_BN256_FROM=n 256-wide tiles from this N (8192)
   // ---- codec ----
   int codec_simt;          // VAURA_CODEC_SIMT=1         every convolution on the CUDA-core kernel (read when a codec is created)
