@@ -485,7 +485,7 @@ static int transformer_pass_bf16(const vaura_sampler* s, const Workspace& ws, co
       fa.R = R; fa.L = d.num_layers; fa.D = d.d_model; fa.F = d.ffn_dim; fa.H = d.nhead; fa.NH = d.num_codebooks * d.vocab;
       fa.wo_ksplit = kFusedKsplit; fa.w2_ksplit = kFusedKsplit;
       // split-K sums of wo / w2: float reductions into h (default), or - reproducible mode - one partial slice per K split,
-      // added in order by the CTA that normalises the row (measured 7 % slower per step: 1102 vs 1029 us at 64 rows)
+      // added in order by the CTA that normalises the row (measured 11 % slower per step: 1095 vs 990 us at 64 rows)
       fa.part = deterministic_mode() ? ws.part : nullptr;
       fa.eps = d.norm_eps; fa.scale = 1.0f / sqrtf((float)kHeadDim);
       fa.timing = knobs().phase_timing ? ws.timing : nullptr;

@@ -1450,7 +1450,8 @@ __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap
   pp.tiles += 1;
 }
 
-template <int TM>
+// DET: reproducible mode (FusedStepArgs::part), a separate instantiation so that the default kernel's code is untouched
+template <int TM, bool DET>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_constant__ CUtensorMap tm_attn,
                        const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wqkv,
@@ -1543,7 +1544,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
         if (c < n4) {
           if (!embed) {
             v[i] = __ldcg(reinterpret_cast<const float4*>(hrow) + c);
-            if (nparts > 0) {
+            if (DET && nparts > 0) {
               float4 pv[fused::kMaxParts];
 #pragma unroll
               for (int sp = 0; sp < fused::kMaxParts; ++sp)
@@ -1855,7 +1856,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   // with vector float reductions, whose order is not fixed
   auto resid_target = [&](int split) {
     ep.N = D; ep.ldo = D; ep.perm_S = 0;
-    if (a.part) { ep.mode = EPI_STORE; ep.out_f32 = a.part + (size_t)split * R * D; ep.atomic = 0; }
+    if constexpr (DET) { ep.mode = EPI_STORE; ep.out_f32 = a.part + (size_t)split * R * D; ep.atomic = 0; }
     else { ep.mode = EPI_RESID; ep.out_f32 = a.h; ep.atomic = 1; }
   };
 
@@ -1886,7 +1887,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       tiles_seen += tiles_wo;
       if (cta < R) {
         tiles_wait();
-        rmsnorm_phase(a.ffn_norm + (size_t)l * D, false, a.part ? a.wo_ksplit : 0);
+        rmsnorm_phase(a.ffn_norm + (size_t)l * D, false, DET ? a.wo_ksplit : 0);
       }
     }
     sync_all();
@@ -1911,7 +1912,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
       tiles_seen += tiles_w2;
       if (cta < R) {
         tiles_wait();
-        rmsnorm_phase(l + 1 < a.L ? a.attn_norm + (size_t)(l + 1) * D : a.final_norm, false, a.part ? a.w2_ksplit : 0);
+        rmsnorm_phase(l + 1 < a.L ? a.attn_norm + (size_t)(l + 1) * D : a.final_norm, false, DET ? a.w2_ksplit : 0);
       }
     }
     sync_all();
@@ -2172,18 +2173,18 @@ bool fused_step_supported(int R, int D, int F, int NH) {
 
 size_t fused_part_bytes(int R, int D) { return (size_t)kFusedKsplit * R * D * sizeof(float); }
 
-template <int TM>
+template <int TM, bool DET>
 static cudaError_t launch_decode_fused_t(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
                                          const void* w_heads, cudaStream_t st) {
   static int sms_tab[64] = {0};
   const int slot = current_device_slot();
   if (!sms_tab[slot]) {
-    cudaError_t e = cudaFuncSetAttribute(decode_step_fused_bf16<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(decode_step_fused_bf16<TM, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::kSmem);
     if (e != cudaSuccess) return e;
     int dev = 0, occ = 0, n = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_step_fused_bf16<TM>, kGemmThreads, fused::kSmem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_step_fused_bf16<TM, DET>, kGemmThreads, fused::kSmem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     sms_tab[slot] = n;
@@ -2227,14 +2228,17 @@ static cudaError_t launch_decode_fused_t(const FusedStepArgs& a, const void* wqk
   b.w_2 = static_cast<const __nv_bfloat16*>(w2);
   b.w_heads = static_cast<const __nv_bfloat16*>(w_heads);
   b.l2_prefetch = knobs().fused_l2_prefetch;
-  return cudaLaunchKernelEx(&cfg, decode_step_fused_bf16<TM>, m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads, b);
+  return cudaLaunchKernelEx(&cfg, decode_step_fused_bf16<TM, DET>, m_xn, m_attn, m_act, m_wqkv, m_wo, m_w13, m_w2, m_heads, b);
 }
 
 cudaError_t launch_decode_fused_bf16(const FusedStepArgs& a, const void* wqkv, const void* wo, const void* w13, const void* w2,
                                      const void* w_heads, cudaStream_t st) {
   if (!fused_step_supported(a.R, a.D, a.F, a.NH)) return cudaErrorInvalidValue;
-  return a.R <= 64 && !knobs().fused_tm128 ? launch_decode_fused_t<64>(a, wqkv, wo, w13, w2, w_heads, st)
-                                            : launch_decode_fused_t<128>(a, wqkv, wo, w13, w2, w_heads, st);
+  const bool tm64 = a.R <= 64 && !knobs().fused_tm128;
+  if (a.part) return tm64 ? launch_decode_fused_t<64, true>(a, wqkv, wo, w13, w2, w_heads, st)
+                          : launch_decode_fused_t<128, true>(a, wqkv, wo, w13, w2, w_heads, st);
+  return tm64 ? launch_decode_fused_t<64, false>(a, wqkv, wo, w13, w2, w_heads, st)
+              : launch_decode_fused_t<128, false>(a, wqkv, wo, w13, w2, w_heads, st);
 }
 
 static int mt_for(int R) { return (R + kTileM - 1) / kTileM; }

@@ -10,7 +10,7 @@ namespace vaura {
 
 struct Knobs {
   // ---- sampler dispatch (cabi.cu) ----
-  int deterministic;       // VAURA_DETERMINISTIC=1      bf16 step kernel: split-K slices added in a fixed order (7 % slower)
+  int deterministic;       // VAURA_DETERMINISTIC=1      bf16 step kernel: split-K slices added in a fixed order (11 % slower)
   int prefill_tc;          // VAURA_PREFILL_TC=0         multi-position fp32-activation passes stay on the GEMV kernels
   int fused_step;          // VAURA_FUSED_STEP=0         bf16 decode step as a graph of ~170 kernels instead of one kernel
   int fused_io;            // VAURA_FUSED_IO=0           embedding / sampling as separate launches around the fused step
