@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libvaura_b200.so")
+# VAURA_B200_LIB: another build of the same library (A/B measurements of compile-time variants, profiles/scripts/)
+LIB_PATH = os.environ.get("VAURA_B200_LIB") or os.path.join(HERE, "_lib", "libvaura_b200.so")
 
 EXPORTS = [
     "vaura_version", "vaura_arch", "vaura_last_error", "vaura_launch_count", "vaura_gemv_bf16w", "vaura_linear_bf16",

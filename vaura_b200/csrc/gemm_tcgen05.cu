@@ -1290,7 +1290,10 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // of the previous phase before the async-proxy reads (a second fence on the writer's side measured 1.6 % slower).
 // ------------------------------------------------------------------------------------------------
 namespace fused {
-constexpr int kKsub = 4, kBlockK = 64;
+#ifndef VAURA_FUSED_KSUB
+#define VAURA_FUSED_KSUB 4  // K blocks per ring stage (A/B builds: -DVAURA_FUSED_KSUB=2 -> twice as many half-size stages)
+#endif
+constexpr int kKsub = VAURA_FUSED_KSUB, kBlockK = 64;
 constexpr int kAccCols = 64;  // TMEM columns of the accumulator (BN <= 64)
 constexpr int kMaxParts = kFusedKsplit;  // K slices of a residual GEMM (wo, w2) = partial-sum slices a row CTA adds up
 constexpr int kBMax = 64 * kBlockK * 2;                   // 8 KB weight sub-tile (BN = 64; BN = 32 uses half of it)
@@ -1300,7 +1303,7 @@ struct Geo {
   static constexpr int kABytes = TM * kBlockK * 2;                 // 8 / 16 KB activation sub-tile
   static constexpr int kSubBytes = kABytes + kBMax;
   static constexpr int kStageBytes = kKsub * kSubBytes;            // 64 / 96 KB per stage
-  static constexpr int kStages = TM == 64 ? 3 : 2;                 // 192 KB of ring either way
+  static constexpr int kStages = (TM == 64 ? 12 : 8) / kKsub;      // 192 KB of ring either way (3 / 2 stages of 4 K blocks)
   static constexpr int kRing = kStages * kStageBytes;
 };
 constexpr int kAttnScratch = 10 * (kHeadDim + kMaxCtx) * 4;                  // per-warp q + scores
