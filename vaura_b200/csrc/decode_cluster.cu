@@ -131,15 +131,6 @@ __device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
   while (!mb_try_wait(bar, parity))
     if (clock64() - t0 > kSpinTimeoutCycles) __trap();
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 // Warp-uniform variants for the producer warp: every lane executes the statement with identical operands and one
 // elected lane issues.  Inside `if (lane == 0)` the compiler wraps every copy instruction in an ELECT + R2UR loop
 // (~0.13 us per copy of the issuing thread's time, profiles/probes/tma_rate.cu).

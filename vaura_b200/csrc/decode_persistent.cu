@@ -35,9 +35,6 @@ __device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
-}
 __device__ __forceinline__ bool mb_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -65,9 +62,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)),
                "l"(src), "r"(bytes), "r"(s_u32(bar))
                : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
 
@@ -404,7 +398,6 @@ __global__ void __launch_bounds__(kThreadsP, 1) decode_step_persistent(const Per
   const int part_off = red_off + 64 * 4;
   const int page_off = part_off + 128 * 4;
   const int bar_off = page_off + 8 * 4;
-  uint8_t* slots = smem + slots_off;
   float* xs = reinterpret_cast<float*>(smem + xs_off);
   float* scr = reinterpret_cast<float*>(smem + scr_off);
   float* hown = reinterpret_cast<float*>(smem + hown_off);

@@ -1363,7 +1363,7 @@ __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap
   };
   using namespace fused;
   using GE = Geo<TM>;
-  constexpr int kStages = GE::kStages, kStageBytes = GE::kStageBytes, kSubBytes = GE::kSubBytes, kABytes = GE::kABytes;
+  constexpr int kStages = GE::kStages, kStageBytes = GE::kStageBytes, kABytes = GE::kABytes;
   constexpr int B_BYTES = BN * kBlockK * 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int iters = (kb1 - kb0 + kKsub - 1) / kKsub;
