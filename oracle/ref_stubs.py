@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE ONLY — not part of the product path.
 
 Import stubs that let the *unmodified* reference (``/root/reference``) run in a container
-that lacks pytorch_lightning / av / dac / omegaconf.  Only ``oracle/make_golden.py``
-and ``tests/test_reference_crosscheck.py`` use this, and only when ``/root/reference`` exists
-(it does not exist on the GPU box).
+that lacks pytorch_lightning / av / dac / omegaconf.  Only the golden-vector generators
+(``oracle/make_golden.py``, ``oracle/make_golden_motionformer.py``) and the CPU tests that re-check
+the oracle against the live reference (``tests/test_host.py``, ``tests/test_oracle_golden.py``)
+use this, and only when ``/root/reference`` exists (it does not exist on the GPU box).
 
 Nothing here re-implements reference arithmetic: the transformer, the delay pattern, the
 samplers and ``VAURAModel.generate`` all execute from the reference's own files.  The only
