@@ -29,6 +29,9 @@ CASES = [  # (batch, new tokens, prompt tokens, cfg_scale)
     (1, 1, 0, 1.0), (1, 7, 0, 6.0), (2, 13, 3, 1.0), (3, 9, 0, 1.0), (4, 5, 2, 1.0), (5, 11, 0, 6.0), (9, 6, 0, 1.0),
     (15, 4, 1, 1.0), (16, 10, 0, 1.0), (17, 3, 0, 1.0), (33, 12, 5, 6.0), (64, 6, 0, 1.0), (65, 5, 0, 1.0), (100, 4, 2, 1.0),
     (128, 3, 0, 1.0), (70, 4, 0, 6.0),
+    # maximum length: T + prompt = 248 tokens -> 257 columns, the last step feeds position 255 = the last row of the RoPE table
+    # (llama.py:364-368, :493-497) and the last slot of the eighth K/V page; with and without a long prompt prefill
+    (1, 248, 0, 1.0), (16, 248, 0, 1.0), (3, 120, 128, 1.0), (40, 100, 148, 6.0),
 ]
 
 

@@ -179,6 +179,18 @@ def test_product_package_never_imports_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
 
 
+def test_environment_knobs_live_in_one_place():
+    """csrc/knobs.h declares every environment variable the library reads; knobs.cu is the only file that calls getenv, and
+    every variable it reads is documented in the header."""
+    csrc = os.path.join(ROOT, "vaura_b200", "csrc")
+    for f in os.listdir(csrc):
+        if f.endswith((".cu", ".cuh", ".h")) and f != "knobs.cu":
+            assert "getenv" not in open(os.path.join(csrc, f)).read(), f
+    read = set(re.findall(r'"(VAURA_[A-Z0-9_]+)"', open(os.path.join(csrc, "knobs.cu")).read()))
+    documented = set(re.findall(r"\b(VAURA_[A-Z0-9_]+)", open(os.path.join(csrc, "knobs.h")).read()))
+    assert read and read <= documented, read - documented
+
+
 # ---- weight streams of the cluster-persistent decode kernel (weights.py: pack_cluster_stream) --------------------
 STREAM_SHAPES = {"qkv": (4608, 1536), "wo": (1536, 1536), "w13": (8192, 1536), "w2": (1536, 4096), "heads": (9216, 1536)}
 
