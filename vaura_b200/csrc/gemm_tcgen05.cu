@@ -1365,7 +1365,7 @@ __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap
   using GE = Geo<TM>;
   constexpr int kStages = GE::kStages, kStageBytes = GE::kStageBytes, kABytes = GE::kABytes;
   constexpr int B_BYTES = BN * kBlockK * 2;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const int iters = (kb1 - kb0 + kKsub - 1) / kKsub;
   const int rot = blockIdx.x % iters;
   if (warp == 0) {
@@ -1403,7 +1403,10 @@ __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap
       // descriptors differ only in their 14-bit address field: +2 per 32-byte K step inside the swizzle atom
       const uint32_t st_addr = smem_u32(pp.smem + s * kStageBytes);
       static_assert((make_smem_desc<128>(0) >> 32) == 0x40004040ull, "descriptor high word");
-      const uint32_t a_lo = (st_addr & 0x3FFFF) >> 4, b_lo = ((st_addr + kKsub * kABytes) & 0x3FFFF) >> 4;
+      // broadcast from lane 0: the compiler then keeps the descriptor words in uniform registers (UIADD3 per MMA instead of four
+      // R2UR.BROADCAST from vector registers)
+      const uint32_t a_lo = __shfl_sync(0xffffffffu, (st_addr & 0x3FFFF) >> 4, 0);
+      const uint32_t b_lo = __shfl_sync(0xffffffffu, ((st_addr + kKsub * kABytes) & 0x3FFFF) >> 4, 0);
       if (nsub == kKsub) {
 #pragma unroll
         for (int sub = 0; sub < kKsub; ++sub)
@@ -1477,7 +1480,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   pp.git = 0;
   pp.tiles = 0;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // provably warp-uniform
   const int cta = blockIdx.x, G = gridDim.x;
   const int R = a.R, D = a.D, F = a.F;
   const unsigned epoch = a.state->epoch;
@@ -1519,7 +1522,7 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  pp.tmem_base = *tmem_slot;
+  pp.tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // ---- RMSNorm of the residual row `cta` (llama.py:147-158): fp32 math, bf16 output = the next GEMM's A operand.
   //      embed = true (first phase of a step with fuse_io): the row is built here from the conditioning row and the 9
