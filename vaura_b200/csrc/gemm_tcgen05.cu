@@ -554,7 +554,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   static_assert(CK == 1 || (size_t)(CK - 1) * 128 * (BLOCK_N / CK + 4) * 4 <= (size_t)STAGES * STAGE_BYTES,
                 "the receive buffer aliases the stage ring");
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const int m0 = blockIdx.x * TILE_M, n0 = blockIdx.y * BLOCK_N;
   const int split = blockIdx.z % g.ksplit, zz = blockIdx.z / g.ksplit;
   const int b = zz / g.nphase, phase = zz % g.nphase;
@@ -584,7 +584,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (CK > 1) cluster_sync_all();  // every peer's exchange barrier is initialised and armed before anything can reach it
 
   // NOTE: triggering the dependent grid BEFORE this grid's own griddepcontrol.wait was measured to break the chain
@@ -765,7 +765,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   uint64_t* tempty = tfull + 2;       // [2] accumulator buffer drained by the 8 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const int kgroups = g.kblocks / KSUB;  // stages per tap
   const int iters = g.ntaps * kgroups;
   const int zdim = g.batch * g.nphase;
@@ -791,7 +791,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // tile -> (m0, n0, batch, phase); m fastest so that neighbouring CTAs share the weight tile in L2
   auto tile_coords = [&](int t, int& m0, int& n0, int& b, int& phase) {
@@ -964,7 +964,7 @@ gemm_tc2_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   uint64_t* tempty = tfull + 2;       // [2] leader only: drained by the 2 x EW epilogue warps of the pair
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int iters = g.kblocks;
@@ -991,7 +991,7 @@ gemm_tc2_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   auto tile_coords = [&](int t, int& m0, int& n0) {  // N first: the pairs that run together share activation rows in L2
     n0 = (t % n_tiles) * BLOCK_N;
@@ -1116,7 +1116,7 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* acc2_free = acc2_full + 1; // 8 arrivals: acc2 drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_free + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const int units7 = g.ntaps * KB;  // ring stages of the k7 mainloop per tile; KB more carry the W1 K blocks
   const int ntiles = m_tiles * g.batch;
 
@@ -1146,7 +1146,7 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     int git = 0;
