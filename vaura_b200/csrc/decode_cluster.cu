@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) decode_step_cluster(const __grid
   constexpr int UPL = LY::upl;          // units per layer: 6 qkv + NB wo + 4 w13 + 2 w2
   constexpr int U_WO = 6, U_W13 = 6 + NB, U_W2 = 10 + NB;
   extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int cta = blockIdx.x, G = gridDim.x;
   const int rank = (int)cluster_rank();
   const int cl = cta / CL;                // cluster
