@@ -1,0 +1,14 @@
+#!/bin/bash
+# the arrival stamps (debug only, a.timing == nullptr in normal runs) must not cost anything: same-box A/B against the build before
+L=$PWD/vaura_b200/_lib
+one() {
+  VAURA_B200_LIB=$1 python bench.py --workload $3 --steps 3 --warmup 2 --no-cpu-baseline --no-sub 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('$2 $3', round(d['value'],1), round(d['roofline']['us_per_launch'],1), d['decode_step']['p50_us'])"
+}
+for i in 1 2; do
+one $L/libvaura_b200_head.so head b64
+one $L/libvaura_b200.so new b64
+done
+one $L/libvaura_b200_head.so head b64_cfg
+one $L/libvaura_b200.so new b64_cfg

@@ -1322,9 +1322,10 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 // device-wide barrier: no bulk copy is in flight when a CTA arrives (its mainloop has drained), so the release /
 // acquire pair costs its idle latency (~0.75 us, profiles/r01_probe_sync_latency_under_tma.txt)
-__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned target) {
+__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned target, unsigned long long* arrival = nullptr) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (arrival) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(*arrival));  // every warp of the CTA is done with the phase
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     if ((int)(ld_acquire_u32(counter) - target) < 0) {
       const long long t0 = clock64();
@@ -1502,7 +1503,22 @@ decode_step_fused_bf16(const __grid_constant__ CUtensorMap tm_xn, const __grid_c
     }
     ++stamp_i;
   };
-  auto sync_all = [&]() { stamp(); grid_sync(&a.state->barrier, (epoch * nbar + (++bi)) * (unsigned)G); stamp(); };
+  auto sync_all = [&]() {
+    stamp();
+    ++bi;
+    // optional: when every CTA arrives at the five barriers of the last layer (timing[1300 + phase * G + cta];
+    // profiles/fused_arrivals.py): which CTAs a phase waits for
+    // (compiled in with -DVAURA_FUSED_ARRIVALS only: the stamps cost 0.3 % of a step even when they are off)
+    unsigned long long* arrival = nullptr;
+#ifdef VAURA_FUSED_ARRIVALS
+    if (a.timing) {
+      const int pi = (int)bi - (2 + 5 * (a.L - 1));
+      if (pi >= 0 && pi < 5 && 1300 + pi * G + cta < 2048) arrival = a.timing + 1300 + pi * G + cta;
+    }
+#endif
+    grid_sync(&a.state->barrier, (epoch * nbar + bi) * (unsigned)G, arrival);
+    stamp();
+  };
 
   if (warp == 0 && lane == 0) {
     const CUtensorMap* maps[8] = {&tm_xn, &tm_attn, &tm_act, &tm_wqkv, &tm_wo, &tm_w13, &tm_w2, &tm_heads};
