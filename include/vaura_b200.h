@@ -36,7 +36,12 @@ extern "C" {
 
 #define VAURA_PRECISION_AUTO 0    /* BF16 from 16 sequence rows, and from 3 rows when the call samples (top-k / top-p /
                                      temperature: no bit-exactness contract); FP32ACT otherwise (greedy, rows <= 2) */
-#define VAURA_PRECISION_FP32ACT 1 /* bf16 weights, fp32 activations + fp32 KV, CUDA-core FMA (HBM-bound small batch) */
+#define VAURA_PRECISION_FP32ACT 1 /* bf16 weights, fp32 activations + fp32 KV (HBM-bound small batch).  Decode steps: fp32-exact
+                                     products (cluster / persistent kernels).  Multi-position passes (prompt prefill, teacher-forced
+                                     forward) run on tcgen05 with every fp32 operand split into three bf16 terms (fp32-equivalent,
+                                     greedy tokens stay bit-exact); the prompt prefill of a call that samples rounds the GEMM
+                                     operands to bf16 once instead (residual stream, q, K/V and attention still fp32; logits
+                                     within the BF16 tolerance; csrc/knobs.h: VAURA_PREFILL_BF16=0 turns that off) */
 #define VAURA_PRECISION_BF16 2    /* bf16 weights + bf16 activations/KV, tcgen05 GEMMs, fp32 accumulate */
 
 #define VAURA_KV_F32 0
