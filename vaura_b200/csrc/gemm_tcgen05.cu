@@ -1088,6 +1088,22 @@ gemm_tc2_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 // measured slower (9.23 vs 8.45 ms per 16 clips): with two 256-column buffers the second epilogue then sits between two k7
 // mainloops instead of under one.
 // ------------------------------------------------------------------------------------------------
+#ifdef VAURA_RU_TIMING
+// debug build only (profiles/ru_timing.py): %globaltimer stamps of CTA 0, tiles 8..15: [tile][role 0 = MMA warp, 1 = epilogue warp 2,
+// 2 = producer][8 events]
+__device__ unsigned long long g_ru_timing[8 * 3 * 8];
+#define RU_STAMP(tile_i, role, ev)                                                                     \
+  do {                                                                                                 \
+    if (blockIdx.x == 0 && lane == 0 && (tile_i) >= 8 && (tile_i) < 16) {                              \
+      unsigned long long t_;                                                                           \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                           \
+      g_ru_timing[(((tile_i) - 8) * 3 + (role)) * 8 + (ev)] = t_;                                      \
+    }                                                                                                  \
+  } while (0)
+#else
+#define RU_STAMP(tile_i, role, ev) do {} while (0)
+#endif
+
 struct RuParams {
   const float *bias7, *alpha2;   // conv k7 bias; Snake after it ([C] alpha | [C] 1 / (alpha + 1e-9))
   EpiConv::Params k1;            // conv k1 epilogue: bias, Snake of the consumer, residual x, raw / activated outputs
@@ -1150,9 +1166,12 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   if (warp == 0) {
     int git = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int tcp = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcp) {
       const int m0 = (t % m_tiles) * kTileM, b = t / m_tiles;
+      RU_STAMP(tcp, 2, 0);
       for (int it = 0; it < units7 + KB; ++it, ++git) {
+        if (it == units7) RU_STAMP(tcp, 2, 1);
         const int s = git % STAGES;
         const uint32_t ph = (git / STAGES) & 1;
         uint8_t* ss = smem + s * STAGE_BYTES;
@@ -1167,6 +1186,7 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tma_load_3d_elect(ss + A_BYTES, &tmW1, &full[s], (it - units7) * BLOCK_K, 0, 0);
         }
       }
+      RU_STAMP(tcp, 2, 2);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -1174,10 +1194,12 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int git = 0, tc = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
       const uint32_t tph = tc & 1;
+      RU_STAMP(tc, 0, 0);
       for (int it = 0; it < units7; ++it, ++git) {
         const int s = git % STAGES;
         mbar_wait(&full[s], (git / STAGES) & 1);
         tcgen05_fence_after();
+        if (it == 0) RU_STAMP(tc, 0, 1);
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
         const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
 #pragma unroll
@@ -1185,10 +1207,13 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         umma_commit_elect(&empty[s]);
       }
       umma_commit_elect(acc1_full);
+      RU_STAMP(tc, 0, 2);
       mbar_wait(acc2_free, tph ^ 1);       // the previous tile's second epilogue has drained acc2 (first use passes)
+      RU_STAMP(tc, 0, 3);
       for (int kb = 0; kb < KB; ++kb, ++git) {
         const int s = git % STAGES;
         mbar_wait(&h_ready[kb], tph);      // K block kb of this tile's h is in shared memory
+        if (kb == 0) RU_STAMP(tc, 0, 4);
         mbar_wait(&full[s], (git / STAGES) & 1);
         tcgen05_fence_after();
         const uint64_t adesc = make_smem_desc<SW>(smem_u32(hs + kb * A_BYTES));
@@ -1198,6 +1223,7 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         umma_commit_elect(&empty[s]);
       }
       umma_commit_elect(acc2_full);
+      RU_STAMP(tc, 0, 5);
     }
     __syncwarp();
   } else {
@@ -1212,6 +1238,7 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
       const int m0 = (t % m_tiles) * kTileM, b = t / m_tiles, m = m0 + row;
       const uint32_t tph = tc & 1;
+      if (warp == 2) RU_STAMP(tc, 1, 0);
       // residual rows of the second epilogue: in flight while the tile's MMAs run
       uint4 res[kHalf][2];
 #pragma unroll
@@ -1222,6 +1249,7 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // ---- first epilogue: h = Snake(acc1 + b7) -> shared memory, K-major, 128B / 64B swizzle (what a tensor copy would write)
       mbar_wait(acc1_full, tph);
       tcgen05_fence_after();
+      if (warp == 2) RU_STAMP(tc, 1, 1);
 #pragma unroll 1
       for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
@@ -1255,8 +1283,10 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&h_ready[kb])) : "memory");
       }
       // ---- second epilogue: acc2 + b1 + x -> raw x' and Snake(x') for the consumer
+      if (warp == 2) RU_STAMP(tc, 1, 2);
       mbar_wait(acc2_full, tph);
       tcgen05_fence_after();
+      if (warp == 2) RU_STAMP(tc, 1, 3);
 #pragma unroll
       for (int i = 0; i < kHalf; ++i) {
         const int c = c_begin + 16 * i;
@@ -1268,6 +1298,7 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       tcgen05_fence_before();
       __syncwarp();
+      if (warp == 2) RU_STAMP(tc, 1, 4);
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc2_free)) : "memory");
     }
   }
@@ -2109,6 +2140,12 @@ static cudaError_t launch_ru_fused_t(const RuArgs& a, const int* taps7_host, int
   kern<<<dim3(ntiles < sms ? ntiles : sms), dim3(kGemmThreads), smem, st>>>(ta, t7, t1, g, rp, mt);
   return cudaGetLastError();
 }
+
+#ifdef VAURA_RU_TIMING
+extern "C" int vaura_debug_ru_timing(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_ru_timing, sizeof(g_ru_timing));
+}
+#endif
 
 bool ru_fused_supported(int C) { return C == 192 || C == 96 || C == 128 || C == 64 || C == 256; }
 
