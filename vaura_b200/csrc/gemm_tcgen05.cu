@@ -1310,6 +1310,218 @@ gemm_ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Same unit for C <= 128, skewed by one tile: with 3 x ACC <= 384 TMEM columns there is room for two acc1 buffers, and with a
+// second h tile in shared memory the MMA warp never waits for the first epilogue (a third of a tile in the kernel above,
+// profiles/r02_codec_fused_ru.summary.txt).  Used for the encoder's 64- and 128-channel units (launch_ru_fused):
+//   MMA warp        k7(0) | k7(1) k1(0) | k7(2) k1(1) | ...      k7(t) -> acc1[t & 1], k1(t): hs[t & 1] x W1 -> acc2
+//   epilogue warps  epi1(0) | epi1(1) epi2(0) | epi1(2) epi2(1) | ...   epi1(t): acc1[t & 1] -> hs[t & 1], epi2(t): acc2 -> outputs
+//   producer        the ring stages in the MMA warp's order
+// acc1[t & 1] is free for k7(t + 2) because k1(t), issued before it, waited for every K block of h(t); hs[t & 1] is free for
+// epi1(t + 2) because epi2(t), which precedes it, waited for k1(t)'s commit; acc2 is single-buffered (acc2_free as above).
+// ------------------------------------------------------------------------------------------------
+template <int C, int BLOCK_K, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_ru_fused_skew_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW7,
+                          const __grid_constant__ CUtensorMap tmW1, const TcShape g, const RuParams rp, const int m_tiles) {
+  constexpr int SW = BLOCK_K * 2, KB = C / BLOCK_K;
+  constexpr int A_BYTES = kTileM * BLOCK_K * 2, B_BYTES = C * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int H_BYTES = KB * A_BYTES;
+  constexpr int ACC = C <= 32 ? 32 : C <= 64 ? 64 : 128, TMEM_COLS = ACC == 128 ? 512 : 4 * ACC;  // 3 x ACC, rounded up to 2^n
+  static_assert(C % BLOCK_K == 0 && C % 16 == 0 && C <= 128, "channel count");
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "stage buffers must stay 1024B aligned for the swizzle");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* hs = smem + STAGES * STAGE_BYTES;  // two h tiles: KB sub-tiles [128 rows][BLOCK_K] fp16 each, swizzled like a TMA-written A tile
+  float* par = reinterpret_cast<float*>(hs + 2 * H_BYTES);  // [3][C]: conv k7 bias | Snake alpha | 1 / (alpha + 1e-9)
+  uint64_t* full = reinterpret_cast<uint64_t*>(par + 3 * C);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc1_full = empty + STAGES;  // [2]
+  uint64_t* h_ready = acc1_full + 2;     // [2][KB] 8 arrivals each
+  uint64_t* acc2_full = h_ready + 2 * KB;
+  uint64_t* acc2_free = acc2_full + 1;   // 8 arrivals: acc2 drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_free + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
+  const int units7 = g.ntaps * KB;
+  const int ntiles = m_tiles * g.batch;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW7) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) mbar_init(&acc1_full[i], 1);
+    for (int i = 0; i < 2 * KB; ++i) mbar_init(&h_ready[i], 8);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_free, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  for (int i = threadIdx.x; i < C; i += kGemmThreads) {
+    par[i] = rp.bias7[i];
+    par[C + i] = rp.alpha2[i];
+    par[2 * C + i] = rp.alpha2[C + i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    int git = 0;
+    auto load_k7 = [&](int t) {
+      const int m0 = (t % m_tiles) * kTileM, b = t / m_tiles;
+      for (int it = 0; it < units7; ++it, ++git) {
+        const int s = git % STAGES;
+        uint8_t* ss = smem + s * STAGE_BYTES;
+        mbar_wait(&empty[s], ((git / STAGES) & 1) ^ 1);
+        const int tap = it / KB, kb = it % KB;
+        mbar_expect_tx_elect(&full[s], STAGE_BYTES);
+        tma_load_3d_elect(ss + A_BYTES, &tmW7, &full[s], kb * BLOCK_K, 0, tap);
+        tma_load_3d_elect(ss, &tmA, &full[s], kb * BLOCK_K, m0 + g.tap_off[tap], b);
+      }
+    };
+    auto load_w1 = [&]() {
+      for (int kb = 0; kb < KB; ++kb, ++git) {
+        const int s = git % STAGES;
+        uint8_t* ss = smem + s * STAGE_BYTES;
+        mbar_wait(&empty[s], ((git / STAGES) & 1) ^ 1);
+        mbar_expect_tx_elect(&full[s], B_BYTES);
+        tma_load_3d_elect(ss + A_BYTES, &tmW1, &full[s], kb * BLOCK_K, 0, 0);
+      }
+    };
+    if (my_tiles > 0) load_k7(blockIdx.x);
+    for (int tc = 0; tc < my_tiles; ++tc) {
+      if (tc + 1 < my_tiles) load_k7(blockIdx.x + (tc + 1) * gridDim.x);
+      load_w1();
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(kTileM, C, 0);
+    int git = 0;
+    auto mma_k7 = [&](int tc) {  // tile tc of this CTA -> acc1[tc & 1]
+      const uint32_t acc = tmem_base + (uint32_t)((tc & 1) * ACC);
+      for (int it = 0; it < units7; ++it, ++git) {
+        const int s = git % STAGES;
+        mbar_wait(&full[s], (git / STAGES) & 1);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc<SW>(a_addr), bdesc = make_smem_desc<SW>(a_addr + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) umma_bf16_f16_elect(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        umma_commit_elect(&empty[s]);
+      }
+      umma_commit_elect(&acc1_full[tc & 1]);
+    };
+    if (my_tiles > 0) mma_k7(0);
+    for (int tc = 0; tc < my_tiles; ++tc) {
+      if (tc + 1 < my_tiles) mma_k7(tc + 1);
+      mbar_wait(acc2_free, (tc & 1) ^ 1);  // the previous tile's second epilogue has drained acc2 (first use passes)
+      const uint32_t hph = (tc >> 1) & 1;
+      for (int kb = 0; kb < KB; ++kb, ++git) {
+        const int s = git % STAGES;
+        mbar_wait(&h_ready[(tc & 1) * KB + kb], hph);  // K block kb of this tile's h is in shared memory
+        mbar_wait(&full[s], (git / STAGES) & 1);
+        tcgen05_fence_after();
+        const uint64_t adesc = make_smem_desc<SW>(smem_u32(hs + (tc & 1) * H_BYTES + kb * A_BYTES));
+        const uint64_t bdesc = make_smem_desc<SW>(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k)
+          umma_bf16_f16_elect(tmem_base + 2 * ACC, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit_elect(&empty[s]);
+      }
+      umma_commit_elect(acc2_full);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, row = q * 32 + lane, half = (warp - 2) >> 2;
+    constexpr int kChunks = C / 16, kHalf = (kChunks + 1) / 2;
+    constexpr int CPB = BLOCK_K / 16, CPH = (CPB + 1) / 2;  // 16-column chunks per K block / per warp and K block
+    const int c_begin = half == 0 ? 0 : kHalf * 16, c_end = half == 0 ? kHalf * 16 : C;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    // second epilogue of tile tc: acc2 + b1 + x -> raw x' and Snake(x') for the consumer
+    auto epi2 = [&](int tc) {
+      const int t = blockIdx.x + tc * gridDim.x;
+      const int m = (t % m_tiles) * kTileM + row, b = t / m_tiles;
+      uint4 res[kHalf][2];
+#pragma unroll
+      for (int i = 0; i < kHalf; ++i) {
+        const int c = c_begin + 16 * i;
+        if (c < c_end) EpiConv::load_residual(rp.k1, b, 0, m, c, res[i][0], res[i][1]);
+      }
+      mbar_wait(acc2_full, tc & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int i = 0; i < kHalf; ++i) {
+        const int c = c_begin + 16 * i;
+        if (c < c_end) {
+          float v[16];
+          tmem_ld16(tq + 2 * ACC + c, v);
+          EpiConv::apply(rp.k1, b, 0, m, c, v, res[i][0], res[i][1]);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc2_free)) : "memory");
+    };
+    for (int tc = 0; tc < my_tiles; ++tc) {
+      // ---- first epilogue of tile tc: h = Snake(acc1 + b7) -> hs[tc & 1], K block by K block
+      uint8_t* hb = hs + (tc & 1) * H_BYTES;
+      const uint32_t ta = tq + (uint32_t)((tc & 1) * ACC);
+      mbar_wait(&acc1_full[tc & 1], (tc >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+        for (int i = 0; i < CPH; ++i) {
+          const int cc = half * CPH + i;  // chunk inside the K block
+          if (cc < CPB) {
+            const int c = kb * BLOCK_K + 16 * cc;
+            float v[16];
+            tmem_ld16(ta + c, v);
+            uint4 o[2];
+            __half2* h2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(par + c + e);
+              const float4 al = *reinterpret_cast<const float4*>(par + C + c + e);
+              const float4 ia = *reinterpret_cast<const float4*>(par + 2 * C + c + e);
+              h2[e / 2] = __floats2half2_rn(snake_eval(v[e] + bb.x, al.x, ia.x), snake_eval(v[e + 1] + bb.y, al.y, ia.y));
+              h2[e / 2 + 1] = __floats2half2_rn(snake_eval(v[e + 2] + bb.z, al.z, ia.z), snake_eval(v[e + 3] + bb.w, al.w, ia.w));
+            }
+            const int j = 2 * cc;  // first 16-byte chunk inside the row of this K block
+            uint8_t* rowp = hb + kb * A_BYTES + row * SW;
+            const int sw = SW == 128 ? (row & 7) : ((row >> 1) & 3);
+            *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = o[0];
+            *reinterpret_cast<uint4*>(rowp + (((j + 1) ^ sw) << 4)) = o[1];
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&h_ready[(tc & 1) * KB + kb])) : "memory");
+      }
+      if (tc > 0) epi2(tc - 1);
+    }
+    if (my_tiles > 0) epi2(my_tiles - 1);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused decode step of the bf16 path for up to 64 sequence rows (one new position per row): ONE cooperative kernel runs
 // the 24 layers + final norm + heads that transformer_pass_bf16 issues as 170 launches.  Each phase is the same tile
 // arithmetic as the stand-alone kernels (rmsnorm_bf16_kernel, gemm_tc_kernel with UMMA M = 64 and 4 K blocks per stage,
@@ -2147,10 +2359,50 @@ extern "C" int vaura_debug_ru_timing(unsigned long long* out) {
 }
 #endif
 
+template <int C, int BLOCK_K, int STAGES>
+static cudaError_t launch_ru_fused_skew_t(const RuArgs& a, const int* taps7_host, int B, cudaStream_t st) {
+  constexpr int KB = C / BLOCK_K;
+  constexpr int smem = STAGES * (kTileM * BLOCK_K * 2 + C * BLOCK_K * 2) + 2 * KB * kTileM * BLOCK_K * 2 + 3 * C * 4 + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "ring + two h tiles exceed shared memory");
+  CUtensorMap ta, t7, t1;
+  if (!make_map(&ta, a.act, C, a.T, B, C, (uint64_t)a.T * C, BLOCK_K, kTileM, true) ||
+      !make_map(&t7, a.W7, C, C, 7, C, (uint64_t)C * C, BLOCK_K, C, true) ||
+      !make_map(&t1, a.W1, C, C, 1, C, (uint64_t)C * C, BLOCK_K, C, true))
+    return cudaErrorUnknown;
+  auto kern = gemm_ru_fused_skew_kernel<C, BLOCK_K, STAGES>;
+  static int sms_tab[64] = {0};
+  const int slot = current_device_slot();
+  if (!sms_tab[slot]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms_tab[slot], cudaDevAttrMultiProcessorCount, dev);
+  }
+  TcShape g{};
+  g.ntaps = 7; g.nphase = 1; g.kblocks = KB; g.batch = B; g.ksplit = 1;
+  for (int i = 0; i < 7; ++i) g.tap_off[i] = taps7_host[i];
+  RuParams rp{};
+  rp.bias7 = a.bias7; rp.alpha2 = a.alpha2;
+  rp.k1 = EpiConv::Params{a.bias1, a.alpha_next, a.x, a.out_raw, a.out_act, a.T, a.T, C, 1};
+  const int mt = (a.T + kTileM - 1) / kTileM, ntiles = mt * B, sms = sms_tab[slot];
+  kern<<<dim3(ntiles < sms ? ntiles : sms), dim3(kGemmThreads), smem, st>>>(ta, t7, t1, g, rp, mt);
+  return cudaGetLastError();
+}
+
 bool ru_fused_supported(int C) { return C == 192 || C == 96 || C == 128 || C == 64 || C == 256; }
 
 // One launch per ResidualUnit (see gemm_ru_fused_kernel)
 cudaError_t launch_ru_fused(const RuArgs& a, const int* taps7_host, int B, cudaStream_t st) {
+  // The variant skewed by one tile (two acc1 buffers, two h tiles) for the encoder's 64- and 128-channel units: DAC encode of
+  // 64 clips 21.7 -> 21.0 ms.  The decoder's 96-channel units gain 3-4 % at dilation 1 and 3 and lose 5 % at dilation 9
+  // (629 / 618 / 570 us against 646 / 645 / 542 us per launch, profiles/scripts/r02_run76.sh): they stay on the kernel above.
+  if (knobs().codec_ru_skew) {
+    switch (a.C) {
+      case 128: return launch_ru_fused_skew_t<128, 64, 4>(a, taps7_host, B, st);
+      case 64: return launch_ru_fused_skew_t<64, 64, 8>(a, taps7_host, B, st);
+    }
+  }
   switch (a.C) {
     case 256: return launch_ru_fused_t<256, 64, 3>(a, taps7_host, B, st);
     case 192: return launch_ru_fused_t<192, 64, 4>(a, taps7_host, B, st);

@@ -49,6 +49,7 @@ Knobs read_env() {
   k.prefill_bn256_from = env_int("VAURA_PREFILL_BN256_FROM", 8192);
   k.codec_simt = env_flag("VAURA_CODEC_SIMT", 0);
   k.codec_fused_ru = env_flag("VAURA_CODEC_FUSED_RU", 1);
+  k.codec_ru_skew = env_flag("VAURA_CODEC_RU_SKEW", 1);
   k.conv_persistent = env_flag("VAURA_CONV_PERSISTENT", 1);
   k.conv_ksub = env_flag("VAURA_CONV_KSUB", 1);
   k.conv_occ2 = env_flag("VAURA_CONV_OCC2", 0);

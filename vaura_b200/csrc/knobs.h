@@ -44,6 +44,7 @@ struct Knobs {
   // ---- codec ----
   int codec_simt;          // VAURA_CODEC_SIMT=1         every convolution on the CUDA-core kernel (read when a codec is created)
   int codec_fused_ru;      // VAURA_CODEC_FUSED_RU=0     residual units as two launches
+  int codec_ru_skew;       // VAURA_CODEC_RU_SKEW=0      encoder's 64- / 128-channel fused residual units without the one-tile skew
   int conv_persistent;     // VAURA_CONV_PERSISTENT=0    one CTA per tile instead of the persistent tile loop
   int conv_ksub;           // VAURA_CONV_KSUB=0
   int conv_occ2;           // VAURA_CONV_OCC2=1          two CTAs per SM for the 96-channel layers (measured neutral)
