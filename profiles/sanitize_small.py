@@ -1,5 +1,5 @@
 """Small invocations of the round-2 kernels for compute-sanitizer (memcheck):
-    compute-sanitizer --tool memcheck python profiles/sanitize_small.py [avclip|encode|decode|prefill]"""
+    compute-sanitizer --tool memcheck python profiles/sanitize_small.py [avclip|encode|decode|prefill|prefill_bf16|step]"""
 import os
 import sys
 
@@ -26,6 +26,20 @@ elif what in ("encode", "decode"):
     else:
         wav = c.decode(torch.randint(0, 1024, (2, 9, 7)).cuda())
         print("decode", tuple(wav.shape), float(wav.float().abs().max()))
+elif what == "step":  # decode_step_fused_bf16 (16 rows, a few columns) and decode_step_cluster (1 row)
+    from vaura_b200.synthetic import FULL_CODEC, FULL_SAMPLER, build_model, make_avclip_features
+    m = build_model(FULL_SAMPLER, FULL_CODEC)
+    for B in (16, 1):
+        o = m.generate(frames=make_avclip_features(B, 3).cuda(), max_new_tokens=3, prompt_is_encoded=True, _decode_audio=False,
+                       use_sampling=True, top_k=64, return_sampled_indices=True)
+        print("step", B, tuple(o["sampled_indices"].shape))
+elif what == "prefill_bf16":  # prompt prefill of a sampling call: bf16 GEMM operands (transformer_pass_tc1)
+    from vaura_b200.synthetic import FULL_CODEC, FULL_SAMPLER, build_model, make_avclip_features
+    m = build_model(FULL_SAMPLER, FULL_CODEC)
+    prompt = torch.randint(0, 1024, (1, 9, 150)).cuda()
+    o = m.generate(frames=make_avclip_features(1, 3).cuda(), audio=prompt, max_new_tokens=160, prompt_is_encoded=True,
+                   _decode_audio=False, _end_offset=153, use_sampling=True, top_k=64, return_sampled_indices=True)
+    print("prefill_bf16", tuple(o["sampled_indices"].shape))
 else:
     from vaura_b200.synthetic import FULL_CODEC, FULL_SAMPLER, build_model, make_avclip_features
     m = build_model(FULL_SAMPLER, FULL_CODEC)
