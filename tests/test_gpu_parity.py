@@ -288,8 +288,11 @@ def test_bf16_path_with_cfg_and_prompt_prefill(tiny_model, tiny_oracle):
     assert rel_err(mine, ref[:, :, Tp:]) < 2 * BF16_LOGIT_TOL  # CFG amplifies the error by ~cfg_scale
 
 
-def test_bf16_path_128_row_fused_step(tiny_model, tiny_oracle):
-    """48 clips with CFG = 96 sequence rows: the fused decode-step kernel's 128-row instance (UMMA M = 128)."""
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_bf16_path_128_row_fused_step(tiny_model, tiny_oracle, deterministic, monkeypatch):
+    """48 clips with CFG = 96 sequence rows: the fused decode-step kernel's 128-row instance (UMMA M = 128), in the default and
+    in the reproducible mode (VAURA_DETERMINISTIC=1: a repeated call returns the same bits)."""
+    monkeypatch.setenv("VAURA_DETERMINISTIC", "1" if deterministic else "0")
     B, T = 48, 12
     feats = make_avclip_features(B, 41)
     out = tiny_model.generate(frames=feats.cuda(), max_new_tokens=T, use_sampling=False, prompt_is_encoded=True,
@@ -303,6 +306,12 @@ def test_bf16_path_128_row_fused_step(tiny_model, tiny_oracle):
     ref = lg[B:] + (lg[:B] - lg[B:]) * 2.0
     mine = out["_logits"][1:].cpu().permute(1, 2, 0, 3)
     assert rel_err(mine, ref) < 2 * BF16_LOGIT_TOL  # CFG amplifies the error by ~cfg_scale
+    if deterministic:
+        again = tiny_model.generate(frames=feats.cuda(), max_new_tokens=T, use_sampling=False, prompt_is_encoded=True,
+                                    return_sampled_indices=True, cfg_scale=2.0, check=True, _return_logits=True,
+                                    _decode_audio=False)
+        assert torch.equal(again["_logits"][1:], out["_logits"][1:])
+        assert torch.equal(again["sampled_indices"], out["sampled_indices"])
 
 
 def test_bf16_fused_step_with_16_position_pages(tiny_model, tiny_oracle, monkeypatch):
