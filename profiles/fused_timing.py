@@ -35,6 +35,15 @@ for l in range(L):
         bar[i] += after - before
         idx += 2
 print(f"layers total {(t[idx - 1] - t0) / 1e3:.1f} us at position {T + 7}")
+# outside the layers: kernel start (step_times[offset], stamped by CTA 0 at entry) -> first barrier open (embedding + first norm),
+# last layer's barrier open -> heads tiles done -> barrier open -> next launch's start (sampling, teardown, launch gap)
+st = t[1024:1024 + 300]
+off = T + 8  # the last launch of the call sampled column `off`
+if st[off] and st[off - 1]:
+    print(f"step period {(st[off] - st[off - 1]) / 1e3:.1f} us; last launch: entry -> first barrier open {(t[1] - st[off]) / 1e3:.2f} us, "
+          f"heads tiles {(t[idx] - t[idx - 1]) / 1e3:.2f} us, heads barrier {(t[idx + 1] - t[idx]) / 1e3:.2f} us")
+    print(f"previous launch's layers end -> this launch's entry (heads + barrier + sampling + teardown + launch gap): "
+          f"{(st[off] - st[off - 1]) / 1e3 - (t[idx - 1] - st[off]) / 1e3:.2f} us (period - (entry -> layers end))")
 for n, w, b in zip(names, work, bar):
     print(f"  {n:7s} work {w / L / 1e3:6.2f} us   barrier wait {b / L / 1e3:6.2f} us   phase {(w + b) / L / 1e3:6.2f} us (per layer, CTA {os.environ.get('VAURA_TIMING_CTA', '0')})")
 a = t[900:908]
