@@ -1651,20 +1651,14 @@ __device__ __forceinline__ void fused_gemm_tile(FusedPipe& pp, const CUtensorMap
       // R2UR.BROADCAST from vector registers)
       const uint32_t a_lo = __shfl_sync(0xffffffffu, (st_addr & 0x3FFFF) >> 4, 0);
       const uint32_t b_lo = __shfl_sync(0xffffffffu, ((st_addr + kKsub * kABytes) & 0x3FFFF) >> 4, 0);
-      if (nsub == kKsub) {
+      // one rolled loop over the stage's K blocks (four MMAs each): the tile is paced by the SM's L2 port, not by MMA issue, and
+      // the kernel is several times the L1.5 instruction cache - smaller code, not faster issue, is what helps here
+#pragma unroll 1
+      for (int sub = 0; sub < nsub; ++sub)
 #pragma unroll
-        for (int sub = 0; sub < kKsub; ++sub)
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16_f16_elect_lo(pp.tmem_base, a_lo + sub * (kABytes >> 4) + 2 * k, b_lo + sub * (B_BYTES >> 4) + 2 * k, idesc,
-                                   (it | sub | k) != 0);
-      } else {
-        for (int sub = 0; sub < nsub; ++sub)
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16_f16_elect_lo(pp.tmem_base, a_lo + sub * (kABytes >> 4) + 2 * k, b_lo + sub * (B_BYTES >> 4) + 2 * k, idesc,
-                                   (it | sub | k) != 0);
-      }
+        for (int k = 0; k < kBlockK / 16; ++k)
+          umma_bf16_f16_elect_lo(pp.tmem_base, a_lo + sub * (kABytes >> 4) + 2 * k, b_lo + sub * (B_BYTES >> 4) + 2 * k, idesc,
+                                 (it | sub | k) != 0);
       umma_commit_elect(&pp.empty[s]);
       if (dbg && lane == 0 && it < 8) dstamp(16 + it);
     }
